@@ -1,0 +1,101 @@
+"""Environment configuration — same keys as the reference's YAML files
+(agents/config/train_config.yaml:3-31, agents/config/rewards_config.yaml) and the keyword
+arguments of CyberBattleEnv / CyberBattleCompressedEnv (cyberbattle_env.py:38-60,
+cyberbattle_env_compressed.py:74-89)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict
+
+import numpy as np
+
+from . import constants as C
+
+# agents/config/rewards_config.yaml:4-14 / :72-90 (goal "control")
+DEFAULT_REWARDS = {
+    "control": dict(value_coefficient=3, cost_coefficient=1, node_discovered_coefficient=25,
+                    data_collected_reward=20, data_exfiltrated_reward=20, persistence_reward=20,
+                    privilege_escalation_reward=100, acquired_visibility_reward=20, dos_coefficient=-2,
+                    defense_evaded_reward=20),
+    "disruption": dict(value_coefficient=0.5, cost_coefficient=1, node_discovered_coefficient=10,
+                       data_collected_reward=0, data_exfiltrated_reward=0, persistence_reward=0,
+                       privilege_escalation_reward=0, acquired_visibility_reward=10, dos_coefficient=5,
+                       defense_evaded_reward=10),
+    "discovery": dict(value_coefficient=1, cost_coefficient=1, node_discovered_coefficient=100,
+                      data_collected_reward=100, data_exfiltrated_reward=100, persistence_reward=0,
+                      privilege_escalation_reward=50, acquired_visibility_reward=100, dos_coefficient=-2,
+                      defense_evaded_reward=25),
+}
+_PEN_COMMON = dict(no_vulnerability_in_node=-10, no_enough_privileges=-10, success_rate_failed=0,
+                   no_data_to_collect=-10, no_data_to_exfiltrate=-10, already_persistent=-10,
+                   node_already_stopped=-10, node_already_owned=-10, node_already_visible=-10,
+                   already_defense_evasion=-10, scanning_unopen_port=-10,
+                   privilege_escalation_in_node_not_owned=-10, privilege_escalation_to_level_already_had=-10,
+                   outcome_not_valid=-10, blocked_by_local_firewall=-10, blocked_by_remote_firewall=-10,
+                   invalid_action=0, distance_penalty=-3)
+DEFAULT_PENALTIES = {
+    "control": dict(_PEN_COMMON, invalid_action=-50),
+    "disruption": dict(_PEN_COMMON),
+    "discovery": dict(_PEN_COMMON),
+}
+
+
+@dataclass
+class EnvConfig:
+    goal: str = "control"
+    winning_reward: float = 5000.0
+    losing_reward: float = -5000.0
+    episode_iterations: int = 200
+    proportional_cutoff_coefficient: float = 1
+    absolute_reward: bool = False
+    stop_at_goal_reached: bool = True
+    isolation_filter_threshold: float = 0.1
+    remove_main_obstacles: bool = True
+    remove_all_obstacles: bool = False
+    random_starter_node: bool = True
+    switch_interval: int = 5
+    rewards_dict: Dict[str, float] = field(default_factory=dict)
+    penalties_dict: Dict[str, float] = field(default_factory=dict)
+
+    def __post_init__(self):
+        self.goal = self.goal.lower()
+        if self.goal not in C.GOALS:
+            raise ValueError(f"goal '{self.goal}' is not supported by the batched env "
+                             f"(supported: {sorted(C.GOALS)}; *_node goals are listed as 'next' in DESIGN.md)")
+        if not self.rewards_dict:
+            self.rewards_dict = dict(DEFAULT_REWARDS[self.goal])
+        if not self.penalties_dict:
+            self.penalties_dict = dict(DEFAULT_PENALTIES[self.goal])
+
+    @classmethod
+    def from_reference_dicts(cls, train_config: dict, rewards_config: dict, goal: str = "control") -> "EnvConfig":
+        """Build from the dicts the reference loads with yaml (agents/train_agent.py:229-239)."""
+        keys = {f for f in cls.__dataclass_fields__}
+        kw = {k: v for k, v in train_config.items() if k in keys}
+        kw["goal"] = goal
+        kw["rewards_dict"] = dict(rewards_config["rewards_dict"][goal])
+        kw["penalties_dict"] = dict(rewards_config["penalties_dict"][goal])
+        return cls(**kw)
+
+    def reward_vector(self) -> np.ndarray:
+        return np.array([float(self.rewards_dict[k]) for k in C.REWARD_KEYS], dtype=np.float64)
+
+    def penalty_vector(self) -> np.ndarray:
+        p = dict(self.penalties_dict)
+        # the control table spells it `machine_already_stopped` (rewards_config.yaml:79); the code
+        # reads `node_already_stopped` (attacker_actions.py:235) on an unreachable branch
+        p.setdefault("node_already_stopped", p.get("machine_already_stopped", -10))
+        return np.array([float(p[k]) for k in C.PENALTY_KEYS], dtype=np.float64)
+
+    def reference_kwargs(self) -> dict:
+        """kwargs for the reference CyberBattleCompressedEnv constructor (used by the golden generator)."""
+        pen = dict(self.penalties_dict)
+        pen.setdefault("node_already_stopped", pen.get("machine_already_stopped", -10))
+        return dict(goal=self.goal, winning_reward=self.winning_reward, losing_reward=self.losing_reward,
+                    episode_iterations=self.episode_iterations,
+                    proportional_cutoff_coefficient=self.proportional_cutoff_coefficient,
+                    absolute_reward=self.absolute_reward, stop_at_goal_reached=self.stop_at_goal_reached,
+                    isolation_filter_threshold=self.isolation_filter_threshold,
+                    remove_main_obstacles=self.remove_main_obstacles, remove_all_obstacles=self.remove_all_obstacles,
+                    random_starter_node=self.random_starter_node, rewards_dict=dict(self.rewards_dict),
+                    penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None)

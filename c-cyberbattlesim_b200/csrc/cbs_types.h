@@ -1,0 +1,110 @@
+// cbs_types.h — device-side layout shared by all kernels of libcbsim.
+// Numbers mirror c-cyberbattlesim_b200/constants.py (tests/test_constants.py keeps them in sync).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cbs {
+
+constexpr int NODE_EMB = 64;
+constexpr int VULN_EMB = 768;
+constexpr int OUTCOME_DIM = 9;
+constexpr int ACTION_DIM = 905;
+constexpr int OBS_GRAPH = 192;
+constexpr int OBS_DIM = 194;
+constexpr int NN_CH = 16;
+constexpr int PROJ_ROWS = 18;  // 16 hidden + bias slot + root term
+constexpr int NUM_DYN = 6;     // persistence, collected, exfiltrated, evasion, privilege, status
+constexpr int MAX_NODES = 128;
+
+// outcome kinds (simulation/model.py:66-193)
+enum Kind : int { K_DOS = 0, K_DISCOVERY, K_COLLECTION, K_EXFILTRATION, K_RECON, K_EVASION, K_PERSISTENCE,
+                  K_PRIVESC, K_CREDACCESS, K_LATERAL, K_EXECUTION, N_KINDS };
+// obtained-outcome codes for failures (simulation/attacker_actions.py)
+enum Code : int { OC_INVALID_SRC_NOT_OWNED = 16, OC_INVALID_TGT_NOT_DISCOVERED, OC_SRC_NOT_RUNNING, OC_TGT_NOT_RUNNING,
+                  OC_NO_VULNERABILITY, OC_NO_PRIVILEGE, OC_OUTCOME_NOT_PRESENT, OC_PORT_NOT_LISTENING, OC_FW_OUTGOING,
+                  OC_FW_INCOMING, OC_UNSUCCESSFUL, OC_NO_NEEDED, OC_REPEATED, OC_REMOTE_OUTCOME_LOCAL };
+enum Goal : int { GOAL_CONTROL = 0, GOAL_DISCOVERY = 1, GOAL_DISRUPTION = 2 };
+enum Mask : int { M_OWNED = 0, M_DISCOVERED, M_VISIBLE, M_HAS_DATA, M_COLLECTED, M_EXFILTRATED, M_PERSISTENCE,
+                  M_EVASION, M_STOPPED, M_PRIV_USER, M_PRIV_ROOT, N_MASKS };
+enum Reward : int { R_VALUE = 0, R_COST, R_NODE_DISCOVERED, R_COLLECTED, R_EXFILTRATED, R_PERSISTENCE, R_PRIVESC,
+                    R_VISIBILITY, R_DOS, R_EVASION, N_REWARDS };
+enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLECT, P_NO_DATA_EXFIL, P_ALREADY_PERSISTENT,
+                     P_ALREADY_STOPPED, P_ALREADY_OWNED, P_ALREADY_VISIBLE, P_ALREADY_EVASION, P_UNOPEN_PORT,
+                     P_PRIVESC_NOT_OWNED, P_PRIVESC_ALREADY, P_OUTCOME_NOT_VALID, P_FW_LOCAL, P_FW_REMOTE,
+                     P_INVALID_ACTION, P_DISTANCE, N_PENALTIES };
+// per-env int32 scalar planes
+enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE,
+                    S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES,
+                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_SPARE, N_SCALARS };
+// S_FLAGS bits
+constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
+              FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128;
+// vi_flags bits (scenario.py VI_*)
+constexpr uint32_t VI_LISTENING = 1u, VI_IN_ALLOWED = 2u;
+constexpr int VI_PRIVREQ_SHIFT = 2, VI_LEVEL_ANY_SHIFT = 4, VI_LEVEL_REMOTE_SHIFT = 6;
+// stat accumulators (sums over finished episodes on this GPU)
+enum Accum : int { A_EPISODES = 0, A_RETURN, A_LENGTH, A_WINS, A_LOST, A_CUTOFF, A_STAT0 /* .. A_STAT0+13 */, N_ACCUM = 20 };
+
+struct Tables {  // immutable, device pointers
+  int num_scenarios, max_nodes, words, num_global_vulns;
+  const int32_t *sc_num_nodes, *sc_node_off, *sc_port_off, *sc_uvuln_off, *sc_num_uvuln, *sc_discoverable_amount,
+      *sc_feasible_off, *feasible_starters;
+  const int64_t* sc_instof_off;
+  const uint32_t *sc_init_has_data, *sc_init_visible;
+  const int32_t *nd_value, *nd_ownable, *nd_discoverable, *nd_disruptable, *nd_row_off;
+  const uint8_t* nd_level_at_access;
+  const uint32_t* outblock;
+  const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst;
+  const uint32_t *vi_flags, *row_packed;
+  const uint16_t *vi_kinds_any, *vi_kinds_remote;
+  const double *vi_success, *vi_cost, *vemb64, *vnorm2;
+  const uint8_t* recon_nodes;
+  const float* vemb32;
+  // GAE
+  const float *node_static, *dyn_proj, *vuln_h, *nn0_b, *bn1_scale, *bn1_shift, *gcn_wt, *bn2_scale, *bn2_shift;
+};
+
+struct Params {  // configuration, by value
+  int B, ncap, words, slots, ecap;
+  long long global_env_offset;
+  unsigned long long seed;
+  int goal, episode_iterations, absolute_reward, stop_at_goal, remove_main, remove_all, switch_interval, auto_reset;
+  double prop_coeff, winning_reward, losing_reward;
+  double rew[N_REWARDS], pen[N_PENALTIES];
+  float margin;
+  int qlen;
+};
+
+struct State {  // mutable, device pointers
+  uint32_t* masks;       // [N_MASKS][words][B]
+  int32_t* scal;         // [N_SCALARS][B]
+  uint8_t* disc_order;   // [B][ncap]
+  uint8_t* owned_order;  // [B][ncap]
+  uint8_t* pair_slot;    // [B][ncap*ncap]   0xFF = pair not in the action table
+  float* z_hist;         // [B][slots][ncap][64]  node embeddings of the encode that created the slot
+  float* zn2_hist;       // [B][slots][ncap]      their squared norms
+  uint8_t* edge_src;     // [B][ecap]
+  uint8_t* edge_dst;     // [B][ecap]
+  int32_t* edge_cnt;     // [B][ecap]   live accumulator length (0 after the compressed:237 reset)
+  float* edge_sum;       // [B][ecap][16]  running sum of W1*emb over the accumulator
+  float* edge_m;         // [B][ecap][16]  W1 * (stored edge attribute)
+  float* obs;            // [B][OBS_DIM] cached observation
+  float* term_obs;       // [B][OBS_DIM]
+  int32_t* sel;          // [B][4]
+  double* dist;          // [B]
+  double* reward64;      // [B]
+  double* ep_return;     // [B]
+  double* last_stats;    // [B][14]
+  double* accum;         // [N_ACCUM]
+  int32_t* starter_queue;  // [B][qlen] or nullptr
+  float* vt;             // [B][Ug]  action x vulnerability-embedding products (decode GEMM output)
+  float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
+  int32_t* errflag;      // [1]
+};
+
+__host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {
+  return masks[((size_t)plane * words + w) * B + b];
+}
+
+}  // namespace cbs

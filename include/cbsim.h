@@ -1,0 +1,223 @@
+/*
+ * cbsim.h — C ABI of libcbsim.so: the B200 batched continuous-env step path for C-CyberBattleSim.
+ *
+ * Plain C, plain pointers and sizes, no torch / C++ types.  One handle per GPU, one host thread per
+ * handle.  Every call returns 0 on success or a negative cbs_status; the message is available through
+ * cbs_last_error().  No C++ exception crosses this boundary.  Functions that take a `stream` enqueue
+ * work on that CUDA stream (pass the integer value of a cudaStream_t; 0 = legacy default stream) and
+ * return without synchronising, unless stated otherwise.
+ *
+ * Each entry point names the reference interface (zsh239040/C-CyberBattleSim, path relative to
+ * cyberbattle/) it replaces.  There is no CPU fallback: if no CUDA device is usable cbs_create fails.
+ *
+ * Pointer suffixes:  _host = host memory, _dev = device memory on the handle's GPU.
+ */
+#ifndef CBSIM_H
+#define CBSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CBS_ABI_VERSION 1
+
+/* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
+ * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
+#define CBS_NODE_EMB_DIM 64
+#define CBS_VULN_EMB_DIM 768
+#define CBS_OUTCOME_DIM 9
+#define CBS_ACTION_DIM 905 /* 64 + 64 + 768 + 9 */
+#define CBS_OBS_DIM 194    /* graph_embeddings[192] (mean|max|min) + discrete_features[2] (discovered, owned) */
+#define CBS_NUM_STATS 14   /* cyberbattle_env.py:517-524 get_statistics() tuple */
+#define CBS_NUM_REWARDS 10
+#define CBS_NUM_PENALTIES 18
+#define CBS_MAX_NODES 128
+#define CBS_INFO_INTS 8
+
+typedef enum {
+  CBS_OK = 0,
+  CBS_ERR_INVALID_ARG = -1,
+  CBS_ERR_CUDA = -2,
+  CBS_ERR_NOT_READY = -3, /* scenarios not loaded / env not reset */
+  CBS_ERR_CAPACITY = -4,  /* a per-env capacity (snapshot slots, edges) overflowed on the device */
+  CBS_ERR_NO_DEVICE = -5
+} cbs_status;
+
+typedef struct cbs_handle cbs_handle;
+
+/* Environment configuration == kwargs of CyberBattleEnv.__init__ (_env/cyberbattle_env.py:38-60) and
+ * CyberBattleCompressedEnv.__init__ (_env/cyberbattle_env_compressed.py:74-89) that the step path reads,
+ * plus the reward tables of agents/config/rewards_config.yaml in the order of constants.REWARD_KEYS /
+ * PENALTY_KEYS. */
+typedef struct {
+  int32_t abi_version;          /* must be CBS_ABI_VERSION */
+  int32_t device;               /* CUDA device ordinal */
+  int32_t num_envs;             /* envs held by this handle (this GPU's shard) */
+  int64_t global_env_offset;    /* index of env 0 in the whole batch: keys the Philox streams so results do not depend on the GPU count */
+  uint64_t seed;                /* Philox key */
+  int32_t goal;                 /* 0 control, 1 discovery, 2 disruption (cyberbattle_env.py:467-487) */
+  int32_t episode_iterations;   /* constant cut-off (cyberbattle_env.py:366) */
+  double proportional_cutoff_coefficient; /* 0 = off (cyberbattle_env.py:361,457-460) */
+  double winning_reward, losing_reward;
+  int32_t absolute_reward;      /* cyberbattle_env.py:379 */
+  int32_t stop_at_goal_reached; /* cyberbattle_env.py:348 */
+  int32_t remove_main_obstacles, remove_all_obstacles; /* compressed:536-543 */
+  int32_t switch_interval;      /* episodes between scenario switches (cyberbattle_env_switch.py:218-220); <=0 = never */
+  int32_t auto_reset;           /* 1: cbs_observe resets finished envs in place (DummyVecEnv semantics) */
+  double rewards[CBS_NUM_REWARDS];
+  double penalties[CBS_NUM_PENALTIES];
+  int32_t max_slots;            /* embedding-snapshot slots per env; 0 = derive from the cut-offs */
+  int32_t max_edges;            /* visible-graph edges per env; 0 = derive from the cut-offs */
+  float decode_margin;          /* cosine-score margin inside which candidates are re-scored in float64; 0 = default */
+  int32_t decode_gemm;          /* 0 = default (tcgen05 TF32 when built in), 1 = force the SIMT fp32 path */
+} cbs_config;
+
+/* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the
+ * device by cbs_load_scenarios).  They flatten simulation/model.py NodeInfo / VulnerabilityInfo /
+ * PredictedResult / FirewallConfiguration and the reach counts of cyberbattle_env.py:205-217. */
+typedef struct {
+  int32_t num_scenarios, max_nodes, words;
+  int32_t num_nodes_total, num_inst, num_rows, num_recon, num_ports_total, num_uvuln_total, num_global_vulns;
+  int64_t num_instof;
+  const int32_t* sc_num_nodes;           /* [S] */
+  const int32_t* sc_node_off;            /* [S+1] */
+  const int32_t* sc_port_off;            /* [S+1] */
+  const int32_t* sc_uvuln_off;           /* [S+1] */
+  const int32_t* sc_num_uvuln;           /* [S] */
+  const int64_t* sc_instof_off;          /* [S+1] */
+  const int32_t* sc_discoverable_amount; /* [S] */
+  const uint32_t* sc_init_has_data;      /* [S][words] */
+  const uint32_t* sc_init_visible;       /* [S][words] */
+  const int32_t* sc_feasible_off;        /* [S+1] for the configured goal */
+  const int32_t* feasible_starters;      /* [sc_feasible_off[S]] */
+  int32_t num_feasible;
+  const int32_t* nd_value;               /* [Nn] */
+  const uint8_t* nd_level_at_access;     /* [Nn] */
+  const int32_t* nd_ownable;             /* [Nn] */
+  const int32_t* nd_discoverable;        /* [Nn] */
+  const int32_t* nd_disruptable;         /* [Nn] */
+  const int32_t* nd_row_off;             /* [2*Nn+1] local|remote candidate lists */
+  const uint32_t* outblock;              /* [ports][words] */
+  const int32_t* inst_of;                /* [num_instof] */
+  const int32_t* vi_port;                /* [I] */
+  const uint32_t* vi_flags;              /* [I] */
+  const uint16_t* vi_kinds_any;          /* [I] */
+  const uint16_t* vi_kinds_remote;       /* [I] */
+  const double* vi_success;              /* [I] */
+  const double* vi_cost;                 /* [I] */
+  const int32_t* vi_recon_any;           /* [I][2] */
+  const int32_t* vi_recon_remote;        /* [I][2] */
+  const int32_t* vi_ulocal;              /* [I] */
+  const uint8_t* recon_nodes;            /* [num_recon] */
+  const uint32_t* row_packed;            /* [R] */
+  const int32_t* row_inst;               /* [R] */
+  const float* vemb32;                   /* [Ug][768] */
+  const double* vemb64;                  /* [Ug][768] */
+  const double* vnorm2;                  /* [Ug] */
+} cbs_scenario_tables;
+
+/* Folded graph-encoder tables (ccbs_b200.gae.fold_gae) for gae/model.py:25-82 GAEEncoder.forward with the
+ * default layer config, eval mode. */
+typedef struct {
+  const float* node_static; /* [Nn][2][18][64] */
+  const float* dyn_proj;    /* [6][18][64] */
+  const float* vuln_h;      /* [Ug][16] */
+  const float* nn0_b;       /* [16] */
+  const float* bn1_scale;   /* [64] */
+  const float* bn1_shift;   /* [64] */
+  const float* gcn_wt;      /* [64][64] (in, out) */
+  const float* bn2_scale;   /* [64] */
+  const float* bn2_shift;   /* [64] */
+} cbs_gae_tables;
+
+/* ---- lifetime ---------------------------------------------------------------------------------- */
+int cbs_abi_version(void);
+/* replaces: construction of CyberBattleCompressedEnv objects (utils/envs_utils.py:23-32) for num_envs envs */
+int cbs_create(const cbs_config* cfg, cbs_handle** out);
+void cbs_destroy(cbs_handle* h);
+const char* cbs_last_error(const cbs_handle* h); /* h may be NULL: last error of a failed cbs_create */
+
+/* replaces: pickle.load of scenario envs (cyberbattle_env_switch.py:72-89) + env.set_graph_encoder (compressed:643) */
+int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_gae_tables* g);
+/* scenario of every env ([num_envs], host).  replaces RandomSwitchEnv._switch_environment (switch.py:102-106) */
+int cbs_set_scenarios(cbs_handle* h, const int32_t* scenario_of_env_host);
+/* optional deterministic starter nodes: queue_host[num_envs][qlen]; episode e of env b starts at
+ * queue[b][e % qlen].  NULL restores random starters (Philox over the feasible set == the rejection loop of
+ * cyberbattle_env.py:195-248). */
+int cbs_set_starter_queue(cbs_handle* h, const int32_t* queue_host, int32_t qlen);
+/* replaces set_cut_off / set_proportional_cutoff_coefficient (cyberbattle_env_switch.py:198-203) */
+int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double proportional_cutoff_coefficient);
+
+/* ---- the step path ----------------------------------------------------------------------------- */
+/* replaces RandomSwitchEnv.reset -> CyberBattleCompressedEnv.reset (switch.py:151-167, compressed:158-189,
+ * cyberbattle_env.py:134-186).  env_mask_dev: [num_envs] bytes, non-zero = reset; NULL = all.
+ * obs_dev (optional): [num_envs][CBS_OBS_DIM] float32, written for every env. */
+int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintptr_t stream);
+
+/* replaces find_closest_action_embedding (compressed:570-590, scipy cdist 'cosine' + argmin over the action
+ * table).  actions_dev: [num_envs][905] float32.  sel_dev: [num_envs][4] = source node, target node,
+ * scenario-local vulnerability index, outcome kind.  dist_dev: [num_envs] float64 cosine distance. */
+int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double* dist_dev, uintptr_t stream);
+
+/* replaces CyberBattleEnv.step_attacker_env (cyberbattle_env.py:299-394) incl.
+ * AttackerAgentActions.exploit_{local,remote}_vulnerability (simulation/attacker_actions.py:92-547), goal /
+ * termination checks and the distance penalty of compressed:430.
+ * sel_dev as produced by cbs_decode (any indices are accepted: invalid ones take the reference's penalty
+ * branches).  dist_dev may be NULL (distance 0).  uniforms_dev: [num_envs] float32 success-rate draws, or NULL
+ * to draw from Philox(seed, global env index, env step counter).
+ * Outputs (each may be NULL): reward_dev float32, done_dev = done|truncated (compressed:451), truncated_dev,
+ * outcome_dev = obtained outcome code (ccbs_b200.constants K_* / OC_*). */
+int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev, const float* uniforms_dev,
+                   float* reward_dev, uint8_t* done_dev, uint8_t* truncated_dev, uint8_t* outcome_dev,
+                   uintptr_t stream);
+
+/* replaces update_evolving_visible_graph_after_step + encode + create_continuous_action_space
+ * (compressed:399-428, 465-550) and, with auto_reset, the VecEnv reset of finished envs.
+ * obs_dev: [num_envs][CBS_OBS_DIM] float32.  The terminal observation of envs that finished in this step
+ * stays readable through cbs_read_state(CBS_F_TERMINAL_OBS). */
+int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream);
+
+/* decode + transition + observe, device buffers.  info_dev (optional): [num_envs][CBS_INFO_INTS] int32 =
+ * source, target, vulnerability, desired outcome kind, obtained outcome code, end_episode_reason, step_count,
+ * truncated. */
+int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* obs_dev, float* reward_dev,
+             uint8_t* done_dev, int32_t* info_dev, uintptr_t stream);
+
+/* Same through HOST buffers (pinned memory recommended): copies actions in, runs the step, copies
+ * obs / reward / done (/ info) out, and synchronises.  This is the call the VecEnv adapter makes. */
+int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host,
+                  float* reward_host, uint8_t* done_host, int32_t* info_host);
+
+/* ---- introspection (parity tests, statistics) ----------------------------------------------------- */
+typedef enum {
+  CBS_F_MASKS = 0,        /* uint32 [11][words][B] */
+  CBS_F_DISC_ORDER = 1,   /* uint8 [B][max_nodes] */
+  CBS_F_OWNED_ORDER = 2,  /* uint8 [B][max_nodes] */
+  CBS_F_SCALARS = 3,      /* int32 [CBS_NUM_SCALARS][B] */
+  CBS_F_TERMINAL_OBS = 4, /* float32 [B][194] */
+  CBS_F_OBS = 5,          /* float32 [B][194] cached observation */
+  CBS_F_LAST_STATS = 6,   /* float64 [B][14] get_statistics() of the last finished episode */
+  CBS_F_STAT_ACCUM = 7,   /* float64 [CBS_NUM_ACCUM] sums over finished episodes (NCCL all-reduce input) */
+  CBS_F_PAIR_SLOT = 8,    /* uint8 [B][max_nodes*max_nodes] */
+  CBS_F_DIST = 9,         /* float64 [B] last decode distance */
+  CBS_F_REWARD64 = 10,    /* float64 [B] last step reward */
+  CBS_F_ERRFLAG = 11      /* int32 [1] device-side capacity error flag */
+} cbs_field;
+#define CBS_NUM_SCALARS 20
+#define CBS_NUM_ACCUM 20
+/* synchronous device->host copy of one state field; bytes must equal the field size (query with dst NULL). */
+int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes);
+/* device pointer of a state field (for zero-copy consumers such as an NCCL all-reduce of CBS_F_STAT_ACCUM) */
+void* cbs_state_ptr(cbs_handle* h, int32_t field);
+int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream);
+/* number of kernels this library launched since creation (bench.py reports it) */
+int64_t cbs_launch_count(const cbs_handle* h);
+int cbs_sync(cbs_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CBSIM_H */

@@ -1,0 +1,637 @@
+"""TEST INFRASTRUCTURE — CPU restatement ("oracle") of the reference's continuous-env step path.
+
+This file restates, in plain Python/numpy (+ torch fp32 for the graph encoder), what
+C-CyberBattleSim computes on ``RandomSwitchEnv.step/reset -> CyberBattleCompressedEnv.step/reset``
+for one environment.  Every method cites the reference file:line it follows.  It is **not** part of
+the product: only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` leg may import it.  The product path (``c-cyberbattlesim_b200/``) never does.
+
+Parity status: PINNED against the reference's own Python code, run unmodified in the build
+container under the stub modules in ``oracle/shims`` by ``oracle/gen_golden.py``; the recorded traces
+live in ``tests/golden/`` and ``tests/test_oracle_golden.py`` replays them through this file.  The
+graph-encoder layers (torch_geometric 2.5.3 NNConv / GCNConv / BatchNorm) are third-party code that is
+absent from /root/reference and from this image; their published semantics are restated both here
+and in the shim, so the GAE part is pinned to that restatement, not to a PyG binary.
+
+Inputs are the product's own neutral containers (``ScenarioSpec``, ``GaeWeights``, ``EnvConfig``) —
+*not* the compiled SoA tables — so a GPU-vs-oracle test also covers the scenario compiler.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy.spatial import distance as _sp_distance
+
+import ccbs_b200.constants as C
+
+_LOCAL_LABELS = [C.K_DOS, C.K_DISCOVERY, C.K_COLLECTION, C.K_EXFILTRATION, C.K_RECON, C.K_EVASION,
+                 C.K_PERSISTENCE, C.K_PRIVESC]                                  # compressed:595-597
+_REMOTE_LABELS = [C.K_DOS, C.K_DISCOVERY, C.K_COLLECTION, C.K_EXFILTRATION, C.K_RECON, C.K_EVASION,
+                  C.K_PERSISTENCE, C.K_CREDACCESS, C.K_LATERAL]                 # compressed:598-600
+_REENCODE_KINDS = (C.K_LATERAL, C.K_DOS, C.K_RECON)                             # compressed:462
+_REFRESH_KINDS = (C.K_DISCOVERY, C.K_COLLECTION, C.K_PERSISTENCE, C.K_PRIVESC, C.K_EXFILTRATION,
+                  C.K_EVASION, C.K_DOS, C.K_LATERAL, C.K_CREDACCESS)            # compressed:472-479
+
+
+class _Node:
+    """Mutable NodeInfo fields (model.py:294-338) over an immutable NodeSpec."""
+    __slots__ = ("spec", "agent_installed", "privilege_level", "status", "has_data", "data_collected",
+                 "data_exfiltrated", "visible", "persistence", "defense_evasion", "vulns")
+
+    def __init__(self, spec):
+        self.spec = spec
+        self.agent_installed = False
+        self.privilege_level = C.PRIV_NONE
+        self.status = C.ST_RUNNING
+        self.has_data = spec.has_data
+        self.data_collected = False
+        self.data_exfiltrated = False
+        self.visible = spec.visible
+        self.persistence = False
+        self.defense_evasion = False
+        self.vulns = {v.vid: v for v in spec.vulns}
+
+
+class GaeOracle:
+    """gae/model.py:70-82 GAEEncoder.forward for the default layer config, eval mode, torch fp32 on CPU.
+    NNConv / GCNConv / BatchNorm follow torch_geometric 2.5.3 (see module docstring)."""
+
+    def __init__(self, w):
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))  # noqa: E731
+        self.nn0_w, self.nn0_b = t(w.nn0_w), t(w.nn0_b)
+        self.nn2_w, self.nn2_b = t(w.nn2_w), t(w.nn2_b)
+        self.root_w, self.conv1_b = t(w.root_w), t(w.conv1_b)
+        self.gcn_w, self.gcn_b = t(w.gcn_w), t(w.gcn_b)
+        self.bn1 = {k: t(v) for k, v in w.bn1.items()}
+        self.bn2 = {k: t(v) for k, v in w.bn2.items()}
+        self.eps = w.bn_eps
+
+    def _bn(self, x, bn):
+        return torch.nn.functional.batch_norm(x, bn["running_mean"], bn["running_var"], bn["weight"], bn["bias"],
+                                              False, 0.0, self.eps)
+
+    @torch.no_grad()
+    def forward(self, x, edge_index, edge_attr):
+        n, d_in, d_out = x.shape[0], x.shape[1], self.conv1_b.shape[0]
+        src, dst = edge_index[0], edge_index[1]
+        # NNConv (aggr=add, root weight, bias)
+        h = torch.relu(torch.nn.functional.linear(edge_attr, self.nn0_w, self.nn0_b))
+        theta = torch.nn.functional.linear(h, self.nn2_w, self.nn2_b).view(-1, d_in, d_out)
+        msg = torch.matmul(x[src].unsqueeze(1), theta).squeeze(1)
+        out = torch.zeros(n, d_out, dtype=x.dtype).index_add_(0, dst, msg)
+        out = out + torch.nn.functional.linear(x, self.root_w) + self.conv1_b
+        out = torch.relu(self._bn(out, self.bn1))
+        # GCNConv: add_remaining_self_loops, symmetric normalisation by in-degree
+        keep = src != dst
+        loop = torch.arange(n, dtype=src.dtype)
+        s2, d2 = torch.cat([src[keep], loop]), torch.cat([dst[keep], loop])
+        deg = torch.zeros(n, dtype=x.dtype).index_add_(0, d2, torch.ones(s2.shape[0], dtype=x.dtype))
+        dinv = deg.pow(-0.5)
+        dinv[torch.isinf(dinv)] = 0
+        hw = torch.nn.functional.linear(out, self.gcn_w)
+        agg = torch.zeros_like(hw).index_add_(0, d2, (dinv[s2] * dinv[d2]).unsqueeze(1) * hw[s2])
+        return torch.relu(self._bn(agg + self.gcn_b, self.bn2))
+
+
+class OracleEnv:
+    """One continuous env.  ``step(action, uniform)`` = RandomSwitchEnv.step -> CyberBattleCompressedEnv.step
+    with the success-rate draw replaced by the supplied uniform (consumed only where the reference
+    calls ``random.random()``, attacker_actions.py:190,409)."""
+
+    def __init__(self, spec, gae_weights, cfg):
+        self.spec, self.cfg = spec, cfg
+        self.gae = GaeOracle(gae_weights)
+        self.N = spec.num_nodes
+        self.rew, self.pen = dict(cfg.rewards_dict), dict(cfg.penalties_dict)
+        self.pen.setdefault("node_already_stopped", self.pen.get("machine_already_stopped", -10))
+        self.goal = cfg.goal
+        self.episode_iterations = cfg.episode_iterations
+        self.proportional_cutoff_coefficient = cfg.proportional_cutoff_coefficient
+        # create_vulnerabilities_embeddings (compressed:614-618)
+        self.vuln_emb = {k: np.asarray(v, dtype=np.float64) for k, v in spec.vuln_emb.items()}
+        # create_vulnerabilities_embeddings_per_node_type (compressed:621-637)
+        self.per_node_type = []
+        for nd in spec.nodes:
+            lists = {0: [], 1: []}
+            for v in nd.vulns:
+                for ri, r in enumerate(v.results):
+                    oh = self._onehot(r.vtype, r.kind)
+                    if oh is None:
+                        continue
+                    lists[r.vtype].append((v.vid, ri, r.kind, np.concatenate((self.vuln_emb[v.vid], oh))))
+            self.per_node_type.append(lists)
+        # reach counts: all-pairs shortest paths of the access / knows / dos graphs
+        # (model.py:418-420 + networkx_utils.py:19-58), generate_network.py:258-306 for the graphs
+        self._reach = self._reach_counts()
+        self.episode_id = 0
+        self.done = False
+        self.nodes = None
+
+    # ---- static helpers -------------------------------------------------------------------
+    @staticmethod
+    def _onehot(vtype, kind):
+        """compressed:593-611 map_outcome_to_onehot"""
+        if kind == C.K_EXECUTION:
+            return None
+        labels = _LOCAL_LABELS if vtype == 0 else _REMOTE_LABELS
+        if kind not in labels:
+            return None
+        oh = np.zeros(C.OUTCOME_DIM, dtype=np.float64)
+        oh[labels.index(kind)] = 1
+        return oh
+
+    def _reach_counts(self):
+        N, nodes = self.N, self.spec.nodes
+        knows = [set() for _ in range(N)]
+        for i, nd in enumerate(nodes):                               # generate_network.py:259-267
+            for v in nd.vulns:
+                for r in v.results:
+                    if r.kind == C.K_RECON:
+                        knows[i].update(j for j in r.nodes if j != i)
+
+        def reach_from(adj, s):
+            seen, stack = {s}, [s]
+            while stack:
+                u = stack.pop()
+                for w in adj[u]:
+                    if w not in seen:
+                        seen.add(w)
+                        stack.append(w)
+            seen.discard(s)
+            return seen
+        knows_reach = [reach_from(knows, s) for s in range(N)]
+        access = [set() for _ in range(N)]
+        dos = [set() for _ in range(N)]
+        for i, nd in enumerate(nodes):                               # generate_network.py:271-306
+            for v in nd.vulns:
+                for r in v.results:
+                    if r.kind not in (C.K_LATERAL, C.K_CREDACCESS, C.K_DOS):
+                        continue
+                    if any(p == v.port and perm == 1 for p, perm in nd.fw_in):
+                        continue
+                    for s in range(N):
+                        if s == i or i not in knows_reach[s]:        # nx.has_path(knows_graph, s, i)
+                            continue
+                        if any(p == v.port and perm == 1 for p, perm in nodes[s].fw_out):
+                            continue
+                        (dos if r.kind == C.K_DOS else access)[s].add(i)
+        return {"control": [len(reach_from(access, s)) for s in range(N)],
+                "discovery": [len(x) for x in knows_reach],
+                "disruption": [len(reach_from(dos, s)) for s in range(N)]}
+
+    def feasible_starters(self):
+        thr = self.cfg.isolation_filter_threshold * self.N           # cyberbattle_env.py:206
+        return [s for s in range(self.N) if not (self._reach[self.goal][s] < thr)]
+
+    # ---- reset ----------------------------------------------------------------------------
+    def reset(self, starter=None, rng=None):
+        """compressed:158-189 reset -> cyberbattle_env.py:134-186 reset_env (+ pick_starter_node :189-296)."""
+        self.nodes = [_Node(nd) for nd in self.spec.nodes]           # deepcopy of the pristine network (:145)
+        if starter is None:
+            if not self.cfg.random_starter_node:
+                starter = 0                                          # :191
+            else:
+                feas = self.feasible_starters()
+                if not feas:
+                    raise RuntimeError("NoSuitableStarterNode")      # :198-199
+                # rejection sampling with randrange(N) (:201) == uniform over feasible starters
+                starter = feas[int(rng.integers(len(feas)))] if rng is not None else feas[0]
+        self.starter = int(starter)
+        self.ownable_count = self._reach["control"][self.starter]            # :209
+        self.discoverable_count = self._reach["discovery"][self.starter]     # :213
+        self.disruptable_count = self._reach["disruption"][self.starter]     # :217
+        self.proportional_nodes = {"control": self.ownable_count, "discovery": self.discoverable_count,
+                                   "disruption": self.disruptable_count}[self.goal]   # :226-248
+        # :279-288 — both dict-key tests are true for every node, so every node counts
+        self.discoverable_amount = 0
+        for nd in self.nodes:
+            self.discoverable_amount += 1
+            if nd.has_data:
+                self.discoverable_amount += 2
+            if not nd.visible:
+                self.discoverable_amount += 1
+        self.nodes[self.starter].agent_installed = True              # :296
+        self.network_availability = 1.0
+        self.episode_id += 1
+        self.done = False
+        self.truncated = False
+        self.end_episode_reason = 0
+        self.num_iterations = 0
+        self.discovered_amount = 0
+        self.stepcount = 0
+        self.discovered_nodes = [self.starter]                       # :178
+        self.owned_nodes = [self.starter]                            # :179
+        # AttackerAgentActions.__init__ (attacker_actions.py:50-53): starter owned at level_at_access
+        self._discovered = {}                                        # node -> last_owned (bool) tracking
+        self._mark_owned(self.starter, self.nodes[self.starter].spec.level_at_access)
+        # compressed:167-188
+        self.processed_pairs = set()
+        self.graph_nodes = []            # insertion order of the evolving visible graph
+        self.node_x = {}
+        self.graph_edges = {}            # src -> {tgt: float64[768]}
+        self._add_graph_node(self.starter)
+        self.action_keys, self.action_rows = [], []
+        self._rows_cache = None
+        self.exploited = {}
+        self.node_embeddings, emb = self.encode()
+        self.create_continuous_action_space()
+        self.observation = {"graph_embeddings": emb, "discrete_features": self._discrete_features()}
+        self.n_encodes = 1
+        return self.observation
+
+    # ---- attacker actions (simulation/attacker_actions.py) -----------------------------------
+    def _mark_owned(self, n, level):
+        """attacker_actions.py:70-89 __mark_node_as_owned; returns (was ever owned, is currently owned)."""
+        ever = self._discovered.get(n)
+        was = bool(ever)
+        self._discovered.setdefault(n, False)
+        node = self.nodes[n]
+        node.agent_installed = True
+        node.privilege_level = max(int(node.privilege_level), int(level))    # model.py:340
+        self._discovered[n] = True
+        return was, was     # no defender: last_reimaging is None, so "currently owned" == "ever owned"
+
+    @staticmethod
+    def _passing(rules, port):
+        """attacker_actions.py:550-559"""
+        for p, perm in rules:
+            if p == port:
+                return perm == 0
+        return True
+
+    def _exploit_remote(self, s, t, vid, kind, u):
+        """attacker_actions.py:92-351.  Returns (reward, obtained code, recon list or None)."""
+        P, R = self.pen, self.rew
+        src, tgt = self.nodes[s], self.nodes[t]
+        if not src.agent_installed:
+            return P["invalid_action"], C.OC_INVALID_SRC_NOT_OWNED, None                  # :109
+        if t not in self._discovered:
+            return P["invalid_action"], C.OC_INVALID_TGT_NOT_DISCOVERED, None             # :115
+        if src.status != C.ST_RUNNING:
+            return P["invalid_action"], C.OC_SRC_NOT_RUNNING, None                        # :121
+        if tgt.status != C.ST_RUNNING:
+            return P["invalid_action"], C.OC_TGT_NOT_RUNNING, None                        # :127
+        v = tgt.vulns.get(vid)
+        if v is None:
+            return P["no_vulnerability_in_node"], C.OC_NO_VULNERABILITY, None             # :133
+        if v.priv_required and not tgt.privilege_level >= v.priv_required:
+            return P["no_enough_privileges"], C.OC_NO_PRIVILEGE, None                     # :141
+        res = next((r for r in v.results if r.vtype == 1 and r.kind == kind), None)       # :149-152
+        if res is None:
+            return P["invalid_action"], C.OC_OUTCOME_NOT_PRESENT, None                    # :153
+        if v.port not in [sv.port for sv in tgt.spec.services if sv.running]:
+            return P["scanning_unopen_port"], C.OC_PORT_NOT_LISTENING, None               # :161
+        if not src.defense_evasion and not self._passing(src.spec.fw_out, v.port):
+            return P["blocked_by_local_firewall"], C.OC_FW_OUTGOING, None                 # :170
+        if not tgt.defense_evasion and not self._passing(tgt.spec.fw_in, v.port):
+            return P["blocked_by_remote_firewall"], C.OC_FW_INCOMING, None                # :180
+        if u >= v.success_rate:
+            return P["success_rate_failed"], C.OC_UNSUCCESSFUL, None                      # :190
+        return self._apply(t, tgt, v, res, remote=True)
+
+    def _exploit_local(self, n, vid, kind, u):
+        """attacker_actions.py:353-547"""
+        P = self.pen
+        node = self.nodes[n]
+        if not node.agent_installed:
+            return P["invalid_action"], C.OC_INVALID_SRC_NOT_OWNED, None                  # :363
+        if node.status != C.ST_RUNNING:
+            return P["invalid_action"], C.OC_SRC_NOT_RUNNING, None                        # :370
+        v = node.vulns.get(vid)
+        if v is None:
+            return P["no_vulnerability_in_node"], C.OC_NO_VULNERABILITY, None             # :377
+        if v.priv_required and not node.privilege_level >= v.priv_required:
+            return P["no_enough_privileges"], C.OC_NO_PRIVILEGE, None                     # :386
+        res = next((r for r in v.results if r.kind == kind), None)                        # :397-400 (no type test)
+        if res is None:
+            return P["invalid_action"], C.OC_OUTCOME_NOT_PRESENT, None                    # :401
+        if u >= v.success_rate:
+            return P["success_rate_failed"], C.OC_UNSUCCESSFUL, None                      # :409
+        return self._apply(n, node, v, res, remote=False)
+
+    def _apply(self, t, tgt, v, res, remote):
+        """Per-outcome mutation and reward: attacker_actions.py:199-351 (remote) / :418-547 (local)."""
+        P, R = self.pen, self.rew
+        total, recon = 0, None
+        k = res.kind
+        if k == C.K_COLLECTION:
+            if not tgt.has_data:
+                return P["no_data_to_collect"], C.OC_NO_NEEDED, None
+            tgt.has_data, tgt.data_collected = False, True
+            total += R["data_collected_reward"]
+        elif k == C.K_PERSISTENCE:
+            if tgt.persistence:
+                return P["already_persistent"], C.OC_REPEATED, None
+            tgt.persistence = True
+            total += R["persistence_reward"]
+        elif k == C.K_DOS:
+            if remote and tgt.status == C.ST_STOPPED:                                     # :232 (unreachable, :127)
+                return P["node_already_stopped"], C.OC_REPEATED, None
+            tgt.status = C.ST_STOPPED
+            total += R["dos_coefficient"] * tgt.spec.value
+        elif k == C.K_DISCOVERY:
+            if tgt.visible:
+                return P["node_already_visible"], C.OC_REPEATED, None
+            tgt.visible = True
+            total += R["acquired_visibility_reward"]
+        elif k == C.K_EXFILTRATION:
+            if not (tgt.data_collected and not tgt.data_exfiltrated):
+                return P["no_data_to_exfiltrate"], C.OC_NO_NEEDED, None
+            tgt.data_exfiltrated = True
+            total += R["data_exfiltrated_reward"]
+        elif k == C.K_EVASION:
+            if tgt.defense_evasion:
+                return P["already_defense_evasion"], C.OC_REPEATED, None
+            tgt.defense_evasion = True
+            total += R["defense_evaded_reward"]
+        elif k == C.K_RECON:
+            new = 0
+            for n in res.nodes:                                                           # :291-296 / :506-511
+                if n not in self._discovered:
+                    self._discovered[n] = False
+                    new += 1
+            total += R["node_discovered_coefficient"] * new
+            recon = list(res.nodes)
+        elif k == C.K_PRIVESC:
+            if remote and tgt.privilege_level == C.PRIV_NONE:                             # :303 (remote only)
+                return P["privilege_escalation_in_node_not_owned"], C.OC_NO_PRIVILEGE, None
+            if tgt.privilege_level >= res.level:                                          # :309 / :518
+                return P["privilege_escalation_to_level_already_had"], C.OC_REPEATED, None
+            self._mark_owned(t, res.level)
+            total += R["privilege_escalation_reward"]
+        elif remote and k in (C.K_LATERAL, C.K_CREDACCESS):
+            ever, already = self._mark_owned(t, tgt.spec.level_at_access)                 # :327 (before the test!)
+            if already:
+                return P["node_already_owned"], C.OC_REPEATED, None                       # :331-335
+            if not ever:
+                total += R["value_coefficient"] * float(tgt.spec.value)                   # :336-340
+        else:
+            return P["outcome_not_valid"], C.OC_REMOTE_OUTCOME_LOCAL, None                # :345 / :536-540
+        total -= R["cost_coefficient"] * v.cost                                           # :348 / :544
+        return total, k, recon
+
+    # ---- episode logic (cyberbattle_env.py) ------------------------------------------------
+    def step_attacker_env(self, s, t, vid, kind, u):
+        """cyberbattle_env.py:299-394 step_attacker_env."""
+        if self.done:
+            raise RuntimeError("New episode must be started with env.reset()")            # :300-302
+        self.stepcount += 1
+        if s == t:
+            reward, code, recon = self._exploit_local(s, vid, kind, u)
+            self.vulnerability_type = "local"
+        else:
+            reward, code, recon = self._exploit_remote(s, t, vid, kind, u)
+            self.vulnerability_type = "remote"
+        self.reward = reward
+        self.outcome = code
+        # update_episode_by_outcome (:397-413)
+        if code == C.K_RECON:
+            new = 0
+            for n in recon:
+                if n not in self.discovered_nodes:
+                    self.discovered_nodes.append(n)
+                    new += 1
+            self.discovered_amount += new
+        elif code in (C.K_CREDACCESS, C.K_LATERAL):
+            self.owned_nodes.append(t)
+        elif code in (C.K_COLLECTION, C.K_EXFILTRATION, C.K_DISCOVERY):
+            self.discovered_amount += 1
+        # end checks (:338-370)
+        self.end_episode_reason = 0
+        self.truncated = False
+        if self.attacker_goal_reached():
+            if self.goal == "disruption" or self.cfg.stop_at_goal_reached:
+                self.done = True
+            self.reward = self.cfg.winning_reward
+            self.end_episode_reason = 1
+        elif self.check_end_game():
+            self.done = True
+            self.reward = self.cfg.losing_reward
+            self.end_episode_reason = 2
+        elif self.proportional_cutoff_coefficient and \
+                self.num_iterations >= self.proportional_nodes * self.proportional_cutoff_coefficient:   # :361,:457-460
+            self.truncated = True
+            self.end_episode_reason = 3
+        elif self.num_iterations >= self.episode_iterations:                               # :366
+            self.truncated = True
+            self.end_episode_reason = 3
+        if self.cfg.absolute_reward:
+            self.reward = max(0, self.reward)                                              # :379-380
+        running = [n for n in self.discovered_nodes if self.nodes[n].status == C.ST_RUNNING]
+        self.network_availability = len(running) / len(self.discovered_nodes)              # :389
+        self.num_iterations += 1                                                           # :394
+
+    def attacker_goal_reached(self):
+        """cyberbattle_env.py:467-514 (network-wide goals)."""
+        if self.goal == "control":
+            roots = [n for n in self.owned_nodes if self.nodes[n].privilege_level == C.PRIV_ROOT and n != self.starter]
+            return len(roots) == self.ownable_count
+        if self.goal == "disruption":
+            stopped = [n for n in self.discovered_nodes if self.nodes[n].status == C.ST_STOPPED and n != self.starter]
+            return len(stopped) == self.disruptable_count
+        if self.goal == "discovery":
+            disc = [n for n in self.discovered_nodes if n != self.starter]
+            data = [n for n in self.discovered_nodes if self.nodes[n].has_data]
+            pend = [n for n in self.discovered_nodes if self.nodes[n].data_collected and not self.nodes[n].data_exfiltrated]
+            return len(disc) == self.discoverable_count and not data and not pend
+        return False
+
+    def check_end_game(self):
+        """cyberbattle_env.py:438-454: lost when no owned node is Running."""
+        return not any(self.nodes[n].status == C.ST_RUNNING for n in self.owned_nodes)
+
+    def get_statistics(self):
+        """cyberbattle_env.py:517-524 (14-tuple)."""
+        owned = sum(1 for nd in self.nodes if nd.agent_installed)
+        disrupted = sum(1 for n in self.discovered_nodes if self.nodes[n].status == C.ST_STOPPED)
+        running = sum(1 for n in self.discovered_nodes if self.nodes[n].status == C.ST_RUNNING)
+        self.network_availability = running / len(self.discovered_nodes)
+        return (owned, len(self.discovered_nodes), self.N - len(self.discovered_nodes), disrupted, self.N,
+                self.ownable_count, self.discoverable_count, self.disruptable_count, self.network_availability,
+                0, 0, self.discovered_amount, self.discoverable_amount, self.attacker_goal_reached())
+
+    # ---- evolving visible graph + observation (cyberbattle_env_compressed.py) -----------------
+    def node_feature_vector(self, n):
+        """compressed:319-380 convert_node_info_to_observation + :198-203 (float32, flatten order)."""
+        nd, sp = self.nodes[n], self.nodes[n].spec
+        M, D = C.MAX_SERVICES, C.VULN_EMB_DIM
+        ports = [s.port for s in sp.services]
+        fw = [0] * (2 * M)
+        if nd.visible:
+            for port, perm in sp.fw_in:
+                i = ports.index(port) if port in ports else -1
+                if i != -1 and i < M:
+                    fw[i] = perm
+            for port, perm in sp.fw_out:
+                i = ports.index(port) if port in ports else -1
+                if i != -1 and i < M:
+                    fw[M + i] = perm
+        running = [0] * M
+        fv = [0.0] * D
+        if nd.visible:
+            acc = np.zeros(D, dtype=np.float64)
+            for i, s in enumerate(sp.services):
+                if i >= M:
+                    break
+                running[i] = int(s.running)
+                acc = acc + np.asarray(s.fv, dtype=np.float64)
+            if len(sp.services) > 0:
+                acc = acc / len(sp.services)
+            fv = list(acc)
+        mean = np.zeros(D, dtype=np.float64)
+        if sp.vulns:
+            for v in sp.vulns:
+                mean = mean + self.vuln_emb[v.vid]
+            mean = mean / len(sp.vulns)
+        flat = fw + running + [int(nd.visible), int(nd.persistence), int(nd.data_collected), int(nd.data_exfiltrated),
+                               int(nd.defense_evasion), int(sp.reimageable), int(nd.privilege_level), int(nd.status),
+                               sp.value, sp.sla_weight] + fv + list(mean)
+        return np.array(flat, dtype=np.float32)
+
+    def _add_graph_node(self, n):
+        self.graph_nodes.append(n)
+        self.node_x[n] = self.node_feature_vector(n)                                       # :206-207
+
+    def _add_edge(self, s, t, vid):
+        """compressed:214-246 add_edge_evolving_visible_graph (mean aggregation) incl. the accumulator reset."""
+        if t in self.graph_edges.get(s, {}):
+            if not self.exploited.get(s).get(t):                                           # :226-227
+                self.exploited[s][t] = []
+            self.exploited[s][t].append(self.vuln_emb[vid])
+        else:
+            self.graph_edges.setdefault(s, {})
+            self.exploited[s] = {}                                                         # :237 (wipes s's other lists)
+            self.exploited[s][t] = [self.vuln_emb[vid]]
+        self.graph_edges[s][t] = np.mean(self.exploited[s][t], axis=0)
+
+    def encode(self):
+        """compressed:249-306 encode (non *_node goals)."""
+        order = self.graph_nodes
+        pos = {n: i for i, n in enumerate(order)}
+        x = torch.from_numpy(np.stack([self.node_x[n] for n in order]))
+        src, dst, attrs = [], [], []
+        for s in order:                                   # networkx DiGraph.edges order: by source insertion order
+            for t, a in self.graph_edges.get(s, {}).items():
+                src.append(pos[s])
+                dst.append(pos[t])
+                attrs.append(a)
+        edge_index = torch.tensor([src, dst], dtype=torch.long).view(2, -1)
+        if attrs:
+            e = torch.from_numpy(np.array(attrs)).float()
+        else:
+            e = torch.zeros(C.VULN_EMB_DIM, dtype=torch.float32)                           # :258-259 (1-D)
+        z = self.gae.forward(x.float(), edge_index, e).numpy()
+        self.z_all = z
+        running = [n for n in order if self.nodes[n].status == C.ST_RUNNING]
+        node_embeddings = {}
+        if not running:                                                                    # :269-274
+            return node_embeddings, np.zeros(C.OBS_DIM, dtype=np.float32)
+        for n in running:
+            node_embeddings[n] = z[pos[n]]
+        arr = np.array([node_embeddings[n] for n in node_embeddings], dtype=np.float32)
+        obs = np.concatenate([np.average(arr, axis=0), np.max(arr, axis=0), np.min(arr, axis=0)])   # :285-298
+        return node_embeddings, obs
+
+    def _discrete_features(self):
+        return np.array([len(self.discovered_nodes), len(self.owned_nodes)])               # :309-316
+
+    def create_continuous_action_space(self):
+        """compressed:487-523 (+ :526-550) with sample_subset_samples=False."""
+        run_owned = [n for n in self.owned_nodes if self.nodes[n].status == C.ST_RUNNING]
+        run_disc = [n for n in self.discovered_nodes if self.nodes[n].status == C.ST_RUNNING]
+        # dict comprehension semantics (:491-494): duplicate keys collapse, first position kept
+        run_owned = list(dict.fromkeys(run_owned))
+        run_disc = list(dict.fromkeys(run_disc))
+        for s in run_owned:
+            es = self.node_embeddings[s]
+            for t in run_disc:
+                if (s, t) in self.processed_pairs:
+                    continue
+                et = self.node_embeddings[t]
+                if s == t:
+                    self._add_rows(s, es, t, et, 0)
+                self._add_rows(s, es, t, et, 1)
+                self.processed_pairs.add((s, t))
+
+    def _add_rows(self, s, es, t, et, vtype):
+        for vid, ri, kind, emb in self.per_node_type[t][vtype]:
+            if (s == t and kind == C.K_LATERAL) or kind == C.K_CREDACCESS:                 # :532 (precedence)
+                continue
+            if self.cfg.remove_all_obstacles and self.goal in ("control", "discovery") and kind == C.K_DOS:
+                continue                                                                   # :536-538
+            if self.cfg.remove_main_obstacles and kind == C.K_DOS and t == self.starter:
+                continue                                                                   # :541-543
+            self.action_keys.append((s, t, vid, kind, vtype, ri))
+            self.action_rows.append(np.concatenate((es, et, emb)))                         # :550
+            self._rows_cache = None
+
+    def find_closest_action_embedding(self, action_vector):
+        """compressed:570-590 with distance_metric='cosine'."""
+        if self._rows_cache is None:
+            self._rows_cache = np.array(self.action_rows)
+        seg = np.atleast_2d(np.array(action_vector, dtype=np.float32))
+        d = _sp_distance.cdist(seg, self._rows_cache, "cosine").flatten()
+        i = int(np.argmin(d))
+        s, t, vid, kind, vtype, ri = self.action_keys[i]
+        return s, t, vid, kind, d[i], i
+
+    def step(self, action_vector, uniform, forced=None):
+        """compressed:389-451.  ``forced`` = (s, t, vid, kind, distance) overrides the decode (used by the
+        GPU parity tests to follow a verified near-tie)."""
+        if forced is None:
+            s, t, vid, kind, dist, row = self.find_closest_action_embedding(action_vector)
+        else:
+            s, t, vid, kind, dist = forced
+            row = -1
+        self.last_row = row
+        self.step_attacker_env(s, t, vid, kind, float(uniform))
+        # update_evolving_visible_graph_after_step (:465-484)
+        for n in self.discovered_nodes:
+            if n not in self.node_x:
+                self._add_graph_node(n)
+        if self.outcome in _REFRESH_KINDS:
+            self.node_x[t] = self.node_feature_vector(t)
+        self.edge_added = self.reward > 0
+        if self.edge_added:
+            self._add_edge(s, t, vid)
+        self.reencoded = kind in _REENCODE_KINDS                                           # :401 (desired outcome)
+        if self.reencoded:
+            self.node_embeddings, emb = self.encode()
+            self.n_encodes += 1
+            self.observation = {"graph_embeddings": emb, "discrete_features": self._discrete_features()}
+            self.create_continuous_action_space()
+        self.reward += self.pen["distance_penalty"] * dist                                 # :430
+        info = dict(source_node=s, target_node=t, vulnerability=vid, outcome_kind=kind, outcome_obtained=self.outcome,
+                    vulnerability_type=self.vulnerability_type, end_episode_reason=self.end_episode_reason,
+                    min_distance_action=dist, step_count=self.stepcount, network_availability=self.network_availability)
+        return self.observation, self.reward, self.done or self.truncated, info           # :451
+
+    # ---- state export for bit-exact comparison ---------------------------------------------
+    def masks(self):
+        """Per-plane bitmask (Python int) in constants.M_* order."""
+        m = [0] * C.N_MASKS
+        for j, nd in enumerate(self.nodes):
+            b = 1 << j
+            if nd.agent_installed:
+                m[C.M_OWNED] |= b
+            if j in self.discovered_nodes:
+                m[C.M_DISCOVERED] |= b
+            if nd.visible:
+                m[C.M_VISIBLE] |= b
+            if nd.has_data:
+                m[C.M_HAS_DATA] |= b
+            if nd.data_collected:
+                m[C.M_COLLECTED] |= b
+            if nd.data_exfiltrated:
+                m[C.M_EXFILTRATED] |= b
+            if nd.persistence:
+                m[C.M_PERSISTENCE] |= b
+            if nd.defense_evasion:
+                m[C.M_EVASION] |= b
+            if nd.status == C.ST_STOPPED:
+                m[C.M_STOPPED] |= b
+            if nd.privilege_level >= C.PRIV_USER:
+                m[C.M_PRIV_USER] |= b
+            if nd.privilege_level == C.PRIV_ROOT:
+                m[C.M_PRIV_ROOT] |= b
+        return m

@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE (build container only) — generate tests/golden/*.npz from the UNMODIFIED reference.
+
+    python oracle/gen_golden.py            # regenerate every case
+    python oracle/gen_golden.py g20_control
+
+For each case: build a reference-schema input graph (ccbs_b200.scenario.synthetic_input_graph), run
+the reference's own scenario generator on it (``Model(network=G)``, simulation/model.py:353), construct
+the reference ``CyberBattleCompressedEnv`` behind ``RandomSwitchEnv`` with a seeded default-architecture
+GAE encoder, and step it with seeded actions / pre-drawn uniforms / pre-drawn starters
+(oracle/trace.py).  The fixture stores the *structure* the reference generator produced (JSON inside
+the npz) plus the seeds that regenerate every 768-d vector, and the per-step trace.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+import ccbs_b200 as cb                                                  # noqa: E402
+from ccbs_b200.gae import GaeWeights                                    # noqa: E402
+from ccbs_b200.scenario import spec_to_dict, spec_from_dict, embeddings_of_input_graph  # noqa: E402
+from oracle import trace as tr                                          # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+# name -> parameters.  `cfg` entries override EnvConfig defaults (= agents/config/train_config.yaml).
+CASES = {
+    # ~20-node generator-default scenarios (configs[1])
+    "g20_control": dict(graph_seed=11, nodes=20, steps=1500, cfg=dict(goal="control")),
+    "g12_discovery": dict(graph_seed=12, nodes=12, steps=800, cfg=dict(goal="discovery")),
+    "g16_disruption": dict(graph_seed=13, nodes=16, steps=800, cfg=dict(goal="disruption", remove_main_obstacles=False)),
+    # 32-node (configs[2])
+    "g32_control": dict(graph_seed=14, nodes=32, steps=1500, cfg=dict(goal="control")),
+    # long episodes: no proportional cut-off, goal does not stop the episode, clamped reward
+    "g10_long": dict(graph_seed=15, nodes=10, steps=900,
+                     cfg=dict(goal="control", proportional_cutoff_coefficient=0, episode_iterations=120,
+                              stop_at_goal_reached=False, absolute_reward=True, remove_main_obstacles=False)),
+    # 100-node "default-like" scenario (configs[0]); >64 nodes exercises 4-word masks
+    "g100_control": dict(graph_seed=16, nodes=100, steps=1200, pool_size=560, services_range=(1, 4),
+                         vulns_per_service_range=(8, 18), cfg=dict(goal="control")),
+}
+POOL_SEED = 1234
+GAE_SEED = 0
+
+
+def build_case(name):
+    p = CASES[name]
+    from oracle import ref_bridge as rb
+    pool = cb.synthetic_vuln_pool(POOL_SEED, p.get("pool_size", 200))
+    gkw = {k: p[k] for k in ("services_range", "vulns_per_service_range") if k in p}
+    graph = cb.synthetic_input_graph(p["graph_seed"], p["nodes"], pool=pool, **gkw)
+    model = rb.reference_model_from_input_graph(graph, seed=p["graph_seed"])
+    spec = cb.spec_from_model(model, name=name)
+    cfg = cb.EnvConfig(**p["cfg"])
+    weights = GaeWeights.random(GAE_SEED)
+    return p, graph, model, spec, cfg, weights
+
+
+def generate(name):
+    from oracle import ref_bridge as rb
+    t0 = time.time()
+    p, graph, model, spec, cfg, weights = build_case(name)
+    tables = cb.compile_scenarios([spec], cfg.isolation_filter_threshold)      # also cross-checks reach counts
+    feasible = tables.feasible_starters[cb.constants.GOALS[cfg.goal]]
+    actions, uniforms = tr.make_inputs(p["graph_seed"] * 1000 + 1, p["steps"])
+    starters = tr.make_starters(p["graph_seed"] * 1000 + 2, feasible, p["steps"] + 2)
+    runner = rb.ReferenceRunner(model, weights, cfg)
+    rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters)
+    meta = dict(name=name, params={k: v for k, v in p.items() if k != "cfg"}, cfg=p["cfg"], pool_seed=POOL_SEED,
+                gae_seed=GAE_SEED, input_seed=p["graph_seed"] * 1000 + 1, starter_seed=p["graph_seed"] * 1000 + 2,
+                spec=spec_to_dict(spec),
+                emb_checksum=float(sum(float(np.sum(v)) for v in spec.vuln_emb.values())))
+    out = {k: v for k, v in rec.items()}
+    # store obs compactly: unique consecutive rows + index
+    obs = out.pop("obs")
+    change = np.ones(len(obs), bool)
+    change[1:] = np.any(obs[1:] != obs[:-1], axis=1)
+    out["obs_rows"] = obs[change]
+    out["obs_idx"] = (np.cumsum(change) - 1).astype(np.int32)
+    out["starters"] = starters[: int(rec["num_episodes"])]
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **out)
+    eps = int(rec["num_episodes"])
+    print(f"{name}: {p['steps']} steps, {eps} episodes, {os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.1f}s; "
+          f"success codes seen: {sorted(set(rec['code'].tolist()))}; end reasons: {np.bincount(rec['reason'], minlength=4).tolist()}")
+
+
+def load_case(path):
+    """Rebuild (spec, cfg, weights, actions, uniforms, starters, trace) from a fixture — no reference needed."""
+    z = np.load(path)
+    meta = json.loads(bytes(z["meta"]).decode())
+    p = meta["params"]
+    pool = cb.synthetic_vuln_pool(meta["pool_seed"], p.get("pool_size", 200))
+    gkw = {k: tuple(p[k]) for k in ("services_range", "vulns_per_service_range") if k in p}
+    graph = cb.synthetic_input_graph(p["graph_seed"], p["nodes"], pool=pool, **gkw)
+    vuln_emb, service_fv = embeddings_of_input_graph(graph)
+    spec = spec_from_dict(meta["spec"], vuln_emb, service_fv)
+    chk = float(sum(float(np.sum(v)) for v in spec.vuln_emb.values()))
+    if abs(chk - meta["emb_checksum"]) > 1e-6 * max(1.0, abs(chk)):
+        raise RuntimeError("golden fixture: regenerated embeddings do not match the recorded checksum")
+    cfg = cb.EnvConfig(**meta["cfg"])
+    weights = GaeWeights.random(meta["gae_seed"])
+    actions, uniforms = tr.make_inputs(meta["input_seed"], p["steps"])
+    rec = {k: z[k] for k in z.files if k not in ("meta", "obs_rows", "obs_idx")}
+    rec["obs"] = z["obs_rows"][z["obs_idx"]]
+    return dict(meta=meta, spec=spec, cfg=cfg, weights=weights, actions=actions, uniforms=uniforms,
+                starters=z["starters"], trace=rec)
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        generate(n)

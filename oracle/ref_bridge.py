@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE (build container only) — drive the UNMODIFIED reference env.
+
+Imports ``/root/reference/cyberbattle`` under the stub modules of ``oracle/shims`` and records
+traces from the reference's own ``RandomSwitchEnv -> CyberBattleCompressedEnv`` with the
+success-rate draws and the starter choice replaced by pre-drawn values.  Nothing here is copied from
+the reference; nothing here runs on the GPU box (``/root/reference`` does not exist there).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import random as _py_random
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get("CBS_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+
+
+def reference_available() -> bool:
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "cyberbattle"))
+
+
+def import_reference():
+    """Put the shims and the read-only reference tree on sys.path (never writes bytecode there)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    sys.dont_write_bytecode = True
+    for p in (_SHIMS, REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import cyberbattle.simulation.model as m                       # noqa: F401
+    import cyberbattle.simulation.attacker_actions as aa           # noqa: F401
+    import cyberbattle._env.cyberbattle_env as ce                  # noqa: F401
+    import cyberbattle._env.cyberbattle_env_compressed as cc       # noqa: F401
+    import cyberbattle._env.cyberbattle_env_switch as cs           # noqa: F401
+    import cyberbattle.gae.model as gm                             # noqa: F401
+    # imported eagerly: its import chain (transformers, ...) draws from the global `random`, which must
+    # not happen between random.seed() and Model() in reference_model_from_input_graph
+    import cyberbattle.simulation.generate_network                 # noqa: F401
+    return dict(model=m, attacker_actions=aa, env=ce, compressed=cc, switch=cs, gae=gm)
+
+
+def reference_model_from_input_graph(graph: dict, seed: int, **model_kwargs):
+    """Run the reference's own scenario generator (model.py:353-420 -> generate_network.py:97) on a
+    reference-schema input graph."""
+    import networkx as nx
+    ref = import_reference()
+    G = nx.DiGraph()
+    for nid, attrs in graph.items():
+        services = []
+        for svc in attrs["services"]:
+            s = dict(svc)
+            s["feature_vector"] = [float(x) for x in svc["feature_vector"]]
+            s["vulnerabilities"] = [dict(v, feature_vector=[float(x) for x in v["feature_vector"]])
+                                    for v in svc.get("vulnerabilities", [])]
+            services.append(s)
+        G.add_node(nid, category=attrs["category"], services=services)
+    _py_random.seed(seed)
+    return ref["model"].Model(network=G, vulnerability_classifier=None, **model_kwargs)
+
+
+class _FakeRandom:
+    """Stands in for the ``random`` module inside attacker_actions / cyberbattle_env."""
+
+    def __init__(self):
+        self.next_uniform = None
+        self.next_starter = None
+        self.uniform_consumed = False
+
+    def random(self):
+        self.uniform_consumed = True
+        return float(self.next_uniform)
+
+    def randrange(self, n):
+        return int(self.next_starter)
+
+    def choice(self, seq):
+        return seq[0]
+
+    def __getattr__(self, name):
+        return getattr(_py_random, name)
+
+
+class ReferenceRunner:
+    """One reference ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv])`` with controlled randomness."""
+
+    def __init__(self, model, gae_weights, cfg):
+        import torch
+        ref = import_reference()
+        self.ref = ref
+        logger = logging.getLogger("cbs_ref")
+        logger.setLevel(logging.CRITICAL)
+        self.fake = _FakeRandom()
+        ref["attacker_actions"].random = self.fake
+        ref["env"].random = self.fake
+        layers = [dict(type="NNConv", NN_channels=16, out_channels=64, activation="ReLU"),
+                  dict(type="GCNConv", out_channels=64, activation="ReLU")]
+        torch.manual_seed(0)
+        enc = ref["gae"].GAEEncoder(1576, layers, 768)
+        enc.load_state_dict(gae_weights.state_dict())
+        enc.eval()                                                     # agents/train_agent.py:333
+        self.fake.next_starter = 0
+        kw = cfg.reference_kwargs()
+        env = ref["compressed"].CyberBattleCompressedEnv(initial_environment=model, logger=logger, verbose=0, **kw)
+        env.set_graph_encoder(enc)
+        env.set_pca_components(768)
+        self.env = env
+        self.ids = list(model.network.nodes)
+        self.index = {n: i for i, n in enumerate(self.ids)}
+        self.wrapper = None
+
+    def reset(self, starter: int):
+        self.fake.next_starter = int(starter)
+        if self.wrapper is None:
+            np.random.seed(0)
+            self.wrapper = self.ref["switch"].RandomSwitchEnv(envs_ids=[0], switch_interval=10 ** 9,
+                                                              envs_list=[self.env], verbose=0)
+        obs, _ = self.wrapper.reset()
+        return obs
+
+    def step(self, action, uniform):
+        self.fake.next_uniform = float(uniform)
+        self.fake.uniform_consumed = False
+        obs, reward, done, truncated, info = self.wrapper.step(action)
+        return obs, reward, done, truncated, info
+
+    # ---- state extraction --------------------------------------------------------------
+    def masks(self):
+        import ccbs_b200.constants as C
+        env = self.env
+        m = [0] * C.N_MASKS
+        for j, nid in enumerate(self.ids):
+            nd = env.get_node(nid)
+            b = 1 << j
+            if nd.agent_installed:
+                m[C.M_OWNED] |= b
+            if nid in env.discovered_nodes:
+                m[C.M_DISCOVERED] |= b
+            if nd.visible:
+                m[C.M_VISIBLE] |= b
+            if nd.has_data:
+                m[C.M_HAS_DATA] |= b
+            if nd.data_collected:
+                m[C.M_COLLECTED] |= b
+            if nd.data_exfiltrated:
+                m[C.M_EXFILTRATED] |= b
+            if nd.persistence:
+                m[C.M_PERSISTENCE] |= b
+            if nd.defense_evasion:
+                m[C.M_EVASION] |= b
+            if nd.status.value == C.ST_STOPPED:
+                m[C.M_STOPPED] |= b
+            if int(nd.privilege_level) >= C.PRIV_USER:
+                m[C.M_PRIV_USER] |= b
+            if int(nd.privilege_level) == C.PRIV_ROOT:
+                m[C.M_PRIV_ROOT] |= b
+        return m
+
+    def obtained_code(self):
+        """Map env.outcome (a model.VulnerabilityOutcome instance) to constants.OC_* / K_*."""
+        import ccbs_b200.constants as C
+        from ccbs_b200.scenario import _KIND_BY_CLASSNAME
+        o = self.env.outcome
+        name = type(o).__name__
+        if name in _KIND_BY_CLASSNAME:
+            return _KIND_BY_CLASSNAME[name]
+        if name == "InvalidAction":
+            return C.OC_INVALID_SRC_NOT_OWNED if "source" in o.reason else C.OC_INVALID_TGT_NOT_DISCOVERED
+        if name == "NonRunningMachine":
+            return C.OC_SRC_NOT_RUNNING if o.source_or_target == 0 else C.OC_TGT_NOT_RUNNING
+        if name == "FirewallBlock":
+            return C.OC_FW_OUTGOING if o.incoming_or_outgoing == 1 else C.OC_FW_INCOMING
+        return {"NoVulnerability": C.OC_NO_VULNERABILITY, "NoEnoughPrivilege": C.OC_NO_PRIVILEGE,
+                "OutcomeNonPresent": C.OC_OUTCOME_NOT_PRESENT, "NonListeningPort": C.OC_PORT_NOT_LISTENING,
+                "UnsuccessfulAction": C.OC_UNSUCCESSFUL, "NoNeededAction": C.OC_NO_NEEDED,
+                "RepeatedResult": C.OC_REPEATED, "RemoteOutcomeInLocalNode": C.OC_REMOTE_OUTCOME_LOCAL}[name]

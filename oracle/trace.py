@@ -1,0 +1,179 @@
+"""TEST INFRASTRUCTURE — trace protocol shared by the golden generator (reference side) and the
+oracle / GPU parity tests.
+
+A trace is: a scenario, GAE weights (seeded), an env config, a float32 action sequence, a float32
+uniform sequence (success-rate draws) and one starter node per episode.  The env is stepped with
+auto-reset (reset right after a step that returned done-or-truncated, as DummyVecEnv does) and after
+every step the full integer state, the reward, the flags, the decoded action and the observation are
+recorded.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import ccbs_b200.constants as C
+
+
+def make_inputs(seed: int, steps: int):
+    """Actions U(-4,4)^905 float32 (the action_space bounds, compressed:112-114) and uniforms in [0,1)."""
+    rng = np.random.default_rng(seed)
+    actions = rng.uniform(-4.0, 4.0, size=(steps, C.ACTION_DIM)).astype(np.float32)
+    uniforms = rng.random(steps, dtype=np.float32)
+    return actions, uniforms
+
+
+def make_starters(seed: int, feasible, count: int):
+    rng = np.random.default_rng(seed)
+    feasible = np.asarray(feasible)
+    return feasible[rng.integers(len(feasible), size=count)].astype(np.int32)
+
+
+def vuln_index(spec):
+    """vulnerability_ID -> scenario-local unique index (first-appearance order, same as the compiler)."""
+    idx = {}
+    for nd in spec.nodes:
+        for v in nd.vulns:
+            idx.setdefault(v.vid, len(idx))
+    return idx
+
+
+def masks_to_array(masks):
+    out = np.zeros((C.N_MASKS, 2), dtype=np.uint64)
+    for i, m in enumerate(masks):
+        out[i, 0] = m & 0xFFFFFFFFFFFFFFFF
+        out[i, 1] = (m >> 64) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+class OracleAdapter:
+    def __init__(self, env, spec):
+        self.env, self.vidx, self.N = env, vuln_index(spec), spec.num_nodes
+
+    def reset(self, starter):
+        o = self.env.reset(starter=int(starter))
+        return np.concatenate([o["graph_embeddings"].astype(np.float32), o["discrete_features"].astype(np.float32)])
+
+    def step(self, action, u, forced=None):
+        o, r, d, info = self.env.step(action, u, forced=forced)
+        obs = np.concatenate([o["graph_embeddings"].astype(np.float32), o["discrete_features"].astype(np.float32)])
+        e = self.env
+        sel = (info["source_node"], info["target_node"], self.vidx[info["vulnerability"]], info["outcome_kind"])
+        return obs, float(r), bool(e.done), bool(e.truncated), sel, int(e.outcome), int(e.end_episode_reason), \
+            float(info["min_distance_action"])
+
+    def masks(self):
+        return self.env.masks()
+
+    def lists(self):
+        return list(self.env.discovered_nodes), list(self.env.owned_nodes)
+
+    def counters(self):
+        e = self.env
+        return (e.stepcount, e.num_iterations, e.discovered_amount, e.ownable_count, e.discoverable_count,
+                e.disruptable_count, e.discoverable_amount)
+
+    def statistics(self):
+        return self.env.get_statistics()
+
+
+class ReferenceAdapter:
+    """Same surface over oracle.ref_bridge.ReferenceRunner (build container only)."""
+
+    def __init__(self, runner, spec):
+        self.r, self.vidx, self.N = runner, vuln_index(spec), spec.num_nodes
+
+    @staticmethod
+    def _obs(o):
+        return np.concatenate([np.asarray(o["graph_embeddings"], dtype=np.float32),
+                               np.asarray(o["discrete_features"], dtype=np.float32)])
+
+    def reset(self, starter):
+        return self._obs(self.r.reset(starter))
+
+    def step(self, action, u, forced=None):
+        from ccbs_b200.scenario import _KIND_BY_CLASSNAME
+        o, reward, done_or_trunc, truncated, info = self.r.step(action, u)
+        env = self.r.env
+        kind = _KIND_BY_CLASSNAME[type(info["outcome_class"]).__name__]
+        sel = (self.r.index[info["source_node"]], self.r.index[info["target_node"]], self.vidx[info["vulnerability"]], kind)
+        assert bool(done_or_trunc) == bool(env.done or env.truncated)
+        return self._obs(o), float(reward), bool(env.done), bool(env.truncated), sel, self.r.obtained_code(), \
+            int(info["end_episode_reason"]), float(info["min_distance_action"])
+
+    def masks(self):
+        return self.r.masks()
+
+    def lists(self):
+        e = self.r.env
+        return [self.r.index[n] for n in e.discovered_nodes], [self.r.index[n] for n in e.owned_nodes]
+
+    def counters(self):
+        e = self.r.env
+        return (e.stepcount, e.num_iterations, e.discovered_amount, e.ownable_count, e.discoverable_count,
+                e.disruptable_count, e.discoverable_amount)
+
+    def statistics(self):
+        return self.r.wrapper.get_statistics()
+
+
+def record(adapter, actions, uniforms, starters):
+    """Step ``adapter`` through the whole action sequence with auto-reset; return a dict of arrays."""
+    T, N = len(actions), adapter.N
+    rec = dict(sel=np.zeros((T, 4), np.int32), code=np.zeros(T, np.int32), reward=np.zeros(T, np.float64),
+               done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
+               dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
+               disc_order=np.full((T, N), -1, np.int16), owned_order=np.full((T, N), -1, np.int16),
+               counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, C.OBS_DIM + 2), np.float32),
+               episode=np.zeros(T, np.int32))
+    reset_obs, reset_masks, stats = [], [], []
+    ep = 0
+    reset_obs.append(adapter.reset(starters[ep]))
+    reset_masks.append(masks_to_array(adapter.masks()))
+    for t in range(T):
+        obs, r, done, trunc, sel, code, reason, dist = adapter.step(actions[t], uniforms[t])
+        rec["sel"][t], rec["code"][t], rec["reward"][t] = sel, code, r
+        rec["done"][t], rec["truncated"][t], rec["reason"][t], rec["dist"][t] = done, trunc, reason, dist
+        rec["masks"][t] = masks_to_array(adapter.masks())
+        d, o = adapter.lists()
+        rec["disc_order"][t, :len(d)] = d
+        rec["owned_order"][t, :len(o)] = o
+        rec["counters"][t] = adapter.counters()
+        rec["obs"][t] = obs
+        rec["episode"][t] = ep
+        if done or trunc:
+            stats.append([float(x) for x in adapter.statistics()])
+            ep += 1
+            if ep >= len(starters):
+                raise RuntimeError("not enough starters for the number of episodes")
+            reset_obs.append(adapter.reset(starters[ep]))
+            reset_masks.append(masks_to_array(adapter.masks()))
+    rec["reset_obs"] = np.array(reset_obs, np.float32)
+    rec["reset_masks"] = np.array(reset_masks, np.uint64)
+    rec["stats"] = np.array(stats, np.float64).reshape(-1, 14)
+    rec["num_episodes"] = np.array(ep + 1, np.int32)
+    return rec
+
+
+INT_KEYS = ("sel", "code", "done", "truncated", "reason", "masks", "disc_order", "owned_order", "counters",
+            "episode", "reset_masks", "num_episodes")
+
+
+def compare(a, b, rtol=1e-5, atol=1e-5, label=""):
+    """Integer state bit-exact; reward / distance / obs / stats within tolerance.  Returns a report."""
+    report = {}
+    for k in INT_KEYS:
+        if not np.array_equal(a[k], b[k]):
+            bad = np.argwhere(np.asarray(a[k]) != np.asarray(b[k]))
+            raise AssertionError(f"{label}: integer field '{k}' differs first at {bad[0].tolist()} "
+                                 f"({np.asarray(a[k])[tuple(bad[0])]} vs {np.asarray(b[k])[tuple(bad[0])]})")
+    for k in ("reward", "dist", "obs", "reset_obs", "stats"):
+        x, y = np.asarray(a[k], np.float64), np.asarray(b[k], np.float64)
+        if x.shape != y.shape:
+            raise AssertionError(f"{label}: '{k}' shape {x.shape} vs {y.shape}")
+        err = np.abs(x - y)
+        tol = atol + rtol * np.abs(y)
+        report[k] = float(err.max()) if err.size else 0.0
+        if np.any(err > tol):
+            i = np.unravel_index(np.argmax(err - tol), err.shape)
+            raise AssertionError(f"{label}: '{k}' differs at {i}: {x[i]} vs {y[i]} (|d|={err[i]:.3e})")
+    return report

@@ -1,0 +1,41 @@
+"""The oracle (oracle/cbs_oracle.py) against golden traces recorded from the UNMODIFIED reference
+(oracle/gen_golden.py): integer state bit-exact, reward / distance / observation within 1e-5."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gen_golden as gg, trace as tr
+from oracle.cbs_oracle import OracleEnv
+
+CASES = sorted(os.path.splitext(os.path.basename(p))[0]
+               for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def test_fixtures_present():
+    assert set(gg.CASES) <= set(CASES), "regenerate with `python oracle/gen_golden.py`"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_replays_reference_trace(name, golden_dir):
+    case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
+    env = OracleEnv(case["spec"], case["weights"], case["cfg"])
+    rec = tr.record(tr.OracleAdapter(env, case["spec"]), case["actions"], case["uniforms"], case["starters"])
+    report = tr.compare(rec, case["trace"], rtol=1e-5, atol=1e-6, label=name)
+    assert report["obs"] <= 1e-5
+    # the fixtures exercise what they claim to
+    codes = set(case["trace"]["code"].tolist())
+    assert {0, 1, 2, 3, 4, 5, 6, 7, 9} <= codes          # every success kind that can enter the table
+    assert int(case["trace"]["num_episodes"]) > 5
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
+def test_golden_regenerates_identically(golden_dir, tmp_path, monkeypatch):
+    """Re-run the reference on the smallest case and check the committed fixture is reproducible."""
+    monkeypatch.setattr(gg, "GOLDEN_DIR", str(tmp_path))
+    gg.generate("g10_long")
+    a = gg.load_case(os.path.join(str(tmp_path), "g10_long.npz"))["trace"]
+    b = gg.load_case(os.path.join(golden_dir, "g10_long.npz"))["trace"]
+    tr.compare(a, b, rtol=0, atol=0, label="regen")
