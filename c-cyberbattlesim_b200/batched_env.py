@@ -1,0 +1,231 @@
+"""BatchedCyberBattleEnv — B independent continuous envs on one GPU behind libcbsim's C ABI.
+
+Mirrors, per env, ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv...])`` of the reference
+(_env/cyberbattle_env_switch.py:109-167, _env/cyberbattle_env_compressed.py:158-189,389-451):
+``reset()`` -> observations, ``step(actions)`` -> (obs, reward, done, info).  PyTorch supplies device
+buffers and the CUDA stream; all env logic runs in the library's kernels.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import constants as C
+from . import lib as L
+from .config import EnvConfig
+from .gae import GaeWeights, fold_gae
+from .scenario import ScenarioSpec, ScenarioTables, compile_scenarios
+
+
+class CbsError(RuntimeError):
+    pass
+
+
+class BatchedCyberBattleEnv:
+    def __init__(self, specs: Sequence[ScenarioSpec], gae_weights: GaeWeights, cfg: Optional[EnvConfig] = None,
+                 num_envs: int = 1, device: int = 0, scenario_of_env: Optional[np.ndarray] = None, seed: int = 0,
+                 global_env_offset: int = 0, auto_reset: bool = True, switch_interval: int = 0,
+                 tables: Optional[ScenarioTables] = None, **cfg_overrides):
+        if not torch.cuda.is_available():
+            raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
+        self.cfg = cfg or EnvConfig()
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", device)
+        self.lib = L.load_library()
+        self.tables = tables if tables is not None else compile_scenarios(specs, self.cfg.isolation_filter_threshold)
+        self.gae_tables = fold_gae(self.tables, gae_weights)
+        ccfg = L.make_config(self.cfg, self.num_envs, device=device, global_env_offset=global_env_offset, seed=seed,
+                             auto_reset=auto_reset, switch_interval=switch_interval, **cfg_overrides)
+        self._h = ct.c_void_p()
+        rc = self.lib.cbs_create(ct.byref(ccfg), ct.byref(self._h))
+        if rc != 0:
+            raise CbsError(f"cbs_create failed ({rc}): {self.lib.cbs_last_error(None).decode()}")
+        st, keep1 = L.make_scenario_struct(self.tables, C.GOALS[self.cfg.goal])
+        gt, keep2 = L.make_gae_struct(self.gae_tables)
+        self._check(self.lib.cbs_load_scenarios(self._h, ct.byref(st), ct.byref(gt)))
+        del keep1, keep2
+        if scenario_of_env is None:
+            scenario_of_env = np.arange(self.num_envs, dtype=np.int32) % self.tables.num_scenarios
+        self.scenario_of_env = np.ascontiguousarray(scenario_of_env, dtype=np.int32)
+        self._check(self.lib.cbs_set_scenarios(self._h, self.scenario_of_env.ctypes.data_as(ct.c_void_p)))
+        caps = (ct.c_int32 * 4)()
+        self.lib.cbs_capacities(self._h, caps)
+        self.ncap, self.slots, self.ecap, self.tensor_core_decode = caps[0], caps[1], caps[2], bool(caps[3])
+        B = self.num_envs
+        with torch.cuda.device(self.device):
+            self.obs = torch.zeros(B, C.OBS_DIM + 2, dtype=torch.float32, device=self.device)
+            self.reward = torch.zeros(B, dtype=torch.float32, device=self.device)
+            self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
+            self.truncated = torch.zeros(B, dtype=torch.uint8, device=self.device)
+            self.outcome = torch.zeros(B, dtype=torch.uint8, device=self.device)
+            self.info = torch.zeros(B, 8, dtype=torch.int32, device=self.device)
+            self.sel = torch.zeros(B, 4, dtype=torch.int32, device=self.device)
+            self.dist = torch.zeros(B, dtype=torch.float64, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise CbsError(f"libcbsim error {rc}: {self.lib.cbs_last_error(self._h).decode()}")
+
+    def _stream(self):
+        return ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else ct.c_void_p(t.data_ptr())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.cbs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-facing surface ------------------------------------------------------------
+    def set_starter_queue(self, queue: Optional[np.ndarray]):
+        """queue[num_envs, qlen] explicit starter nodes per episode (tests); None = random feasible starters."""
+        if queue is None:
+            self._check(self.lib.cbs_set_starter_queue(self._h, None, 0))
+        else:
+            q = np.ascontiguousarray(queue, dtype=np.int32)
+            assert q.shape[0] == self.num_envs
+            self._check(self.lib.cbs_set_starter_queue(self._h, q.ctypes.data_as(ct.c_void_p), q.shape[1]))
+
+    def set_cut_off(self, cut_off: int):
+        """cyberbattle_env_switch.py:198-199"""
+        self.cfg.episode_iterations = int(cut_off)
+        self._check(self.lib.cbs_set_cutoffs(self._h, int(cut_off), float(self.cfg.proportional_cutoff_coefficient or 0)))
+
+    def set_proportional_cutoff_coefficient(self, coefficient: float):
+        """cyberbattle_env_switch.py:202-203"""
+        self.cfg.proportional_cutoff_coefficient = coefficient
+        self._check(self.lib.cbs_set_cutoffs(self._h, int(self.cfg.episode_iterations), float(coefficient or 0)))
+
+    def reset(self, env_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all envs (or those with env_mask != 0).  Returns obs[B, 194] (device tensor, reused)."""
+        if env_mask is not None:
+            env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._check(self.lib.cbs_reset(self._h, self._p(env_mask), self._p(self.obs), self._stream()))
+        return self.obs
+
+    def decode(self, actions: torch.Tensor):
+        actions = self._actions(actions)
+        self._check(self.lib.cbs_decode(self._h, self._p(actions), self._p(self.sel), self._p(self.dist), self._stream()))
+        return self.sel, self.dist
+
+    def transition(self, sel: torch.Tensor, dist: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None):
+        sel = sel.to(device=self.device, dtype=torch.int32).contiguous()
+        if dist is not None:
+            dist = dist.to(device=self.device, dtype=torch.float64).contiguous()
+        uniforms = self._uniforms(uniforms)
+        self._check(self.lib.cbs_transition(self._h, self._p(sel), self._p(dist), self._p(uniforms), self._p(self.reward),
+                                            self._p(self.done), self._p(self.truncated), self._p(self.outcome), self._stream()))
+        return self.reward, self.done, self.truncated, self.outcome
+
+    def observe(self) -> torch.Tensor:
+        self._check(self.lib.cbs_observe(self._h, self._p(self.obs), self._stream()))
+        return self.obs
+
+    def step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None, want_info: bool = True):
+        """One batched step with device tensors.  Returns (obs[B,194], reward[B], done[B] (= done|truncated,
+        compressed:451), info[B,8] int32).  Finished envs are reset in place when auto_reset is on; their last
+        observation is available from :meth:`terminal_obs`."""
+        actions = self._actions(actions)
+        uniforms = self._uniforms(uniforms)
+        self._check(self.lib.cbs_step(self._h, self._p(actions), self._p(uniforms), self._p(self.obs), self._p(self.reward),
+                                      self._p(self.done), self._p(self.info) if want_info else None, self._stream()))
+        return self.obs, self.reward, self.done, self.info
+
+    def step_host(self, actions: np.ndarray, uniforms: Optional[np.ndarray], obs: np.ndarray, reward: np.ndarray,
+                  done: np.ndarray, info: Optional[np.ndarray] = None):
+        """The same step through HOST buffers (numpy, ideally pinned): copies in, steps, copies out, synchronises."""
+        assert actions.dtype == np.float32 and actions.shape == (self.num_envs, C.ACTION_DIM) and actions.flags.c_contiguous
+        v = lambda a: None if a is None else a.ctypes.data_as(ct.c_void_p)  # noqa: E731
+        self._check(self.lib.cbs_step_host(self._h, v(actions), v(uniforms), v(obs), v(reward), v(done), v(info)))
+
+    def _actions(self, actions):
+        if actions.shape != (self.num_envs, C.ACTION_DIM):
+            raise ValueError(f"actions must have shape ({self.num_envs}, {C.ACTION_DIM})")
+        return actions.to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _uniforms(self, uniforms):
+        if uniforms is None:
+            return None
+        return uniforms.to(device=self.device, dtype=torch.float32).contiguous()
+
+    # ---- state access ---------------------------------------------------------------------
+    def sync(self):
+        self._check(self.lib.cbs_sync(self._h))
+
+    def read(self, field: int, dtype, shape):
+        out = np.empty(shape, dtype=dtype)
+        n = self.lib.cbs_read_state(self._h, field, out.ctypes.data_as(ct.c_void_p), out.nbytes)
+        if n < 0:
+            self._check(int(n))
+        return out
+
+    def masks(self) -> np.ndarray:
+        """uint32[N_MASKS, words, B]"""
+        return self.read(L.F_MASKS, np.uint32, (C.N_MASKS, self.tables.words, self.num_envs))
+
+    def scalars(self) -> np.ndarray:
+        return self.read(L.F_SCALARS, np.int32, (L.NUM_SCALARS, self.num_envs))
+
+    def disc_order(self) -> np.ndarray:
+        return self.read(L.F_DISC_ORDER, np.uint8, (self.num_envs, self.ncap))
+
+    def owned_order(self) -> np.ndarray:
+        return self.read(L.F_OWNED_ORDER, np.uint8, (self.num_envs, self.ncap))
+
+    def terminal_obs(self) -> np.ndarray:
+        return self.read(L.F_TERMINAL_OBS, np.float32, (self.num_envs, C.OBS_DIM + 2))
+
+    def last_stats(self) -> np.ndarray:
+        """get_statistics() 14-tuple of the last finished episode of every env (cyberbattle_env.py:517-524)."""
+        return self.read(L.F_LAST_STATS, np.float64, (self.num_envs, 14))
+
+    def reward64(self) -> np.ndarray:
+        return self.read(L.F_REWARD64, np.float64, (self.num_envs,))
+
+    def stat_accum(self) -> dict:
+        a = self.read(L.F_STAT_ACCUM, np.float64, (L.NUM_ACCUM,))
+        return dict(zip(L.ACCUM_NAMES, a.tolist()))
+
+    def stat_accum_tensor(self) -> torch.Tensor:
+        """Zero-copy float64[20] view of the device-side episode accumulators (input of the NCCL all-reduce)."""
+        ptr = self.lib.cbs_state_ptr(self._h, L.F_STAT_ACCUM)
+        return _tensor_from_ptr(ptr, (L.NUM_ACCUM,), torch.float64, self.device, self)
+
+    def reset_stat_accum(self):
+        self._check(self.lib.cbs_reset_stat_accum(self._h, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.cbs_launch_count(self._h))
+
+    @property
+    def state_bytes(self) -> int:
+        return int(self.lib.cbs_state_bytes(self._h))
+
+
+def _tensor_from_ptr(ptr, shape, dtype, device, owner):
+    """Wrap raw device memory as a torch tensor through the CUDA array interface."""
+    itemsize = torch.tensor([], dtype=dtype).element_size()
+    typestr = {torch.float64: "<f8", torch.float32: "<f4", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+
+    class _Holder:
+        pass
+    hld = _Holder()
+    hld.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2,
+                                        strides=None)
+    hld._owner = owner
+    t = torch.as_tensor(hld, device=device)
+    assert t.element_size() == itemsize
+    return t

@@ -1,0 +1,445 @@
+// cbs_api.cu — C ABI (include/cbsim.h): handle lifetime, table upload, kernel launches.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cbsim.h"
+#include "cbs_types.h"
+
+namespace cbs {
+cudaError_t launch_decode_gemm_simt(const float*, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_decode_gemm_tc(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+bool decode_gemm_tc_available();
+cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int32_t*, double*, cudaStream_t);
+cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, float*, int, cudaStream_t);
+cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, float*,
+                              uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
+
+__global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
+  const int flags = S.scal[(size_t)S_FLAGS * P.B + b];
+  int32_t* o = info + (size_t)b * CBS_INFO_INTS;
+  o[0] = sl.x; o[1] = sl.y; o[2] = sl.z; o[3] = sl.w;
+  o[4] = S.scal[(size_t)S_OUTCOME * P.B + b];
+  o[5] = (flags >> FL_REASON_SHIFT) & 3;
+  o[6] = S.scal[(size_t)S_STEPCOUNT * P.B + b];
+  o[7] = (flags & FL_TRUNC) ? 1 : 0;
+}
+
+__global__ void init_flags_kernel(int32_t* scal, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) scal[(size_t)S_FLAGS * B + b] = FL_NEEDS_RESET;
+}
+}  // namespace cbs
+
+using namespace cbs;
+
+static thread_local std::string g_create_error;
+
+struct cbs_handle {
+  cbs_config cfg{};
+  Params P{};
+  Tables T{};
+  State S{};
+  std::vector<void*> table_allocs, state_allocs;
+  std::string err;
+  bool loaded = false;
+  int Ug = 0, vt_stride = 0;
+  int64_t launches = 0;
+  bool use_tc = false;
+  float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
+  // host-step staging
+  cudaStream_t hstream = nullptr;
+  float *h_actions = nullptr, *h_uniforms = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+  uint8_t* h_done = nullptr;
+  int32_t* h_info = nullptr;
+  // io scratch for cbs_step
+  int32_t* d_sel = nullptr;
+  double* d_dist = nullptr;
+  size_t state_bytes = 0;
+};
+
+static int fail(cbs_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CK(h, expr)                                                                                     \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) return fail(h, CBS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+template <typename Tp>
+static int dalloc(cbs_handle* h, std::vector<void*>& pool, Tp** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(Tp);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(h, CBS_ERR_CUDA, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  if (zero) cudaMemset(p, 0, bytes);
+  pool.push_back(p);
+  h->state_bytes += bytes;
+  *out = static_cast<Tp*>(p);
+  return 0;
+}
+
+template <typename Tp>
+static int upload(cbs_handle* h, const Tp** out, const Tp* src, size_t count) {
+  Tp* p = nullptr;
+  int rc = dalloc(h, h->table_allocs, &p, count, false);
+  if (rc) return rc;
+  if (count) {
+    if (!src) return fail(h, CBS_ERR_INVALID_ARG, "null table pointer");
+    cudaError_t e = cudaMemcpy(p, src, count * sizeof(Tp), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return fail(h, CBS_ERR_CUDA, "table upload failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" {
+
+int cbs_abi_version(void) { return CBS_ABI_VERSION; }
+
+const char* cbs_last_error(const cbs_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cbs_create(const cbs_config* cfg, cbs_handle** out) {
+  if (!cfg || !out) return fail(nullptr, CBS_ERR_INVALID_ARG, "cbs_create: null argument");
+  if (cfg->abi_version != CBS_ABI_VERSION) return fail(nullptr, CBS_ERR_INVALID_ARG, "ABI version mismatch (%d vs %d)", cfg->abi_version, CBS_ABI_VERSION);
+  if (cfg->num_envs <= 0) return fail(nullptr, CBS_ERR_INVALID_ARG, "num_envs must be positive");
+  if (cfg->goal < 0 || cfg->goal > 2) return fail(nullptr, CBS_ERR_INVALID_ARG, "unsupported goal %d", cfg->goal);
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, CBS_ERR_NO_DEVICE, "no CUDA device available (libcbsim has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CBS_ERR_INVALID_ARG, "device %d out of range", cfg->device);
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e != cudaSuccess) return fail(nullptr, CBS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cbs_handle* h = new cbs_handle();
+  h->cfg = *cfg;
+  Params& P = h->P;
+  P.B = cfg->num_envs;
+  P.global_env_offset = cfg->global_env_offset;
+  P.seed = cfg->seed;
+  P.goal = cfg->goal;
+  P.episode_iterations = cfg->episode_iterations;
+  P.prop_coeff = cfg->proportional_cutoff_coefficient;
+  P.winning_reward = cfg->winning_reward;
+  P.losing_reward = cfg->losing_reward;
+  P.absolute_reward = cfg->absolute_reward;
+  P.stop_at_goal = cfg->stop_at_goal_reached;
+  P.remove_main = cfg->remove_main_obstacles;
+  P.remove_all = cfg->remove_all_obstacles;
+  P.switch_interval = cfg->switch_interval;
+  P.auto_reset = cfg->auto_reset;
+  for (int i = 0; i < N_REWARDS; ++i) P.rew[i] = cfg->rewards[i];
+  for (int i = 0; i < N_PENALTIES; ++i) P.pen[i] = cfg->penalties[i];
+  P.qlen = 0;
+  *out = h;
+  return CBS_OK;
+}
+
+void cbs_destroy(cbs_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  for (void* p : h->table_allocs) cudaFree(p);
+  for (void* p : h->state_allocs) cudaFree(p);
+  if (h->hstream) cudaStreamDestroy(h->hstream);
+  delete h;
+}
+
+int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_gae_tables* g) {
+  if (!h || !t || !g) return fail(h, CBS_ERR_INVALID_ARG, "cbs_load_scenarios: null argument");
+  if (h->loaded) return fail(h, CBS_ERR_INVALID_ARG, "scenarios already loaded (create a new handle)");
+  if (t->max_nodes < 1 || t->max_nodes > CBS_MAX_NODES) return fail(h, CBS_ERR_INVALID_ARG, "max_nodes %d out of range", t->max_nodes);
+  if (t->words != (t->max_nodes + 31) / 32) return fail(h, CBS_ERR_INVALID_ARG, "words does not match max_nodes");
+  CK(h, cudaSetDevice(h->cfg.device));
+  Tables& T = h->T;
+  Params& P = h->P;
+  const int S_ = t->num_scenarios, Nn = t->num_nodes_total, I = t->num_inst;
+  T.num_scenarios = S_; T.max_nodes = t->max_nodes; T.words = t->words; T.num_global_vulns = t->num_global_vulns;
+  int rc = 0;
+#define UP(field, count) if ((rc = upload(h, &T.field, t->field, (size_t)(count)))) return rc
+  UP(sc_num_nodes, S_); UP(sc_node_off, S_ + 1); UP(sc_port_off, S_ + 1); UP(sc_uvuln_off, S_ + 1); UP(sc_num_uvuln, S_);
+  UP(sc_instof_off, S_ + 1); UP(sc_discoverable_amount, S_);
+  UP(sc_init_has_data, (size_t)S_ * t->words); UP(sc_init_visible, (size_t)S_ * t->words);
+  UP(sc_feasible_off, S_ + 1); UP(feasible_starters, t->num_feasible);
+  UP(nd_value, Nn); UP(nd_level_at_access, Nn); UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
+  UP(nd_row_off, 2 * (size_t)Nn + 1); UP(outblock, (size_t)t->num_ports_total * t->words);
+  UP(uvuln_global, t->num_uvuln_total); UP(inst_of, t->num_instof);
+  UP(vi_port, I); UP(vi_flags, I); UP(vi_kinds_any, I); UP(vi_kinds_remote, I); UP(vi_success, I); UP(vi_cost, I);
+  UP(vi_recon_any, 2 * (size_t)I); UP(vi_recon_remote, 2 * (size_t)I); UP(vi_ulocal, I); UP(recon_nodes, t->num_recon);
+  UP(row_packed, t->num_rows); UP(row_inst, t->num_rows);
+  UP(vemb32, (size_t)t->num_global_vulns * VULN_EMB); UP(vemb64, (size_t)t->num_global_vulns * VULN_EMB);
+  UP(vnorm2, t->num_global_vulns);
+#undef UP
+#define UPG(field, count) if ((rc = upload(h, &T.field, g->field, (size_t)(count)))) return rc
+  UPG(node_static, (size_t)Nn * 2 * PROJ_ROWS * NODE_EMB); UPG(dyn_proj, NUM_DYN * PROJ_ROWS * NODE_EMB);
+  UPG(vuln_h, (size_t)t->num_global_vulns * NN_CH); UPG(nn0_b, NN_CH); UPG(bn1_scale, NODE_EMB); UPG(bn1_shift, NODE_EMB);
+  UPG(gcn_wt, NODE_EMB * NODE_EMB); UPG(bn2_scale, NODE_EMB); UPG(bn2_shift, NODE_EMB);
+#undef UPG
+
+  // capacities
+  P.ncap = ((t->max_nodes + 3) / 4) * 4;
+  P.words = t->words;
+  int max_steps = h->cfg.episode_iterations;
+  if (P.prop_coeff > 0) {
+    const double lim = (double)(t->max_nodes - 1) * P.prop_coeff;
+    const int l = (int)lim + ((double)(int)lim < lim ? 1 : 0);
+    if (l < max_steps) max_steps = l;
+  }
+  max_steps += 1;   // the cut-offs test the pre-increment counter (cyberbattle_env.py:361-366, :394)
+  int slots = 2 * t->max_nodes - 1;
+  if (max_steps + 1 < slots) slots = max_steps + 1;
+  if (slots > 255) slots = 255;
+  P.slots = h->cfg.max_slots > 0 ? h->cfg.max_slots : slots;
+  if (P.slots > 255) return fail(h, CBS_ERR_INVALID_ARG, "max_slots must be <= 255");
+  int ecap = t->max_nodes * t->max_nodes;
+  if (max_steps < ecap) ecap = max_steps;
+  P.ecap = h->cfg.max_edges > 0 ? h->cfg.max_edges : ecap;
+  h->Ug = t->num_global_vulns;
+  h->vt_stride = ((h->Ug + 63) / 64) * 64;
+  h->use_tc = (h->cfg.decode_gemm == 0) && decode_gemm_tc_available();
+  P.margin = h->cfg.decode_margin > 0 ? h->cfg.decode_margin : (h->use_tc ? 4e-4f : 2e-5f);
+
+  State& S = h->S;
+  const size_t B = P.B;
+  h->state_bytes = 0;
+#define AL(field, count) if ((rc = dalloc(h, h->state_allocs, &S.field, (size_t)(count)))) return rc
+  AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
+  AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
+  AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
+  AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
+  AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
+  AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
+  AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 1);
+  if (P.ncap > 32) { AL(scratch, B * 2 * P.ncap * NODE_EMB); }
+#undef AL
+  if ((rc = dalloc(h, h->state_allocs, &h->d_sel, B * 4))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->d_dist, B))) return rc;
+  if (h->use_tc && (rc = dalloc(h, h->state_allocs, &h->a_packed, B * VULN_EMB))) return rc;
+  init_flags_kernel<<<(P.B + 255) / 256, 256>>>(S.scal, P.B);
+  CK(h, cudaGetLastError());
+  CK(h, cudaDeviceSynchronize());
+  h->loaded = true;
+  return CBS_OK;
+}
+
+int cbs_set_scenarios(cbs_handle* h, const int32_t* sc_host) {
+  if (!h || !sc_host) return fail(h, CBS_ERR_INVALID_ARG, "cbs_set_scenarios: null argument");
+  if (!h->loaded) return fail(h, CBS_ERR_NOT_READY, "load scenarios first");
+  for (int b = 0; b < h->P.B; ++b)
+    if (sc_host[b] < 0 || sc_host[b] >= h->T.num_scenarios) return fail(h, CBS_ERR_INVALID_ARG, "scenario id %d out of range (env %d)", sc_host[b], b);
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaMemcpy(h->S.scal + (size_t)S_SCENARIO * h->P.B, sc_host, sizeof(int32_t) * h->P.B, cudaMemcpyHostToDevice));
+  return CBS_OK;
+}
+
+int cbs_set_starter_queue(cbs_handle* h, const int32_t* q, int32_t qlen) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  if (!h->loaded) return fail(h, CBS_ERR_NOT_READY, "load scenarios first");
+  CK(h, cudaSetDevice(h->cfg.device));
+  CK(h, cudaDeviceSynchronize());
+  if (!q || qlen <= 0) { h->S.starter_queue = nullptr; h->P.qlen = 0; return CBS_OK; }
+  int32_t* d = nullptr;
+  int rc = dalloc(h, h->state_allocs, &d, (size_t)h->P.B * qlen, false);
+  if (rc) return rc;
+  CK(h, cudaMemcpy(d, q, sizeof(int32_t) * (size_t)h->P.B * qlen, cudaMemcpyHostToDevice));
+  h->S.starter_queue = d;
+  h->P.qlen = qlen;
+  return CBS_OK;
+}
+
+int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double prop) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  h->P.episode_iterations = episode_iterations;
+  h->P.prop_coeff = prop;
+  return CBS_OK;
+}
+
+static int check_ready(cbs_handle* h) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  if (!h->loaded) return fail(h, CBS_ERR_NOT_READY, "scenarios not loaded");
+  cudaError_t e = cudaSetDevice(h->cfg.device);
+  if (e != cudaSuccess) return fail(h, CBS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CK(h, launch_observe(h->T, h->P, h->S, env_mask_dev, obs_dev, 1, (cudaStream_t)stream));
+  h->launches += 1;
+  return CBS_OK;
+}
+
+int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double* dist_dev, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_decode: actions is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (h->use_tc) {
+    CK(h, launch_decode_gemm_tc(actions_dev, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    h->launches += 2;
+  } else {
+    CK(h, launch_decode_gemm_simt(actions_dev, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    h->launches += 1;
+  }
+  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, sel_dev, dist_dev, st));
+  h->launches += 1;
+  return CBS_OK;
+}
+
+int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev, const float* uniforms_dev, float* reward_dev,
+                   uint8_t* done_dev, uint8_t* truncated_dev, uint8_t* outcome_dev, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!sel_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_transition: sel is null");
+  CK(h, launch_transition(h->T, h->P, h->S, sel_dev, dist_dev, uniforms_dev, reward_dev, done_dev, truncated_dev, outcome_dev,
+                          (cudaStream_t)stream));
+  h->launches += 1;
+  return CBS_OK;
+}
+
+int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CK(h, launch_observe(h->T, h->P, h->S, nullptr, obs_dev, 0, (cudaStream_t)stream));
+  h->launches += 1;
+  return CBS_OK;
+}
+
+int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* obs_dev, float* reward_dev,
+             uint8_t* done_dev, int32_t* info_dev, uintptr_t stream) {
+  int rc = cbs_decode(h, actions_dev, h ? h->d_sel : nullptr, h ? h->d_dist : nullptr, stream);
+  if (rc) return rc;
+  rc = cbs_transition(h, h->d_sel, h->d_dist, uniforms_dev, reward_dev, done_dev, nullptr, nullptr, stream);
+  if (rc) return rc;
+  if (info_dev) {   // before observe: an auto-reset clears the per-step flags
+    info_kernel<<<(h->P.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, info_dev);
+    CK(h, cudaGetLastError());
+    h->launches += 1;
+  }
+  return cbs_observe(h, obs_dev, stream);
+}
+
+static int ensure_host_staging(cbs_handle* h) {
+  if (h->hstream) return 0;
+  const size_t B = h->P.B;
+  int rc;
+  CK(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  if ((rc = dalloc(h, h->state_allocs, &h->h_actions, B * ACTION_DIM, false))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->h_uniforms, B, false))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->h_obs, B * OBS_DIM, false))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->h_reward, B, false))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->h_done, B, false))) return rc;
+  if ((rc = dalloc(h, h->state_allocs, &h->h_info, B * CBS_INFO_INTS, false))) return rc;
+  return 0;
+}
+
+int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host, float* reward_host,
+                  uint8_t* done_host, int32_t* info_host) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!actions_host) return fail(h, CBS_ERR_INVALID_ARG, "cbs_step_host: actions is null");
+  if ((rc = ensure_host_staging(h))) return rc;
+  const size_t B = h->P.B;
+  cudaStream_t st = h->hstream;
+  CK(h, cudaMemcpyAsync(h->h_actions, actions_host, B * ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (uniforms_host) CK(h, cudaMemcpyAsync(h->h_uniforms, uniforms_host, B * sizeof(float), cudaMemcpyHostToDevice, st));
+  rc = cbs_step(h, h->h_actions, uniforms_host ? h->h_uniforms : nullptr, h->h_obs, h->h_reward, h->h_done,
+                info_host ? h->h_info : nullptr, (uintptr_t)st);
+  if (rc) return rc;
+  if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->h_obs, B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (done_host) CK(h, cudaMemcpyAsync(done_host, h->h_done, B, cudaMemcpyDeviceToHost, st));
+  if (info_host) CK(h, cudaMemcpyAsync(info_host, h->h_info, B * CBS_INFO_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaStreamSynchronize(st));
+  return CBS_OK;
+}
+
+static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
+  const Params& P = h->P;
+  const State& S = h->S;
+  const int64_t B = P.B;
+  switch (field) {
+    case CBS_F_MASKS: *p = S.masks; *bytes = (int64_t)N_MASKS * P.words * B * 4; break;
+    case CBS_F_DISC_ORDER: *p = S.disc_order; *bytes = B * P.ncap; break;
+    case CBS_F_OWNED_ORDER: *p = S.owned_order; *bytes = B * P.ncap; break;
+    case CBS_F_SCALARS: *p = S.scal; *bytes = (int64_t)N_SCALARS * B * 4; break;
+    case CBS_F_TERMINAL_OBS: *p = S.term_obs; *bytes = B * OBS_DIM * 4; break;
+    case CBS_F_OBS: *p = S.obs; *bytes = B * OBS_DIM * 4; break;
+    case CBS_F_LAST_STATS: *p = S.last_stats; *bytes = B * 14 * 8; break;
+    case CBS_F_STAT_ACCUM: *p = S.accum; *bytes = N_ACCUM * 8; break;
+    case CBS_F_PAIR_SLOT: *p = S.pair_slot; *bytes = B * P.ncap * P.ncap; break;
+    case CBS_F_DIST: *p = S.dist; *bytes = B * 8; break;
+    case CBS_F_REWARD64: *p = S.reward64; *bytes = B * 8; break;
+    case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
+    default: return fail(h, CBS_ERR_INVALID_ARG, "unknown state field %d", field);
+  }
+  return 0;
+}
+
+int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  void* p = nullptr;
+  int64_t n = 0;
+  if ((rc = field_ptr(h, field, &p, &n))) return rc;
+  if (!dst_host) return n;
+  if (bytes != n) return fail(h, CBS_ERR_INVALID_ARG, "field %d holds %lld bytes, caller passed %lld", field, (long long)n, (long long)bytes);
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(dst_host, p, (size_t)n, cudaMemcpyDeviceToHost));
+  return n;
+}
+
+void* cbs_state_ptr(cbs_handle* h, int32_t field) {
+  if (!h || !h->loaded) return nullptr;
+  void* p = nullptr;
+  int64_t n = 0;
+  if (field_ptr(h, field, &p, &n)) return nullptr;
+  return p;
+}
+
+int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CK(h, cudaMemsetAsync(h->S.accum, 0, N_ACCUM * sizeof(double), (cudaStream_t)stream));
+  return CBS_OK;
+}
+
+int64_t cbs_launch_count(const cbs_handle* h) { return h ? h->launches : 0; }
+
+int cbs_sync(cbs_handle* h) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  CK(h, cudaDeviceSynchronize());
+  int flag = 0;
+  CK(h, cudaMemcpy(&flag, h->S.errflag, 4, cudaMemcpyDeviceToHost));
+  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table)", flag);
+  return CBS_OK;
+}
+
+int cbs_struct_sizes(int32_t* out3) {
+  if (!out3) return CBS_ERR_INVALID_ARG;
+  out3[0] = (int32_t)sizeof(cbs_config); out3[1] = (int32_t)sizeof(cbs_scenario_tables); out3[2] = (int32_t)sizeof(cbs_gae_tables);
+  return CBS_OK;
+}
+
+int64_t cbs_state_bytes(const cbs_handle* h) { return h ? (int64_t)h->state_bytes : 0; }
+int cbs_capacities(const cbs_handle* h, int32_t* out4) {
+  if (!h || !out4) return CBS_ERR_INVALID_ARG;
+  out4[0] = h->P.ncap; out4[1] = h->P.slots; out4[2] = h->P.ecap; out4[3] = h->use_tc ? 1 : 0;
+  return CBS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,48 @@
+// cbs_device.cuh — small device helpers shared by the kernels.
+#pragma once
+#include "cbs_types.h"
+
+namespace cbs {
+
+__device__ __forceinline__ uint32_t ld_mask(const State& S, const Params& P, int plane, int w, int b) {
+  return S.masks[((size_t)plane * P.words + w) * P.B + b];
+}
+__device__ __forceinline__ bool bit_of(const State& S, const Params& P, int plane, int node, int b) {
+  return (ld_mask(S, P, plane, node >> 5, b) >> (node & 31)) & 1u;
+}
+__device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int plane, int b) {
+  return S.scal[(size_t)plane * P.B + b];
+}
+
+// attacker_goal_reached (cyberbattle_env.py:467-487) for the three network-wide goals, on mask words
+__device__ inline bool goal_reached(const State& S, const Params& P, int b) {
+  const int starter = scalar(S, P, S_STARTER, b);
+  int n_goal = 0, n_data = 0, n_pending = 0;
+  for (int w = 0; w < P.words; ++w) {
+    const uint32_t disc = ld_mask(S, P, M_DISCOVERED, w, b);
+    const uint32_t not_starter = ((starter >> 5) == w) ? ~(1u << (starter & 31)) : 0xFFFFFFFFu;
+    if (P.goal == GOAL_CONTROL) n_goal += __popc(ld_mask(S, P, M_OWNED, w, b) & ld_mask(S, P, M_PRIV_ROOT, w, b) & not_starter);
+    else if (P.goal == GOAL_DISRUPTION) n_goal += __popc(disc & ld_mask(S, P, M_STOPPED, w, b) & not_starter);
+    else {
+      n_goal += __popc(disc & not_starter);
+      n_data += __popc(disc & ld_mask(S, P, M_HAS_DATA, w, b));
+      n_pending += __popc(disc & ld_mask(S, P, M_COLLECTED, w, b) & ~ld_mask(S, P, M_EXFILTRATED, w, b));
+    }
+  }
+  if (P.goal == GOAL_CONTROL) return n_goal == scalar(S, P, S_OWNABLE, b);
+  if (P.goal == GOAL_DISRUPTION) return n_goal == scalar(S, P, S_DISRUPTABLE, b);
+  return n_goal == scalar(S, P, S_DISCOVERABLE, b) && n_data == 0 && n_pending == 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+}  // namespace cbs

@@ -55,7 +55,7 @@ struct Tables {  // immutable, device pointers
   const int32_t *nd_value, *nd_ownable, *nd_discoverable, *nd_disruptable, *nd_row_off;
   const uint8_t* nd_level_at_access;
   const uint32_t* outblock;
-  const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst;
+  const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst, *uvuln_global;
   const uint32_t *vi_flags, *row_packed;
   const uint16_t *vi_kinds_any, *vi_kinds_remote;
   const double *vi_success, *vi_cost, *vemb64, *vnorm2;

@@ -1,0 +1,455 @@
+// k_observe.cu — evolving visible graph, graph auto-encoder forward, action-table maintenance and reset.
+//
+// One warp per env.  Follows CyberBattleCompressedEnv.step after the inner transition
+// (_env/cyberbattle_env_compressed.py:399-428): update_evolving_visible_graph_after_step (:465-484),
+// add_edge_evolving_visible_graph (:214-246), encode (:249-306) with GAEEncoder.forward (gae/model.py:70-82),
+// create_continuous_action_space (:487-523), and reset (:158-189 + _env/cyberbattle_env.py:134-186).
+//
+// The 1576-wide node feature vector is never materialised: ccbs_b200.gae.fold_gae pre-multiplies the static
+// part of every scenario node with the NNConv edge-network output basis (17 x 64 per node) and the root
+// weight (64 per node); here only the `visible` gate and six dynamic scalars are applied.  Per edge the
+// message is a 17-term combination of those rows with [ReLU(W1 e + b1); 1].  GCNConv is a 64x64 projection
+// (weights staged once per CTA in shared memory) followed by the degree-normalised neighbour sum.  Node
+// embeddings of one env live in shared memory (<= 32 nodes) or in an L2-resident scratch slab (<= 128 nodes).
+#include "cbs_device.cuh"
+#include "philox.cuh"
+
+namespace cbs {
+
+constexpr int OBS_WARPS = 4;
+constexpr int SMEM_NODES = 32;
+
+struct SharedWeights {
+  float gcn[NODE_EMB * NODE_EMB];               // [in][out]
+  float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]
+  float bn1s[NODE_EMB], bn1h[NODE_EMB], bn2s[NODE_EMB], bn2h[NODE_EMB];
+  float nn0b[NN_CH];
+};
+
+struct WarpScratch {
+  float* y;           // [n][64]
+  float* g;           // [n][64]
+  float* dinv;        // [ncap]
+  uint8_t* pos;       // [MAX_NODES] node id -> position in discovered order
+};
+
+__device__ __forceinline__ void node_dyn(const State& S, const Params& P, int b, int node, float& vis, float x[NUM_DYN]) {
+  vis = bit_of(S, P, M_VISIBLE, node, b) ? 1.f : 0.f;
+  x[0] = bit_of(S, P, M_PERSISTENCE, node, b) ? 1.f : 0.f;
+  x[1] = bit_of(S, P, M_COLLECTED, node, b) ? 1.f : 0.f;
+  x[2] = bit_of(S, P, M_EXFILTRATED, node, b) ? 1.f : 0.f;
+  x[3] = bit_of(S, P, M_EVASION, node, b) ? 1.f : 0.f;
+  x[4] = bit_of(S, P, M_PRIV_ROOT, node, b) ? 3.f : (bit_of(S, P, M_PRIV_USER, node, b) ? 1.f : 0.f);
+  x[5] = bit_of(S, P, M_STOPPED, node, b) ? 0.f : 1.f;    // MachineStatus value: Stopped 0, Running 1
+}
+
+// ---- add_edge_evolving_visible_graph (compressed:214-246), mean aggregation, in the W1-projected space ----
+__device__ void edge_update(const Tables& T, const Params& P, const State& S, int b, int lane) {
+  const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
+  const int s = sl.x, t = sl.y, u = sl.z;
+  const int sc = scalar(S, P, S_SCENARIO, b);
+  const int gv = T.uvuln_global[T.sc_uvuln_off[sc] + u];
+  const float p = lane < NN_CH ? T.vuln_h[(size_t)gv * NN_CH + lane] : 0.f;
+  int E = scalar(S, P, S_N_EDGES, b);
+  uint8_t* es = S.edge_src + (size_t)b * P.ecap;
+  uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
+  int32_t* ec = S.edge_cnt + (size_t)b * P.ecap;
+  int found = -1;
+  for (int base = 0; base < E; base += 32) {
+    const int e = base + lane;
+    const bool hit = e < E && es[e] == s && ed[e] == t;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+    if (m) { found = base + __ffs(m) - 1; break; }
+  }
+  if (found >= 0) {
+    const int cnt = ec[found];
+    float* sum = S.edge_sum + ((size_t)b * P.ecap + found) * NN_CH;
+    if (lane < NN_CH) {
+      const float v = (cnt == 0 ? 0.f : sum[lane]) + p;   // :226-228 (a wiped accumulator restarts)
+      sum[lane] = v;
+      S.edge_m[((size_t)b * P.ecap + found) * NN_CH + lane] = v / (float)(cnt + 1);
+    }
+    __syncwarp();
+    if (lane == 0) ec[found] = cnt + 1;
+  } else {
+    if (E >= P.ecap) { if (lane == 0) atomicExch(S.errflag, 2); return; }
+    for (int base = 0; base < E; base += 32) {             // :237 wipes every accumulator of this source
+      const int e = base + lane;
+      if (e < E && es[e] == s) ec[e] = 0;
+    }
+    if (lane < NN_CH) {
+      S.edge_sum[((size_t)b * P.ecap + E) * NN_CH + lane] = p;
+      S.edge_m[((size_t)b * P.ecap + E) * NN_CH + lane] = p;
+    }
+    if (lane == 0) { es[E] = (uint8_t)s; ed[E] = (uint8_t)t; ec[E] = 1; scalar(S, P, S_N_EDGES, b) = E + 1; }
+  }
+  __syncwarp();
+}
+
+// ---- encode (compressed:249-306) : returns node embeddings z in W.y (position-major) and writes S.obs ----
+__device__ void encode_env(const Tables& T, const Params& P, const State& S, const SharedWeights& SW, WarpScratch& W, int b,
+                           int lane) {
+  const int sc = scalar(S, P, S_SCENARIO, b);
+  const int node_off = T.sc_node_off[sc];
+  const int n = scalar(S, P, S_N_DISC, b);
+  const int E = scalar(S, P, S_N_EDGES, b);
+  const uint8_t* order = S.disc_order + (size_t)b * P.ncap;
+  const int c0 = lane, c1 = lane + 32;
+  constexpr int ROW = PROJ_ROWS * NODE_EMB;   // floats per (node, part)
+
+  for (int i = lane; i < n; i += 32) { W.pos[order[i]] = (uint8_t)i; W.dinv[i] = 1.f; }
+  __syncwarp();
+
+  // root term x_i W_root (+ conv bias folded into bn1 shift)
+  for (int i = 0; i < n; ++i) {
+    const int node = order[i];
+    float vis, x[NUM_DYN];
+    node_dyn(S, P, b, node, vis, x);
+    const float* ns = T.node_static + (size_t)(node_off + node) * 2 * ROW + 17 * NODE_EMB;
+    float a0 = ns[c0] + vis * ns[ROW + c0], a1 = ns[c1] + vis * ns[ROW + c1];
+#pragma unroll
+    for (int d = 0; d < NUM_DYN; ++d) {
+      a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
+      a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
+    }
+    W.y[i * NODE_EMB + c0] = a0;
+    W.y[i * NODE_EMB + c1] = a1;
+  }
+  __syncwarp();
+
+  // NNConv messages: y[dst] += [relu(m_e + b1); 1] . T_src
+  const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
+  const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
+  for (int e = 0; e < E; ++e) {
+    const int js = es[e], jd = ed[e];
+    const int is = W.pos[js], id = W.pos[jd];
+    float hl = 0.f;
+    if (lane < NN_CH) hl = fmaxf(S.edge_m[((size_t)b * P.ecap + e) * NN_CH + lane] + SW.nn0b[lane], 0.f);
+    else if (lane == NN_CH) hl = 1.f;
+    float vis, x[NUM_DYN];
+    node_dyn(S, P, b, js, vis, x);
+    const float* ns = T.node_static + (size_t)(node_off + js) * 2 * ROW;
+    float m0 = 0.f, m1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NN_CH + 1; ++k) {
+      const float hk = __shfl_sync(0xFFFFFFFFu, hl, k);
+      float t0 = ns[k * NODE_EMB + c0] + vis * ns[ROW + k * NODE_EMB + c0];
+      float t1 = ns[k * NODE_EMB + c1] + vis * ns[ROW + k * NODE_EMB + c1];
+#pragma unroll
+      for (int d = 0; d < NUM_DYN; ++d) {
+        t0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c0], t0);
+        t1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c1], t1);
+      }
+      m0 = fmaf(hk, t0, m0);
+      m1 = fmaf(hk, t1, m1);
+    }
+    W.y[id * NODE_EMB + c0] += m0;
+    W.y[id * NODE_EMB + c1] += m1;
+    if (lane == 0 && is != id) W.dinv[id] += 1.f;           // GCN in-degree (self loops are replaced, not counted)
+    __syncwarp();
+  }
+  for (int i = lane; i < n; i += 32) W.dinv[i] = rsqrtf(W.dinv[i]);
+  // BatchNorm(eval) + ReLU, then the GCN projection G = H1 Wg^T
+  for (int i = 0; i < n; ++i) {
+    W.y[i * NODE_EMB + c0] = fmaxf(fmaf(W.y[i * NODE_EMB + c0], SW.bn1s[c0], SW.bn1h[c0]), 0.f);
+    W.y[i * NODE_EMB + c1] = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn1s[c1], SW.bn1h[c1]), 0.f);
+  }
+  __syncwarp();
+  for (int i = 0; i < n; ++i) {
+    float g0 = 0.f, g1 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < NODE_EMB; ++k) {
+      const float h = W.y[i * NODE_EMB + k];
+      g0 = fmaf(h, SW.gcn[k * NODE_EMB + c0], g0);
+      g1 = fmaf(h, SW.gcn[k * NODE_EMB + c1], g1);
+    }
+    W.g[i * NODE_EMB + c0] = g0;
+    W.g[i * NODE_EMB + c1] = g1;
+  }
+  __syncwarp();
+  // normalised aggregation, edges first and the self loop last (the order PyG's add_remaining_self_loops +
+  // scatter-add gives).  Products and sums are rounded separately (no FMA contraction): a pair of nodes that
+  // attack each other then gets bit-identical embeddings, exactly as in the reference, and the exact ties this
+  // creates in the action table resolve by insertion order instead of by rounding noise.
+  for (int i = 0; i < n; ++i) {
+    W.y[i * NODE_EMB + c0] = 0.f;
+    W.y[i * NODE_EMB + c1] = 0.f;
+  }
+  __syncwarp();
+  for (int e = 0; e < E; ++e) {
+    const int is = W.pos[es[e]], id = W.pos[ed[e]];
+    if (is == id) continue;
+    const float w = __fmul_rn(W.dinv[is], W.dinv[id]);
+    W.y[id * NODE_EMB + c0] = __fadd_rn(W.y[id * NODE_EMB + c0], __fmul_rn(w, W.g[is * NODE_EMB + c0]));
+    W.y[id * NODE_EMB + c1] = __fadd_rn(W.y[id * NODE_EMB + c1], __fmul_rn(w, W.g[is * NODE_EMB + c1]));
+    __syncwarp();
+  }
+  for (int i = 0; i < n; ++i) {
+    const float d2 = __fmul_rn(W.dinv[i], W.dinv[i]);
+    W.y[i * NODE_EMB + c0] = __fadd_rn(W.y[i * NODE_EMB + c0], __fmul_rn(d2, W.g[i * NODE_EMB + c0]));
+    W.y[i * NODE_EMB + c1] = __fadd_rn(W.y[i * NODE_EMB + c1], __fmul_rn(d2, W.g[i * NODE_EMB + c1]));
+  }
+  __syncwarp();
+  // BatchNorm + ReLU -> z ; readout over Running nodes (mean | max | min), compressed:266-298
+  float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY;
+  int running = 0;
+  for (int i = 0; i < n; ++i) {
+    const float z0 = fmaxf(fmaf(W.y[i * NODE_EMB + c0], SW.bn2s[c0], SW.bn2h[c0]), 0.f);
+    const float z1 = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn2s[c1], SW.bn2h[c1]), 0.f);
+    W.y[i * NODE_EMB + c0] = z0;
+    W.y[i * NODE_EMB + c1] = z1;
+    if (!bit_of(S, P, M_STOPPED, order[i], b)) {
+      ++running;
+      s0 += z0; s1 += z1;
+      mx0 = fmaxf(mx0, z0); mx1 = fmaxf(mx1, z1);
+      mn0 = fminf(mn0, z0); mn1 = fminf(mn1, z1);
+    }
+  }
+  float* obs = S.obs + (size_t)b * OBS_DIM;
+  if (running == 0) { s0 = s1 = mx0 = mx1 = mn0 = mn1 = 0.f; running = 1; }
+  obs[c0] = s0 / (float)running;
+  obs[c1] = s1 / (float)running;
+  obs[NODE_EMB + c0] = mx0;
+  obs[NODE_EMB + c1] = mx1;
+  obs[2 * NODE_EMB + c0] = mn0;
+  obs[2 * NODE_EMB + c1] = mn1;
+  if (lane == 0) {
+    obs[OBS_GRAPH] = (float)n;                              // create_discrete_features, compressed:309-316
+    obs[OBS_GRAPH + 1] = (float)scalar(S, P, S_N_OWNED, b);
+    scalar(S, P, S_N_ENCODES, b) += 1;
+  }
+  __syncwarp();
+}
+
+// ---- create_continuous_action_space (compressed:487-523): new (source,target) pairs freeze the embeddings
+//      of THIS encode; they are stored once per table-growing encode in a snapshot slot ----
+__device__ void build_table(const Params& P, const State& S, WarpScratch& W, int b, int lane) {
+  const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, S_N_OWNED, b);
+  const uint8_t* dorder = S.disc_order + (size_t)b * P.ncap;
+  const uint8_t* oorder = S.owned_order + (size_t)b * P.ncap;
+  uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
+  const int slot = scalar(S, P, S_N_SLOTS, b);
+  bool any_new = false;
+  for (int op = 0; op < n_owned; ++op) {
+    const int s = oorder[op];
+    if (bit_of(S, P, M_STOPPED, s, b)) continue;
+    for (int base = 0; base < n_disc; base += 32) {
+      const int dp = base + lane;
+      bool fresh = false;
+      if (dp < n_disc) {
+        const int t = dorder[dp];
+        fresh = !bit_of(S, P, M_STOPPED, t, b) && ps[s * P.ncap + t] == 0xFF;
+        if (fresh && slot < P.slots) ps[s * P.ncap + t] = (uint8_t)slot;
+      }
+      any_new |= __any_sync(0xFFFFFFFFu, fresh);
+    }
+  }
+  if (!any_new) return;
+  if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
+  float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
+  float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
+  for (int i = 0; i < n_disc; ++i) {
+    const int node = dorder[i];
+    const float z0 = W.y[i * NODE_EMB + lane], z1 = W.y[i * NODE_EMB + lane + 32];
+    zh[node * NODE_EMB + lane] = z0;
+    zh[node * NODE_EMB + lane + 32] = z1;
+    const float n2 = warp_sum(z0 * z0 + z1 * z1);
+    if (lane == 0) zn[node] = n2;
+  }
+  if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
+  __syncwarp();
+}
+
+// ---- get_statistics (cyberbattle_env.py:517-524) + episode accumulators ----
+__device__ void finish_episode(const Tables& T, const Params& P, const State& S, int b, int lane) {
+  const int sc = scalar(S, P, S_SCENARIO, b);
+  const int N = T.sc_num_nodes[sc];
+  int owned = 0, disrupted = 0, running = 0;
+  for (int w = 0; w < P.words; ++w) {
+    const uint32_t disc = ld_mask(S, P, M_DISCOVERED, w, b), stop = ld_mask(S, P, M_STOPPED, w, b);
+    owned += __popc(ld_mask(S, P, M_OWNED, w, b));
+    disrupted += __popc(disc & stop);
+    running += __popc(disc & ~stop);
+  }
+  const int n_disc = scalar(S, P, S_N_DISC, b);
+  const int flags = scalar(S, P, S_FLAGS, b);
+  const int reason = (flags >> FL_REASON_SHIFT) & 3;
+  double st[14];
+  st[0] = owned; st[1] = n_disc; st[2] = N - n_disc; st[3] = disrupted; st[4] = N;
+  st[5] = scalar(S, P, S_OWNABLE, b); st[6] = scalar(S, P, S_DISCOVERABLE, b); st[7] = scalar(S, P, S_DISRUPTABLE, b);
+  st[8] = (double)running / (double)n_disc; st[9] = 0; st[10] = 0;
+  st[11] = scalar(S, P, S_DISC_AMOUNT, b); st[12] = scalar(S, P, S_DISCOVERABLE_AMOUNT, b);
+  st[13] = goal_reached(S, P, b) ? 1.0 : 0.0;
+  double v = 0.0;
+  if (lane < 14) {
+#pragma unroll
+    for (int i = 0; i < 14; ++i) if (i == lane) v = st[i];
+    S.last_stats[(size_t)b * 14 + lane] = v;
+    atomicAdd(&S.accum[A_STAT0 + lane], v);
+  } else if (lane == 14) atomicAdd(&S.accum[A_EPISODES], 1.0);
+  else if (lane == 15) atomicAdd(&S.accum[A_RETURN], S.ep_return[b]);
+  else if (lane == 16) atomicAdd(&S.accum[A_LENGTH], (double)scalar(S, P, S_STEPCOUNT, b));
+  else if (lane == 17 && reason >= 1) atomicAdd(&S.accum[A_WINS + reason - 1], 1.0);
+  for (int i = lane; i < OBS_DIM; i += 32) S.term_obs[(size_t)b * OBS_DIM + i] = S.obs[(size_t)b * OBS_DIM + i];
+  __syncwarp();
+  if (lane == 0) scalar(S, P, S_EPISODES, b) += 1;
+  __syncwarp();
+}
+
+// ---- reset (cyberbattle_env.py:134-186,189-296 ; compressed:158-189 ; switch.py:151-167,218-220) ----
+__device__ void reset_env(const Tables& T, const Params& P, const State& S, int b, int lane) {
+  const uint64_t genv = (uint64_t)(P.global_env_offset + b);
+  const int episodes = scalar(S, P, S_EPISODES, b);
+  int sc = scalar(S, P, S_SCENARIO, b);
+  if (P.switch_interval > 0 && episodes > 0 && (episodes + 1) % (P.switch_interval + 1) == 0) {   // _check_switch
+    const Philox4 r = philox4x32_10(P.seed, genv, (uint32_t)episodes, 2u);
+    sc = (int)(((uint64_t)r.x * (uint64_t)T.num_scenarios) >> 32);
+  }
+  int starter;
+  if (S.starter_queue) starter = S.starter_queue[(size_t)b * P.qlen + (episodes % P.qlen)];
+  else {
+    const int f0 = T.sc_feasible_off[sc], f1 = T.sc_feasible_off[sc + 1];
+    const Philox4 r = philox4x32_10(P.seed, genv, (uint32_t)episodes, 1u);
+    starter = (f1 > f0) ? T.feasible_starters[f0 + (int)(((uint64_t)r.x * (uint64_t)(f1 - f0)) >> 32)] : 0;
+  }
+  const int g = T.sc_node_off[sc] + starter;
+  const int laa = T.nd_level_at_access[g];
+  const uint32_t sbit = 1u << (starter & 31);
+  const int sw = starter >> 5;
+  for (int i = lane; i < N_MASKS * P.words; i += 32) {
+    const int plane = i / P.words, w = i % P.words;
+    uint32_t v = 0;
+    if (plane == M_HAS_DATA) v = T.sc_init_has_data[sc * P.words + w];
+    else if (plane == M_VISIBLE) v = T.sc_init_visible[sc * P.words + w];
+    else if (w == sw && (plane == M_OWNED || plane == M_DISCOVERED || (plane == M_PRIV_USER && laa >= 1) ||
+                         (plane == M_PRIV_ROOT && laa == 3))) v = sbit;
+    S.masks[((size_t)plane * P.words + w) * P.B + b] = v;
+  }
+  uint32_t* ps = reinterpret_cast<uint32_t*>(S.pair_slot + (size_t)b * P.ncap * P.ncap);
+  for (int i = lane; i < P.ncap * P.ncap / 4; i += 32) ps[i] = 0xFFFFFFFFu;
+  if (lane == 0) {
+    scalar(S, P, S_SCENARIO, b) = sc;
+    scalar(S, P, S_STARTER, b) = starter;
+    scalar(S, P, S_STEPCOUNT, b) = 0;
+    scalar(S, P, S_NUM_ITER, b) = 0;
+    scalar(S, P, S_N_DISC, b) = 1;
+    scalar(S, P, S_N_OWNED, b) = 1;
+    scalar(S, P, S_DISC_AMOUNT, b) = 0;
+    const int own = T.nd_ownable[g], dis = T.nd_discoverable[g], dsr = T.nd_disruptable[g];
+    scalar(S, P, S_OWNABLE, b) = own;
+    scalar(S, P, S_DISCOVERABLE, b) = dis;
+    scalar(S, P, S_DISRUPTABLE, b) = dsr;
+    scalar(S, P, S_PROP_NODES, b) = P.goal == GOAL_CONTROL ? own : (P.goal == GOAL_DISCOVERY ? dis : dsr);
+    scalar(S, P, S_DISCOVERABLE_AMOUNT, b) = T.sc_discoverable_amount[sc];
+    scalar(S, P, S_N_SLOTS, b) = 0;
+    scalar(S, P, S_N_EDGES, b) = 0;
+    scalar(S, P, S_FLAGS, b) = 0;
+    scalar(S, P, S_OUTCOME, b) = -1;
+    S.disc_order[(size_t)b * P.ncap] = (uint8_t)starter;
+    S.owned_order[(size_t)b * P.ncap] = (uint8_t)starter;
+    S.ep_return[b] = 0.0;
+  }
+  __syncwarp();
+}
+
+template <bool SMEM_BUF>
+__global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Params P, State S,
+                                                                const uint8_t* __restrict__ reset_mask,
+                                                                float* __restrict__ obs_out, int mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SharedWeights& SW = *reinterpret_cast<SharedWeights*>(smem_raw);
+  for (int i = threadIdx.x; i < NODE_EMB * NODE_EMB; i += blockDim.x) SW.gcn[i] = T.gcn_wt[i];
+  for (int i = threadIdx.x; i < NUM_DYN * PROJ_ROWS * NODE_EMB; i += blockDim.x) SW.dyn[i] = T.dyn_proj[i];
+  if (threadIdx.x < NODE_EMB) {
+    SW.bn1s[threadIdx.x] = T.bn1_scale[threadIdx.x];
+    SW.bn1h[threadIdx.x] = T.bn1_shift[threadIdx.x];
+    SW.bn2s[threadIdx.x] = T.bn2_scale[threadIdx.x];
+    SW.bn2h[threadIdx.x] = T.bn2_shift[threadIdx.x];
+  }
+  if (threadIdx.x < NN_CH) SW.nn0b[threadIdx.x] = T.nn0_b[threadIdx.x];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * OBS_WARPS + warp;
+  if (b >= P.B) return;
+
+  // per-warp scratch
+  unsigned char* wbase = smem_raw + sizeof(SharedWeights);
+  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + MAX_NODES;
+  constexpr size_t kWarpBytesGlob = (size_t)MAX_NODES * 4 + MAX_NODES;
+  WarpScratch W;
+  if (SMEM_BUF) {
+    unsigned char* p = wbase + (size_t)warp * kWarpBytesSmem;
+    W.y = reinterpret_cast<float*>(p);
+    W.g = W.y + SMEM_NODES * NODE_EMB;
+    W.dinv = W.g + SMEM_NODES * NODE_EMB;
+    W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
+  } else {
+    unsigned char* p = wbase + (size_t)warp * kWarpBytesGlob;
+    W.dinv = reinterpret_cast<float*>(p);
+    W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
+    W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
+    W.g = W.y + (size_t)P.ncap * NODE_EMB;
+  }
+
+  int flags = scalar(S, P, S_FLAGS, b);
+  bool do_reset = false;
+  if (mode == 1) {
+    do_reset = reset_mask ? (reset_mask[b] != 0) : true;
+  } else if (!(flags & FL_NEEDS_RESET)) {
+    if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
+    if (flags & FL_REENCODE) {
+      encode_env(T, P, S, SW, W, b, lane);
+      build_table(P, S, W, b, lane);
+    }
+    if (flags & FL_FINISHED_THIS_STEP) {
+      finish_episode(T, P, S, b, lane);
+      if (P.auto_reset) do_reset = true;
+    }
+    __syncwarp();
+    if (lane == 0) scalar(S, P, S_FLAGS, b) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+    __syncwarp();
+  }
+  if (do_reset) {
+    reset_env(T, P, S, b, lane);
+    encode_env(T, P, S, SW, W, b, lane);
+    build_table(P, S, W, b, lane);
+  }
+  if (obs_out) {
+    const float* src = S.obs + (size_t)b * OBS_DIM;
+    float* dst = obs_out + (size_t)b * OBS_DIM;
+    for (int i = lane; i < OBS_DIM; i += 32) dst[i] = src[i];
+  }
+}
+
+size_t observe_smem_bytes(bool smem_buf) {
+  const size_t per_warp = smem_buf ? ((size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + MAX_NODES)
+                                   : ((size_t)MAX_NODES * 4 + MAX_NODES);
+  return sizeof(SharedWeights) + OBS_WARPS * per_warp;
+}
+
+cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, float* obs_out,
+                           int mode, cudaStream_t stream) {
+  const bool smem_buf = P.ncap <= SMEM_NODES;
+  const size_t smem = observe_smem_bytes(smem_buf);
+  const int grid = (P.B + OBS_WARPS - 1) / OBS_WARPS;
+  static bool attr_set[2] = {false, false};
+  if (smem_buf) {
+    if (!attr_set[0]) {
+      cudaError_t e = cudaFuncSetAttribute(observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set[0] = true;
+    }
+    observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, obs_out, mode);
+  } else {
+    if (!attr_set[1]) {
+      cudaError_t e = cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      attr_set[1] = true;
+    }
+    observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, obs_out, mode);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace cbs

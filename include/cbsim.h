@@ -101,6 +101,7 @@ typedef struct {
   const int32_t* nd_disruptable;         /* [Nn] */
   const int32_t* nd_row_off;             /* [2*Nn+1] local|remote candidate lists */
   const uint32_t* outblock;              /* [ports][words] */
+  const int32_t* uvuln_global;           /* [num_uvuln_total] scenario-local vuln index -> row of vemb */
   const int32_t* inst_of;                /* [num_instof] */
   const int32_t* vi_port;                /* [I] */
   const uint32_t* vi_flags;              /* [I] */
@@ -215,7 +216,15 @@ void* cbs_state_ptr(cbs_handle* h, int32_t field);
 int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream);
 /* number of kernels this library launched since creation (bench.py reports it) */
 int64_t cbs_launch_count(const cbs_handle* h);
+/* cudaDeviceSynchronize + device error flag (capacity overflow, empty action table) -> CBS_ERR_CAPACITY */
 int cbs_sync(cbs_handle* h);
+/* out3 = { sizeof(cbs_config), sizeof(cbs_scenario_tables), sizeof(cbs_gae_tables) } — lets a foreign-function
+ * binding verify its struct layout without a GPU */
+int cbs_struct_sizes(int32_t* out3);
+/* bytes of device memory held by the handle (tables + env state) */
+int64_t cbs_state_bytes(const cbs_handle* h);
+/* out4 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active } */
+int cbs_capacities(const cbs_handle* h, int32_t* out4);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,123 @@
+"""Helpers for the -m gpu parity tests: drive BatchedCyberBattleEnv through the split C-ABI calls
+(decode -> transition -> observe) and collect the same record oracle/trace.py produces."""
+import numpy as np
+import torch
+
+import ccbs_b200.constants as C
+from ccbs_b200 import lib as L
+
+
+def masks_to_u64(m, b):
+    """uint32[N_MASKS, words, B] -> uint64[N_MASKS, 2] for env b (trace.masks_to_array layout)."""
+    out = np.zeros((C.N_MASKS, 2), dtype=np.uint64)
+    words = m.shape[1]
+    for w in range(words):
+        out[:, w // 2] |= m[:, w, b].astype(np.uint64) << np.uint64(32 * (w % 2))
+    return out
+
+
+class TieFollower:
+    """Runs the oracle in lockstep.  When the CUDA decode picks a different table row than the oracle, the
+    pick is accepted only if the ORACLE's own float64 distances of the two rows differ by < tol (a genuine
+    near-tie, decided by float32 rounding of the node embeddings); the step then continues with the oracle's
+    choice on both sides so that the rest of the trace stays comparable.  Every such event is counted."""
+
+    def __init__(self, oracle_env, spec, starters, tol=1e-6):
+        from oracle import trace as tr
+        self.env, self.vidx, self.starters, self.tol = oracle_env, tr.vuln_index(spec), starters, tol
+        self.ep, self.flips, self.max_gap = 0, 0, 0.0
+        self.env.reset(starter=int(starters[0]))
+
+    def resolve(self, action, gpu_sel):
+        s, t, vid, kind, d, _ = self.env.find_closest_action_embedding(action)
+        want = (s, t, self.vidx[vid], kind)
+        self._forced = (s, t, vid, kind, d)
+        if tuple(int(x) for x in gpu_sel) == want:
+            return None
+        rows = self.env._rows_cache
+        from scipy.spatial import distance
+        dd = distance.cdist(np.atleast_2d(np.asarray(action, np.float32)), rows, "cosine").flatten()
+        cand = [i for i, k in enumerate(self.env.action_keys)
+                if (k[0], k[1], self.vidx[k[2]], k[3]) == tuple(int(x) for x in gpu_sel)]
+        assert cand, f"CUDA decode chose {tuple(gpu_sel)} which is not in the oracle's action table (oracle: {want})"
+        gap = float(min(dd[i] for i in cand) - d)
+        assert gap < self.tol, f"CUDA decode chose {tuple(gpu_sel)} (d gap {gap:.3e}) instead of {want}"
+        self.flips += 1
+        self.max_gap = max(self.max_gap, gap)
+        return np.array(want, np.int32), d
+
+    def advance(self, action, u):
+        self.env.step(action, u, forced=self._forced)
+        if self.env.done or self.env.truncated:
+            self.ep += 1
+            self.env.reset(starter=int(self.starters[self.ep]))
+
+
+def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None):
+    """Step every env of `env` with the same action/uniform sequence; returns a trace record for env
+    `check_env` plus the per-step cross-env consistency flag."""
+    B, T = env.num_envs, len(actions)
+    rec = dict(sel=np.zeros((T, 4), np.int32), code=np.zeros(T, np.int32), reward=np.zeros(T, np.float64),
+               done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
+               dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
+               disc_order=np.full((T, n_nodes), -1, np.int16), owned_order=np.full((T, n_nodes), -1, np.int16),
+               counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, C.OBS_DIM + 2), np.float32),
+               episode=np.zeros(T, np.int32))
+    reset_obs, reset_masks, stats = [], [], []
+    obs = env.reset()
+    env.sync()
+    reset_obs.append(obs[check_env].cpu().numpy().copy())
+    reset_masks.append(masks_to_u64(env.masks(), check_env))
+    consistent = True
+    ep = 0
+    b = check_env
+    for t in range(T):
+        a = torch.from_numpy(np.ascontiguousarray(actions[t])).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
+        u = torch.full((B,), float(uniforms[t]), dtype=torch.float32, device=env.device)
+        sel, dist = env.decode(a)
+        if follower is not None:
+            env.sync()
+            fix = follower.resolve(actions[t], sel[check_env].cpu().numpy())
+            if fix is not None:
+                sel = torch.from_numpy(fix[0]).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
+                dist = torch.full((B,), fix[1], dtype=torch.float64, device=env.device)
+            follower.advance(actions[t], uniforms[t])
+        reward, done, trunc, outcome = env.transition(sel, dist, u)
+        env.sync()
+        sel_h, dist_h = sel.cpu().numpy(), dist.cpu().numpy()
+        m, sc = env.masks(), env.scalars()
+        do, oo = env.disc_order(), env.owned_order()
+        r64 = env.reward64()
+        consistent &= bool((sel_h == sel_h[0]).all() and (m == m[:, :, :1]).all())
+        flags = int(sc[L.S_FLAGS, b])
+        rec["sel"][t] = sel_h[b]
+        rec["code"][t] = int(outcome[b])
+        rec["reward"][t] = r64[b]
+        rec["done"][t] = flags & 1
+        rec["truncated"][t] = (flags >> 1) & 1
+        rec["reason"][t] = (flags >> 2) & 3
+        rec["dist"][t] = dist_h[b]
+        rec["masks"][t] = masks_to_u64(m, b)
+        nd, no = int(sc[L.S_N_DISC, b]), int(sc[L.S_N_OWNED, b])
+        rec["disc_order"][t, :nd] = do[b, :nd]
+        rec["owned_order"][t, :no] = oo[b, :no]
+        rec["counters"][t] = [sc[L.S_STEPCOUNT, b], sc[L.S_NUM_ITER, b], sc[L.S_DISC_AMOUNT, b], sc[L.S_OWNABLE, b],
+                              sc[L.S_DISCOVERABLE, b], sc[L.S_DISRUPTABLE, b], sc[L.S_DISCOVERABLE_AMOUNT, b]]
+        rec["episode"][t] = ep
+        finished = bool(int(done[b]))
+        assert finished == bool(flags & 3)
+        obs = env.observe()
+        env.sync()
+        if finished:
+            rec["obs"][t] = env.terminal_obs()[b]
+            stats.append(env.last_stats()[b].copy())
+            ep += 1
+            reset_obs.append(obs[b].cpu().numpy().copy())
+            reset_masks.append(masks_to_u64(env.masks(), b))
+        else:
+            rec["obs"][t] = obs[b].cpu().numpy()
+    rec["reset_obs"] = np.array(reset_obs, np.float32)
+    rec["reset_masks"] = np.array(reset_masks, np.uint64)
+    rec["stats"] = np.array(stats, np.float64).reshape(-1, 14)
+    rec["num_episodes"] = np.array(ep + 1, np.int32)
+    return rec, consistent
