@@ -1,0 +1,113 @@
+"""-m gpu: heterogeneous batch (different scenarios, sizes, action streams per env) in lockstep with one
+oracle per env.  Covers per-env scenario offsets, the fused cbs_step call with auto-reset, on-device Philox
+uniforms and random starters (both restated on the host from the same counters)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _philox_uniform(seed, env, step, stream):
+    """Host restatement of csrc/philox.cuh (Philox4x32-10, first word, 24-bit uniform)."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    c = [env & 0xFFFFFFFF, (env >> 32) & 0xFFFFFFFF, step & 0xFFFFFFFF, stream & 0xFFFFFFFF]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return c[0]
+
+
+def philox_u01(seed, env, step, stream):
+    return np.float32((_philox_uniform(seed, env, step, stream) >> 8) * (1.0 / 16777216.0))
+
+
+def philox_pick(seed, env, step, stream, n):
+    return (_philox_uniform(seed, env, step, stream) * n) >> 32
+
+
+@pytest.mark.parametrize("goal,sizes", [("control", (8, 24)), ("discovery", (8, 14)), ("control", (40, 70))])
+def test_lockstep_heterogeneous_batch(goal, sizes):
+    import torch
+    from scipy.spatial import distance
+    import ccbs_b200 as cb
+    from ccbs_b200 import lib as L
+    from ccbs_b200.batched_env import BatchedCyberBattleEnv
+    from ccbs_b200.gae import GaeWeights
+    from oracle import trace as tr
+    from oracle.cbs_oracle import OracleEnv
+    from tests.gpu_harness import masks_to_u64
+
+    rng = np.random.default_rng(5)
+    pool = cb.synthetic_vuln_pool(99, 120)
+    S, B, T, seed, offset = 6, 40, 70, 12345, 1000
+    specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool) for k in range(S)]
+    cfg = cb.EnvConfig(goal=goal)
+    w = GaeWeights.random(3)
+    sc_of_env = rng.integers(0, S, size=B).astype(np.int32)
+    env = BatchedCyberBattleEnv(specs, w, cfg, num_envs=B, scenario_of_env=sc_of_env, seed=seed, global_env_offset=offset,
+                                auto_reset=True)
+    tables = env.tables
+    g = cb.constants.GOALS[goal]
+    oracles = [OracleEnv(specs[sc_of_env[b]], w, cfg) for b in range(B)]
+    vidx = [tr.vuln_index(specs[sc_of_env[b]]) for b in range(B)]
+    episodes = [0] * B
+    total_steps = [0] * B
+
+    def starter_for(b):
+        sc = sc_of_env[b]
+        f0, f1 = tables.sc_feasible_off[g][sc], tables.sc_feasible_off[g][sc + 1]
+        return int(tables.feasible_starters[g][f0 + philox_pick(seed, offset + b, episodes[b], 1, int(f1 - f0))])
+
+    obs = env.reset()
+    env.sync()
+    obs_h = obs.cpu().numpy()
+    for b in range(B):
+        o = oracles[b].reset(starter=starter_for(b))
+        np.testing.assert_allclose(obs_h[b, :192], o["graph_embeddings"], rtol=1e-5, atol=2e-5)
+    flips = 0
+    actions = rng.uniform(-4, 4, size=(T, B, 905)).astype(np.float32)
+    for t in range(T):
+        obs, reward, done, info = env.step(torch.from_numpy(actions[t]).to(env.device), None)
+        env.sync()
+        obs_h, rew_h, done_h, info_h = obs.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
+        m = env.masks()
+        term = env.terminal_obs()
+        for b in range(B):
+            o = oracles[b]
+            u = philox_u01(seed, offset + b, total_steps[b], 0)
+            total_steps[b] += 1
+            s, t_, vid, kind, d, _ = o.find_closest_action_embedding(actions[t, b])
+            want = (s, t_, vidx[b][vid], kind)
+            got = tuple(int(x) for x in info_h[b, :4])
+            forced = None
+            if got != want:
+                # accepted only as a genuine near-tie of the ORACLE's float64 distances (two table rows whose
+                # node embeddings agree to the last float32 bit or so); the oracle then follows the CUDA pick
+                dd = distance.cdist(np.atleast_2d(actions[t, b]), o._rows_cache, "cosine").flatten()
+                cand = [i for i, k in enumerate(o.action_keys) if (k[0], k[1], vidx[b][k[2]], k[3]) == got]
+                assert cand, f"step {t} env {b}: decode {got} is not in the oracle's table (oracle {want})"
+                i = min(cand, key=lambda j: dd[j])
+                assert dd[i] - d < 1e-6, f"step {t} env {b}: decode {got} (gap {dd[i] - d:.3e}) vs oracle {want}"
+                flips += 1
+                forced = (got[0], got[1], o.action_keys[i][2], got[3], dd[i])
+            ob, r, dn, inf = o.step(actions[t, b], u, forced=forced)
+            assert int(info_h[b, 4]) == o.outcome and int(info_h[b, 5]) == o.end_episode_reason
+            assert bool(done_h[b]) == bool(dn)
+            np.testing.assert_allclose(rew_h[b], r, rtol=1e-5, atol=1e-4)
+            if dn:
+                np.testing.assert_allclose(term[b, :192], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
+                assert tuple(term[b, 192:]) == tuple(float(x) for x in ob["discrete_features"])
+                episodes[b] += 1
+                ob = o.reset(starter=starter_for(b))
+            np.testing.assert_allclose(obs_h[b, :192], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
+            assert tuple(obs_h[b, 192:]) == tuple(float(x) for x in ob["discrete_features"])
+            assert np.array_equal(masks_to_u64(m, b), tr.masks_to_array(o.masks())), f"step {t} env {b}: masks differ"
+    sc = env.scalars()
+    assert flips <= max(1, B * T // 200), f"{flips} near-tie flips in {B * T} env-steps"
+    assert np.array_equal(sc[L.S_EPISODES], np.array(episodes))
+    assert sum(episodes) > B, "test too short to exercise auto-reset"
+    acc = env.stat_accum()
+    assert acc["episodes"] == sum(episodes)
+    env.close()
