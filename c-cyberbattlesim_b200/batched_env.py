@@ -51,12 +51,15 @@ class BatchedCyberBattleEnv:
             scenario_of_env = np.arange(self.num_envs, dtype=np.int32) % self.tables.num_scenarios
         self.scenario_of_env = np.ascontiguousarray(scenario_of_env, dtype=np.int32)
         self._check(self.lib.cbs_set_scenarios(self._h, self.scenario_of_env.ctypes.data_as(ct.c_void_p)))
-        caps = (ct.c_int32 * 4)()
+        caps = (ct.c_int32 * 5)()
         self.lib.cbs_capacities(self._h, caps)
         self.ncap, self.slots, self.ecap, self.tensor_core_decode = caps[0], caps[1], caps[2], bool(caps[3])
+        self.vt_stride = caps[4]
         B = self.num_envs
         with torch.cuda.device(self.device):
-            self.obs = torch.zeros(B, C.OBS_DIM + 2, dtype=torch.float32, device=self.device)
+            # zero-copy view of the library's observation cache [B, 194]
+            self.obs = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_OBS), (B, C.OBS_DIM + 2), torch.float32,
+                                        self.device, self)
             self.reward = torch.zeros(B, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.truncated = torch.zeros(B, dtype=torch.uint8, device=self.device)
@@ -112,7 +115,7 @@ class BatchedCyberBattleEnv:
         """Reset all envs (or those with env_mask != 0).  Returns obs[B, 194] (device tensor, reused)."""
         if env_mask is not None:
             env_mask = env_mask.to(device=self.device, dtype=torch.uint8).contiguous()
-        self._check(self.lib.cbs_reset(self._h, self._p(env_mask), self._p(self.obs), self._stream()))
+        self._check(self.lib.cbs_reset(self._h, self._p(env_mask), None, self._stream()))
         return self.obs
 
     def decode(self, actions: torch.Tensor):
@@ -130,7 +133,7 @@ class BatchedCyberBattleEnv:
         return self.reward, self.done, self.truncated, self.outcome
 
     def observe(self) -> torch.Tensor:
-        self._check(self.lib.cbs_observe(self._h, self._p(self.obs), self._stream()))
+        self._check(self.lib.cbs_observe(self._h, None, self._stream()))
         return self.obs
 
     def step(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None, want_info: bool = True):
@@ -139,7 +142,7 @@ class BatchedCyberBattleEnv:
         observation is available from :meth:`terminal_obs`."""
         actions = self._actions(actions)
         uniforms = self._uniforms(uniforms)
-        self._check(self.lib.cbs_step(self._h, self._p(actions), self._p(uniforms), self._p(self.obs), self._p(self.reward),
+        self._check(self.lib.cbs_step(self._h, self._p(actions), self._p(uniforms), None, self._p(self.reward),
                                       self._p(self.done), self._p(self.info) if want_info else None, self._stream()))
         return self.obs, self.reward, self.done, self.info
 
@@ -190,6 +193,10 @@ class BatchedCyberBattleEnv:
     def last_stats(self) -> np.ndarray:
         """get_statistics() 14-tuple of the last finished episode of every env (cyberbattle_env.py:517-524)."""
         return self.read(L.F_LAST_STATS, np.float64, (self.num_envs, 14))
+
+    def vt(self) -> np.ndarray:
+        """float32[B, vt_stride]: a_v . v_u of the last decode (columns >= global_vulns are padding)."""
+        return self.read(L.F_VT, np.float32, (self.num_envs, self.vt_stride))
 
     def reward64(self) -> np.ndarray:
         return self.read(L.F_REWARD64, np.float64, (self.num_envs,))

@@ -10,10 +10,10 @@
 
 namespace cbs {
 cudaError_t launch_decode_gemm_simt(const float*, const float*, float*, int, int, int, cudaStream_t);
-cudaError_t launch_decode_gemm_tc(const float*, const float*, float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_decode_gemm_tc(const float*, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
 bool decode_gemm_tc_available();
 cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int32_t*, double*, cudaStream_t);
-cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, float*, int, cudaStream_t);
+cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, int, int, cudaStream_t);
 cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, float*,
                               uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
 
@@ -51,10 +51,11 @@ struct cbs_handle {
   int Ug = 0, vt_stride = 0;
   int64_t launches = 0;
   bool use_tc = false;
+  int num_sms = 148;
   float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
   // host-step staging
   cudaStream_t hstream = nullptr;
-  float *h_actions = nullptr, *h_uniforms = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+  float *h_actions = nullptr, *h_uniforms = nullptr, *h_reward = nullptr;
   uint8_t* h_done = nullptr;
   int32_t* h_info = nullptr;
   // io scratch for cbs_step
@@ -125,6 +126,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   if (e != cudaSuccess) return fail(nullptr, CBS_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
   cbs_handle* h = new cbs_handle();
   h->cfg = *cfg;
+  cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
   Params& P = h->P;
   P.B = cfg->num_envs;
   P.global_env_offset = cfg->global_env_offset;
@@ -209,7 +211,8 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   h->Ug = t->num_global_vulns;
   h->vt_stride = ((h->Ug + 63) / 64) * 64;
   h->use_tc = (h->cfg.decode_gemm == 0) && decode_gemm_tc_available();
-  P.margin = h->cfg.decode_margin > 0 ? h->cfg.decode_margin : (h->use_tc ? 4e-4f : 2e-5f);
+  // float32-scan error budget: half-precision snapshot copies (~6e-5 worst case) + TF32 products (~2e-5)
+  P.margin = h->cfg.decode_margin > 0 ? h->cfg.decode_margin : (h->use_tc ? 1e-3f : 5e-4f);
 
   State& S = h->S;
   const size_t B = P.B;
@@ -218,6 +221,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
+  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, B); AL(work_ctr, 2);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
@@ -277,8 +281,9 @@ static int check_ready(cbs_handle* h) {
 int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintptr_t stream) {
   int rc = check_ready(h);
   if (rc) return rc;
-  CK(h, launch_observe(h->T, h->P, h->S, env_mask_dev, obs_dev, 1, (cudaStream_t)stream));
+  CK(h, launch_observe(h->T, h->P, h->S, env_mask_dev, 1, h->num_sms, (cudaStream_t)stream));
   h->launches += 1;
+  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CBS_OK;
 }
 
@@ -288,7 +293,7 @@ int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double
   if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_decode: actions is null");
   cudaStream_t st = (cudaStream_t)stream;
   if (h->use_tc) {
-    CK(h, launch_decode_gemm_tc(actions_dev, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    CK(h, launch_decode_gemm_tc(actions_dev, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
     h->launches += 2;
   } else {
     CK(h, launch_decode_gemm_simt(actions_dev, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
@@ -313,8 +318,9 @@ int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev
 int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
   int rc = check_ready(h);
   if (rc) return rc;
-  CK(h, launch_observe(h->T, h->P, h->S, nullptr, obs_dev, 0, (cudaStream_t)stream));
+  CK(h, launch_observe(h->T, h->P, h->S, nullptr, 0, h->num_sms, (cudaStream_t)stream));
   h->launches += 1;
+  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CBS_OK;
 }
 
@@ -339,7 +345,6 @@ static int ensure_host_staging(cbs_handle* h) {
   CK(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
   if ((rc = dalloc(h, h->state_allocs, &h->h_actions, B * ACTION_DIM, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_uniforms, B, false))) return rc;
-  if ((rc = dalloc(h, h->state_allocs, &h->h_obs, B * OBS_DIM, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_reward, B, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_done, B, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_info, B * CBS_INFO_INTS, false))) return rc;
@@ -356,10 +361,10 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
   cudaStream_t st = h->hstream;
   CK(h, cudaMemcpyAsync(h->h_actions, actions_host, B * ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
   if (uniforms_host) CK(h, cudaMemcpyAsync(h->h_uniforms, uniforms_host, B * sizeof(float), cudaMemcpyHostToDevice, st));
-  rc = cbs_step(h, h->h_actions, uniforms_host ? h->h_uniforms : nullptr, h->h_obs, h->h_reward, h->h_done,
+  rc = cbs_step(h, h->h_actions, uniforms_host ? h->h_uniforms : nullptr, nullptr, h->h_reward, h->h_done,
                 info_host ? h->h_info : nullptr, (uintptr_t)st);
   if (rc) return rc;
-  if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->h_obs, B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->S.obs, B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (done_host) CK(h, cudaMemcpyAsync(done_host, h->h_done, B, cudaMemcpyDeviceToHost, st));
   if (info_host) CK(h, cudaMemcpyAsync(info_host, h->h_info, B * CBS_INFO_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -384,6 +389,7 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_DIST: *p = S.dist; *bytes = B * 8; break;
     case CBS_F_REWARD64: *p = S.reward64; *bytes = B * 8; break;
     case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
+    case CBS_F_VT: *p = S.vt; *bytes = B * h->vt_stride * 4; break;
     default: return fail(h, CBS_ERR_INVALID_ARG, "unknown state field %d", field);
   }
   return 0;
@@ -425,7 +431,7 @@ int cbs_sync(cbs_handle* h) {
   CK(h, cudaDeviceSynchronize());
   int flag = 0;
   CK(h, cudaMemcpy(&flag, h->S.errflag, 4, cudaMemcpyDeviceToHost));
-  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table)", flag);
+  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 9 tensor-core pipeline timeout)", flag);
   return CBS_OK;
 }
 
@@ -436,9 +442,10 @@ int cbs_struct_sizes(int32_t* out3) {
 }
 
 int64_t cbs_state_bytes(const cbs_handle* h) { return h ? (int64_t)h->state_bytes : 0; }
-int cbs_capacities(const cbs_handle* h, int32_t* out4) {
+int cbs_capacities(const cbs_handle* h, int32_t* out4 /* 5 ints */) {
   if (!h || !out4) return CBS_ERR_INVALID_ARG;
   out4[0] = h->P.ncap; out4[1] = h->P.slots; out4[2] = h->P.ecap; out4[3] = h->use_tc ? 1 : 0;
+  out4[4] = h->vt_stride;
   return CBS_OK;
 }
 

@@ -2,6 +2,7 @@
 // Numbers mirror c-cyberbattlesim_b200/constants.py (tests/test_constants.py keeps them in sync).
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace cbs {
@@ -84,6 +85,7 @@ struct State {  // mutable, device pointers
   uint8_t* pair_slot;    // [B][ncap*ncap]   0xFF = pair not in the action table
   float* z_hist;         // [B][slots][ncap][64]  node embeddings of the encode that created the slot
   float* zn2_hist;       // [B][slots][ncap]      their squared norms
+  __half* z16_hist;      // [B][slots][ncap][64]  half-precision copy read by the approximate decode scan
   uint8_t* edge_src;     // [B][ecap]
   uint8_t* edge_dst;     // [B][ecap]
   int32_t* edge_cnt;     // [B][ecap]   live accumulator length (0 after the compressed:237 reset)
@@ -101,6 +103,8 @@ struct State {  // mutable, device pointers
   float* vt;             // [B][Ug]  action x vulnerability-embedding products (decode GEMM output)
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   int32_t* errflag;      // [1]
+  int32_t* worklist;     // [B] envs whose step needs graph work (edge / re-encode / episode end)
+  int32_t* work_ctr;     // [0] worklist length, [1] finished-CTA counter of the observe kernel
 };
 
 __host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {

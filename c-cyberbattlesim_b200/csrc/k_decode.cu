@@ -6,8 +6,9 @@
 //     a_s.z_s + a_t.z_t + a_v.v_u + a_o[onehot]      and      |row|^2 = |z_s|^2 + |z_t|^2 + |v_u|^2 + 1 ,
 // where z_s, z_t are the embeddings frozen when the pair entered the table (snapshot slot) and a_v.v_u comes from
 // one dense contraction  VT[B,Ug] = A_v[B,768] x Vemb[Ug,768]^T  shared by every row (decode_gemm_*).
-// decode_select scans the rows in float32, then re-scores every row within `margin` of the best one in
-// float64 with the same formula scipy uses, so the chosen (s,t,vuln,outcome) and the returned distance match a
+// decode_select scans the rows in float32 (half-precision copies of the frozen embeddings, TF32/FP32 products
+// from the contraction), and re-scores every row within `margin` of the best one in float64 from the float32
+// embeddings and the float64 vulnerability table with the same formula scipy uses, so the chosen (s,t,vuln,outcome) and the returned distance match a
 // float64 evaluation; ties break on insertion order (epoch, source position, target position, row) like
 // np.argmin over the reference's insertion-ordered dict.
 #include "cbs_device.cuh"
@@ -129,7 +130,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     return;
   }
   const float* act = actions + (size_t)b * ACTION_DIM;
-  const float as0 = act[lane], as1 = act[lane + 32], at0 = act[NODE_EMB + lane], at1 = act[NODE_EMB + lane + 32];
+  // lane l holds channels 2l, 2l+1 of the source and target parts (matches the half2 snapshot layout)
+  const float as0 = act[2 * lane], as1 = act[2 * lane + 1];
+  const float at0 = act[NODE_EMB + 2 * lane], at1 = act[NODE_EMB + 2 * lane + 1];
   if (lane < OUTCOME_DIM) s_ao[warp][lane] = act[2 * NODE_EMB + VULN_EMB + lane];
   double na2 = 0.0;
   for (int i = lane; i < ACTION_DIM; i += 32) { const double a = act[i]; na2 = fma(a, a, na2); }
@@ -147,74 +150,62 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
   const float* vt = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
 
-  float smax = -INFINITY;
+  // Single pass.  run_max only grows, so a row within `margin` of the final maximum is also within `margin` of
+  // run_max when it is visited: every such row is re-scored in float64 on the spot; rows that were only
+  // "records so far" cost a few extra re-scores.
+  float run_max = -INFINITY;
   double best_d = INFINITY;
   unsigned long long best_key = ~0ull;
   RowRef best{0, 0, 0, -1, ~0ull};
-  bool any_row = false;
 
-  for (int pass = 0; pass < 2; ++pass) {
-    float lane_best = -INFINITY;
-    for (int op = 0; op < n_owned; ++op) {
-      const int s = oorder[op];
-      for (int dp = 0; dp < n_disc; ++dp) {
-        const int t = dorder[dp];
-        const int slot = ps[s * P.ncap + t];
-        if (slot == 0xFF) continue;
-        const float* zs = S.z_hist + (((size_t)b * P.slots + slot) * P.ncap + s) * NODE_EMB;
-        const float* zt = S.z_hist + (((size_t)b * P.slots + slot) * P.ncap + t) * NODE_EMB;
-        float st = as0 * zs[lane] + as1 * zs[lane + 32] + at0 * zt[lane] + at1 * zt[lane + 32];
-        st = warp_sum(st);
-        const float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
-        const float n2 = zn[s] + zn[t] + 1.f;
-        const int g = node_off + t;
-        const int r0 = (s == t) ? T.nd_row_off[2 * g] : T.nd_row_off[2 * g + 1];
-        const int r1 = T.nd_row_off[2 * g + 2];
-        for (int base = r0; base < r1; base += 32) {
-          const int r = base + lane;
-          float score = -INFINITY;
-          bool valid = false;
-          if (r < r1) {
-            const uint32_t packed = T.row_packed[r];
-            const int kind = (packed >> 20) & 15;
-            if (!row_filtered(P, kind, s, t, starter)) {
-              const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-              score = (st + vt[u] + s_ao[warp][oh]) * rsqrtf(n2 + (float)T.vnorm2[u]);
-              valid = true;
-            }
-          }
-          if (pass == 0) {
-            if (valid) lane_best = (score > lane_best || score != score) ? score : lane_best;   // NaN is sticky
-            any_row |= valid;
-          } else {
-            // every row whose float32 score is not provably below the best one is re-scored in float64
-            unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < smax - margin_s));
-            while (cand) {
-              const int src_lane = __ffs(cand) - 1;
-              cand &= cand - 1;
-              RowRef rr;
-              rr.s = s; rr.t = t; rr.slot = slot; rr.r = base + src_lane;
-              rr.key = ((unsigned long long)slot << 56) | ((unsigned long long)op << 48) | ((unsigned long long)dp << 40) |
-                       (unsigned long long)(unsigned)rr.r;
-              const double d = exact_distance(T, P, S, act, b, rr, na, lane);
-              // np.argmin: the first NaN wins if any distance is NaN, else the first minimum
-              const bool dn = d != d, bn = best_d != best_d;
-              const bool better = best.r < 0 || (dn ? (!bn || rr.key < best_key)
-                                                    : (!bn && (d < best_d || (d == best_d && rr.key < best_key))));
-              if (better) { best = rr; best_d = d; best_key = rr.key; }
-            }
+  for (int op = 0; op < n_owned; ++op) {
+    const int s = oorder[op];
+    for (int dp = 0; dp < n_disc; ++dp) {
+      const int t = dorder[dp];
+      const int slot = ps[s * P.ncap + t];
+      if (slot == 0xFF) continue;
+      const __half2* z16 = reinterpret_cast<const __half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
+      const float2 zs = __half22float2(z16[s * (NODE_EMB / 2) + lane]);
+      const float2 zt = __half22float2(z16[t * (NODE_EMB / 2) + lane]);
+      const float st = warp_sum(as0 * zs.x + as1 * zs.y + at0 * zt.x + at1 * zt.y);
+      const float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
+      const float n2 = zn[s] + zn[t] + 1.f;
+      const int g = node_off + t;
+      const int r0 = (s == t) ? T.nd_row_off[2 * g] : T.nd_row_off[2 * g + 1];
+      const int r1 = T.nd_row_off[2 * g + 2];
+      for (int base = r0; base < r1; base += 32) {
+        const int r = base + lane;
+        float score = -INFINITY;
+        bool valid = false;
+        if (r < r1) {
+          const uint32_t packed = T.row_packed[r];
+          const int kind = (packed >> 20) & 15;
+          if (!row_filtered(P, kind, s, t, starter)) {
+            const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
+            score = (st + vt[u] + s_ao[warp][oh]) * rsqrtf(n2 + (float)T.vnorm2[u]);
+            valid = true;
           }
         }
-      }
-    }
-    if (pass == 0) {
-      if (!__any_sync(0xFFFFFFFFu, any_row)) break;         // empty table
+        float cmax = valid ? score : -INFINITY;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float other = __shfl_xor_sync(0xFFFFFFFFu, lane_best, o);
-        lane_best = (other > lane_best || other != other) ? other : lane_best;
+        for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+        run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < run_max - margin_s));
+        while (cand) {
+          const int src_lane = __ffs(cand) - 1;
+          cand &= cand - 1;
+          RowRef rr;
+          rr.s = s; rr.t = t; rr.slot = slot; rr.r = base + src_lane;
+          rr.key = ((unsigned long long)slot << 56) | ((unsigned long long)op << 48) | ((unsigned long long)dp << 40) |
+                   (unsigned long long)(unsigned)rr.r;
+          const double d = exact_distance(T, P, S, act, b, rr, na, lane);
+          // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
+          const bool dn = d != d, bn = best_d != best_d;
+          const bool better = best.r < 0 || (dn ? (!bn || rr.key < best_key)
+                                                : (!bn && (d < best_d || (d == best_d && rr.key < best_key))));
+          if (better) { best = rr; best_d = d; best_key = rr.key; }
+        }
       }
-      smax = lane_best;                                    // NaN => `score < smax - margin` is false for every row
     }
   }
   if (lane == 0) {

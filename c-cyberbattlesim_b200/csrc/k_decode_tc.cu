@@ -1,9 +1,241 @@
-// k_decode_tc.cu — tcgen05 (TF32) contraction for the decode: placeholder until the kernel lands.
+// k_decode_tc.cu — the decode contraction  VT[B, Ug] = A_v[B, 768] x Vemb[Ug, 768]^T  on tcgen05 (TF32 in, FP32
+// accumulate in TMEM), operands staged by TMA.
+//
+// This is the one GEMM-shaped piece of the step path (find_closest_action_embedding,
+// _env/cyberbattle_env_compressed.py:570-590: the 768-wide vulnerability part of every action against every
+// vulnerability embedding).  TF32 keeps the float32 inputs as they are (no conversion pass); its ~2^-11 operand
+// rounding is covered by decode_select's float64 re-score margin, so the chosen action is unaffected.
+//
+// Shape: one CTA per 128 envs x (<=256) vulnerabilities; K = 768 in 24 slabs of 32 floats (= one 128-byte
+// swizzle row), 4-stage TMA -> smem ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues 4 UMMAs (K = 8) per
+// slab and commits to the ring's empty barriers; all four warps drain the 128 x N accumulator from TMEM with
+// tcgen05.ld.32x32b and store float4 rows.  The action tensor's rows are 3620 bytes apart (not a multiple of
+// 16), which TMA cannot address, so pack_actions first copies the 768-float slice into an aligned [B,768] slab.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "cbs_types.h"
 
 namespace cbs {
-bool decode_gemm_tc_available() { return false; }
-cudaError_t launch_decode_gemm_tc(const float*, const float*, float*, float*, int, int, int, cudaStream_t) {
-  return cudaErrorNotSupported;
+
+namespace {
+
+constexpr int BM = 128;        // envs per CTA (UMMA M)
+constexpr int BK = 32;         // floats per K slab = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
+constexpr int STAGES = 4;
+constexpr int NT_MAX = 256;    // UMMA N limit
+constexpr int TMEM_COLS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug must end the kernel with an error flag, never hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int32_t* errflag) {
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return true;
+  }
+  atomicExch(errflag, 9);
+  return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout): start address >> 4 in
+// [0,14), stride byte offset (8 rows x 128 B = 1024) >> 4 in [32,46), version 1 in [46,48), layout type 2 in [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restrict__ actions, float* __restrict__ packed, int B) {
+  const int row = blockIdx.x * 2 + (threadIdx.x >> 7);
+  if (row >= B) return;
+  const float* src = actions + (size_t)row * ACTION_DIM + 2 * NODE_EMB;
+  float* dst = packed + (size_t)row * VULN_EMB;
+  for (int i = threadIdx.x & 127; i < VULN_EMB; i += 128) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                const __grid_constant__ CUtensorMap map_b,
+                                                                float* __restrict__ vt, int B, int Upad, int nt_box,
+                                                                int vt_stride, int32_t* errflag) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = A_STAGE_BYTES + nt_box * BK * 4;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT_MAX;
+  const int nt = min(NT_MAX, Upad - n0);             // columns this CTA produces (multiple of 16)
+  constexpr int KB = VULN_EMB / BK;                  // 24 slabs
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer ----
+    const uint32_t bytes = (uint32_t)stage_bytes;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (!mbar_wait(empty0 + 8 * s, ph ^ 1, errflag)) break;
+      mbar_expect_tx(full0 + 8 * s, bytes);
+      const uint32_t sa = smem_u32(smem + s * stage_bytes);
+      tma_load_2d(sa, &map_a, full0 + 8 * s, kb * BK, m0);
+      tma_load_2d(sa + A_STAGE_BYTES, &map_b, full0 + 8 * s, kb * BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer ----  instruction descriptor: D=F32 (bit 4), A=B=TF32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    bool ok = true;
+    for (int kb = 0; kb < KB && ok; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      ok = mbar_wait(full0 + 8 * s, ph, errflag);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem_u32(smem + s * stage_bytes);
+      const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k)   // advance 32 bytes along K inside the swizzle row: +2 in the >>4 address field
+        umma_tf32(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+      umma_commit(empty0 + 8 * s);            // frees the smem stage when these MMAs retire
+    }
+    umma_commit(tfull);                       // accumulator complete
+  }
+  __syncwarp();
+
+  // ---- epilogue: TMEM -> registers -> global (every warp owns TMEM lanes [32w, 32w+32) = tile rows) ----
+  const bool ready = mbar_wait(tfull, 0, errflag);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = m0 + warp * 32 + lane;
+  if (ready) {
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < B) {
+        float4* dst = reinterpret_cast<float4*>(vt + (size_t)row * vt_stride + n0 + c0);
+        const int ncols = min(32, vt_stride - n0 - c0);   // multiple of 4
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (4 * i < ncols)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+
+static bool load_encode() {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return true;
+}
+
+bool decode_gemm_tc_available() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10 && load_encode();
+}
+
+static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)VULN_EMB, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)VULN_EMB * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_decode_gemm_tc(const float* actions, const float* vemb, float* a_packed, float* vt, int B, int Ug,
+                                  int vt_stride, int32_t* errflag, cudaStream_t stream) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  const int Upad = ((Ug + 15) / 16) * 16;
+  const int nt_box = Upad < NT_MAX ? Upad : NT_MAX;
+  // tensor maps are rebuilt per launch (host-side encode, ~1 us each): the operands never move, but keeping the
+  // maps out of the handle keeps this translation unit self-contained
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, a_packed, (uint64_t)B, BM) || !make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box))
+    return cudaErrorInvalidValue;
+  pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B);
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)nt_box * BK * 4) + 1024 + 256;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(decode_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  dim3 grid((B + BM - 1) / BM, (Upad + NT_MAX - 1) / NT_MAX);
+  decode_gemm_tc_kernel<<<grid, 128, smem, stream>>>(map_a, map_b, vt, B, Upad, nt_box, vt_stride, errflag);
+  return cudaGetLastError();
+}
+
 }  // namespace cbs

@@ -16,7 +16,7 @@
 
 namespace cbs {
 
-constexpr int OBS_WARPS = 4;
+constexpr int OBS_WARPS = 8;
 constexpr int SMEM_NODES = 32;
 
 struct SharedWeights {
@@ -248,12 +248,14 @@ __device__ void build_table(const Params& P, const State& S, WarpScratch& W, int
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
+  __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
   for (int i = 0; i < n_disc; ++i) {
     const int node = dorder[i];
-    const float z0 = W.y[i * NODE_EMB + lane], z1 = W.y[i * NODE_EMB + lane + 32];
-    zh[node * NODE_EMB + lane] = z0;
-    zh[node * NODE_EMB + lane + 32] = z1;
-    const float n2 = warp_sum(z0 * z0 + z1 * z1);
+    if (bit_of(S, P, M_STOPPED, node, b)) continue;      // only Running nodes have embeddings (compressed:266-280)
+    const float2 z = reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane];   // channels 2*lane, 2*lane+1
+    reinterpret_cast<float2*>(zh + node * NODE_EMB)[lane] = z;
+    zh16[node * (NODE_EMB / 2) + lane] = __floats2half2_rn(z.x, z.y);
+    const float n2 = warp_sum(z.x * z.x + z.y * z.y);
     if (lane == 0) zn[node] = n2;
   }
   if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
@@ -354,8 +356,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
 
 template <bool SMEM_BUF>
 __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Params P, State S,
-                                                                const uint8_t* __restrict__ reset_mask,
-                                                                float* __restrict__ obs_out, int mode) {
+                                                                const uint8_t* __restrict__ reset_mask, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SharedWeights& SW = *reinterpret_cast<SharedWeights*>(smem_raw);
   for (int i = threadIdx.x; i < NODE_EMB * NODE_EMB; i += blockDim.x) SW.gcn[i] = T.gcn_wt[i];
@@ -370,8 +371,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * OBS_WARPS + warp;
-  if (b >= P.B) return;
+  const int gw = blockIdx.x * OBS_WARPS + warp, total_warps = gridDim.x * OBS_WARPS;
 
   // per-warp scratch
   unsigned char* wbase = smem_raw + sizeof(SharedWeights);
@@ -388,37 +388,49 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     unsigned char* p = wbase + (size_t)warp * kWarpBytesGlob;
     W.dinv = reinterpret_cast<float*>(p);
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
-    W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
-    W.g = W.y + (size_t)P.ncap * NODE_EMB;
+    W.y = W.g = nullptr;
   }
 
-  int flags = scalar(S, P, S_FLAGS, b);
-  bool do_reset = false;
-  if (mode == 1) {
-    do_reset = reset_mask ? (reset_mask[b] != 0) : true;
-  } else if (!(flags & FL_NEEDS_RESET)) {
-    if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
-    if (flags & FL_REENCODE) {
+  // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
+  // transition kernel put on the worklist — the others keep their cached observation untouched.
+  const int count = (mode == 1) ? P.B : S.work_ctr[0];
+  for (int i = gw; i < count; i += total_warps) {
+    const int b = (mode == 1) ? i : S.worklist[i];
+    if (!SMEM_BUF) {
+      W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
+      W.g = W.y + (size_t)P.ncap * NODE_EMB;
+    }
+    const int flags = scalar(S, P, S_FLAGS, b);
+    bool do_reset = false;
+    if (mode == 1) {
+      do_reset = reset_mask ? (reset_mask[b] != 0) : true;
+    } else if (!(flags & FL_NEEDS_RESET)) {
+      if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
+      if (flags & FL_REENCODE) {
+        encode_env(T, P, S, SW, W, b, lane);
+        build_table(P, S, W, b, lane);
+      }
+      if (flags & FL_FINISHED_THIS_STEP) {
+        finish_episode(T, P, S, b, lane);
+        if (P.auto_reset) do_reset = true;
+      }
+      __syncwarp();
+      if (lane == 0) scalar(S, P, S_FLAGS, b) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+      __syncwarp();
+    }
+    if (do_reset) {
+      reset_env(T, P, S, b, lane);
       encode_env(T, P, S, SW, W, b, lane);
       build_table(P, S, W, b, lane);
     }
-    if (flags & FL_FINISHED_THIS_STEP) {
-      finish_episode(T, P, S, b, lane);
-      if (P.auto_reset) do_reset = true;
+    __syncwarp();
+  }
+  if (mode == 0) {   // the last CTA to finish clears the worklist for the next transition
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(&S.work_ctr[1], 1) == (int)gridDim.x - 1) { S.work_ctr[0] = 0; S.work_ctr[1] = 0; __threadfence(); }
     }
-    __syncwarp();
-    if (lane == 0) scalar(S, P, S_FLAGS, b) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
-    __syncwarp();
-  }
-  if (do_reset) {
-    reset_env(T, P, S, b, lane);
-    encode_env(T, P, S, SW, W, b, lane);
-    build_table(P, S, W, b, lane);
-  }
-  if (obs_out) {
-    const float* src = S.obs + (size_t)b * OBS_DIM;
-    float* dst = obs_out + (size_t)b * OBS_DIM;
-    for (int i = lane; i < OBS_DIM; i += 32) dst[i] = src[i];
   }
 }
 
@@ -428,11 +440,14 @@ size_t observe_smem_bytes(bool smem_buf) {
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 
-cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, float* obs_out,
-                           int mode, cudaStream_t stream) {
+cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, int mode,
+                           int num_sms, cudaStream_t stream) {
   const bool smem_buf = P.ncap <= SMEM_NODES;
   const size_t smem = observe_smem_bytes(smem_buf);
-  const int grid = (P.B + OBS_WARPS - 1) / OBS_WARPS;
+  // persistent grid: one CTA per SM when the node buffers live in shared memory (181 KB), four otherwise
+  int grid = num_sms * (smem_buf ? 1 : 4);
+  const int need = (P.B + OBS_WARPS - 1) / OBS_WARPS;
+  if (grid > need) grid = need;
   static bool attr_set[2] = {false, false};
   if (smem_buf) {
     if (!attr_set[0]) {
@@ -440,14 +455,14 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
       if (e != cudaSuccess) return e;
       attr_set[0] = true;
     }
-    observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, obs_out, mode);
+    observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
   } else {
     if (!attr_set[1]) {
       cudaError_t e = cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       attr_set[1] = true;
     }
-    observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, obs_out, mode);
+    observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
   }
   return cudaGetLastError();
 }

@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, Sta
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (reencode ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0);
   SC(S_FLAGS) = flags;
+  if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
+    const int slot = atomicAdd(&S.work_ctr[0], 1);
+    if (slot < P.B) S.worklist[slot] = b; else atomicExch(S.errflag, 4);
+  }
   S.reward64[b] = reward;
   S.ep_return[b] += reward;
   if (reward_out) reward_out[b] = (float)reward;

@@ -58,7 +58,7 @@ SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cb
 
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
-    F_DIST, F_REWARD64, F_ERRFLAG = range(12)
+    F_DIST, F_REWARD64, F_ERRFLAG, F_VT = range(13)
 NUM_SCALARS, NUM_ACCUM = 20, 20
 # scalar planes (csrc/cbs_types.h enum Scalar)
 (S_SCENARIO, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE, S_DISCOVERABLE,

@@ -177,8 +177,10 @@ int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev
 
 /* replaces update_evolving_visible_graph_after_step + encode + create_continuous_action_space
  * (compressed:399-428, 465-550) and, with auto_reset, the VecEnv reset of finished envs.
- * obs_dev: [num_envs][CBS_OBS_DIM] float32.  The terminal observation of envs that finished in this step
- * stays readable through cbs_read_state(CBS_F_TERMINAL_OBS). */
+ * obs_dev: [num_envs][CBS_OBS_DIM] float32, or NULL: the observation cache itself is addressable through
+ * cbs_state_ptr(CBS_F_OBS) (zero copy).  The terminal observation of envs that finished in this step stays
+ * readable through cbs_read_state(CBS_F_TERMINAL_OBS).  Must follow a cbs_transition (it consumes the worklist
+ * that call produced). */
 int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream);
 
 /* decode + transition + observe, device buffers.  info_dev (optional): [num_envs][CBS_INFO_INTS] int32 =
@@ -205,7 +207,8 @@ typedef enum {
   CBS_F_PAIR_SLOT = 8,    /* uint8 [B][max_nodes*max_nodes] */
   CBS_F_DIST = 9,         /* float64 [B] last decode distance */
   CBS_F_REWARD64 = 10,    /* float64 [B] last step reward */
-  CBS_F_ERRFLAG = 11      /* int32 [1] device-side capacity error flag */
+  CBS_F_ERRFLAG = 11,     /* int32 [1] device-side capacity error flag */
+  CBS_F_VT = 12           /* float32 [B][vt_stride] action x vulnerability-embedding products of the last decode */
 } cbs_field;
 #define CBS_NUM_SCALARS 20
 #define CBS_NUM_ACCUM 20
@@ -223,8 +226,8 @@ int cbs_sync(cbs_handle* h);
 int cbs_struct_sizes(int32_t* out3);
 /* bytes of device memory held by the handle (tables + env state) */
 int64_t cbs_state_bytes(const cbs_handle* h);
-/* out4 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active } */
-int cbs_capacities(const cbs_handle* h, int32_t* out4);
+/* out5 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active, vt_stride } */
+int cbs_capacities(const cbs_handle* h, int32_t* out5);
 
 #ifdef __cplusplus
 }

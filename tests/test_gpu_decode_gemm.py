@@ -1,0 +1,31 @@
+"""-m gpu: the decode contraction VT = A_v x Vemb^T (tcgen05 TF32 path and SIMT float32 path) against float64."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("gemm,tol", [(1, 1e-3), (0, 0.35)], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("num_envs,pool", [(300, 40), (1024, 200), (130, 330)])
+def test_decode_products(gemm, tol, num_envs, pool):
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200.batched_env import BatchedCyberBattleEnv
+    from ccbs_b200.gae import GaeWeights
+    p = cb.synthetic_vuln_pool(7, pool)
+    specs = [cb.synthetic_spec(300 + k, 14, pool=p, vulns_per_service_range=(6, 14)) for k in range(12)]
+    env = BatchedCyberBattleEnv(specs, GaeWeights.random(0), cb.EnvConfig(), num_envs=num_envs, decode_gemm=gemm)
+    if gemm == 0:
+        assert env.tensor_core_decode, "tcgen05 path not active on this device"
+    env.reset()
+    rng = np.random.default_rng(1)
+    a = rng.uniform(-4, 4, size=(num_envs, 905)).astype(np.float32)
+    env.decode(torch.from_numpy(a).to(env.device))
+    env.sync()
+    Ug = env.tables.vemb32.shape[0]
+    got = env.vt()[:, :Ug].astype(np.float64)
+    want = a[:, 128:896].astype(np.float64) @ env.tables.vemb64.T
+    err = np.abs(got - want)
+    print("Ug", Ug, "max abs err", err.max(), "rel fro", np.linalg.norm(got - want) / np.linalg.norm(want))
+    assert err.max() < tol
+    env.close()
