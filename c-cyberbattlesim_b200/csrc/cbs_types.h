@@ -40,7 +40,8 @@ enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC
                     S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_SPARE, N_SCALARS };
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
-              FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128;
+              FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
+              FL_DIRTY = 256;  // node features / edges / node sets changed since the last encode
 // vi_flags bits (scenario.py VI_*)
 constexpr uint32_t VI_LISTENING = 1u, VI_IN_ALLOWED = 2u;
 constexpr int VI_PRIVREQ_SHIFT = 2, VI_LEVEL_ANY_SHIFT = 4, VI_LEVEL_REMOTE_SHIFT = 6;
@@ -104,7 +105,7 @@ struct State {  // mutable, device pointers
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   int32_t* errflag;      // [1]
   int32_t* worklist;     // [B] envs whose step needs graph work (edge / re-encode / episode end)
-  int32_t* work_ctr;     // [0] worklist length, [1] finished-CTA counter of the observe kernel
+  int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling)
 };
 
 __host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {

@@ -75,8 +75,6 @@ cudaError_t launch_decode_gemm_simt(const float* actions, const float* vemb, flo
 // ------------------------------------------------------------------------------------------------
 constexpr int SEL_WARPS = 4;
 
-struct RowRef { int s, t, slot, r; unsigned long long key; };
-
 __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter) {
   if ((s == t && kind == K_LATERAL) || kind == K_CREDACCESS) return true;                         // compressed:532
   if (P.remove_all && (P.goal == GOAL_CONTROL || P.goal == GOAL_DISCOVERY) && kind == K_DOS) return true;   // :536-538
@@ -84,41 +82,114 @@ __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, i
   return false;
 }
 
+// Per-lane slice of the action kept in registers for the float64 re-score: lane l owns vulnerability-part elements
+// 128*i + 4*l + j (i < 6, j < 4) and channels 2l, 2l+1 of the source / target parts.
+struct LaneAction {
+  float av[24];
+  float2 as, at;
+};
+
 // float64 cosine distance of one table row, warp-cooperative; mirrors scipy's cdist 'cosine'
 // (1 - u.v / (|u| |v|) on float64 inputs; the action is float32 widened to float64, compressed:582)
-__device__ double exact_distance(const Tables& T, const Params& P, const State& S, const float* __restrict__ act, int b,
-                                 const RowRef& rr, double na, int lane) {
-  const uint32_t packed = T.row_packed[rr.r];
+__device__ __forceinline__ double exact_distance(const Tables& T, const Params& P, const State& S, const LaneAction& A,
+                                                 const float* s_ao, int b, int s, int t, int slot, int r, double na, int lane) {
+  const uint32_t packed = T.row_packed[r];
   const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-  const float* zs = S.z_hist + (((size_t)b * P.slots + rr.slot) * P.ncap + rr.s) * NODE_EMB;
-  const float* zt = S.z_hist + (((size_t)b * P.slots + rr.slot) * P.ncap + rr.t) * NODE_EMB;
-  double dot = 0.0, ne2 = 0.0;
+  const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
+  const float2 zs = reinterpret_cast<const float2*>(S.z_hist + (zbase + s) * NODE_EMB)[lane];
+  const float2 zt = reinterpret_cast<const float2*>(S.z_hist + (zbase + t) * NODE_EMB)[lane];
+  const double2* v = reinterpret_cast<const double2*>(T.vemb64 + (size_t)u * VULN_EMB) + 2 * lane;
+  double2 vv[12];
 #pragma unroll
-  for (int i = lane; i < NODE_EMB; i += 32) {
-    const double a = act[i], z = zs[i], a2 = act[NODE_EMB + i], z2 = zt[i];
-    dot = fma(a, z, dot); ne2 = fma(z, z, ne2);
-    dot = fma(a2, z2, dot); ne2 = fma(z2, z2, ne2);
+  for (int i = 0; i < 6; ++i) { vv[2 * i] = v[64 * i]; vv[2 * i + 1] = v[64 * i + 1]; }
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    d0 = fma((double)A.av[4 * i + 0], vv[2 * i].x, d0);
+    d1 = fma((double)A.av[4 * i + 1], vv[2 * i].y, d1);
+    d2 = fma((double)A.av[4 * i + 2], vv[2 * i + 1].x, d2);
+    d3 = fma((double)A.av[4 * i + 3], vv[2 * i + 1].y, d3);
   }
-  const double* v = T.vemb64 + (size_t)u * VULN_EMB;
-  const float* av = act + 2 * NODE_EMB;
-  for (int i = lane; i < VULN_EMB; i += 32) dot = fma((double)av[i], v[i], dot);
-  dot = warp_sum(dot);
+  d0 = fma((double)A.as.x, (double)zs.x, d0);
+  d1 = fma((double)A.as.y, (double)zs.y, d1);
+  d2 = fma((double)A.at.x, (double)zt.x, d2);
+  d3 = fma((double)A.at.y, (double)zt.y, d3);
+  double ne2 = fma((double)zs.x, (double)zs.x, (double)zs.y * (double)zs.y) +
+               fma((double)zt.x, (double)zt.x, (double)zt.y * (double)zt.y);
+  double dot = warp_sum((d0 + d1) + (d2 + d3));
   ne2 = warp_sum(ne2);
-  dot += (double)act[2 * NODE_EMB + VULN_EMB + oh];
+  dot += (double)s_ao[oh];
   ne2 += T.vnorm2[u] + 1.0;
   double c = dot / (na * sqrt(ne2));
   if (fabs(c) > 1.0) c = copysign(1.0, c);
   return 1.0 - c;
 }
 
+constexpr int CAND_CAP = 8;
+
+struct SelShared {
+  float a_st[2 * NODE_EMB];   // source | target parts of the action
+  float a_o[16];
+  float p_st[32], p_n2[32];   // per staged pair: a_s.z_s + a_t.z_t (from the fp16 snapshots), |z_s|^2 + |z_t|^2 + 1
+  int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
+  uint32_t p_key[32];         // slot << 16 | owned position << 8 | discovered position
+  float c_score[CAND_CAP];    // rows still within `margin` of the running maximum, waiting for the float64 re-score
+  uint32_t c_key[CAND_CAP];
+  int c_row[CAND_CAP];
+};
+
+__device__ __forceinline__ float dot8(const uint4 h, const float* a) {
+  const __half2* q = reinterpret_cast<const __half2*>(&h);
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(q[i]);
+    acc = fmaf(f.x, a[2 * i], acc);
+    acc = fmaf(f.y, a[2 * i + 1], acc);
+  }
+  return acc;
+}
+
+struct Best {
+  double d;
+  unsigned long long key;
+  int s, t, r;
+};
+
+// re-score the pending candidates that are still within `margin` of run_max; empties the list
+__device__ __forceinline__ void flush_candidates(const Tables& T, const Params& P, const State& S, const LaneAction& A,
+                                                 SelShared& sh, int& ncand, float threshold, int b, double na, int lane,
+                                                 const uint8_t* oorder, const uint8_t* dorder, Best& best) {
+  for (int i = 0; i < ncand; ++i) {
+    if (sh.c_score[i] < threshold) continue;               // NaN scores are kept (comparison false)
+    const uint32_t k = sh.c_key[i];
+    const int r = sh.c_row[i];
+    const int slot = (int)(k >> 16), s = oorder[(k >> 8) & 0xFF], t = dorder[k & 0xFF];
+    const unsigned long long key = ((unsigned long long)k << 40) | (unsigned long long)(unsigned)r;
+    const double d = exact_distance(T, P, S, A, sh.a_o, b, s, t, slot, r, na, lane);
+    // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
+    const bool dn = d != d, bn = best.d != best.d;
+    const bool better = best.r < 0 || (dn ? (!bn || key < best.key) : (!bn && (d < best.d || (d == best.d && key < best.key))));
+    if (better) { best.d = d; best.key = key; best.s = s; best.t = t; best.r = r; }
+  }
+  ncand = 0;
+}
+
+// Table scan.  Pairs (owned source x discovered target, in insertion order) are staged 32 at a time: lane-per-pair
+// for the two 64-wide dot products against the half-precision snapshot rows, then the candidate rows of the 32
+// staged pairs are flattened over the lanes (binary search in the row-count prefix), so short and long candidate
+// lists cost the same per row.  Rows whose float32 score is within `margin` of the running maximum are parked in a
+// small list; the list is pruned as the maximum grows and its survivors are re-scored in float64 (every row
+// within `margin` of the FINAL maximum is guaranteed to be among them, because the running maximum only grows).
 __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T, Params P, State S,
                                                                       const float* __restrict__ actions, int vt_stride,
                                                                       int32_t* __restrict__ sel_out,
                                                                       double* __restrict__ dist_out) {
-  __shared__ float s_ao[SEL_WARPS][16];
+  __shared__ SelShared sh_all[SEL_WARPS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * SEL_WARPS + warp;
   if (b >= P.B) return;
+  SelShared& sh = sh_all[warp];
   const int flags = scalar(S, P, S_FLAGS, b);
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     if (lane == 0) {
@@ -130,12 +201,23 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     return;
   }
   const float* act = actions + (size_t)b * ACTION_DIM;
-  // lane l holds channels 2l, 2l+1 of the source and target parts (matches the half2 snapshot layout)
-  const float as0 = act[2 * lane], as1 = act[2 * lane + 1];
-  const float at0 = act[NODE_EMB + 2 * lane], at1 = act[NODE_EMB + 2 * lane + 1];
-  if (lane < OUTCOME_DIM) s_ao[warp][lane] = act[2 * NODE_EMB + VULN_EMB + lane];
+  LaneAction A;
   double na2 = 0.0;
-  for (int i = lane; i < ACTION_DIM; i += 32) { const double a = act[i]; na2 = fma(a, a, na2); }
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) A.av[4 * i + j] = act[2 * NODE_EMB + 128 * i + 4 * lane + j];
+  A.as = make_float2(act[2 * lane], act[2 * lane + 1]);
+  A.at = make_float2(act[NODE_EMB + 2 * lane], act[NODE_EMB + 2 * lane + 1]);
+  const float ao = lane < OUTCOME_DIM ? act[2 * NODE_EMB + VULN_EMB + lane] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) na2 = fma((double)A.av[i], (double)A.av[i], na2);
+  na2 = fma((double)A.as.x, (double)A.as.x, na2); na2 = fma((double)A.as.y, (double)A.as.y, na2);
+  na2 = fma((double)A.at.x, (double)A.at.x, na2); na2 = fma((double)A.at.y, (double)A.at.y, na2);
+  na2 = fma((double)ao, (double)ao, na2);
+  sh.a_st[2 * lane] = A.as.x; sh.a_st[2 * lane + 1] = A.as.y;
+  sh.a_st[NODE_EMB + 2 * lane] = A.at.x; sh.a_st[NODE_EMB + 2 * lane + 1] = A.at.y;
+  if (lane < 16) sh.a_o[lane] = ao;
   na2 = warp_sum(na2);
   const double na = sqrt(na2);
   __syncwarp();
@@ -150,71 +232,111 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
   const float* vt = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
 
-  // Single pass.  run_max only grows, so a row within `margin` of the final maximum is also within `margin` of
-  // run_max when it is visited: every such row is re-scored in float64 on the spot; rows that were only
-  // "records so far" cost a few extra re-scores.
   float run_max = -INFINITY;
-  double best_d = INFINITY;
-  unsigned long long best_key = ~0ull;
-  RowRef best{0, 0, 0, -1, ~0ull};
+  Best best{INFINITY, ~0ull, 0, 0, -1};
+  int ncand = 0;
 
-  for (int op = 0; op < n_owned; ++op) {
-    const int s = oorder[op];
-    for (int dp = 0; dp < n_disc; ++dp) {
-      const int t = dorder[dp];
+  const int combos = n_owned * n_disc;
+  for (int cbase = 0; cbase < combos; cbase += 32) {
+    // ---- phase A: one (source, target) combination per lane ----
+    const int c = cbase + lane;
+    bool live = false;
+    float st = 0.f, n2 = 0.f;
+    int r0 = 0, cnt = 0;
+    uint32_t key = 0;
+    if (c < combos) {
+      const int op = c / n_disc, dp = c - op * n_disc;
+      const int s = oorder[op], t = dorder[dp];
       const int slot = ps[s * P.ncap + t];
-      if (slot == 0xFF) continue;
-      const __half2* z16 = reinterpret_cast<const __half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
-      const float2 zs = __half22float2(z16[s * (NODE_EMB / 2) + lane]);
-      const float2 zt = __half22float2(z16[t * (NODE_EMB / 2) + lane]);
-      const float st = warp_sum(as0 * zs.x + as1 * zs.y + at0 * zt.x + at1 * zt.y);
-      const float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
-      const float n2 = zn[s] + zn[t] + 1.f;
-      const int g = node_off + t;
-      const int r0 = (s == t) ? T.nd_row_off[2 * g] : T.nd_row_off[2 * g + 1];
-      const int r1 = T.nd_row_off[2 * g + 2];
-      for (int base = r0; base < r1; base += 32) {
-        const int r = base + lane;
-        float score = -INFINITY;
-        bool valid = false;
-        if (r < r1) {
-          const uint32_t packed = T.row_packed[r];
-          const int kind = (packed >> 20) & 15;
-          if (!row_filtered(P, kind, s, t, starter)) {
-            const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-            score = (st + vt[u] + s_ao[warp][oh]) * rsqrtf(n2 + (float)T.vnorm2[u]);
-            valid = true;
-          }
-        }
-        float cmax = valid ? score : -INFINITY;
+      if (slot != 0xFF) {
+        const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
+        const uint4* zs = reinterpret_cast<const uint4*>(S.z16_hist + (zbase + s) * NODE_EMB);
+        const uint4* zt = reinterpret_cast<const uint4*>(S.z16_hist + (zbase + t) * NODE_EMB);
+        uint4 hs[NODE_EMB / 8], ht[NODE_EMB / 8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
-        run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
-        unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < run_max - margin_s));
-        while (cand) {
-          const int src_lane = __ffs(cand) - 1;
-          cand &= cand - 1;
-          RowRef rr;
-          rr.s = s; rr.t = t; rr.slot = slot; rr.r = base + src_lane;
-          rr.key = ((unsigned long long)slot << 56) | ((unsigned long long)op << 48) | ((unsigned long long)dp << 40) |
-                   (unsigned long long)(unsigned)rr.r;
-          const double d = exact_distance(T, P, S, act, b, rr, na, lane);
-          // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
-          const bool dn = d != d, bn = best_d != best_d;
-          const bool better = best.r < 0 || (dn ? (!bn || rr.key < best_key)
-                                                : (!bn && (d < best_d || (d == best_d && rr.key < best_key))));
-          if (better) { best = rr; best_d = d; best_key = rr.key; }
+        for (int i = 0; i < NODE_EMB / 8; ++i) { hs[i] = zs[i]; ht[i] = zt[i]; }
+        n2 = S.zn2_hist[zbase + s] + S.zn2_hist[zbase + t] + 1.f;
+        const int g = node_off + t;
+        r0 = (s == t) ? T.nd_row_off[2 * g] : T.nd_row_off[2 * g + 1];
+        cnt = T.nd_row_off[2 * g + 2] - r0;
+#pragma unroll
+        for (int i = 0; i < NODE_EMB / 8; ++i) {
+          st += dot8(hs[i], sh.a_st + 8 * i);
+          st += dot8(ht[i], sh.a_st + NODE_EMB + 8 * i);
         }
+        key = ((uint32_t)slot << 16) | ((uint32_t)op << 8) | (uint32_t)dp;
+        live = cnt > 0;
       }
     }
+    const unsigned lmask = __ballot_sync(0xFFFFFFFFu, live);
+    const int npairs = __popc(lmask);
+    if (npairs == 0) continue;
+    const int idx = __popc(lmask & ((1u << lane) - 1u));
+    if (live) { sh.p_st[idx] = st; sh.p_n2[idx] = n2; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_pre[idx + 1] = cnt; }
+    if (lane == 0) sh.p_pre[0] = 0;
+    __syncwarp();
+    int run = (lane < npairs) ? sh.p_pre[lane + 1] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, run, o);
+      if (lane >= o) run += v;
+    }
+    __syncwarp();
+    if (lane < npairs) sh.p_pre[lane + 1] = run;
+    __syncwarp();
+    const int total = sh.p_pre[npairs];
+
+    // ---- phase B: candidate rows of the staged pairs, flattened over the lanes ----
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      float score = -INFINITY;
+      bool valid = false;
+      int pi = 0, r = 0;
+      if (j < total) {
+        int lo = 0, hi = npairs;           // largest pi with p_pre[pi] <= j
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (sh.p_pre[mid] <= j) lo = mid; else hi = mid;
+        }
+        pi = lo;
+        r = sh.p_r0[pi] + (j - sh.p_pre[pi]);
+        const uint32_t packed = T.row_packed[r];
+        const int kind = (packed >> 20) & 15;
+        const uint32_t k = sh.p_key[pi];
+        const int s = oorder[(k >> 8) & 0xFF], t = dorder[k & 0xFF];
+        if (!row_filtered(P, kind, s, t, starter)) {
+          const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
+          score = (sh.p_st[pi] + vt[u] + sh.a_o[oh]) * rsqrtf(sh.p_n2[pi] + (float)T.vnorm2[u]);
+          valid = true;
+        }
+      }
+      float cmax = valid ? score : -INFINITY;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+      run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
+      unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < run_max - margin_s));
+      while (cand) {
+        const int src_lane = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (ncand == CAND_CAP) flush_candidates(T, P, S, A, sh, ncand, run_max - margin_s, b, na, lane, oorder, dorder, best);
+        const float cs = __shfl_sync(0xFFFFFFFFu, score, src_lane);
+        const int cpi = __shfl_sync(0xFFFFFFFFu, pi, src_lane);
+        const int cr = __shfl_sync(0xFFFFFFFFu, r, src_lane);
+        if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_row[ncand] = cr; }
+        ++ncand;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
   }
+  flush_candidates(T, P, S, A, sh, ncand, run_max - margin_s, b, na, lane, oorder, dorder, best);
   if (lane == 0) {
     int4 out = make_int4(starter, starter, 0, 0);
     double d = 1.0;
     if (best.r >= 0) {
       const uint32_t packed = T.row_packed[best.r];
       out = make_int4(best.s, best.t, T.vi_ulocal[T.row_inst[best.r]], (int)((packed >> 20) & 15));
-      d = best_d;
+      d = best.d;
     } else {
       atomicExch(S.errflag, 3);   // empty action table: outside the reference's domain (cdist would raise)
     }

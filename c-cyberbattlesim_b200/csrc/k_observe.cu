@@ -11,6 +11,8 @@
 // message is a 17-term combination of those rows with [ReLU(W1 e + b1); 1].  GCNConv is a 64x64 projection
 // (weights staged once per CTA in shared memory) followed by the degree-normalised neighbour sum.  Node
 // embeddings of one env live in shared memory (<= 32 nodes) or in an L2-resident scratch slab (<= 128 nodes).
+#include <cstdlib>
+
 #include "cbs_device.cuh"
 #include "philox.cuh"
 
@@ -31,16 +33,25 @@ struct WarpScratch {
   float* g;           // [n][64]
   float* dinv;        // [ncap]
   uint8_t* pos;       // [MAX_NODES] node id -> position in discovered order
+  uint8_t* dynb;      // [MAX_NODES] per position: visible | persistence<<1 | collected<<2 | exfiltrated<<3 | evasion<<4 | privilege<<5 | running<<7
 };
 
-__device__ __forceinline__ void node_dyn(const State& S, const Params& P, int b, int node, float& vis, float x[NUM_DYN]) {
-  vis = bit_of(S, P, M_VISIBLE, node, b) ? 1.f : 0.f;
-  x[0] = bit_of(S, P, M_PERSISTENCE, node, b) ? 1.f : 0.f;
-  x[1] = bit_of(S, P, M_COLLECTED, node, b) ? 1.f : 0.f;
-  x[2] = bit_of(S, P, M_EXFILTRATED, node, b) ? 1.f : 0.f;
-  x[3] = bit_of(S, P, M_EVASION, node, b) ? 1.f : 0.f;
-  x[4] = bit_of(S, P, M_PRIV_ROOT, node, b) ? 3.f : (bit_of(S, P, M_PRIV_USER, node, b) ? 1.f : 0.f);
-  x[5] = bit_of(S, P, M_STOPPED, node, b) ? 0.f : 1.f;    // MachineStatus value: Stopped 0, Running 1
+// the dynamic part of a node's feature vector (compressed:365-380), packed once per encode by lane-per-node
+__device__ __forceinline__ uint8_t pack_dyn(const State& S, const Params& P, int b, int node) {
+  const int w = node >> 5, sh = node & 31;
+  auto bit = [&](int plane) -> uint32_t { return (ld_mask(S, P, plane, w, b) >> sh) & 1u; };
+  const uint32_t priv = bit(M_PRIV_ROOT) ? 3u : bit(M_PRIV_USER);
+  return (uint8_t)(bit(M_VISIBLE) | (bit(M_PERSISTENCE) << 1) | (bit(M_COLLECTED) << 2) | (bit(M_EXFILTRATED) << 3) |
+                   (bit(M_EVASION) << 4) | (priv << 5) | ((bit(M_STOPPED) ^ 1u) << 7));
+}
+__device__ __forceinline__ void node_dyn(uint8_t d, float& vis, float x[NUM_DYN]) {
+  vis = (float)(d & 1);
+  x[0] = (float)((d >> 1) & 1);
+  x[1] = (float)((d >> 2) & 1);
+  x[2] = (float)((d >> 3) & 1);
+  x[3] = (float)((d >> 4) & 1);
+  x[4] = (float)((d >> 5) & 3);     // privilege level 0 / 1 / 3
+  x[5] = (float)((d >> 7) & 1);     // MachineStatus value: Stopped 0, Running 1
 }
 
 // ---- add_edge_evolving_visible_graph (compressed:214-246), mean aggregation, in the W1-projected space ----
@@ -97,14 +108,19 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   const int c0 = lane, c1 = lane + 32;
   constexpr int ROW = PROJ_ROWS * NODE_EMB;   // floats per (node, part)
 
-  for (int i = lane; i < n; i += 32) { W.pos[order[i]] = (uint8_t)i; W.dinv[i] = 1.f; }
+  for (int i = lane; i < n; i += 32) {
+    const int node = order[i];
+    W.pos[node] = (uint8_t)i;
+    W.dinv[i] = 1.f;
+    W.dynb[i] = pack_dyn(S, P, b, node);
+  }
   __syncwarp();
 
   // root term x_i W_root (+ conv bias folded into bn1 shift)
   for (int i = 0; i < n; ++i) {
     const int node = order[i];
     float vis, x[NUM_DYN];
-    node_dyn(S, P, b, node, vis, x);
+    node_dyn(W.dynb[i], vis, x);
     const float* ns = T.node_static + (size_t)(node_off + node) * 2 * ROW + 17 * NODE_EMB;
     float a0 = ns[c0] + vis * ns[ROW + c0], a1 = ns[c1] + vis * ns[ROW + c1];
 #pragma unroll
@@ -127,7 +143,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     if (lane < NN_CH) hl = fmaxf(S.edge_m[((size_t)b * P.ecap + e) * NN_CH + lane] + SW.nn0b[lane], 0.f);
     else if (lane == NN_CH) hl = 1.f;
     float vis, x[NUM_DYN];
-    node_dyn(S, P, b, js, vis, x);
+    node_dyn(W.dynb[is], vis, x);
     const float* ns = T.node_static + (size_t)(node_off + js) * 2 * ROW;
     float m0 = 0.f, m1 = 0.f;
 #pragma unroll
@@ -198,7 +214,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     const float z1 = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn2s[c1], SW.bn2h[c1]), 0.f);
     W.y[i * NODE_EMB + c0] = z0;
     W.y[i * NODE_EMB + c1] = z1;
-    if (!bit_of(S, P, M_STOPPED, order[i], b)) {
+    if (W.dynb[i] & 0x80) {
       ++running;
       s0 += z0; s1 += z1;
       mx0 = fmaxf(mx0, z0); mx1 = fmaxf(mx1, z1);
@@ -232,13 +248,13 @@ __device__ void build_table(const Params& P, const State& S, WarpScratch& W, int
   bool any_new = false;
   for (int op = 0; op < n_owned; ++op) {
     const int s = oorder[op];
-    if (bit_of(S, P, M_STOPPED, s, b)) continue;
+    if (!(W.dynb[W.pos[s]] & 0x80)) continue;               // stopped sources add no rows (compressed:491-492)
     for (int base = 0; base < n_disc; base += 32) {
       const int dp = base + lane;
       bool fresh = false;
       if (dp < n_disc) {
         const int t = dorder[dp];
-        fresh = !bit_of(S, P, M_STOPPED, t, b) && ps[s * P.ncap + t] == 0xFF;
+        fresh = (W.dynb[dp] & 0x80) && ps[s * P.ncap + t] == 0xFF;
         if (fresh && slot < P.slots) ps[s * P.ncap + t] = (uint8_t)slot;
       }
       any_new |= __any_sync(0xFFFFFFFFu, fresh);
@@ -251,7 +267,7 @@ __device__ void build_table(const Params& P, const State& S, WarpScratch& W, int
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
   for (int i = 0; i < n_disc; ++i) {
     const int node = dorder[i];
-    if (bit_of(S, P, M_STOPPED, node, b)) continue;      // only Running nodes have embeddings (compressed:266-280)
+    if (!(W.dynb[i] & 0x80)) continue;                   // only Running nodes have embeddings (compressed:266-280)
     const float2 z = reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane];   // channels 2*lane, 2*lane+1
     reinterpret_cast<float2*>(zh + node * NODE_EMB)[lane] = z;
     zh16[node * (NODE_EMB / 2) + lane] = __floats2half2_rn(z.x, z.y);
@@ -375,8 +391,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 
   // per-warp scratch
   unsigned char* wbase = smem_raw + sizeof(SharedWeights);
-  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + MAX_NODES;
-  constexpr size_t kWarpBytesGlob = (size_t)MAX_NODES * 4 + MAX_NODES;
+  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
+  constexpr size_t kWarpBytesGlob = (size_t)MAX_NODES * 4 + 2 * MAX_NODES;
   WarpScratch W;
   if (SMEM_BUF) {
     unsigned char* p = wbase + (size_t)warp * kWarpBytesSmem;
@@ -384,17 +400,25 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     W.g = W.y + SMEM_NODES * NODE_EMB;
     W.dinv = W.g + SMEM_NODES * NODE_EMB;
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
+    W.dynb = W.pos + MAX_NODES;
   } else {
     unsigned char* p = wbase + (size_t)warp * kWarpBytesGlob;
     W.dinv = reinterpret_cast<float*>(p);
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
+    W.dynb = W.pos + MAX_NODES;
     W.y = W.g = nullptr;
   }
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
   // transition kernel put on the worklist — the others keep their cached observation untouched.
   const int count = (mode == 1) ? P.B : S.work_ctr[0];
-  for (int i = gw; i < count; i += total_warps) {
+  int i = gw;                                   // mode 1: static stride.  mode 0: items are claimed one at a time
+  for (;;) {
+    if (mode == 0) {
+      if (lane == 0) i = atomicAdd(&S.work_ctr[2], 1);
+      i = __shfl_sync(0xFFFFFFFFu, i, 0);
+    }
+    if (i >= count) break;
     const int b = (mode == 1) ? i : S.worklist[i];
     if (!SMEM_BUF) {
       W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
@@ -405,17 +429,19 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     if (mode == 1) {
       do_reset = reset_mask ? (reset_mask[b] != 0) : true;
     } else if (!(flags & FL_NEEDS_RESET)) {
+      int keep = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
       if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
       if (flags & FL_REENCODE) {
         encode_env(T, P, S, SW, W, b, lane);
         build_table(P, S, W, b, lane);
+        keep &= ~FL_DIRTY;
       }
       if (flags & FL_FINISHED_THIS_STEP) {
         finish_episode(T, P, S, b, lane);
         if (P.auto_reset) do_reset = true;
       }
       __syncwarp();
-      if (lane == 0) scalar(S, P, S_FLAGS, b) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+      if (lane == 0) scalar(S, P, S_FLAGS, b) = keep;
       __syncwarp();
     }
     if (do_reset) {
@@ -424,25 +450,27 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       build_table(P, S, W, b, lane);
     }
     __syncwarp();
+    if (mode == 1) i += total_warps;
   }
-  if (mode == 0) {   // the last CTA to finish clears the worklist for the next transition
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  if (mode == 0 && lane == 0) {   // the last warp to run dry clears the counters for the next transition
+    __threadfence();
+    if (atomicAdd(&S.work_ctr[1], 1) == total_warps - 1) {
+      S.work_ctr[0] = 0; S.work_ctr[1] = 0; S.work_ctr[2] = 0;
       __threadfence();
-      if (atomicAdd(&S.work_ctr[1], 1) == (int)gridDim.x - 1) { S.work_ctr[0] = 0; S.work_ctr[1] = 0; __threadfence(); }
     }
   }
 }
 
 size_t observe_smem_bytes(bool smem_buf) {
-  const size_t per_warp = smem_buf ? ((size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + MAX_NODES)
-                                   : ((size_t)MAX_NODES * 4 + MAX_NODES);
+  const size_t per_warp = smem_buf ? ((size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES)
+                                   : ((size_t)MAX_NODES * 4 + 2 * MAX_NODES);
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 
 cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, int mode,
                            int num_sms, cudaStream_t stream) {
-  const bool smem_buf = P.ncap <= SMEM_NODES;
+  static const bool force_global = getenv("CBS_OBS_GLOBAL") != nullptr;   // experiment switch
+  const bool smem_buf = P.ncap <= SMEM_NODES && !force_global;
   const size_t smem = observe_smem_bytes(smem_buf);
   // persistent grid: one CTA per SM when the node buffers live in shared memory (181 KB), four otherwise
   int grid = num_sms * (smem_buf ? 1 : 4);

@@ -233,8 +233,13 @@ __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, Sta
   SC(S_NUM_ITER) = num_iter + 1;                                 // :394
   SC(S_OUTCOME) = code;
 
+  // A re-encode of an unchanged graph reproduces the cached embeddings bit for bit, so it is skipped: `dirty`
+  // records whether any node feature, edge or node set changed since the last encode (successful outcomes mutate
+  // the target or the discovered set; reward > 0 adds / updates an edge).
+  const bool dirty = (flags & FL_DIRTY) || code < 16 || add_edge;
+  const bool encode_now = reencode && dirty;
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
-          (reencode ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0);
+          (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0);
   SC(S_FLAGS) = flags;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
     const int slot = atomicAdd(&S.work_ctr[0], 1);
