@@ -8,4 +8,18 @@ from .scenario import (ScenarioSpec, NodeSpec, VulnSpec, ResultSpec, ServiceSpec
                        compile_scenarios, spec_from_model, synthetic_spec, synthetic_input_graph,
                        spec_from_input_graph, synthetic_vuln_pool)
 
+from .gae import GaeWeights, fold_gae  # noqa: F401,E402
+
+
+def __getattr__(name):
+    # torch-dependent modules are imported lazily so that `import ccbs_b200` stays cheap
+    if name in ("BatchedCyberBattleEnv", "CbsError"):
+        from . import batched_env
+        return getattr(batched_env, name)
+    if name in ("CyberBattleVecEnv", "RandomSwitchEnvB200"):
+        from . import vec_env
+        return getattr(vec_env, name)
+    raise AttributeError(name)
+
+
 __version__ = "0.1.0"
