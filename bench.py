@@ -136,6 +136,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram read+write bytes per launch of `kernel` from the last committed `ncu --set full` capture
+    (profiles/traffic.json, written by tools/summarize_ncu.py); None if that kernel was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel)
+
+
 def run_reference(args, wl_key, rank):
     """--impl reference: the CPU restatement of the same path on all host cores (rank 0 only)."""
     if rank != 0:
@@ -283,24 +293,13 @@ def main():
     h2d = B * C.ACTION_DIM * 4
     d2h = B * ((C.OBS_DIM + 2) * 4 + 4 + 1)
 
-    # ---- per-kernel durations (split calls, CUDA events on the launching stream) ----
-    kern = {"decode": 0.0, "transition": 0.0, "observe": 0.0}
+    # ---- per-kernel durations: CUDA events between the launches, on the launching stream (cbs_profile_step) ----
     n_prof = min(50, args.steps)
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    kern = {}
     for i in range(n_prof):
-        a = ring[i % R]
-        evs[0].record()
-        sel, dd = env.decode(a)
-        evs[1].record()
-        env.transition(sel, dd, None)
-        evs[2].record()
-        env.observe()
-        evs[3].record()
-        torch.cuda.synchronize()
-        kern["decode"] += evs[0].elapsed_time(evs[1])
-        kern["transition"] += evs[1].elapsed_time(evs[2])
-        kern["observe"] += evs[2].elapsed_time(evs[3])
-    kern = {k: v / n_prof for k, v in kern.items()}   # ms per launch group
+        ms_k = env.profile_step(ring[i % R])
+        for k, v in ms_k.items():
+            kern[k] = kern.get(k, 0.0) + v / n_prof
     env.sync()
 
     if rank == 0:
@@ -310,14 +309,18 @@ def main():
         Ug = env.tables.vemb32.shape[0]
         sc = env.scalars()
         pairs = float(np.mean(sc[5] * sc[4]))                       # n_owned * n_disc  (upper bound of table pairs)
+        rows = pairs * 24.0                                         # ~24 candidate rows per pair (tools/workload_stats.py)
         alg = {
-            "decode": B * (C.ACTION_DIM * 4 + 2 * 4 * Ug + pairs * (2 * 256 + 9) + 20) + Ug * 768 * 4,
+            # A_v read (+ the aligned repack write/read on the tensor-core path) + Vemb + VT write
+            "decode_gemm": B * 768 * 4 * (3 if env.tensor_core_decode else 1) + Ug * 768 * 4 + B * Ug * 4,
+            # action read + VT row read + per pair two half-precision snapshot rows + norms, per row 16 B of table
+            "decode_select": B * (C.ACTION_DIM * 4 + 4 * Ug + pairs * (2 * 128 + 9) + rows * 16 + 28),
             "transition": B * 220.0,
-            "observe": B * (776.0 + 10240.0 / 3.0),
+            "observe": B * 0.45 * 10240.0,
         }
         dom = max(kern, key=kern.get)
         roof = {"bound": "hbm", "kernel": dom, "achieved": alg[dom] / (kern[dom] * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "peak_source": peak_src, "traffic": None,
+                "unit": "GB/s", "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "kernels_ms": kern, "kernels_gbs": {k: alg[k] / (kern[k] * 1e-3) / 1e9 for k in kern}}
         roof["frac"] = roof["achieved"] / peak
         acc = env.stat_accum()

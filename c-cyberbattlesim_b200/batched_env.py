@@ -146,6 +146,13 @@ class BatchedCyberBattleEnv:
                                       self._p(self.done), self._p(self.info) if want_info else None, self._stream()))
         return self.obs, self.reward, self.done, self.info
 
+    def profile_step(self, actions: torch.Tensor) -> dict:
+        """One step with CUDA events between the launches; returns milliseconds per kernel group."""
+        actions = self._actions(actions)
+        out = (ct.c_float * 5)()
+        self._check(self.lib.cbs_profile_step(self._h, self._p(actions), None, out, self._stream()))
+        return {"decode_gemm": out[0] + out[1], "decode_select": out[2], "transition": out[3], "observe": out[4]}
+
     def step_host(self, actions: np.ndarray, uniforms: Optional[np.ndarray], obs: np.ndarray, reward: np.ndarray,
                   done: np.ndarray, info: Optional[np.ndarray] = None):
         """The same step through HOST buffers (numpy, ideally pinned): copies in, steps, copies out, synchronises."""

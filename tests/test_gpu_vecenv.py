@@ -1,0 +1,60 @@
+"""-m gpu: the SB3-VecEnv-shaped adapter and the single-env gymnasium-shaped wrapper."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vec_env_protocol():
+    import ccbs_b200 as cb
+    from ccbs_b200.vec_env import CyberBattleVecEnv
+    specs = [cb.synthetic_spec(500 + k, 10) for k in range(3)]
+    benv = cb.BatchedCyberBattleEnv(specs, cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=24, seed=3)
+    venv = CyberBattleVecEnv(benv)
+    obs = venv.reset()
+    assert obs["graph_embeddings"].shape == (24, 192) and obs["discrete_features"].shape == (24, 2)
+    assert obs["graph_embeddings"].dtype == np.float64 and np.all(obs["discrete_features"] == 1)
+    rng = np.random.default_rng(0)
+    episodes, ret = 0, np.zeros(24)
+    for t in range(40):
+        a = rng.uniform(-4, 4, size=(24, 905)).astype(np.float32)
+        obs, rew, done, infos = venv.step(a)
+        assert rew.shape == (24,) and done.dtype == bool and len(infos) == 24
+        ret += rew
+        for b in range(24):
+            i = infos[b]
+            assert i["source_node"] in benv.tables.node_ids[benv.scenario_of_env[b]]
+            assert i["vulnerability_type"] in ("local", "remote") and i["outcome"] is not None
+            if done[b]:
+                episodes += 1
+                assert i["terminal_observation"]["graph_embeddings"].shape == (192,)
+                assert i["TimeLimit.truncated"] is False and i["end_episode_reason"] in (1, 2, 3)
+                assert len(i["episode_stats"]) == 14 and i["episode_stats"][4] == 10
+                assert abs(i["episode"]["r"] - ret[b]) < 1e-2 * max(1.0, abs(ret[b])) and i["episode"]["l"] >= 1
+                ret[b] = 0
+                assert obs["discrete_features"][b, 0] == 1          # already reset
+    assert episodes > 24
+    stats = venv.env_method("get_statistics")
+    assert len(stats) == 24 and len(stats[0]) == 14
+    assert venv.env_is_wrapped(object) == [False] * 24
+    venv.close()
+
+
+def test_single_env_wrapper_raises_after_done():
+    import ccbs_b200 as cb
+    from ccbs_b200.vec_env import RandomSwitchEnvB200
+    env = RandomSwitchEnvB200([cb.synthetic_spec(7, 9)], cb.GaeWeights.random(0), cb.EnvConfig())
+    obs, info = env.reset()
+    assert obs["graph_embeddings"].shape == (192,) and info == {}
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        obs, r, done, trunc, info = env.step(rng.uniform(-4, 4, size=905).astype(np.float32))
+        assert 0.0 <= info["min_distance_action"] <= 2.0
+        if done:
+            break
+    assert done and len(env.get_statistics()) == 14
+    with pytest.raises(RuntimeError):
+        env.step(np.zeros(905, np.float32))
+    obs, _ = env.reset()
+    assert obs["discrete_features"][0] == 1
+    env.close()
