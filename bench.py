@@ -186,6 +186,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--decode-gemm", type=int, default=0)
+    ap.add_argument("--action-pitch", type=int, default=905,
+                    help="row pitch (floats) of the device-resident action batches; 905 = dense like the reference's "
+                         "action array, 908 lets TMA read them in place (no repack kernel)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,7 +232,7 @@ def main():
     R = max(2, int(np.ceil(160e6 / (B * C.ACTION_DIM * 4))))
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
-    ring = (torch.rand(R, B, C.ACTION_DIM, device=dev, generator=gen) * 8.0 - 4.0).contiguous()
+    ring = (torch.rand(R, B, args.action_pitch, device=dev, generator=gen) * 8.0 - 4.0).contiguous()[:, :, :C.ACTION_DIM]
     env.reset()
     env.sync()
 
@@ -273,7 +276,7 @@ def main():
     # ---- end-to-end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region) ----
     h_ring = [torch.empty(B, C.ACTION_DIM, dtype=torch.float32).pin_memory() for _ in range(2)]
     for k in range(2):
-        h_ring[k].copy_(ring[k].cpu())
+        h_ring[k].copy_(ring[k].cpu().contiguous())
     h_obs = torch.empty(B, C.OBS_DIM + 2, dtype=torch.float32).pin_memory()
     h_rew = torch.empty(B, dtype=torch.float32).pin_memory()
     h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
@@ -329,6 +332,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bitmasks + f32 GAE + f64 decode re-score", "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": B, "scenarios": wl["scenarios"], "global_vulns": int(Ug),
+                       "action_pitch_floats": args.action_pitch,
                        "actions": f"ring of {R} x [{B},905] f32 batches = {R * B * 905 * 4 / 1e6:.0f} MB (> 126 MB L2), no L2 flush",
                        "decode_gemm": "tcgen05-tf32" if env.tensor_core_decode else "simt-f32",
                        "state_gb": env.state_bytes / 1e9},

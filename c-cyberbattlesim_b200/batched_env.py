@@ -56,6 +56,7 @@ class BatchedCyberBattleEnv:
         self.ncap, self.slots, self.ecap, self.tensor_core_decode = caps[0], caps[1], caps[2], bool(caps[3])
         self.vt_stride = caps[4]
         B = self.num_envs
+        self._act_stride = C.ACTION_DIM
         with torch.cuda.device(self.device):
             # zero-copy view of the library's observation cache [B, 194]
             self.obs = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_OBS), (B, C.OBS_DIM + 2), torch.float32,
@@ -161,9 +162,17 @@ class BatchedCyberBattleEnv:
         self._check(self.lib.cbs_step_host(self._h, v(actions), v(uniforms), v(obs), v(reward), v(done), v(info)))
 
     def _actions(self, actions):
+        """Accepts a dense [B, 905] tensor or a [B, 905] view of a wider row-pitched buffer (stride(0) >= 905,
+        stride(1) == 1); the pitch is forwarded so that a 16-byte-multiple pitch is read in place by TMA."""
         if actions.shape != (self.num_envs, C.ACTION_DIM):
             raise ValueError(f"actions must have shape ({self.num_envs}, {C.ACTION_DIM})")
-        return actions.to(device=self.device, dtype=torch.float32).contiguous()
+        actions = actions.to(device=self.device, dtype=torch.float32)
+        if actions.stride(1) != 1 or actions.stride(0) < C.ACTION_DIM:
+            actions = actions.contiguous()
+        if actions.stride(0) != self._act_stride:
+            self._act_stride = int(actions.stride(0))
+            self._check(self.lib.cbs_set_action_stride(self._h, self._act_stride))
+        return actions
 
     def _uniforms(self, uniforms):
         if uniforms is None:

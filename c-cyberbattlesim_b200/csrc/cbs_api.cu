@@ -9,8 +9,8 @@
 #include "cbs_types.h"
 
 namespace cbs {
-cudaError_t launch_decode_gemm_simt(const float*, const float*, float*, int, int, int, cudaStream_t);
-cudaError_t launch_decode_gemm_tc(const float*, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
+cudaError_t launch_decode_gemm_simt(const float*, int, const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
 bool decode_gemm_tc_available();
 cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int32_t*, double*, cudaStream_t);
 cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, int, int, cudaStream_t);
@@ -145,6 +145,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   for (int i = 0; i < N_REWARDS; ++i) P.rew[i] = cfg->rewards[i];
   for (int i = 0; i < N_PENALTIES; ++i) P.pen[i] = cfg->penalties[i];
   P.qlen = 0;
+  P.act_stride = ACTION_DIM;
   *out = h;
   return CBS_OK;
 }
@@ -263,6 +264,13 @@ int cbs_set_starter_queue(cbs_handle* h, const int32_t* q, int32_t qlen) {
   return CBS_OK;
 }
 
+int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  if (stride_floats < ACTION_DIM) return fail(h, CBS_ERR_INVALID_ARG, "action stride must be >= %d floats", ACTION_DIM);
+  h->P.act_stride = stride_floats;
+  return CBS_OK;
+}
+
 int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double prop) {
   if (!h) return CBS_ERR_INVALID_ARG;
   h->P.episode_iterations = episode_iterations;
@@ -293,10 +301,10 @@ int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double
   if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_decode: actions is null");
   cudaStream_t st = (cudaStream_t)stream;
   if (h->use_tc) {
-    CK(h, launch_decode_gemm_tc(actions_dev, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
     h->launches += 2;
   } else {
-    CK(h, launch_decode_gemm_simt(actions_dev, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
     h->launches += 1;
   }
   CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, sel_dev, dist_dev, st));
@@ -350,12 +358,12 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
   CK(h, cudaEventRecord(ev[0], st));
   if (h->use_tc) {
     // the tensor-core path is two launches; time them separately by splitting the helper's work
-    CK(h, launch_decode_gemm_tc(actions_dev, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
     CK(h, cudaEventRecord(ev[1], st));   // (pack + gemm together; split below by a second, gemm-only launch)
     CK(h, cudaEventRecord(ev[2], st));
   } else {
     CK(h, cudaEventRecord(ev[1], st));
-    CK(h, launch_decode_gemm_simt(actions_dev, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
     CK(h, cudaEventRecord(ev[2], st));
   }
   CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->d_sel, h->d_dist, st));
@@ -392,10 +400,15 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
   if ((rc = ensure_host_staging(h))) return rc;
   const size_t B = h->P.B;
   cudaStream_t st = h->hstream;
+  // one dense copy: a pitched (2-D) host-to-device copy of 3620-byte rows runs at less than half the PCIe rate
+  // (measured 4.4 M vs 9.5 M env-steps/s end to end), which costs more than the repack kernel it would save
   CK(h, cudaMemcpyAsync(h->h_actions, actions_host, B * ACTION_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int saved_stride = h->P.act_stride;
+  h->P.act_stride = ACTION_DIM;
   if (uniforms_host) CK(h, cudaMemcpyAsync(h->h_uniforms, uniforms_host, B * sizeof(float), cudaMemcpyHostToDevice, st));
   rc = cbs_step(h, h->h_actions, uniforms_host ? h->h_uniforms : nullptr, nullptr, h->h_reward, h->h_done,
                 info_host ? h->h_info : nullptr, (uintptr_t)st);
+  h->P.act_stride = saved_stride;
   if (rc) return rc;
   if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->S.obs, B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -76,6 +76,7 @@ struct Params {  // configuration, by value
   double rew[N_REWARDS], pen[N_PENALTIES];
   float margin;
   int qlen;
+  int act_stride;   // row pitch (floats) of the action tensors handed to decode; 905 = dense
 };
 
 struct State {  // mutable, device pointers

@@ -20,8 +20,9 @@ namespace cbs {
 // ------------------------------------------------------------------------------------------------
 constexpr int GT_M = 64, GT_N = 64, GT_K = 16;
 
-__global__ void __launch_bounds__(256) decode_gemm_simt_kernel(const float* __restrict__ actions, const float* __restrict__ vemb,
-                                                               float* __restrict__ vt, int B, int Ug, int vt_stride) {
+__global__ void __launch_bounds__(256) decode_gemm_simt_kernel(const float* __restrict__ actions, int act_stride,
+                                                               const float* __restrict__ vemb, float* __restrict__ vt, int B, int Ug,
+                                                               int vt_stride) {
   __shared__ float As[GT_K][GT_M + 1];
   __shared__ float Bs[GT_K][GT_N + 1];
   const int m0 = blockIdx.x * GT_M, n0 = blockIdx.y * GT_N;
@@ -31,7 +32,7 @@ __global__ void __launch_bounds__(256) decode_gemm_simt_kernel(const float* __re
     for (int i = threadIdx.x; i < GT_M * GT_K; i += 256) {
       const int r = i / GT_K, k = i % GT_K;
       const int m = m0 + r;
-      As[k][r] = m < B ? actions[(size_t)m * ACTION_DIM + 2 * NODE_EMB + k0 + k] : 0.f;
+      As[k][r] = m < B ? actions[(size_t)m * act_stride + 2 * NODE_EMB + k0 + k] : 0.f;
     }
     for (int i = threadIdx.x; i < GT_N * GT_K; i += 256) {
       const int r = i / GT_K, k = i % GT_K;
@@ -63,10 +64,10 @@ __global__ void __launch_bounds__(256) decode_gemm_simt_kernel(const float* __re
   }
 }
 
-cudaError_t launch_decode_gemm_simt(const float* actions, const float* vemb, float* vt, int B, int Ug, int vt_stride,
-                                    cudaStream_t stream) {
+cudaError_t launch_decode_gemm_simt(const float* actions, int act_stride, const float* vemb, float* vt, int B, int Ug,
+                                    int vt_stride, cudaStream_t stream) {
   dim3 grid((B + GT_M - 1) / GT_M, (Ug + GT_N - 1) / GT_N);
-  decode_gemm_simt_kernel<<<grid, 256, 0, stream>>>(actions, vemb, vt, B, Ug, vt_stride);
+  decode_gemm_simt_kernel<<<grid, 256, 0, stream>>>(actions, act_stride, vemb, vt, B, Ug, vt_stride);
   return cudaGetLastError();
 }
 
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     }
     return;
   }
-  const float* act = actions + (size_t)b * ACTION_DIM;
+  const float* act = actions + (size_t)b * P.act_stride;
   LaneAction A;
   double na2 = 0.0;
 #pragma unroll

@@ -9,10 +9,13 @@
 // Shape: one CTA per 128 envs x (<=256) vulnerabilities; K = 768 in 24 slabs of 32 floats (= one 128-byte
 // swizzle row), 4-stage TMA -> smem ring; warp 0 lane 0 issues TMA, warp 1 lane 0 issues 4 UMMAs (K = 8) per
 // slab and commits to the ring's empty barriers; all four warps drain the 128 x N accumulator from TMEM with
-// tcgen05.ld.32x32b and store float4 rows.  The action tensor's rows are 3620 bytes apart (not a multiple of
-// 16), which TMA cannot address, so pack_actions first copies the 768-float slice into an aligned [B,768] slab.
+// tcgen05.ld.32x32b and store float4 rows.  A dense [B,905] action tensor has rows 3620 bytes apart (not a
+// multiple of 16), which TMA cannot address, so pack_actions first copies the 768-float slice into an aligned
+// [B,768] slab; with a 16-byte-multiple row pitch (cbs_set_action_stride) TMA reads in place.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+
+#include <cstdlib>
 
 #include "cbs_types.h"
 
@@ -77,10 +80,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restrict__ actions, float* __restrict__ packed, int B) {
+__global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restrict__ actions, float* __restrict__ packed, int B,
+                                                           int act_stride) {
   const int row = blockIdx.x * 2 + (threadIdx.x >> 7);
   if (row >= B) return;
-  const float* src = actions + (size_t)row * ACTION_DIM + 2 * NODE_EMB;
+  const float* src = actions + (size_t)row * act_stride + 2 * NODE_EMB;
   float* dst = packed + (size_t)row * VULN_EMB;
   for (int i = threadIdx.x & 127; i < VULN_EMB; i += 128) dst[i] = src[i];
 }
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restri
 __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                 const __grid_constant__ CUtensorMap map_b,
                                                                 float* __restrict__ vt, int B, int Upad, int nt_box,
-                                                                int vt_stride, int32_t* errflag) {
+                                                                int vt_stride, int32_t* errflag, int direct) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = A_STAGE_BYTES + nt_box * BK * 4;
@@ -125,7 +129,9 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
       if (!mbar_wait(empty0 + 8 * s, ph ^ 1, errflag)) break;
       mbar_expect_tx(full0 + 8 * s, bytes);
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
-      tma_load_2d(sa, &map_a, full0 + 8 * s, kb * BK, m0);
+      // direct: map_a is the caller's action tensor itself (row pitch a multiple of 16 bytes), the 768-float
+      // vulnerability part starts 128 floats into each row; otherwise map_a is the repacked [B,768] slab
+      tma_load_2d(sa, &map_a, full0 + 8 * s, (direct ? 2 * NODE_EMB : 0) + kb * BK, m0);
       tma_load_2d(sa + A_STAGE_BYTES, &map_b, full0 + 8 * s, kb * BK, n0);
     }
   } else if (warp == 1 && lane == 0) {
@@ -205,9 +211,10 @@ bool decode_gemm_tc_available() {
   return major == 10 && load_encode();
 }
 
-static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows) {
-  const cuuint64_t dims[2] = {(cuuint64_t)VULN_EMB, (cuuint64_t)rows};
-  const cuuint64_t strides[1] = {(cuuint64_t)VULN_EMB * sizeof(float)};
+static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_t box_rows, uint64_t pitch_floats = VULN_EMB,
+                     uint64_t row_floats = VULN_EMB) {
+  const cuuint64_t dims[2] = {(cuuint64_t)row_floats, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch_floats * sizeof(float)};
   const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -215,17 +222,24 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-cudaError_t launch_decode_gemm_tc(const float* actions, const float* vemb, float* a_packed, float* vt, int B, int Ug,
-                                  int vt_stride, int32_t* errflag, cudaStream_t stream) {
+cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const float* vemb, float* a_packed, float* vt, int B,
+                                  int Ug, int vt_stride, int32_t* errflag, cudaStream_t stream) {
   if (!load_encode()) return cudaErrorNotSupported;
   const int Upad = ((Ug + 15) / 16) * 16;
   const int nt_box = Upad < NT_MAX ? Upad : NT_MAX;
   // tensor maps are rebuilt per launch (host-side encode, ~1 us each): the operands never move, but keeping the
   // maps out of the handle keeps this translation unit self-contained
   CUtensorMap map_a, map_b;
-  if (!make_map(&map_a, a_packed, (uint64_t)B, BM) || !make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box))
-    return cudaErrorInvalidValue;
-  pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B);
+  // Direct mode: TMA reads the action tensor in place when its row pitch is a multiple of 16 bytes (e.g. 908 floats).  A dense [B,905] tensor has 3620-byte rows, which
+  // TMA cannot address (an unaligned box start faults as an illegal instruction), so it is repacked first.
+  const bool direct = (act_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(actions) & 15) == 0);
+  if (direct) {
+    if (!make_map(&map_a, actions, (uint64_t)B, BM, (uint64_t)act_stride, (uint64_t)ACTION_DIM)) return cudaErrorInvalidValue;
+  } else {
+    if (!make_map(&map_a, a_packed, (uint64_t)B, BM)) return cudaErrorInvalidValue;
+    pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B, act_stride);
+  }
+  if (!make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)nt_box * BK * 4) + 1024 + 256;
   static size_t attr = 0;
   if (smem > attr) {
@@ -234,7 +248,7 @@ cudaError_t launch_decode_gemm_tc(const float* actions, const float* vemb, float
     attr = smem;
   }
   dim3 grid((B + BM - 1) / BM, (Upad + NT_MAX - 1) / NT_MAX);
-  decode_gemm_tc_kernel<<<grid, 128, smem, stream>>>(map_a, map_b, vt, B, Upad, nt_box, vt_stride, errflag);
+  decode_gemm_tc_kernel<<<grid, 128, smem, stream>>>(map_a, map_b, vt, B, Upad, nt_box, vt_stride, errflag, direct ? 1 : 0);
   return cudaGetLastError();
 }
 

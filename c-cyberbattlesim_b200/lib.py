@@ -52,7 +52,7 @@ class CbsGaeTables(ct.Structure):
 
 # every symbol include/cbsim.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
-           "cbs_set_starter_queue", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
+           "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
            "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_read_state", "cbs_state_ptr", "cbs_reset_stat_accum", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
 
@@ -105,6 +105,7 @@ def load_library():
     lib.cbs_set_scenarios.argtypes = [H, P]
     lib.cbs_set_starter_queue.argtypes = [H, P, i32]
     lib.cbs_set_cutoffs.argtypes = [H, i32, f64]
+    lib.cbs_set_action_stride.argtypes = [H, i32]
     lib.cbs_reset.argtypes = [H, P, P, P]
     lib.cbs_decode.argtypes = [H, P, P, P, P]
     lib.cbs_transition.argtypes = [H, P, P, P, P, P, P, P, P]

@@ -149,6 +149,10 @@ int cbs_set_scenarios(cbs_handle* h, const int32_t* scenario_of_env_host);
  * queue[b][e % qlen].  NULL restores random starters (Philox over the feasible set == the rejection loop of
  * cyberbattle_env.py:195-248). */
 int cbs_set_starter_queue(cbs_handle* h, const int32_t* queue_host, int32_t qlen);
+/* Row pitch, in floats, of the action tensors handed to cbs_decode / cbs_step (default 905 = dense).  With a pitch
+ * that is a multiple of 4 floats the tensor-core contraction reads the tensor in place through TMA; a dense tensor
+ * is repacked first (TMA cannot address 3620-byte rows). */
+int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats);
 /* replaces set_cut_off / set_proportional_cutoff_coefficient (cyberbattle_env_switch.py:198-203) */
 int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double proportional_cutoff_coefficient);
 
