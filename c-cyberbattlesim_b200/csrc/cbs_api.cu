@@ -37,6 +37,7 @@ __global__ void init_flags_kernel(int32_t* scal, int B) {
 }  // namespace cbs
 
 using namespace cbs;
+namespace cbs { extern long long* g_sel_trace; }
 
 static thread_local std::string g_create_error;
 
@@ -182,6 +183,11 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   UP(vi_port, I); UP(vi_flags, I); UP(vi_kinds_any, I); UP(vi_kinds_remote, I); UP(vi_success, I); UP(vi_cost, I);
   UP(vi_recon_any, 2 * (size_t)I); UP(vi_recon_remote, 2 * (size_t)I); UP(vi_ulocal, I); UP(recon_nodes, t->num_recon);
   UP(row_packed, t->num_rows); UP(row_inst, t->num_rows);
+  {   // derived: scenario-local vulnerability index of every candidate row (saves a dependent lookup in decode)
+    std::vector<int32_t> ru((size_t)t->num_rows);
+    for (int r = 0; r < t->num_rows; ++r) ru[r] = t->vi_ulocal[t->row_inst[r]];
+    if ((rc = upload(h, &T.row_ulocal, ru.data(), ru.size()))) return rc;
+  }
   UP(vemb32, (size_t)t->num_global_vulns * VULN_EMB); UP(vemb64, (size_t)t->num_global_vulns * VULN_EMB);
   UP(vnorm2, t->num_global_vulns);
 #undef UP
@@ -222,7 +228,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
-  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, B); AL(work_ctr, 4);
+  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, B); AL(work_ctr, 4); AL(work_est, B); AL(bin_cnt, SCHED_BINS + 1); AL(bin_list, (size_t)SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
@@ -466,6 +472,12 @@ int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream) {
   int rc = check_ready(h);
   if (rc) return rc;
   CK(h, cudaMemsetAsync(h->S.accum, 0, N_ACCUM * sizeof(double), (cudaStream_t)stream));
+  return CBS_OK;
+}
+
+int cbs_debug_select_trace(cbs_handle* h, long long* trace_dev) {
+  (void)h;
+  cbs::g_sel_trace = trace_dev;   // [num_envs][6] int64 device buffer, or NULL to switch tracing off
   return CBS_OK;
 }
 

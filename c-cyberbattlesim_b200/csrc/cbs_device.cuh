@@ -34,6 +34,17 @@ __device__ inline bool goal_reached(const State& S, const Params& P, int b) {
   return n_goal == scalar(S, P, S_DISCOVERABLE, b) && n_data == 0 && n_pending == 0;
 }
 
+// cost bin of an env for the longest-first decode schedule
+__device__ __forceinline__ int sched_bin(int rows) {
+  const int b = 31 - __clz((rows >> 5) | 1);   // rows < 64 -> 0, < 128 -> 1, ...
+  return b < SCHED_BINS - 1 ? b : SCHED_BINS - 1;
+}
+__device__ __forceinline__ void sched_enqueue(const State& S, const Params& P, int b) {
+  const int bin = sched_bin(S.work_est[b]);
+  const int pos = atomicAdd(&S.bin_cnt[bin], 1);
+  if (pos < P.B) S.bin_list[(size_t)bin * P.B + pos] = b;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);

@@ -17,6 +17,7 @@ constexpr int NN_CH = 16;
 constexpr int PROJ_ROWS = 18;  // 16 hidden + bias slot + root term
 constexpr int NUM_DYN = 6;     // persistence, collected, exfiltrated, evasion, privilege, status
 constexpr int MAX_NODES = 128;
+constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 
 // outcome kinds (simulation/model.py:66-193)
 enum Kind : int { K_DOS = 0, K_DISCOVERY, K_COLLECTION, K_EXFILTRATION, K_RECON, K_EVASION, K_PERSISTENCE,
@@ -37,7 +38,7 @@ enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLE
 // per-env int32 scalar planes
 enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE,
                     S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES,
-                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_SPARE, N_SCALARS };
+                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF, N_SCALARS };
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
               FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
@@ -57,7 +58,7 @@ struct Tables {  // immutable, device pointers
   const int32_t *nd_value, *nd_ownable, *nd_discoverable, *nd_disruptable, *nd_row_off;
   const uint8_t* nd_level_at_access;
   const uint32_t* outblock;
-  const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst, *uvuln_global;
+  const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst, *uvuln_global, *row_ulocal;
   const uint32_t *vi_flags, *row_packed;
   const uint16_t *vi_kinds_any, *vi_kinds_remote;
   const double *vi_success, *vi_cost, *vemb64, *vnorm2;
@@ -107,6 +108,9 @@ struct State {  // mutable, device pointers
   int32_t* errflag;      // [1]
   int32_t* worklist;     // [B] envs whose step needs graph work (edge / re-encode / episode end)
   int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling)
+  int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)
+  int32_t* bin_cnt;      // [SCHED_BINS + 1] envs per cost bin (filled by the transition for the next decode), [SCHED_BINS] = finished-CTA counter
+  int32_t* bin_list;     // [SCHED_BINS][B] env ids per bin
 };
 
 __host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {

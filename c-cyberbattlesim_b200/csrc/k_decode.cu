@@ -11,6 +11,8 @@
 // embeddings and the float64 vulnerability table with the same formula scipy uses, so the chosen (s,t,vuln,outcome) and the returned distance match a
 // float64 evaluation; ties break on insertion order (epoch, source position, target position, row) like
 // np.argmin over the reference's insertion-ordered dict.
+#include <cstdlib>
+
 #include "cbs_device.cuh"
 
 namespace cbs {
@@ -74,8 +76,6 @@ cudaError_t launch_decode_gemm_simt(const float* actions, int act_stride, const 
 // ------------------------------------------------------------------------------------------------
 // candidate scan + float64 re-score + argmin
 // ------------------------------------------------------------------------------------------------
-constexpr int SEL_WARPS = 4;
-
 __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter) {
   if ((s == t && kind == K_LATERAL) || kind == K_CREDACCESS) return true;                         // compressed:532
   if (P.remove_all && (P.goal == GOAL_CONTROL || P.goal == GOAL_DISCOVERY) && kind == K_DOS) return true;   // :536-538
@@ -83,60 +83,34 @@ __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, i
   return false;
 }
 
-// Per-lane slice of the action kept in registers for the float64 re-score: lane l owns vulnerability-part elements
-// 128*i + 4*l + j (i < 6, j < 4) and channels 2l, 2l+1 of the source / target parts.
-struct LaneAction {
-  float av[24];
-  float2 as, at;
-};
+// ------------------------------------------------------------------------------------------------
+// decode_select: one warp per env.  Measured with a per-env cycle trace (tools/select_trace.py): the kernel is a
+// chain of dependent memory round trips (~1500-2000 cycles each under load), not bandwidth or issue bound, and its
+// duration is set by the envs with the longest action tables (max ~3200 rows, mean ~270).  Hence:
+//   * everything that does not depend on other loads is requested in one prologue burst (scalars, the two order
+//     lists, the env's VT row -> shared memory, the action -> shared memory + its norm);
+//   * the candidate-row templates are prefetched one trip ahead and the VT / norm gathers hit shared memory, so a
+//     trip of 128 rows costs no exposed global round trip;
+//   * parked candidates carry their row template, so the float64 re-score starts its loads immediately.
+// Narrower per-env tiles were tried (4 / 8 / 16 lanes: 428 / 212 / 121 us against 83 us for a full warp): lanes per
+// env matter more than envs in flight.
+// ------------------------------------------------------------------------------------------------
+constexpr int SEL_WARPS = 4;
+constexpr int SEL_THREADS = SEL_WARPS * 32;
+constexpr int CAND_CAP = 4;
+constexpr int RPL = 4;          // rows per lane per trip
+constexpr int SEL_VT_SMEM_MAX = 2048;   // floats of VT row cached per warp (larger tables fall back to global gathers)
 
-// float64 cosine distance of one table row, warp-cooperative; mirrors scipy's cdist 'cosine'
-// (1 - u.v / (|u| |v|) on float64 inputs; the action is float32 widened to float64, compressed:582)
-__device__ __forceinline__ double exact_distance(const Tables& T, const Params& P, const State& S, const LaneAction& A,
-                                                 const float* s_ao, int b, int s, int t, int slot, int r, double na, int lane) {
-  const uint32_t packed = T.row_packed[r];
-  const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-  const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
-  const float2 zs = reinterpret_cast<const float2*>(S.z_hist + (zbase + s) * NODE_EMB)[lane];
-  const float2 zt = reinterpret_cast<const float2*>(S.z_hist + (zbase + t) * NODE_EMB)[lane];
-  const double2* v = reinterpret_cast<const double2*>(T.vemb64 + (size_t)u * VULN_EMB) + 2 * lane;
-  double2 vv[12];
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { vv[2 * i] = v[64 * i]; vv[2 * i + 1] = v[64 * i + 1]; }
-  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) {
-    d0 = fma((double)A.av[4 * i + 0], vv[2 * i].x, d0);
-    d1 = fma((double)A.av[4 * i + 1], vv[2 * i].y, d1);
-    d2 = fma((double)A.av[4 * i + 2], vv[2 * i + 1].x, d2);
-    d3 = fma((double)A.av[4 * i + 3], vv[2 * i + 1].y, d3);
-  }
-  d0 = fma((double)A.as.x, (double)zs.x, d0);
-  d1 = fma((double)A.as.y, (double)zs.y, d1);
-  d2 = fma((double)A.at.x, (double)zt.x, d2);
-  d3 = fma((double)A.at.y, (double)zt.y, d3);
-  double ne2 = fma((double)zs.x, (double)zs.x, (double)zs.y * (double)zs.y) +
-               fma((double)zt.x, (double)zt.x, (double)zt.y * (double)zt.y);
-  double dot = warp_sum((d0 + d1) + (d2 + d3));
-  ne2 = warp_sum(ne2);
-  dot += (double)s_ao[oh];
-  ne2 += T.vnorm2[u] + 1.0;
-  double c = dot / (na * sqrt(ne2));
-  if (fabs(c) > 1.0) c = copysign(1.0, c);
-  return 1.0 - c;
-}
-
-constexpr int CAND_CAP = 8;
-
-struct SelShared {
+struct SelWarp {
   float a_st[2 * NODE_EMB];   // source | target parts of the action
   float a_o[16];
   float p_st[32], p_n2[32];   // per staged pair: a_s.z_s + a_t.z_t (from the fp16 snapshots), |z_s|^2 + |z_t|^2 + 1
   int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
   uint32_t p_key[32];         // slot << 16 | owned position << 8 | discovered position
   float c_score[CAND_CAP];    // rows still within `margin` of the running maximum, waiting for the float64 re-score
-  uint32_t c_key[CAND_CAP];
+  uint32_t c_key[CAND_CAP], c_packed[CAND_CAP];
   int c_row[CAND_CAP];
+  uint8_t oorder[MAX_NODES], dorder[MAX_NODES];
 };
 
 __device__ __forceinline__ float dot8(const uint4 h, const float* a) {
@@ -151,47 +125,153 @@ __device__ __forceinline__ float dot8(const uint4 h, const float* a) {
   return acc;
 }
 
+// float64 cosine distance of one table row, warp-cooperative; mirrors scipy's cdist 'cosine'
+// (1 - u.v / (|u| |v|) on float64 inputs; the action is float32 widened to float64, compressed:582)
+__device__ __forceinline__ double exact_distance(const Tables& T, const Params& P, const State& S, const float* __restrict__ act,
+                                                 int b, int s, int t, int slot, uint32_t packed, double na, int lane) {
+  const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
+  const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
+  const float2 zs = reinterpret_cast<const float2*>(S.z_hist + (zbase + s) * NODE_EMB)[lane];
+  const float2 zt = reinterpret_cast<const float2*>(S.z_hist + (zbase + t) * NODE_EMB)[lane];
+  const double2* v = reinterpret_cast<const double2*>(T.vemb64 + (size_t)u * VULN_EMB) + 2 * lane;
+  const float* av = act + 2 * NODE_EMB + 4 * lane;
+  double2 vv[12];
+  float aa[24];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    vv[2 * i] = v[64 * i]; vv[2 * i + 1] = v[64 * i + 1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) aa[4 * i + j] = av[128 * i + j];
+  }
+  const float as0 = act[2 * lane], as1 = act[2 * lane + 1], at0 = act[NODE_EMB + 2 * lane], at1 = act[NODE_EMB + 2 * lane + 1];
+  const float ao = act[2 * NODE_EMB + VULN_EMB + oh];
+  const double vn2 = T.vnorm2[u];
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    d0 = fma((double)aa[4 * i + 0], vv[2 * i].x, d0);
+    d1 = fma((double)aa[4 * i + 1], vv[2 * i].y, d1);
+    d2 = fma((double)aa[4 * i + 2], vv[2 * i + 1].x, d2);
+    d3 = fma((double)aa[4 * i + 3], vv[2 * i + 1].y, d3);
+  }
+  d0 = fma((double)as0, (double)zs.x, d0);
+  d1 = fma((double)as1, (double)zs.y, d1);
+  d2 = fma((double)at0, (double)zt.x, d2);
+  d3 = fma((double)at1, (double)zt.y, d3);
+  double ne2 = fma((double)zs.x, (double)zs.x, (double)zs.y * (double)zs.y) +
+               fma((double)zt.x, (double)zt.x, (double)zt.y * (double)zt.y);
+  double dot = warp_sum((d0 + d1) + (d2 + d3));
+  ne2 = warp_sum(ne2);
+  dot += (double)ao;
+  ne2 += vn2 + 1.0;
+  double c = dot / (na * sqrt(ne2));
+  if (fabs(c) > 1.0) c = copysign(1.0, c);
+  return 1.0 - c;
+}
+
 struct Best {
   double d;
   unsigned long long key;
   int s, t, r;
+  uint32_t packed;
 };
 
 // re-score the pending candidates that are still within `margin` of run_max; empties the list
-__device__ __forceinline__ void flush_candidates(const Tables& T, const Params& P, const State& S, const LaneAction& A,
-                                                 SelShared& sh, int& ncand, float threshold, int b, double na, int lane,
-                                                 const uint8_t* oorder, const uint8_t* dorder, Best& best) {
+__device__ __forceinline__ void flush_candidates(const Tables& T, const Params& P, const State& S, const float* act, SelWarp& sh,
+                                                 int& ncand, float threshold, int b, double na, int lane, Best& best) {
   for (int i = 0; i < ncand; ++i) {
     if (sh.c_score[i] < threshold) continue;               // NaN scores are kept (comparison false)
     const uint32_t k = sh.c_key[i];
     const int r = sh.c_row[i];
-    const int slot = (int)(k >> 16), s = oorder[(k >> 8) & 0xFF], t = dorder[k & 0xFF];
+    const int slot = (int)(k >> 16), s = sh.oorder[(k >> 8) & 0xFF], t = sh.dorder[k & 0xFF];
     const unsigned long long key = ((unsigned long long)k << 40) | (unsigned long long)(unsigned)r;
-    const double d = exact_distance(T, P, S, A, sh.a_o, b, s, t, slot, r, na, lane);
+    const double d = exact_distance(T, P, S, act, b, s, t, slot, sh.c_packed[i], na, lane);
     // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
     const bool dn = d != d, bn = best.d != best.d;
     const bool better = best.r < 0 || (dn ? (!bn || key < best.key) : (!bn && (d < best.d || (d == best.d && key < best.key))));
-    if (better) { best.d = d; best.key = key; best.s = s; best.t = t; best.r = r; }
+    if (better) { best.d = d; best.key = key; best.s = s; best.t = t; best.r = r; best.packed = sh.c_packed[i]; }
   }
   ncand = 0;
 }
 
-// Table scan.  Pairs (owned source x discovered target, in insertion order) are staged 32 at a time: lane-per-pair
-// for the two 64-wide dot products against the half-precision snapshot rows, then the candidate rows of the 32
-// staged pairs are flattened over the lanes (binary search in the row-count prefix), so short and long candidate
-// lists cost the same per row.  Rows whose float32 score is within `margin` of the running maximum are parked in a
-// small list; the list is pruned as the maximum grows and its survivors are re-scored in float64 (every row
-// within `margin` of the FINAL maximum is guaranteed to be among them, because the running maximum only grows).
-__global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T, Params P, State S,
-                                                                      const float* __restrict__ actions, int vt_stride,
-                                                                      int32_t* __restrict__ sel_out,
-                                                                      double* __restrict__ dist_out) {
-  __shared__ SelShared sh_all[SEL_WARPS];
+// every warp calls this exactly once when it is finished; the last one clears the cost bins for the next transition
+__device__ __forceinline__ void sched_done(const State& S) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+    __threadfence();
+    if (atomicAdd(&S.bin_cnt[SCHED_BINS], 1) == (int)(gridDim.x * SEL_WARPS) - 1) {
+#pragma unroll
+      for (int k = 0; k <= SCHED_BINS; ++k) S.bin_cnt[k] = 0;
+      __threadfence();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
+                                                                   int vt_stride, int vt_cached, int32_t* __restrict__ sel_out,
+                                                                   double* __restrict__ dist_out, long long* __restrict__ trace) {
+  extern __shared__ __align__(16) unsigned char sel_smem[];
+  SelWarp* sh_all = reinterpret_cast<SelWarp*>(sel_smem);
+  float* vn2_sh = reinterpret_cast<float*>(sel_smem + SEL_WARPS * sizeof(SelWarp));          // [vt_cached] shared by the CTA
+  float* vt_sh_all = vn2_sh + vt_cached;                                                      // [SEL_WARPS][vt_cached]
+  const long long t_begin = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * SEL_WARPS + warp;
-  if (b >= P.B) return;
-  SelShared& sh = sh_all[warp];
-  const int flags = scalar(S, P, S_FLAGS, b);
+  // Longest-first schedule: the transition kernel of the previous step binned every env by the size of its action
+  // table; warp w takes the w-th env counting from the heaviest bin.  The kernel's duration is set by the largest
+  // tables, so they must start first.  (No complete binning -> identity order.)
+  int b = blockIdx.x * SEL_WARPS + warp;
+  {
+    int cnt[SCHED_BINS], tot = 0;
+#pragma unroll
+    for (int k = 0; k < SCHED_BINS; ++k) { cnt[k] = S.bin_cnt[k]; tot += cnt[k]; }
+    if (tot == P.B && b < P.B) {
+      int w = b;
+#pragma unroll
+      for (int k = SCHED_BINS - 1; k >= 0; --k) {
+        if (w >= 0 && w < cnt[k]) { b = S.bin_list[(size_t)k * P.B + w]; w = -1; }
+        else if (w >= 0) w -= cnt[k];
+      }
+    }
+  }
+  for (int i = threadIdx.x; i < vt_cached; i += SEL_THREADS) vn2_sh[i] = i < T.num_global_vulns ? (float)T.vnorm2[i] : 1.f;
+  const bool in_range = b < P.B;
+  SelWarp& sh = sh_all[warp];
+  float* vt_sh = vt_sh_all + (size_t)warp * vt_cached;
+
+  // ---- prologue: one burst of independent loads ----
+  int flags = FL_NEEDS_RESET, node_off = 0, starter = 0, n_disc = 0, n_owned = 0;
+  const float* act = actions;
+  double na = 0.0;
+  if (in_range) {
+    flags = scalar(S, P, S_FLAGS, b);
+    node_off = scalar(S, P, S_NODE_OFF, b);
+    starter = scalar(S, P, S_STARTER, b);
+    n_disc = scalar(S, P, S_N_DISC, b);
+    n_owned = scalar(S, P, S_N_OWNED, b);
+    act = actions + (size_t)b * P.act_stride;
+    const uint32_t* dsrc = reinterpret_cast<const uint32_t*>(S.disc_order + (size_t)b * P.ncap);
+    const uint32_t* osrc = reinterpret_cast<const uint32_t*>(S.owned_order + (size_t)b * P.ncap);
+    if (lane < P.ncap / 4) {
+      reinterpret_cast<uint32_t*>(sh.dorder)[lane] = dsrc[lane];
+      reinterpret_cast<uint32_t*>(sh.oorder)[lane] = osrc[lane];
+    }
+    const float* vt_row = S.vt + (size_t)b * vt_stride;
+    for (int i = lane; i < vt_cached; i += 32) vt_sh[i] = vt_row[i];
+    float a[29];
+#pragma unroll
+    for (int i = 0; i < 29; ++i) { const int e = lane + 32 * i; a[i] = e < ACTION_DIM ? act[e] : 0.f; }
+    double n0 = 0.0, n1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 29; ++i) {
+      const int e = lane + 32 * i;
+      if (i < 4) sh.a_st[e] = a[i];                                     // e < 128
+      if (i >= 28 && e >= 2 * NODE_EMB + VULN_EMB && e < ACTION_DIM) sh.a_o[e - 2 * NODE_EMB - VULN_EMB] = a[i];
+      if (i & 1) n1 = fma((double)a[i], (double)a[i], n1); else n0 = fma((double)a[i], (double)a[i], n0);
+    }
+    na = sqrt(warp_sum(n0 + n1));
+  }
+  __syncthreads();
+  if (!in_range) { sched_done(S); return; }
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     if (lane == 0) {
       reinterpret_cast<int4*>(S.sel)[b] = make_int4(0, 0, 0, 0);
@@ -199,43 +279,17 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
       if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
       if (dist_out) dist_out[b] = 0.0;
     }
+    sched_done(S);
     return;
   }
-  const float* act = actions + (size_t)b * P.act_stride;
-  LaneAction A;
-  double na2 = 0.0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) A.av[4 * i + j] = act[2 * NODE_EMB + 128 * i + 4 * lane + j];
-  A.as = make_float2(act[2 * lane], act[2 * lane + 1]);
-  A.at = make_float2(act[NODE_EMB + 2 * lane], act[NODE_EMB + 2 * lane + 1]);
-  const float ao = lane < OUTCOME_DIM ? act[2 * NODE_EMB + VULN_EMB + lane] : 0.f;
-#pragma unroll
-  for (int i = 0; i < 24; ++i) na2 = fma((double)A.av[i], (double)A.av[i], na2);
-  na2 = fma((double)A.as.x, (double)A.as.x, na2); na2 = fma((double)A.as.y, (double)A.as.y, na2);
-  na2 = fma((double)A.at.x, (double)A.at.x, na2); na2 = fma((double)A.at.y, (double)A.at.y, na2);
-  na2 = fma((double)ao, (double)ao, na2);
-  sh.a_st[2 * lane] = A.as.x; sh.a_st[2 * lane + 1] = A.as.y;
-  sh.a_st[NODE_EMB + 2 * lane] = A.at.x; sh.a_st[NODE_EMB + 2 * lane + 1] = A.at.y;
-  if (lane < 16) sh.a_o[lane] = ao;
-  na2 = warp_sum(na2);
-  const double na = sqrt(na2);
-  __syncwarp();
-
-  const int sc = scalar(S, P, S_SCENARIO, b);
-  const int node_off = T.sc_node_off[sc];
-  const int starter = scalar(S, P, S_STARTER, b);
-  const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, S_N_OWNED, b);
-  const uint8_t* dorder = S.disc_order + (size_t)b * P.ncap;
-  const uint8_t* oorder = S.owned_order + (size_t)b * P.ncap;
   const uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
-  const float* vt = S.vt + (size_t)b * vt_stride;
+  const float* vt_g = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
+  const int ug = T.num_global_vulns;
 
   float run_max = -INFINITY;
-  Best best{INFINITY, ~0ull, 0, 0, -1};
-  int ncand = 0;
+  Best best{INFINITY, ~0ull, 0, 0, -1, 0u};
+  int ncand = 0, n_rows = 0, n_live = 0, n_exact = 0;
 
   const int combos = n_owned * n_disc;
   for (int cbase = 0; cbase < combos; cbase += 32) {
@@ -247,7 +301,9 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     uint32_t key = 0;
     if (c < combos) {
       const int op = c / n_disc, dp = c - op * n_disc;
-      const int s = oorder[op], t = dorder[dp];
+      const int s = sh.oorder[op], t = sh.dorder[dp];
+      const int g = node_off + t;
+      const int ra = T.nd_row_off[2 * g], rb = T.nd_row_off[2 * g + 1], rc = T.nd_row_off[2 * g + 2];   // independent of the slot
       const int slot = ps[s * P.ncap + t];
       if (slot != 0xFF) {
         const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
@@ -257,9 +313,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
 #pragma unroll
         for (int i = 0; i < NODE_EMB / 8; ++i) { hs[i] = zs[i]; ht[i] = zt[i]; }
         n2 = S.zn2_hist[zbase + s] + S.zn2_hist[zbase + t] + 1.f;
-        const int g = node_off + t;
-        r0 = (s == t) ? T.nd_row_off[2 * g] : T.nd_row_off[2 * g + 1];
-        cnt = T.nd_row_off[2 * g + 2] - r0;
+        r0 = (s == t) ? ra : rb;
+        cnt = rc - r0;
 #pragma unroll
         for (int i = 0; i < NODE_EMB / 8; ++i) {
           st += dot8(hs[i], sh.a_st + 8 * i);
@@ -271,6 +326,7 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     }
     const unsigned lmask = __ballot_sync(0xFFFFFFFFu, live);
     const int npairs = __popc(lmask);
+    n_live += npairs;
     if (npairs == 0) continue;
     const int idx = __popc(lmask & ((1u << lane) - 1u));
     if (live) { sh.p_st[idx] = st; sh.p_n2[idx] = n2; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_pre[idx + 1] = cnt; }
@@ -286,57 +342,90 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     if (lane < npairs) sh.p_pre[lane + 1] = run;
     __syncwarp();
     const int total = sh.p_pre[npairs];
+    n_rows += total;
 
-    // ---- phase B: candidate rows of the staged pairs, flattened over the lanes ----
-    for (int j0 = 0; j0 < total; j0 += 32) {
-      const int j = j0 + lane;
-      float score = -INFINITY;
-      bool valid = false;
-      int pi = 0, r = 0;
+    // ---- phase B: candidate rows of the staged pairs, flattened over the lanes, RPL rows per lane per trip; the
+    //      row templates of the NEXT trip are requested before the current trip is scored ----
+    int pi = 0;                                             // rows are visited in increasing order: the pair index only grows
+    int rr_n[RPL], pp_n[RPL];
+    uint32_t packed_n[RPL];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+      const int j = q * 32 + lane;
+      rr_n[q] = 0; pp_n[q] = 0; packed_n[q] = 0;
       if (j < total) {
-        int lo = 0, hi = npairs;           // largest pi with p_pre[pi] <= j
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (sh.p_pre[mid] <= j) lo = mid; else hi = mid;
-        }
-        pi = lo;
-        r = sh.p_r0[pi] + (j - sh.p_pre[pi]);
-        const uint32_t packed = T.row_packed[r];
-        const int kind = (packed >> 20) & 15;
-        const uint32_t k = sh.p_key[pi];
-        const int s = oorder[(k >> 8) & 0xFF], t = dorder[k & 0xFF];
-        if (!row_filtered(P, kind, s, t, starter)) {
-          const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-          score = (sh.p_st[pi] + vt[u] + sh.a_o[oh]) * rsqrtf(sh.p_n2[pi] + (float)T.vnorm2[u]);
-          valid = true;
+        while (sh.p_pre[pi + 1] <= j) ++pi;
+        pp_n[q] = pi;
+        rr_n[q] = sh.p_r0[pi] + (j - sh.p_pre[pi]);
+        packed_n[q] = T.row_packed[rr_n[q]];
+      }
+    }
+    for (int j0 = 0; j0 < total; j0 += RPL * 32) {
+      int rr[RPL], pp[RPL];
+      uint32_t packed[RPL];
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) { rr[q] = rr_n[q]; pp[q] = pp_n[q]; packed[q] = packed_n[q]; }
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {                       // prefetch the next trip
+        const int j = j0 + RPL * 32 + q * 32 + lane;
+        if (j < total) {
+          while (sh.p_pre[pi + 1] <= j) ++pi;
+          pp_n[q] = pi;
+          rr_n[q] = sh.p_r0[pi] + (j - sh.p_pre[pi]);
+          packed_n[q] = T.row_packed[rr_n[q]];
         }
       }
-      float cmax = valid ? score : -INFINITY;
+      float score[RPL];
+      bool valid[RPL];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        const int j = j0 + q * 32 + lane;
+        score[q] = -INFINITY; valid[q] = false;
+        if (j < total) {
+          const int kind = (packed[q] >> 20) & 15;
+          const uint32_t k = sh.p_key[pp[q]];
+          const int s = sh.oorder[(k >> 8) & 0xFF], t = sh.dorder[k & 0xFF];
+          if (!row_filtered(P, kind, s, t, starter)) {
+            const int u = packed[q] & 0xFFFFF, oh = (packed[q] >> 24) & 15;
+            const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
+            const float vn2 = u < vt_cached ? vn2_sh[u] : (float)T.vnorm2[u];
+            score[q] = (sh.p_st[pp[q]] + vtu + sh.a_o[oh]) * rsqrtf(sh.p_n2[pp[q]] + vn2);
+            valid[q] = true;
+            cmax = fmaxf(cmax, score[q]);
+          }
+        }
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
       run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
-      unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < run_max - margin_s));
-      while (cand) {
-        const int src_lane = __ffs(cand) - 1;
-        cand &= cand - 1;
-        if (ncand == CAND_CAP) flush_candidates(T, P, S, A, sh, ncand, run_max - margin_s, b, na, lane, oorder, dorder, best);
-        const float cs = __shfl_sync(0xFFFFFFFFu, score, src_lane);
-        const int cpi = __shfl_sync(0xFFFFFFFFu, pi, src_lane);
-        const int cr = __shfl_sync(0xFFFFFFFFu, r, src_lane);
-        if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_row[ncand] = cr; }
-        ++ncand;
-        __syncwarp();
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) {
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, valid[q] && !(score[q] < run_max - margin_s));
+        while (cand) {
+          const int src = __ffs(cand) - 1;
+          cand &= cand - 1;
+          if (ncand == CAND_CAP) { n_exact += ncand; flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best); }
+          const float cs = __shfl_sync(0xFFFFFFFFu, score[q], src);
+          const int cpi = __shfl_sync(0xFFFFFFFFu, pp[q], src);
+          const int cr = __shfl_sync(0xFFFFFFFFu, rr[q], src);
+          const uint32_t cp = __shfl_sync(0xFFFFFFFFu, packed[q], src);
+          if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp; }
+          ++ncand;
+          __syncwarp();
+        }
       }
     }
     __syncwarp();
   }
-  flush_candidates(T, P, S, A, sh, ncand, run_max - margin_s, b, na, lane, oorder, dorder, best);
+  (void)ug;
+  n_exact += ncand;
+  flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best);
   if (lane == 0) {
     int4 out = make_int4(starter, starter, 0, 0);
     double d = 1.0;
     if (best.r >= 0) {
-      const uint32_t packed = T.row_packed[best.r];
-      out = make_int4(best.s, best.t, T.vi_ulocal[T.row_inst[best.r]], (int)((packed >> 20) & 15));
+      out = make_int4(best.s, best.t, T.row_ulocal[best.r], (int)((best.packed >> 20) & 15));
       d = best.d;
     } else {
       atomicExch(S.errflag, 3);   // empty action table: outside the reference's domain (cdist would raise)
@@ -345,13 +434,28 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) decode_select_kernel(Tables T,
     S.dist[b] = d;
     if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = out;
     if (dist_out) dist_out[b] = d;
+    if (trace) {
+      long long* tr = trace + (size_t)b * 6;
+      tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
+    }
   }
+  sched_done(S);
 }
+
+long long* g_sel_trace = nullptr;   // debug: per-env {cycles, rows, live pairs, parked candidates, combos, start clock}
 
 cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& S, const float* actions, int vt_stride,
                                  int32_t* sel_out, double* dist_out, cudaStream_t stream) {
-  const int grid = (P.B + SEL_WARPS - 1) / SEL_WARPS;
-  decode_select_kernel<<<grid, SEL_WARPS * 32, 0, stream>>>(T, P, S, actions, vt_stride, sel_out, dist_out);
+  const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
+  const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  decode_select_kernel<<<(P.B + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached,
+                                                                                        sel_out, dist_out, g_sel_trace);
   return cudaGetLastError();
 }
 

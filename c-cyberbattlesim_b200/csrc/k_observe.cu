@@ -239,7 +239,9 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 
 // ---- create_continuous_action_space (compressed:487-523): new (source,target) pairs freeze the embeddings
 //      of THIS encode; they are stored once per table-growing encode in a snapshot slot ----
-__device__ void build_table(const Params& P, const State& S, WarpScratch& W, int b, int lane) {
+__device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane) {
+  const int node_off_bt = scalar(S, P, S_NODE_OFF, b);
+  int new_rows = 0;
   const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, S_N_OWNED, b);
   const uint8_t* dorder = S.disc_order + (size_t)b * P.ncap;
   const uint8_t* oorder = S.owned_order + (size_t)b * P.ncap;
@@ -255,13 +257,19 @@ __device__ void build_table(const Params& P, const State& S, WarpScratch& W, int
       if (dp < n_disc) {
         const int t = dorder[dp];
         fresh = (W.dynb[dp] & 0x80) && ps[s * P.ncap + t] == 0xFF;
-        if (fresh && slot < P.slots) ps[s * P.ncap + t] = (uint8_t)slot;
+        if (fresh && slot < P.slots) {
+          ps[s * P.ncap + t] = (uint8_t)slot;
+          const int g = node_off_bt + t;
+          new_rows += T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g + (s == t ? 0 : 1)];
+        }
       }
       any_new |= __any_sync(0xFFFFFFFFu, fresh);
     }
   }
   if (!any_new) return;
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
+  new_rows = (int)warp_sum((float)new_rows);
+  if (lane == 0) S.work_est[b] += new_rows;
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
@@ -347,6 +355,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
   for (int i = lane; i < P.ncap * P.ncap / 4; i += 32) ps[i] = 0xFFFFFFFFu;
   if (lane == 0) {
     scalar(S, P, S_SCENARIO, b) = sc;
+    scalar(S, P, S_NODE_OFF, b) = T.sc_node_off[sc];
     scalar(S, P, S_STARTER, b) = starter;
     scalar(S, P, S_STEPCOUNT, b) = 0;
     scalar(S, P, S_NUM_ITER, b) = 0;
@@ -360,6 +369,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     scalar(S, P, S_PROP_NODES, b) = P.goal == GOAL_CONTROL ? own : (P.goal == GOAL_DISCOVERY ? dis : dsr);
     scalar(S, P, S_DISCOVERABLE_AMOUNT, b) = T.sc_discoverable_amount[sc];
     scalar(S, P, S_N_SLOTS, b) = 0;
+    S.work_est[b] = 0;
     scalar(S, P, S_N_EDGES, b) = 0;
     scalar(S, P, S_FLAGS, b) = 0;
     scalar(S, P, S_OUTCOME, b) = -1;
@@ -433,7 +443,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
       if (flags & FL_REENCODE) {
         encode_env(T, P, S, SW, W, b, lane);
-        build_table(P, S, W, b, lane);
+        build_table(T, P, S, W, b, lane);
         keep &= ~FL_DIRTY;
       }
       if (flags & FL_FINISHED_THIS_STEP) {
@@ -447,7 +457,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     if (do_reset) {
       reset_env(T, P, S, b, lane);
       encode_env(T, P, S, SW, W, b, lane);
-      build_table(P, S, W, b, lane);
+      build_table(T, P, S, W, b, lane);
     }
     __syncwarp();
     if (mode == 1) i += total_warps;

@@ -5,7 +5,7 @@
 // per-env bitmask planes and the flattened scenario tables.  One thread per env: the per-env work is a few
 // dozen dependent integer ops on ~200 B of state, so the kernel is bound by the coalesced SoA loads/stores
 // (masks/scalars are [plane][env]); goal / lost tests are popcounts over the node-mask words.
-#include "cbs_types.h"
+#include "cbs_device.cuh"
 #include "philox.cuh"
 
 namespace cbs {
@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, Sta
   auto SC = [&](int plane) -> int32_t& { return scal[(size_t)plane * B + b]; };
 
   int flags = SC(S_FLAGS);
+  sched_enqueue(S, P, b);   // cost-binned env list for the next decode (longest tables first)
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     // the reference raises RuntimeError here (cyberbattle_env.py:300-302); a finished env is left untouched
     if (reward_out) reward_out[b] = 0.f;

@@ -11,7 +11,7 @@ import numpy as np
 from . import constants as C
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcbsim.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("CBS_LIB", "libcbsim.so"))
 CSRC = os.path.join(_HERE, "csrc")
 ABI_VERSION = 1
 
@@ -53,7 +53,7 @@ class CbsGaeTables(ct.Structure):
 # every symbol include/cbsim.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
            "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
-           "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_read_state", "cbs_state_ptr", "cbs_reset_stat_accum", "cbs_launch_count",
+           "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_read_state", "cbs_state_ptr", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
 
 # cbs_field
@@ -63,7 +63,7 @@ NUM_SCALARS, NUM_ACCUM = 20, 20
 # scalar planes (csrc/cbs_types.h enum Scalar)
 (S_SCENARIO, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE, S_DISCOVERABLE,
  S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES, S_FLAGS, S_OUTCOME,
- S_TOTAL_STEPS, S_N_ENCODES, S_SPARE) = range(20)
+ S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF) = range(20)
 ACCUM_NAMES = ["episodes", "return_sum", "length_sum", "wins", "lost", "cutoff"] + [f"stat{i}" for i in range(14)]
 
 
@@ -118,6 +118,7 @@ def load_library():
     lib.cbs_state_ptr.argtypes = [H, i32]
     lib.cbs_state_ptr.restype = P
     lib.cbs_reset_stat_accum.argtypes = [H, P]
+    lib.cbs_debug_select_trace.argtypes = [H, P]
     lib.cbs_launch_count.argtypes = [H]
     lib.cbs_launch_count.restype = i64
     lib.cbs_sync.argtypes = [H]

@@ -226,6 +226,9 @@ int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t byt
 /* device pointer of a state field (for zero-copy consumers such as an NCCL all-reduce of CBS_F_STAT_ACCUM) */
 void* cbs_state_ptr(cbs_handle* h, int32_t field);
 int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream);
+/* debugging aid: per-env {cycles, rows scanned, live pairs, float64 re-scores, pair combinations, start clock} of the
+ * following cbs_decode calls are written to trace_dev ([num_envs][6] int64, device); NULL switches it off */
+int cbs_debug_select_trace(cbs_handle* h, long long* trace_dev);
 /* number of kernels this library launched since creation (bench.py reports it) */
 int64_t cbs_launch_count(const cbs_handle* h);
 /* cudaDeviceSynchronize + device error flag (capacity overflow, empty action table) -> CBS_ERR_CAPACITY */
