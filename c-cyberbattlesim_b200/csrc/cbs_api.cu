@@ -228,7 +228,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
-  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, B); AL(work_ctr, 4); AL(work_est, B); AL(bin_cnt, SCHED_BINS + 1); AL(bin_list, (size_t)SCHED_BINS * B);
+  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, SCHED_BINS + 1); AL(bin_list, (size_t)SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);

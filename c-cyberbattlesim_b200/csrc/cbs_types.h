@@ -106,8 +106,8 @@ struct State {  // mutable, device pointers
   float* vt;             // [B][Ug]  action x vulnerability-embedding products (decode GEMM output)
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   int32_t* errflag;      // [1]
-  int32_t* worklist;     // [B] envs whose step needs graph work (edge / re-encode / episode end)
-  int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling)
+  int32_t* worklist;     // [3][B] envs whose step needs graph work, by cost class (episode end / re-encode / edge only)
+  int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling), [4..6] class list lengths
   int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)
   int32_t* bin_cnt;      // [SCHED_BINS + 1] envs per cost bin (filled by the transition for the next decode), [SCHED_BINS] = finished-CTA counter
   int32_t* bin_list;     // [SCHED_BINS][B] env ids per bin

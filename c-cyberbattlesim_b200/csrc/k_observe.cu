@@ -23,7 +23,7 @@ constexpr int SMEM_NODES = 32;
 
 struct SharedWeights {
   float gcn[NODE_EMB * NODE_EMB];               // [in][out]
-  float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]
+  float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]  (reading it through L1 instead of staging it was measured slower)
   float bn1s[NODE_EMB], bn1h[NODE_EMB], bn2s[NODE_EMB], bn2h[NODE_EMB];
   float nn0b[NN_CH];
 };
@@ -171,16 +171,24 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     W.y[i * NODE_EMB + c1] = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn1s[c1], SW.bn1h[c1]), 0.f);
   }
   __syncwarp();
-  for (int i = 0; i < n; ++i) {
-    float g0 = 0.f, g1 = 0.f;
+  for (int i = 0; i < n; i += 2) {                // two nodes per pass: each weight pair feeds four FMAs
+    const int i2 = (i + 1 < n) ? i + 1 : i;
+    float g0 = 0.f, g1 = 0.f, h0 = 0.f, h1 = 0.f;
 #pragma unroll 8
     for (int k = 0; k < NODE_EMB; ++k) {
-      const float h = W.y[i * NODE_EMB + k];
-      g0 = fmaf(h, SW.gcn[k * NODE_EMB + c0], g0);
-      g1 = fmaf(h, SW.gcn[k * NODE_EMB + c1], g1);
+      const float w0 = SW.gcn[k * NODE_EMB + c0], w1 = SW.gcn[k * NODE_EMB + c1];
+      const float a = W.y[i * NODE_EMB + k], bq = W.y[i2 * NODE_EMB + k];
+      g0 = fmaf(a, w0, g0);
+      g1 = fmaf(a, w1, g1);
+      h0 = fmaf(bq, w0, h0);
+      h1 = fmaf(bq, w1, h1);
     }
     W.g[i * NODE_EMB + c0] = g0;
     W.g[i * NODE_EMB + c1] = g1;
+    if (i2 != i) {
+      W.g[i2 * NODE_EMB + c0] = h0;
+      W.g[i2 * NODE_EMB + c1] = h1;
+    }
   }
   __syncwarp();
   // normalised aggregation, edges first and the self loop last (the order PyG's add_remaining_self_loops +
@@ -385,8 +393,23 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
                                                                 const uint8_t* __restrict__ reset_mask, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SharedWeights& SW = *reinterpret_cast<SharedWeights*>(smem_raw);
-  for (int i = threadIdx.x; i < NODE_EMB * NODE_EMB; i += blockDim.x) SW.gcn[i] = T.gcn_wt[i];
-  for (int i = threadIdx.x; i < NUM_DYN * PROJ_ROWS * NODE_EMB; i += blockDim.x) SW.dyn[i] = T.dyn_proj[i];
+  {   // stage the weights with 128-bit loads, all requests in flight before the first store
+    constexpr int NT = OBS_WARPS * 32;
+    constexpr int G4 = NODE_EMB * NODE_EMB / 4, D4 = NUM_DYN * PROJ_ROWS * NODE_EMB / 4;   // 1024, 1728 float4
+    const float4* gsrc = reinterpret_cast<const float4*>(T.gcn_wt);
+    const float4* dsrc = reinterpret_cast<const float4*>(T.dyn_proj);
+    float4* gdst = reinterpret_cast<float4*>(SW.gcn);
+    float4* ddst = reinterpret_cast<float4*>(SW.dyn);
+    float4 tg[G4 / NT], td[(D4 + NT - 1) / NT];
+#pragma unroll
+    for (int i = 0; i < G4 / NT; ++i) tg[i] = gsrc[threadIdx.x + i * NT];
+#pragma unroll
+    for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; td[i] = j < D4 ? dsrc[j] : make_float4(0, 0, 0, 0); }
+#pragma unroll
+    for (int i = 0; i < G4 / NT; ++i) gdst[threadIdx.x + i * NT] = tg[i];
+#pragma unroll
+    for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; if (j < D4) ddst[j] = td[i]; }
+  }
   if (threadIdx.x < NODE_EMB) {
     SW.bn1s[threadIdx.x] = T.bn1_scale[threadIdx.x];
     SW.bn1h[threadIdx.x] = T.bn1_shift[threadIdx.x];
@@ -421,7 +444,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
   // transition kernel put on the worklist — the others keep their cached observation untouched.
-  const int count = (mode == 1) ? P.B : S.work_ctr[0];
+  // mode 0: three class lists (episode end, re-encode, edge only) are consumed as one sequence, heaviest class first
+  const int c0 = (mode == 1) ? P.B : S.work_ctr[4], c1 = (mode == 1) ? 0 : S.work_ctr[5], c2 = (mode == 1) ? 0 : S.work_ctr[6];
+  const int count = c0 + c1 + c2;
   int i = gw;                                   // mode 1: static stride.  mode 0: items are claimed one at a time
   for (;;) {
     if (mode == 0) {
@@ -429,7 +454,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       i = __shfl_sync(0xFFFFFFFFu, i, 0);
     }
     if (i >= count) break;
-    const int b = (mode == 1) ? i : S.worklist[i];
+    int b = i;
+    if (mode == 0) {
+      if (i < c0) b = S.worklist[i];
+      else if (i < c0 + c1) b = S.worklist[(size_t)P.B + (i - c0)];
+      else b = S.worklist[(size_t)2 * P.B + (i - c0 - c1)];
+    }
     if (!SMEM_BUF) {
       W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
       W.g = W.y + (size_t)P.ncap * NODE_EMB;
@@ -465,7 +495,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
   if (mode == 0 && lane == 0) {   // the last warp to run dry clears the counters for the next transition
     __threadfence();
     if (atomicAdd(&S.work_ctr[1], 1) == total_warps - 1) {
-      S.work_ctr[0] = 0; S.work_ctr[1] = 0; S.work_ctr[2] = 0;
+      S.work_ctr[0] = 0; S.work_ctr[1] = 0; S.work_ctr[2] = 0; S.work_ctr[4] = 0; S.work_ctr[5] = 0; S.work_ctr[6] = 0;
       __threadfence();
     }
   }

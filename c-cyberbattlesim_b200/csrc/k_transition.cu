@@ -243,8 +243,10 @@ __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, Sta
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0);
   SC(S_FLAGS) = flags;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
-    const int slot = atomicAdd(&S.work_ctr[0], 1);
-    if (slot < P.B) S.worklist[slot] = b; else atomicExch(S.errflag, 4);
+    // three cost classes, claimed heaviest first: episode end (statistics + reset + encode + table), re-encode, edge only
+    const int cls = (flags & FL_FINISHED_THIS_STEP) ? 0 : ((flags & FL_REENCODE) ? 1 : 2);
+    const int slot = atomicAdd(&S.work_ctr[4 + cls], 1);
+    if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);
   }
   S.reward64[b] = reward;
   S.ep_return[b] += reward;
