@@ -45,6 +45,17 @@ CASES = {
     # 100-node "default-like" scenario (configs[0]); >64 nodes exercises 4-word masks
     "g100_control": dict(graph_seed=16, nodes=100, steps=1200, pool_size=560, services_range=(1, 4),
                          vulns_per_service_range=(8, 18), cfg=dict(goal="control")),
+    # scripted attacker (oracle.trace.policy_pick): owns many nodes, escalates, reaches the goal -> winning reward,
+    # large action tables, many snapshot slots.  `policy` = noise sigma added to the chosen table row.
+    "p6_control_win": dict(graph_seed=30, nodes=6, steps=500, policy=0.02,
+                           cfg=dict(goal="control", proportional_cutoff_coefficient=25, episode_iterations=400)),
+    "p8_control_win": dict(graph_seed=53, nodes=8, steps=500, policy=0.02,
+                           cfg=dict(goal="control", proportional_cutoff_coefficient=25, episode_iterations=400)),
+    "p6_control_nostop": dict(graph_seed=30, nodes=6, steps=500, policy=0.02,
+                              cfg=dict(goal="control", proportional_cutoff_coefficient=25, episode_iterations=400,
+                                       stop_at_goal_reached=False)),
+    "p24_control_big": dict(graph_seed=18, nodes=24, steps=700, policy=0.02,
+                            cfg=dict(goal="control", proportional_cutoff_coefficient=5, episode_iterations=200)),
 }
 POOL_SEED = 1234
 GAE_SEED = 0
@@ -63,16 +74,26 @@ def build_case(name):
     return p, graph, model, spec, cfg, weights
 
 
+def make_case_inputs(p):
+    """Random-action cases: actions U(-4,4)^905.  Policy cases: `actions` is N(0, sigma) noise added to a table row."""
+    actions, uniforms = tr.make_inputs(p["graph_seed"] * 1000 + 1, p["steps"])
+    if "policy" in p:
+        rng = np.random.default_rng(p["graph_seed"] * 1000 + 4)
+        actions = (rng.standard_normal(actions.shape) * p["policy"]).astype(np.float32)
+    return actions, uniforms
+
+
 def generate(name):
     from oracle import ref_bridge as rb
     t0 = time.time()
     p, graph, model, spec, cfg, weights = build_case(name)
     tables = cb.compile_scenarios([spec], cfg.isolation_filter_threshold)      # also cross-checks reach counts
     feasible = tables.feasible_starters[cb.constants.GOALS[cfg.goal]]
-    actions, uniforms = tr.make_inputs(p["graph_seed"] * 1000 + 1, p["steps"])
+    actions, uniforms = make_case_inputs(p)
     starters = tr.make_starters(p["graph_seed"] * 1000 + 2, feasible, p["steps"] + 2)
     runner = rb.ReferenceRunner(model, weights, cfg)
-    rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters)
+    rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters,
+                    policy_seed=(p["graph_seed"] * 1000 + 3) if "policy" in p else None)
     meta = dict(name=name, params={k: v for k, v in p.items() if k != "cfg"}, cfg=p["cfg"], pool_seed=POOL_SEED,
                 gae_seed=GAE_SEED, input_seed=p["graph_seed"] * 1000 + 1, starter_seed=p["graph_seed"] * 1000 + 2,
                 spec=spec_to_dict(spec),
@@ -91,7 +112,8 @@ def generate(name):
     np.savez_compressed(path, **out)
     eps = int(rec["num_episodes"])
     print(f"{name}: {p['steps']} steps, {eps} episodes, {os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.1f}s; "
-          f"success codes seen: {sorted(set(rec['code'].tolist()))}; end reasons: {np.bincount(rec['reason'], minlength=4).tolist()}")
+          f"success codes seen: {sorted(set(rec['code'].tolist()))}; end reasons: {np.bincount(rec['reason'], minlength=4).tolist()}; "
+          f"max owned {int((rec['owned_order'] >= 0).sum(1).max())}, max discovered {int((rec['disc_order'] >= 0).sum(1).max())}")
 
 
 def load_case(path):
@@ -109,11 +131,12 @@ def load_case(path):
         raise RuntimeError("golden fixture: regenerated embeddings do not match the recorded checksum")
     cfg = cb.EnvConfig(**meta["cfg"])
     weights = GaeWeights.random(meta["gae_seed"])
-    actions, uniforms = tr.make_inputs(meta["input_seed"], p["steps"])
+    actions, uniforms = make_case_inputs(p)
     rec = {k: z[k] for k in z.files if k not in ("meta", "obs_rows", "obs_idx")}
     rec["obs"] = z["obs_rows"][z["obs_idx"]]
     return dict(meta=meta, spec=spec, cfg=cfg, weights=weights, actions=actions, uniforms=uniforms,
-                starters=z["starters"], trace=rec)
+                starters=z["starters"], trace=rec, policy_seed=0 if "policy" in p else None,
+                policy_rows=rec.get("policy_rows"))
 
 
 if __name__ == "__main__":

@@ -64,6 +64,16 @@ class OracleAdapter:
     def masks(self):
         return self.env.masks()
 
+    def table_keys(self):
+        return [(k[0], k[1], k[3]) for k in self.env.action_keys]
+
+    def table_row(self, i):
+        return np.asarray(self.env.action_rows[i], dtype=np.float64)
+
+    def owned_and_root(self):
+        e = self.env
+        return set(e.owned_nodes), {n for n in e.owned_nodes if e.nodes[n].privilege_level == C.PRIV_ROOT}
+
     def lists(self):
         return list(self.env.discovered_nodes), list(self.env.owned_nodes)
 
@@ -103,6 +113,19 @@ class ReferenceAdapter:
     def masks(self):
         return self.r.masks()
 
+    def table_keys(self):
+        from ccbs_b200.scenario import _KIND_BY_CLASSNAME
+        ix = self.r.index
+        return [(ix[k[0]], ix[k[1]], _KIND_BY_CLASSNAME[type(k[3]).__name__]) for k in self.r.env.action_embeddings]
+
+    def table_row(self, i):
+        return np.asarray(list(self.r.env.action_embeddings.values())[i], dtype=np.float64)
+
+    def owned_and_root(self):
+        e, ix = self.r.env, self.r.index
+        return ({ix[n] for n in e.owned_nodes},
+                {ix[n] for n in e.owned_nodes if int(e.get_node(n).privilege_level) == C.PRIV_ROOT})
+
     def lists(self):
         e = self.r.env
         return [self.r.index[n] for n in e.discovered_nodes], [self.r.index[n] for n in e.owned_nodes]
@@ -116,9 +139,29 @@ class ReferenceAdapter:
         return self.r.wrapper.get_statistics()
 
 
-def record(adapter, actions, uniforms, starters):
-    """Step ``adapter`` through the whole action sequence with auto-reset; return a dict of arrays."""
+def policy_pick(keys, owned, root, rng, p_greedy=0.85):
+    """Scripted attacker used for the 'policy' golden cases: prefer lateral moves onto nodes not yet owned, then
+    privilege escalation on owned non-root nodes, then reconnaissance; otherwise (and with prob. 1 - p_greedy) a
+    uniformly random table row.  ``keys`` = [(source, target, kind)] in table order.  Returns a row index."""
+    if rng.random() < p_greedy:
+        lateral = [i for i, (s, t, k) in enumerate(keys) if k == C.K_LATERAL and t not in owned]
+        privesc = [i for i, (s, t, k) in enumerate(keys) if k == C.K_PRIVESC and t in owned and t not in root]
+        recon = [i for i, (s, t, k) in enumerate(keys) if k == C.K_RECON]
+        for cls, p in ((lateral, 0.6), (privesc, 0.8), (recon, 0.5)):
+            if cls and rng.random() < p:
+                return int(cls[rng.integers(len(cls))])
+    return int(rng.integers(len(keys)))
+
+
+def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=None):
+    """Step ``adapter`` through the whole action sequence with auto-reset; return a dict of arrays.
+
+    Policy mode (``policy_seed`` set): ``actions`` holds small float32 noise only; the action of step t is a row of the
+    env's current action table plus that noise.  When ``policy_rows`` is None the row is chosen by :func:`policy_pick`
+    (generation, reference side) and recorded; otherwise the recorded rows are replayed (oracle / CUDA side)."""
     T, N = len(actions), adapter.N
+    prng = np.random.default_rng(policy_seed) if policy_seed is not None else None
+    chosen_rows = np.zeros(T, np.int32)
     rec = dict(sel=np.zeros((T, 4), np.int32), code=np.zeros(T, np.int32), reward=np.zeros(T, np.float64),
                done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
                dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
@@ -130,7 +173,15 @@ def record(adapter, actions, uniforms, starters):
     reset_obs.append(adapter.reset(starters[ep]))
     reset_masks.append(masks_to_array(adapter.masks()))
     for t in range(T):
-        obs, r, done, trunc, sel, code, reason, dist = adapter.step(actions[t], uniforms[t])
+        action = actions[t]
+        if policy_seed is not None:
+            if policy_rows is None:
+                owned, root = adapter.owned_and_root()
+                chosen_rows[t] = policy_pick(adapter.table_keys(), owned, root, prng)
+            else:
+                chosen_rows[t] = policy_rows[t]
+            action = (adapter.table_row(int(chosen_rows[t])) + actions[t].astype(np.float64)).astype(np.float32)
+        obs, r, done, trunc, sel, code, reason, dist = adapter.step(action, uniforms[t])
         rec["sel"][t], rec["code"][t], rec["reward"][t] = sel, code, r
         rec["done"][t], rec["truncated"][t], rec["reason"][t], rec["dist"][t] = done, trunc, reason, dist
         rec["masks"][t] = masks_to_array(adapter.masks())
@@ -151,11 +202,13 @@ def record(adapter, actions, uniforms, starters):
     rec["reset_masks"] = np.array(reset_masks, np.uint64)
     rec["stats"] = np.array(stats, np.float64).reshape(-1, 14)
     rec["num_episodes"] = np.array(ep + 1, np.int32)
+    if policy_seed is not None:
+        rec["policy_rows"] = chosen_rows
     return rec
 
 
 INT_KEYS = ("sel", "code", "done", "truncated", "reason", "masks", "disc_order", "owned_order", "counters",
-            "episode", "reset_masks", "num_episodes")
+            "episode", "reset_masks", "num_episodes")   # "policy_rows" is an input, not compared
 
 
 def compare(a, b, rtol=1e-5, atol=1e-5, label=""):

@@ -53,7 +53,7 @@ class TieFollower:
             self.env.reset(starter=int(self.starters[self.ep]))
 
 
-def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None):
+def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_rows=None):
     """Step every env of `env` with the same action/uniform sequence; returns a trace record for env
     `check_env` plus the per-step cross-env consistency flag."""
     B, T = env.num_envs, len(actions)
@@ -71,7 +71,11 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None):
     consistent = True
     ep = 0
     b = check_env
+    actions = np.array(actions, copy=True)
     for t in range(T):
+        if policy_rows is not None:   # scripted-attacker traces: action = recorded row of the (oracle's) action table + noise
+            actions[t] = (np.asarray(follower.env.action_rows[int(policy_rows[t])], np.float64)
+                          + actions[t].astype(np.float64)).astype(np.float32)
         a = torch.from_numpy(np.ascontiguousarray(actions[t])).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
         u = torch.full((B,), float(uniforms[t]), dtype=torch.float32, device=env.device)
         sel, dist = env.decode(a)

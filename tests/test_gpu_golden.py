@@ -26,7 +26,7 @@ def test_cuda_replays_reference_trace(name, gemm, golden_dir):
     env.set_starter_queue(np.tile(case["starters"][None, :], (B, 1)))
     follower = TieFollower(OracleEnv(case["spec"], case["weights"], case["cfg"]), case["spec"], case["starters"])
     rec, consistent = replay(env, case["actions"], case["uniforms"], case["spec"].num_nodes, check_env=B - 1,
-                             follower=follower)
+                             follower=follower, policy_rows=case["policy_rows"])
     env.close()
     assert consistent, "envs fed identical inputs diverged"
     report = tr.compare(rec, case["trace"], rtol=1e-5, atol=2e-5, label=f"{name}/gemm{gemm}")

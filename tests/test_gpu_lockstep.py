@@ -10,6 +10,7 @@ pytestmark = pytest.mark.gpu
 def _philox_uniform(seed, env, step, stream):
     """Host restatement of csrc/philox.cuh (Philox4x32-10, first word, 24-bit uniform)."""
     M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    seed, env, step, stream = int(seed), int(env), int(step), int(stream)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     c = [env & 0xFFFFFFFF, (env >> 32) & 0xFFFFFFFF, step & 0xFFFFFFFF, stream & 0xFFFFFFFF]
     for _ in range(10):
