@@ -29,13 +29,15 @@ WORKLOADS = {
                envs_per_gpu=8192, nodes=(32, 32), scenarios=16),
     "c1": dict(name="configs[1]: 4096 envs x 10-25-node synthetic scenarios on 1 GPU", envs_per_gpu=4096, nodes=(10, 25),
                scenarios=16),
+    "c4": dict(name="configs[3]: mixed-topology batch, 10-100-node scenarios (padded to 100 nodes), 768-d embeddings, pool 600",
+               envs_per_gpu=4096, nodes=(10, 100), scenarios=20, pool=600),
 }
 POOL_SEED, GAE_SEED = 1234, 0
 
 
 def build_specs(wl):
     import ccbs_b200 as cb
-    pool = cb.synthetic_vuln_pool(POOL_SEED, 200)
+    pool = cb.synthetic_vuln_pool(POOL_SEED, wl.get("pool", 200))
     rng = np.random.default_rng(2024)
     specs = []
     for k in range(wl["scenarios"]):

@@ -32,6 +32,7 @@ struct WarpScratch {
   float* y;           // [n][64]
   float* g;           // [n][64]
   float* dinv;        // [ncap]
+  float* ysm;         // this warp's shared-memory buffers (2 x [32][64])
   uint8_t* pos;       // [MAX_NODES] node id -> position in discovered order
   uint8_t* dynb;      // [MAX_NODES] per position: visible | persistence<<1 | collected<<2 | exfiltrated<<3 | evasion<<4 | privilege<<5 | running<<7
 };
@@ -425,21 +426,15 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
   // per-warp scratch
   unsigned char* wbase = smem_raw + sizeof(SharedWeights);
   constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
-  constexpr size_t kWarpBytesGlob = (size_t)MAX_NODES * 4 + 2 * MAX_NODES;
   WarpScratch W;
-  if (SMEM_BUF) {
+  {
     unsigned char* p = wbase + (size_t)warp * kWarpBytesSmem;
-    W.y = reinterpret_cast<float*>(p);
+    W.ysm = reinterpret_cast<float*>(p);
+    W.y = W.ysm;
     W.g = W.y + SMEM_NODES * NODE_EMB;
     W.dinv = W.g + SMEM_NODES * NODE_EMB;
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
     W.dynb = W.pos + MAX_NODES;
-  } else {
-    unsigned char* p = wbase + (size_t)warp * kWarpBytesGlob;
-    W.dinv = reinterpret_cast<float*>(p);
-    W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
-    W.dynb = W.pos + MAX_NODES;
-    W.y = W.g = nullptr;
   }
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
@@ -460,9 +455,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       else if (i < c0 + c1) b = S.worklist[(size_t)P.B + (i - c0)];
       else b = S.worklist[(size_t)2 * P.B + (i - c0 - c1)];
     }
+    // node-embedding buffers: shared memory while the env's visible graph has <= 32 nodes (always, when the
+    // scenarios have <= 32 nodes), its slab of the L2-resident scratch otherwise.  A reset shrinks the graph to 1 node.
     if (!SMEM_BUF) {
-      W.y = S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
-      W.g = W.y + (size_t)P.ncap * NODE_EMB;
+      const bool small = scalar(S, P, S_N_DISC, b) <= SMEM_NODES;
+      W.y = small ? W.ysm : S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
+      W.g = small ? W.ysm + SMEM_NODES * NODE_EMB : W.y + (size_t)P.ncap * NODE_EMB;
     }
     const int flags = scalar(S, P, S_FLAGS, b);
     bool do_reset = false;
@@ -486,6 +484,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     }
     if (do_reset) {
       reset_env(T, P, S, b, lane);
+      W.y = W.ysm;                               // a fresh episode's graph is one node
+      W.g = W.ysm + SMEM_NODES * NODE_EMB;
       encode_env(T, P, S, SW, W, b, lane);
       build_table(T, P, S, W, b, lane);
     }
@@ -502,8 +502,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 }
 
 size_t observe_smem_bytes(bool smem_buf) {
-  const size_t per_warp = smem_buf ? ((size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES)
-                                   : ((size_t)MAX_NODES * 4 + 2 * MAX_NODES);
+  (void)smem_buf;
+  const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 
@@ -512,8 +512,8 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
   static const bool force_global = getenv("CBS_OBS_GLOBAL") != nullptr;   // experiment switch
   const bool smem_buf = P.ncap <= SMEM_NODES && !force_global;
   const size_t smem = observe_smem_bytes(smem_buf);
-  // persistent grid: one CTA per SM when the node buffers live in shared memory (181 KB), four otherwise
-  int grid = num_sms * (smem_buf ? 1 : 4);
+  // persistent grid: one CTA of 8 warps per SM (181 KB of shared memory: weights + per-warp node buffers)
+  int grid = num_sms;
   const int need = (P.B + OBS_WARPS - 1) / OBS_WARPS;
   if (grid > need) grid = need;
   static bool attr_set[2] = {false, false};
