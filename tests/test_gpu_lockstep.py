@@ -28,8 +28,15 @@ def philox_pick(seed, env, step, stream, n):
     return (_philox_uniform(seed, env, step, stream) * n) >> 32
 
 
-@pytest.mark.parametrize("goal,sizes", [("control", (8, 24)), ("discovery", (8, 14)), ("control", (40, 70))])
-def test_lockstep_heterogeneous_batch(goal, sizes):
+@pytest.mark.parametrize("goal,sizes,pool_size,B,T", [
+    ("control", (8, 24), 120, 40, 70),
+    ("discovery", (8, 14), 120, 40, 70),
+    ("control", (40, 70), 120, 40, 70),
+    ("disruption", (6, 12), 60, 33, 60),          # odd batch size
+    ("control", (120, 128), 330, 4, 140),         # maximum node count (4 mask words, 255 snapshot slots), Ug > 256: two GEMM N-tiles
+    ("control", (3, 5), 30, 1, 80),               # a single env, tiny scenarios
+], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny"])
+def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
     import torch
     from scipy.spatial import distance
     import ccbs_b200 as cb
@@ -41,9 +48,10 @@ def test_lockstep_heterogeneous_batch(goal, sizes):
     from tests.gpu_harness import masks_to_u64
 
     rng = np.random.default_rng(5)
-    pool = cb.synthetic_vuln_pool(99, 120)
-    S, B, T, seed, offset = 6, 40, 70, 12345, 1000
-    specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool) for k in range(S)]
+    pool = cb.synthetic_vuln_pool(99, pool_size)
+    S, seed, offset = (6 if sizes[1] < 100 else 2), 12345, 1000
+    gkw = dict(vulns_per_service_range=(6, 14)) if pool_size > 256 else {}
+    specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool, **gkw) for k in range(S)]
     cfg = cb.EnvConfig(goal=goal)
     w = GaeWeights.random(3)
     sc_of_env = rng.integers(0, S, size=B).astype(np.int32)
@@ -108,7 +116,9 @@ def test_lockstep_heterogeneous_batch(goal, sizes):
     sc = env.scalars()
     assert flips <= max(1, B * T // 200), f"{flips} near-tie flips in {B * T} env-steps"
     assert np.array_equal(sc[L.S_EPISODES], np.array(episodes))
-    assert sum(episodes) > B, "test too short to exercise auto-reset"
+    assert sum(episodes) >= (B if sizes[1] < 100 else 1), "test too short to exercise auto-reset"
+    if pool_size > 256:
+        assert tables.vemb32.shape[0] > 256
     acc = env.stat_accum()
     assert acc["episodes"] == sum(episodes)
     env.close()
