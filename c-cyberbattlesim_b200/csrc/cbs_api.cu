@@ -12,9 +12,10 @@ namespace cbs {
 cudaError_t launch_decode_gemm_simt(const float*, int, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
 bool decode_gemm_tc_available();
-cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int32_t*, double*, cudaStream_t);
+cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int, int, const float*, float*, uint8_t*,
+                                 int32_t*, double*, cudaStream_t);
 cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, int, int, cudaStream_t);
-cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, float*,
+cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, int, float*,
                               uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
 
 __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
@@ -52,6 +53,7 @@ struct cbs_handle {
   int Ug = 0, vt_stride = 0;
   int64_t launches = 0;
   bool use_tc = false;
+  int sched_buf = 0;     // cost-bin buffer the next decode reads (the transitions of that step fill the other one)
   int num_sms = 148;
   float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
   // host-step staging
@@ -228,7 +230,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
-  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, SCHED_BINS + 1); AL(bin_list, (size_t)SCHED_BINS * B);
+  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
@@ -284,6 +286,8 @@ int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double prop) {
   return CBS_OK;
 }
 
+static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st);
+
 static int check_ready(cbs_handle* h) {
   if (!h) return CBS_ERR_INVALID_ARG;
   if (!h->loaded) return fail(h, CBS_ERR_NOT_READY, "scenarios not loaded");
@@ -306,14 +310,8 @@ int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double
   if (rc) return rc;
   if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_decode: actions is null");
   cudaStream_t st = (cudaStream_t)stream;
-  if (h->use_tc) {
-    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
-    h->launches += 2;
-  } else {
-    CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
-    h->launches += 1;
-  }
-  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, sel_dev, dist_dev, st));
+  if ((rc = launch_gemm(h, actions_dev, st))) return rc;
+  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, sel_dev, dist_dev, st));
   h->launches += 1;
   return CBS_OK;
 }
@@ -323,8 +321,9 @@ int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev
   int rc = check_ready(h);
   if (rc) return rc;
   if (!sel_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_transition: sel is null");
-  CK(h, launch_transition(h->T, h->P, h->S, sel_dev, dist_dev, uniforms_dev, reward_dev, done_dev, truncated_dev, outcome_dev,
-                          (cudaStream_t)stream));
+  CK(h, launch_transition(h->T, h->P, h->S, sel_dev, dist_dev, uniforms_dev, h->sched_buf ^ 1, reward_dev, done_dev, truncated_dev,
+                          outcome_dev, (cudaStream_t)stream));
+  h->sched_buf ^= 1;
   h->launches += 1;
   return CBS_OK;
 }
@@ -338,14 +337,31 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
   return CBS_OK;
 }
 
+static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st) {
+  if (h->use_tc) {
+    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+    h->launches += (h->P.act_stride % 4 == 0) ? 1 : 2;
+  } else {
+    CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
+    h->launches += 1;
+  }
+  return CBS_OK;
+}
+
 int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* obs_dev, float* reward_dev,
              uint8_t* done_dev, int32_t* info_dev, uintptr_t stream) {
-  int rc = cbs_decode(h, actions_dev, h ? h->d_sel : nullptr, h ? h->d_dist : nullptr, stream);
+  int rc = check_ready(h);
   if (rc) return rc;
-  rc = cbs_transition(h, h->d_sel, h->d_dist, uniforms_dev, reward_dev, done_dev, nullptr, nullptr, stream);
-  if (rc) return rc;
+  if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_step: actions is null");
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = launch_gemm(h, actions_dev, st))) return rc;
+  // fused: every warp runs the transition of its env right after decoding it (no separate transition launch)
+  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 1, uniforms_dev, reward_dev, done_dev,
+                             nullptr, nullptr, st));
+  h->sched_buf ^= 1;
+  h->launches += 1;
   if (info_dev) {   // before observe: an auto-reset clears the per-step flags
-    info_kernel<<<(h->P.B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, info_dev);
+    info_kernel<<<(h->P.B + 255) / 256, 256, 0, st>>>(h->P, h->S, info_dev);
     CK(h, cudaGetLastError());
     h->launches += 1;
   }
@@ -372,9 +388,10 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
     CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
     CK(h, cudaEventRecord(ev[2], st));
   }
-  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->d_sel, h->d_dist, st));
+  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, h->d_sel, h->d_dist, st));
   CK(h, cudaEventRecord(ev[3], st));
-  CK(h, launch_transition(h->T, h->P, h->S, h->d_sel, h->d_dist, uniforms_dev, nullptr, nullptr, nullptr, nullptr, st));
+  CK(h, launch_transition(h->T, h->P, h->S, h->d_sel, h->d_dist, uniforms_dev, h->sched_buf ^ 1, nullptr, nullptr, nullptr, nullptr, st));
+  h->sched_buf ^= 1;
   CK(h, cudaEventRecord(ev[4], st));
   CK(h, launch_observe(h->T, h->P, h->S, nullptr, 0, h->num_sms, st));
   CK(h, cudaEventRecord(ev[5], st));

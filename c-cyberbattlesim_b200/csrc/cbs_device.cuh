@@ -39,10 +39,12 @@ __device__ __forceinline__ int sched_bin(int rows) {
   const int b = 31 - __clz((rows >> 5) | 1);   // rows < 64 -> 0, < 128 -> 1, ...
   return b < SCHED_BINS - 1 ? b : SCHED_BINS - 1;
 }
-__device__ __forceinline__ void sched_enqueue(const State& S, const Params& P, int b) {
+// The bins are double buffered: a decode reads (and finally clears) buffer `p` while the transitions of the same
+// step fill buffer `p ^ 1` for the next decode.
+__device__ __forceinline__ void sched_enqueue(const State& S, const Params& P, int b, int buf) {
   const int bin = sched_bin(S.work_est[b]);
-  const int pos = atomicAdd(&S.bin_cnt[bin], 1);
-  if (pos < P.B) S.bin_list[(size_t)bin * P.B + pos] = b;
+  const int pos = atomicAdd(&S.bin_cnt[buf * (SCHED_BINS + 1) + bin], 1);
+  if (pos < P.B) S.bin_list[((size_t)buf * SCHED_BINS + bin) * P.B + pos] = b;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

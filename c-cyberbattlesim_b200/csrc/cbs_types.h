@@ -109,8 +109,8 @@ struct State {  // mutable, device pointers
   int32_t* worklist;     // [3][B] envs whose step needs graph work, by cost class (episode end / re-encode / edge only)
   int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling), [4..6] class list lengths
   int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)
-  int32_t* bin_cnt;      // [SCHED_BINS + 1] envs per cost bin (filled by the transition for the next decode), [SCHED_BINS] = finished-CTA counter
-  int32_t* bin_list;     // [SCHED_BINS][B] env ids per bin
+  int32_t* bin_cnt;      // [2][SCHED_BINS + 1] envs per cost bin (double buffered; filled by the transition for the next decode), [SCHED_BINS] = finished-warp counter
+  int32_t* bin_list;     // [2][SCHED_BINS][B] env ids per bin
 };
 
 __host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {

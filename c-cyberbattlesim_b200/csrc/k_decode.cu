@@ -13,7 +13,7 @@
 // np.argmin over the reference's insertion-ordered dict.
 #include <cstdlib>
 
-#include "cbs_device.cuh"
+#include "transition.cuh"
 
 namespace cbs {
 
@@ -195,21 +195,32 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
 }
 
 // every warp calls this exactly once when it is finished; the last one clears the cost bins for the next transition
-__device__ __forceinline__ void sched_done(const State& S) {
+__device__ __forceinline__ void sched_done(const State& S, int buf) {
   __syncwarp();
   if ((threadIdx.x & 31) == 0) {
+    int32_t* cnt = S.bin_cnt + buf * (SCHED_BINS + 1);
     __threadfence();
-    if (atomicAdd(&S.bin_cnt[SCHED_BINS], 1) == (int)(gridDim.x * SEL_WARPS) - 1) {
+    if (atomicAdd(&cnt[SCHED_BINS], 1) == (int)(gridDim.x * SEL_WARPS) - 1) {
 #pragma unroll
-      for (int k = 0; k <= SCHED_BINS; ++k) S.bin_cnt[k] = 0;
+      for (int k = 0; k <= SCHED_BINS; ++k) cnt[k] = 0;
       __threadfence();
     }
   }
 }
 
+// what the fused kernel needs to run the transition right after the decode (cbs_step)
+struct FusedTransition {
+  int enabled;
+  const float* uniforms;
+  float* reward;
+  uint8_t* done;
+};
+
+template <bool FUSE>
 __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
-                                                                   int vt_stride, int vt_cached, int32_t* __restrict__ sel_out,
-                                                                   double* __restrict__ dist_out, long long* __restrict__ trace) {
+                                                                   int vt_stride, int vt_cached, int sched_buf, FusedTransition ft,
+                                                                   int32_t* __restrict__ sel_out, double* __restrict__ dist_out,
+                                                                   long long* __restrict__ trace) {
   extern __shared__ __align__(16) unsigned char sel_smem[];
   SelWarp* sh_all = reinterpret_cast<SelWarp*>(sel_smem);
   float* vn2_sh = reinterpret_cast<float*>(sel_smem + SEL_WARPS * sizeof(SelWarp));          // [vt_cached] shared by the CTA
@@ -223,12 +234,12 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
   {
     int cnt[SCHED_BINS], tot = 0;
 #pragma unroll
-    for (int k = 0; k < SCHED_BINS; ++k) { cnt[k] = S.bin_cnt[k]; tot += cnt[k]; }
+    for (int k = 0; k < SCHED_BINS; ++k) { cnt[k] = S.bin_cnt[sched_buf * (SCHED_BINS + 1) + k]; tot += cnt[k]; }
     if (tot == P.B && b < P.B) {
       int w = b;
 #pragma unroll
       for (int k = SCHED_BINS - 1; k >= 0; --k) {
-        if (w >= 0 && w < cnt[k]) { b = S.bin_list[(size_t)k * P.B + w]; w = -1; }
+        if (w >= 0 && w < cnt[k]) { b = S.bin_list[((size_t)sched_buf * SCHED_BINS + k) * P.B + w]; w = -1; }
         else if (w >= 0) w -= cnt[k];
       }
     }
@@ -271,21 +282,21 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
     na = sqrt(warp_sum(n0 + n1));
   }
   __syncthreads();
-  if (!in_range) { sched_done(S); return; }
+  if (!in_range) { sched_done(S, sched_buf); return; }
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     if (lane == 0) {
       reinterpret_cast<int4*>(S.sel)[b] = make_int4(0, 0, 0, 0);
       S.dist[b] = 0.0;
       if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
       if (dist_out) dist_out[b] = 0.0;
+      if (FUSE) transition_env(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
     }
-    sched_done(S);
+    sched_done(S, sched_buf);
     return;
   }
   const uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
   const float* vt_g = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
-  const int ug = T.num_global_vulns;
 
   float run_max = -INFINITY;
   Best best{INFINITY, ~0ull, 0, 0, -1, 0u};
@@ -418,7 +429,6 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
     }
     __syncwarp();
   }
-  (void)ug;
   n_exact += ncand;
   flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best);
   if (lane == 0) {
@@ -438,24 +448,36 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       long long* tr = trace + (size_t)b * 6;
       tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
     }
+    // fused step: the transition of this env runs here, on one lane, while the other warps are still scanning
+    if (FUSE) transition_env(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
   }
-  sched_done(S);
+  sched_done(S, sched_buf);
 }
 
 long long* g_sel_trace = nullptr;   // debug: per-env {cycles, rows, live pairs, parked candidates, combos, start clock}
 
 cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& S, const float* actions, int vt_stride,
+                                 int sched_buf, int fuse_transition, const float* uniforms, float* reward, uint8_t* done,
                                  int32_t* sel_out, double* dist_out, cudaStream_t stream) {
+  const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
   const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(decode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr[2] = {0, 0};
+  const int which = fuse_transition ? 1 : 0;
+  if (smem > 48 * 1024 && smem > attr[which]) {
+    cudaError_t e = fuse_transition
+                        ? cudaFuncSetAttribute(decode_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(decode_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
+    attr[which] = smem;
   }
-  decode_select_kernel<<<(P.B + SEL_WARPS - 1) / SEL_WARPS, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached,
-                                                                                        sel_out, dist_out, g_sel_trace);
+  const int grid = (P.B + SEL_WARPS - 1) / SEL_WARPS;
+  if (fuse_transition)
+    decode_select_kernel<true><<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,
+                                                                   dist_out, g_sel_trace);
+  else
+    decode_select_kernel<false><<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,
+                                                                    dist_out, g_sel_trace);
   return cudaGetLastError();
 }
 

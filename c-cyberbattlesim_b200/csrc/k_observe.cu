@@ -11,8 +11,6 @@
 // message is a 17-term combination of those rows with [ReLU(W1 e + b1); 1].  GCNConv is a 64x64 projection
 // (weights staged once per CTA in shared memory) followed by the degree-normalised neighbour sum.  Node
 // embeddings of one env live in shared memory (<= 32 nodes) or in an L2-resident scratch slab (<= 128 nodes).
-#include <cstdlib>
-
 #include "cbs_device.cuh"
 #include "philox.cuh"
 
@@ -389,7 +387,8 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
   __syncwarp();
 }
 
-template <bool SMEM_BUF>
+// BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
+template <bool BIG_GRAPHS>
 __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Params P, State S,
                                                                 const uint8_t* __restrict__ reset_mask, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -457,7 +456,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     }
     // node-embedding buffers: shared memory while the env's visible graph has <= 32 nodes (always, when the
     // scenarios have <= 32 nodes), its slab of the L2-resident scratch otherwise.  A reset shrinks the graph to 1 node.
-    if (!SMEM_BUF) {
+    if (BIG_GRAPHS) {
       const bool small = scalar(S, P, S_N_DISC, b) <= SMEM_NODES;
       W.y = small ? W.ysm : S.scratch + (size_t)b * 2 * P.ncap * NODE_EMB;
       W.g = small ? W.ysm + SMEM_NODES * NODE_EMB : W.y + (size_t)P.ncap * NODE_EMB;
@@ -501,37 +500,28 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
   }
 }
 
-size_t observe_smem_bytes(bool smem_buf) {
-  (void)smem_buf;
+size_t observe_smem_bytes() {
   const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 
 cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, int mode,
                            int num_sms, cudaStream_t stream) {
-  static const bool force_global = getenv("CBS_OBS_GLOBAL") != nullptr;   // experiment switch
-  const bool smem_buf = P.ncap <= SMEM_NODES && !force_global;
-  const size_t smem = observe_smem_bytes(smem_buf);
+  const bool big = P.ncap > SMEM_NODES;
+  const size_t smem = observe_smem_bytes();
   // persistent grid: one CTA of 8 warps per SM (181 KB of shared memory: weights + per-warp node buffers)
   int grid = num_sms;
   const int need = (P.B + OBS_WARPS - 1) / OBS_WARPS;
   if (grid > need) grid = need;
   static bool attr_set[2] = {false, false};
-  if (smem_buf) {
-    if (!attr_set[0]) {
-      cudaError_t e = cudaFuncSetAttribute(observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set[0] = true;
-    }
-    observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
-  } else {
-    if (!attr_set[1]) {
-      cudaError_t e = cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      attr_set[1] = true;
-    }
-    observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
+  if (!attr_set[big]) {
+    cudaError_t e = big ? cudaFuncSetAttribute(observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set[big] = true;
   }
+  if (big) observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
+  else observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
   return cudaGetLastError();
 }
 
