@@ -45,6 +45,10 @@ CASES = {
     # 100-node "default-like" scenario (configs[0]); >64 nodes exercises 4-word masks
     "g100_control": dict(graph_seed=16, nodes=100, steps=1200, pool_size=560, services_range=(1, 4),
                          vulns_per_service_range=(8, 18), cfg=dict(goal="control")),
+    # every DoS row filtered out of the action table (compressed:536-538), non-default reward scale, stricter isolation filter
+    "g14_removeall": dict(graph_seed=19, nodes=14, steps=600,
+                          cfg=dict(goal="discovery", remove_all_obstacles=True, remove_main_obstacles=False, winning_reward=300,
+                                   losing_reward=-700, isolation_filter_threshold=0.3, proportional_cutoff_coefficient=2)),
     # scripted attacker (oracle.trace.policy_pick): owns many nodes, escalates, reaches the goal -> winning reward,
     # large action tables, many snapshot slots.  `policy` = noise sigma added to the chosen table row.
     "p6_control_win": dict(graph_seed=30, nodes=6, steps=500, policy=0.02,

@@ -27,7 +27,10 @@ def test_oracle_replays_reference_trace(name, golden_dir):
     assert report["obs"] <= 1e-5
     # the fixtures exercise what they claim to
     codes = set(case["trace"]["code"].tolist())
-    assert {0, 1, 2, 3, 4, 5, 6, 7, 9} <= codes          # every success kind that can enter the table
+    if name == "g14_removeall":                           # remove_all_obstacles: no DoS row is ever in the table
+        assert 0 not in codes and {1, 2, 3, 4, 5, 6, 7, 9} <= codes
+    else:
+        assert {0, 1, 2, 3, 4, 5, 6, 7, 9} <= codes      # every success kind that can enter the table
     assert int(case["trace"]["num_episodes"]) > (5 if name.startswith("g") else 1)
     if name in ("p6_control_win", "p6_control_nostop"):   # scripted-attacker cases that must actually reach the goal
         assert (case["trace"]["reason"] == 1).sum() > 0
