@@ -340,7 +340,7 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
 static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st) {
   if (h->use_tc) {
     CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
-    h->launches += (h->P.act_stride % 4 == 0) ? 1 : 2;
+    h->launches += 1;
   } else {
     CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
     h->launches += 1;

@@ -89,10 +89,18 @@ __global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restri
   for (int i = threadIdx.x & 127; i < VULN_EMB; i += 128) dst[i] = src[i];
 }
 
-__global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                                const __grid_constant__ CUtensorMap map_b,
-                                                                float* __restrict__ vt, int B, int Upad, int nt_box,
-                                                                int vt_stride, int32_t* errflag, int direct) {
+// LDGSTS_A = false: both operands arrive by TMA (A from the repacked slab, or in place when the caller's action rows
+//            have a 16-byte-multiple pitch).  128 threads.
+// LDGSTS_A = true:  the caller's action rows are only 4-byte aligned (dense [B,905]); four extra producer warps stage
+//            the A slab with 4-byte cp.async straight into the 128-byte-swizzled layout the UMMA descriptor expects
+//            (16-byte chunk c of row r lands at chunk c ^ (r & 7)) and arrive on the stage's full barrier when their
+//            copies land (cp.async.mbarrier.arrive.noinc); no repack pass over HBM.  256 threads.
+template <bool LDGSTS_A>
+__global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                                 const __grid_constant__ CUtensorMap map_b,
+                                                                                 const float* __restrict__ actions, int act_stride,
+                                                                                 float* __restrict__ vt, int B, int Upad, int nt_box,
+                                                                                 int vt_stride, int32_t* errflag, int direct) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = A_STAGE_BYTES + nt_box * BK * 4;
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
   constexpr int KB = VULN_EMB / BK;                  // 24 slabs
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, LDGSTS_A ? 1 + 128 : 1); mbar_init(empty0 + 8 * s, 1); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,7 +130,7 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
 
   if (warp == 0 && lane == 0) {
     // ---- TMA producer ----
-    const uint32_t bytes = (uint32_t)stage_bytes;
+    const uint32_t bytes = (uint32_t)(LDGSTS_A ? stage_bytes - A_STAGE_BYTES : stage_bytes);
     for (int kb = 0; kb < KB; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (kb / STAGES) & 1;
@@ -131,7 +139,7 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       // direct: map_a is the caller's action tensor itself (row pitch a multiple of 16 bytes), the 768-float
       // vulnerability part starts 128 floats into each row; otherwise map_a is the repacked [B,768] slab
-      tma_load_2d(sa, &map_a, full0 + 8 * s, (direct ? 2 * NODE_EMB : 0) + kb * BK, m0);
+      if (!LDGSTS_A) tma_load_2d(sa, &map_a, full0 + 8 * s, (direct ? 2 * NODE_EMB : 0) + kb * BK, m0);
       tma_load_2d(sa + A_STAGE_BYTES, &map_b, full0 + 8 * s, kb * BK, n0);
     }
   } else if (warp == 1 && lane == 0) {
@@ -143,6 +151,7 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
       const uint32_t ph = (kb / STAGES) & 1;
       ok = mbar_wait(full0 + 8 * s, ph, errflag);
       if (!ok) break;
+      if (LDGSTS_A) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async wrote through the generic proxy
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sa = smem_u32(smem + s * stage_bytes);
       const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_STAGE_BYTES);
@@ -152,11 +161,31 @@ __global__ void __launch_bounds__(128, 1) decode_gemm_tc_kernel(const __grid_con
       umma_commit(empty0 + 8 * s);            // frees the smem stage when these MMAs retire
     }
     umma_commit(tfull);                       // accumulator complete
+  } else if (LDGSTS_A && warp >= 4) {
+    // ---- A producers (4 warps): 32 coalesced 4-byte cp.async per thread per slab, rows beyond B are zero-filled ----
+    const int t = threadIdx.x - 128;
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (!mbar_wait(empty0 + 8 * s, ph ^ 1, errflag)) break;
+      const uint32_t sa = smem_u32(smem + s * stage_bytes);
+#pragma unroll 8
+      for (int i = 0; i < BM * BK / 128; ++i) {
+        const int idx = i * 128 + t, r = idx >> 5, k = idx & 31;
+        const uint32_t dst = sa + r * 128 + ((((uint32_t)k >> 2) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)k & 3u) * 4;
+        const int row = m0 + r;
+        const float* src = actions + (size_t)(row < B ? row : 0) * act_stride + 2 * NODE_EMB + kb * BK + k;
+        const uint32_t nbytes = row < B ? 4u : 0u;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(nbytes) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full0 + 8 * s) : "memory");
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   }
   __syncwarp();
 
   // ---- epilogue: TMEM -> registers -> global (every warp owns TMEM lanes [32w, 32w+32) = tile rows) ----
-  const bool ready = mbar_wait(tfull, 0, errflag);
+  const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const int row = m0 + warp * 32 + lane;
   if (ready) {
@@ -230,25 +259,34 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
   // tensor maps are rebuilt per launch (host-side encode, ~1 us each): the operands never move, but keeping the
   // maps out of the handle keeps this translation unit self-contained
   CUtensorMap map_a, map_b;
-  // Direct mode: TMA reads the action tensor in place when its row pitch is a multiple of 16 bytes (e.g. 908 floats).  A dense [B,905] tensor has 3620-byte rows, which
-  // TMA cannot address (an unaligned box start faults as an illegal instruction), so it is repacked first.
+  // A operand: (1) row pitch a multiple of 16 bytes (e.g. 908 floats): TMA reads the action tensor in place;
+  // (2) dense [B,905] (3620-byte rows: TMA cannot address them, an unaligned box start faults as an illegal
+  // instruction): producer warps stage it with 4-byte cp.async; (3) CBS_TMA_PACK=1: repack into an aligned slab first
+  // (the first working version, kept for comparison).
+  static const bool force_pack = getenv("CBS_TMA_PACK") != nullptr;
   const bool direct = (act_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(actions) & 15) == 0);
+  const bool ldgsts = !direct && !force_pack;
   if (direct) {
     if (!make_map(&map_a, actions, (uint64_t)B, BM, (uint64_t)act_stride, (uint64_t)ACTION_DIM)) return cudaErrorInvalidValue;
   } else {
     if (!make_map(&map_a, a_packed, (uint64_t)B, BM)) return cudaErrorInvalidValue;
-    pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B, act_stride);
+    if (!ldgsts) pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B, act_stride);
   }
   if (!make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box)) return cudaErrorInvalidValue;
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)nt_box * BK * 4) + 1024 + 256;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(decode_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[ldgsts]) {
+    cudaError_t e = ldgsts ? cudaFuncSetAttribute(decode_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(decode_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
+    attr[ldgsts] = smem;
   }
   dim3 grid((B + BM - 1) / BM, (Upad + NT_MAX - 1) / NT_MAX);
-  decode_gemm_tc_kernel<<<grid, 128, smem, stream>>>(map_a, map_b, vt, B, Upad, nt_box, vt_stride, errflag, direct ? 1 : 0);
+  if (ldgsts)
+    decode_gemm_tc_kernel<true><<<grid, 256, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag, 0);
+  else
+    decode_gemm_tc_kernel<false><<<grid, 128, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag,
+                                                             direct ? 1 : 0);
   return cudaGetLastError();
 }
 
