@@ -2,11 +2,11 @@
 
 Importable as ``ccbs_b200`` (see ``ccbs_b200.py`` at the repo root; the directory name
 ``c-cyberbattlesim_b200`` is not a valid Python identifier)."""
-from . import constants  # noqa: F401
+from . import constants, config  # noqa: F401
 from .config import EnvConfig  # noqa: F401
 from .scenario import (ScenarioSpec, NodeSpec, VulnSpec, ResultSpec, ServiceSpec, ScenarioTables,  # noqa: F401
                        compile_scenarios, spec_from_model, synthetic_spec, synthetic_input_graph,
-                       spec_from_input_graph, synthetic_vuln_pool)
+                       spec_from_input_graph, synthetic_vuln_pool, load_scenario_folder)
 
 from .gae import GaeWeights, fold_gae  # noqa: F401,E402
 

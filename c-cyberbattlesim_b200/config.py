@@ -71,6 +71,17 @@ class EnvConfig:
     def from_reference_dicts(cls, train_config: dict, rewards_config: dict, goal: str = "control") -> "EnvConfig":
         """Build from the dicts the reference loads with yaml (agents/train_agent.py:229-239)."""
         keys = {f for f in cls.__dataclass_fields__}
+        # reference options the batched env does not implement must not be dropped silently
+        if train_config.get("static_defender_agent"):
+            raise ValueError("static defenders are not implemented by the batched env (DESIGN.md §5)")
+        if train_config.get("distance_metric", "cosine") != "cosine":
+            raise ValueError("only the cosine decode metric is implemented")
+        if train_config.get("sample_subset_samples"):
+            import warnings
+            warnings.warn("sample_subset_samples is ignored: the batched decode always scans the full action table "
+                          "(the reference sub-samples it with np.random.choice to bound cdist time)", stacklevel=2)
+        if train_config.get("pca_components") not in (None, False, 768):
+            raise ValueError("only 768-dimensional vulnerability embeddings are implemented")
         kw = {k: v for k, v in train_config.items() if k in keys}
         kw["goal"] = goal
         kw["rewards_dict"] = dict(rewards_config["rewards_dict"][goal])

@@ -99,10 +99,20 @@ _KIND_BY_CLASSNAME = {
 }
 
 
-def spec_from_model(model, name: str = "") -> ScenarioSpec:
-    """Flatten a reference ``Model`` (model.py:349-437) whose feature vectors were already
-    resolved to one LM (``update_feature_vectors``, model.py:423-430).  Node order = order of
-    ``model.network.nodes`` (that order defines starter indices and graph insertion order)."""
+def _vector(v, feature_extractor):
+    """A feature vector is a list of floats, or a dict {LM name: list} before Model.update_feature_vectors
+    (model.py:423-430) resolved it."""
+    if isinstance(v, dict):
+        if feature_extractor is None or feature_extractor not in v:
+            raise ValueError(f"feature vectors are per-LM dicts {sorted(v)}; pass feature_extractor=<one of them>")
+        v = v[feature_extractor]
+    return np.asarray(v, dtype=np.float64)
+
+
+def spec_from_model(model, name: str = "", feature_extractor: Optional[str] = None) -> ScenarioSpec:
+    """Flatten a reference ``Model`` (model.py:349-437).  Feature vectors may already be resolved to one LM
+    (``update_feature_vectors``, model.py:423-430) or still be per-LM dicts (then ``feature_extractor`` picks one).
+    Node order = order of ``model.network.nodes`` (that order defines starter indices and graph insertion order)."""
     net = model.network
     ids = list(net.nodes)
     index = {nid: i for i, nid in enumerate(ids)}
@@ -111,7 +121,7 @@ def spec_from_model(model, name: str = "") -> ScenarioSpec:
     for nid in ids:
         info = net.nodes[nid]["data"]
         services = [ServiceSpec(port=int(s.name), running=bool(s.running),
-                                fv=np.asarray(s.feature_vector, dtype=np.float64)) for s in info.services]
+                                fv=_vector(s.feature_vector, feature_extractor)) for s in info.services]
         vulns = []
         for vid, v in info.vulnerabilities.items():
             results = []
@@ -128,7 +138,7 @@ def spec_from_model(model, name: str = "") -> ScenarioSpec:
             vulns.append(VulnSpec(vid=str(vid), port=int(v.port), priv_required=int(v.privileges_required),
                                   success_rate=float(v.rates.successRate), cost=float(v.cost), results=results))
             # create_vulnerabilities_embeddings (compressed:614-618): later nodes overwrite earlier ones
-            vuln_emb[str(vid)] = np.asarray(v.embedding, dtype=np.float64)
+            vuln_emb[str(vid)] = _vector(v.embedding, feature_extractor)
         nodes.append(NodeSpec(
             node_id=str(nid), tag=str(info.tag), value=int(info.value), has_data=bool(info.has_data),
             visible=bool(info.visible), level_at_access=int(info.level_at_access),
@@ -148,6 +158,30 @@ def spec_from_model(model, name: str = "") -> ScenarioSpec:
     except Exception:
         spec.ref_counts = None
     return spec
+
+
+def load_scenario_folder(folder: str, nlp_extractor: str, pca_components: int = 768, subset: Optional[str] = None):
+    """Load the reference's scenario layout ``<folder>/<id>/network_<nlp>.pkl`` (+ ``pca/num_components=<k>/`` when PCA was
+    applied) exactly as agents/train_agent.py:380-390 does, optionally restricted to the ids of ``split.yaml``'s
+    ``training_set`` / ``validation_set`` (agents/train_agent.py:419-428).  The pickles hold reference ``Model`` objects, so
+    the reference package must be importable for unpickling; nothing else of it is used.  Returns (ids, specs)."""
+    import os
+    import pickle
+    ids = sorted(int(e) for e in os.listdir(folder) if e.isdigit() and os.path.isdir(os.path.join(folder, e)))
+    if subset is not None:
+        import yaml
+        with open(os.path.join(folder, "split.yaml")) as f:
+            wanted = {int(e["id"]) for e in yaml.safe_load(f)[subset]}
+        ids = [i for i in ids if i in wanted]
+    specs = []
+    for i in ids:
+        sub = os.path.join(folder, str(i))
+        if pca_components != 768:
+            sub = os.path.join(sub, "pca", f"num_components={pca_components}")
+        with open(os.path.join(sub, f"network_{nlp_extractor}.pkl"), "rb") as f:
+            model = pickle.load(f)
+        specs.append(spec_from_model(model, name=str(i), feature_extractor=nlp_extractor))
+    return ids, specs
 
 
 # --------------------------------------------------------------------------------------------

@@ -1,0 +1,64 @@
+"""Scenario folders in the reference's layout (pickled reference Models + split.yaml) load into the same tables as the
+in-memory Models; reference-only (needs /root/reference for the Model class)."""
+import os
+import pickle
+
+import numpy as np
+import pytest
+import yaml
+
+import ccbs_b200 as cb
+
+pytestmark = [pytest.mark.reference,
+              pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")]
+
+
+def test_load_scenario_folder_roundtrip(tmp_path):
+    from oracle import ref_bridge as rb
+    pool = cb.synthetic_vuln_pool(3, 40)
+    models = {}
+    for i in (1, 2, 3):
+        g = cb.synthetic_input_graph(900 + i, 6 + i, pool=pool)
+        models[i] = rb.reference_model_from_input_graph(g, seed=i)
+        os.makedirs(tmp_path / str(i))
+        with open(tmp_path / str(i) / "network_bert.pkl", "wb") as f:
+            pickle.dump(models[i], f)
+    with open(tmp_path / "split.yaml", "w") as f:
+        yaml.safe_dump({"training_set": [{"id": 1}, {"id": 3}], "validation_set": [{"id": 2}]}, f)
+    ids, specs = cb.load_scenario_folder(str(tmp_path), "bert", subset="training_set")
+    assert ids == [1, 3]
+    direct = cb.compile_scenarios([cb.spec_from_model(models[1]), cb.spec_from_model(models[3])])
+    loaded = cb.compile_scenarios(specs)
+    for name in ("row_packed", "vi_flags", "vi_success", "nd_ownable", "nd_discoverable", "recon_nodes", "outblock", "vemb64"):
+        assert np.array_equal(getattr(direct, name), getattr(loaded, name)), name
+    ids_all, _ = cb.load_scenario_folder(str(tmp_path), "bert")
+    assert ids_all == [1, 2, 3]
+
+
+def test_per_lm_feature_vectors_are_resolved():
+    from oracle import ref_bridge as rb
+    g = cb.synthetic_input_graph(950, 5, pool=cb.synthetic_vuln_pool(3, 40))
+    model = rb.reference_model_from_input_graph(g, seed=1)
+    want = cb.spec_from_model(model)
+    for n in model.network.nodes:                      # un-resolve: {LM: vector} as the scenario generator stores them
+        info = model.network.nodes[n]["data"]
+        for s in info.services:
+            s.feature_vector = {"bert": s.feature_vector, "gpt2": [0.0] * 768}
+        for v in info.vulnerabilities.values():
+            v.embedding = {"bert": v.embedding, "gpt2": [0.0] * 768}
+    got = cb.spec_from_model(model, feature_extractor="bert")
+    assert np.array_equal(cb.compile_scenarios([want]).vemb64, cb.compile_scenarios([got]).vemb64)
+    with pytest.raises(ValueError):
+        cb.spec_from_model(model)
+
+
+def test_unsupported_reference_options_are_not_silently_dropped():
+    rewards = {"rewards_dict": {"control": cb.config.DEFAULT_REWARDS["control"]},
+               "penalties_dict": {"control": cb.config.DEFAULT_PENALTIES["control"]}}
+    with pytest.raises(ValueError):
+        cb.EnvConfig.from_reference_dicts({"static_defender_agent": "reimage"}, rewards)
+    with pytest.raises(ValueError):
+        cb.EnvConfig.from_reference_dicts({"distance_metric": "l2"}, rewards)
+    with pytest.warns(UserWarning):
+        cfg = cb.EnvConfig.from_reference_dicts({"sample_subset_samples": 100, "episode_iterations": 77}, rewards)
+    assert cfg.episode_iterations == 77
