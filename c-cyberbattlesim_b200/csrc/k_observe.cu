@@ -16,8 +16,14 @@
 
 namespace cbs {
 
-constexpr int OBS_WARPS = 8;
-constexpr int SMEM_NODES = 32;
+#ifndef CBS_OBS_WARPS
+#define CBS_OBS_WARPS 8
+#endif
+#ifndef CBS_OBS_SMEM_NODES
+#define CBS_OBS_SMEM_NODES 32
+#endif
+constexpr int OBS_WARPS = CBS_OBS_WARPS;          // warps per CTA (one CTA per SM)
+constexpr int SMEM_NODES = CBS_OBS_SMEM_NODES;    // graphs up to this many nodes keep their embeddings in shared memory
 
 struct SharedWeights {
   float gcn[NODE_EMB * NODE_EMB];               // [in][out]
@@ -400,13 +406,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     const float4* dsrc = reinterpret_cast<const float4*>(T.dyn_proj);
     float4* gdst = reinterpret_cast<float4*>(SW.gcn);
     float4* ddst = reinterpret_cast<float4*>(SW.dyn);
-    float4 tg[G4 / NT], td[(D4 + NT - 1) / NT];
+    float4 tg[(G4 + NT - 1) / NT], td[(D4 + NT - 1) / NT];
 #pragma unroll
-    for (int i = 0; i < G4 / NT; ++i) tg[i] = gsrc[threadIdx.x + i * NT];
+    for (int i = 0; i < (G4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; tg[i] = j < G4 ? gsrc[j] : make_float4(0, 0, 0, 0); }
 #pragma unroll
     for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; td[i] = j < D4 ? dsrc[j] : make_float4(0, 0, 0, 0); }
 #pragma unroll
-    for (int i = 0; i < G4 / NT; ++i) gdst[threadIdx.x + i * NT] = tg[i];
+    for (int i = 0; i < (G4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; if (j < G4) gdst[j] = tg[i]; }
 #pragma unroll
     for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; if (j < D4) ddst[j] = td[i]; }
   }
