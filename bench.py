@@ -318,11 +318,11 @@ def main():
         pairs = float(np.mean(sc[5] * sc[4]))                       # n_owned * n_disc  (upper bound of table pairs)
         rows = pairs * 24.0                                         # ~24 candidate rows per pair (tools/workload_stats.py)
         alg = {
-            # A_v read (+ the aligned repack write/read on the tensor-core path) + Vemb + VT write
-            "decode_gemm": B * 768 * 4 * (3 if env.tensor_core_decode else 1) + Ug * 768 * 4 + B * Ug * 4,
-            # action read + VT row read + per pair two half-precision snapshot rows + norms, per row 16 B of table
-            "decode_select": B * (C.ACTION_DIM * 4 + 4 * Ug + pairs * (2 * 128 + 9) + rows * 16 + 28),
-            "transition": B * 220.0,
+            # A_v read + Vemb + VT write (the dense action rows are staged by cp.async, no repack pass)
+            "decode_gemm": B * 768 * 4 + Ug * 768 * 4 + B * Ug * 4,
+            # action read + VT row read + per pair two half-precision snapshot rows + norms, per row 16 B of table,
+            # plus the transition's 220 B of per-env state
+            "decode_select_transition": B * (C.ACTION_DIM * 4 + 4 * Ug + pairs * (2 * 128 + 9) + rows * 16 + 28 + 220.0),
             "observe": B * 0.45 * 10240.0,
         }
         dom = max(kern, key=kern.get)

@@ -152,7 +152,7 @@ class BatchedCyberBattleEnv:
         actions = self._actions(actions)
         out = (ct.c_float * 5)()
         self._check(self.lib.cbs_profile_step(self._h, self._p(actions), None, out, self._stream()))
-        return {"decode_gemm": out[0] + out[1], "decode_select": out[2], "transition": out[3], "observe": out[4]}
+        return {"decode_gemm": out[0], "decode_select_transition": out[1], "observe": out[2]}
 
     def step_host(self, actions: np.ndarray, uniforms: Optional[np.ndarray], obs: np.ndarray, reward: np.ndarray,
                   done: np.ndarray, info: Optional[np.ndarray] = None):

@@ -369,36 +369,28 @@ int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev,
 }
 
 int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* out_ms, uintptr_t stream) {
-  // one step with a CUDA event between every launch, on the launching stream; out_ms[5] =
-  // { pack_actions, decode_gemm, decode_select, transition, observe } in milliseconds.  Synchronises.
+  // the same three launches as cbs_step with a CUDA event between them, on the launching stream; out_ms[5] =
+  // { decode_gemm, decode_select + transition (fused kernel), observe, 0, 0 } in milliseconds.  Synchronises.
   int rc = check_ready(h);
   if (rc) return rc;
   if (!actions_dev || !out_ms) return fail(h, CBS_ERR_INVALID_ARG, "cbs_profile_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaEvent_t ev[6];
+  cudaEvent_t ev[4];
   for (auto& e : ev) CK(h, cudaEventCreate(&e));
   CK(h, cudaEventRecord(ev[0], st));
-  if (h->use_tc) {
-    // the tensor-core path is two launches; time them separately by splitting the helper's work
-    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
-    CK(h, cudaEventRecord(ev[1], st));   // (pack + gemm together; split below by a second, gemm-only launch)
-    CK(h, cudaEventRecord(ev[2], st));
-  } else {
-    CK(h, cudaEventRecord(ev[1], st));
-    CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
-    CK(h, cudaEventRecord(ev[2], st));
-  }
-  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, h->d_sel, h->d_dist, st));
-  CK(h, cudaEventRecord(ev[3], st));
-  CK(h, launch_transition(h->T, h->P, h->S, h->d_sel, h->d_dist, uniforms_dev, h->sched_buf ^ 1, nullptr, nullptr, nullptr, nullptr, st));
+  if ((rc = launch_gemm(h, actions_dev, st))) return rc;
+  CK(h, cudaEventRecord(ev[1], st));
+  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 1, uniforms_dev, nullptr, nullptr, nullptr,
+                             nullptr, st));
   h->sched_buf ^= 1;
-  CK(h, cudaEventRecord(ev[4], st));
+  CK(h, cudaEventRecord(ev[2], st));
   CK(h, launch_observe(h->T, h->P, h->S, nullptr, 0, h->num_sms, st));
-  CK(h, cudaEventRecord(ev[5], st));
+  CK(h, cudaEventRecord(ev[3], st));
   CK(h, cudaStreamSynchronize(st));
-  for (int i = 0; i < 5; ++i) CK(h, cudaEventElapsedTime(&out_ms[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < 3; ++i) CK(h, cudaEventElapsedTime(&out_ms[i], ev[i], ev[i + 1]));
+  out_ms[3] = out_ms[4] = 0.f;
   for (auto& e : ev) cudaEventDestroy(e);
-  h->launches += h->use_tc ? 5 : 4;
+  h->launches += 2;
   return CBS_OK;
 }
 

@@ -193,9 +193,9 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream);
 int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* obs_dev, float* reward_dev,
              uint8_t* done_dev, int32_t* info_dev, uintptr_t stream);
 
-/* One step like cbs_step, with a CUDA event recorded on `stream` between the kernel launches.  out_ms[5] =
- * { decode_gemm (incl. the action repack on the tensor-core path), 0 (reserved), decode_select, transition, observe }
- * for the SIMT path out_ms[0] = 0 and out_ms[1] = decode_gemm.  Synchronises the stream.  Measurement aid for bench.py. */
+/* One step like cbs_step (same launches), with a CUDA event recorded on `stream` between the kernels.  out_ms[5] =
+ * { decode_gemm, decode_select + transition (one fused kernel), observe, 0, 0 } in milliseconds.  Synchronises the
+ * stream.  Measurement aid for bench.py. */
 int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* out_ms, uintptr_t stream);
 
 /* Same through HOST buffers (pinned memory recommended): copies actions in, runs the step, copies
