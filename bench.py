@@ -148,7 +148,7 @@ def ncu_traffic(kernel):
         return json.load(f).get(kernel)
 
 
-def run_reference(args, wl_key, rank):
+def run_reference(args, wl_key, rank, emit):
     """--impl reference: the CPU restatement of the same path on all host cores (rank 0 only)."""
     if rank != 0:
         return
@@ -167,14 +167,14 @@ def run_reference(args, wl_key, rank):
     wall = sum(v["wall_s"] for v in vals)
     v = steps / wall
     sample = f"{len(vals)} x {per_step:.1f}s windows, {procs} processes each stepping one OracleEnv (random actions, auto-reset)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "env-steps/sec", "value": v, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": len(vals), "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, len(vals)), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (python)", "data": "synthetic",
         "config": {"workload": wl["name"]},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": procs, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
@@ -192,6 +192,17 @@ def main():
                     help="row pitch (floats) of the device-resident action batches; 905 = dense like the reference's "
                          "action array, 908 lets TMA read them in place (no repack kernel)")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 meanwhile (e.g. NCCL's version banner)
+    # is diverted to stderr until the result is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -199,7 +210,7 @@ def main():
     if args.envs_per_gpu:
         wl["envs_per_gpu"] = args.envs_per_gpu
     if args.impl == "reference":
-        run_reference(args, args.workload, rank)
+        run_reference(args, args.workload, rank, emit)
         return
 
     # CPU baseline first (rank 0, N=1 only), before CUDA is initialised in this process
@@ -258,9 +269,9 @@ def main():
     e0.record()
     for i in range(args.steps):
         env.step(ring[(args.warmup + i) % R], None, want_info=False)
+    acc_all = env.stat_accum_tensor().clone()
     if world > 1:   # the only collective: episode statistics, once per logging interval
-        acc = env.stat_accum_tensor().clone()
-        dist.all_reduce(acc)
+        dist.all_reduce(acc_all)
     e1.record()
     barrier()
     launches = env.launch_count - l0
@@ -330,7 +341,8 @@ def main():
                 "unit": "GB/s", "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "kernels_ms": kern, "kernels_gbs": {k: alg[k] / (kern[k] * 1e-3) / 1e9 for k in kern}}
         roof["frac"] = roof["achieved"] / peak
-        acc = env.stat_accum()
+        from ccbs_b200 import lib as _L
+        acc = dict(zip(_L.ACCUM_NAMES, acc_all.cpu().tolist()))   # summed over all ranks, timed-region episodes + warm-up
         out = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -346,7 +358,7 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
         }
-        print(json.dumps(out))
+        emit(out)
     env.close()
     if world > 1:
         dist.destroy_process_group()
