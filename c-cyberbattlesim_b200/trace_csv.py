@@ -1,0 +1,95 @@
+"""Per-step CSV trace of selected envs, in the column layout of RandomSwitchEnv.add_to_csv
+(_env/cyberbattle_env_switch.py:223-279: the variant without embeddings).
+
+The reference writes one row per step from Python object state; here the integer state of the traced envs is read back from
+the device before and after each step (a debugging aid: it synchronises, keep the traced subset small).  Node detail
+strings follow get_str_info (switch.py:307-334)."""
+from __future__ import annotations
+
+import csv
+from typing import Sequence
+
+import numpy as np
+
+from . import constants as C
+from . import lib as L
+
+HEADER = ["Environment", "Episode", "Iteration", "Discovered Nodes", "Owned Nodes", "Alive nodes", "Source node",
+          "Target node", "Vulnerability ID", "Outcome Mapped", "Reward", "Outcome", "Done", "Source Node Details",
+          "Target Node Details", "Previous Source Node Details", "Previous Target Node Details", "Edges"]
+_PRIV = {0: "PrivilegeLevel.NoAccess", 1: "PrivilegeLevel.LocalUser", 3: "PrivilegeLevel.ROOT"}
+
+
+class TraceCsvWriter:
+    def __init__(self, env, path: str, env_ids: Sequence[int] = (0,)):
+        self.env, self.ids = env, [int(i) for i in env_ids]
+        self.file = open(path, "w", newline="")
+        self.writer = csv.writer(self.file)
+        self.writer.writerow(HEADER)
+        self.edges = {b: [] for b in self.ids}
+        self._before = None
+
+    # ---- state snapshots -------------------------------------------------------------------------
+    def _snapshot(self):
+        env = self.env
+        env.sync()
+        return dict(masks=env.masks(), scal=env.scalars(), disc=env.disc_order(), owned=env.owned_order())
+
+    def _node_str(self, snap, b, node):
+        t = self.env.tables
+        sc = int(snap["scal"][L.S_SCENARIO, b])
+        nd = t.specs[sc].nodes[node]
+        bit = lambda plane: bool((snap["masks"][plane, node >> 5, b] >> (node & 31)) & 1)   # noqa: E731
+        priv = 3 if bit(C.M_PRIV_ROOT) else (1 if bit(C.M_PRIV_USER) else 0)
+        s = (f"status : {'MachineStatus.Stopped' if bit(C.M_STOPPED) else 'MachineStatus.Running'} / tag : {nd.tag} / value : "
+             f"{nd.value} / privilege level : {_PRIV[priv]} / has data : {bit(C.M_HAS_DATA)} / data collected : "
+             f"{bit(C.M_COLLECTED)} / data exfiltrated : {bit(C.M_EXFILTRATED)} / visible : {bit(C.M_VISIBLE)} / persistence : "
+             f"{bit(C.M_PERSISTENCE)} / defense evasion : {bit(C.M_EVASION)} / level at access : {_PRIV[nd.level_at_access]} / services : ")
+        for svc in nd.services:
+            fin = int(any(p == svc.port and perm == 0 for p, perm in nd.fw_in))
+            fout = int(any(p == svc.port and perm == 0 for p, perm in nd.fw_out))
+            s += f"{svc.port} {svc.running} {fin} {fout} "
+        s += " / vulnerabilities : "
+        for v in nd.vulns:
+            s += f"{v.vid}  " + "".join(f"{'remote' if r.vtype else 'local'}--{C.KIND_NAMES[r.kind]}  " for r in v.results)
+        return s
+
+    def _lists(self, snap, b):
+        t = self.env.tables
+        sc = int(snap["scal"][L.S_SCENARIO, b])
+        ids = t.node_ids[sc]
+        nd, no = int(snap["scal"][L.S_N_DISC, b]), int(snap["scal"][L.S_N_OWNED, b])
+        disc = [ids[j] for j in snap["disc"][b, :nd]]
+        owned = [ids[j] for j in snap["owned"][b, :no]]
+        alive = [ids[j] for j in snap["disc"][b, :nd] if not (snap["masks"][C.M_STOPPED, j >> 5, b] >> (j & 31)) & 1]
+        return sc, ids, disc, owned, alive
+
+    # ---- per-step protocol -----------------------------------------------------------------------
+    def before_step(self):
+        self._before = self._snapshot()
+
+    def after_step(self, reward, done, info):
+        """reward[B], done[B], info[B,8] as returned by BatchedCyberBattleEnv.step (tensors or arrays)."""
+        to_np = lambda x: x.cpu().numpy() if hasattr(x, "cpu") else np.asarray(x)   # noqa: E731
+        reward, done, info = to_np(reward), to_np(done), to_np(info)
+        after, before = self._snapshot(), self._before
+        t = self.env.tables
+        for b in self.ids:
+            sc, ids, disc, owned, alive = self._lists(before, b)
+            s, tg, u, kind, code, _, step_count, _ = (int(x) for x in info[b])
+            finished = bool(done[b])
+            # after an in-place reset the post-step node state is gone: the details columns then show the fresh episode
+            src_now = self._node_str(after, b, s) if int(after["scal"][L.S_SCENARIO, b]) == sc else ""
+            tgt_now = self._node_str(after, b, tg) if int(after["scal"][L.S_SCENARIO, b]) == sc else ""
+            if float(reward[b]) > 0 and not finished:    # an edge is added when the step's reward is positive (compressed:483)
+                self.edges[b].append(f"{ids[s]}:{ids[tg]}:{t.vuln_ids[sc][u]}")
+            self.writer.writerow([sc, int(before["scal"][L.S_EPISODES, b]), step_count, disc, owned, alive, ids[s], ids[tg],
+                                  t.vuln_ids[sc][u], C.KIND_NAMES[kind], float(reward[b]),
+                                  C.KIND_NAMES[code] if code < 16 else C.OC_NAMES.get(code), finished, src_now, tgt_now,
+                                  self._node_str(before, b, s), self._node_str(before, b, tg), ",".join(self.edges[b])])
+            if finished:
+                self.edges[b] = []
+        self.file.flush()
+
+    def close(self):
+        self.file.close()

@@ -58,3 +58,43 @@ def test_single_env_wrapper_raises_after_done():
     obs, _ = env.reset()
     assert obs["discrete_features"][0] == 1
     env.close()
+
+
+def test_csv_trace_writer(tmp_path):
+    import csv
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200.trace_csv import TraceCsvWriter, HEADER
+    env = cb.BatchedCyberBattleEnv([cb.synthetic_spec(11, 9)], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=6, seed=2)
+    env.reset()
+    path = tmp_path / "logs.csv"
+    w = TraceCsvWriter(env, str(path), env_ids=(0, 4))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    for t in range(25):
+        w.before_step()
+        obs, rew, done, info = env.step(torch.rand(6, 905, device="cuda", generator=g) * 8 - 4, None)
+        w.after_step(rew, done, info)
+    w.close()
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == HEADER and len(rows) == 1 + 2 * 25
+    assert all(len(r) == len(HEADER) for r in rows)
+    assert {r[11] for r in rows[1:]} & {"Reconnaissance", "RepeatedResult", "InvalidAction", "Discovery", "NoNeededAction"}
+    assert "status : MachineStatus.Running" in rows[1][15]
+    env.close()
+
+
+def test_device_vec_normalize_runs():
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200.normalize import DeviceVecNormalize
+    env = cb.BatchedCyberBattleEnv([cb.synthetic_spec(12, 10)], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=128, seed=2)
+    vn = DeviceVecNormalize(env)
+    obs = vn.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    for t in range(20):
+        obs, rew, done, _ = vn.step(torch.rand(128, 905, device="cuda", generator=g) * 8 - 4)
+    assert obs.shape == (128, 194) and torch.isfinite(obs).all() and obs.abs().max() <= 10.0
+    assert torch.isfinite(rew).all() and rew.abs().max() <= 10.0 and float(vn.ret_rms.count) > 2000
+    env.close()
