@@ -29,6 +29,9 @@ WORKLOADS = {
                envs_per_gpu=8192, nodes=(32, 32), scenarios=16),
     "c1": dict(name="configs[1]: 4096 envs x 10-25-node synthetic scenarios on 1 GPU", envs_per_gpu=4096, nodes=(10, 25),
                scenarios=16),
+    "cd": dict(name="default-like deployment set (docs/ch2_env_stats.md): 20 scenarios x 100 nodes, ~33 vulnerabilities/node, "
+                    "pool of 3000 CVEs, 4096 envs", envs_per_gpu=4096, nodes=(100, 100), scenarios=20, pool=3000,
+               services_range=(1, 4), vulns_per_service_range=(8, 20)),
     "c4": dict(name="configs[3]: mixed-topology batch, 10-100-node scenarios (padded to 100 nodes), 768-d embeddings, pool 600",
                envs_per_gpu=4096, nodes=(10, 100), scenarios=20, pool=600),
 }
@@ -42,7 +45,8 @@ def build_specs(wl):
     specs = []
     for k in range(wl["scenarios"]):
         n = int(rng.integers(wl["nodes"][0], wl["nodes"][1] + 1))
-        specs.append(cb.synthetic_spec(100 + k, n, pool=pool))
+        gkw = {k2: wl[k2] for k2 in ("services_range", "vulns_per_service_range") if k2 in wl}
+        specs.append(cb.synthetic_spec(100 + k, n, pool=pool, **gkw))
     return specs
 
 

@@ -25,6 +25,16 @@ DEFAULT_REWARDS = {
                       data_collected_reward=100, data_exfiltrated_reward=100, persistence_reward=0,
                       privilege_escalation_reward=50, acquired_visibility_reward=100, dos_coefficient=-2,
                       defense_evaded_reward=25),
+    # agents/config/rewards_config.yaml:15-25,37-47,59-69
+    "control_node": dict(value_coefficient=2, cost_coefficient=1, node_discovered_coefficient=15, data_collected_reward=10,
+                         data_exfiltrated_reward=10, persistence_reward=10, privilege_escalation_reward=50,
+                         acquired_visibility_reward=10, dos_coefficient=-1, defense_evaded_reward=10),
+    "disruption_node": dict(value_coefficient=0.5, cost_coefficient=1, node_discovered_coefficient=5, data_collected_reward=0,
+                            data_exfiltrated_reward=0, persistence_reward=0, privilege_escalation_reward=0,
+                            acquired_visibility_reward=10, dos_coefficient=1, defense_evaded_reward=10),
+    "discovery_node": dict(value_coefficient=1, cost_coefficient=1, node_discovered_coefficient=20, data_collected_reward=50,
+                           data_exfiltrated_reward=500, persistence_reward=0, privilege_escalation_reward=25,
+                           acquired_visibility_reward=50, dos_coefficient=-1, defense_evaded_reward=10),
 }
 _PEN_COMMON = dict(no_vulnerability_in_node=-10, no_enough_privileges=-10, success_rate_failed=0,
                    no_data_to_collect=-10, no_data_to_exfiltrate=-10, already_persistent=-10,
@@ -37,6 +47,7 @@ DEFAULT_PENALTIES = {
     "control": dict(_PEN_COMMON, invalid_action=-50),
     "disruption": dict(_PEN_COMMON),
     "discovery": dict(_PEN_COMMON),
+    "control_node": dict(_PEN_COMMON), "disruption_node": dict(_PEN_COMMON), "discovery_node": dict(_PEN_COMMON),
 }
 
 
@@ -54,14 +65,14 @@ class EnvConfig:
     remove_all_obstacles: bool = False
     random_starter_node: bool = True
     switch_interval: int = 5
+    interest_node_value: int = 200        # agents/config/train_config.yaml:16 (value of the node of interest, *_node goals)
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
 
     def __post_init__(self):
         self.goal = self.goal.lower()
         if self.goal not in C.GOALS:
-            raise ValueError(f"goal '{self.goal}' is not supported by the batched env "
-                             f"(supported: {sorted(C.GOALS)}; *_node goals are listed as 'next' in DESIGN.md)")
+            raise ValueError(f"goal '{self.goal}' is not supported by the batched env (supported: {sorted(C.GOALS)})")
         if not self.rewards_dict:
             self.rewards_dict = dict(DEFAULT_REWARDS[self.goal])
         if not self.penalties_dict:
@@ -109,4 +120,5 @@ class EnvConfig:
                     isolation_filter_threshold=self.isolation_filter_threshold,
                     remove_main_obstacles=self.remove_main_obstacles, remove_all_obstacles=self.remove_all_obstacles,
                     random_starter_node=self.random_starter_node, rewards_dict=dict(self.rewards_dict),
+                    interest_node_value=self.interest_node_value, switch_interest_node_interval=1,
                     penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None)

@@ -106,9 +106,17 @@ OC_NAMES = {
 PRIV_NONE, PRIV_USER, PRIV_ROOT = 0, 1, 3
 ST_STOPPED, ST_RUNNING, ST_IMAGING = 0, 1, 2
 
-# goals (cyberbattle_env.py:467-514). Round 1 implements the three network-wide goals.
+# goals (cyberbattle_env.py:467-514): three network-wide goals and their node-specific variants (one "interest node"
+# per scenario; the observation then carries that node's embedding as 64 extra floats, compressed:119-125)
 GOAL_CONTROL, GOAL_DISCOVERY, GOAL_DISRUPTION = 0, 1, 2
-GOALS = {"control": GOAL_CONTROL, "discovery": GOAL_DISCOVERY, "disruption": GOAL_DISRUPTION}
+GOAL_CONTROL_NODE, GOAL_DISCOVERY_NODE, GOAL_DISRUPTION_NODE = 3, 4, 5
+GOALS = {"control": GOAL_CONTROL, "discovery": GOAL_DISCOVERY, "disruption": GOAL_DISRUPTION,
+         "control_node": GOAL_CONTROL_NODE, "discovery_node": GOAL_DISCOVERY_NODE, "disruption_node": GOAL_DISRUPTION_NODE}
+
+
+def obs_dim_for_goal(goal: str) -> int:
+    """Length of the flat observation: graph_embeddings (192, or 256 for *_node goals) + discrete_features (2)."""
+    return OBS_DIM + (NODE_EMB_DIM if goal.endswith("node") else 0) + 2
 
 # end_episode_reason (cyberbattle_env.py:338-370)
 END_NONE, END_GOAL, END_LOST, END_CUTOFF = 0, 1, 2, 3

@@ -98,8 +98,12 @@ class OracleEnv:
     with the success-rate draw replaced by the supplied uniform (consumed only where the reference
     calls ``random.random()``, attacker_actions.py:190,409)."""
 
-    def __init__(self, spec, gae_weights, cfg):
+    def __init__(self, spec, gae_weights, cfg, interest_node=None):
         self.spec, self.cfg = spec, cfg
+        self.node_goal = cfg.goal.endswith("node")
+        self.interest = None if interest_node is None else int(interest_node)      # cyberbattle_env.py:127-131 (fixed per env object)
+        if self.node_goal and self.interest is None:
+            raise ValueError("*_node goals need an interest node")
         self.gae = GaeOracle(gae_weights)
         self.N = spec.num_nodes
         self.rew, self.pen = dict(cfg.rewards_dict), dict(cfg.penalties_dict)
@@ -175,11 +179,14 @@ class OracleEnv:
                         if any(p == v.port and perm == 1 for p, perm in nodes[s].fw_out):
                             continue
                         (dos if r.kind == C.K_DOS else access)[s].add(i)
-        return {"control": [len(reach_from(access, s)) for s in range(N)],
-                "discovery": [len(x) for x in knows_reach],
-                "disruption": [len(reach_from(dos, s)) for s in range(N)]}
+        self._reach_sets = {"control": [reach_from(access, s) for s in range(N)], "discovery": knows_reach,
+                            "disruption": [reach_from(dos, s) for s in range(N)]}
+        return {k: [len(x) for x in v] for k, v in self._reach_sets.items()}
 
     def feasible_starters(self):
+        if self.node_goal:                                           # cyberbattle_env.py:249-275
+            base = self.goal[:-5]
+            return [s for s in range(self.N) if s != self.interest and self.interest in self._reach_sets[base][s]]
         thr = self.cfg.isolation_filter_threshold * self.N           # cyberbattle_env.py:206
         return [s for s in range(self.N) if not (self._reach[self.goal][s] < thr)]
 
@@ -201,7 +208,11 @@ class OracleEnv:
         self.discoverable_count = self._reach["discovery"][self.starter]     # :213
         self.disruptable_count = self._reach["disruption"][self.starter]     # :217
         self.proportional_nodes = {"control": self.ownable_count, "discovery": self.discoverable_count,
-                                   "disruption": self.disruptable_count}[self.goal]   # :226-248
+                                   "disruption": self.disruptable_count}[self.goal[:-5] if self.node_goal else self.goal]   # :226-275
+        if self.node_goal:
+            self.node_value = {self.interest: self.cfg.interest_node_value}      # :277 set_node_property(interest, "value", ...)
+        else:
+            self.node_value = {}
         # :279-288 — both dict-key tests are true for every node, so every node counts
         self.discoverable_amount = 0
         for nd in self.nodes:
@@ -250,6 +261,9 @@ class OracleEnv:
         node.privilege_level = max(int(node.privilege_level), int(level))    # model.py:340
         self._discovered[n] = True
         return was, was     # no defender: last_reimaging is None, so "currently owned" == "ever owned"
+
+    def _value(self, n):
+        return self.node_value.get(n, self.nodes[n].spec.value)
 
     @staticmethod
     def _passing(rules, port):
@@ -328,7 +342,7 @@ class OracleEnv:
             if remote and tgt.status == C.ST_STOPPED:                                     # :232 (unreachable, :127)
                 return P["node_already_stopped"], C.OC_REPEATED, None
             tgt.status = C.ST_STOPPED
-            total += R["dos_coefficient"] * tgt.spec.value
+            total += R["dos_coefficient"] * self._value(t)
         elif k == C.K_DISCOVERY:
             if tgt.visible:
                 return P["node_already_visible"], C.OC_REPEATED, None
@@ -364,7 +378,7 @@ class OracleEnv:
             if already:
                 return P["node_already_owned"], C.OC_REPEATED, None                       # :331-335
             if not ever:
-                total += R["value_coefficient"] * float(tgt.spec.value)                   # :336-340
+                total += R["value_coefficient"] * float(self._value(t))                   # :336-340
         else:
             return P["outcome_not_valid"], C.OC_REMOTE_OUTCOME_LOCAL, None                # :345 / :536-540
         total -= R["cost_coefficient"] * v.cost                                           # :348 / :544
@@ -396,6 +410,8 @@ class OracleEnv:
             self.owned_nodes.append(t)
         elif code in (C.K_COLLECTION, C.K_EXFILTRATION, C.K_DISCOVERY):
             self.discovered_amount += 1
+        if self.node_goal and self.interest in self.discovered_nodes and t != self.interest:
+            self.reward = 0                                                                # :322-326
         # end checks (:338-370)
         self.end_episode_reason = 0
         self.truncated = False
@@ -434,10 +450,23 @@ class OracleEnv:
             data = [n for n in self.discovered_nodes if self.nodes[n].has_data]
             pend = [n for n in self.discovered_nodes if self.nodes[n].data_collected and not self.nodes[n].data_exfiltrated]
             return len(disc) == self.discoverable_count and not data and not pend
+        it = self.nodes[self.interest] if self.node_goal else None
+        if self.goal == "control_node":                                                    # :488-492
+            return self.interest in self.owned_nodes and it.privilege_level == C.PRIV_ROOT
+        if self.goal == "discovery_node":                                                  # :493-508
+            if self.interest in self.discovered_nodes and it.visible:
+                if it.has_data:
+                    return bool(it.data_collected and it.data_exfiltrated)
+                return True
+            return False
+        if self.goal == "disruption_node":                                                 # :509-513
+            return it.status == C.ST_STOPPED
         return False
 
     def check_end_game(self):
-        """cyberbattle_env.py:438-454: lost when no owned node is Running."""
+        """cyberbattle_env.py:438-454: lost when no owned node is Running (or the interest node was killed)."""
+        if self.goal in ("control_node", "discovery_node") and self.nodes[self.interest].status == C.ST_STOPPED:
+            return True
         return not any(self.nodes[n].status == C.ST_RUNNING for n in self.owned_nodes)
 
     def get_statistics(self):
@@ -485,7 +514,7 @@ class OracleEnv:
             mean = mean / len(sp.vulns)
         flat = fw + running + [int(nd.visible), int(nd.persistence), int(nd.data_collected), int(nd.data_exfiltrated),
                                int(nd.defense_evasion), int(sp.reimageable), int(nd.privilege_level), int(nd.status),
-                               sp.value, sp.sla_weight] + fv + list(mean)
+                               self._value(n), sp.sla_weight] + fv + list(mean)
         return np.array(flat, dtype=np.float32)
 
     def _add_graph_node(self, n):
@@ -505,8 +534,11 @@ class OracleEnv:
         self.graph_edges[s][t] = np.mean(self.exploited[s][t], axis=0)
 
     def encode(self):
-        """compressed:249-306 encode (non *_node goals)."""
-        order = self.graph_nodes
+        """compressed:249-306 encode.  *_node goals: the interest node is added to the LIVE graph during an encode, the
+        copy being encoded does not have it yet (compressed:254-256), so it takes part from the next encode on."""
+        order = list(self.graph_nodes)
+        if self.node_goal and self.interest not in self.node_x:
+            self._add_graph_node(self.interest)
         pos = {n: i for i, n in enumerate(order)}
         x = torch.from_numpy(np.stack([self.node_x[n] for n in order]))
         src, dst, attrs = [], [], []
@@ -524,12 +556,20 @@ class OracleEnv:
         self.z_all = z
         running = [n for n in order if self.nodes[n].status == C.ST_RUNNING]
         node_embeddings = {}
+        extra = C.NODE_EMB_DIM if self.node_goal else 0
         if not running:                                                                    # :269-274
-            return node_embeddings, np.zeros(C.OBS_DIM, dtype=np.float32)
+            return node_embeddings, np.zeros(C.OBS_DIM + extra, dtype=np.float32)
         for n in running:
             node_embeddings[n] = z[pos[n]]
         arr = np.array([node_embeddings[n] for n in node_embeddings], dtype=np.float32)
         obs = np.concatenate([np.average(arr, axis=0), np.max(arr, axis=0), np.min(arr, axis=0)])   # :285-298
+        if self.node_goal:                                                                 # :299-305
+            if self.interest in running:
+                obs = np.concatenate([obs, node_embeddings[self.interest]])
+            else:
+                obs = np.concatenate([obs, np.zeros(C.NODE_EMB_DIM, dtype=np.float32)])
+            if self.interest not in self.discovered_nodes and self.interest in node_embeddings:
+                node_embeddings.pop(self.interest)
         return node_embeddings, obs
 
     def _discrete_features(self):
@@ -557,10 +597,14 @@ class OracleEnv:
         for vid, ri, kind, emb in self.per_node_type[t][vtype]:
             if (s == t and kind == C.K_LATERAL) or kind == C.K_CREDACCESS:                 # :532 (precedence)
                 continue
-            if self.cfg.remove_all_obstacles and self.goal in ("control", "discovery") and kind == C.K_DOS:
+            if self.cfg.remove_all_obstacles and self.goal in ("control", "discovery", "control_node", "discovery_node") \
+                    and kind == C.K_DOS:
                 continue                                                                   # :536-538
             if self.cfg.remove_main_obstacles and kind == C.K_DOS and t == self.starter:
                 continue                                                                   # :541-543
+            if self.cfg.remove_main_obstacles and self.node_goal and self.goal != "disruption_node" and \
+                    kind == C.K_DOS and t == self.interest:
+                continue                                                                   # :545-547
             self.action_keys.append((s, t, vid, kind, vtype, ri))
             self.action_rows.append(np.concatenate((es, et, emb)))                         # :550
             self._rows_cache = None

@@ -49,6 +49,13 @@ CASES = {
     "g14_removeall": dict(graph_seed=19, nodes=14, steps=600,
                           cfg=dict(goal="discovery", remove_all_obstacles=True, remove_main_obstacles=False, winning_reward=300,
                                    losing_reward=-700, isolation_filter_threshold=0.3, proportional_cutoff_coefficient=2)),
+    # node-specific goals (one interest node per env object; observation carries its embedding: 256 + 2 floats)
+    "n12_control_node": dict(graph_seed=21, nodes=12, steps=700, interest=5,
+                             cfg=dict(goal="control_node", proportional_cutoff_coefficient=2, interest_node_value=200)),
+    "n12_discovery_node": dict(graph_seed=22, nodes=12, steps=700, interest=3,
+                               cfg=dict(goal="discovery_node", proportional_cutoff_coefficient=3, interest_node_value=150)),
+    "n10_disruption_node": dict(graph_seed=23, nodes=10, steps=700, interest=7,
+                                cfg=dict(goal="disruption_node", proportional_cutoff_coefficient=3)),
     # scripted attacker (oracle.trace.policy_pick): owns many nodes, escalates, reaches the goal -> winning reward,
     # large action tables, many snapshot slots.  `policy` = noise sigma added to the chosen table row.
     "p6_control_win": dict(graph_seed=30, nodes=6, steps=500, policy=0.02,
@@ -91,11 +98,14 @@ def generate(name):
     from oracle import ref_bridge as rb
     t0 = time.time()
     p, graph, model, spec, cfg, weights = build_case(name)
-    tables = cb.compile_scenarios([spec], cfg.isolation_filter_threshold)      # also cross-checks reach counts
-    feasible = tables.feasible_starters[cb.constants.GOALS[cfg.goal]]
+    interest = p.get("interest")
+    from oracle.cbs_oracle import OracleEnv
+    cb.compile_scenarios([spec], cfg.isolation_filter_threshold)               # cross-checks reach counts against the Model
+    feasible = OracleEnv(spec, weights, cfg, interest_node=interest).feasible_starters()
+    assert feasible, "no feasible starter for this case"
     actions, uniforms = make_case_inputs(p)
     starters = tr.make_starters(p["graph_seed"] * 1000 + 2, feasible, p["steps"] + 2)
-    runner = rb.ReferenceRunner(model, weights, cfg)
+    runner = rb.ReferenceRunner(model, weights, cfg, interest_node=interest)
     rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters,
                     policy_seed=(p["graph_seed"] * 1000 + 3) if "policy" in p else None)
     meta = dict(name=name, params={k: v for k, v in p.items() if k != "cfg"}, cfg=p["cfg"], pool_seed=POOL_SEED,
@@ -140,7 +150,7 @@ def load_case(path):
     rec["obs"] = z["obs_rows"][z["obs_idx"]]
     return dict(meta=meta, spec=spec, cfg=cfg, weights=weights, actions=actions, uniforms=uniforms,
                 starters=z["starters"], trace=rec, policy_seed=0 if "policy" in p else None,
-                policy_rows=rec.get("policy_rows"))
+                policy_rows=rec.get("policy_rows"), interest=p.get("interest"))
 
 
 if __name__ == "__main__":

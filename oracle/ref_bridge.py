@@ -68,6 +68,7 @@ class _FakeRandom:
         self.next_uniform = None
         self.next_starter = None
         self.uniform_consumed = False
+        self.next_choice = None
 
     def random(self):
         self.uniform_consumed = True
@@ -77,7 +78,8 @@ class _FakeRandom:
         return int(self.next_starter)
 
     def choice(self, seq):
-        return seq[0]
+        # cyberbattle_env.py:129 switch_interest_node: random.choice(list(nodes)) -> the configured interest node
+        return self.next_choice if self.next_choice in seq else seq[0]
 
     def __getattr__(self, name):
         return getattr(_py_random, name)
@@ -86,7 +88,7 @@ class _FakeRandom:
 class ReferenceRunner:
     """One reference ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv])`` with controlled randomness."""
 
-    def __init__(self, model, gae_weights, cfg):
+    def __init__(self, model, gae_weights, cfg, interest_node=None):
         import torch
         ref = import_reference()
         self.ref = ref
@@ -102,6 +104,10 @@ class ReferenceRunner:
         enc.load_state_dict(gae_weights.state_dict())
         enc.eval()                                                     # agents/train_agent.py:333
         self.fake.next_starter = 0
+        ids0 = list(model.network.nodes)
+        if interest_node is not None:
+            self.fake.next_choice = ids0[int(interest_node)]
+            self.fake.next_starter = (int(interest_node) + 1) % len(ids0)   # constructor's reset_env: any starter != interest that passes
         kw = cfg.reference_kwargs()
         env = ref["compressed"].CyberBattleCompressedEnv(initial_environment=model, logger=logger, verbose=0, **kw)
         env.set_graph_encoder(enc)

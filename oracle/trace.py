@@ -166,11 +166,11 @@ def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=N
                done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
                dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
                disc_order=np.full((T, N), -1, np.int16), owned_order=np.full((T, N), -1, np.int16),
-               counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, C.OBS_DIM + 2), np.float32),
-               episode=np.zeros(T, np.int32))
+               counters=np.zeros((T, 7), np.int32), obs=None, episode=np.zeros(T, np.int32))
     reset_obs, reset_masks, stats = [], [], []
     ep = 0
     reset_obs.append(adapter.reset(starters[ep]))
+    rec["obs"] = np.zeros((T, len(reset_obs[0])), np.float32)      # 194, or 258 for *_node goals
     reset_masks.append(masks_to_array(adapter.masks()))
     for t in range(T):
         action = actions[t]
