@@ -28,14 +28,21 @@ class BatchedCyberBattleEnv:
     def __init__(self, specs: Sequence[ScenarioSpec], gae_weights: GaeWeights, cfg: Optional[EnvConfig] = None,
                  num_envs: int = 1, device: int = 0, scenario_of_env: Optional[np.ndarray] = None, seed: int = 0,
                  global_env_offset: int = 0, auto_reset: bool = True, switch_interval: int = 0,
-                 tables: Optional[ScenarioTables] = None, **cfg_overrides):
+                 tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None, **cfg_overrides):
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = cfg or EnvConfig()
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", device)
         self.lib = L.load_library()
-        self.tables = tables if tables is not None else compile_scenarios(specs, self.cfg.isolation_filter_threshold)
+        node_goal = self.cfg.goal.endswith("node")
+        if node_goal and tables is None and interest_nodes is None:
+            raise CbsError("*_node goals need interest_nodes (one node index per scenario; the reference draws it with "
+                           "random.choice when the env object is built, cyberbattle_env.py:127-131)")
+        self.tables = tables if tables is not None else compile_scenarios(
+            specs, self.cfg.isolation_filter_threshold, interest_nodes=interest_nodes if node_goal else None,
+            interest_node_value=self.cfg.interest_node_value if node_goal else None)
+        self.obs_dim = C.obs_dim_for_goal(self.cfg.goal)
         self.gae_tables = fold_gae(self.tables, gae_weights)
         ccfg = L.make_config(self.cfg, self.num_envs, device=device, global_env_offset=global_env_offset, seed=seed,
                              auto_reset=auto_reset, switch_interval=switch_interval, **cfg_overrides)
@@ -51,15 +58,16 @@ class BatchedCyberBattleEnv:
             scenario_of_env = np.arange(self.num_envs, dtype=np.int32) % self.tables.num_scenarios
         self.scenario_of_env = np.ascontiguousarray(scenario_of_env, dtype=np.int32)
         self._check(self.lib.cbs_set_scenarios(self._h, self.scenario_of_env.ctypes.data_as(ct.c_void_p)))
-        caps = (ct.c_int32 * 5)()
+        caps = (ct.c_int32 * 6)()
         self.lib.cbs_capacities(self._h, caps)
         self.ncap, self.slots, self.ecap, self.tensor_core_decode = caps[0], caps[1], caps[2], bool(caps[3])
         self.vt_stride = caps[4]
+        assert caps[5] == self.obs_dim
         B = self.num_envs
         self._act_stride = C.ACTION_DIM
         with torch.cuda.device(self.device):
             # zero-copy view of the library's observation cache [B, 194]
-            self.obs = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_OBS), (B, C.OBS_DIM + 2), torch.float32,
+            self.obs = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_OBS), (B, self.obs_dim), torch.float32,
                                         self.device, self)
             self.reward = torch.zeros(B, dtype=torch.float32, device=self.device)
             self.done = torch.zeros(B, dtype=torch.uint8, device=self.device)
@@ -204,7 +212,7 @@ class BatchedCyberBattleEnv:
         return self.read(L.F_OWNED_ORDER, np.uint8, (self.num_envs, self.ncap))
 
     def terminal_obs(self) -> np.ndarray:
-        return self.read(L.F_TERMINAL_OBS, np.float32, (self.num_envs, C.OBS_DIM + 2))
+        return self.read(L.F_TERMINAL_OBS, np.float32, (self.num_envs, self.obs_dim))
 
     def last_stats(self) -> np.ndarray:
         """get_statistics() 14-tuple of the last finished episode of every env (cyberbattle_env.py:517-524)."""

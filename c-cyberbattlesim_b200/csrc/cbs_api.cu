@@ -120,7 +120,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   if (!cfg || !out) return fail(nullptr, CBS_ERR_INVALID_ARG, "cbs_create: null argument");
   if (cfg->abi_version != CBS_ABI_VERSION) return fail(nullptr, CBS_ERR_INVALID_ARG, "ABI version mismatch (%d vs %d)", cfg->abi_version, CBS_ABI_VERSION);
   if (cfg->num_envs <= 0) return fail(nullptr, CBS_ERR_INVALID_ARG, "num_envs must be positive");
-  if (cfg->goal < 0 || cfg->goal > 2) return fail(nullptr, CBS_ERR_INVALID_ARG, "unsupported goal %d", cfg->goal);
+  if (cfg->goal < 0 || cfg->goal > 5) return fail(nullptr, CBS_ERR_INVALID_ARG, "unsupported goal %d", cfg->goal);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CBS_ERR_NO_DEVICE, "no CUDA device available (libcbsim has no CPU fallback)");
@@ -135,6 +135,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.global_env_offset = cfg->global_env_offset;
   P.seed = cfg->seed;
   P.goal = cfg->goal;
+  P.obs_dim = cfg->goal >= GOAL_CONTROL_NODE ? OBS_DIM + NODE_EMB : OBS_DIM;
   P.episode_iterations = cfg->episode_iterations;
   P.prop_coeff = cfg->proportional_cutoff_coefficient;
   P.winning_reward = cfg->winning_reward;
@@ -179,6 +180,12 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   UP(sc_instof_off, S_ + 1); UP(sc_discoverable_amount, S_);
   UP(sc_init_has_data, (size_t)S_ * t->words); UP(sc_init_visible, (size_t)S_ * t->words);
   UP(sc_feasible_off, S_ + 1); UP(feasible_starters, t->num_feasible);
+  if (h->cfg.goal >= GOAL_CONTROL_NODE) {
+    if (!t->sc_interest) return fail(h, CBS_ERR_INVALID_ARG, "*_node goals need sc_interest (one interest node per scenario)");
+    for (int s = 0; s < S_; ++s)
+      if (t->sc_interest[s] < 0 || t->sc_interest[s] >= t->sc_num_nodes[s]) return fail(h, CBS_ERR_INVALID_ARG, "interest node of scenario %d out of range", s);
+    UP(sc_interest, S_);
+  }
   UP(nd_value, Nn); UP(nd_level_at_access, Nn); UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
   UP(nd_row_off, 2 * (size_t)Nn + 1); UP(outblock, (size_t)t->num_ports_total * t->words);
   UP(uvuln_global, t->num_uvuln_total); UP(inst_of, t->num_instof);
@@ -233,7 +240,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
-  AL(obs, B * OBS_DIM); AL(term_obs, B * OBS_DIM); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
+  AL(obs, B * P.obs_dim); AL(term_obs, B * P.obs_dim); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
   AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 1);
   AL(scratch, B * 2 * P.ncap * NODE_EMB);
 #undef AL
@@ -301,7 +308,7 @@ int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintpt
   if (rc) return rc;
   CK(h, launch_observe(h->T, h->P, h->S, env_mask_dev, 1, h->num_sms, (cudaStream_t)stream));
   h->launches += 1;
-  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * h->P.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CBS_OK;
 }
 
@@ -333,7 +340,7 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
   if (rc) return rc;
   CK(h, launch_observe(h->T, h->P, h->S, nullptr, 0, h->num_sms, (cudaStream_t)stream));
   h->launches += 1;
-  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (obs_dev) CK(h, cudaMemcpyAsync(obs_dev, h->S.obs, (size_t)h->P.B * h->P.obs_dim * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return CBS_OK;
 }
 
@@ -425,7 +432,7 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
                 info_host ? h->h_info : nullptr, (uintptr_t)st);
   h->P.act_stride = saved_stride;
   if (rc) return rc;
-  if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->S.obs, B * OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (obs_host) CK(h, cudaMemcpyAsync(obs_host, h->S.obs, B * h->P.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (done_host) CK(h, cudaMemcpyAsync(done_host, h->h_done, B, cudaMemcpyDeviceToHost, st));
   if (info_host) CK(h, cudaMemcpyAsync(info_host, h->h_info, B * CBS_INFO_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -442,8 +449,8 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_DISC_ORDER: *p = S.disc_order; *bytes = B * P.ncap; break;
     case CBS_F_OWNED_ORDER: *p = S.owned_order; *bytes = B * P.ncap; break;
     case CBS_F_SCALARS: *p = S.scal; *bytes = (int64_t)N_SCALARS * B * 4; break;
-    case CBS_F_TERMINAL_OBS: *p = S.term_obs; *bytes = B * OBS_DIM * 4; break;
-    case CBS_F_OBS: *p = S.obs; *bytes = B * OBS_DIM * 4; break;
+    case CBS_F_TERMINAL_OBS: *p = S.term_obs; *bytes = B * P.obs_dim * 4; break;
+    case CBS_F_OBS: *p = S.obs; *bytes = B * P.obs_dim * 4; break;
     case CBS_F_LAST_STATS: *p = S.last_stats; *bytes = B * 14 * 8; break;
     case CBS_F_STAT_ACCUM: *p = S.accum; *bytes = N_ACCUM * 8; break;
     case CBS_F_PAIR_SLOT: *p = S.pair_slot; *bytes = B * P.ncap * P.ncap; break;
@@ -509,10 +516,11 @@ int cbs_struct_sizes(int32_t* out3) {
 }
 
 int64_t cbs_state_bytes(const cbs_handle* h) { return h ? (int64_t)h->state_bytes : 0; }
-int cbs_capacities(const cbs_handle* h, int32_t* out4 /* 5 ints */) {
+int cbs_capacities(const cbs_handle* h, int32_t* out4 /* 6 ints */) {
   if (!h || !out4) return CBS_ERR_INVALID_ARG;
   out4[0] = h->P.ncap; out4[1] = h->P.slots; out4[2] = h->P.ecap; out4[3] = h->use_tc ? 1 : 0;
   out4[4] = h->vt_stride;
+  out4[5] = h->P.obs_dim;
   return CBS_OK;
 }
 

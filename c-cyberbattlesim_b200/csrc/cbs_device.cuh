@@ -14,8 +14,17 @@ __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int 
   return S.scal[(size_t)plane * P.B + b];
 }
 
-// attacker_goal_reached (cyberbattle_env.py:467-487) for the three network-wide goals, on mask words
-__device__ inline bool goal_reached(const State& S, const Params& P, int b) {
+__device__ __forceinline__ bool is_node_goal(const Params& P) { return P.goal >= GOAL_CONTROL_NODE; }
+__device__ __forceinline__ int base_goal(const Params& P) { return is_node_goal(P) ? P.goal - GOAL_CONTROL_NODE : P.goal; }
+
+// attacker_goal_reached (cyberbattle_env.py:467-514), on mask words.  `interest` = the env's interest node (*_node goals)
+__device__ inline bool goal_reached(const State& S, const Params& P, int b, int interest) {
+  if (P.goal == GOAL_CONTROL_NODE) return bit_of(S, P, M_OWNED, interest, b) && bit_of(S, P, M_PRIV_ROOT, interest, b);
+  if (P.goal == GOAL_DISCOVERY_NODE)    // :493-508 (has_data is cleared by the collection, so "collected and exfiltrated" cannot hold with it)
+    return bit_of(S, P, M_DISCOVERED, interest, b) && bit_of(S, P, M_VISIBLE, interest, b) &&
+           (!bit_of(S, P, M_HAS_DATA, interest, b) ||
+            (bit_of(S, P, M_COLLECTED, interest, b) && bit_of(S, P, M_EXFILTRATED, interest, b)));
+  if (P.goal == GOAL_DISRUPTION_NODE) return bit_of(S, P, M_STOPPED, interest, b);
   const int starter = scalar(S, P, S_STARTER, b);
   int n_goal = 0, n_data = 0, n_pending = 0;
   for (int w = 0; w < P.words; ++w) {

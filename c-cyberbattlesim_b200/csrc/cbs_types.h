@@ -26,7 +26,8 @@ enum Kind : int { K_DOS = 0, K_DISCOVERY, K_COLLECTION, K_EXFILTRATION, K_RECON,
 enum Code : int { OC_INVALID_SRC_NOT_OWNED = 16, OC_INVALID_TGT_NOT_DISCOVERED, OC_SRC_NOT_RUNNING, OC_TGT_NOT_RUNNING,
                   OC_NO_VULNERABILITY, OC_NO_PRIVILEGE, OC_OUTCOME_NOT_PRESENT, OC_PORT_NOT_LISTENING, OC_FW_OUTGOING,
                   OC_FW_INCOMING, OC_UNSUCCESSFUL, OC_NO_NEEDED, OC_REPEATED, OC_REMOTE_OUTCOME_LOCAL };
-enum Goal : int { GOAL_CONTROL = 0, GOAL_DISCOVERY = 1, GOAL_DISRUPTION = 2 };
+enum Goal : int { GOAL_CONTROL = 0, GOAL_DISCOVERY = 1, GOAL_DISRUPTION = 2, GOAL_CONTROL_NODE = 3, GOAL_DISCOVERY_NODE = 4,
+                  GOAL_DISRUPTION_NODE = 5 };
 enum Mask : int { M_OWNED = 0, M_DISCOVERED, M_VISIBLE, M_HAS_DATA, M_COLLECTED, M_EXFILTRATED, M_PERSISTENCE,
                   M_EVASION, M_STOPPED, M_PRIV_USER, M_PRIV_ROOT, N_MASKS };
 enum Reward : int { R_VALUE = 0, R_COST, R_NODE_DISCOVERED, R_COLLECTED, R_EXFILTRATED, R_PERSISTENCE, R_PRIVESC,
@@ -42,7 +43,8 @@ enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
               FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
-              FL_DIRTY = 256;  // node features / edges / node sets changed since the last encode
+              FL_DIRTY = 256,  // node features / edges / node sets changed since the last encode
+              FL_INTEREST_IN_GRAPH = 512;  // *_node goals: the interest node was added to the visible graph (compressed:254-256)
 // vi_flags bits (scenario.py VI_*)
 constexpr uint32_t VI_LISTENING = 1u, VI_IN_ALLOWED = 2u;
 constexpr int VI_PRIVREQ_SHIFT = 2, VI_LEVEL_ANY_SHIFT = 4, VI_LEVEL_REMOTE_SHIFT = 6;
@@ -52,7 +54,7 @@ enum Accum : int { A_EPISODES = 0, A_RETURN, A_LENGTH, A_WINS, A_LOST, A_CUTOFF,
 struct Tables {  // immutable, device pointers
   int num_scenarios, max_nodes, words, num_global_vulns;
   const int32_t *sc_num_nodes, *sc_node_off, *sc_port_off, *sc_uvuln_off, *sc_num_uvuln, *sc_discoverable_amount,
-      *sc_feasible_off, *feasible_starters;
+      *sc_feasible_off, *feasible_starters, *sc_interest;
   const int64_t* sc_instof_off;
   const uint32_t *sc_init_has_data, *sc_init_visible;
   const int32_t *nd_value, *nd_ownable, *nd_discoverable, *nd_disruptable, *nd_row_off;
@@ -70,6 +72,7 @@ struct Tables {  // immutable, device pointers
 
 struct Params {  // configuration, by value
   int B, ncap, words, slots, ecap;
+  int obs_dim;      // 194, or 258 for the *_node goals (64 extra floats: the interest node's embedding)
   long long global_env_offset;
   unsigned long long seed;
   int goal, episode_iterations, absolute_reward, stop_at_goal, remove_main, remove_all, switch_interval, auto_reset;

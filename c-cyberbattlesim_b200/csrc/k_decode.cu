@@ -76,10 +76,12 @@ cudaError_t launch_decode_gemm_simt(const float* actions, int act_stride, const 
 // ------------------------------------------------------------------------------------------------
 // candidate scan + float64 re-score + argmin
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter) {
+__device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter, int interest) {
   if ((s == t && kind == K_LATERAL) || kind == K_CREDACCESS) return true;                         // compressed:532
-  if (P.remove_all && (P.goal == GOAL_CONTROL || P.goal == GOAL_DISCOVERY) && kind == K_DOS) return true;   // :536-538
-  if (P.remove_main && kind == K_DOS && t == starter) return true;                                // :541-543
+  if (kind != K_DOS) return false;
+  if (P.remove_all && P.goal != GOAL_DISRUPTION && P.goal != GOAL_DISRUPTION_NODE) return true;    // :536-538
+  if (P.remove_main && t == starter) return true;                                                 // :541-543
+  if (P.remove_main && interest >= 0 && P.goal != GOAL_DISRUPTION_NODE && t == interest) return true;   // :545-547
   return false;
 }
 
@@ -297,6 +299,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
   const uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
   const float* vt_g = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
+  const int interest = is_node_goal(P) ? T.sc_interest[scalar(S, P, S_SCENARIO, b)] : -1;
 
   float run_max = -INFINITY;
   Best best{INFINITY, ~0ull, 0, 0, -1, 0u};
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
           const int kind = (packed[q] >> 20) & 15;
           const uint32_t k = sh.p_key[pp[q]];
           const int s = sh.oorder[(k >> 8) & 0xFF], t = sh.dorder[k & 0xFF];
-          if (!row_filtered(P, kind, s, t, starter)) {
+          if (!row_filtered(P, kind, s, t, starter, interest)) {
             const int u = packed[q] & 0xFFFFF, oh = (packed[q] >> 24) & 15;
             const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
             const float vn2 = u < vt_cached ? vn2_sh[u] : (float)T.vnorm2[u];

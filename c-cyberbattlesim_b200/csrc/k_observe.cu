@@ -38,6 +38,7 @@ struct WarpScratch {
   float* dinv;        // [ncap]
   float* ysm;         // this warp's shared-memory buffers (2 x [32][64])
   uint8_t* pos;       // [MAX_NODES] node id -> position in discovered order
+  uint8_t* ord;       // [MAX_NODES] graph node ids by position (discovered order, then the interest node of *_node goals)
   uint8_t* dynb;      // [MAX_NODES] per position: visible | persistence<<1 | collected<<2 | exfiltrated<<3 | evasion<<4 | privilege<<5 | running<<7
 };
 
@@ -107,14 +108,22 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
                            int lane) {
   const int sc = scalar(S, P, S_SCENARIO, b);
   const int node_off = T.sc_node_off[sc];
-  const int n = scalar(S, P, S_N_DISC, b);
+  const int n_disc = scalar(S, P, S_N_DISC, b);
   const int E = scalar(S, P, S_N_EDGES, b);
-  const uint8_t* order = S.disc_order + (size_t)b * P.ncap;
+  const uint8_t* disc_order = S.disc_order + (size_t)b * P.ncap;
   const int c0 = lane, c1 = lane + 32;
   constexpr int ROW = PROJ_ROWS * NODE_EMB;   // floats per (node, part)
+  // *_node goals: once an encode has added the interest node to the live graph (compressed:254-256) it is part of
+  // every later encode, discovered or not
+  const int interest = is_node_goal(P) ? T.sc_interest[sc] : -1;
+  const bool interest_known = interest >= 0 && bit_of(S, P, M_DISCOVERED, interest, b);
+  const bool extra = interest >= 0 && !interest_known && (scalar(S, P, S_FLAGS, b) & FL_INTEREST_IN_GRAPH);
+  const int n = n_disc + (extra ? 1 : 0);
+  uint8_t* order = W.ord;
 
   for (int i = lane; i < n; i += 32) {
-    const int node = order[i];
+    const int node = i < n_disc ? disc_order[i] : interest;
+    W.ord[i] = (uint8_t)node;
     W.pos[node] = (uint8_t)i;
     W.dinv[i] = 1.f;
     W.dynb[i] = pack_dyn(S, P, b, node);
@@ -234,17 +243,24 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
       mn0 = fminf(mn0, z0); mn1 = fminf(mn1, z1);
     }
   }
-  float* obs = S.obs + (size_t)b * OBS_DIM;
-  if (running == 0) { s0 = s1 = mx0 = mx1 = mn0 = mn1 = 0.f; running = 1; }
+  float* obs = S.obs + (size_t)b * P.obs_dim;
+  const bool none_running = running == 0;
+  if (none_running) { s0 = s1 = mx0 = mx1 = mn0 = mn1 = 0.f; running = 1; }
   obs[c0] = s0 / (float)running;
   obs[c1] = s1 / (float)running;
   obs[NODE_EMB + c0] = mx0;
   obs[NODE_EMB + c1] = mx1;
   obs[2 * NODE_EMB + c0] = mn0;
   obs[2 * NODE_EMB + c1] = mn1;
+  if (interest >= 0) {   // compressed:299-303: the interest node's own embedding, zeros if it is not in the graph / not Running
+    const int ip = interest_known ? (int)W.pos[interest] : (extra ? n_disc : -1);
+    const bool have = ip >= 0 && !none_running && (W.dynb[ip] & 0x80);
+    obs[OBS_GRAPH + c0] = have ? W.y[ip * NODE_EMB + c0] : 0.f;
+    obs[OBS_GRAPH + c1] = have ? W.y[ip * NODE_EMB + c1] : 0.f;
+  }
   if (lane == 0) {
-    obs[OBS_GRAPH] = (float)n;                              // create_discrete_features, compressed:309-316
-    obs[OBS_GRAPH + 1] = (float)scalar(S, P, S_N_OWNED, b);
+    obs[P.obs_dim - 2] = (float)n_disc;                     // create_discrete_features, compressed:309-316
+    obs[P.obs_dim - 1] = (float)scalar(S, P, S_N_OWNED, b);
     scalar(S, P, S_N_ENCODES, b) += 1;
   }
   __syncwarp();
@@ -318,7 +334,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
   st[5] = scalar(S, P, S_OWNABLE, b); st[6] = scalar(S, P, S_DISCOVERABLE, b); st[7] = scalar(S, P, S_DISRUPTABLE, b);
   st[8] = (double)running / (double)n_disc; st[9] = 0; st[10] = 0;
   st[11] = scalar(S, P, S_DISC_AMOUNT, b); st[12] = scalar(S, P, S_DISCOVERABLE_AMOUNT, b);
-  st[13] = goal_reached(S, P, b) ? 1.0 : 0.0;
+  st[13] = goal_reached(S, P, b, is_node_goal(P) ? T.sc_interest[sc] : -1) ? 1.0 : 0.0;
   double v = 0.0;
   if (lane < 14) {
 #pragma unroll
@@ -329,7 +345,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
   else if (lane == 15) atomicAdd(&S.accum[A_RETURN], S.ep_return[b]);
   else if (lane == 16) atomicAdd(&S.accum[A_LENGTH], (double)scalar(S, P, S_STEPCOUNT, b));
   else if (lane == 17 && reason >= 1) atomicAdd(&S.accum[A_WINS + reason - 1], 1.0);
-  for (int i = lane; i < OBS_DIM; i += 32) S.term_obs[(size_t)b * OBS_DIM + i] = S.obs[(size_t)b * OBS_DIM + i];
+  for (int i = lane; i < P.obs_dim; i += 32) S.term_obs[(size_t)b * P.obs_dim + i] = S.obs[(size_t)b * P.obs_dim + i];
   __syncwarp();
   if (lane == 0) scalar(S, P, S_EPISODES, b) += 1;
   __syncwarp();
@@ -379,7 +395,8 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     scalar(S, P, S_OWNABLE, b) = own;
     scalar(S, P, S_DISCOVERABLE, b) = dis;
     scalar(S, P, S_DISRUPTABLE, b) = dsr;
-    scalar(S, P, S_PROP_NODES, b) = P.goal == GOAL_CONTROL ? own : (P.goal == GOAL_DISCOVERY ? dis : dsr);
+    const int bg = base_goal(P);
+    scalar(S, P, S_PROP_NODES, b) = bg == GOAL_CONTROL ? own : (bg == GOAL_DISCOVERY ? dis : dsr);
     scalar(S, P, S_DISCOVERABLE_AMOUNT, b) = T.sc_discoverable_amount[sc];
     scalar(S, P, S_N_SLOTS, b) = 0;
     S.work_est[b] = 0;
@@ -430,7 +447,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 
   // per-warp scratch
   unsigned char* wbase = smem_raw + sizeof(SharedWeights);
-  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
+  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 3 * MAX_NODES;
   WarpScratch W;
   {
     unsigned char* p = wbase + (size_t)warp * kWarpBytesSmem;
@@ -440,6 +457,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     W.dinv = W.g + SMEM_NODES * NODE_EMB;
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
     W.dynb = W.pos + MAX_NODES;
+    W.ord = W.dynb + MAX_NODES;
   }
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
@@ -478,6 +496,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
         encode_env(T, P, S, SW, W, b, lane);
         build_table(T, P, S, W, b, lane);
         keep &= ~FL_DIRTY;
+        if (is_node_goal(P)) keep |= FL_INTEREST_IN_GRAPH;
       }
       if (flags & FL_FINISHED_THIS_STEP) {
         finish_episode(T, P, S, b, lane);
@@ -493,6 +512,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       W.g = W.ysm + SMEM_NODES * NODE_EMB;
       encode_env(T, P, S, SW, W, b, lane);
       build_table(T, P, S, W, b, lane);
+      // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even
+      // if nothing else changes
+      if (is_node_goal(P) && lane == 0) scalar(S, P, S_FLAGS, b) = FL_DIRTY | FL_INTEREST_IN_GRAPH;
     }
     __syncwarp();
     if (mode == 1) i += total_warps;
@@ -507,7 +529,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 }
 
 size_t observe_smem_bytes() {
-  const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 2 * MAX_NODES;
+  const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 3 * MAX_NODES;
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 

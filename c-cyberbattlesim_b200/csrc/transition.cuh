@@ -50,7 +50,6 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   const int sc = SC(S_SCENARIO);
   const int N = T.sc_num_nodes[sc];
   const int node_off = T.sc_node_off[sc];
-  const int starter = SC(S_STARTER);
   EnvBits M{S.masks, P.words, B, b};
 
   SC(S_STEPCOUNT) += 1;                                   // :303
@@ -190,33 +189,42 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
     }
   }
 
+  // ---- node-specific games: the reward is zeroed once the interest node is discovered and not targeted (:322-326) ----
+  const int interest = is_node_goal(P) ? T.sc_interest[sc] : -1;
+  if (interest >= 0 && t != interest && M.get(M_DISCOVERED, interest)) reward = 0.0;
+
   // ---- goal / termination (cyberbattle_env.py:338-370, 438-514) ----
+  const int starter = SC(S_STARTER);
   int n_goal = 0, n_data = 0, n_pending = 0;
   bool any_running_owned = false;
-  for (int w = 0; w < P.words; ++w) {
+  for (int w = 0; w < P.words; ++w) {     // one pass over the mask words: goal popcounts and the lost test
     const uint32_t own = M.word(M_OWNED, w), disc = M.word(M_DISCOVERED, w), stop = M.word(M_STOPPED, w);
     const uint32_t not_starter = ((starter >> 5) == w) ? ~(1u << (starter & 31)) : 0xFFFFFFFFu;
     if (P.goal == GOAL_CONTROL) n_goal += __popc(own & M.word(M_PRIV_ROOT, w) & not_starter);
     else if (P.goal == GOAL_DISRUPTION) n_goal += __popc(disc & stop & not_starter);
-    else {
+    else if (P.goal == GOAL_DISCOVERY) {
       n_goal += __popc(disc & not_starter);
       n_data += __popc(disc & M.word(M_HAS_DATA, w));
       n_pending += __popc(disc & M.word(M_COLLECTED, w) & ~M.word(M_EXFILTRATED, w));
     }
     any_running_owned |= (own & ~stop) != 0u;
   }
-  bool goal_reached;
-  if (P.goal == GOAL_CONTROL) goal_reached = (n_goal == SC(S_OWNABLE));
-  else if (P.goal == GOAL_DISRUPTION) goal_reached = (n_goal == SC(S_DISRUPTABLE));
-  else goal_reached = (n_goal == SC(S_DISCOVERABLE) && n_data == 0 && n_pending == 0);
+  bool goal_ok;
+  if (P.goal == GOAL_CONTROL) goal_ok = (n_goal == SC(S_OWNABLE));
+  else if (P.goal == GOAL_DISRUPTION) goal_ok = (n_goal == SC(S_DISRUPTABLE));
+  else if (P.goal == GOAL_DISCOVERY) goal_ok = (n_goal == SC(S_DISCOVERABLE) && n_data == 0 && n_pending == 0);
+  else goal_ok = goal_reached(S, P, b, interest);     // *_node goals: a few bit tests on the interest node
+  // check_end_game (:438-454): killing the interest node loses control_node / discovery_node games
+  const bool lost = ((P.goal == GOAL_CONTROL_NODE || P.goal == GOAL_DISCOVERY_NODE) && M.get(M_STOPPED, interest)) ||
+                    !any_running_owned;
 
   const int num_iter = SC(S_NUM_ITER);
   int reason = 0;
   bool done = false, trunc = false;
-  if (goal_reached) {
+  if (goal_ok) {
     if (P.goal == GOAL_DISRUPTION || P.stop_at_goal) done = true;
     reward = P.winning_reward; reason = 1;
-  } else if (!any_running_owned) {
+  } else if (lost) {
     done = true; reward = P.losing_reward; reason = 2;
   } else if (P.prop_coeff != 0.0 && (double)num_iter >= (double)SC(S_PROP_NODES) * P.prop_coeff) {
     trunc = true; reason = 3;
@@ -234,9 +242,10 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   // records whether any node feature, edge or node set changed since the last encode (successful outcomes mutate
   // the target or the discovered set; reward > 0 adds / updates an edge).
   const bool dirty = (flags & FL_DIRTY) || code < 16 || add_edge;
+  const int sticky = flags & FL_INTEREST_IN_GRAPH;          // survives until the episode's reset
   const bool encode_now = reencode && dirty;
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
-          (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0);
+          (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
   SC(S_FLAGS) = flags;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
     // three cost classes, claimed heaviest first: episode end (statistics + reset + encode + table), re-encode, edge only

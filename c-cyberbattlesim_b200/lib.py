@@ -13,7 +13,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("CBS_LIB", "libcbsim.so"))
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 i32, i64, u64, f32, f64 = ct.c_int32, ct.c_int64, ct.c_uint64, ct.c_float, ct.c_double
 P = ct.c_void_p
@@ -40,7 +40,7 @@ class CbsScenarioTables(ct.Structure):
     _fields_ = ([("num_scenarios", i32), ("max_nodes", i32), ("words", i32), ("num_nodes_total", i32), ("num_inst", i32),
                  ("num_rows", i32), ("num_recon", i32), ("num_ports_total", i32), ("num_uvuln_total", i32),
                  ("num_global_vulns", i32), ("num_instof", i64)] + [(n, P) for n in _SCENARIO_PTRS] +
-                [("num_feasible", i32)] + [(n, P) for n in _SCENARIO_PTRS2])
+                [("num_feasible", i32), ("sc_interest", P)] + [(n, P) for n in _SCENARIO_PTRS2])
 
 
 _GAE_PTRS = ["node_static", "dyn_proj", "vuln_h", "nn0_b", "bn1_scale", "bn1_shift", "gcn_wt", "bn2_scale", "bn2_shift"]
@@ -166,6 +166,7 @@ def make_scenario_struct(tables, goal: int):
     t.sc_feasible_off = arr(tables.sc_feasible_off[goal], np.int32)
     t.feasible_starters = arr(tables.feasible_starters[goal], np.int32)
     t.num_feasible = len(tables.feasible_starters[goal])
+    t.sc_interest = arr(tables.sc_interest, np.int32) if goal >= C.GOAL_CONTROL_NODE else None
     for name, dt in (("nd_value", np.int32), ("nd_level_at_access", np.uint8), ("nd_ownable", np.int32),
                      ("nd_discoverable", np.int32), ("nd_disruptable", np.int32), ("nd_row_off", np.int32),
                      ("outblock", np.uint32), ("uvuln_global", np.int32), ("inst_of", np.int32), ("vi_port", np.int32),

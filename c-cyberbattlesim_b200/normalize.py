@@ -33,10 +33,11 @@ class DeviceVecNormalize:
     with SB3's per-key treatment of Dict observations) and the reward vector of a BatchedCyberBattleEnv."""
 
     def __init__(self, env, norm_obs: bool = True, norm_reward: bool = True, clip_obs: float = 10.0, clip_reward: float = 10.0,
-                 gamma: float = 0.99, epsilon: float = 1e-8, training: bool = True, obs_split: int = 192):
+                 gamma: float = 0.99, epsilon: float = 1e-8, training: bool = True, obs_split: int = None):
         self.env, self.norm_obs, self.norm_reward = env, norm_obs, norm_reward
         self.clip_obs, self.clip_reward, self.gamma, self.epsilon, self.training = clip_obs, clip_reward, gamma, epsilon, training
         dev = env.device
+        obs_split = env.obs.shape[1] - 2 if obs_split is None else obs_split
         self.split = obs_split
         self.obs_rms = {"graph_embeddings": RunningMeanStd((obs_split,), dev),
                         "discrete_features": RunningMeanStd((env.obs.shape[1] - obs_split,), dev)}

@@ -412,8 +412,9 @@ class ScenarioTables:
     sc_discoverable_amount: np.ndarray  # i32[S]
     sc_init_has_data: np.ndarray   # u32[S, words]
     sc_init_visible: np.ndarray    # u32[S, words]
-    sc_feasible_off: np.ndarray    # i32[3, S+1]  per goal: offsets into feasible_starters[goal]
-    feasible_starters: List[np.ndarray]   # 3 x i32[...]  starters passing the isolation filter
+    sc_feasible_off: np.ndarray    # i32[6, S+1]  per goal (constants.GOAL_*): offsets into feasible_starters[goal]
+    feasible_starters: List[np.ndarray]   # 6 x i32[...]  starters passing the isolation filter / able to reach the interest node
+    sc_interest: np.ndarray        # i32[S]  interest node per scenario (-1: none; *_node goals need one)
     # per node (global node index)
     nd_value: np.ndarray           # i32
     nd_level_at_access: np.ndarray  # u8
@@ -460,8 +461,25 @@ VI_LEVEL_REMOTE_SHIFT = 6  # 2 bits: same, first REMOTE privesc result
 
 
 def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold: float = 0.1,
-                      check_ref_counts: bool = True) -> ScenarioTables:
+                      check_ref_counts: bool = True, interest_nodes: Optional[Sequence[int]] = None,
+                      interest_node_value: Optional[int] = None) -> ScenarioTables:
+    """``interest_nodes[s]`` (one node index per scenario) enables the *_node goals: it defines their feasible starters
+    (cyberbattle_env.py:249-275) and, with ``interest_node_value``, overrides that node's value (:277) in the compiled
+    tables and in the specs kept for the GAE folding."""
     S = len(specs)
+    if interest_nodes is not None:
+        if len(interest_nodes) != S:
+            raise ValueError("interest_nodes needs one entry per scenario")
+        patched = []
+        for spec, it in zip(specs, interest_nodes):
+            if not (0 <= int(it) < spec.num_nodes):
+                raise ValueError(f"interest node {it} out of range for scenario '{spec.name}'")
+            if interest_node_value is not None:
+                nodes = list(spec.nodes)
+                nodes[int(it)] = dataclasses.replace(nodes[int(it)], value=int(interest_node_value))
+                spec = dataclasses.replace(spec, nodes=nodes)
+            patched.append(spec)
+        specs = patched
     max_nodes = max(s.num_nodes for s in specs)
     if max_nodes > C.MAX_NODES:
         raise ValueError(f"scenario with {max_nodes} nodes exceeds MAX_NODES={C.MAX_NODES}")
@@ -476,8 +494,8 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
     sc_num_ports, sc_port_off = [], [0]
     sc_num_uvuln, sc_uvuln_off, sc_instof_off = [], [0], [0]
     sc_da, sc_hd, sc_vis = [], [], []
-    feas = [[], [], []]
-    feas_off = [[0], [0], [0]]
+    feas = [[] for _ in range(6)]
+    feas_off = [[0] for _ in range(6)]
     nd_value, nd_laa, nd_own, nd_disc, nd_disr = [], [], [], [], []
     nd_row_off = [0]
     outblock = []
@@ -600,9 +618,9 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
         sc_vis.append(vis)
         # reachability (cyberbattle_env.py:205-217) and feasible starters (:219-248)
         knows, access, dos = scenario_graphs(spec)
-        own, _ = _reach_counts(access)
-        disc, _ = _reach_counts(knows)
-        disr, _ = _reach_counts(dos)
+        own, own_reach = _reach_counts(access)
+        disc, disc_reach = _reach_counts(knows)
+        disr, disr_reach = _reach_counts(dos)
         if check_ref_counts and spec.ref_counts is not None:
             for key, mine in (("ownable", own), ("discoverable", disc), ("disruptable", disr)):
                 if not np.array_equal(spec.ref_counts[key], mine):
@@ -613,6 +631,11 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
         thr = isolation_filter_threshold * n
         for g, cnt in ((C.GOAL_CONTROL, own), (C.GOAL_DISCOVERY, disc), (C.GOAL_DISRUPTION, disr)):
             ok = [j for j in range(n) if not (cnt[j] < thr)]
+            feas[g].extend(ok)
+            feas_off[g].append(len(feas[g]))
+        it = -1 if interest_nodes is None else int(interest_nodes[len(sc_node_off) - 1])
+        for g, reach in ((C.GOAL_CONTROL_NODE, own_reach), (C.GOAL_DISCOVERY_NODE, disc_reach), (C.GOAL_DISRUPTION_NODE, disr_reach)):
+            ok = [] if it < 0 else [j for j in range(n) if j != it and reach[j, it]]     # cyberbattle_env.py:249-275
             feas[g].extend(ok)
             feas_off[g].append(len(feas[g]))
         sc_node_off.append(sc_node_off[-1] + n)
@@ -628,6 +651,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
         sc_init_has_data=np.stack(sc_hd), sc_init_visible=np.stack(sc_vis),
         sc_feasible_off=np.array(feas_off, np.int32),
         feasible_starters=[np.array(f, np.int32) for f in feas],
+        sc_interest=np.array([-1] * S if interest_nodes is None else [int(x) for x in interest_nodes], np.int32),
         nd_value=np.array(nd_value, np.int32), nd_level_at_access=np.array(nd_laa, np.uint8),
         nd_ownable=np.array(nd_own, np.int32), nd_discoverable=np.array(nd_disc, np.int32),
         nd_disruptable=np.array(nd_disr, np.int32), nd_row_off=np.array(nd_row_off, np.int32),

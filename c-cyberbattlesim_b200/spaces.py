@@ -43,7 +43,8 @@ def action_space():
     return Box(low=-4.0, high=4.0, shape=(C.ACTION_DIM,), dtype=np.float32)
 
 
-def observation_space():
-    """Dict(graph_embeddings Box(-16,16,(192,)), discrete_features Box(0,300,(2,))) — compressed:128-142"""
-    return Dict({"graph_embeddings": Box(low=-16.0, high=16.0, shape=(C.OBS_DIM,), dtype=np.float64),
+def observation_space(graph_dim: int = C.OBS_DIM):
+    """Dict(graph_embeddings Box(-16,16,(192,)) [(256,) for *_node goals], discrete_features Box(0,300,(2,))) —
+    compressed:119-142"""
+    return Dict({"graph_embeddings": Box(low=-16.0, high=16.0, shape=(graph_dim,), dtype=np.float64),
                  "discrete_features": Box(low=0.0, high=300.0, shape=(2,), dtype=np.float64)})

@@ -29,22 +29,22 @@ except Exception:  # noqa: BLE001
 
 
 def _obs_dict(obs: np.ndarray):
-    return {"graph_embeddings": obs[:, :C.OBS_DIM].astype(np.float64),
-            "discrete_features": obs[:, C.OBS_DIM:].astype(np.float64)}
+    """[B, 194 | 258] flat observation -> the reference's Dict (the last two floats are the discrete features)."""
+    return {"graph_embeddings": obs[:, :-2].astype(np.float64), "discrete_features": obs[:, -2:].astype(np.float64)}
 
 
 class CyberBattleVecEnv(_SB3VecEnv):
     def __init__(self, env: BatchedCyberBattleEnv, lazy_infos: bool = False):
         self.env = env
         self.num_envs = env.num_envs
-        self.observation_space = spaces.observation_space()
+        self.observation_space = spaces.observation_space(env.obs_dim - 2)
         self.action_space = spaces.action_space()
         self.lazy_infos = lazy_infos
         self.render_mode = None
         self._actions = None
         B = self.num_envs
         self._h_actions = torch.empty(B, C.ACTION_DIM, dtype=torch.float32).pin_memory()
-        self._h_obs = torch.empty(B, C.OBS_DIM + 2, dtype=torch.float32).pin_memory()
+        self._h_obs = torch.empty(B, env.obs_dim, dtype=torch.float32).pin_memory()
         self._h_rew = torch.empty(B, dtype=torch.float32).pin_memory()
         self._h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
         self._h_info = torch.empty(B, 8, dtype=torch.int32).pin_memory()
@@ -90,8 +90,8 @@ class CyberBattleVecEnv(_SB3VecEnv):
             infos.append(self._info_dict(b, info[b]))
         for b in finished:
             d = infos[b]
-            d["terminal_observation"] = {"graph_embeddings": term[b, :C.OBS_DIM].astype(np.float64),
-                                         "discrete_features": term[b, C.OBS_DIM:].astype(np.float64)}
+            d["terminal_observation"] = {"graph_embeddings": term[b, :-2].astype(np.float64),
+                                         "discrete_features": term[b, -2:].astype(np.float64)}
             # the reference reports done|truncated as `terminated` (compressed:451 via switch.py:121,148), so SB3 never
             # bootstraps at a cut-off; kept identical here
             d["TimeLimit.truncated"] = False
@@ -178,10 +178,11 @@ class RandomSwitchEnvB200:
     truncated, info), get_statistics(), set_cut_off(), set_proportional_cutoff_coefficient()
     (_env/cyberbattle_env_switch.py:109-167,194-203).  auto_reset is off: the caller resets, as gymnasium expects."""
 
-    def __init__(self, specs, gae_weights, cfg=None, device: int = 0, switch_interval: int = 0, seed: int = 0):
+    def __init__(self, specs, gae_weights, cfg=None, device: int = 0, switch_interval: int = 0, seed: int = 0,
+                 interest_nodes=None):
         self.env = BatchedCyberBattleEnv(specs, gae_weights, cfg, num_envs=1, device=device, auto_reset=False,
-                                         switch_interval=switch_interval, seed=seed)
-        self.observation_space = spaces.observation_space()
+                                         switch_interval=switch_interval, seed=seed, interest_nodes=interest_nodes)
+        self.observation_space = spaces.observation_space(self.env.obs_dim - 2)
         self.action_space = spaces.action_space()
         self.num_envs = 1
         self.done = False

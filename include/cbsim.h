@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CBS_ABI_VERSION 1
+#define CBS_ABI_VERSION 2
 
 /* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
  * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
@@ -31,6 +31,7 @@ extern "C" {
 #define CBS_OUTCOME_DIM 9
 #define CBS_ACTION_DIM 905 /* 64 + 64 + 768 + 9 */
 #define CBS_OBS_DIM 194    /* graph_embeddings[192] (mean|max|min) + discrete_features[2] (discovered, owned) */
+#define CBS_OBS_DIM_NODE_GOAL 258 /* *_node goals: + the interest node's embedding[64] before the discrete features (compressed:119-125) */
 #define CBS_NUM_STATS 14   /* cyberbattle_env.py:517-524 get_statistics() tuple */
 #define CBS_NUM_REWARDS 10
 #define CBS_NUM_PENALTIES 18
@@ -58,7 +59,8 @@ typedef struct {
   int32_t num_envs;             /* envs held by this handle (this GPU's shard) */
   int64_t global_env_offset;    /* index of env 0 in the whole batch: keys the Philox streams so results do not depend on the GPU count */
   uint64_t seed;                /* Philox key */
-  int32_t goal;                 /* 0 control, 1 discovery, 2 disruption (cyberbattle_env.py:467-487) */
+  int32_t goal;                 /* 0 control, 1 discovery, 2 disruption, 3 control_node, 4 discovery_node, 5 disruption_node
+                                   (cyberbattle_env.py:467-514); 3..5 need cbs_scenario_tables.sc_interest */
   int32_t episode_iterations;   /* constant cut-off (cyberbattle_env.py:366) */
   double proportional_cutoff_coefficient; /* 0 = off (cyberbattle_env.py:361,457-460) */
   double winning_reward, losing_reward;
@@ -94,6 +96,7 @@ typedef struct {
   const int32_t* sc_feasible_off;        /* [S+1] for the configured goal */
   const int32_t* feasible_starters;      /* [sc_feasible_off[S]] */
   int32_t num_feasible;
+  const int32_t* sc_interest;            /* [S] interest node of each scenario (cyberbattle_env.py:127-131), NULL for the network-wide goals */
   const int32_t* nd_value;               /* [Nn] */
   const uint8_t* nd_level_at_access;     /* [Nn] */
   const int32_t* nd_ownable;             /* [Nn] */
@@ -159,7 +162,7 @@ int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double proportion
 /* ---- the step path ----------------------------------------------------------------------------- */
 /* replaces RandomSwitchEnv.reset -> CyberBattleCompressedEnv.reset (switch.py:151-167, compressed:158-189,
  * cyberbattle_env.py:134-186).  env_mask_dev: [num_envs] bytes, non-zero = reset; NULL = all.
- * obs_dev (optional): [num_envs][CBS_OBS_DIM] float32, written for every env. */
+ * obs_dev (optional): [num_envs][obs_len] float32 (obs_len = 194, or 258 for *_node goals), written for every env. */
 int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintptr_t stream);
 
 /* replaces find_closest_action_embedding (compressed:570-590, scipy cdist 'cosine' + argmin over the action
@@ -238,8 +241,8 @@ int cbs_sync(cbs_handle* h);
 int cbs_struct_sizes(int32_t* out3);
 /* bytes of device memory held by the handle (tables + env state) */
 int64_t cbs_state_bytes(const cbs_handle* h);
-/* out5 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active, vt_stride } */
-int cbs_capacities(const cbs_handle* h, int32_t* out5);
+/* out6 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active, vt_stride, observation length } */
+int cbs_capacities(const cbs_handle* h, int32_t* out6);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,7 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
                done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
                dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
                disc_order=np.full((T, n_nodes), -1, np.int16), owned_order=np.full((T, n_nodes), -1, np.int16),
-               counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, C.OBS_DIM + 2), np.float32),
+               counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, env.obs_dim), np.float32),
                episode=np.zeros(T, np.int32))
     reset_obs, reset_masks, stats = [], [], []
     obs = env.reset()

@@ -73,4 +73,4 @@ def test_rejects_bad_arguments(lib):
     assert b"ABI" in lib.cbs_last_error(None)
     assert lib.cbs_create(None, ct.byref(h)) == -1
     with pytest.raises(ValueError):
-        cb.EnvConfig(goal="control_node")
+        cb.EnvConfig(goal="conquer")

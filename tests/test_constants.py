@@ -58,6 +58,14 @@ def test_scalars_match_lib():
     assert _enum("Accum")["N_ACCUM"] == L.NUM_ACCUM == len(L.ACCUM_NAMES)
 
 
+def test_goals():
+    g = _enum("Goal")
+    for name, v in g.items():
+        assert getattr(C, name) == v
+    assert sorted(C.GOALS.values()) == list(range(6))
+    assert C.obs_dim_for_goal("control") == 194 and C.obs_dim_for_goal("discovery_node") == 258
+
+
 def test_dimensions():
     assert C.ACTION_DIM == 905 and C.NODE_FEAT_DIM == 1576 and C.OBS_DIM == 192
     assert re.search(r"ACTION_DIM = (\d+)", HDR).group(1) == "905"

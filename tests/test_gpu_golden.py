@@ -21,10 +21,12 @@ def test_cuda_replays_reference_trace(name, gemm, golden_dir):
     from tests.gpu_harness import replay, TieFollower
     case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
     B = 5
+    interest = None if case["interest"] is None else [case["interest"]]
     env = BatchedCyberBattleEnv([case["spec"]], case["weights"], case["cfg"], num_envs=B, auto_reset=True,
-                                decode_gemm=gemm)
+                                decode_gemm=gemm, interest_nodes=interest)
     env.set_starter_queue(np.tile(case["starters"][None, :], (B, 1)))
-    follower = TieFollower(OracleEnv(case["spec"], case["weights"], case["cfg"]), case["spec"], case["starters"])
+    follower = TieFollower(OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"]), case["spec"],
+                           case["starters"])
     rec, consistent = replay(env, case["actions"], case["uniforms"], case["spec"].num_nodes, check_env=B - 1,
                              follower=follower, policy_rows=case["policy_rows"])
     env.close()

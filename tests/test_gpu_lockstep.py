@@ -35,7 +35,10 @@ def philox_pick(seed, env, step, stream, n):
     ("disruption", (6, 12), 60, 33, 60),          # odd batch size
     ("control", (120, 128), 330, 4, 140),         # maximum node count (4 mask words, 255 snapshot slots), Ug > 256: two GEMM N-tiles
     ("control", (3, 5), 30, 1, 80),               # a single env, tiny scenarios
-], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny"])
+    ("control_node", (8, 16), 100, 24, 60),       # node-specific goals: one interest node per scenario, 258-float observation
+    ("discovery_node", (8, 16), 100, 24, 60),
+], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
+        "control-node", "discovery-node"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
     import torch
     from scipy.spatial import distance
@@ -54,12 +57,25 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
     specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool, **gkw) for k in range(S)]
     cfg = cb.EnvConfig(goal=goal)
     w = GaeWeights.random(3)
+    interest = None
+    if goal.endswith("node"):      # an interest node that some starter can reach, per scenario
+        interest, keep = [], []
+        for sp in specs:
+            probe = OracleEnv(sp, w, cfg, interest_node=0)
+            cand = [i for i in range(sp.num_nodes) if any(i in probe._reach_sets[goal[:-5]][s] for s in range(sp.num_nodes) if s != i)]
+            if cand:
+                interest.append(int(cand[len(cand) // 2]))
+                keep.append(sp)
+        specs, S = keep, len(keep)
+        assert S >= 2
     sc_of_env = rng.integers(0, S, size=B).astype(np.int32)
     env = BatchedCyberBattleEnv(specs, w, cfg, num_envs=B, scenario_of_env=sc_of_env, seed=seed, global_env_offset=offset,
-                                auto_reset=True)
+                                auto_reset=True, interest_nodes=interest)
     tables = env.tables
     g = cb.constants.GOALS[goal]
-    oracles = [OracleEnv(specs[sc_of_env[b]], w, cfg) for b in range(B)]
+    G = env.obs_dim - 2
+    oracles = [OracleEnv(specs[sc_of_env[b]], w, cfg, interest_node=None if interest is None else interest[sc_of_env[b]])
+               for b in range(B)]
     vidx = [tr.vuln_index(specs[sc_of_env[b]]) for b in range(B)]
     episodes = [0] * B
     total_steps = [0] * B
@@ -74,7 +90,7 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
     obs_h = obs.cpu().numpy()
     for b in range(B):
         o = oracles[b].reset(starter=starter_for(b))
-        np.testing.assert_allclose(obs_h[b, :192], o["graph_embeddings"], rtol=1e-5, atol=2e-5)
+        np.testing.assert_allclose(obs_h[b, :G], o["graph_embeddings"], rtol=1e-5, atol=2e-5)
     flips = 0
     actions = rng.uniform(-4, 4, size=(T, B, 905)).astype(np.float32)
     for t in range(T):
@@ -106,12 +122,12 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
             assert bool(done_h[b]) == bool(dn)
             np.testing.assert_allclose(rew_h[b], r, rtol=1e-5, atol=1e-4)
             if dn:
-                np.testing.assert_allclose(term[b, :192], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
-                assert tuple(term[b, 192:]) == tuple(float(x) for x in ob["discrete_features"])
+                np.testing.assert_allclose(term[b, :G], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
+                assert tuple(term[b, G:]) == tuple(float(x) for x in ob["discrete_features"])
                 episodes[b] += 1
                 ob = o.reset(starter=starter_for(b))
-            np.testing.assert_allclose(obs_h[b, :192], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
-            assert tuple(obs_h[b, 192:]) == tuple(float(x) for x in ob["discrete_features"])
+            np.testing.assert_allclose(obs_h[b, :G], ob["graph_embeddings"], rtol=1e-5, atol=2e-5)
+            assert tuple(obs_h[b, G:]) == tuple(float(x) for x in ob["discrete_features"])
             assert np.array_equal(masks_to_u64(m, b), tr.masks_to_array(o.masks())), f"step {t} env {b}: masks differ"
     sc = env.scalars()
     assert flips <= max(1, B * T // 200), f"{flips} near-tie flips in {B * T} env-steps"
