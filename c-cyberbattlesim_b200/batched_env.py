@@ -110,6 +110,21 @@ class BatchedCyberBattleEnv:
             assert q.shape[0] == self.num_envs
             self._check(self.lib.cbs_set_starter_queue(self._h, q.ctypes.data_as(ct.c_void_p), q.shape[1]))
 
+    def set_defender_draws(self, scan_nodes: Optional[torch.Tensor], detect_uniforms: Optional[torch.Tensor]):
+        """Test hook: replace the static defender's random draws (static_defender.py:48,53) by device tensors
+        scan_nodes int32[B, scan_capacity] / detect_uniforms float32[B, scan_capacity]; the tensors are read by every
+        following step (update them in place), ``None, None`` restores the Philox streams."""
+        if scan_nodes is None:
+            self._def_draws = None
+            self._check(self.lib.cbs_set_defender_draws(self._h, None, None))
+            return
+        k = int(self.cfg.scan_capacity)
+        assert scan_nodes.shape == (self.num_envs, k) and detect_uniforms.shape == (self.num_envs, k)
+        assert scan_nodes.dtype == torch.int32 and detect_uniforms.dtype == torch.float32
+        assert scan_nodes.is_contiguous() and detect_uniforms.is_contiguous() and scan_nodes.device == self.device
+        self._def_draws = (scan_nodes, detect_uniforms)          # keep them alive
+        self._check(self.lib.cbs_set_defender_draws(self._h, self._p(scan_nodes), self._p(detect_uniforms)))
+
     def set_cut_off(self, cut_off: int):
         """cyberbattle_env_switch.py:198-199"""
         self.cfg.episode_iterations = int(cut_off)
@@ -210,6 +225,13 @@ class BatchedCyberBattleEnv:
 
     def owned_order(self) -> np.ndarray:
         return self.read(L.F_OWNED_ORDER, np.uint8, (self.num_envs, self.ncap))
+
+    def owned_raw(self) -> np.ndarray:
+        """env.owned_nodes exactly as the reference keeps it under a static defender (removals, duplicates): uint8[B, 2*ncap],
+        length in scalars()[S_N_OWNED_RAW]."""
+        if not self.cfg.static_defender_agent:
+            raise RuntimeError("owned_raw() is only maintained with a static defender; use owned_order()")
+        return self.read(L.F_OWNED_RAW, np.uint8, (self.num_envs, 2 * self.ncap))
 
     def terminal_obs(self) -> np.ndarray:
         return self.read(L.F_TERMINAL_OBS, np.float32, (self.num_envs, self.obs_dim))

@@ -5,7 +5,7 @@ cyberbattle_env_compressed.py:74-89)."""
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict
+from typing import Dict, Optional
 
 import numpy as np
 
@@ -66,6 +66,13 @@ class EnvConfig:
     random_starter_node: bool = True
     switch_interval: int = 5
     interest_node_value: int = 200        # agents/config/train_config.yaml:16 (value of the node of interest, *_node goals)
+    # static defender (_env/static_defender.py): None or "reimage" (ScanAndReimageCompromisedMachines, :27-60)
+    static_defender_agent: Optional[str] = None
+    detect_probability: float = 0.05      # train_config.yaml:39-40
+    scan_capacity: int = 3                # :41-42
+    scan_frequency: int = 3               # :43-44
+    # compressed:455-462: when set, every step whose DESIRED outcome is a success class re-encodes the graph - i.e. every step
+    precise_graph_encoding: bool = False
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
 
@@ -77,14 +84,37 @@ class EnvConfig:
             self.rewards_dict = dict(DEFAULT_REWARDS[self.goal])
         if not self.penalties_dict:
             self.penalties_dict = dict(DEFAULT_PENALTIES[self.goal])
+        if self.static_defender_agent not in (None, "reimage"):
+            raise ValueError("static_defender_agent must be None or 'reimage' (the 'events' defender is not implemented, DESIGN.md §5)")
+        if self.static_defender_agent:
+            if not (1 <= int(self.scan_capacity) <= C.MAX_SCAN_CAPACITY):
+                raise ValueError(f"scan_capacity must be in 1..{C.MAX_SCAN_CAPACITY}")
+            if int(self.scan_frequency) < 1:
+                raise ValueError("scan_frequency must be >= 1")
 
     @classmethod
     def from_reference_dicts(cls, train_config: dict, rewards_config: dict, goal: str = "control") -> "EnvConfig":
         """Build from the dicts the reference loads with yaml (agents/train_agent.py:229-239)."""
         keys = {f for f in cls.__dataclass_fields__}
         # reference options the batched env does not implement must not be dropped silently
-        if train_config.get("static_defender_agent"):
-            raise ValueError("static defenders are not implemented by the batched env (DESIGN.md §5)")
+        train_config = dict(train_config)
+        sda = train_config.get("static_defender_agent")
+        if sda is not None and not isinstance(sda, (str, bool)):     # already mapped to an object (train_agent.py:393-399)
+            sda = {"ScanAndReimageCompromisedMachines": "reimage", "ExternalRandomEvents": "events"}.get(type(sda).__name__, "?")
+            obj = train_config["static_defender_agent"]
+            for k_obj, k_cfg in (("probability", "detect_probability"), ("scan_capacity", "scan_capacity"),
+                                 ("scan_frequency", "scan_frequency")):
+                if hasattr(obj, k_obj):
+                    train_config[k_cfg] = getattr(obj, k_obj)
+        train_config["static_defender_agent"] = sda or None
+        if sda and sda != "reimage":
+            raise ValueError("only the 'reimage' static defender is implemented by the batched env (DESIGN.md §5)")
+        if sda:
+            # train_agent.py:395-397 draws the three parameters once per run from [min, max]; the midpoint is used here
+            for k in ("detect_probability", "scan_capacity", "scan_frequency"):
+                if k not in train_config and f"{k}_min" in train_config:
+                    mid = (train_config[f"{k}_min"] + train_config[f"{k}_max"]) / 2
+                    train_config[k] = mid if k == "detect_probability" else int(round(mid))
         if train_config.get("distance_metric", "cosine") != "cosine":
             raise ValueError("only the cosine decode metric is implemented")
         if train_config.get("sample_subset_samples"):
@@ -121,4 +151,5 @@ class EnvConfig:
                     remove_main_obstacles=self.remove_main_obstacles, remove_all_obstacles=self.remove_all_obstacles,
                     random_starter_node=self.random_starter_node, rewards_dict=dict(self.rewards_dict),
                     interest_node_value=self.interest_node_value, switch_interest_node_interval=1,
-                    penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None)
+                    penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None,
+                    precise_graph_encoding=self.precise_graph_encoding)

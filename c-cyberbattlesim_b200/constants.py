@@ -133,9 +133,17 @@ M_EVASION = 7
 M_STOPPED = 8      # status == Stopped
 M_PRIV_USER = 9    # privilege_level >= LocalUser
 M_PRIV_ROOT = 10   # privilege_level == ROOT
-N_MASKS = 11
+# planes that only change under the re-imaging static defender (_env/static_defender.py:27-60)
+M_IMAGING = 11      # status == Imaging (static_defender_actions.py:37-52)
+M_X_IMAGING = 12    # the node's CACHED feature vector in the evolving visible graph says Imaging (compressed:472-479 refresh rule)
+M_EVER_OWNED = 13   # NodeTrackingInformation.last_owned_at is not None (attacker_actions.py:32,87)
+M_OWN_STALE = 14    # re-imaged after it was last owned: last_owned_at < last_reimaging (attacker_actions.py:561-573)
+N_MASKS = 15
+N_MASKS_V1 = 11     # fixtures recorded before the defender planes existed hold the first 11
 MASK_NAMES = ["owned", "discovered", "visible", "has_data", "collected", "exfiltrated", "persistence",
-              "evasion", "stopped", "priv_user", "priv_root"]
+              "evasion", "stopped", "priv_user", "priv_root", "imaging", "x_imaging", "ever_owned", "own_stale"]
+REIMAGING_DURATION = 15   # static_defender_actions.py:19
+MAX_SCAN_CAPACITY = 8     # scan draws per step the device path supports (train_config.yaml:41-42 uses 3)
 
 # reward / penalty vector slots (agents/config/rewards_config.yaml). Order shared with the CUDA side.
 REWARD_KEYS = ["value_coefficient", "cost_coefficient", "node_discovered_coefficient",

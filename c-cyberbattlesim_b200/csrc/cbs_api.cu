@@ -121,6 +121,10 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   if (cfg->abi_version != CBS_ABI_VERSION) return fail(nullptr, CBS_ERR_INVALID_ARG, "ABI version mismatch (%d vs %d)", cfg->abi_version, CBS_ABI_VERSION);
   if (cfg->num_envs <= 0) return fail(nullptr, CBS_ERR_INVALID_ARG, "num_envs must be positive");
   if (cfg->goal < 0 || cfg->goal > 5) return fail(nullptr, CBS_ERR_INVALID_ARG, "unsupported goal %d", cfg->goal);
+  if (cfg->static_defender != 0 && cfg->static_defender != 1)
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "static_defender must be 0 (none) or 1 (scan and re-image)");
+  if (cfg->static_defender && (cfg->scan_capacity < 1 || cfg->scan_capacity > MAX_SCAN_CAPACITY || cfg->scan_frequency < 1))
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "scan_capacity must be in 1..%d and scan_frequency >= 1", MAX_SCAN_CAPACITY);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CBS_ERR_NO_DEVICE, "no CUDA device available (libcbsim has no CPU fallback)");
@@ -150,6 +154,11 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   for (int i = 0; i < N_PENALTIES; ++i) P.pen[i] = cfg->penalties[i];
   P.qlen = 0;
   P.act_stride = ACTION_DIM;
+  P.defender = cfg->static_defender;
+  P.scan_capacity = cfg->scan_capacity;
+  P.scan_frequency = cfg->scan_frequency;
+  P.detect_prob = cfg->detect_probability;
+  P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
   *out = h;
   return CBS_OK;
 }
@@ -186,7 +195,11 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
       if (t->sc_interest[s] < 0 || t->sc_interest[s] >= t->sc_num_nodes[s]) return fail(h, CBS_ERR_INVALID_ARG, "interest node of scenario %d out of range", s);
     UP(sc_interest, S_);
   }
-  UP(nd_value, Nn); UP(nd_level_at_access, Nn); UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
+  UP(nd_value, Nn); UP(nd_level_at_access, Nn);
+  if (h->cfg.static_defender) {
+    if (!t->nd_reimageable) return fail(h, CBS_ERR_INVALID_ARG, "the static defender needs nd_reimageable");
+    UP(nd_reimageable, Nn);
+  } UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
   UP(nd_row_off, 2 * (size_t)Nn + 1); UP(outblock, (size_t)t->num_ports_total * t->words);
   UP(uvuln_global, t->num_uvuln_total); UP(inst_of, t->num_instof);
   UP(vi_port, I); UP(vi_flags, I); UP(vi_kinds_any, I); UP(vi_kinds_remote, I); UP(vi_success, I); UP(vi_cost, I);
@@ -216,7 +229,9 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
     if (l < max_steps) max_steps = l;
   }
   max_steps += 1;   // the cut-offs test the pre-increment counter (cyberbattle_env.py:361-366, :394)
-  int slots = 2 * t->max_nodes - 1;
+  // table-growing encodes: each adds an owned or a discovered node ... or, under a defender, sees a node come back from
+  // re-imaging with pairs still missing
+  int slots = (h->cfg.static_defender ? 4 : 2) * t->max_nodes - 1;
   if (max_steps + 1 < slots) slots = max_steps + 1;
   if (slots > 255) slots = 255;
   P.slots = h->cfg.max_slots > 0 ? h->cfg.max_slots : slots;
@@ -236,6 +251,9 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
 #define AL(field, count) if ((rc = dalloc(h, h->state_allocs, &S.field, (size_t)(count)))) return rc
   AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
+  P.ocap = 2 * P.ncap;
+  if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
+  else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
   AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
@@ -283,6 +301,14 @@ int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats) {
   if (!h) return CBS_ERR_INVALID_ARG;
   if (stride_floats < ACTION_DIM) return fail(h, CBS_ERR_INVALID_ARG, "action stride must be >= %d floats", ACTION_DIM);
   h->P.act_stride = stride_floats;
+  return CBS_OK;
+}
+
+int cbs_set_defender_draws(cbs_handle* h, const int32_t* scan_nodes_dev, const float* detect_uniforms_dev) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  if (!h->P.defender) return fail(h, CBS_ERR_INVALID_ARG, "no static defender configured");
+  h->S.def_nodes = scan_nodes_dev;
+  h->S.def_uniforms = detect_uniforms_dev;
   return CBS_OK;
 }
 
@@ -448,6 +474,9 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_MASKS: *p = S.masks; *bytes = (int64_t)N_MASKS * P.words * B * 4; break;
     case CBS_F_DISC_ORDER: *p = S.disc_order; *bytes = B * P.ncap; break;
     case CBS_F_OWNED_ORDER: *p = S.owned_order; *bytes = B * P.ncap; break;
+    case CBS_F_OWNED_RAW: *p = S.owned_raw; *bytes = P.defender ? B * P.ocap : 1; break;
+    case CBS_F_Z_HIST: *p = S.z_hist; *bytes = B * P.slots * P.ncap * NODE_EMB * 4; break;
+    case CBS_F_REIMAGE_LEFT: *p = S.reimage_left; *bytes = P.defender ? B * P.ncap : 1; break;
     case CBS_F_SCALARS: *p = S.scal; *bytes = (int64_t)N_SCALARS * B * 4; break;
     case CBS_F_TERMINAL_OBS: *p = S.term_obs; *bytes = B * P.obs_dim * 4; break;
     case CBS_F_OBS: *p = S.obs; *bytes = B * P.obs_dim * 4; break;
@@ -505,7 +534,7 @@ int cbs_sync(cbs_handle* h) {
   CK(h, cudaDeviceSynchronize());
   int flag = 0;
   CK(h, cudaMemcpy(&flag, h->S.errflag, 4, cudaMemcpyDeviceToHost));
-  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 9 tensor-core pipeline timeout)", flag);
+  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 5 owned-node list, 9 tensor-core pipeline timeout)", flag);
   return CBS_OK;
 }
 

@@ -29,7 +29,15 @@ enum Code : int { OC_INVALID_SRC_NOT_OWNED = 16, OC_INVALID_TGT_NOT_DISCOVERED, 
 enum Goal : int { GOAL_CONTROL = 0, GOAL_DISCOVERY = 1, GOAL_DISRUPTION = 2, GOAL_CONTROL_NODE = 3, GOAL_DISCOVERY_NODE = 4,
                   GOAL_DISRUPTION_NODE = 5 };
 enum Mask : int { M_OWNED = 0, M_DISCOVERED, M_VISIBLE, M_HAS_DATA, M_COLLECTED, M_EXFILTRATED, M_PERSISTENCE,
-                  M_EVASION, M_STOPPED, M_PRIV_USER, M_PRIV_ROOT, N_MASKS };
+                  M_EVASION, M_STOPPED, M_PRIV_USER, M_PRIV_ROOT,
+                  // planes that only change under the re-imaging static defender (_env/static_defender.py:27-60)
+                  M_IMAGING,      // status == Imaging (simulation/static_defender_actions.py:37-52)
+                  M_X_IMAGING,    // the node's cached feature vector in the visible graph says Imaging (compressed:472-479)
+                  M_EVER_OWNED,   // last_owned_at is not None (attacker_actions.py:87)
+                  M_OWN_STALE,    // re-imaged after it was last owned (attacker_actions.py:561-573)
+                  N_MASKS };
+constexpr int REIMAGING_DURATION = 15;   // static_defender_actions.py:19
+constexpr int MAX_SCAN_CAPACITY = 8;
 enum Reward : int { R_VALUE = 0, R_COST, R_NODE_DISCOVERED, R_COLLECTED, R_EXFILTRATED, R_PERSISTENCE, R_PRIVESC,
                     R_VISIBILITY, R_DOS, R_EVASION, N_REWARDS };
 enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLECT, P_NO_DATA_EXFIL, P_ALREADY_PERSISTENT,
@@ -39,7 +47,10 @@ enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLE
 // per-env int32 scalar planes
 enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE,
                     S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES,
-                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF, N_SCALARS };
+                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF,
+                    S_N_OWNED_RAW,   // len(env.owned_nodes) under a defender (the list can hold duplicates, cyberbattle_env.py:425-430)
+                    S_N_REIMAGED,    // len(overall_reimaged) == num_events of the episode (cyberbattle_env.py:419-422)
+                    N_SCALARS };
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
               FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
@@ -59,6 +70,7 @@ struct Tables {  // immutable, device pointers
   const uint32_t *sc_init_has_data, *sc_init_visible;
   const int32_t *nd_value, *nd_ownable, *nd_discoverable, *nd_disruptable, *nd_row_off;
   const uint8_t* nd_level_at_access;
+  const uint8_t* nd_reimageable;
   const uint32_t* outblock;
   const int32_t *inst_of, *vi_port, *vi_recon_any, *vi_recon_remote, *vi_ulocal, *row_inst, *uvuln_global, *row_ulocal;
   const uint32_t *vi_flags, *row_packed;
@@ -81,6 +93,11 @@ struct Params {  // configuration, by value
   float margin;
   int qlen;
   int act_stride;   // row pitch (floats) of the action tensors handed to decode; 905 = dense
+  // static defender ScanAndReimageCompromisedMachines (_env/static_defender.py:27-60); defender == 0: none
+  int defender, scan_capacity, scan_frequency;
+  double detect_prob;
+  int always_encode;   // defender or precise_graph_encoding: every step re-encodes (compressed:401,455-462)
+  int ocap;            // capacity of owned_raw
 };
 
 struct State {  // mutable, device pointers
@@ -89,6 +106,13 @@ struct State {  // mutable, device pointers
   uint8_t* disc_order;   // [B][ncap]
   uint8_t* owned_order;  // [B][ncap]
   uint8_t* pair_slot;    // [B][ncap*ncap]   0xFF = pair not in the action table
+  // defender only (1-byte dummies otherwise):
+  uint8_t* owned_raw;    // [B][ocap]  env.owned_nodes exactly as the reference keeps it (removals, duplicates); owned_order
+                         //            stays the append-only list of every node that ever was a source of table rows
+  uint8_t* reimage_left; // [B][ncap]  node_reimaging_progress (static_defender_actions.py:23)
+  uint8_t* pair_opos;    // [B][ncap*ncap]  position of the source in owned_raw when the pair entered the table (tie order)
+  const int32_t* def_nodes;     // [B][scan_capacity] test override of the scan draws (random.choices), or nullptr -> Philox
+  const float* def_uniforms;    // [B][scan_capacity] test override of the detection uniforms, consumed in call order
   float* z_hist;         // [B][slots][ncap][64]  node embeddings of the encode that created the slot
   float* zn2_hist;       // [B][slots][ncap]      their squared norms
   __half* z16_hist;      // [B][slots][ncap][64]  half-precision copy read by the approximate decode scan

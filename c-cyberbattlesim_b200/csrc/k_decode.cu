@@ -108,7 +108,7 @@ struct SelWarp {
   float a_o[16];
   float p_st[32], p_n2[32];   // per staged pair: a_s.z_s + a_t.z_t (from the fp16 snapshots), |z_s|^2 + |z_t|^2 + 1
   int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
-  uint32_t p_key[32];         // slot << 16 | owned position << 8 | discovered position
+  uint32_t p_key[32];         // slot << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
   float c_score[CAND_CAP];    // rows still within `margin` of the running maximum, waiting for the float64 re-score
   uint32_t c_key[CAND_CAP], c_packed[CAND_CAP];
   int c_row[CAND_CAP];
@@ -185,8 +185,8 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
     if (sh.c_score[i] < threshold) continue;               // NaN scores are kept (comparison false)
     const uint32_t k = sh.c_key[i];
     const int r = sh.c_row[i];
-    const int slot = (int)(k >> 16), s = sh.oorder[(k >> 8) & 0xFF], t = sh.dorder[k & 0xFF];
-    const unsigned long long key = ((unsigned long long)k << 40) | (unsigned long long)(unsigned)r;
+    const int slot = (int)(k >> 24), s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
+    const unsigned long long key = ((unsigned long long)k << 32) | (unsigned long long)(unsigned)r;
     const double d = exact_distance(T, P, S, act, b, s, t, slot, sh.c_packed[i], na, lane);
     // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
     const bool dn = d != d, bn = best.d != best.d;
@@ -218,7 +218,7 @@ struct FusedTransition {
   uint8_t* done;
 };
 
-template <bool FUSE>
+template <bool FUSE, bool DEF>
 __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
                                                                    int vt_stride, int vt_cached, int sched_buf, FusedTransition ft,
                                                                    int32_t* __restrict__ sel_out, double* __restrict__ dist_out,
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       S.dist[b] = 0.0;
       if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
       if (dist_out) dist_out[b] = 0.0;
-      if (FUSE) transition_env(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      if (FUSE) transition_env<DEF>(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
     }
     sched_done(S, sched_buf);
     return;
@@ -334,7 +334,10 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
           st += dot8(hs[i], sh.a_st + 8 * i);
           st += dot8(ht[i], sh.a_st + NODE_EMB + 8 * i);
         }
-        key = ((uint32_t)slot << 16) | ((uint32_t)op << 8) | (uint32_t)dp;
+        // exact ties resolve in table-insertion order: slot, then the source's position in owned_nodes WHEN the pair was
+        // added (== its current position unless a defender removed nodes from the list), then the target's position
+        const int opk = DEF ? (int)S.pair_opos[(size_t)b * P.ncap * P.ncap + s * P.ncap + t] : op;
+        key = ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)op;
         live = cnt > 0;
       }
     }
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
         if (j < total) {
           const int kind = (packed[q] >> 20) & 15;
           const uint32_t k = sh.p_key[pp[q]];
-          const int s = sh.oorder[(k >> 8) & 0xFF], t = sh.dorder[k & 0xFF];
+          const int s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
           if (!row_filtered(P, kind, s, t, starter, interest)) {
             const int u = packed[q] & 0xFFFFF, oh = (packed[q] >> 24) & 15;
             const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
     }
     // fused step: the transition of this env runs here, on one lane, while the other warps are still scanning
-    if (FUSE) transition_env(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+    if (FUSE) transition_env<DEF>(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
   }
   sched_done(S, sched_buf);
 }
@@ -465,22 +468,19 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
   const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
   const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
-  static size_t attr[2] = {0, 0};
-  const int which = fuse_transition ? 1 : 0;
+  static size_t attr[4] = {0, 0, 0, 0};
+  const int which = (fuse_transition ? 1 : 0) | (P.defender ? 2 : 0);
+  using KernelFn = void (*)(Tables, Params, State, const float*, int, int, int, FusedTransition, int32_t*, double*, long long*);
+  const KernelFn kernels[4] = {decode_select_kernel<false, false>, decode_select_kernel<true, false>,
+                               decode_select_kernel<false, true>, decode_select_kernel<true, true>};
+  const KernelFn kern = kernels[which];
   if (smem > 48 * 1024 && smem > attr[which]) {
-    cudaError_t e = fuse_transition
-                        ? cudaFuncSetAttribute(decode_select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(decode_select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr[which] = smem;
   }
   const int grid = (P.B + SEL_WARPS - 1) / SEL_WARPS;
-  if (fuse_transition)
-    decode_select_kernel<true><<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,
-                                                                   dist_out, g_sel_trace);
-  else
-    decode_select_kernel<false><<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,
-                                                                    dist_out, g_sel_trace);
+  kern<<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out, dist_out, g_sel_trace);
   return cudaGetLastError();
 }
 

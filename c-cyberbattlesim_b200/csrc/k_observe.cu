@@ -40,6 +40,8 @@ struct WarpScratch {
   uint8_t* pos;       // [MAX_NODES] node id -> position in discovered order
   uint8_t* ord;       // [MAX_NODES] graph node ids by position (discovered order, then the interest node of *_node goals)
   uint8_t* dynb;      // [MAX_NODES] per position: visible | persistence<<1 | collected<<2 | exfiltrated<<3 | evasion<<4 | privilege<<5 | running<<7
+  uint8_t* xst;       // [MAX_NODES] per position: MachineStatus value in the node's CACHED feature vector (differs from the live
+                      //             status only under a defender: the vector is rebuilt only when the node is a successful target)
 };
 
 // the dynamic part of a node's feature vector (compressed:365-380), packed once per encode by lane-per-node
@@ -47,17 +49,23 @@ __device__ __forceinline__ uint8_t pack_dyn(const State& S, const Params& P, int
   const int w = node >> 5, sh = node & 31;
   auto bit = [&](int plane) -> uint32_t { return (ld_mask(S, P, plane, w, b) >> sh) & 1u; };
   const uint32_t priv = bit(M_PRIV_ROOT) ? 3u : bit(M_PRIV_USER);
+  const uint32_t running = (bit(M_STOPPED) | (P.defender ? bit(M_IMAGING) : 0u)) ^ 1u;
   return (uint8_t)(bit(M_VISIBLE) | (bit(M_PERSISTENCE) << 1) | (bit(M_COLLECTED) << 2) | (bit(M_EXFILTRATED) << 3) |
-                   (bit(M_EVASION) << 4) | (priv << 5) | ((bit(M_STOPPED) ^ 1u) << 7));
+                   (bit(M_EVASION) << 4) | (priv << 5) | (running << 7));
 }
-__device__ __forceinline__ void node_dyn(uint8_t d, float& vis, float x[NUM_DYN]) {
+// MachineStatus in the cached feature vector: Stopped 0, Running 1, Imaging 2 (model.py:287-291)
+__device__ __forceinline__ uint8_t pack_xstatus(const State& S, const Params& P, int b, int node) {
+  if (bit_of(S, P, M_STOPPED, node, b)) return 0;
+  return (P.defender && bit_of(S, P, M_X_IMAGING, node, b)) ? 2 : 1;
+}
+__device__ __forceinline__ void node_dyn(uint8_t d, uint8_t xstatus, float& vis, float x[NUM_DYN]) {
   vis = (float)(d & 1);
   x[0] = (float)((d >> 1) & 1);
   x[1] = (float)((d >> 2) & 1);
   x[2] = (float)((d >> 3) & 1);
   x[3] = (float)((d >> 4) & 1);
   x[4] = (float)((d >> 5) & 3);     // privilege level 0 / 1 / 3
-  x[5] = (float)((d >> 7) & 1);     // MachineStatus value: Stopped 0, Running 1
+  x[5] = (float)xstatus;
 }
 
 // ---- add_edge_evolving_visible_graph (compressed:214-246), mean aggregation, in the W1-projected space ----
@@ -127,6 +135,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     W.pos[node] = (uint8_t)i;
     W.dinv[i] = 1.f;
     W.dynb[i] = pack_dyn(S, P, b, node);
+    W.xst[i] = pack_xstatus(S, P, b, node);
   }
   __syncwarp();
 
@@ -134,7 +143,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   for (int i = 0; i < n; ++i) {
     const int node = order[i];
     float vis, x[NUM_DYN];
-    node_dyn(W.dynb[i], vis, x);
+    node_dyn(W.dynb[i], W.xst[i], vis, x);
     const float* ns = T.node_static + (size_t)(node_off + node) * 2 * ROW + 17 * NODE_EMB;
     float a0 = ns[c0] + vis * ns[ROW + c0], a1 = ns[c1] + vis * ns[ROW + c1];
 #pragma unroll
@@ -157,7 +166,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     if (lane < NN_CH) hl = fmaxf(S.edge_m[((size_t)b * P.ecap + e) * NN_CH + lane] + SW.nn0b[lane], 0.f);
     else if (lane == NN_CH) hl = 1.f;
     float vis, x[NUM_DYN];
-    node_dyn(W.dynb[is], vis, x);
+    node_dyn(W.dynb[is], W.xst[is], vis, x);
     const float* ns = T.node_static + (size_t)(node_off + js) * 2 * ROW;
     float m0 = 0.f, m1 = 0.f;
 #pragma unroll
@@ -260,7 +269,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   }
   if (lane == 0) {
     obs[P.obs_dim - 2] = (float)n_disc;                     // create_discrete_features, compressed:309-316
-    obs[P.obs_dim - 1] = (float)scalar(S, P, S_N_OWNED, b);
+    obs[P.obs_dim - 1] = (float)scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);   // len(owned_nodes)
     scalar(S, P, S_N_ENCODES, b) += 1;
   }
   __syncwarp();
@@ -271,14 +280,22 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 __device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane) {
   const int node_off_bt = scalar(S, P, S_NODE_OFF, b);
   int new_rows = 0;
-  const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, S_N_OWNED, b);
+  // sources: env.owned_nodes.  Under a defender that is the exact list (removals, duplicates: the dict comprehension of
+  // compressed:491-492 keeps the first occurrence); otherwise the append-only list.
+  const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);
   const uint8_t* dorder = S.disc_order + (size_t)b * P.ncap;
-  const uint8_t* oorder = S.owned_order + (size_t)b * P.ncap;
+  const uint8_t* oorder = P.defender ? S.owned_raw + (size_t)b * P.ocap : S.owned_order + (size_t)b * P.ncap;
   uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
+  uint8_t* po = S.pair_opos + (size_t)b * P.ncap * P.ncap;
   const int slot = scalar(S, P, S_N_SLOTS, b);
   bool any_new = false;
+  uint32_t seen[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
   for (int op = 0; op < n_owned; ++op) {
     const int s = oorder[op];
+    if (P.defender) {
+      if ((seen[s >> 5] >> (s & 31)) & 1u) continue;
+      seen[s >> 5] |= 1u << (s & 31);
+    }
     if (!(W.dynb[W.pos[s]] & 0x80)) continue;               // stopped sources add no rows (compressed:491-492)
     for (int base = 0; base < n_disc; base += 32) {
       const int dp = base + lane;
@@ -288,6 +305,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
         fresh = (W.dynb[dp] & 0x80) && ps[s * P.ncap + t] == 0xFF;
         if (fresh && slot < P.slots) {
           ps[s * P.ncap + t] = (uint8_t)slot;
+          if (P.defender) po[s * P.ncap + t] = (uint8_t)op;   // insertion order inside the slot (exact-tie order of the decode)
           const int g = node_off_bt + t;
           new_rows += T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g + (s == t ? 0 : 1)];
         }
@@ -324,7 +342,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
     const uint32_t disc = ld_mask(S, P, M_DISCOVERED, w, b), stop = ld_mask(S, P, M_STOPPED, w, b);
     owned += __popc(ld_mask(S, P, M_OWNED, w, b));
     disrupted += __popc(disc & stop);
-    running += __popc(disc & ~stop);
+    running += __popc(disc & ~stop & ~(P.defender ? ld_mask(S, P, M_IMAGING, w, b) : 0u));
   }
   const int n_disc = scalar(S, P, S_N_DISC, b);
   const int flags = scalar(S, P, S_FLAGS, b);
@@ -332,7 +350,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
   double st[14];
   st[0] = owned; st[1] = n_disc; st[2] = N - n_disc; st[3] = disrupted; st[4] = N;
   st[5] = scalar(S, P, S_OWNABLE, b); st[6] = scalar(S, P, S_DISCOVERABLE, b); st[7] = scalar(S, P, S_DISRUPTABLE, b);
-  st[8] = (double)running / (double)n_disc; st[9] = 0; st[10] = 0;
+  st[8] = (double)running / (double)n_disc; st[9] = st[10] = P.defender ? scalar(S, P, S_N_REIMAGED, b) : 0;   // len(overall_reimaged), num_events
   st[11] = scalar(S, P, S_DISC_AMOUNT, b); st[12] = scalar(S, P, S_DISCOVERABLE_AMOUNT, b);
   st[13] = goal_reached(S, P, b, is_node_goal(P) ? T.sc_interest[sc] : -1) ? 1.0 : 0.0;
   double v = 0.0;
@@ -377,7 +395,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     if (plane == M_HAS_DATA) v = T.sc_init_has_data[sc * P.words + w];
     else if (plane == M_VISIBLE) v = T.sc_init_visible[sc * P.words + w];
     else if (w == sw && (plane == M_OWNED || plane == M_DISCOVERED || (plane == M_PRIV_USER && laa >= 1) ||
-                         (plane == M_PRIV_ROOT && laa == 3))) v = sbit;
+                         (plane == M_PRIV_ROOT && laa == 3) || (plane == M_EVER_OWNED && P.defender))) v = sbit;
     S.masks[((size_t)plane * P.words + w) * P.B + b] = v;
   }
   uint32_t* ps = reinterpret_cast<uint32_t*>(S.pair_slot + (size_t)b * P.ncap * P.ncap);
@@ -405,6 +423,11 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     scalar(S, P, S_OUTCOME, b) = -1;
     S.disc_order[(size_t)b * P.ncap] = (uint8_t)starter;
     S.owned_order[(size_t)b * P.ncap] = (uint8_t)starter;
+    if (P.defender) {
+      S.owned_raw[(size_t)b * P.ocap] = (uint8_t)starter;
+      scalar(S, P, S_N_OWNED_RAW, b) = 1;
+      scalar(S, P, S_N_REIMAGED, b) = 0;
+    }
     S.ep_return[b] = 0.0;
   }
   __syncwarp();
@@ -447,7 +470,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 
   // per-warp scratch
   unsigned char* wbase = smem_raw + sizeof(SharedWeights);
-  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 3 * MAX_NODES;
+  constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 4 * MAX_NODES;
   WarpScratch W;
   {
     unsigned char* p = wbase + (size_t)warp * kWarpBytesSmem;
@@ -458,6 +481,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     W.pos = reinterpret_cast<uint8_t*>(W.dinv + MAX_NODES);
     W.dynb = W.pos + MAX_NODES;
     W.ord = W.dynb + MAX_NODES;
+    W.xst = W.ord + MAX_NODES;
   }
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
@@ -529,7 +553,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
 }
 
 size_t observe_smem_bytes() {
-  const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 3 * MAX_NODES;
+  const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 4 * MAX_NODES;
   return sizeof(SharedWeights) + OBS_WARPS * per_warp;
 }
 

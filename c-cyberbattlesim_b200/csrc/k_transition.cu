@@ -5,6 +5,7 @@
 
 namespace cbs {
 
+template <bool DEF>
 __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_in,
                                                          const double* __restrict__ dist_in,
                                                          const float* __restrict__ uniforms, int sched_out,
@@ -12,14 +13,17 @@ __global__ void __launch_bounds__(128) transition_kernel(Tables T, Params P, Sta
                                                          uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
-  transition_env(T, P, S, b, reinterpret_cast<const int4*>(sel_in)[b], dist_in ? dist_in[b] : 0.0, uniforms, sched_out,
+  transition_env<DEF>(T, P, S, b, reinterpret_cast<const int4*>(sel_in)[b], dist_in ? dist_in[b] : 0.0, uniforms, sched_out,
                  reward_out, done_out, trunc_out, outcome_out);
 }
 
 cudaError_t launch_transition(const Tables& T, const Params& P, const State& S, const int32_t* sel, const double* dist,
                               const float* uniforms, int sched_out, float* reward, uint8_t* done, uint8_t* trunc,
                               uint8_t* outcome, cudaStream_t stream) {
-  transition_kernel<<<(P.B + 127) / 128, 128, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
+  if (P.defender)
+    transition_kernel<true><<<(P.B + 127) / 128, 128, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
+  else
+    transition_kernel<false><<<(P.B + 127) / 128, 128, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
   return cudaGetLastError();
 }
 

@@ -22,8 +22,101 @@ struct EnvBits {
   __device__ void clr(int plane, int node) { masks[((size_t)plane * words + (node >> 5)) * B + b] &= ~(1u << (node & 31)); }
 };
 
+// Philox draw j of a stream family: component (j & 3) of stream `base + (j >> 2)`
+__device__ __forceinline__ uint32_t philox_word(uint64_t key, uint64_t env, uint32_t step, uint32_t base, int j) {
+  const Philox4 r = philox4x32_10(key, env, step, base + (uint32_t)(j >> 2));
+  const int c = j & 3;
+  return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
+}
+
+// ---- static defender step (cyberbattle_env.py:416-430) with ScanAndReimageCompromisedMachines (static_defender.py:45-60)
+//      and StaticDefenderAgentActions (static_defender_actions.py:37-68).  Returns true when anything changed. ----
+// Everything it needs is passed by value: handing the kernel-parameter structs to a non-inlined function by reference
+// would copy them to the caller's stack on the hot path.
+struct DefenderCtx {
+  uint8_t *left, *raw, *oo;                 // this env's reimage_left / owned_raw / owned_order rows
+  int32_t *n_raw, *n_owned, *n_reimaged;    // this env's scalars
+  const int32_t* def_nodes;                 // this env's override rows (or nullptr)
+  const float* def_uniforms;
+  const uint8_t* reimageable;               // this scenario's nd_reimageable row
+  int32_t* errflag;
+  uint64_t seed, genv;
+  double detect_prob;
+  int words, ocap, scan_capacity, scan_frequency;
+};
+__device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int stepcount, int total_steps, bool check_reown) {
+  bool event = false;
+  uint8_t* left = P.left;
+  uint8_t* raw = P.raw;
+  int32_t& n_raw = *P.n_raw;
+  // on_attacker_step_taken (:54-68): count down, then bring the node back (with the agent if it was persistent)
+  for (int w = 0; w < P.words; ++w) {
+    uint32_t img = M.word(M_IMAGING, w);
+    while (img) {
+      const int n = (w << 5) + __ffs(img) - 1;
+      img &= img - 1;
+      const int l = left[n];
+      if (l > 0) left[n] = (uint8_t)(l - 1);
+      else {
+        M.clr(M_IMAGING, n);
+        if (M.get(M_PERSISTENCE, n)) M.set(M_OWNED, n);
+        event = check_reown = true;
+      }
+    }
+  }
+  // scan (:46-57): scan_capacity nodes drawn with replacement; a detection uniform is drawn only for eligible nodes
+  if (stepcount % P.scan_frequency == 0) {
+    int ui = 0, reimaged = 0;
+    for (int j = 0; j < P.scan_capacity; ++j) {
+      int n;
+      if (P.def_nodes) n = P.def_nodes[j];
+      else n = (int)(((uint64_t)philox_word(P.seed, P.genv, (uint32_t)total_steps, 3u, j) * (uint64_t)N) >> 32);
+      if (n < 0 || n >= N) continue;
+      if (M.get(M_STOPPED, n) || M.get(M_IMAGING, n) || !M.get(M_OWNED, n) || M.get(M_EVASION, n)) continue;
+      float u;
+      if (P.def_uniforms) u = P.def_uniforms[ui];
+      else u = (float)(philox_word(P.seed, P.genv, (uint32_t)total_steps, 5u, ui) >> 8) * (1.0f / 16777216.0f);
+      ++ui;
+      if ((double)u <= P.detect_prob && P.reimageable[n]) {     // reimage_node (:37-52)
+        left[n] = (uint8_t)REIMAGING_DURATION;
+        M.clr(M_OWNED, n);
+        M.set(M_IMAGING, n);
+        M.set(M_OWN_STALE, n);                    // last_reimaging = now > last_owned_at
+        ++reimaged;
+        int k = 0;                                // owned_nodes.remove(node): first occurrence (cyberbattle_env.py:425)
+        while (k < n_raw && raw[k] != n) ++k;
+        if (k < n_raw) { for (; k + 1 < n_raw; ++k) raw[k] = raw[k + 1]; --n_raw; }
+        event = true;
+      }
+    }
+    *P.n_reimaged += reimaged;
+  }
+  // :427-430 every Running node with the agent installed that is not in owned_nodes is appended, in node order
+  if (check_reown) {
+    uint32_t inl[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
+    for (int k = 0; k < n_raw; ++k) inl[raw[k] >> 5] |= 1u << (raw[k] & 31);
+    uint8_t* oo = P.oo;
+    int32_t& n_owned = *P.n_owned;
+    for (int w = 0; w < P.words; ++w) {
+      uint32_t add = M.word(M_OWNED, w) & ~M.word(M_STOPPED, w) & ~M.word(M_IMAGING, w) & ~inl[w];
+      while (add) {
+        const int n = (w << 5) + __ffs(add) - 1;
+        add &= add - 1;
+        if (n_raw < P.ocap) raw[n_raw++] = (uint8_t)n; else atomicExch(P.errflag, 5);
+        int k = 0;
+        while (k < n_owned && oo[k] != n) ++k;
+        if (k == n_owned) { oo[n_owned] = (uint8_t)n; ++n_owned; }
+        event = true;
+      }
+    }
+  }
+  return event;
+}
+
 }  // namespace
 
+// DEF: a static defender is configured (compile-time, so the default kernels carry none of its code or registers)
+template <bool DEF>
 static __device__ __forceinline__ void transition_env(const Tables& T, const Params& P, const State& S, int b, int4 sl, double dist,
                                             const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
@@ -68,9 +161,9 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
     reward = P.pen[P_INVALID_ACTION]; code = OC_INVALID_SRC_NOT_OWNED;
   } else if (!local && !M.get(M_DISCOVERED, t)) {
     reward = P.pen[P_INVALID_ACTION]; code = OC_INVALID_TGT_NOT_DISCOVERED;
-  } else if (M.get(M_STOPPED, s)) {
+  } else if (M.get(M_STOPPED, s) || (DEF && M.get(M_IMAGING, s))) {
     reward = P.pen[P_INVALID_ACTION]; code = OC_SRC_NOT_RUNNING;
-  } else if (!local && M.get(M_STOPPED, t)) {
+  } else if (!local && (M.get(M_STOPPED, t) || (DEF && M.get(M_IMAGING, t)))) {
     reward = P.pen[P_INVALID_ACTION]; code = OC_TGT_NOT_RUNNING;
   } else {
     const int U = T.sc_num_uvuln[sc];
@@ -152,6 +245,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
         else if (cur >= lvl) { reward = P.pen[P_PRIVESC_ALREADY]; code = OC_REPEATED; ok = false; }
         else {                                              // __mark_node_as_owned(t, level) :70-89
           M.set(M_OWNED, t); M.set(M_DISCOVERED, t);
+          if (DEF) { M.set(M_EVER_OWNED, t); M.clr(M_OWN_STALE, t); }
           if (lvl >= 1) M.set(M_PRIV_USER, t);
           if (lvl == 3) M.set(M_PRIV_ROOT, t);
           total += P.rew[R_PRIVESC];
@@ -162,18 +256,34 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
       case K_CREDACCESS:
         if (local) { reward = P.pen[P_OUTCOME_NOT_VALID]; code = OC_REMOTE_OUTCOME_LOCAL; ok = false; }  // :536-540
         else {
-          const bool was_owned = M.get(M_OWNED, t);         // :327 marks before testing
+          // :327 marks before testing.  "Currently owned" = owned since the last re-imaging (:561-573); without a
+          // defender that is the same as "ever owned" == agent installed
+          bool ever = M.get(M_OWNED, t), was_owned = ever;
+          if (DEF) {
+            ever = M.get(M_EVER_OWNED, t);
+            was_owned = ever && !M.get(M_OWN_STALE, t);
+            M.set(M_EVER_OWNED, t); M.clr(M_OWN_STALE, t);
+          }
           const int laa = T.nd_level_at_access[node_off + t];
           M.set(M_OWNED, t);
           if (laa >= 1) M.set(M_PRIV_USER, t);
           if (laa == 3) M.set(M_PRIV_ROOT, t);
           if (was_owned) { reward = P.pen[P_ALREADY_OWNED]; code = OC_REPEATED; ok = false; }
           else {
-            total += P.rew[R_VALUE] * (double)T.nd_value[node_off + t];
+            if (!ever) total += P.rew[R_VALUE] * (double)T.nd_value[node_off + t];   // :336-340 first ownership only
             uint8_t* oo = S.owned_order + (size_t)b * P.ncap;   // cyberbattle_env.py:408-410
             int n_owned = SC(S_N_OWNED);
-            oo[n_owned] = (uint8_t)t;
-            SC(S_N_OWNED) = n_owned + 1;
+            if (DEF) {        // owned_nodes.append(t): the exact list may now hold t twice
+              uint8_t* raw = S.owned_raw + (size_t)b * P.ocap;
+              const int n_raw = SC(S_N_OWNED_RAW);
+              if (n_raw < P.ocap) { raw[n_raw] = (uint8_t)t; SC(S_N_OWNED_RAW) = n_raw + 1; } else atomicExch(S.errflag, 5);
+              int k = 0;
+              while (k < n_owned && oo[k] != t) ++k;
+              if (k == n_owned) { oo[n_owned] = (uint8_t)t; SC(S_N_OWNED) = n_owned + 1; }
+            } else {
+              oo[n_owned] = (uint8_t)t;
+              SC(S_N_OWNED) = n_owned + 1;
+            }
           }
         }
         break;
@@ -193,10 +303,44 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   const int interest = is_node_goal(P) ? T.sc_interest[sc] : -1;
   if (interest >= 0 && t != interest && M.get(M_DISCOVERED, interest)) reward = 0.0;
 
+  // ---- static defender (cyberbattle_env.py:331-332), then the cached-feature rule of the visible graph: the target's
+  //      vector is rebuilt from the post-defender state for these obtained outcomes only (compressed:472-479) ----
+  bool def_event = false;
+  if (DEF) {
+    DefenderCtx D;
+    D.left = S.reimage_left + (size_t)b * P.ncap;
+    D.raw = S.owned_raw + (size_t)b * P.ocap;
+    D.oo = S.owned_order + (size_t)b * P.ncap;
+    D.n_raw = &SC(S_N_OWNED_RAW); D.n_owned = &SC(S_N_OWNED); D.n_reimaged = &SC(S_N_REIMAGED);
+    D.def_nodes = S.def_nodes ? S.def_nodes + (size_t)b * P.scan_capacity : nullptr;
+    D.def_uniforms = S.def_uniforms ? S.def_uniforms + (size_t)b * P.scan_capacity : nullptr;
+    D.reimageable = T.nd_reimageable + node_off;
+    D.errflag = S.errflag;
+    D.seed = P.seed; D.genv = (uint64_t)(P.global_env_offset + b);
+    D.detect_prob = P.detect_prob;
+    D.words = P.words; D.ocap = P.ocap; D.scan_capacity = P.scan_capacity; D.scan_frequency = P.scan_frequency;
+    def_event = defender_step(D, M, N, SC(S_STEPCOUNT), total_steps, code == K_PRIVESC);
+    if (code < 16 && code != K_RECON) {
+      if (M.get(M_IMAGING, t)) M.set(M_X_IMAGING, t); else M.clr(M_X_IMAGING, t);
+    }
+  }
+
   // ---- goal / termination (cyberbattle_env.py:338-370, 438-514) ----
   const int starter = SC(S_STARTER);
   int n_goal = 0, n_data = 0, n_pending = 0;
   bool any_running_owned = false;
+  int roots_in_list = 0;
+  bool interest_in_list = false;
+  if (DEF) {   // the tests below run over env.owned_nodes, which is no longer the agent_installed set
+    const uint8_t* raw = S.owned_raw + (size_t)b * P.ocap;
+    const int n_raw = SC(S_N_OWNED_RAW);
+    for (int k = 0; k < n_raw; ++k) {
+      const int n = raw[k];
+      if (!M.get(M_STOPPED, n) && !M.get(M_IMAGING, n)) any_running_owned = true;
+      if (n != starter && M.get(M_PRIV_ROOT, n)) ++roots_in_list;        // duplicates count twice (:471-475)
+      if (n == interest) interest_in_list = true;
+    }
+  }
   for (int w = 0; w < P.words; ++w) {     // one pass over the mask words: goal popcounts and the lost test
     const uint32_t own = M.word(M_OWNED, w), disc = M.word(M_DISCOVERED, w), stop = M.word(M_STOPPED, w);
     const uint32_t not_starter = ((starter >> 5) == w) ? ~(1u << (starter & 31)) : 0xFFFFFFFFu;
@@ -207,12 +351,14 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
       n_data += __popc(disc & M.word(M_HAS_DATA, w));
       n_pending += __popc(disc & M.word(M_COLLECTED, w) & ~M.word(M_EXFILTRATED, w));
     }
-    any_running_owned |= (own & ~stop) != 0u;
+    if (!DEF) any_running_owned |= (own & ~stop) != 0u;
   }
+  if (DEF && P.goal == GOAL_CONTROL) n_goal = roots_in_list;
   bool goal_ok;
   if (P.goal == GOAL_CONTROL) goal_ok = (n_goal == SC(S_OWNABLE));
   else if (P.goal == GOAL_DISRUPTION) goal_ok = (n_goal == SC(S_DISRUPTABLE));
   else if (P.goal == GOAL_DISCOVERY) goal_ok = (n_goal == SC(S_DISCOVERABLE) && n_data == 0 && n_pending == 0);
+  else if (DEF && P.goal == GOAL_CONTROL_NODE) goal_ok = interest_in_list && M.get(M_PRIV_ROOT, interest);
   else goal_ok = goal_reached(S, P, b, interest);     // *_node goals: a few bit tests on the interest node
   // check_end_game (:438-454): killing the interest node loses control_node / discovery_node games
   const bool lost = ((P.goal == GOAL_CONTROL_NODE || P.goal == GOAL_DISCOVERY_NODE) && M.get(M_STOPPED, interest)) ||
@@ -233,7 +379,8 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   }
   if (P.absolute_reward) reward = reward > 0.0 ? reward : 0.0;   // :379
   const bool add_edge = reward > 0.0;                            // compressed:483 (before the distance penalty)
-  const bool reencode = (kind == K_LATERAL || kind == K_DOS || kind == K_RECON);   // compressed:401,462 (desired outcome)
+  // compressed:401,462: the DESIRED outcome decides; with a defender or precise_graph_encoding every step re-encodes
+  const bool reencode = P.always_encode || (kind == K_LATERAL || kind == K_DOS || kind == K_RECON);
   reward += P.pen[P_DISTANCE] * dist;                            // compressed:430
   SC(S_NUM_ITER) = num_iter + 1;                                 // :394
   SC(S_OUTCOME) = code;
@@ -241,7 +388,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   // A re-encode of an unchanged graph reproduces the cached embeddings bit for bit, so it is skipped: `dirty`
   // records whether any node feature, edge or node set changed since the last encode (successful outcomes mutate
   // the target or the discovered set; reward > 0 adds / updates an edge).
-  const bool dirty = (flags & FL_DIRTY) || code < 16 || add_edge;
+  const bool dirty = (flags & FL_DIRTY) || code < 16 || add_edge || def_event;
   const int sticky = flags & FL_INTEREST_IN_GRAPH;          // survives until the episode's reset
   const bool encode_now = reencode && dirty;
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |

@@ -13,7 +13,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("CBS_LIB", "libcbsim.so"))
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 i32, i64, u64, f32, f64 = ct.c_int32, ct.c_int64, ct.c_uint64, ct.c_float, ct.c_double
 P = ct.c_void_p
@@ -25,12 +25,14 @@ class CbsConfig(ct.Structure):
                 ("winning_reward", f64), ("losing_reward", f64), ("absolute_reward", i32), ("stop_at_goal_reached", i32),
                 ("remove_main_obstacles", i32), ("remove_all_obstacles", i32), ("switch_interval", i32), ("auto_reset", i32),
                 ("rewards", f64 * 10), ("penalties", f64 * 18), ("max_slots", i32), ("max_edges", i32),
-                ("decode_margin", f32), ("decode_gemm", i32)]
+                ("decode_margin", f32), ("decode_gemm", i32),
+                ("static_defender", i32), ("scan_capacity", i32), ("scan_frequency", i32), ("precise_graph_encoding", i32),
+                ("detect_probability", f64)]
 
 
 _SCENARIO_PTRS = ["sc_num_nodes", "sc_node_off", "sc_port_off", "sc_uvuln_off", "sc_num_uvuln", "sc_instof_off",
                   "sc_discoverable_amount", "sc_init_has_data", "sc_init_visible", "sc_feasible_off", "feasible_starters"]
-_SCENARIO_PTRS2 = ["nd_value", "nd_level_at_access", "nd_ownable", "nd_discoverable", "nd_disruptable", "nd_row_off",
+_SCENARIO_PTRS2 = ["nd_value", "nd_level_at_access", "nd_reimageable", "nd_ownable", "nd_discoverable", "nd_disruptable", "nd_row_off",
                    "outblock", "uvuln_global", "inst_of", "vi_port", "vi_flags", "vi_kinds_any", "vi_kinds_remote",
                    "vi_success", "vi_cost", "vi_recon_any", "vi_recon_remote", "vi_ulocal", "recon_nodes", "row_packed",
                    "row_inst", "vemb32", "vemb64", "vnorm2"]
@@ -52,18 +54,18 @@ class CbsGaeTables(ct.Structure):
 
 # every symbol include/cbsim.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
-           "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
+           "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_defender_draws", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
            "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_read_state", "cbs_state_ptr", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
 
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
-    F_DIST, F_REWARD64, F_ERRFLAG, F_VT = range(13)
-NUM_SCALARS, NUM_ACCUM = 20, 20
+    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST = range(16)
+NUM_SCALARS, NUM_ACCUM = 22, 20
 # scalar planes (csrc/cbs_types.h enum Scalar)
 (S_SCENARIO, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE, S_DISCOVERABLE,
  S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES, S_FLAGS, S_OUTCOME,
- S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF) = range(20)
+ S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF, S_N_OWNED_RAW, S_N_REIMAGED) = range(22)
 ACCUM_NAMES = ["episodes", "return_sum", "length_sum", "wins", "lost", "cutoff"] + [f"stat{i}" for i in range(14)]
 
 
@@ -105,6 +107,7 @@ def load_library():
     lib.cbs_set_scenarios.argtypes = [H, P]
     lib.cbs_set_starter_queue.argtypes = [H, P, i32]
     lib.cbs_set_cutoffs.argtypes = [H, i32, f64]
+    lib.cbs_set_defender_draws.argtypes = [H, P, P]
     lib.cbs_set_action_stride.argtypes = [H, i32]
     lib.cbs_reset.argtypes = [H, P, P, P]
     lib.cbs_decode.argtypes = [H, P, P, P, P]
@@ -167,7 +170,7 @@ def make_scenario_struct(tables, goal: int):
     t.feasible_starters = arr(tables.feasible_starters[goal], np.int32)
     t.num_feasible = len(tables.feasible_starters[goal])
     t.sc_interest = arr(tables.sc_interest, np.int32) if goal >= C.GOAL_CONTROL_NODE else None
-    for name, dt in (("nd_value", np.int32), ("nd_level_at_access", np.uint8), ("nd_ownable", np.int32),
+    for name, dt in (("nd_value", np.int32), ("nd_level_at_access", np.uint8), ("nd_reimageable", np.uint8), ("nd_ownable", np.int32),
                      ("nd_discoverable", np.int32), ("nd_disruptable", np.int32), ("nd_row_off", np.int32),
                      ("outblock", np.uint32), ("uvuln_global", np.int32), ("inst_of", np.int32), ("vi_port", np.int32),
                      ("vi_flags", np.uint32), ("vi_kinds_any", np.uint16), ("vi_kinds_remote", np.uint16),
@@ -207,4 +210,8 @@ def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0,
     for i, v in enumerate(cfg.penalty_vector()):
         c.penalties[i] = v
     c.max_slots, c.max_edges, c.decode_margin, c.decode_gemm = max_slots, max_edges, decode_margin, decode_gemm
+    c.static_defender = {None: 0, "reimage": 1}[getattr(cfg, "static_defender_agent", None)]
+    c.scan_capacity, c.scan_frequency = int(cfg.scan_capacity), int(cfg.scan_frequency)
+    c.detect_probability = float(cfg.detect_probability)
+    c.precise_graph_encoding = int(bool(cfg.precise_graph_encoding))
     return c

@@ -418,6 +418,7 @@ class ScenarioTables:
     # per node (global node index)
     nd_value: np.ndarray           # i32
     nd_level_at_access: np.ndarray  # u8
+    nd_reimageable: np.ndarray     # u8    NodeInfo.reimageable (model.py:312), read by the static defender
     nd_ownable: np.ndarray         # i32   reach counts with this node as starter
     nd_discoverable: np.ndarray    # i32
     nd_disruptable: np.ndarray     # i32
@@ -496,7 +497,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
     sc_da, sc_hd, sc_vis = [], [], []
     feas = [[] for _ in range(6)]
     feas_off = [[0] for _ in range(6)]
-    nd_value, nd_laa, nd_own, nd_disc, nd_disr = [], [], [], [], []
+    nd_value, nd_laa, nd_own, nd_disc, nd_disr, nd_reim = [], [], [], [], [], []
     nd_row_off = [0]
     outblock = []
     uvuln_global, inst_of = [], []
@@ -559,6 +560,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
                 da += 1
             nd_value.append(nd.value)
             nd_laa.append(nd.level_at_access)
+            nd_reim.append(1 if nd.reimageable else 0)
             running_ports = [s.port for s in nd.services if s.running]
             local_rows, remote_rows = [], []
             for v in nd.vulns:
@@ -653,6 +655,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
         feasible_starters=[np.array(f, np.int32) for f in feas],
         sc_interest=np.array([-1] * S if interest_nodes is None else [int(x) for x in interest_nodes], np.int32),
         nd_value=np.array(nd_value, np.int32), nd_level_at_access=np.array(nd_laa, np.uint8),
+        nd_reimageable=np.array(nd_reim, np.uint8),
         nd_ownable=np.array(nd_own, np.int32), nd_discoverable=np.array(nd_disc, np.int32),
         nd_disruptable=np.array(nd_disr, np.int32), nd_row_off=np.array(nd_row_off, np.int32),
         outblock=np.concatenate(outblock, axis=0),

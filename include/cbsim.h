@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CBS_ABI_VERSION 2
+#define CBS_ABI_VERSION 3
 
 /* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
  * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
@@ -75,6 +75,15 @@ typedef struct {
   int32_t max_edges;            /* visible-graph edges per env; 0 = derive from the cut-offs */
   float decode_margin;          /* cosine-score margin inside which candidates are re-scored in float64; 0 = default */
   int32_t decode_gemm;          /* 0 = default (tcgen05 TF32 when built in), 1 = force the SIMT fp32 path */
+  /* static defender (cyberbattle_env.py:52,331-332,416-430): 0 none, 1 ScanAndReimageCompromisedMachines
+   * (_env/static_defender.py:27-60: every scan_frequency steps scan_capacity nodes are drawn with replacement; an owned,
+   * Running node without defense evasion is detected with detect_probability and, if re-imageable, goes to Imaging for
+   * 15 steps, static_defender_actions.py:19,37-68).  Needs cbs_scenario_tables.nd_reimageable. */
+  int32_t static_defender;
+  int32_t scan_capacity;        /* 1..8 */
+  int32_t scan_frequency;       /* >= 1 */
+  int32_t precise_graph_encoding; /* compressed:455-462: re-encode the visible graph on every step */
+  double detect_probability;
 } cbs_config;
 
 /* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the
@@ -99,6 +108,7 @@ typedef struct {
   const int32_t* sc_interest;            /* [S] interest node of each scenario (cyberbattle_env.py:127-131), NULL for the network-wide goals */
   const int32_t* nd_value;               /* [Nn] */
   const uint8_t* nd_level_at_access;     /* [Nn] */
+  const uint8_t* nd_reimageable;         /* [Nn] NodeInfo.reimageable (model.py:312); only read with a static defender */
   const int32_t* nd_ownable;             /* [Nn] */
   const int32_t* nd_discoverable;        /* [Nn] */
   const int32_t* nd_disruptable;         /* [Nn] */
@@ -156,6 +166,11 @@ int cbs_set_starter_queue(cbs_handle* h, const int32_t* queue_host, int32_t qlen
  * that is a multiple of 4 floats the tensor-core contraction reads the tensor in place through TMA; a dense tensor
  * is repacked first (TMA cannot address 3620-byte rows). */
 int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats);
+/* Test hook for the static defender's randomness: scan_nodes_dev [num_envs][scan_capacity] int32 replaces the
+ * random.choices draw of _env/static_defender.py:48, detect_uniforms_dev [num_envs][scan_capacity] float32 replaces the
+ * numpy.random.random() calls of :53 (consumed in call order, as the reference consumes its stream).  The pointers are
+ * read by every following step until cleared with NULLs (then Philox streams 3.. and 5.. are used). */
+int cbs_set_defender_draws(cbs_handle* h, const int32_t* scan_nodes_dev, const float* detect_uniforms_dev);
 /* replaces set_cut_off / set_proportional_cutoff_coefficient (cyberbattle_env_switch.py:198-203) */
 int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double proportional_cutoff_coefficient);
 
@@ -208,9 +223,9 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
 
 /* ---- introspection (parity tests, statistics) ----------------------------------------------------- */
 typedef enum {
-  CBS_F_MASKS = 0,        /* uint32 [11][words][B] */
+  CBS_F_MASKS = 0,        /* uint32 [CBS_NUM_MASKS][words][B] */
   CBS_F_DISC_ORDER = 1,   /* uint8 [B][max_nodes] */
-  CBS_F_OWNED_ORDER = 2,  /* uint8 [B][max_nodes] */
+  CBS_F_OWNED_ORDER = 2,  /* uint8 [B][max_nodes] every node that entered env.owned_nodes, in first-entry order */
   CBS_F_SCALARS = 3,      /* int32 [CBS_NUM_SCALARS][B] */
   CBS_F_TERMINAL_OBS = 4, /* float32 [B][194] */
   CBS_F_OBS = 5,          /* float32 [B][194] cached observation */
@@ -220,9 +235,13 @@ typedef enum {
   CBS_F_DIST = 9,         /* float64 [B] last decode distance */
   CBS_F_REWARD64 = 10,    /* float64 [B] last step reward */
   CBS_F_ERRFLAG = 11,     /* int32 [1] device-side capacity error flag */
-  CBS_F_VT = 12           /* float32 [B][vt_stride] action x vulnerability-embedding products of the last decode */
+  CBS_F_VT = 12,          /* float32 [B][vt_stride] action x vulnerability-embedding products of the last decode */
+  CBS_F_OWNED_RAW = 13,   /* uint8 [B][2*max_nodes] env.owned_nodes as the reference holds it under a defender (removals, duplicates) */
+  CBS_F_REIMAGE_LEFT = 14,/* uint8 [B][max_nodes] node_reimaging_progress of nodes whose Imaging bit is set */
+  CBS_F_Z_HIST = 15       /* float32 [B][slots][max_nodes][64] node-embedding snapshots the action-table rows refer to (cbs_capacities: slots) */
 } cbs_field;
-#define CBS_NUM_SCALARS 20
+#define CBS_NUM_MASKS 15
+#define CBS_NUM_SCALARS 22
 #define CBS_NUM_ACCUM 20
 /* synchronous device->host copy of one state field; bytes must equal the field size (query with dst NULL). */
 int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes);

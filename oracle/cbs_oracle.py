@@ -110,6 +110,9 @@ class OracleEnv:
         self.pen.setdefault("node_already_stopped", self.pen.get("machine_already_stopped", -10))
         self.goal = cfg.goal
         self.episode_iterations = cfg.episode_iterations
+        # ScanAndReimageCompromisedMachines (_env/static_defender.py:27-60); None -> no defender
+        self.defender = getattr(cfg, "static_defender_agent", None) == "reimage"
+        self.always_encode = self.defender or bool(getattr(cfg, "precise_graph_encoding", False))   # compressed:401,455-462
         self.proportional_cutoff_coefficient = cfg.proportional_cutoff_coefficient
         # create_vulnerabilities_embeddings (compressed:614-618)
         self.vuln_emb = {k: np.asarray(v, dtype=np.float64) for k, v in spec.vuln_emb.items()}
@@ -234,6 +237,9 @@ class OracleEnv:
         self.owned_nodes = [self.starter]                            # :179
         # AttackerAgentActions.__init__ (attacker_actions.py:50-53): starter owned at level_at_access
         self._discovered = {}                                        # node -> last_owned (bool) tracking
+        self._stale = set()                                          # nodes re-imaged after they were last owned
+        self.reimaging = {}                                          # StaticDefenderAgentActions.node_reimaging_progress (:23)
+        self.overall_reimaged, self.num_events = [], 0               # cyberbattle_env.py:160-161
         self._mark_owned(self.starter, self.nodes[self.starter].spec.level_at_access)
         # compressed:167-188
         self.processed_pairs = set()
@@ -260,7 +266,9 @@ class OracleEnv:
         node.agent_installed = True
         node.privilege_level = max(int(node.privilege_level), int(level))    # model.py:340
         self._discovered[n] = True
-        return was, was     # no defender: last_reimaging is None, so "currently owned" == "ever owned"
+        cur = was and n not in self._stale                                   # attacker_actions.py:561-573
+        self._stale.discard(n)                                               # last_owned_at = now (:87)
+        return was, cur
 
     def _value(self, n):
         return self.node_value.get(n, self.nodes[n].spec.value)
@@ -385,7 +393,45 @@ class OracleEnv:
         return total, k, recon
 
     # ---- episode logic (cyberbattle_env.py) ------------------------------------------------
-    def step_attacker_env(self, s, t, vid, kind, u):
+    def static_defender_step(self, draws):
+        """cyberbattle_env.py:416-430 static_defender_step with ScanAndReimageCompromisedMachines.  ``draws`` =
+        (node indices for random.choices, uniforms for numpy.random.random() in CALL order)."""
+        # StaticDefenderAgentActions.on_attacker_step_taken (static_defender_actions.py:54-68)
+        for n in list(self.reimaging):
+            if self.reimaging[n] > 0:
+                self.reimaging[n] -= 1
+            else:
+                nd = self.nodes[n]
+                nd.status = C.ST_RUNNING
+                if nd.persistence:
+                    nd.agent_installed = True
+                del self.reimaging[n]
+        # ScanAndReimageCompromisedMachines.step (static_defender.py:45-60)
+        changed = []
+        if self.stepcount % int(self.cfg.scan_frequency) == 0:
+            scan_nodes, scan_uniforms = draws
+            ui = 0
+            for n in list(scan_nodes)[: int(self.cfg.scan_capacity)]:
+                nd = self.nodes[int(n)]
+                if nd.status == C.ST_RUNNING and nd.agent_installed and not nd.defense_evasion:
+                    u = float(scan_uniforms[ui])
+                    ui += 1
+                    if u <= self.cfg.detect_probability and nd.spec.reimageable:
+                        self.reimaging[int(n)] = C.REIMAGING_DURATION             # reimage_node (:37-52)
+                        nd.agent_installed = False
+                        nd.status = C.ST_IMAGING
+                        self._stale.add(int(n))                                  # last_reimaging = now
+                        changed.append(int(n))
+        self.num_events += len(changed)                                           # :419
+        self.overall_reimaged.extend(changed)                                     # :422
+        for n in changed:
+            self.owned_nodes.remove(n)                                            # :425 (first occurrence)
+        for n in range(self.N):                                                   # :427-430 persistence re-owns a re-imaged node
+            nd = self.nodes[n]
+            if nd.agent_installed and nd.status == C.ST_RUNNING and n not in self.owned_nodes:
+                self.owned_nodes.append(n)
+
+    def step_attacker_env(self, s, t, vid, kind, u, defender_draws=None):
         """cyberbattle_env.py:299-394 step_attacker_env."""
         if self.done:
             raise RuntimeError("New episode must be started with env.reset()")            # :300-302
@@ -412,6 +458,8 @@ class OracleEnv:
             self.discovered_amount += 1
         if self.node_goal and self.interest in self.discovered_nodes and t != self.interest:
             self.reward = 0                                                                # :322-326
+        if self.defender:
+            self.static_defender_step(defender_draws)                                      # :331-332
         # end checks (:338-370)
         self.end_episode_reason = 0
         self.truncated = False
@@ -477,7 +525,8 @@ class OracleEnv:
         self.network_availability = running / len(self.discovered_nodes)
         return (owned, len(self.discovered_nodes), self.N - len(self.discovered_nodes), disrupted, self.N,
                 self.ownable_count, self.discoverable_count, self.disruptable_count, self.network_availability,
-                0, 0, self.discovered_amount, self.discoverable_amount, self.attacker_goal_reached())
+                len(self.overall_reimaged), self.num_events, self.discovered_amount, self.discoverable_amount,
+                self.attacker_goal_reached())
 
     # ---- evolving visible graph + observation (cyberbattle_env_compressed.py) -----------------
     def node_feature_vector(self, n):
@@ -619,7 +668,7 @@ class OracleEnv:
         s, t, vid, kind, vtype, ri = self.action_keys[i]
         return s, t, vid, kind, d[i], i
 
-    def step(self, action_vector, uniform, forced=None):
+    def step(self, action_vector, uniform, forced=None, defender_draws=None):
         """compressed:389-451.  ``forced`` = (s, t, vid, kind, distance) overrides the decode (used by the
         GPU parity tests to follow a verified near-tie)."""
         if forced is None:
@@ -628,7 +677,7 @@ class OracleEnv:
             s, t, vid, kind, dist = forced
             row = -1
         self.last_row = row
-        self.step_attacker_env(s, t, vid, kind, float(uniform))
+        self.step_attacker_env(s, t, vid, kind, float(uniform), defender_draws)
         # update_evolving_visible_graph_after_step (:465-484)
         for n in self.discovered_nodes:
             if n not in self.node_x:
@@ -638,7 +687,7 @@ class OracleEnv:
         self.edge_added = self.reward > 0
         if self.edge_added:
             self._add_edge(s, t, vid)
-        self.reencoded = kind in _REENCODE_KINDS                                           # :401 (desired outcome)
+        self.reencoded = kind in _REENCODE_KINDS or self.always_encode                     # :401 (desired outcome / defender)
         if self.reencoded:
             self.node_embeddings, emb = self.encode()
             self.n_encodes += 1
@@ -678,4 +727,13 @@ class OracleEnv:
                 m[C.M_PRIV_USER] |= b
             if nd.privilege_level == C.PRIV_ROOT:
                 m[C.M_PRIV_ROOT] |= b
+            if nd.status == C.ST_IMAGING:
+                m[C.M_IMAGING] |= b
+            if j in self.node_x and int(self.node_x[j][C.F_STATUS]) == C.ST_IMAGING:
+                m[C.M_X_IMAGING] |= b
+            if self.defender:        # tracking planes the device only maintains under a defender
+                if self._discovered.get(j):
+                    m[C.M_EVER_OWNED] |= b
+                if j in self._stale:
+                    m[C.M_OWN_STALE] |= b
         return m

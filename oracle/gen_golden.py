@@ -67,6 +67,23 @@ CASES = {
                                        stop_at_goal_reached=False)),
     "p24_control_big": dict(graph_seed=18, nodes=24, steps=700, policy=0.02,
                             cfg=dict(goal="control", proportional_cutoff_coefficient=5, episode_iterations=200)),
+    # re-imaging static defender (_env/static_defender.py:27-60): scan draws and detection uniforms are pre-drawn inputs.
+    # Random attacker + aggressive defender: the starter is evicted -> owned list empties -> lost.
+    "d12_reimage_random": dict(graph_seed=41, nodes=12, steps=600,
+                               cfg=dict(goal="control", static_defender_agent="reimage", detect_probability=0.3, scan_capacity=3,
+                                        scan_frequency=2, proportional_cutoff_coefficient=4)),
+    # scripted attacker that also makes nodes persistent: re-imaged nodes come back owned (env:427-430), get re-owned by
+    # lateral moves (duplicates in owned_nodes), stale feature vectors in the visible graph, long episodes
+    "d8_reimage_policy": dict(graph_seed=53, nodes=8, steps=900, policy=0.02, p_persist=0.25,
+                              cfg=dict(goal="control", static_defender_agent="reimage", detect_probability=0.25, scan_capacity=3,
+                                       scan_frequency=3, proportional_cutoff_coefficient=25, episode_iterations=400)),
+    "d6_reimage_discovery": dict(graph_seed=30, nodes=6, steps=700, policy=0.02, p_persist=0.3,
+                                 cfg=dict(goal="discovery", static_defender_agent="reimage", detect_probability=0.6, scan_capacity=4,
+                                          scan_frequency=5, proportional_cutoff_coefficient=30, episode_iterations=300,
+                                          stop_at_goal_reached=False)),
+    # precise_graph_encoding: every step re-encodes (compressed:455-462)
+    "g12_precise": dict(graph_seed=12, nodes=12, steps=500, cfg=dict(goal="control", precise_graph_encoding=True,
+                                                                      proportional_cutoff_coefficient=3)),
 }
 POOL_SEED = 1234
 GAE_SEED = 0
@@ -94,6 +111,12 @@ def make_case_inputs(p):
     return actions, uniforms
 
 
+def make_case_defender_draws(p, cfg):
+    if cfg.static_defender_agent is None:
+        return None
+    return tr.make_defender_draws(p["graph_seed"] * 1000 + 5, p["steps"], p["nodes"], int(cfg.scan_capacity))
+
+
 def generate(name):
     from oracle import ref_bridge as rb
     t0 = time.time()
@@ -107,7 +130,8 @@ def generate(name):
     starters = tr.make_starters(p["graph_seed"] * 1000 + 2, feasible, p["steps"] + 2)
     runner = rb.ReferenceRunner(model, weights, cfg, interest_node=interest)
     rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters,
-                    policy_seed=(p["graph_seed"] * 1000 + 3) if "policy" in p else None)
+                    policy_seed=(p["graph_seed"] * 1000 + 3) if "policy" in p else None,
+                    defender_draws=make_case_defender_draws(p, cfg), p_persist=p.get("p_persist", 0.0))
     meta = dict(name=name, params={k: v for k, v in p.items() if k != "cfg"}, cfg=p["cfg"], pool_seed=POOL_SEED,
                 gae_seed=GAE_SEED, input_seed=p["graph_seed"] * 1000 + 1, starter_seed=p["graph_seed"] * 1000 + 2,
                 spec=spec_to_dict(spec),
@@ -127,7 +151,8 @@ def generate(name):
     eps = int(rec["num_episodes"])
     print(f"{name}: {p['steps']} steps, {eps} episodes, {os.path.getsize(path) / 1e6:.2f} MB, {time.time() - t0:.1f}s; "
           f"success codes seen: {sorted(set(rec['code'].tolist()))}; end reasons: {np.bincount(rec['reason'], minlength=4).tolist()}; "
-          f"max owned {int((rec['owned_order'] >= 0).sum(1).max())}, max discovered {int((rec['disc_order'] >= 0).sum(1).max())}")
+          f"max owned {int((rec['owned_order'] >= 0).sum(1).max())}, max discovered {int((rec['disc_order'] >= 0).sum(1).max())}; "
+          f"re-imaged per episode {rec['stats'][:, 9].tolist() if len(rec['stats']) else []}")
 
 
 def load_case(path):
@@ -150,7 +175,8 @@ def load_case(path):
     rec["obs"] = z["obs_rows"][z["obs_idx"]]
     return dict(meta=meta, spec=spec, cfg=cfg, weights=weights, actions=actions, uniforms=uniforms,
                 starters=z["starters"], trace=rec, policy_seed=0 if "policy" in p else None,
-                policy_rows=rec.get("policy_rows"), interest=p.get("interest"))
+                policy_rows=rec.get("policy_rows"), interest=p.get("interest"),
+                defender_draws=make_case_defender_draws(p, cfg))
 
 
 if __name__ == "__main__":

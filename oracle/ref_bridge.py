@@ -81,8 +81,27 @@ class _FakeRandom:
         # cyberbattle_env.py:129 switch_interest_node: random.choice(list(nodes)) -> the configured interest node
         return self.next_choice if self.next_choice in seq else seq[0]
 
+    def choices(self, population, k=1):
+        # static_defender.py:48 random.choices(list(nodes), k=scan_capacity) -> the pre-drawn node indices
+        self.scan_pos = 0
+        return [population[int(i)] for i in list(self.next_scan_nodes)[:k]]
+
     def __getattr__(self, name):
         return getattr(_py_random, name)
+
+
+def _fake_numpy_random(fake):
+    class _R:
+        @staticmethod
+        def random():
+            u = float(fake.next_scan_uniforms[fake.scan_pos])
+            fake.scan_pos += 1
+            return u
+    class _N:
+        random = _R()
+        def __getattr__(self, name):
+            return getattr(np, name)
+    return _N()
 
 
 class ReferenceRunner:
@@ -109,6 +128,12 @@ class ReferenceRunner:
             self.fake.next_choice = ids0[int(interest_node)]
             self.fake.next_starter = (int(interest_node) + 1) % len(ids0)   # constructor's reset_env: any starter != interest that passes
         kw = cfg.reference_kwargs()
+        if getattr(cfg, "static_defender_agent", None) == "reimage":
+            import cyberbattle._env.static_defender as sd
+            sd.random = self.fake
+            sd.numpy = _fake_numpy_random(self.fake)
+            kw["static_defender_agent"] = sd.ScanAndReimageCompromisedMachines(
+                cfg.detect_probability, int(cfg.scan_capacity), int(cfg.scan_frequency), logger=logger, verbose=0)
         env = ref["compressed"].CyberBattleCompressedEnv(initial_environment=model, logger=logger, verbose=0, **kw)
         env.set_graph_encoder(enc)
         env.set_pca_components(768)
@@ -126,8 +151,11 @@ class ReferenceRunner:
         obs, _ = self.wrapper.reset()
         return obs
 
-    def step(self, action, uniform):
+    def step(self, action, uniform, defender_draws=None):
         self.fake.next_uniform = float(uniform)
+        if defender_draws is not None:
+            self.fake.next_scan_nodes, self.fake.next_scan_uniforms = defender_draws
+            self.fake.scan_pos = 0
         self.fake.uniform_consumed = False
         obs, reward, done, truncated, info = self.wrapper.step(action)
         return obs, reward, done, truncated, info
@@ -162,6 +190,17 @@ class ReferenceRunner:
                 m[C.M_PRIV_USER] |= b
             if int(nd.privilege_level) == C.PRIV_ROOT:
                 m[C.M_PRIV_ROOT] |= b
+            if nd.status.value == C.ST_IMAGING:
+                m[C.M_IMAGING] |= b
+            g = env.evolving_visible_graph
+            if nid in g.nodes and int(g.nodes[nid]["x"][C.F_STATUS]) == C.ST_IMAGING:
+                m[C.M_X_IMAGING] |= b
+            if env.static_defender_agent:
+                track = env._actuator._discovered_nodes.get(nid)
+                if track is not None and track.last_owned_at is not None:
+                    m[C.M_EVER_OWNED] |= b
+                    if nd.last_reimaging is not None and track.last_owned_at < nd.last_reimaging:
+                        m[C.M_OWN_STALE] |= b
         return m
 
     def obtained_code(self):

@@ -22,6 +22,14 @@ def make_inputs(seed: int, steps: int):
     return actions, uniforms
 
 
+def make_defender_draws(seed: int, steps: int, num_nodes: int, capacity: int):
+    """Per step: `capacity` node indices (random.choices, static_defender.py:48) and `capacity` detection uniforms
+    (numpy.random.random, :53; consumed in call order)."""
+    rng = np.random.default_rng(seed)
+    return (rng.integers(num_nodes, size=(steps, capacity)).astype(np.int32),
+            rng.random((steps, capacity), dtype=np.float32))
+
+
 def make_starters(seed: int, feasible, count: int):
     rng = np.random.default_rng(seed)
     feasible = np.asarray(feasible)
@@ -53,8 +61,8 @@ class OracleAdapter:
         o = self.env.reset(starter=int(starter))
         return np.concatenate([o["graph_embeddings"].astype(np.float32), o["discrete_features"].astype(np.float32)])
 
-    def step(self, action, u, forced=None):
-        o, r, d, info = self.env.step(action, u, forced=forced)
+    def step(self, action, u, forced=None, defender_draws=None):
+        o, r, d, info = self.env.step(action, u, forced=forced, defender_draws=defender_draws)
         obs = np.concatenate([o["graph_embeddings"].astype(np.float32), o["discrete_features"].astype(np.float32)])
         e = self.env
         sel = (info["source_node"], info["target_node"], self.vidx[info["vulnerability"]], info["outcome_kind"])
@@ -100,9 +108,9 @@ class ReferenceAdapter:
     def reset(self, starter):
         return self._obs(self.r.reset(starter))
 
-    def step(self, action, u, forced=None):
+    def step(self, action, u, forced=None, defender_draws=None):
         from ccbs_b200.scenario import _KIND_BY_CLASSNAME
-        o, reward, done_or_trunc, truncated, info = self.r.step(action, u)
+        o, reward, done_or_trunc, truncated, info = self.r.step(action, u, defender_draws)
         env = self.r.env
         kind = _KIND_BY_CLASSNAME[type(info["outcome_class"]).__name__]
         sel = (self.r.index[info["source_node"]], self.r.index[info["target_node"]], self.vidx[info["vulnerability"]], kind)
@@ -139,10 +147,14 @@ class ReferenceAdapter:
         return self.r.wrapper.get_statistics()
 
 
-def policy_pick(keys, owned, root, rng, p_greedy=0.85):
+def policy_pick(keys, owned, root, rng, p_greedy=0.85, p_persist=0.0):
     """Scripted attacker used for the 'policy' golden cases: prefer lateral moves onto nodes not yet owned, then
     privilege escalation on owned non-root nodes, then reconnaissance; otherwise (and with prob. 1 - p_greedy) a
     uniformly random table row.  ``keys`` = [(source, target, kind)] in table order.  Returns a row index."""
+    if p_persist and rng.random() < p_persist:      # defender cases: make owned nodes persistent so re-imaging hands them back
+        pers = [i for i, (s, t, k) in enumerate(keys) if k == C.K_PERSISTENCE and t in owned]
+        if pers:
+            return int(pers[rng.integers(len(pers))])
     if rng.random() < p_greedy:
         lateral = [i for i, (s, t, k) in enumerate(keys) if k == C.K_LATERAL and t not in owned]
         privesc = [i for i, (s, t, k) in enumerate(keys) if k == C.K_PRIVESC and t in owned and t not in root]
@@ -153,19 +165,20 @@ def policy_pick(keys, owned, root, rng, p_greedy=0.85):
     return int(rng.integers(len(keys)))
 
 
-def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=None):
+def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=None, defender_draws=None, p_persist=0.0):
     """Step ``adapter`` through the whole action sequence with auto-reset; return a dict of arrays.
 
     Policy mode (``policy_seed`` set): ``actions`` holds small float32 noise only; the action of step t is a row of the
     env's current action table plus that noise.  When ``policy_rows`` is None the row is chosen by :func:`policy_pick`
     (generation, reference side) and recorded; otherwise the recorded rows are replayed (oracle / CUDA side)."""
     T, N = len(actions), adapter.N
+    OW = N if defender_draws is None else 2 * N      # under a defender env.owned_nodes can hold duplicates (env:425-430)
     prng = np.random.default_rng(policy_seed) if policy_seed is not None else None
     chosen_rows = np.zeros(T, np.int32)
     rec = dict(sel=np.zeros((T, 4), np.int32), code=np.zeros(T, np.int32), reward=np.zeros(T, np.float64),
                done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
                dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
-               disc_order=np.full((T, N), -1, np.int16), owned_order=np.full((T, N), -1, np.int16),
+               disc_order=np.full((T, N), -1, np.int16), owned_order=np.full((T, OW), -1, np.int16),
                counters=np.zeros((T, 7), np.int32), obs=None, episode=np.zeros(T, np.int32))
     reset_obs, reset_masks, stats = [], [], []
     ep = 0
@@ -177,11 +190,12 @@ def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=N
         if policy_seed is not None:
             if policy_rows is None:
                 owned, root = adapter.owned_and_root()
-                chosen_rows[t] = policy_pick(adapter.table_keys(), owned, root, prng)
+                chosen_rows[t] = policy_pick(adapter.table_keys(), owned, root, prng, p_persist=p_persist)
             else:
                 chosen_rows[t] = policy_rows[t]
             action = (adapter.table_row(int(chosen_rows[t])) + actions[t].astype(np.float64)).astype(np.float32)
-        obs, r, done, trunc, sel, code, reason, dist = adapter.step(action, uniforms[t])
+        dd = None if defender_draws is None else (defender_draws[0][t], defender_draws[1][t])
+        obs, r, done, trunc, sel, code, reason, dist = adapter.step(action, uniforms[t], defender_draws=dd)
         rec["sel"][t], rec["code"][t], rec["reward"][t] = sel, code, r
         rec["done"][t], rec["truncated"][t], rec["reason"][t], rec["dist"][t] = done, trunc, reason, dist
         rec["masks"][t] = masks_to_array(adapter.masks())
@@ -215,6 +229,14 @@ def compare(a, b, rtol=1e-5, atol=1e-5, label=""):
     """Integer state bit-exact; reward / distance / obs / stats within tolerance.  Returns a report."""
     report = {}
     for k in INT_KEYS:
+        if k in ("masks", "reset_masks") and a[k].shape[-2] != b[k].shape[-2]:
+            # fixtures recorded before the defender planes existed: the extra planes must be empty, the rest equal
+            n = min(a[k].shape[-2], b[k].shape[-2])
+            for x in (a[k], b[k]):
+                if np.any(x[..., n:, :]):
+                    raise AssertionError(f"{label}: '{k}' has defender-plane bits set but the other side does not record them")
+            a, b = dict(a), dict(b)
+            a[k], b[k] = a[k][..., :n, :], b[k][..., :n, :]
         if not np.array_equal(a[k], b[k]):
             bad = np.argwhere(np.asarray(a[k]) != np.asarray(b[k]))
             raise AssertionError(f"{label}: integer field '{k}' differs first at {bad[0].tolist()} "

@@ -46,21 +46,28 @@ class TieFollower:
         self.max_gap = max(self.max_gap, gap)
         return np.array(want, np.int32), d
 
-    def advance(self, action, u):
-        self.env.step(action, u, forced=self._forced)
+    def advance(self, action, u, defender_draws=None):
+        self.env.step(action, u, forced=self._forced, defender_draws=defender_draws)
         if self.env.done or self.env.truncated:
             self.ep += 1
             self.env.reset(starter=int(self.starters[self.ep]))
 
 
-def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_rows=None):
+def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_rows=None, defender_draws=None):
     """Step every env of `env` with the same action/uniform sequence; returns a trace record for env
     `check_env` plus the per-step cross-env consistency flag."""
     B, T = env.num_envs, len(actions)
+    defender = defender_draws is not None
+    OW = 2 * n_nodes if defender else n_nodes   # under a defender the record holds env.owned_nodes itself (duplicates possible)
+    if defender:
+        k = defender_draws[0].shape[1]
+        scan_nodes = torch.zeros((B, k), dtype=torch.int32, device=env.device)
+        scan_u = torch.zeros((B, k), dtype=torch.float32, device=env.device)
+        env.set_defender_draws(scan_nodes, scan_u)
     rec = dict(sel=np.zeros((T, 4), np.int32), code=np.zeros(T, np.int32), reward=np.zeros(T, np.float64),
                done=np.zeros(T, np.uint8), truncated=np.zeros(T, np.uint8), reason=np.zeros(T, np.uint8),
                dist=np.zeros(T, np.float64), masks=np.zeros((T, C.N_MASKS, 2), np.uint64),
-               disc_order=np.full((T, n_nodes), -1, np.int16), owned_order=np.full((T, n_nodes), -1, np.int16),
+               disc_order=np.full((T, n_nodes), -1, np.int16), owned_order=np.full((T, OW), -1, np.int16),
                counters=np.zeros((T, 7), np.int32), obs=np.zeros((T, env.obs_dim), np.float32),
                episode=np.zeros(T, np.int32))
     reset_obs, reset_masks, stats = [], [], []
@@ -85,12 +92,16 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
             if fix is not None:
                 sel = torch.from_numpy(fix[0]).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
                 dist = torch.full((B,), fix[1], dtype=torch.float64, device=env.device)
-            follower.advance(actions[t], uniforms[t])
+            follower.advance(actions[t], uniforms[t],
+                             (defender_draws[0][t], defender_draws[1][t]) if defender else None)
+        if defender:
+            scan_nodes.copy_(torch.from_numpy(np.tile(defender_draws[0][t][None, :], (B, 1))))
+            scan_u.copy_(torch.from_numpy(np.tile(defender_draws[1][t][None, :], (B, 1))))
         reward, done, trunc, outcome = env.transition(sel, dist, u)
         env.sync()
         sel_h, dist_h = sel.cpu().numpy(), dist.cpu().numpy()
         m, sc = env.masks(), env.scalars()
-        do, oo = env.disc_order(), env.owned_order()
+        do, oo = env.disc_order(), (env.owned_raw() if defender else env.owned_order())
         r64 = env.reward64()
         consistent &= bool((sel_h == sel_h[0]).all() and (m == m[:, :, :1]).all())
         flags = int(sc[L.S_FLAGS, b])
@@ -102,7 +113,7 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
         rec["reason"][t] = (flags >> 2) & 3
         rec["dist"][t] = dist_h[b]
         rec["masks"][t] = masks_to_u64(m, b)
-        nd, no = int(sc[L.S_N_DISC, b]), int(sc[L.S_N_OWNED, b])
+        nd, no = int(sc[L.S_N_DISC, b]), int(sc[L.S_N_OWNED_RAW if defender else L.S_N_OWNED, b])
         rec["disc_order"][t, :nd] = do[b, :nd]
         rec["owned_order"][t, :no] = oo[b, :no]
         rec["counters"][t] = [sc[L.S_STEPCOUNT, b], sc[L.S_NUM_ITER, b], sc[L.S_DISC_AMOUNT, b], sc[L.S_OWNABLE, b],

@@ -11,6 +11,7 @@ HDR = open(os.path.join(ROOT, "c-cyberbattlesim_b200", "csrc", "cbs_types.h")).r
 def _enum(name):
     body = re.search(r"enum\s+" + name + r"\s*:\s*int\s*\{(.*?)\};", HDR, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    body = re.sub(r"//[^\n]*", "", body)
     out, nxt = {}, 0
     for item in body.split(","):
         item = item.strip()
@@ -53,7 +54,7 @@ def test_scalars_match_lib():
     s = _enum("Scalar")
     assert s["N_SCALARS"] == L.NUM_SCALARS
     for name in ("S_SCENARIO", "S_STARTER", "S_STEPCOUNT", "S_NUM_ITER", "S_N_DISC", "S_N_OWNED", "S_DISC_AMOUNT",
-                 "S_EPISODES", "S_FLAGS", "S_OUTCOME", "S_N_SLOTS", "S_N_EDGES"):
+                 "S_EPISODES", "S_FLAGS", "S_OUTCOME", "S_N_SLOTS", "S_N_EDGES", "S_N_OWNED_RAW", "S_N_REIMAGED"):
         assert s[name] == getattr(L, name)
     assert _enum("Accum")["N_ACCUM"] == L.NUM_ACCUM == len(L.ACCUM_NAMES)
 

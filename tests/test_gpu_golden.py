@@ -28,7 +28,7 @@ def test_cuda_replays_reference_trace(name, gemm, golden_dir):
     follower = TieFollower(OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"]), case["spec"],
                            case["starters"])
     rec, consistent = replay(env, case["actions"], case["uniforms"], case["spec"].num_nodes, check_env=B - 1,
-                             follower=follower, policy_rows=case["policy_rows"])
+                             follower=follower, policy_rows=case["policy_rows"], defender_draws=case["defender_draws"])
     env.close()
     assert consistent, "envs fed identical inputs diverged"
     report = tr.compare(rec, case["trace"], rtol=1e-5, atol=2e-5, label=f"{name}/gemm{gemm}")

@@ -7,8 +7,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _philox_uniform(seed, env, step, stream):
-    """Host restatement of csrc/philox.cuh (Philox4x32-10, first word, 24-bit uniform)."""
+def _philox_words(seed, env, step, stream):
+    """Host restatement of csrc/philox.cuh (Philox4x32-10): the four output words."""
     M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
     seed, env, step, stream = int(seed), int(env), int(step), int(stream)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
@@ -17,7 +17,19 @@ def _philox_uniform(seed, env, step, stream):
         p0, p1 = M0 * c[0], M1 * c[2]
         c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
         k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
-    return c[0]
+    return c
+
+
+def _philox_uniform(seed, env, step, stream):
+    return _philox_words(seed, env, step, stream)[0]
+
+
+def philox_defender_draws(seed, env, step, n_nodes, capacity):
+    """csrc/transition.cuh defender_step: scan draw j = word j&3 of stream 3 + (j>>2), scaled to [0, N); detection uniform i =
+    word i&3 of stream 5 + (i>>2), 24-bit."""
+    nodes = [(_philox_words(seed, env, step, 3 + (j >> 2))[j & 3] * n_nodes) >> 32 for j in range(capacity)]
+    us = [np.float32((_philox_words(seed, env, step, 5 + (j >> 2))[j & 3] >> 8) * (1.0 / 16777216.0)) for j in range(capacity)]
+    return nodes, us
 
 
 def philox_u01(seed, env, step, stream):
@@ -28,18 +40,24 @@ def philox_pick(seed, env, step, stream, n):
     return (_philox_uniform(seed, env, step, stream) * n) >> 32
 
 
-@pytest.mark.parametrize("goal,sizes,pool_size,B,T", [
-    ("control", (8, 24), 120, 40, 70),
-    ("discovery", (8, 14), 120, 40, 70),
-    ("control", (40, 70), 120, 40, 70),
-    ("disruption", (6, 12), 60, 33, 60),          # odd batch size
-    ("control", (120, 128), 330, 4, 140),         # maximum node count (4 mask words, 255 snapshot slots), Ug > 256: two GEMM N-tiles
-    ("control", (3, 5), 30, 1, 80),               # a single env, tiny scenarios
-    ("control_node", (8, 16), 100, 24, 60),       # node-specific goals: one interest node per scenario, 258-float observation
-    ("discovery_node", (8, 16), 100, 24, 60),
+_DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_capacity=5, scan_frequency=2,
+                 proportional_cutoff_coefficient=4)
+
+
+@pytest.mark.parametrize("goal,sizes,pool_size,B,T,extra", [
+    ("control", (8, 24), 120, 40, 70, {}),
+    ("discovery", (8, 14), 120, 40, 70, {}),
+    ("control", (40, 70), 120, 40, 70, {}),
+    ("disruption", (6, 12), 60, 33, 60, {}),          # odd batch size
+    ("control", (120, 128), 330, 4, 140, {}),         # maximum node count (4 mask words, 255 snapshot slots), Ug > 256: two GEMM N-tiles
+    ("control", (3, 5), 30, 1, 80, {}),               # a single env, tiny scenarios
+    ("control_node", (8, 16), 100, 24, 60, {}),       # node-specific goals: one interest node per scenario, 258-float observation
+    ("discovery_node", (8, 16), 100, 24, 60, {}),
+    ("control", (6, 14), 100, 32, 90, _DEFENDER),     # re-imaging defender on its Philox streams (3.. scan, 5.. detection)
+    ("discovery", (8, 16), 100, 24, 60, dict(precise_graph_encoding=True)),
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
-        "control-node", "discovery-node"])
-def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
+        "control-node", "discovery-node", "defender-philox", "precise-encoding"])
+def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
     from scipy.spatial import distance
     import ccbs_b200 as cb
@@ -55,7 +73,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
     S, seed, offset = (6 if sizes[1] < 100 else 2), 12345, 1000
     gkw = dict(vulns_per_service_range=(6, 14)) if pool_size > 256 else {}
     specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool, **gkw) for k in range(S)]
-    cfg = cb.EnvConfig(goal=goal)
+    cfg = cb.EnvConfig(goal=goal, **extra)
+    defender = cfg.static_defender_agent is not None
     w = GaeWeights.random(3)
     interest = None
     if goal.endswith("node"):      # an interest node that some starter can reach, per scenario
@@ -117,7 +136,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
                 assert dd[i] - d < 1e-6, f"step {t} env {b}: decode {got} (gap {dd[i] - d:.3e}) vs oracle {want}"
                 flips += 1
                 forced = (got[0], got[1], o.action_keys[i][2], got[3], dd[i])
-            ob, r, dn, inf = o.step(actions[t, b], u, forced=forced)
+            dd_ = philox_defender_draws(seed, offset + b, total_steps[b] - 1, o.N, int(cfg.scan_capacity)) if defender else None
+            ob, r, dn, inf = o.step(actions[t, b], u, forced=forced, defender_draws=dd_)
             assert int(info_h[b, 4]) == o.outcome and int(info_h[b, 5]) == o.end_episode_reason
             assert bool(done_h[b]) == bool(dn)
             np.testing.assert_allclose(rew_h[b], r, rtol=1e-5, atol=1e-4)
@@ -137,4 +157,6 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T):
         assert tables.vemb32.shape[0] > 256
     acc = env.stat_accum()
     assert acc["episodes"] == sum(episodes)
+    if defender:
+        assert acc["stat9"] > 0 and acc["lost"] > 0, "the defender never re-imaged a node / never evicted the attacker"
     env.close()

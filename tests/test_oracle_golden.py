@@ -22,13 +22,17 @@ def test_oracle_replays_reference_trace(name, golden_dir):
     case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
     env = OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"])
     rec = tr.record(tr.OracleAdapter(env, case["spec"]), case["actions"], case["uniforms"], case["starters"],
-                    policy_seed=case["policy_seed"], policy_rows=case["policy_rows"])
+                    policy_seed=case["policy_seed"], policy_rows=case["policy_rows"], defender_draws=case["defender_draws"])
     report = tr.compare(rec, case["trace"], rtol=1e-5, atol=1e-6, label=name)
     assert report["obs"] <= 1e-5
     # the fixtures exercise what they claim to
     codes = set(case["trace"]["code"].tolist())
     if name == "g14_removeall":                           # remove_all_obstacles: no DoS row is ever in the table
         assert 0 not in codes and {1, 2, 3, 4, 5, 6, 7, 9} <= codes
+    elif name.startswith("d"):                            # defender cases: nodes get re-imaged, the attacker can be evicted
+        st = case["trace"]["stats"]
+        assert st[:, 9].sum() >= 5 and np.array_equal(st[:, 9], st[:, 10])
+        assert np.any(case["trace"]["masks"][:, 11])      # some node was Imaging at some step
     elif name.startswith("n"):                            # node-goal cases: short episodes, most success kinds
         assert len(codes & {0, 1, 2, 3, 4, 5, 6, 7, 9}) >= 7 and case["trace"]["obs"].shape[1] == 258
     else:
@@ -36,6 +40,9 @@ def test_oracle_replays_reference_trace(name, golden_dir):
     assert int(case["trace"]["num_episodes"]) > (5 if name.startswith("g") else 1)
     if name in ("p6_control_win", "p6_control_nostop"):   # scripted-attacker cases that must actually reach the goal
         assert (case["trace"]["reason"] == 1).sum() > 0
+    if name == "d8_reimage_policy":                       # persistence re-own + lateral move: duplicates in owned_nodes
+        oo = case["trace"]["owned_order"]
+        assert any(len(set(r[r >= 0].tolist())) < int((r >= 0).sum()) for r in oo)
     if name.startswith("p"):
         assert (case["trace"]["owned_order"] >= 0).sum(1).max() >= 5
 

@@ -56,7 +56,14 @@ def test_unsupported_reference_options_are_not_silently_dropped():
     rewards = {"rewards_dict": {"control": cb.config.DEFAULT_REWARDS["control"]},
                "penalties_dict": {"control": cb.config.DEFAULT_PENALTIES["control"]}}
     with pytest.raises(ValueError):
-        cb.EnvConfig.from_reference_dicts({"static_defender_agent": "reimage"}, rewards)
+        cb.EnvConfig.from_reference_dicts({"static_defender_agent": "events"}, rewards)
+    # the re-imaging defender is implemented; its parameters come from the [min, max] ranges of train_config.yaml:39-44
+    cfg = cb.EnvConfig.from_reference_dicts({"static_defender_agent": "reimage", "detect_probability_min": 0.05,
+                                             "detect_probability_max": 0.15, "scan_capacity_min": 3, "scan_capacity_max": 3,
+                                             "scan_frequency_min": 2, "scan_frequency_max": 4}, rewards)
+    assert cfg.static_defender_agent == "reimage" and abs(cfg.detect_probability - 0.1) < 1e-12
+    assert (cfg.scan_capacity, cfg.scan_frequency) == (3, 3)
+    assert cb.EnvConfig.from_reference_dicts({"static_defender_agent": None}, rewards).static_defender_agent is None
     with pytest.raises(ValueError):
         cb.EnvConfig.from_reference_dicts({"distance_metric": "l2"}, rewards)
     with pytest.warns(UserWarning):
