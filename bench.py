@@ -192,6 +192,9 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--decode-gemm", type=int, default=0)
+    ap.add_argument("--defender", action="store_true",
+                    help="side measurement: the same workload with the re-imaging static defender of train_config.yaml:39-44 "
+                         "(not the headline configuration)")
     ap.add_argument("--action-pitch", type=int, default=905,
                     help="row pitch (floats) of the device-resident action batches; 905 = dense like the reference's "
                          "action array, 908 lets TMA read them in place (no repack kernel)")
@@ -242,7 +245,7 @@ def main():
     B = wl["envs_per_gpu"]
     specs = build_specs(wl)
     weights = GaeWeights.random(GAE_SEED)
-    cfg = cb.EnvConfig()
+    cfg = cb.EnvConfig(static_defender_agent="reimage") if args.defender else cb.EnvConfig()
     env = BatchedCyberBattleEnv(specs, weights, cfg, num_envs=B, device=local_rank, seed=7, global_env_offset=rank * B,
                                 auto_reset=True, decode_gemm=args.decode_gemm)
     # action ring: R batches of [B, 905] float32, together larger than the 126 MB L2
@@ -351,7 +354,7 @@ def main():
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bitmasks + f32 GAE + f64 decode re-score", "data": "synthetic",
-            "config": {"workload": wl["name"], "envs_per_gpu": B, "scenarios": wl["scenarios"], "global_vulns": int(Ug),
+            "config": {"workload": wl["name"] + (" + static defender (reimage 0.05/3/3)" if args.defender else ""), "envs_per_gpu": B, "scenarios": wl["scenarios"], "global_vulns": int(Ug),
                        "action_pitch_floats": args.action_pitch,
                        "actions": f"ring of {R} x [{B},905] f32 batches = {R * B * 905 * 4 / 1e6:.0f} MB (> 126 MB L2), no L2 flush",
                        "decode_gemm": "tcgen05-tf32" if env.tensor_core_decode else "simt-f32",
