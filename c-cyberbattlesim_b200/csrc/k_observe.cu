@@ -139,20 +139,34 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   }
   __syncwarp();
 
-  // root term x_i W_root (+ conv bias folded into bn1 shift)
-  for (int i = 0; i < n; ++i) {
-    const int node = order[i];
-    float vis, x[NUM_DYN];
-    node_dyn(W.dynb[i], W.xst[i], vis, x);
-    const float* ns = T.node_static + (size_t)(node_off + node) * 2 * ROW + 17 * NODE_EMB;
-    float a0 = ns[c0] + vis * ns[ROW + c0], a1 = ns[c1] + vis * ns[ROW + c1];
+  // root term x_i W_root (+ conv bias folded into bn1 shift); four nodes per pass so that their table rows are in flight together
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    float r0[4], r1[4];
 #pragma unroll
-    for (int d = 0; d < NUM_DYN; ++d) {
-      a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
-      a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j;
+      r0[j] = r1[j] = 0.f;
+      if (i < n) {
+        const float* ns = T.node_static + ((size_t)(node_off + order[i]) * 2 + (W.dynb[i] & 1)) * ROW + 17 * NODE_EMB;
+        r0[j] = ns[c0];
+        r1[j] = ns[c1];
+      }
     }
-    W.y[i * NODE_EMB + c0] = a0;
-    W.y[i * NODE_EMB + c1] = a1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j;
+      if (i >= n) break;
+      float vis, x[NUM_DYN];
+      node_dyn(W.dynb[i], W.xst[i], vis, x);
+      float a0 = r0[j], a1 = r1[j];
+#pragma unroll
+      for (int d = 0; d < NUM_DYN; ++d) {
+        a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
+        a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
+      }
+      W.y[i * NODE_EMB + c0] = a0;
+      W.y[i * NODE_EMB + c1] = a1;
+    }
   }
   __syncwarp();
 
@@ -167,13 +181,13 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     else if (lane == NN_CH) hl = 1.f;
     float vis, x[NUM_DYN];
     node_dyn(W.dynb[is], W.xst[is], vis, x);
-    const float* ns = T.node_static + (size_t)(node_off + js) * 2 * ROW;
+    const float* ns = T.node_static + ((size_t)(node_off + js) * 2 + (vis != 0.f ? 1 : 0)) * ROW;   // visible / not-visible variant
     float m0 = 0.f, m1 = 0.f;
 #pragma unroll
     for (int k = 0; k < NN_CH + 1; ++k) {
       const float hk = __shfl_sync(0xFFFFFFFFu, hl, k);
-      float t0 = ns[k * NODE_EMB + c0] + vis * ns[ROW + k * NODE_EMB + c0];
-      float t1 = ns[k * NODE_EMB + c1] + vis * ns[ROW + k * NODE_EMB + c1];
+      float t0 = ns[k * NODE_EMB + c0];
+      float t1 = ns[k * NODE_EMB + c1];
 #pragma unroll
       for (int d = 0; d < NUM_DYN; ++d) {
         t0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c0], t0);

@@ -88,7 +88,7 @@ class GaeWeights:
 @dataclass
 class GaeTables:
     """Folded tables (host numpy, float32)."""
-    node_static: np.ndarray   # [Nn, 2, 18, 64]: [.,0]=always part, [.,1]=visible-gated part; rows 0..16 = T (k'=0..15 hidden, 16 = bias slot), row 17 = root term
+    node_static: np.ndarray   # [Nn, 2, 18, 64]: [.,0] = the node while NOT visible, [.,1] = while visible (always part + visible-gated part, added in float32); rows 0..16 = T (k'=0..15 hidden, 16 = bias slot), row 17 = root term
     dyn_proj: np.ndarray      # [6, 18, 64]  same layout for the six dynamic scalar features
     vuln_h: np.ndarray        # [Ug, 16]     W1 @ emb_u (no bias)
     nn0_b: np.ndarray         # [16]
@@ -156,7 +156,9 @@ def fold_gae(tables: ScenarioTables, w: GaeWeights, chunk: int = 64) -> GaeTable
         for j, nd in enumerate(spec.nodes):
             X[2 * j], X[2 * j + 1] = node_feature_static(nd, spec.vuln_emb)
         out = (X @ Pf).reshape(spec.num_nodes, 2, 18, D_H)
-        node_static[g:g + spec.num_nodes] = out.astype(np.float32)
+        out = out.astype(np.float32)
+        out[:, 1] = out[:, 0] + out[:, 1]       # the kernel picks one of the two variants by the node's `visible` bit
+        node_static[g:g + spec.num_nodes] = out
         g += spec.num_nodes
     dyn = np.stack([P[f] for f in C.DYN_FEATURES]).astype(np.float32)
     vuln_h = (tables.vemb64.astype(np.float32).astype(np.float64) @ w.nn0_w.astype(np.float64).T).astype(np.float32)

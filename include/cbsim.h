@@ -136,7 +136,7 @@ typedef struct {
 /* Folded graph-encoder tables (ccbs_b200.gae.fold_gae) for gae/model.py:25-82 GAEEncoder.forward with the
  * default layer config, eval mode. */
 typedef struct {
-  const float* node_static; /* [Nn][2][18][64] */
+  const float* node_static; /* [Nn][2][18][64]: the node's folded rows while not visible / while visible */
   const float* dyn_proj;    /* [6][18][64] */
   const float* vuln_h;      /* [Ug][16] */
   const float* nn0_b;       /* [16] */

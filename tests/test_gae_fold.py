@@ -16,7 +16,7 @@ def folded_forward(ft, node_rows, dyn, edges, edge_m):
     T = np.zeros((n, 18, 64), np.float32)
     for i, g in enumerate(node_rows):
         vis, x = dyn[i][0], dyn[i][1:]
-        T[i] = ft.node_static[g, 0] + vis * ft.node_static[g, 1] + np.tensordot(x, ft.dyn_proj, axes=1)
+        T[i] = ft.node_static[g, int(vis)] + np.tensordot(x, ft.dyn_proj, axes=1)
         y[i] = T[i, 17]
     deg = np.ones(n, np.float32)
     for (s, d), m in zip(edges, edge_m):
