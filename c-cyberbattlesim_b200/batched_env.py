@@ -58,10 +58,11 @@ class BatchedCyberBattleEnv:
             scenario_of_env = np.arange(self.num_envs, dtype=np.int32) % self.tables.num_scenarios
         self.scenario_of_env = np.ascontiguousarray(scenario_of_env, dtype=np.int32)
         self._check(self.lib.cbs_set_scenarios(self._h, self.scenario_of_env.ctypes.data_as(ct.c_void_p)))
-        caps = (ct.c_int32 * 6)()
+        caps = (ct.c_int32 * 8)()
         self.lib.cbs_capacities(self._h, caps)
         self.ncap, self.slots, self.ecap, self.tensor_core_decode = caps[0], caps[1], caps[2], bool(caps[3])
         self.vt_stride = caps[4]
+        self._mask_pitch, self._scalar_pitch = caps[6], caps[7]
         assert caps[5] == self.obs_dim
         B = self.num_envs
         self._act_stride = C.ACTION_DIM
@@ -215,10 +216,13 @@ class BatchedCyberBattleEnv:
 
     def masks(self) -> np.ndarray:
         """uint32[N_MASKS, words, B]"""
-        return self.read(L.F_MASKS, np.uint32, (C.N_MASKS, self.tables.words, self.num_envs))
+        raw = self.read(L.F_MASKS, np.uint32, (self.num_envs, self._mask_pitch))       # env-major records on the device
+        w = self.tables.words
+        return np.ascontiguousarray(raw[:, :C.N_MASKS * w].reshape(self.num_envs, C.N_MASKS, w).transpose(1, 2, 0))
 
     def scalars(self) -> np.ndarray:
-        return self.read(L.F_SCALARS, np.int32, (L.NUM_SCALARS, self.num_envs))
+        raw = self.read(L.F_SCALARS, np.int32, (self.num_envs, self._scalar_pitch))  # env-major records on the device
+        return np.ascontiguousarray(raw[:, :L.NUM_SCALARS].T)
 
     def disc_order(self) -> np.ndarray:
         return self.read(L.F_DISC_ORDER, np.uint8, (self.num_envs, self.ncap))

@@ -22,23 +22,24 @@ __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
-  const int flags = S.scal[(size_t)S_FLAGS * P.B + b];
+  const int32_t* sc = S.scal + (size_t)b * SCAL_PITCH;
+  const int flags = sc[S_FLAGS];
   int32_t* o = info + (size_t)b * CBS_INFO_INTS;
   o[0] = sl.x; o[1] = sl.y; o[2] = sl.z; o[3] = sl.w;
-  o[4] = S.scal[(size_t)S_OUTCOME * P.B + b];
+  o[4] = sc[S_OUTCOME];
   o[5] = (flags >> FL_REASON_SHIFT) & 3;
-  o[6] = S.scal[(size_t)S_STEPCOUNT * P.B + b];
+  o[6] = sc[S_STEPCOUNT];
   o[7] = (flags & FL_TRUNC) ? 1 : 0;
 }
 
 __global__ void init_flags_kernel(int32_t* scal, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) scal[(size_t)S_FLAGS * B + b] = FL_NEEDS_RESET;
+  if (b < B) scal[(size_t)b * SCAL_PITCH + S_FLAGS] = FL_NEEDS_RESET;
 }
 }  // namespace cbs
 
 using namespace cbs;
-namespace cbs { extern long long* g_sel_trace; }
+namespace cbs { extern long long* g_sel_trace; extern long long* g_obs_trace; }
 
 static thread_local std::string g_create_error;
 
@@ -249,7 +250,9 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   const size_t B = P.B;
   h->state_bytes = 0;
 #define AL(field, count) if ((rc = dalloc(h, h->state_allocs, &S.field, (size_t)(count)))) return rc
-  AL(masks, (size_t)N_MASKS * P.words * B); AL(scal, (size_t)N_SCALARS * B);
+  static_assert(N_SCALARS <= SCAL_PITCH, "scalar record does not fit its line");
+  P.mpitch = ((N_MASKS * P.words + 15) / 16) * 16;
+  AL(masks, (size_t)P.mpitch * B); AL(scal, (size_t)SCAL_PITCH * B);
   AL(disc_order, B * P.ncap); AL(owned_order, B * P.ncap); AL(pair_slot, B * P.ncap * P.ncap);
   P.ocap = 2 * P.ncap;
   if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
@@ -278,7 +281,9 @@ int cbs_set_scenarios(cbs_handle* h, const int32_t* sc_host) {
   for (int b = 0; b < h->P.B; ++b)
     if (sc_host[b] < 0 || sc_host[b] >= h->T.num_scenarios) return fail(h, CBS_ERR_INVALID_ARG, "scenario id %d out of range (env %d)", sc_host[b], b);
   CK(h, cudaSetDevice(h->cfg.device));
-  CK(h, cudaMemcpy(h->S.scal + (size_t)S_SCENARIO * h->P.B, sc_host, sizeof(int32_t) * h->P.B, cudaMemcpyHostToDevice));
+  // one int32 per env into the env-major scalar records
+  CK(h, cudaMemcpy2D(h->S.scal + S_SCENARIO, SCAL_PITCH * sizeof(int32_t), sc_host, sizeof(int32_t), sizeof(int32_t), h->P.B,
+                     cudaMemcpyHostToDevice));
   return CBS_OK;
 }
 
@@ -471,13 +476,13 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
   const State& S = h->S;
   const int64_t B = P.B;
   switch (field) {
-    case CBS_F_MASKS: *p = S.masks; *bytes = (int64_t)N_MASKS * P.words * B * 4; break;
+    case CBS_F_MASKS: *p = S.masks; *bytes = (int64_t)P.mpitch * B * 4; break;
     case CBS_F_DISC_ORDER: *p = S.disc_order; *bytes = B * P.ncap; break;
     case CBS_F_OWNED_ORDER: *p = S.owned_order; *bytes = B * P.ncap; break;
     case CBS_F_OWNED_RAW: *p = S.owned_raw; *bytes = P.defender ? B * P.ocap : 1; break;
     case CBS_F_Z_HIST: *p = S.z_hist; *bytes = B * P.slots * P.ncap * NODE_EMB * 4; break;
     case CBS_F_REIMAGE_LEFT: *p = S.reimage_left; *bytes = P.defender ? B * P.ncap : 1; break;
-    case CBS_F_SCALARS: *p = S.scal; *bytes = (int64_t)N_SCALARS * B * 4; break;
+    case CBS_F_SCALARS: *p = S.scal; *bytes = (int64_t)SCAL_PITCH * B * 4; break;
     case CBS_F_TERMINAL_OBS: *p = S.term_obs; *bytes = B * P.obs_dim * 4; break;
     case CBS_F_OBS: *p = S.obs; *bytes = B * P.obs_dim * 4; break;
     case CBS_F_LAST_STATS: *p = S.last_stats; *bytes = B * 14 * 8; break;
@@ -526,6 +531,12 @@ int cbs_debug_select_trace(cbs_handle* h, long long* trace_dev) {
   return CBS_OK;
 }
 
+int cbs_debug_observe_trace(cbs_handle* h, long long* trace_dev) {
+  (void)h;
+  cbs::g_obs_trace = trace_dev;   // [num_envs][4] int64 device buffer, or NULL to switch tracing off
+  return CBS_OK;
+}
+
 int64_t cbs_launch_count(const cbs_handle* h) { return h ? h->launches : 0; }
 
 int cbs_sync(cbs_handle* h) {
@@ -545,11 +556,13 @@ int cbs_struct_sizes(int32_t* out3) {
 }
 
 int64_t cbs_state_bytes(const cbs_handle* h) { return h ? (int64_t)h->state_bytes : 0; }
-int cbs_capacities(const cbs_handle* h, int32_t* out4 /* 6 ints */) {
+int cbs_capacities(const cbs_handle* h, int32_t* out4 /* 8 ints */) {
   if (!h || !out4) return CBS_ERR_INVALID_ARG;
   out4[0] = h->P.ncap; out4[1] = h->P.slots; out4[2] = h->P.ecap; out4[3] = h->use_tc ? 1 : 0;
   out4[4] = h->vt_stride;
   out4[5] = h->P.obs_dim;
+  out4[6] = h->P.mpitch;
+  out4[7] = SCAL_PITCH;
   return CBS_OK;
 }
 

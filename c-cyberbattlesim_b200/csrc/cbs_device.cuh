@@ -5,13 +5,13 @@
 namespace cbs {
 
 __device__ __forceinline__ uint32_t ld_mask(const State& S, const Params& P, int plane, int w, int b) {
-  return S.masks[((size_t)plane * P.words + w) * P.B + b];
+  return S.masks[(size_t)b * P.mpitch + plane * P.words + w];
 }
 __device__ __forceinline__ bool bit_of(const State& S, const Params& P, int plane, int node, int b) {
   return (ld_mask(S, P, plane, node >> 5, b) >> (node & 31)) & 1u;
 }
 __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int plane, int b) {
-  return S.scal[(size_t)plane * P.B + b];
+  return S.scal[(size_t)b * SCAL_PITCH + plane];
 }
 
 __device__ __forceinline__ bool is_node_goal(const Params& P) { return P.goal >= GOAL_CONTROL_NODE; }

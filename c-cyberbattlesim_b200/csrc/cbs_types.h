@@ -17,6 +17,7 @@ constexpr int NN_CH = 16;
 constexpr int PROJ_ROWS = 18;  // 16 hidden + bias slot + root term
 constexpr int NUM_DYN = 6;     // persistence, collected, exfiltrated, evasion, privilege, status
 constexpr int MAX_NODES = 128;
+constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: one 128-byte line per env
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 
 // outcome kinds (simulation/model.py:66-193)
@@ -98,11 +99,14 @@ struct Params {  // configuration, by value
   double detect_prob;
   int always_encode;   // defender or precise_graph_encoding: every step re-encodes (compressed:401,455-462)
   int ocap;            // capacity of owned_raw
+  int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
 };
 
 struct State {  // mutable, device pointers
-  uint32_t* masks;       // [N_MASKS][words][B]
-  int32_t* scal;         // [N_SCALARS][B]
+  // Per-env records, env-major: every kernel on the step path handles an env with one warp (or one lane), so the env's
+  // few dozen words must share cache lines; plane-major SoA put each of them in a different 32-byte sector.
+  uint32_t* masks;       // [B][mpitch]  plane p, word w at p * words + w
+  int32_t* scal;         // [B][SCAL_PITCH]
   uint8_t* disc_order;   // [B][ncap]
   uint8_t* owned_order;  // [B][ncap]
   uint8_t* pair_slot;    // [B][ncap*ncap]   0xFF = pair not in the action table
@@ -140,8 +144,5 @@ struct State {  // mutable, device pointers
   int32_t* bin_list;     // [2][SCHED_BINS][B] env ids per bin
 };
 
-__host__ __device__ inline uint32_t& mask_ref(uint32_t* masks, int plane, int w, int words, int B, int b) {
-  return masks[((size_t)plane * words + w) * B + b];
-}
 
 }  // namespace cbs

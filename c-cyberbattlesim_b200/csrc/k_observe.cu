@@ -30,6 +30,8 @@ struct SharedWeights {
   float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]  (reading it through L1 instead of staging it was measured slower)
   float bn1s[NODE_EMB], bn1h[NODE_EMB], bn2s[NODE_EMB], bn2h[NODE_EMB];
   float nn0b[NN_CH];
+  double accum[N_ACCUM];   // this CTA's share of the episode sums (flushed to State::accum by its last warp)
+  int warps_done;
 };
 
 struct WarpScratch {
@@ -348,38 +350,69 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
 }
 
 // ---- get_statistics (cyberbattle_env.py:517-524) + episode accumulators ----
-__device__ void finish_episode(const Tables& T, const Params& P, const State& S, int b, int lane) {
-  const int sc = scalar(S, P, S_SCENARIO, b);
-  const int N = T.sc_num_nodes[sc];
-  int owned = 0, disrupted = 0, running = 0;
-  for (int w = 0; w < P.words; ++w) {
-    const uint32_t disc = ld_mask(S, P, M_DISCOVERED, w, b), stop = ld_mask(S, P, M_STOPPED, w, b);
-    owned += __popc(ld_mask(S, P, M_OWNED, w, b));
-    disrupted += __popc(disc & stop);
-    running += __popc(disc & ~stop & ~(P.defender ? ld_mask(S, P, M_IMAGING, w, b) : 0u));
+__constant__ int kFinishPlanes[11] = {S_N_DISC, S_FLAGS, S_OWNABLE, S_DISCOVERABLE, S_DISRUPTABLE, S_DISC_AMOUNT,
+                                      S_DISCOVERABLE_AMOUNT, S_STEPCOUNT, S_N_REIMAGED, S_SCENARIO, S_EPISODES};
+// Everything the statistics need is fetched by ONE load per lane (mask words on lanes 0-15, scalars on lanes 16-26, the
+// episode return on lane 31) together with the observation to be kept as terminal observation, then exchanged with
+// shuffles: a serial version of this function (a dozen dependent round trips) was the largest single stall source of
+// the kernel.  The episode sums go to per-CTA shared-memory accumulators, flushed once per CTA.
+__device__ void finish_episode(const Tables& T, const Params& P, const State& S, double* __restrict__ cta_accum, int b, int lane) {
+  constexpr int MAX_OBS_PER_LANE = (OBS_DIM + NODE_EMB + 31) / 32;
+  float ob[MAX_OBS_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAX_OBS_PER_LANE; ++i) {
+    const int idx = lane + 32 * i;
+    ob[i] = idx < P.obs_dim ? S.obs[(size_t)b * P.obs_dim + idx] : 0.f;
   }
-  const int n_disc = scalar(S, P, S_N_DISC, b);
-  const int flags = scalar(S, P, S_FLAGS, b);
+  uint32_t mv = 0;
+  int sv = 0;
+  double ret = 0.0;
+  if (lane < 16) {
+    const int w = lane & 3, grp = lane >> 2;
+    const int plane = grp == 0 ? M_OWNED : (grp == 1 ? M_DISCOVERED : (grp == 2 ? M_STOPPED : M_IMAGING));
+    if (w < P.words && (grp < 3 || P.defender)) mv = ld_mask(S, P, plane, w, b);
+  } else if (lane < 27) {
+    sv = scalar(S, P, kFinishPlanes[lane - 16], b);
+  } else if (lane == 31) ret = S.ep_return[b];
+  int owned = 0, disrupted = 0, running = 0;
+#pragma unroll
+  for (int w = 0; w < MAX_NODES / 32; ++w) {
+    const uint32_t own = __shfl_sync(0xFFFFFFFFu, mv, w), disc = __shfl_sync(0xFFFFFFFFu, mv, 4 + w);
+    const uint32_t stop = __shfl_sync(0xFFFFFFFFu, mv, 8 + w), img = __shfl_sync(0xFFFFFFFFu, mv, 12 + w);
+    owned += __popc(own);
+    disrupted += __popc(disc & stop);
+    running += __popc(disc & ~stop & ~img);
+  }
+  auto sc_of = [&](int k) { return __shfl_sync(0xFFFFFFFFu, sv, 16 + k); };
+  const int n_disc = sc_of(0), flags = sc_of(1), stepcount = sc_of(7), sc = sc_of(9), episodes = sc_of(10);
   const int reason = (flags >> FL_REASON_SHIFT) & 3;
+  const int N = T.sc_num_nodes[sc];
   double st[14];
   st[0] = owned; st[1] = n_disc; st[2] = N - n_disc; st[3] = disrupted; st[4] = N;
-  st[5] = scalar(S, P, S_OWNABLE, b); st[6] = scalar(S, P, S_DISCOVERABLE, b); st[7] = scalar(S, P, S_DISRUPTABLE, b);
-  st[8] = (double)running / (double)n_disc; st[9] = st[10] = P.defender ? scalar(S, P, S_N_REIMAGED, b) : 0;   // len(overall_reimaged), num_events
-  st[11] = scalar(S, P, S_DISC_AMOUNT, b); st[12] = scalar(S, P, S_DISCOVERABLE_AMOUNT, b);
-  st[13] = goal_reached(S, P, b, is_node_goal(P) ? T.sc_interest[sc] : -1) ? 1.0 : 0.0;
+  st[5] = sc_of(2); st[6] = sc_of(3); st[7] = sc_of(4);
+  st[8] = (double)running / (double)n_disc;
+  st[9] = st[10] = P.defender ? sc_of(8) : 0;          // len(overall_reimaged), num_events
+  st[11] = sc_of(5); st[12] = sc_of(6);
+  // attacker_goal_reached() at the end of an episode: the goal test comes first in the end-of-step chain
+  // (cyberbattle_env.py:343-370), so it holds exactly when the episode's last step reported reason 1
+  st[13] = reason == 1 ? 1.0 : 0.0;
+  const double ep_ret = __shfl_sync(0xFFFFFFFFu, ret, 31);
   double v = 0.0;
   if (lane < 14) {
 #pragma unroll
     for (int i = 0; i < 14; ++i) if (i == lane) v = st[i];
     S.last_stats[(size_t)b * 14 + lane] = v;
-    atomicAdd(&S.accum[A_STAT0 + lane], v);
-  } else if (lane == 14) atomicAdd(&S.accum[A_EPISODES], 1.0);
-  else if (lane == 15) atomicAdd(&S.accum[A_RETURN], S.ep_return[b]);
-  else if (lane == 16) atomicAdd(&S.accum[A_LENGTH], (double)scalar(S, P, S_STEPCOUNT, b));
-  else if (lane == 17 && reason >= 1) atomicAdd(&S.accum[A_WINS + reason - 1], 1.0);
-  for (int i = lane; i < P.obs_dim; i += 32) S.term_obs[(size_t)b * P.obs_dim + i] = S.obs[(size_t)b * P.obs_dim + i];
-  __syncwarp();
-  if (lane == 0) scalar(S, P, S_EPISODES, b) += 1;
+    atomicAdd(&cta_accum[A_STAT0 + lane], v);
+  } else if (lane == 14) atomicAdd(&cta_accum[A_EPISODES], 1.0);
+  else if (lane == 15) atomicAdd(&cta_accum[A_RETURN], ep_ret);
+  else if (lane == 16) atomicAdd(&cta_accum[A_LENGTH], (double)stepcount);
+  else if (lane == 17 && reason >= 1) atomicAdd(&cta_accum[A_WINS + reason - 1], 1.0);
+#pragma unroll
+  for (int i = 0; i < MAX_OBS_PER_LANE; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < P.obs_dim) S.term_obs[(size_t)b * P.obs_dim + idx] = ob[i];
+  }
+  if (lane == 0) scalar(S, P, S_EPISODES, b) = episodes + 1;
   __syncwarp();
 }
 
@@ -410,7 +443,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     else if (plane == M_VISIBLE) v = T.sc_init_visible[sc * P.words + w];
     else if (w == sw && (plane == M_OWNED || plane == M_DISCOVERED || (plane == M_PRIV_USER && laa >= 1) ||
                          (plane == M_PRIV_ROOT && laa == 3) || (plane == M_EVER_OWNED && P.defender))) v = sbit;
-    S.masks[((size_t)plane * P.words + w) * P.B + b] = v;
+    S.masks[(size_t)b * P.mpitch + i] = v;
   }
   uint32_t* ps = reinterpret_cast<uint32_t*>(S.pair_slot + (size_t)b * P.ncap * P.ncap);
   for (int i = lane; i < P.ncap * P.ncap / 4; i += 32) ps[i] = 0xFFFFFFFFu;
@@ -450,7 +483,8 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
 // BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
 template <bool BIG_GRAPHS>
 __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Params P, State S,
-                                                                const uint8_t* __restrict__ reset_mask, int mode) {
+                                                                const uint8_t* __restrict__ reset_mask, int mode,
+                                                                long long* __restrict__ trace) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SharedWeights& SW = *reinterpret_cast<SharedWeights*>(smem_raw);
   {   // stage the weights with 128-bit loads, all requests in flight before the first store
@@ -477,6 +511,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     SW.bn2h[threadIdx.x] = T.bn2_shift[threadIdx.x];
   }
   if (threadIdx.x < NN_CH) SW.nn0b[threadIdx.x] = T.nn0_b[threadIdx.x];
+  if (threadIdx.x < N_ACCUM) SW.accum[threadIdx.x] = 0.0;
+  if (threadIdx.x == 0) SW.warps_done = 0;
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -524,6 +560,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       W.g = small ? W.ysm + SMEM_NODES * NODE_EMB : W.y + (size_t)P.ncap * NODE_EMB;
     }
     const int flags = scalar(S, P, S_FLAGS, b);
+    long long t_item = 0, t_ph[5] = {0, 0, 0, 0, 0};
+    if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_item));
     bool do_reset = false;
     if (mode == 1) {
       do_reset = reset_mask ? (reset_mask[b] != 0) : true;
@@ -532,12 +570,15 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
       if (flags & FL_REENCODE) {
         encode_env(T, P, S, SW, W, b, lane);
+        if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
         build_table(T, P, S, W, b, lane);
+        if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
         keep &= ~FL_DIRTY;
         if (is_node_goal(P)) keep |= FL_INTEREST_IN_GRAPH;
       }
       if (flags & FL_FINISHED_THIS_STEP) {
-        finish_episode(T, P, S, b, lane);
+        finish_episode(T, P, S, SW.accum, b, lane);
+        if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[2])); }
         if (P.auto_reset) do_reset = true;
       }
       __syncwarp();
@@ -546,16 +587,36 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     }
     if (do_reset) {
       reset_env(T, P, S, b, lane);
+      if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[3])); }
       W.y = W.ysm;                               // a fresh episode's graph is one node
       W.g = W.ysm + SMEM_NODES * NODE_EMB;
       encode_env(T, P, S, SW, W, b, lane);
+      if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[4])); }
       build_table(T, P, S, W, b, lane);
       // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even
       // if nothing else changes
       if (is_node_goal(P) && lane == 0) scalar(S, P, S_FLAGS, b) = FL_DIRTY | FL_INTEREST_IN_GRAPH;
     }
     __syncwarp();
+    if (trace && lane == 0) {   // debug: per item {start ns, duration ns, flags at entry, nodes << 16 | edges}
+      long long t_end;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+      long long* tr = trace + (size_t)b * 9;
+      tr[0] = t_item; tr[1] = t_end - t_item; tr[2] = flags;
+      tr[3] = ((long long)scalar(S, P, S_N_DISC, b) << 16) | scalar(S, P, S_N_EDGES, b);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) tr[4 + k] = t_ph[k] ? t_ph[k] - t_item : 0;   // phase end times relative to the item start
+    }
     if (mode == 1) i += total_warps;
+  }
+  // the CTA's last warp adds the CTA's episode sums to the global accumulators (one atomic per slot and CTA)
+  __syncwarp();
+  int last_in_cta = 0;
+  if (lane == 0) { __threadfence_block(); last_in_cta = atomicAdd(&SW.warps_done, 1) == OBS_WARPS - 1; }
+  last_in_cta = __shfl_sync(0xFFFFFFFFu, last_in_cta, 0);
+  if (last_in_cta && lane < N_ACCUM) {
+    const double v = SW.accum[lane];
+    if (v != 0.0) atomicAdd(&S.accum[lane], v);
   }
   if (mode == 0 && lane == 0) {   // the last warp to run dry clears the counters for the next transition
     __threadfence();
@@ -565,6 +626,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
     }
   }
 }
+
+long long* g_obs_trace = nullptr;   // debug: per-env {start ns, duration ns, flags, nodes << 16 | edges} of the env's last item
 
 size_t observe_smem_bytes() {
   const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 4 * MAX_NODES;
@@ -586,8 +649,8 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
     if (e != cudaSuccess) return e;
     attr_set[big] = true;
   }
-  if (big) observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
-  else observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode);
+  if (big) observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
+  else observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
   return cudaGetLastError();
 }
 

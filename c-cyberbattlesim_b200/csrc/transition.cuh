@@ -14,12 +14,12 @@ namespace cbs {
 namespace {
 
 struct EnvBits {
-  uint32_t* masks;
-  int words, B, b;
-  __device__ uint32_t word(int plane, int w) const { return masks[((size_t)plane * words + w) * B + b]; }
+  uint32_t* masks;   // this env's mask record
+  int words;
+  __device__ uint32_t word(int plane, int w) const { return masks[plane * words + w]; }
   __device__ bool get(int plane, int node) const { return (word(plane, node >> 5) >> (node & 31)) & 1u; }
-  __device__ void set(int plane, int node) { masks[((size_t)plane * words + (node >> 5)) * B + b] |= (1u << (node & 31)); }
-  __device__ void clr(int plane, int node) { masks[((size_t)plane * words + (node >> 5)) * B + b] &= ~(1u << (node & 31)); }
+  __device__ void set(int plane, int node) { masks[plane * words + (node >> 5)] |= (1u << (node & 31)); }
+  __device__ void clr(int plane, int node) { masks[plane * words + (node >> 5)] &= ~(1u << (node & 31)); }
 };
 
 // Philox draw j of a stream family: component (j & 3) of stream `base + (j >> 2)`
@@ -121,9 +121,8 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
                                             const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
-  const int B = P.B;
-  int32_t* scal = S.scal;
-  auto SC = [&](int plane) -> int32_t& { return scal[(size_t)plane * B + b]; };
+  int32_t* scal = S.scal + (size_t)b * SCAL_PITCH;
+  auto SC = [&](int plane) -> int32_t& { return scal[plane]; };
 
   int flags = SC(S_FLAGS);
   sched_enqueue(S, P, b, sched_out);   // cost-binned env list for the next decode (longest tables first)
@@ -143,7 +142,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   const int sc = SC(S_SCENARIO);
   const int N = T.sc_num_nodes[sc];
   const int node_off = T.sc_node_off[sc];
-  EnvBits M{S.masks, P.words, B, b};
+  EnvBits M{S.masks + (size_t)b * P.mpitch, P.words};
 
   SC(S_STEPCOUNT) += 1;                                   // :303
   const int total_steps = SC(S_TOTAL_STEPS);

@@ -223,10 +223,10 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
 
 /* ---- introspection (parity tests, statistics) ----------------------------------------------------- */
 typedef enum {
-  CBS_F_MASKS = 0,        /* uint32 [CBS_NUM_MASKS][words][B] */
+  CBS_F_MASKS = 0,        /* uint32 [B][mask_pitch]: plane p, word w of env b at b * mask_pitch + p * words + w */
   CBS_F_DISC_ORDER = 1,   /* uint8 [B][max_nodes] */
   CBS_F_OWNED_ORDER = 2,  /* uint8 [B][max_nodes] every node that entered env.owned_nodes, in first-entry order */
-  CBS_F_SCALARS = 3,      /* int32 [CBS_NUM_SCALARS][B] */
+  CBS_F_SCALARS = 3,      /* int32 [B][scalar_pitch], the first CBS_NUM_SCALARS entries of a record are used */
   CBS_F_TERMINAL_OBS = 4, /* float32 [B][194] */
   CBS_F_OBS = 5,          /* float32 [B][194] cached observation */
   CBS_F_LAST_STATS = 6,   /* float64 [B][14] get_statistics() of the last finished episode */
@@ -251,6 +251,9 @@ int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream);
 /* debugging aid: per-env {cycles, rows scanned, live pairs, float64 re-scores, pair combinations, start clock} of the
  * following cbs_decode calls are written to trace_dev ([num_envs][6] int64, device); NULL switches it off */
 int cbs_debug_select_trace(cbs_handle* h, long long* trace_dev);
+/* debug aid: per-env {start ns (globaltimer), duration ns, flags at entry, nodes << 16 | edges} of the env's last item in
+ * the observe kernel, followed by five phase end times; trace_dev = int64[num_envs][9] device buffer, or NULL to switch tracing off */
+int cbs_debug_observe_trace(cbs_handle* h, long long* trace_dev);
 /* number of kernels this library launched since creation (bench.py reports it) */
 int64_t cbs_launch_count(const cbs_handle* h);
 /* cudaDeviceSynchronize + device error flag (capacity overflow, empty action table) -> CBS_ERR_CAPACITY */
@@ -260,8 +263,9 @@ int cbs_sync(cbs_handle* h);
 int cbs_struct_sizes(int32_t* out3);
 /* bytes of device memory held by the handle (tables + env state) */
 int64_t cbs_state_bytes(const cbs_handle* h);
-/* out6 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active, vt_stride, observation length } */
-int cbs_capacities(const cbs_handle* h, int32_t* out6);
+/* out8 = { node capacity, snapshot slots, edge capacity, 1 if the tcgen05 decode GEMM is active, vt_stride, observation length,
+ *          mask_pitch (uint32 words per env in CBS_F_MASKS), scalar_pitch (int32 words per env in CBS_F_SCALARS) } */
+int cbs_capacities(const cbs_handle* h, int32_t* out8);
 
 #ifdef __cplusplus
 }
