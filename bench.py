@@ -152,6 +152,51 @@ def ncu_traffic(kernel):
         return json.load(f).get(kernel)
 
 
+def transition_roofline(specs, weights, device_index, n_envs, n_steps=4, seed=11):
+    """Large-batch leg for the transition kernel (at 8192 envs a launch moves 1.8 MB and is latency bound; the
+    HBM roofline is only meaningful at >= 1e6 env-steps per launch).  The same scenario set with `n_envs` envs on one GPU,
+    driven through the split C-ABI calls decode -> transition -> observe from a fresh reset; only `cbs_transition` is
+    timed (CUDA events on the launching stream).  Snapshot capacity is cut to 4 slots so that the state fits HBM; envs
+    that would need more stop growing their tables (flagged, harmless for this measurement).  Returns a dict."""
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200 import constants as C
+    from ccbs_b200.batched_env import BatchedCyberBattleEnv
+    dev = torch.device("cuda", device_index)
+    env = BatchedCyberBattleEnv(specs, weights, cb.EnvConfig(), num_envs=n_envs, device=device_index, seed=seed,
+                                auto_reset=True, max_slots=4, max_edges=8)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    actions = torch.empty(n_envs, C.ACTION_DIM, device=dev)
+    env.reset()
+    torch.cuda.synchronize(dev)
+    times, ok_frac = [], []
+    for k in range(n_steps + 1):            # step 0 is the warm-up launch
+        actions.uniform_(-4.0, 4.0, generator=gen)
+        sel, dist = env.decode(actions)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _, _, _, outcome = env.transition(sel, dist, None)
+        e1.record()
+        env.observe()
+        torch.cuda.synchronize(dev)
+        if k:
+            times.append(e0.elapsed_time(e1))
+            ok_frac.append(float((outcome < 16).float().mean().item()))
+    state_gb = env.state_bytes / 1e9
+    env.close()
+    del actions
+    torch.cuda.empty_cache()
+    ms = float(np.mean(times))
+    peak, peak_src = measured_peaks()
+    alg = 220.0 * n_envs                    # SURVEY 8(d): ~220 B of per-env state and I/O per transition
+    return {"kernel": "transition (split call cbs_transition, large batch)", "envs_per_launch": int(n_envs), "launches_timed": len(times),
+            "ms_per_launch": ms, "ms_all": times, "bytes_per_env_step": 220, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+            "traffic": ncu_traffic("transition_large"), "successful_outcomes": float(np.mean(ok_frac)),
+            "state_gb": state_gb, "env_steps_per_s": n_envs / (ms * 1e-3)}
+
+
 def run_reference(args, wl_key, rank, emit):
     """--impl reference: the CPU restatement of the same path on all host cores (rank 0 only)."""
     if rank != 0:
@@ -195,6 +240,8 @@ def main():
     ap.add_argument("--defender", action="store_true",
                     help="side measurement: the same workload with the re-imaging static defender of train_config.yaml:39-44 "
                          "(not the headline configuration)")
+    ap.add_argument("--transition-envs", type=int, default=1 << 20,
+                    help="envs of the large-batch transition-kernel roofline leg (rank 0, N=1 only; 0 = skip)")
     ap.add_argument("--action-pitch", type=int, default=905,
                     help="row pitch (floats) of the device-resident action batches; 905 = dense like the reference's "
                          "action array, 908 lets TMA read them in place (no repack kernel)")
@@ -365,6 +412,9 @@ def main():
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
         }
+        env.close()
+        if world == 1 and args.transition_envs > 0:
+            out["transition_roofline"] = transition_roofline(specs, weights, local_rank, args.transition_envs)
         emit(out)
     env.close()
     if world > 1:

@@ -263,7 +263,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * P.obs_dim); AL(term_obs, B * P.obs_dim); AL(sel, B * 4); AL(dist, B); AL(reward64, B); AL(ep_return, B);
   AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 1);
-  AL(scratch, B * 2 * P.ncap * NODE_EMB);
+  AL(scratch, P.ncap > CBS_OBS_SMEM_NODES ? B * 2 * P.ncap * NODE_EMB : 1);   // only graphs beyond the shared-memory buffers use it
 #undef AL
   if ((rc = dalloc(h, h->state_allocs, &h->d_sel, B * 4))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->d_dist, B))) return rc;

@@ -17,6 +17,9 @@ constexpr int NN_CH = 16;
 constexpr int PROJ_ROWS = 18;  // 16 hidden + bias slot + root term
 constexpr int NUM_DYN = 6;     // persistence, collected, exfiltrated, evasion, privilege, status
 constexpr int MAX_NODES = 128;
+#ifndef CBS_OBS_SMEM_NODES
+#define CBS_OBS_SMEM_NODES 32   // visible graphs up to this many nodes keep their embeddings in shared memory (k_observe.cu)
+#endif
 constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: one 128-byte line per env
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 

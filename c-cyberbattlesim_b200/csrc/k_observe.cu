@@ -19,9 +19,6 @@ namespace cbs {
 #ifndef CBS_OBS_WARPS
 #define CBS_OBS_WARPS 8
 #endif
-#ifndef CBS_OBS_SMEM_NODES
-#define CBS_OBS_SMEM_NODES 32
-#endif
 constexpr int OBS_WARPS = CBS_OBS_WARPS;          // warps per CTA (one CTA per SM)
 constexpr int SMEM_NODES = CBS_OBS_SMEM_NODES;    // graphs up to this many nodes keep their embeddings in shared memory
 

@@ -116,8 +116,12 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
 }  // namespace
 
 // DEF: a static defender is configured (compile-time, so the default kernels carry none of its code or registers)
-template <bool DEF>
-static __device__ __forceinline__ void transition_env(const Tables& T, const Params& P, const State& S, int b, int4 sl, double dist,
+// ENQ: the function itself appends the env to the decode cost bins and to the observe worklist (one atomic each: the
+//      fused path, one lane per warp).  The thread-per-env kernel passes false and aggregates both per CTA — a million
+//      same-address atomics serialise in L2 and were 90 % of that kernel's time at large batch.
+// Returns the env's observe work class (0 episode end, 1 re-encode, 2 edge only) or -1.
+template <bool DEF, bool ENQ = true>
+static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, int4 sl, double dist,
                                             const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
@@ -125,7 +129,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   auto SC = [&](int plane) -> int32_t& { return scal[plane]; };
 
   int flags = SC(S_FLAGS);
-  sched_enqueue(S, P, b, sched_out);   // cost-binned env list for the next decode (longest tables first)
+  if (ENQ) sched_enqueue(S, P, b, sched_out);   // cost-binned env list for the next decode (longest tables first)
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     // the reference raises RuntimeError here (cyberbattle_env.py:300-302); a finished env is left untouched
     if (reward_out) reward_out[b] = 0.f;
@@ -133,7 +137,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
     if (trunc_out) trunc_out[b] = (flags & FL_TRUNC) ? 1 : 0;
     if (outcome_out) outcome_out[b] = OC_INVALID_SRC_NOT_OWNED;
     SC(S_FLAGS) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
-    return;
+    return -1;
   }
 
     const int s = sl.x, t = sl.y, u = sl.z, kind = sl.w;
@@ -393,11 +397,14 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
   SC(S_FLAGS) = flags;
+  int cls = -1;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
     // three cost classes, claimed heaviest first: episode end (statistics + reset + encode + table), re-encode, edge only
-    const int cls = (flags & FL_FINISHED_THIS_STEP) ? 0 : ((flags & FL_REENCODE) ? 1 : 2);
-    const int slot = atomicAdd(&S.work_ctr[4 + cls], 1);
-    if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);
+    cls = (flags & FL_FINISHED_THIS_STEP) ? 0 : ((flags & FL_REENCODE) ? 1 : 2);
+    if (ENQ) {
+      const int slot = atomicAdd(&S.work_ctr[4 + cls], 1);
+      if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);
+    }
   }
   S.reward64[b] = reward;
   S.ep_return[b] += reward;
@@ -405,6 +412,7 @@ static __device__ __forceinline__ void transition_env(const Tables& T, const Par
   if (done_out) done_out[b] = (done || trunc) ? 1 : 0;
   if (trunc_out) trunc_out[b] = trunc ? 1 : 0;
   if (outcome_out) outcome_out[b] = (uint8_t)code;
+  return cls;
 }
 
 }  // namespace cbs
