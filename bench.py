@@ -378,9 +378,10 @@ def main():
         peak, peak_src = measured_peaks()
         # algorithmic bytes per env-step: decode = action read 3620 B + VT row write+read
         # 2*4*Ug + candidate scan; transition = 220 B; observe = obs write 776 B + (on re-encode) ~10 KB
+        from ccbs_b200 import lib as _L
         Ug = env.tables.vemb32.shape[0]
         sc = env.scalars()
-        pairs = float(np.mean(sc[5] * sc[4]))                       # n_owned * n_disc  (upper bound of table pairs)
+        pairs = float(np.mean(sc[_L.S_N_OWNED] * sc[_L.S_N_DISC]))   # n_owned * n_disc  (upper bound of table pairs)
         rows = pairs * 24.0                                         # ~24 candidate rows per pair (tools/workload_stats.py)
         alg = {
             # A_v read + Vemb + VT write (the dense action rows are staged by cp.async, no repack pass)
@@ -395,7 +396,6 @@ def main():
                 "unit": "GB/s", "peak_source": peak_src, "traffic": ncu_traffic(dom),
                 "kernels_ms": kern, "kernels_gbs": {k: alg[k] / (kern[k] * 1e-3) / 1e9 for k in kern}}
         roof["frac"] = roof["achieved"] / peak
-        from ccbs_b200 import lib as _L
         acc = dict(zip(_L.ACCUM_NAMES, acc_all.cpu().tolist()))   # summed over all ranks, timed-region episodes + warm-up
         out = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,

@@ -17,32 +17,6 @@ __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int 
 __device__ __forceinline__ bool is_node_goal(const Params& P) { return P.goal >= GOAL_CONTROL_NODE; }
 __device__ __forceinline__ int base_goal(const Params& P) { return is_node_goal(P) ? P.goal - GOAL_CONTROL_NODE : P.goal; }
 
-// attacker_goal_reached (cyberbattle_env.py:467-514), on mask words.  `interest` = the env's interest node (*_node goals)
-__device__ inline bool goal_reached(const State& S, const Params& P, int b, int interest) {
-  if (P.goal == GOAL_CONTROL_NODE) return bit_of(S, P, M_OWNED, interest, b) && bit_of(S, P, M_PRIV_ROOT, interest, b);
-  if (P.goal == GOAL_DISCOVERY_NODE)    // :493-508 (has_data is cleared by the collection, so "collected and exfiltrated" cannot hold with it)
-    return bit_of(S, P, M_DISCOVERED, interest, b) && bit_of(S, P, M_VISIBLE, interest, b) &&
-           (!bit_of(S, P, M_HAS_DATA, interest, b) ||
-            (bit_of(S, P, M_COLLECTED, interest, b) && bit_of(S, P, M_EXFILTRATED, interest, b)));
-  if (P.goal == GOAL_DISRUPTION_NODE) return bit_of(S, P, M_STOPPED, interest, b);
-  const int starter = scalar(S, P, S_STARTER, b);
-  int n_goal = 0, n_data = 0, n_pending = 0;
-  for (int w = 0; w < P.words; ++w) {
-    const uint32_t disc = ld_mask(S, P, M_DISCOVERED, w, b);
-    const uint32_t not_starter = ((starter >> 5) == w) ? ~(1u << (starter & 31)) : 0xFFFFFFFFu;
-    if (P.goal == GOAL_CONTROL) n_goal += __popc(ld_mask(S, P, M_OWNED, w, b) & ld_mask(S, P, M_PRIV_ROOT, w, b) & not_starter);
-    else if (P.goal == GOAL_DISRUPTION) n_goal += __popc(disc & ld_mask(S, P, M_STOPPED, w, b) & not_starter);
-    else {
-      n_goal += __popc(disc & not_starter);
-      n_data += __popc(disc & ld_mask(S, P, M_HAS_DATA, w, b));
-      n_pending += __popc(disc & ld_mask(S, P, M_COLLECTED, w, b) & ~ld_mask(S, P, M_EXFILTRATED, w, b));
-    }
-  }
-  if (P.goal == GOAL_CONTROL) return n_goal == scalar(S, P, S_OWNABLE, b);
-  if (P.goal == GOAL_DISRUPTION) return n_goal == scalar(S, P, S_DISRUPTABLE, b);
-  return n_goal == scalar(S, P, S_DISCOVERABLE, b) && n_data == 0 && n_pending == 0;
-}
-
 // cost bin of an env for the longest-first decode schedule
 __device__ __forceinline__ int sched_bin(int rows) {
   const int b = 31 - __clz((rows >> 5) | 1);   // rows < 64 -> 0, < 128 -> 1, ...

@@ -48,13 +48,25 @@ enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLE
                      P_ALREADY_STOPPED, P_ALREADY_OWNED, P_ALREADY_VISIBLE, P_ALREADY_EVASION, P_UNOPEN_PORT,
                      P_PRIVESC_NOT_OWNED, P_PRIVESC_ALREADY, P_OUTCOME_NOT_VALID, P_FW_LOCAL, P_FW_REMOTE,
                      P_INVALID_ACTION, P_DISTANCE, N_PENALTIES };
-// per-env int32 scalar planes
-enum Scalar : int { S_SCENARIO = 0, S_STARTER, S_STEPCOUNT, S_NUM_ITER, S_N_DISC, S_N_OWNED, S_DISC_AMOUNT, S_OWNABLE,
-                    S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT, S_EPISODES, S_N_SLOTS, S_N_EDGES,
-                    S_FLAGS, S_OUTCOME, S_TOTAL_STEPS, S_N_ENCODES, S_NODE_OFF,
-                    S_N_OWNED_RAW,   // len(env.owned_nodes) under a defender (the list can hold duplicates, cyberbattle_env.py:425-430)
-                    S_N_REIMAGED,    // len(overall_reimaged) == num_events of the episode (cyberbattle_env.py:419-422)
-                    N_SCALARS };
+// per-env int32 scalar record: one 128-byte line per env, grouped by 32-byte sector so that a kernel touches (and
+// writes back) only the sectors it needs.  The transition reads and rewrites sector 0 on every step, touches sector 1 only
+// for outcomes that change a list, and never reads sectors 2-3 (episode constants come from the tables via S_SCST).
+enum Scalar : int {
+  // sector 0 — rewritten by every transition
+  S_FLAGS = 0, S_STEPCOUNT, S_NUM_ITER, S_TOTAL_STEPS, S_OUTCOME,
+  S_SCST,           // scenario << 8 | starter node (copy of S_SCENARIO / S_STARTER, written by the reset)
+  S_EP_RETURN,      // float64 episode return, two words (8-byte aligned)
+  S_EP_RETURN_HI,
+  // sector 1 — list lengths and counters
+  S_N_DISC = 8, S_N_OWNED, S_DISC_AMOUNT,
+  S_N_OWNED_RAW,    // len(env.owned_nodes) under a defender (the list can hold duplicates, cyberbattle_env.py:425-430)
+  S_N_REIMAGED,     // len(overall_reimaged) == num_events of the episode (cyberbattle_env.py:419-422)
+  S_N_SLOTS, S_N_EDGES, S_N_ENCODES,
+  // sector 2 — constants of the episode (functions of scenario and starter)
+  S_SCENARIO = 16, S_STARTER, S_NODE_OFF, S_OWNABLE, S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT,
+  // sector 3
+  S_EPISODES = 24,
+  N_SCALARS };
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
               FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
@@ -133,7 +145,6 @@ struct State {  // mutable, device pointers
   int32_t* sel;          // [B][4]
   double* dist;          // [B]
   double* reward64;      // [B]
-  double* ep_return;     // [B]
   double* last_stats;    // [B][14]
   double* accum;         // [N_ACCUM]
   int32_t* starter_queue;  // [B][qlen] or nullptr

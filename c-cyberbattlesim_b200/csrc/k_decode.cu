@@ -218,7 +218,8 @@ struct FusedTransition {
   uint8_t* done;
 };
 
-template <bool FUSE, bool DEF>
+// W1: one-word mask planes and no defender -> the fused transition stages the env's records in registers
+template <bool FUSE, bool DEF, bool W1>
 __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
                                                                    int vt_stride, int vt_cached, int sched_buf, FusedTransition ft,
                                                                    int32_t* __restrict__ sel_out, double* __restrict__ dist_out,
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       S.dist[b] = 0.0;
       if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
       if (dist_out) dist_out[b] = 0.0;
-      if (FUSE) transition_env<DEF>(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      if (FUSE) transition_env<DEF, true, W1>(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
     }
     sched_done(S, sched_buf);
     return;
@@ -455,7 +456,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
     }
     // fused step: the transition of this env runs here, on one lane, while the other warps are still scanning
-    if (FUSE) transition_env<DEF>(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+    if (FUSE) transition_env<DEF, true, W1>(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
   }
   sched_done(S, sched_buf);
 }
@@ -468,11 +469,12 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
   const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
   const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
-  static size_t attr[4] = {0, 0, 0, 0};
-  const int which = (fuse_transition ? 1 : 0) | (P.defender ? 2 : 0);
+  static size_t attr[6] = {0, 0, 0, 0, 0, 0};
+  const int which = (fuse_transition ? 1 : 0) | (P.defender ? 2 : (P.words == 1 ? 4 : 0));
   using KernelFn = void (*)(Tables, Params, State, const float*, int, int, int, FusedTransition, int32_t*, double*, long long*);
-  const KernelFn kernels[4] = {decode_select_kernel<false, false>, decode_select_kernel<true, false>,
-                               decode_select_kernel<false, true>, decode_select_kernel<true, true>};
+  const KernelFn kernels[6] = {decode_select_kernel<false, false, false>, decode_select_kernel<true, false, false>,
+                               decode_select_kernel<false, true, false>,  decode_select_kernel<true, true, false>,
+                               decode_select_kernel<false, false, true>,  decode_select_kernel<true, false, true>};
   const KernelFn kern = kernels[which];
   if (smem > 48 * 1024 && smem > attr[which]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

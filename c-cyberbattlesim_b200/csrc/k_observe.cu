@@ -370,7 +370,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
     if (w < P.words && (grp < 3 || P.defender)) mv = ld_mask(S, P, plane, w, b);
   } else if (lane < 27) {
     sv = scalar(S, P, kFinishPlanes[lane - 16], b);
-  } else if (lane == 31) ret = S.ep_return[b];
+  } else if (lane == 31) ret = *reinterpret_cast<const double*>(&scalar(S, P, S_EP_RETURN, b));
   int owned = 0, disrupted = 0, running = 0;
 #pragma unroll
   for (int w = 0; w < MAX_NODES / 32; ++w) {
@@ -448,6 +448,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     scalar(S, P, S_SCENARIO, b) = sc;
     scalar(S, P, S_NODE_OFF, b) = T.sc_node_off[sc];
     scalar(S, P, S_STARTER, b) = starter;
+    scalar(S, P, S_SCST, b) = (sc << 8) | starter;      // what the transition reads instead of the constant sector
     scalar(S, P, S_STEPCOUNT, b) = 0;
     scalar(S, P, S_NUM_ITER, b) = 0;
     scalar(S, P, S_N_DISC, b) = 1;
@@ -472,7 +473,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
       scalar(S, P, S_N_OWNED_RAW, b) = 1;
       scalar(S, P, S_N_REIMAGED, b) = 0;
     }
-    S.ep_return[b] = 0.0;
+    *reinterpret_cast<double*>(&scalar(S, P, S_EP_RETURN, b)) = 0.0;
   }
   __syncwarp();
 }

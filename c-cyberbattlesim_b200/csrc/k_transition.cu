@@ -26,7 +26,7 @@ __device__ __forceinline__ void cta_append(int which, int b, int32_t* __restrict
   }
 }
 
-template <bool DEF>
+template <bool DEF, bool REG>
 __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_in,
                                                                 const double* __restrict__ dist_in,
                                                                 const float* __restrict__ uniforms, int sched_out,
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
                          S.bin_list + (size_t)sched_out * SCHED_BINS * P.B, P.B, P.B, nullptr, 0, sh_cnt, sh_base);
   int cls = -1;
   if (live)
-    cls = transition_env<DEF, false>(T, P, S, b, reinterpret_cast<const int4*>(sel_in)[b], dist_in ? dist_in[b] : 0.0, uniforms,
+    cls = transition_env<DEF, false, REG>(T, P, S, b, reinterpret_cast<const int4*>(sel_in)[b], dist_in ? dist_in[b] : 0.0, uniforms,
                                      sched_out, reward_out, done_out, trunc_out, outcome_out);
   // the observe kernel's three class lists
   cta_append<3>(cls, b, S.work_ctr + 4, S.worklist, P.B, P.B, S.errflag, 4, sh_cnt, sh_base);
@@ -49,10 +49,13 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
 cudaError_t launch_transition(const Tables& T, const Params& P, const State& S, const int32_t* sel, const double* dist,
                               const float* uniforms, int sched_out, float* reward, uint8_t* done, uint8_t* trunc,
                               uint8_t* outcome, cudaStream_t stream) {
+  const int grid = (P.B + TR_THREADS - 1) / TR_THREADS;
   if (P.defender)
-    transition_kernel<true><<<(P.B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
+    transition_kernel<true, false><<<grid, TR_THREADS, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
+  else if (P.words == 1)   // <= 32 nodes: mask record staged in registers
+    transition_kernel<false, true><<<grid, TR_THREADS, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
   else
-    transition_kernel<false><<<(P.B + TR_THREADS - 1) / TR_THREADS, TR_THREADS, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
+    transition_kernel<false, false><<<grid, TR_THREADS, 0, stream>>>(T, P, S, sel, dist, uniforms, sched_out, reward, done, trunc, outcome);
   return cudaGetLastError();
 }
 

@@ -8,19 +8,54 @@
 #pragma once
 #include "cbs_device.cuh"
 #include "philox.cuh"
+#include <type_traits>
 
 namespace cbs {
 
 namespace {
 
+// the env's mask record, accessed in place (any number of words per plane)
 struct EnvBits {
   uint32_t* masks;   // this env's mask record
   int words;
+  __device__ void open(uint32_t* rec, int w) { masks = rec; words = w; }
+  __device__ void close() {}
   __device__ uint32_t word(int plane, int w) const { return masks[plane * words + w]; }
   __device__ bool get(int plane, int node) const { return (word(plane, node >> 5) >> (node & 31)) & 1u; }
   __device__ void set(int plane, int node) { masks[plane * words + (node >> 5)] |= (1u << (node & 31)); }
   __device__ void clr(int plane, int node) { masks[plane * words + (node >> 5)] &= ~(1u << (node & 31)); }
 };
+
+// Scenarios of <= 32 nodes (one word per plane): the whole 64-byte record is fetched with four 128-bit loads when the
+// env is opened, lives in registers (every plane index below is a compile-time constant), and only the words that
+// changed are written back.  All the state a transition needs is then requested in one burst instead of one dependent
+// round trip per bit test.
+struct EnvBitsReg {
+  uint32_t m[16];
+  uint32_t dirty;
+  uint32_t* rec;
+  __device__ __forceinline__ void open(uint32_t* r, int) {
+    rec = r; dirty = 0u;
+    const uint4* q = reinterpret_cast<const uint4*>(r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const uint4 v = q[i]; m[4 * i] = v.x; m[4 * i + 1] = v.y; m[4 * i + 2] = v.z; m[4 * i + 3] = v.w; }
+  }
+  __device__ __forceinline__ void close() {
+#pragma unroll
+    for (int p = 0; p < N_MASKS; ++p) if ((dirty >> p) & 1u) rec[p] = m[p];
+  }
+  __device__ __forceinline__ uint32_t word(int plane, int) const { return m[plane]; }
+  __device__ __forceinline__ bool get(int plane, int node) const { return (m[plane] >> (node & 31)) & 1u; }
+  __device__ __forceinline__ void set(int plane, int node) {
+    const uint32_t v = m[plane] | (1u << (node & 31));
+    if (v != m[plane]) { m[plane] = v; dirty |= 1u << plane; }
+  }
+  __device__ __forceinline__ void clr(int plane, int node) {
+    const uint32_t v = m[plane] & ~(1u << (node & 31));
+    if (v != m[plane]) { m[plane] = v; dirty |= 1u << plane; }
+  }
+};
+static_assert(N_MASKS <= 16, "EnvBitsReg holds one 64-byte record");
 
 // Philox draw j of a stream family: component (j & 3) of stream `base + (j >> 2)`
 __device__ __forceinline__ uint32_t philox_word(uint64_t key, uint64_t env, uint32_t step, uint32_t base, int j) {
@@ -119,16 +154,24 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
 // ENQ: the function itself appends the env to the decode cost bins and to the observe worklist (one atomic each: the
 //      fused path, one lane per warp).  The thread-per-env kernel passes false and aggregates both per CTA — a million
 //      same-address atomics serialise in L2 and were 90 % of that kernel's time at large batch.
+// REG: one-word planes and no defender -> the mask record is staged in registers (EnvBitsReg).
+// The hot sector of the scalar record (flags, counters of the step, scenario / starter, episode return) is read with two
+// 128-bit loads up front and written back as one full 32-byte sector; episode constants (reachable-node counts) come
+// from the scenario tables, so sectors 2-3 of the record are never touched and sector 1 only when a list changes.
 // Returns the env's observe work class (0 episode end, 1 re-encode, 2 edge only) or -1.
-template <bool DEF, bool ENQ = true>
+template <bool DEF, bool ENQ = true, bool REG = false>
 static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, int4 sl, double dist,
                                             const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
+  static_assert(!(DEF && REG), "the defender path works on the record in place");
   int32_t* scal = S.scal + (size_t)b * SCAL_PITCH;
-  auto SC = [&](int plane) -> int32_t& { return scal[plane]; };
+  auto SC = [&](int plane) -> int32_t& { return scal[plane]; };   // sector 1 (list lengths / counters), on demand
+  const int4 h0 = reinterpret_cast<const int4*>(scal)[0], h1 = reinterpret_cast<const int4*>(scal)[1];
+  typename std::conditional<REG, EnvBitsReg, EnvBits>::type M;
+  M.open(S.masks + (size_t)b * P.mpitch, P.words);
 
-  int flags = SC(S_FLAGS);
+  int flags = h0.x;
   if (ENQ) sched_enqueue(S, P, b, sched_out);   // cost-binned env list for the next decode (longest tables first)
   if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
     // the reference raises RuntimeError here (cyberbattle_env.py:300-302); a finished env is left untouched
@@ -143,14 +186,17 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     const int s = sl.x, t = sl.y, u = sl.z, kind = sl.w;
   reinterpret_cast<int4*>(S.sel)[b] = sl;
 
-  const int sc = SC(S_SCENARIO);
+  const int sc = h1.y >> 8, starter = h1.y & 0xFF;        // S_SCST
   const int N = T.sc_num_nodes[sc];
   const int node_off = T.sc_node_off[sc];
-  EnvBits M{S.masks + (size_t)b * P.mpitch, P.words};
-
-  SC(S_STEPCOUNT) += 1;                                   // :303
-  const int total_steps = SC(S_TOTAL_STEPS);
-  SC(S_TOTAL_STEPS) = total_steps + 1;
+  const int stepcount = h0.y + 1;                         // :303
+  const int num_iter = h0.z;
+  const int total_steps = h0.w;
+  // reachable-node counts of (scenario, starter): what reset_env keeps in S_OWNABLE / S_DISCOVERABLE / S_DISRUPTABLE /
+  // S_PROP_NODES, fetched from the tables (L2) so that the record's constant sector stays untouched
+  const int bg = base_goal(P);
+  const int32_t* reach_tab = bg == GOAL_CONTROL ? T.nd_ownable : (bg == GOAL_DISCOVERY ? T.nd_discoverable : T.nd_disruptable);
+  const int reach = reach_tab[node_off + starter];
 
   double reward = 0.0;
   int code = -1;
@@ -309,7 +355,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   // ---- static defender (cyberbattle_env.py:331-332), then the cached-feature rule of the visible graph: the target's
   //      vector is rebuilt from the post-defender state for these obtained outcomes only (compressed:472-479) ----
   bool def_event = false;
-  if (DEF) {
+  if constexpr (DEF) {
     DefenderCtx D;
     D.left = S.reimage_left + (size_t)b * P.ncap;
     D.raw = S.owned_raw + (size_t)b * P.ocap;
@@ -322,14 +368,13 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     D.seed = P.seed; D.genv = (uint64_t)(P.global_env_offset + b);
     D.detect_prob = P.detect_prob;
     D.words = P.words; D.ocap = P.ocap; D.scan_capacity = P.scan_capacity; D.scan_frequency = P.scan_frequency;
-    def_event = defender_step(D, M, N, SC(S_STEPCOUNT), total_steps, code == K_PRIVESC);
+    def_event = defender_step(D, M, N, stepcount, total_steps, code == K_PRIVESC);
     if (code < 16 && code != K_RECON) {
       if (M.get(M_IMAGING, t)) M.set(M_X_IMAGING, t); else M.clr(M_X_IMAGING, t);
     }
   }
 
   // ---- goal / termination (cyberbattle_env.py:338-370, 438-514) ----
-  const int starter = SC(S_STARTER);
   int n_goal = 0, n_data = 0, n_pending = 0;
   bool any_running_owned = false;
   int roots_in_list = 0;
@@ -358,16 +403,18 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   }
   if (DEF && P.goal == GOAL_CONTROL) n_goal = roots_in_list;
   bool goal_ok;
-  if (P.goal == GOAL_CONTROL) goal_ok = (n_goal == SC(S_OWNABLE));
-  else if (P.goal == GOAL_DISRUPTION) goal_ok = (n_goal == SC(S_DISRUPTABLE));
-  else if (P.goal == GOAL_DISCOVERY) goal_ok = (n_goal == SC(S_DISCOVERABLE) && n_data == 0 && n_pending == 0);
-  else if (DEF && P.goal == GOAL_CONTROL_NODE) goal_ok = interest_in_list && M.get(M_PRIV_ROOT, interest);
-  else goal_ok = goal_reached(S, P, b, interest);     // *_node goals: a few bit tests on the interest node
+  if (P.goal == GOAL_CONTROL || P.goal == GOAL_DISRUPTION) goal_ok = (n_goal == reach);
+  else if (P.goal == GOAL_DISCOVERY) goal_ok = (n_goal == reach && n_data == 0 && n_pending == 0);
+  // *_node goals (cyberbattle_env.py:467-514): a few bit tests on the interest node
+  else if (P.goal == GOAL_CONTROL_NODE) goal_ok = (DEF ? interest_in_list : M.get(M_OWNED, interest)) && M.get(M_PRIV_ROOT, interest);
+  else if (P.goal == GOAL_DISCOVERY_NODE)   // :493-508 (has_data is cleared by the collection, so "collected and exfiltrated" cannot hold with it)
+    goal_ok = M.get(M_DISCOVERED, interest) && M.get(M_VISIBLE, interest) &&
+              (!M.get(M_HAS_DATA, interest) || (M.get(M_COLLECTED, interest) && M.get(M_EXFILTRATED, interest)));
+  else goal_ok = M.get(M_STOPPED, interest);
   // check_end_game (:438-454): killing the interest node loses control_node / discovery_node games
   const bool lost = ((P.goal == GOAL_CONTROL_NODE || P.goal == GOAL_DISCOVERY_NODE) && M.get(M_STOPPED, interest)) ||
                     !any_running_owned;
 
-  const int num_iter = SC(S_NUM_ITER);
   int reason = 0;
   bool done = false, trunc = false;
   if (goal_ok) {
@@ -375,7 +422,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     reward = P.winning_reward; reason = 1;
   } else if (lost) {
     done = true; reward = P.losing_reward; reason = 2;
-  } else if (P.prop_coeff != 0.0 && (double)num_iter >= (double)SC(S_PROP_NODES) * P.prop_coeff) {
+  } else if (P.prop_coeff != 0.0 && (double)num_iter >= (double)reach * P.prop_coeff) {
     trunc = true; reason = 3;
   } else if (num_iter >= P.episode_iterations) {
     trunc = true; reason = 3;
@@ -385,8 +432,6 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   // compressed:401,462: the DESIRED outcome decides; with a defender or precise_graph_encoding every step re-encodes
   const bool reencode = P.always_encode || (kind == K_LATERAL || kind == K_DOS || kind == K_RECON);
   reward += P.pen[P_DISTANCE] * dist;                            // compressed:430
-  SC(S_NUM_ITER) = num_iter + 1;                                 // :394
-  SC(S_OUTCOME) = code;
 
   // A re-encode of an unchanged graph reproduces the cached embeddings bit for bit, so it is skipped: `dirty`
   // records whether any node feature, edge or node set changed since the last encode (successful outcomes mutate
@@ -396,7 +441,12 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const bool encode_now = reencode && dirty;
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
-  SC(S_FLAGS) = flags;
+  M.close();
+  {   // the hot sector goes back as one full 32-byte sector (num_iterations += 1 is :394)
+    const double ep = __hiloint2double(h1.w, h1.z) + reward;
+    reinterpret_cast<int4*>(scal)[0] = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
+    reinterpret_cast<int4*>(scal)[1] = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
+  }
   int cls = -1;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
     // three cost classes, claimed heaviest first: episode end (statistics + reset + encode + table), re-encode, edge only
@@ -407,7 +457,6 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     }
   }
   S.reward64[b] = reward;
-  S.ep_return[b] += reward;
   if (reward_out) reward_out[b] = (float)reward;
   if (done_out) done_out[b] = (done || trunc) ? 1 : 0;
   if (trunc_out) trunc_out[b] = trunc ? 1 : 0;

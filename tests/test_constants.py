@@ -53,9 +53,14 @@ def test_scalars_match_lib():
     from ccbs_b200 import lib as L
     s = _enum("Scalar")
     assert s["N_SCALARS"] == L.NUM_SCALARS
-    for name in ("S_SCENARIO", "S_STARTER", "S_STEPCOUNT", "S_NUM_ITER", "S_N_DISC", "S_N_OWNED", "S_DISC_AMOUNT",
-                 "S_EPISODES", "S_FLAGS", "S_OUTCOME", "S_N_SLOTS", "S_N_EDGES", "S_N_OWNED_RAW", "S_N_REIMAGED"):
-        assert s[name] == getattr(L, name)
+    names = [n for n in s if n.startswith("S_")]
+    assert len(names) == L.NUM_SCALARS
+    for name in names:
+        assert s[name] == getattr(L, name), name
+    # sector grouping the kernels rely on (transition.cuh): hot words 0-7, list lengths 8-15, episode constants 16-23
+    assert s["S_EP_RETURN"] % 2 == 0 and s["S_EP_RETURN_HI"] == s["S_EP_RETURN"] + 1 < 8
+    assert all(s[n] < 8 for n in ("S_FLAGS", "S_STEPCOUNT", "S_NUM_ITER", "S_TOTAL_STEPS", "S_OUTCOME", "S_SCST"))
+    assert all(8 <= s[n] < 16 for n in ("S_N_DISC", "S_N_OWNED", "S_DISC_AMOUNT", "S_N_OWNED_RAW", "S_N_REIMAGED"))
     assert _enum("Accum")["N_ACCUM"] == L.NUM_ACCUM == len(L.ACCUM_NAMES)
 
 
