@@ -211,6 +211,36 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
     for (int r = 0; r < t->num_rows; ++r) ru[r] = t->vi_ulocal[t->row_inst[r]];
     if ((rc = upload(h, &T.row_ulocal, ru.data(), ru.size()))) return rc;
   }
+  {   // derived: packed scenario / instance records and back-to-back Reconnaissance lists (cbs_types.h, Tables::sc_pack ..)
+    std::vector<int32_t> sp((size_t)S_ * 8, 0);
+    for (int s = 0; s < S_; ++s) {
+      int32_t* r = &sp[(size_t)s * 8];
+      r[0] = t->sc_num_nodes[s]; r[1] = t->sc_node_off[s]; r[2] = t->sc_num_uvuln[s]; r[3] = t->sc_port_off[s];
+      const int64_t io = t->sc_instof_off[s];
+      r[4] = (int32_t)(uint32_t)(io & 0xFFFFFFFFll); r[5] = (int32_t)(io >> 32);
+      r[6] = (h->cfg.goal >= GOAL_CONTROL_NODE) ? t->sc_interest[s] : -1;
+    }
+    if ((rc = upload(h, reinterpret_cast<const int32_t**>(&T.sc_pack), sp.data(), sp.size()))) return rc;
+    std::vector<uint32_t> vp((size_t)(I > 0 ? I : 1) * 8, 0u);
+    std::vector<uint8_t> rp;
+    for (int i = 0; i < I; ++i) {
+      uint32_t* r = &vp[(size_t)i * 8];
+      const int oa = t->vi_recon_any[2 * i], la = t->vi_recon_any[2 * i + 1];
+      const int orr = t->vi_recon_remote[2 * i], lr = t->vi_recon_remote[2 * i + 1];
+      if (la < 0 || la > CBS_MAX_NODES || lr < 0 || lr > CBS_MAX_NODES || (t->vi_flags[i] >> 8))
+        return fail(h, CBS_ERR_INVALID_ARG, "vulnerability instance %d: malformed flags / reconnaissance list", i);
+      r[0] = t->vi_flags[i] | ((uint32_t)la << 8) | ((uint32_t)lr << 16);
+      r[1] = (uint32_t)t->vi_kinds_any[i] | ((uint32_t)t->vi_kinds_remote[i] << 16);
+      r[2] = (uint32_t)t->vi_port[i];
+      r[3] = (uint32_t)rp.size();
+      rp.insert(rp.end(), t->recon_nodes + oa, t->recon_nodes + oa + la);
+      rp.insert(rp.end(), t->recon_nodes + orr, t->recon_nodes + orr + lr);
+      memcpy(&r[4], &t->vi_success[i], 8);
+      memcpy(&r[6], &t->vi_cost[i], 8);
+    }
+    if ((rc = upload(h, reinterpret_cast<const uint32_t**>(&T.vi_pack), vp.data(), vp.size()))) return rc;
+    if ((rc = upload(h, &T.recon_pack, rp.data(), rp.size()))) return rc;
+  }
   UP(vemb32, (size_t)t->num_global_vulns * VULN_EMB); UP(vemb64, (size_t)t->num_global_vulns * VULN_EMB);
   UP(vnorm2, t->num_global_vulns);
 #undef UP

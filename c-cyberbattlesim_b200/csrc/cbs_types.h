@@ -94,6 +94,12 @@ struct Tables {  // immutable, device pointers
   const double *vi_success, *vi_cost, *vemb64, *vnorm2;
   const uint8_t* recon_nodes;
   const float* vemb32;
+  // derived at load time for the transition (cbs_load_scenarios): one 32-byte record per scenario and per vulnerability
+  // instance, so that each look-up level of the transition is two 128-bit loads from one sector instead of 4-7 gathers
+  const int4* sc_pack;         // [S][2]  { num_nodes, node_off, num_uvuln, port_off } { instof_off lo, hi, interest node or -1, 0 }
+  const uint4* vi_pack;        // [I][2]  { vi_flags | len_any << 8 | len_remote << 16, kinds_any | kinds_remote << 16, port, recon offset }
+                               //         { success rate (float64), cost (float64) }
+  const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list directly followed by the "REMOTE only" one
   // GAE
   const float *node_static, *dyn_proj, *vuln_h, *nn0_b, *bn1_scale, *bn1_shift, *gcn_wt, *bn2_scale, *bn2_shift;
 };

@@ -292,7 +292,12 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       S.dist[b] = 0.0;
       if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
       if (dist_out) dist_out[b] = 0.0;
-      if (FUSE) transition_env<DEF, true, W1>(T, P, S, b, make_int4(0, 0, 0, 0), 0.0, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      if (FUSE) {
+        TransitionIn<W1> tin;
+        tin.issue(P, S, b, ft.uniforms);
+        tin.sl = make_int4(0, 0, 0, 0); tin.dist = 0.0;
+        transition_env<DEF, true, W1>(T, P, S, b, tin, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      }
     }
     sched_done(S, sched_buf);
     return;
@@ -456,7 +461,12 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
     }
     // fused step: the transition of this env runs here, on one lane, while the other warps are still scanning
-    if (FUSE) transition_env<DEF, true, W1>(T, P, S, b, out, d, ft.uniforms, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+    if (FUSE) {
+      TransitionIn<W1> tin;
+      tin.issue(P, S, b, ft.uniforms);
+      tin.sl = out; tin.dist = d;
+      transition_env<DEF, true, W1>(T, P, S, b, tin, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+    }
   }
   sched_done(S, sched_buf);
 }

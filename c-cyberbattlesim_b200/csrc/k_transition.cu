@@ -7,22 +7,31 @@ namespace cbs {
 
 constexpr int TR_THREADS = 128;
 
-// Appends every thread's env to one of NLISTS lists (`which` < 0: none) with ONE global atomic per list and CTA: positions
-// inside the CTA come from shared-memory counters, the CTA's range from a single atomicAdd on the list's counter.
-template <int NLISTS>
-__device__ __forceinline__ void cta_append(int which, int b, int32_t* __restrict__ counters, int32_t* __restrict__ lists,
-                                           int list_pitch, int cap, int32_t* errflag, int err, int* sh_cnt, int* sh_base) {
-  if (threadIdx.x < NLISTS) sh_cnt[threadIdx.x] = 0;
+// Appends every thread's env to one of the SCHED_BINS decode cost bins (`bin` < 0: none) and to one of the three observe
+// class lists (`cls` < 0: none) with ONE global atomic per list and CTA: positions inside the CTA come from shared-memory
+// counters, the CTA's range from a single atomicAdd on the list's counter.
+__device__ __forceinline__ void cta_append2(int bin, int cls, int b, int32_t* __restrict__ bin_cnt, int32_t* __restrict__ bin_list,
+                                            int32_t* __restrict__ cls_cnt, int32_t* __restrict__ cls_list, int cap, int32_t* errflag,
+                                            int* sh_cnt, int* sh_base) {
+  constexpr int NL = SCHED_BINS + 3;
+  if (threadIdx.x < NL) sh_cnt[threadIdx.x] = 0;
   __syncthreads();
-  int pos = 0;
-  if (which >= 0) pos = atomicAdd(&sh_cnt[which], 1);
+  int pos_bin = 0, pos_cls = 0;
+  if (bin >= 0) pos_bin = atomicAdd(&sh_cnt[bin], 1);
+  if (cls >= 0) pos_cls = atomicAdd(&sh_cnt[SCHED_BINS + cls], 1);
   __syncthreads();
-  if (threadIdx.x < NLISTS) sh_base[threadIdx.x] = sh_cnt[threadIdx.x] ? atomicAdd(&counters[threadIdx.x], sh_cnt[threadIdx.x]) : 0;
+  if (threadIdx.x < NL && sh_cnt[threadIdx.x]) {
+    int32_t* ctr = threadIdx.x < SCHED_BINS ? &bin_cnt[threadIdx.x] : &cls_cnt[threadIdx.x - SCHED_BINS];
+    sh_base[threadIdx.x] = atomicAdd(ctr, sh_cnt[threadIdx.x]);
+  }
   __syncthreads();
-  if (which >= 0) {
-    const int slot = sh_base[which] + pos;
-    if (slot < cap) lists[(size_t)which * list_pitch + slot] = b;
-    else if (errflag) atomicExch(errflag, err);
+  if (bin >= 0) {
+    const int slot = sh_base[bin] + pos_bin;
+    if (slot < cap) bin_list[(size_t)bin * cap + slot] = b;
+  }
+  if (cls >= 0) {
+    const int slot = sh_base[SCHED_BINS + cls] + pos_cls;
+    if (slot < cap) cls_list[(size_t)cls * cap + slot] = b; else atomicExch(errflag, 4);
   }
 }
 
@@ -32,18 +41,26 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
                                                                 const float* __restrict__ uniforms, int sched_out,
                                                                 float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                                                                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
-  __shared__ int sh_cnt[SCHED_BINS], sh_base[SCHED_BINS];
+  __shared__ int sh_cnt[SCHED_BINS + 3], sh_base[SCHED_BINS + 3];
   const int b = blockIdx.x * TR_THREADS + threadIdx.x;
   const bool live = b < P.B;
-  // cost-binned env list for the next decode (longest tables first)
-  cta_append<SCHED_BINS>(live ? sched_bin(S.work_est[b]) : -1, b, S.bin_cnt + sched_out * (SCHED_BINS + 1),
-                         S.bin_list + (size_t)sched_out * SCHED_BINS * P.B, P.B, P.B, nullptr, 0, sh_cnt, sh_base);
+  // one burst: the env's hot scalar sector and mask record, the decoded action, distance, uniform, table-size estimate
+  TransitionIn<REG> in;
+  int west = 0;
+  if (live) {
+    in.issue(P, S, b, uniforms);
+    in.sl = reinterpret_cast<const int4*>(sel_in)[b];
+    in.dist = dist_in ? dist_in[b] : 0.0;
+    west = S.work_est[b];
+  }
   int cls = -1;
   if (live)
-    cls = transition_env<DEF, false, REG>(T, P, S, b, reinterpret_cast<const int4*>(sel_in)[b], dist_in ? dist_in[b] : 0.0, uniforms,
-                                     sched_out, reward_out, done_out, trunc_out, outcome_out);
-  // the observe kernel's three class lists
-  cta_append<3>(cls, b, S.work_ctr + 4, S.worklist, P.B, P.B, S.errflag, 4, sh_cnt, sh_base);
+    cls = transition_env<DEF, false, REG>(T, P, S, b, in, uniforms != nullptr, sel_in != S.sel, sched_out, reward_out, done_out,
+                                          trunc_out, outcome_out);
+  // cost-binned env list for the next decode (longest tables first) and the observe kernel's three class lists: the
+  // two appends share their barriers
+  cta_append2(live ? sched_bin(west) : -1, cls, b, S.bin_cnt + sched_out * (SCHED_BINS + 1),
+              S.bin_list + (size_t)sched_out * SCHED_BINS * P.B, S.work_ctr + 4, S.worklist, P.B, S.errflag, sh_cnt, sh_base);
 }
 
 cudaError_t launch_transition(const Tables& T, const Params& P, const State& S, const int32_t* sel, const double* dist,

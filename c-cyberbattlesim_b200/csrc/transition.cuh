@@ -150,26 +150,45 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
 
 }  // namespace
 
+// Everything a transition reads from the env's own records and the call's per-env inputs, requested in ONE burst before
+// anything is consumed (the loads are independent; issuing them on demand made the kernel a chain of ~10 dependent
+// round trips).  REG: one-word planes and no defender -> the mask record is staged in registers (EnvBitsReg).
+template <bool REG>
+struct TransitionIn {
+  int4 h0, h1;            // hot sector of the scalar record: flags, stepcount, num_iterations, total steps | outcome, S_SCST, return
+  typename std::conditional<REG, EnvBitsReg, EnvBits>::type M;
+  int4 sl;                // decoded action (source, target, vulnerability, outcome kind)
+  double dist;
+  float uniform;
+  __device__ __forceinline__ void issue(const Params& P, const State& S, int b, const float* __restrict__ uniforms) {
+    const int4* q = reinterpret_cast<const int4*>(S.scal + (size_t)b * SCAL_PITCH);
+    h0 = q[0]; h1 = q[1];
+    M.open(S.masks + (size_t)b * P.mpitch, P.words);
+    uniform = uniforms ? uniforms[b] : 0.f;
+  }
+};
+
 // DEF: a static defender is configured (compile-time, so the default kernels carry none of its code or registers)
 // ENQ: the function itself appends the env to the decode cost bins and to the observe worklist (one atomic each: the
 //      fused path, one lane per warp).  The thread-per-env kernel passes false and aggregates both per CTA — a million
 //      same-address atomics serialise in L2 and were 90 % of that kernel's time at large batch.
-// REG: one-word planes and no defender -> the mask record is staged in registers (EnvBitsReg).
-// The hot sector of the scalar record (flags, counters of the step, scenario / starter, episode return) is read with two
-// 128-bit loads up front and written back as one full 32-byte sector; episode constants (reachable-node counts) come
-// from the scenario tables, so sectors 2-3 of the record are never touched and sector 1 only when a list changes.
+// The hot sector of the scalar record is written back as one full 32-byte sector; episode constants (reachable-node
+// counts) come from the scenario tables, so sectors 2-3 of the record are never touched and sector 1 only when a list
+// changes.  Table look-ups go level by level (scenario record -> instance index / node values -> instance record ->
+// firewall word), every level's loads issued together and ahead of the validity chain that consumes them.
 // Returns the env's observe work class (0 episode end, 1 re-encode, 2 edge only) or -1.
 template <bool DEF, bool ENQ = true, bool REG = false>
-static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, int4 sl, double dist,
-                                            const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out,
+static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, TransitionIn<REG>& in,
+                                            bool have_uniform, bool write_sel, int sched_out, float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
   static_assert(!(DEF && REG), "the defender path works on the record in place");
   int32_t* scal = S.scal + (size_t)b * SCAL_PITCH;
   auto SC = [&](int plane) -> int32_t& { return scal[plane]; };   // sector 1 (list lengths / counters), on demand
-  const int4 h0 = reinterpret_cast<const int4*>(scal)[0], h1 = reinterpret_cast<const int4*>(scal)[1];
-  typename std::conditional<REG, EnvBitsReg, EnvBits>::type M;
-  M.open(S.masks + (size_t)b * P.mpitch, P.words);
+  const int4 h0 = in.h0, h1 = in.h1;
+  auto& M = in.M;
+  const int4 sl = in.sl;
+  const double dist = in.dist;
 
   int flags = h0.x;
   if (ENQ) sched_enqueue(S, P, b, sched_out);   // cost-binned env list for the next decode (longest tables first)
@@ -183,27 +202,43 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     return -1;
   }
 
-    const int s = sl.x, t = sl.y, u = sl.z, kind = sl.w;
-  reinterpret_cast<int4*>(S.sel)[b] = sl;
+  const int s = sl.x, t = sl.y, u = sl.z, kind = sl.w;
+  if (write_sel) reinterpret_cast<int4*>(S.sel)[b] = sl;   // what the observe kernel and the info record read
 
+  // ---- level 1: the scenario record ----
   const int sc = h1.y >> 8, starter = h1.y & 0xFF;        // S_SCST
-  const int N = T.sc_num_nodes[sc];
-  const int node_off = T.sc_node_off[sc];
+  const int4 sp0 = T.sc_pack[2 * sc], sp1 = T.sc_pack[2 * sc + 1];
+  const int N = sp0.x, node_off = sp0.y, U = sp0.z, port_off = sp0.w;
+  const int64_t instof_off = ((int64_t)(uint32_t)sp1.x) | ((int64_t)sp1.y << 32);
   const int stepcount = h0.y + 1;                         // :303
   const int num_iter = h0.z;
   const int total_steps = h0.w;
-  // reachable-node counts of (scenario, starter): what reset_env keeps in S_OWNABLE / S_DISCOVERABLE / S_DISRUPTABLE /
-  // S_PROP_NODES, fetched from the tables (L2) so that the record's constant sector stays untouched
+  const bool local = (s == t);                            // :307
+  const bool idx_ok = (s >= 0 && s < N && t >= 0 && t < N);
+  const int tt = idx_ok ? t : 0, ss = idx_ok ? s : 0;     // safe indices for the look-ups issued ahead of the checks
+  // ---- level 2: instance index, node values, reachable-node counts of (scenario, starter) — what reset_env keeps in
+  //      S_OWNABLE / S_DISCOVERABLE / S_DISRUPTABLE / S_PROP_NODES, fetched from the tables (L2) so that the record's
+  //      constant sector stays untouched ----
   const int bg = base_goal(P);
   const int32_t* reach_tab = bg == GOAL_CONTROL ? T.nd_ownable : (bg == GOAL_DISCOVERY ? T.nd_discoverable : T.nd_disruptable);
   const int reach = reach_tab[node_off + starter];
+  int inst = -1;
+  if (idx_ok && u >= 0 && u < U) inst = T.inst_of[instof_off + (int64_t)tt * U + u];
+  const int t_value = T.nd_value[node_off + tt];
+  const int t_laa = T.nd_level_at_access[node_off + tt];
+  const float uf = have_uniform ? in.uniform
+                                : philox_uniform(P.seed, (uint64_t)(P.global_env_offset + b), (uint32_t)total_steps, 0u);
+  // ---- level 3: the instance record (flags | list lengths, outcome kinds, port, recon offset | success rate, cost) ----
+  const int insti = inst >= 0 ? inst : 0;
+  const uint4 vp0 = T.vi_pack[2 * insti], vp1 = T.vi_pack[2 * insti + 1];
+  const uint32_t vf = vp0.x;
+  const int v_port = (int)vp0.z;
+  const double v_success = __hiloint2double((int)vp1.y, (int)vp1.x), v_cost = __hiloint2double((int)vp1.w, (int)vp1.z);
+  // ---- level 4: outgoing-firewall word of (port, source) ----
+  const uint32_t fw_out = T.outblock[(size_t)(port_off + v_port) * P.words + (ss >> 5)];
 
   double reward = 0.0;
   int code = -1;
-  const bool local = (s == t);                            // :307
-  const bool idx_ok = (s >= 0 && s < N && t >= 0 && t < N);
-  int inst = -1;
-  uint32_t vf = 0;
 
   // ---- validity chain (attacker_actions.py:109-197 remote, :363-416 local) ----
   if (!idx_ok || !M.get(M_OWNED, s)) {
@@ -214,34 +249,24 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     reward = P.pen[P_INVALID_ACTION]; code = OC_SRC_NOT_RUNNING;
   } else if (!local && (M.get(M_STOPPED, t) || (DEF && M.get(M_IMAGING, t)))) {
     reward = P.pen[P_INVALID_ACTION]; code = OC_TGT_NOT_RUNNING;
+  } else if (inst < 0) {
+    reward = P.pen[P_NO_VULN]; code = OC_NO_VULNERABILITY;
   } else {
-    const int U = T.sc_num_uvuln[sc];
-    if (u >= 0 && u < U) inst = T.inst_of[T.sc_instof_off[sc] + (int64_t)t * (U > 0 ? U : 1) + u];
-    if (inst < 0) {
-      reward = P.pen[P_NO_VULN]; code = OC_NO_VULNERABILITY;
-    } else {
-      vf = T.vi_flags[inst];
-      const int privreq = (vf >> VI_PRIVREQ_SHIFT) & 3;
-      const int level = M.get(M_PRIV_ROOT, t) ? 3 : (M.get(M_PRIV_USER, t) ? 1 : 0);
-      const uint32_t kinds = local ? T.vi_kinds_any[inst] : T.vi_kinds_remote[inst];
-      if (privreq && level < privreq) {
-        reward = P.pen[P_NO_PRIV]; code = OC_NO_PRIVILEGE;
-      } else if (kind < 0 || kind >= N_KINDS || !((kinds >> kind) & 1u)) {
-        reward = P.pen[P_INVALID_ACTION]; code = OC_OUTCOME_NOT_PRESENT;
-      } else if (!local && !(vf & VI_LISTENING)) {
-        reward = P.pen[P_UNOPEN_PORT]; code = OC_PORT_NOT_LISTENING;
-      } else if (!local && !M.get(M_EVASION, s) &&
-                 ((T.outblock[(size_t)(T.sc_port_off[sc] + T.vi_port[inst]) * P.words + (s >> 5)] >> (s & 31)) & 1u)) {
-        reward = P.pen[P_FW_LOCAL]; code = OC_FW_OUTGOING;
-      } else if (!local && !M.get(M_EVASION, t) && !(vf & VI_IN_ALLOWED)) {
-        reward = P.pen[P_FW_REMOTE]; code = OC_FW_INCOMING;
-      } else {
-        const float uf = uniforms ? uniforms[b]
-                                  : philox_uniform(P.seed, (uint64_t)(P.global_env_offset + b), (uint32_t)total_steps, 0u);
-        if ((double)uf >= T.vi_success[inst]) {            // :190 / :409
-          reward = P.pen[P_SUCCESS_FAILED]; code = OC_UNSUCCESSFUL;
-        }
-      }
+    const int privreq = (vf >> VI_PRIVREQ_SHIFT) & 3;
+    const int level = M.get(M_PRIV_ROOT, t) ? 3 : (M.get(M_PRIV_USER, t) ? 1 : 0);
+    const uint32_t kinds = local ? (vp0.y & 0xFFFFu) : (vp0.y >> 16);
+    if (privreq && level < privreq) {
+      reward = P.pen[P_NO_PRIV]; code = OC_NO_PRIVILEGE;
+    } else if (kind < 0 || kind >= N_KINDS || !((kinds >> kind) & 1u)) {
+      reward = P.pen[P_INVALID_ACTION]; code = OC_OUTCOME_NOT_PRESENT;
+    } else if (!local && !(vf & VI_LISTENING)) {
+      reward = P.pen[P_UNOPEN_PORT]; code = OC_PORT_NOT_LISTENING;
+    } else if (!local && !M.get(M_EVASION, s) && ((fw_out >> (s & 31)) & 1u)) {
+      reward = P.pen[P_FW_LOCAL]; code = OC_FW_OUTGOING;
+    } else if (!local && !M.get(M_EVASION, t) && !(vf & VI_IN_ALLOWED)) {
+      reward = P.pen[P_FW_REMOTE]; code = OC_FW_INCOMING;
+    } else if ((double)uf >= v_success) {                  // :190 / :409
+      reward = P.pen[P_SUCCESS_FAILED]; code = OC_UNSUCCESSFUL;
     }
   }
 
@@ -259,7 +284,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
         else { M.set(M_PERSISTENCE, t); total += P.rew[R_PERSISTENCE]; }
         break;
       case K_DOS:  // a stopped target never gets here (:127), a local DoS has no such test (:450)
-        M.set(M_STOPPED, t); total += P.rew[R_DOS] * (double)T.nd_value[node_off + t];
+        M.set(M_STOPPED, t); total += P.rew[R_DOS] * (double)t_value;
         break;
       case K_DISCOVERY:
         if (M.get(M_VISIBLE, t)) { reward = P.pen[P_ALREADY_VISIBLE]; code = OC_REPEATED; ok = false; }
@@ -274,12 +299,13 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
         else { M.set(M_EVASION, t); total += P.rew[R_EVASION]; }
         break;
       case K_RECON: {
-        const int32_t* rl = local ? T.vi_recon_any : T.vi_recon_remote;
-        const int off = rl[2 * inst], len = rl[2 * inst + 1];
+        // the instance's two Reconnaissance lists sit back to back in recon_pack: "any type" first, then "REMOTE only"
+        const int len_any = (vf >> 8) & 0xFF, len_remote = (vf >> 16) & 0xFF;
+        const int off = (int)vp0.w + (local ? 0 : len_any), len = local ? len_any : len_remote;
         int n_disc = SC(S_N_DISC), fresh = 0;
         uint8_t* order = S.disc_order + (size_t)b * P.ncap;
         for (int i = 0; i < len; ++i) {                     // :291-296 + cyberbattle_env.py:398-407
-          const int node = T.recon_nodes[off + i];
+          const int node = T.recon_pack[off + i];
           if (!M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
         }
         SC(S_N_DISC) = n_disc;
@@ -313,13 +339,13 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
             was_owned = ever && !M.get(M_OWN_STALE, t);
             M.set(M_EVER_OWNED, t); M.clr(M_OWN_STALE, t);
           }
-          const int laa = T.nd_level_at_access[node_off + t];
+          const int laa = t_laa;
           M.set(M_OWNED, t);
           if (laa >= 1) M.set(M_PRIV_USER, t);
           if (laa == 3) M.set(M_PRIV_ROOT, t);
           if (was_owned) { reward = P.pen[P_ALREADY_OWNED]; code = OC_REPEATED; ok = false; }
           else {
-            if (!ever) total += P.rew[R_VALUE] * (double)T.nd_value[node_off + t];   // :336-340 first ownership only
+            if (!ever) total += P.rew[R_VALUE] * (double)t_value;   // :336-340 first ownership only
             uint8_t* oo = S.owned_order + (size_t)b * P.ncap;   // cyberbattle_env.py:408-410
             int n_owned = SC(S_N_OWNED);
             if (DEF) {        // owned_nodes.append(t): the exact list may now hold t twice
@@ -341,7 +367,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
         break;
     }
     if (ok) {
-      total -= P.rew[R_COST] * T.vi_cost[inst];             // :348 / :544
+      total -= P.rew[R_COST] * v_cost;             // :348 / :544
       reward = total;
       code = kind;
       if (kind == K_COLLECTION || kind == K_EXFILTRATION || kind == K_DISCOVERY) SC(S_DISC_AMOUNT) += 1;  // env:411-412
@@ -349,7 +375,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   }
 
   // ---- node-specific games: the reward is zeroed once the interest node is discovered and not targeted (:322-326) ----
-  const int interest = is_node_goal(P) ? T.sc_interest[sc] : -1;
+  const int interest = is_node_goal(P) ? sp1.z : -1;
   if (interest >= 0 && t != interest && M.get(M_DISCOVERED, interest)) reward = 0.0;
 
   // ---- static defender (cyberbattle_env.py:331-332), then the cached-feature rule of the visible graph: the target's
