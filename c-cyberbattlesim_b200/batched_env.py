@@ -75,8 +75,10 @@ class BatchedCyberBattleEnv:
             self.truncated = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.outcome = torch.zeros(B, dtype=torch.uint8, device=self.device)
             self.info = torch.zeros(B, 8, dtype=torch.int32, device=self.device)
-            self.sel = torch.zeros(B, 4, dtype=torch.int32, device=self.device)
-            self.dist = torch.zeros(B, dtype=torch.float64, device=self.device)
+            # zero-copy views of the library's decode result: decode() writes them, transition(self.sel, self.dist)
+            # reads them in place (no copy of the selection on either side)
+            self.sel = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_SEL), (B, 4), torch.int32, self.device, self)
+            self.dist = _tensor_from_ptr(self.lib.cbs_state_ptr(self._h, L.F_DIST), (B,), torch.float64, self.device, self)
 
     # ------------------------------------------------------------------------------------------
     def _check(self, rc):
@@ -145,11 +147,12 @@ class BatchedCyberBattleEnv:
 
     def decode(self, actions: torch.Tensor):
         actions = self._actions(actions)
-        self._check(self.lib.cbs_decode(self._h, self._p(actions), self._p(self.sel), self._p(self.dist), self._stream()))
+        self._check(self.lib.cbs_decode(self._h, self._p(actions), None, None, self._stream()))
         return self.sel, self.dist
 
     def transition(self, sel: torch.Tensor, dist: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None):
-        sel = sel.to(device=self.device, dtype=torch.int32).contiguous()
+        if sel is not self.sel:
+            sel = sel.to(device=self.device, dtype=torch.int32).contiguous()
         if dist is not None:
             dist = dist.to(device=self.device, dtype=torch.float64).contiguous()
         uniforms = self._uniforms(uniforms)
@@ -221,8 +224,9 @@ class BatchedCyberBattleEnv:
         return np.ascontiguousarray(raw[:, :C.N_MASKS * w].reshape(self.num_envs, C.N_MASKS, w).transpose(1, 2, 0))
 
     def scalars(self) -> np.ndarray:
-        raw = self.read(L.F_SCALARS, np.int32, (self.num_envs, self._scalar_pitch))  # env-major records on the device
-        return np.ascontiguousarray(raw[:, :L.NUM_SCALARS].T)
+        """int32[NUM_SCALARS, B], indexed by lib.S_*"""
+        raw = self.read(L.F_SCALARS, np.int32, (self._scalar_pitch // 8, self.num_envs, 8))   # sector-major on the device
+        return np.ascontiguousarray(raw.transpose(0, 2, 1).reshape(self._scalar_pitch, self.num_envs)[:L.NUM_SCALARS])
 
     def disc_order(self) -> np.ndarray:
         return self.read(L.F_DISC_ORDER, np.uint8, (self.num_envs, self.ncap))

@@ -22,7 +22,7 @@ __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
-  const int32_t* sc = S.scal + (size_t)b * SCAL_PITCH;
+  const int32_t* sc = S.scal + (size_t)b * 8;   // sector 0
   const int flags = sc[S_FLAGS];
   int32_t* o = info + (size_t)b * CBS_INFO_INTS;
   o[0] = sl.x; o[1] = sl.y; o[2] = sl.z; o[3] = sl.w;
@@ -34,7 +34,7 @@ __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
 
 __global__ void init_flags_kernel(int32_t* scal, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) scal[(size_t)b * SCAL_PITCH + S_FLAGS] = FL_NEEDS_RESET;
+  if (b < B) scal[(size_t)b * 8 + S_FLAGS] = FL_NEEDS_RESET;   // sector 0
 }
 }  // namespace cbs
 
@@ -109,6 +109,17 @@ static int upload(cbs_handle* h, const Tp** out, const Tp* src, size_t count) {
   }
   *out = p;
   return 0;
+}
+
+// vi_port is scenario-local: the first port of the scenario each vulnerability instance belongs to, found through
+// inst_of (inst_of[sc_instof_off[s] .. sc_instof_off[s+1]) lists the instances of scenario s, or -1)
+static std::vector<int32_t> instance_port_offsets(const cbs_scenario_tables* t) {
+  // inst_of[sc_instof_off[s] .. sc_instof_off[s+1]) holds the instances of scenario s (or -1)
+  std::vector<int32_t> off((size_t)(t->num_inst > 0 ? t->num_inst : 1), 0);
+  for (int s = 0; s < t->num_scenarios; ++s)
+    for (int64_t k = t->sc_instof_off[s]; k < t->sc_instof_off[s + 1]; ++k)
+      if (t->inst_of[k] >= 0) off[t->inst_of[k]] = t->sc_port_off[s];
+  return off;
 }
 
 extern "C" {
@@ -222,6 +233,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
     }
     if ((rc = upload(h, reinterpret_cast<const int32_t**>(&T.sc_pack), sp.data(), sp.size()))) return rc;
     std::vector<uint32_t> vp((size_t)(I > 0 ? I : 1) * 8, 0u);
+    const std::vector<int32_t> inst_port_off = instance_port_offsets(t);
     std::vector<uint8_t> rp;
     for (int i = 0; i < I; ++i) {
       uint32_t* r = &vp[(size_t)i * 8];
@@ -231,7 +243,8 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
         return fail(h, CBS_ERR_INVALID_ARG, "vulnerability instance %d: malformed flags / reconnaissance list", i);
       r[0] = t->vi_flags[i] | ((uint32_t)la << 8) | ((uint32_t)lr << 16);
       r[1] = (uint32_t)t->vi_kinds_any[i] | ((uint32_t)t->vi_kinds_remote[i] << 16);
-      r[2] = (uint32_t)t->vi_port[i];
+      // the port's outgoing-firewall node mask itself when a plane is one word, else the port index into `outblock`
+      r[2] = t->words == 1 ? t->outblock[(size_t)(inst_port_off[i] + t->vi_port[i])] : (uint32_t)t->vi_port[i];
       r[3] = (uint32_t)rp.size();
       rp.insert(rp.end(), t->recon_nodes + oa, t->recon_nodes + oa + la);
       rp.insert(rp.end(), t->recon_nodes + orr, t->recon_nodes + orr + lr);
@@ -311,9 +324,9 @@ int cbs_set_scenarios(cbs_handle* h, const int32_t* sc_host) {
   for (int b = 0; b < h->P.B; ++b)
     if (sc_host[b] < 0 || sc_host[b] >= h->T.num_scenarios) return fail(h, CBS_ERR_INVALID_ARG, "scenario id %d out of range (env %d)", sc_host[b], b);
   CK(h, cudaSetDevice(h->cfg.device));
-  // one int32 per env into the env-major scalar records
-  CK(h, cudaMemcpy2D(h->S.scal + S_SCENARIO, SCAL_PITCH * sizeof(int32_t), sc_host, sizeof(int32_t), sizeof(int32_t), h->P.B,
-                     cudaMemcpyHostToDevice));
+  // one int32 per env into the sector that holds S_SCENARIO (State::scal is [sector][B][8])
+  CK(h, cudaMemcpy2D(h->S.scal + ((size_t)(S_SCENARIO >> 3) * h->P.B) * 8 + (S_SCENARIO & 7), 8 * sizeof(int32_t), sc_host,
+                     sizeof(int32_t), sizeof(int32_t), h->P.B, cudaMemcpyHostToDevice));
   return CBS_OK;
 }
 
@@ -521,6 +534,7 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_DIST: *p = S.dist; *bytes = B * 8; break;
     case CBS_F_REWARD64: *p = S.reward64; *bytes = B * 8; break;
     case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
+    case CBS_F_SEL: *p = S.sel; *bytes = B * 16; break;
     case CBS_F_VT: *p = S.vt; *bytes = B * h->vt_stride * 4; break;
     default: return fail(h, CBS_ERR_INVALID_ARG, "unknown state field %d", field);
   }

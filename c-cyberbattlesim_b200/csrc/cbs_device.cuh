@@ -10,8 +10,9 @@ __device__ __forceinline__ uint32_t ld_mask(const State& S, const Params& P, int
 __device__ __forceinline__ bool bit_of(const State& S, const Params& P, int plane, int node, int b) {
   return (ld_mask(S, P, plane, node >> 5, b) >> (node & 31)) & 1u;
 }
+// scalar `plane` of env b: sector-major arrays, State::scal[sector][B][8]
 __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int plane, int b) {
-  return S.scal[(size_t)b * SCAL_PITCH + plane];
+  return S.scal[((size_t)(plane >> 3) * P.B + b) * 8 + (plane & 7)];
 }
 
 __device__ __forceinline__ bool is_node_goal(const Params& P) { return P.goal >= GOAL_CONTROL_NODE; }

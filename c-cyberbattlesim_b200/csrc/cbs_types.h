@@ -20,7 +20,7 @@ constexpr int MAX_NODES = 128;
 #ifndef CBS_OBS_SMEM_NODES
 #define CBS_OBS_SMEM_NODES 32   // visible graphs up to this many nodes keep their embeddings in shared memory (k_observe.cu)
 #endif
-constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: one 128-byte line per env
+constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: four sectors of 8 words
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 
 // outcome kinds (simulation/model.py:66-193)
@@ -48,9 +48,10 @@ enum Penalty : int { P_NO_VULN = 0, P_NO_PRIV, P_SUCCESS_FAILED, P_NO_DATA_COLLE
                      P_ALREADY_STOPPED, P_ALREADY_OWNED, P_ALREADY_VISIBLE, P_ALREADY_EVASION, P_UNOPEN_PORT,
                      P_PRIVESC_NOT_OWNED, P_PRIVESC_ALREADY, P_OUTCOME_NOT_VALID, P_FW_LOCAL, P_FW_REMOTE,
                      P_INVALID_ACTION, P_DISTANCE, N_PENALTIES };
-// per-env int32 scalar record: one 128-byte line per env, grouped by 32-byte sector so that a kernel touches (and
-// writes back) only the sectors it needs.  The transition reads and rewrites sector 0 on every step, touches sector 1 only
-// for outcomes that change a list, and never reads sectors 2-3 (episode constants come from the tables via S_SCST).
+// per-env int32 scalars, grouped into four 32-byte sectors per env; each sector is its own dense array
+// (State::scal[sector][B][8]) so that a kernel streams only the sectors it needs.  The transition reads and rewrites
+// sector 0 on every step, touches sector 1 only for outcomes that change a list, and never reads sectors 2-3 (episode
+// constants come from the tables via S_SCST).
 enum Scalar : int {
   // sector 0 — rewritten by every transition
   S_FLAGS = 0, S_STEPCOUNT, S_NUM_ITER, S_TOTAL_STEPS, S_OUTCOME,
@@ -97,7 +98,8 @@ struct Tables {  // immutable, device pointers
   // derived at load time for the transition (cbs_load_scenarios): one 32-byte record per scenario and per vulnerability
   // instance, so that each look-up level of the transition is two 128-bit loads from one sector instead of 4-7 gathers
   const int4* sc_pack;         // [S][2]  { num_nodes, node_off, num_uvuln, port_off } { instof_off lo, hi, interest node or -1, 0 }
-  const uint4* vi_pack;        // [I][2]  { vi_flags | len_any << 8 | len_remote << 16, kinds_any | kinds_remote << 16, port, recon offset }
+  const uint4* vi_pack;        // [I][2]  { vi_flags | len_any << 8 | len_remote << 16, kinds_any | kinds_remote << 16,
+                               //           port (words > 1) or the port's outgoing-firewall node mask itself (words == 1), recon offset }
                                //         { success rate (float64), cost (float64) }
   const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list directly followed by the "REMOTE only" one
   // GAE
@@ -124,10 +126,10 @@ struct Params {  // configuration, by value
 };
 
 struct State {  // mutable, device pointers
-  // Per-env records, env-major: every kernel on the step path handles an env with one warp (or one lane), so the env's
-  // few dozen words must share cache lines; plane-major SoA put each of them in a different 32-byte sector.
+  // Per-env records: every kernel on the step path handles an env with one warp (or one lane / thread), so the env's few
+  // dozen words must share 32-byte sectors; plane-major SoA put each of them in a different sector.
   uint32_t* masks;       // [B][mpitch]  plane p, word w at p * words + w
-  int32_t* scal;         // [B][SCAL_PITCH]
+  int32_t* scal;         // [4][B][8]  sector-major (enum Scalar: sector = plane >> 3)
   uint8_t* disc_order;   // [B][ncap]
   uint8_t* owned_order;  // [B][ncap]
   uint8_t* pair_slot;    // [B][ncap*ncap]   0xFF = pair not in the action table

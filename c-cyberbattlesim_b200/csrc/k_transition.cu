@@ -6,6 +6,7 @@
 namespace cbs {
 
 constexpr int TR_THREADS = 128;
+constexpr int TR_SC_SMEM = 64;   // scenario records kept in shared memory (larger sets are read through L2)
 
 // Appends every thread's env to one of the SCHED_BINS decode cost bins (`bin` < 0: none) and to one of the three observe
 // class lists (`cls` < 0: none) with ONE global atomic per list and CTA: positions inside the CTA come from shared-memory
@@ -42,6 +43,7 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
                                                                 float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                                                                 uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
   __shared__ int sh_cnt[SCHED_BINS + 3], sh_base[SCHED_BINS + 3];
+  __shared__ int4 sh_sc[2 * TR_SC_SMEM];
   const int b = blockIdx.x * TR_THREADS + threadIdx.x;
   const bool live = b < P.B;
   // one burst: the env's hot scalar sector and mask record, the decoded action, distance, uniform, table-size estimate
@@ -53,10 +55,16 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
     in.dist = dist_in ? dist_in[b] : 0.0;
     west = S.work_est[b];
   }
+  // the scenario records (32 bytes each) go to shared memory while that burst is in flight: one look-up level less
+  const bool sc_smem = T.num_scenarios <= TR_SC_SMEM;
+  if (sc_smem) {
+    for (int i = threadIdx.x; i < 2 * T.num_scenarios; i += TR_THREADS) sh_sc[i] = T.sc_pack[i];
+    __syncthreads();
+  }
   int cls = -1;
   if (live)
-    cls = transition_env<DEF, false, REG>(T, P, S, b, in, uniforms != nullptr, sel_in != S.sel, sched_out, reward_out, done_out,
-                                          trunc_out, outcome_out);
+    cls = transition_env<DEF, false, REG>(T, P, S, b, in, sc_smem ? sh_sc : T.sc_pack, uniforms != nullptr, sel_in != S.sel, sched_out,
+                                          reward_out, done_out, trunc_out, outcome_out);
   // cost-binned env list for the next decode (longest tables first) and the observe kernel's three class lists: the
   // two appends share their barriers
   cta_append2(live ? sched_bin(west) : -1, cls, b, S.bin_cnt + sched_out * (SCHED_BINS + 1),

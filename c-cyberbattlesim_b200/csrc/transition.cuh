@@ -161,7 +161,7 @@ struct TransitionIn {
   double dist;
   float uniform;
   __device__ __forceinline__ void issue(const Params& P, const State& S, int b, const float* __restrict__ uniforms) {
-    const int4* q = reinterpret_cast<const int4*>(S.scal + (size_t)b * SCAL_PITCH);
+    const int4* q = reinterpret_cast<const int4*>(S.scal + (size_t)b * 8);      // sector 0
     h0 = q[0]; h1 = q[1];
     M.open(S.masks + (size_t)b * P.mpitch, P.words);
     uniform = uniforms ? uniforms[b] : 0.f;
@@ -179,12 +179,14 @@ struct TransitionIn {
 // Returns the env's observe work class (0 episode end, 1 re-encode, 2 edge only) or -1.
 template <bool DEF, bool ENQ = true, bool REG = false>
 static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, TransitionIn<REG>& in,
-                                            bool have_uniform, bool write_sel, int sched_out, float* __restrict__ reward_out,
+                                            const int4* __restrict__ sc_pack, bool have_uniform, bool write_sel, int sched_out,
+                                            float* __restrict__ reward_out,
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
   static_assert(!(DEF && REG), "the defender path works on the record in place");
-  int32_t* scal = S.scal + (size_t)b * SCAL_PITCH;
-  auto SC = [&](int plane) -> int32_t& { return scal[plane]; };   // sector 1 (list lengths / counters), on demand
+  int32_t* hot = S.scal + (size_t)b * 8;                           // sector 0
+  int32_t* cnt = S.scal + ((size_t)P.B + b) * 8;                   // sector 1 (list lengths / counters), on demand
+  auto SC = [&](int plane) -> int32_t& { return cnt[plane - 8]; };
   const int4 h0 = in.h0, h1 = in.h1;
   auto& M = in.M;
   const int4 sl = in.sl;
@@ -198,7 +200,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     if (done_out) done_out[b] = 1;
     if (trunc_out) trunc_out[b] = (flags & FL_TRUNC) ? 1 : 0;
     if (outcome_out) outcome_out[b] = OC_INVALID_SRC_NOT_OWNED;
-    SC(S_FLAGS) = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+    hot[S_FLAGS] = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
     return -1;
   }
 
@@ -207,7 +209,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
 
   // ---- level 1: the scenario record ----
   const int sc = h1.y >> 8, starter = h1.y & 0xFF;        // S_SCST
-  const int4 sp0 = T.sc_pack[2 * sc], sp1 = T.sc_pack[2 * sc + 1];
+  const int4 sp0 = sc_pack[2 * sc], sp1 = sc_pack[2 * sc + 1];
   const int N = sp0.x, node_off = sp0.y, U = sp0.z, port_off = sp0.w;
   const int64_t instof_off = ((int64_t)(uint32_t)sp1.x) | ((int64_t)sp1.y << 32);
   const int stepcount = h0.y + 1;                         // :303
@@ -232,10 +234,9 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const int insti = inst >= 0 ? inst : 0;
   const uint4 vp0 = T.vi_pack[2 * insti], vp1 = T.vi_pack[2 * insti + 1];
   const uint32_t vf = vp0.x;
-  const int v_port = (int)vp0.z;
   const double v_success = __hiloint2double((int)vp1.y, (int)vp1.x), v_cost = __hiloint2double((int)vp1.w, (int)vp1.z);
-  // ---- level 4: outgoing-firewall word of (port, source) ----
-  const uint32_t fw_out = T.outblock[(size_t)(port_off + v_port) * P.words + (ss >> 5)];
+  // ---- outgoing-firewall word of (port, source): with one-word planes the instance record carries it ----
+  const uint32_t fw_out = P.words == 1 ? vp0.z : T.outblock[(size_t)(port_off + (int)vp0.z) * P.words + (ss >> 5)];
 
   double reward = 0.0;
   int code = -1;
@@ -470,8 +471,8 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   M.close();
   {   // the hot sector goes back as one full 32-byte sector (num_iterations += 1 is :394)
     const double ep = __hiloint2double(h1.w, h1.z) + reward;
-    reinterpret_cast<int4*>(scal)[0] = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
-    reinterpret_cast<int4*>(scal)[1] = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
+    reinterpret_cast<int4*>(hot)[0] = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
+    reinterpret_cast<int4*>(hot)[1] = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
   }
   int cls = -1;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs

@@ -226,7 +226,7 @@ typedef enum {
   CBS_F_MASKS = 0,        /* uint32 [B][mask_pitch]: plane p, word w of env b at b * mask_pitch + p * words + w */
   CBS_F_DISC_ORDER = 1,   /* uint8 [B][max_nodes] */
   CBS_F_OWNED_ORDER = 2,  /* uint8 [B][max_nodes] every node that entered env.owned_nodes, in first-entry order */
-  CBS_F_SCALARS = 3,      /* int32 [B][scalar_pitch], the first CBS_NUM_SCALARS entries of a record are used */
+  CBS_F_SCALARS = 3,      /* int32 [scalar_pitch / 8][B][8]: sector-major; scalar k of env b at ((k >> 3) * B + b) * 8 + (k & 7) */
   CBS_F_TERMINAL_OBS = 4, /* float32 [B][194] */
   CBS_F_OBS = 5,          /* float32 [B][194] cached observation */
   CBS_F_LAST_STATS = 6,   /* float64 [B][14] get_statistics() of the last finished episode */
@@ -238,10 +238,12 @@ typedef enum {
   CBS_F_VT = 12,          /* float32 [B][vt_stride] action x vulnerability-embedding products of the last decode */
   CBS_F_OWNED_RAW = 13,   /* uint8 [B][2*max_nodes] env.owned_nodes as the reference holds it under a defender (removals, duplicates) */
   CBS_F_REIMAGE_LEFT = 14,/* uint8 [B][max_nodes] node_reimaging_progress of nodes whose Imaging bit is set */
-  CBS_F_Z_HIST = 15       /* float32 [B][slots][max_nodes][64] node-embedding snapshots the action-table rows refer to (cbs_capacities: slots) */
+  CBS_F_Z_HIST = 15,      /* float32 [B][slots][max_nodes][64] node-embedding snapshots the action-table rows refer to (cbs_capacities: slots) */
+  CBS_F_SEL = 16          /* int32 [B][4] last decoded / applied action (source, target, vulnerability, outcome kind); a caller that
+                             hands this very buffer to cbs_transition saves the copy */
 } cbs_field;
 #define CBS_NUM_MASKS 15
-#define CBS_NUM_SCALARS 22
+#define CBS_NUM_SCALARS 25
 #define CBS_NUM_ACCUM 20
 /* synchronous device->host copy of one state field; bytes must equal the field size (query with dst NULL). */
 int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes);
