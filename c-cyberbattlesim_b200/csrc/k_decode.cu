@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
         tin.issue(P, S, b, ft.uniforms);
         tin.sl = make_int4(0, 0, 0, 0); tin.dist = 0.0;
         transition_env<DEF, true, W1>(T, P, S, b, tin, T.sc_pack, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+        tin.store_hot(S, b);
       }
     }
     sched_done(S, sched_buf);
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Pa
       tin.issue(P, S, b, ft.uniforms);
       tin.sl = out; tin.dist = d;
       transition_env<DEF, true, W1>(T, P, S, b, tin, T.sc_pack, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      tin.store_hot(S, b);
     }
   }
   sched_done(S, sched_buf);

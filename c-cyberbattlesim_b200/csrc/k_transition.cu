@@ -5,7 +5,13 @@
 
 namespace cbs {
 
-constexpr int TR_THREADS = 128;
+#ifndef CBS_TR_THREADS
+#define CBS_TR_THREADS 128
+#endif
+#ifndef CBS_TR_MINB
+#define CBS_TR_MINB 7
+#endif
+constexpr int TR_THREADS = CBS_TR_THREADS;
 constexpr int TR_SC_SMEM = 64;   // scenario records kept in shared memory (larger sets are read through L2)
 
 // Appends every thread's env to one of the SCHED_BINS decode cost bins (`bin` < 0: none) and to one of the three observe
@@ -36,17 +42,20 @@ __device__ __forceinline__ void cta_append2(int bin, int cls, int b, int32_t* __
   }
 }
 
+// One CTA = TR_THREADS consecutive envs, one thread per env.  Every thread requests its env's hot scalar sector, mask
+// record, decoded action, distance, uniform and table-size estimate in one burst (TransitionIn::issue); measured with the
+// transition logic knocked out, these per-thread record loads already stream at the HBM copy peak (27.6 us per 1M envs),
+// so staging them through shared memory with 1-D bulk copies (tried: 99 us against 90 us) buys nothing — the kernel's
+// time is the divergent per-env logic and its chain of L2 table look-ups.
 template <bool DEF, bool REG>
-__global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_in,
-                                                                const double* __restrict__ dist_in,
-                                                                const float* __restrict__ uniforms, int sched_out,
-                                                                float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
-                                                                uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
+__global__ void __launch_bounds__(TR_THREADS, DEF ? 1 : CBS_TR_MINB)
+transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_in, const double* __restrict__ dist_in,
+                  const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
+                  uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
   __shared__ int sh_cnt[SCHED_BINS + 3], sh_base[SCHED_BINS + 3];
   __shared__ int4 sh_sc[2 * TR_SC_SMEM];
   const int b = blockIdx.x * TR_THREADS + threadIdx.x;
   const bool live = b < P.B;
-  // one burst: the env's hot scalar sector and mask record, the decoded action, distance, uniform, table-size estimate
   TransitionIn<REG> in;
   int west = 0;
   if (live) {
@@ -62,9 +71,11 @@ __global__ void __launch_bounds__(TR_THREADS) transition_kernel(Tables T, Params
     __syncthreads();
   }
   int cls = -1;
-  if (live)
+  if (live) {
     cls = transition_env<DEF, false, REG>(T, P, S, b, in, sc_smem ? sh_sc : T.sc_pack, uniforms != nullptr, sel_in != S.sel, sched_out,
                                           reward_out, done_out, trunc_out, outcome_out);
+    in.store_hot(S, b);
+  }
   // cost-binned env list for the next decode (longest tables first) and the observe kernel's three class lists: the
   // two appends share their barriers
   cta_append2(live ? sched_bin(west) : -1, cls, b, S.bin_cnt + sched_out * (SCHED_BINS + 1),

@@ -156,6 +156,8 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
 template <bool REG>
 struct TransitionIn {
   int4 h0, h1;            // hot sector of the scalar record: flags, stepcount, num_iterations, total steps | outcome, S_SCST, return
+  int4 c0;                // first half of sector 1: n_disc, n_owned, disc_amount, n_owned_raw — needed by a third of the outcomes
+                          // only, but fetched with the burst: on demand it is one more exposed DRAM round trip
   typename std::conditional<REG, EnvBitsReg, EnvBits>::type M;
   int4 sl;                // decoded action (source, target, vulnerability, outcome kind)
   double dist;
@@ -163,8 +165,13 @@ struct TransitionIn {
   __device__ __forceinline__ void issue(const Params& P, const State& S, int b, const float* __restrict__ uniforms) {
     const int4* q = reinterpret_cast<const int4*>(S.scal + (size_t)b * 8);      // sector 0
     h0 = q[0]; h1 = q[1];
+    c0 = *reinterpret_cast<const int4*>(S.scal + ((size_t)P.B + b) * 8);
     M.open(S.masks + (size_t)b * P.mpitch, P.words);
     uniform = uniforms ? uniforms[b] : 0.f;
+  }
+  __device__ __forceinline__ void store_hot(const State& S, int b) const {
+    int4* q = reinterpret_cast<int4*>(S.scal + (size_t)b * 8);
+    q[0] = h0; q[1] = h1;
   }
 };
 
@@ -172,7 +179,8 @@ struct TransitionIn {
 // ENQ: the function itself appends the env to the decode cost bins and to the observe worklist (one atomic each: the
 //      fused path, one lane per warp).  The thread-per-env kernel passes false and aggregates both per CTA — a million
 //      same-address atomics serialise in L2 and were 90 % of that kernel's time at large batch.
-// The hot sector of the scalar record is written back as one full 32-byte sector; episode constants (reachable-node
+// The new hot sector of the scalar record comes back in `in.h0 / in.h1` and the caller stores it as one full 32-byte
+// sector (TransitionIn::store_hot); episode constants (reachable-node
 // counts) come from the scenario tables, so sectors 2-3 of the record are never touched and sector 1 only when a list
 // changes.  Table look-ups go level by level (scenario record -> instance index / node values -> instance record ->
 // firewall word), every level's loads issued together and ahead of the validity chain that consumes them.
@@ -184,9 +192,11 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
                                             uint8_t* __restrict__ done_out, uint8_t* __restrict__ trunc_out,
                                             uint8_t* __restrict__ outcome_out) {
   static_assert(!(DEF && REG), "the defender path works on the record in place");
-  int32_t* hot = S.scal + (size_t)b * 8;                           // sector 0
   int32_t* cnt = S.scal + ((size_t)P.B + b) * 8;                   // sector 1 (list lengths / counters), on demand
   auto SC = [&](int plane) -> int32_t& { return cnt[plane - 8]; };
+  // working copies of the list lengths (without a defender nothing else writes them during the step; the defender path
+  // works on the words in place through DefenderCtx)
+  int n_disc_w = in.c0.x, n_owned_w = in.c0.y, disc_amount_w = in.c0.z;
   const int4 h0 = in.h0, h1 = in.h1;
   auto& M = in.M;
   const int4 sl = in.sl;
@@ -200,7 +210,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     if (done_out) done_out[b] = 1;
     if (trunc_out) trunc_out[b] = (flags & FL_TRUNC) ? 1 : 0;
     if (outcome_out) outcome_out[b] = OC_INVALID_SRC_NOT_OWNED;
-    hot[S_FLAGS] = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+    in.h0.x = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
     return -1;
   }
 
@@ -303,14 +313,14 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
         // the instance's two Reconnaissance lists sit back to back in recon_pack: "any type" first, then "REMOTE only"
         const int len_any = (vf >> 8) & 0xFF, len_remote = (vf >> 16) & 0xFF;
         const int off = (int)vp0.w + (local ? 0 : len_any), len = local ? len_any : len_remote;
-        int n_disc = SC(S_N_DISC), fresh = 0;
+        int n_disc = DEF ? SC(S_N_DISC) : n_disc_w, fresh = 0;
         uint8_t* order = S.disc_order + (size_t)b * P.ncap;
         for (int i = 0; i < len; ++i) {                     // :291-296 + cyberbattle_env.py:398-407
           const int node = T.recon_pack[off + i];
           if (!M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
         }
-        SC(S_N_DISC) = n_disc;
-        SC(S_DISC_AMOUNT) += fresh;
+        if (DEF) { SC(S_N_DISC) = n_disc; SC(S_DISC_AMOUNT) += fresh; }
+        else { n_disc_w = n_disc; disc_amount_w += fresh; }
         total += P.rew[R_NODE_DISCOVERED] * (double)fresh;
         break;
       }
@@ -348,7 +358,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
           else {
             if (!ever) total += P.rew[R_VALUE] * (double)t_value;   // :336-340 first ownership only
             uint8_t* oo = S.owned_order + (size_t)b * P.ncap;   // cyberbattle_env.py:408-410
-            int n_owned = SC(S_N_OWNED);
+            int n_owned = DEF ? SC(S_N_OWNED) : n_owned_w;
             if (DEF) {        // owned_nodes.append(t): the exact list may now hold t twice
               uint8_t* raw = S.owned_raw + (size_t)b * P.ocap;
               const int n_raw = SC(S_N_OWNED_RAW);
@@ -358,7 +368,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
               if (k == n_owned) { oo[n_owned] = (uint8_t)t; SC(S_N_OWNED) = n_owned + 1; }
             } else {
               oo[n_owned] = (uint8_t)t;
-              SC(S_N_OWNED) = n_owned + 1;
+              n_owned_w = n_owned + 1;
             }
           }
         }
@@ -371,7 +381,9 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
       total -= P.rew[R_COST] * v_cost;             // :348 / :544
       reward = total;
       code = kind;
-      if (kind == K_COLLECTION || kind == K_EXFILTRATION || kind == K_DISCOVERY) SC(S_DISC_AMOUNT) += 1;  // env:411-412
+      if (kind == K_COLLECTION || kind == K_EXFILTRATION || kind == K_DISCOVERY) {                      // env:411-412
+        if (DEF) SC(S_DISC_AMOUNT) += 1; else disc_amount_w += 1;
+      }
     }
   }
 
@@ -469,10 +481,15 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
   M.close();
-  {   // the hot sector goes back as one full 32-byte sector (num_iterations += 1 is :394)
+  if (!DEF) {   // changed list lengths go back word by word (fire and forget)
+    if (n_disc_w != in.c0.x) SC(S_N_DISC) = n_disc_w;
+    if (n_owned_w != in.c0.y) SC(S_N_OWNED) = n_owned_w;
+    if (disc_amount_w != in.c0.z) SC(S_DISC_AMOUNT) = disc_amount_w;
+  }
+  {   // the new hot sector (num_iterations += 1 is :394); the caller stores it
     const double ep = __hiloint2double(h1.w, h1.z) + reward;
-    reinterpret_cast<int4*>(hot)[0] = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
-    reinterpret_cast<int4*>(hot)[1] = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
+    in.h0 = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
+    in.h1 = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
   }
   int cls = -1;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
