@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--defender", action="store_true",
                     help="side measurement: the same workload with the re-imaging static defender of train_config.yaml:39-44 "
                          "(not the headline configuration)")
+    ap.add_argument("--host-shards", type=int, default=4, help="handles the batch is cut into for the pipelined end-to-end leg")
     ap.add_argument("--transition-envs", type=int, default=1 << 20,
                     help="envs of the large-batch transition-kernel roofline leg (rank 0, N=1 only; 0 = skip)")
     ap.add_argument("--action-pitch", type=int, default=905,
@@ -341,6 +342,8 @@ def main():
     value = total_envs * args.steps / (ms * 1e-3)
 
     # ---- end-to-end through the C ABI with pinned HOST buffers (H2D + D2H inside the timed region) ----
+    # (a) one handle, cbs_step_host: copy in, step, copy out, wait.  (b) the same batch held by 4 handles stepped as a
+    # pipeline (ShardedHostEnv: slice k+1's copy-in runs under slice k's kernels and copy-out) — the reported e2e.
     h_ring = [torch.empty(B, C.ACTION_DIM, dtype=torch.float32).pin_memory() for _ in range(2)]
     for k in range(2):
         h_ring[k].copy_(ring[k].cpu().contiguous())
@@ -348,18 +351,32 @@ def main():
     h_rew = torch.empty(B, dtype=torch.float32).pin_memory()
     h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
     e2e_steps = max(10, args.steps // 2)
-    for i in range(3):
-        env.step_host(h_ring[i % 2].numpy(), None, h_obs.numpy(), h_rew.numpy(), h_done.numpy())
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        env.step_host(h_ring[i % 2].numpy(), None, h_obs.numpy(), h_rew.numpy(), h_done.numpy())
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = total_envs * e2e_steps / float(t.item())
+
+    def time_host_steps(stepper):
+        for i in range(3):
+            stepper(h_ring[i % 2].numpy(), None, h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            stepper(h_ring[i % 2].numpy(), None, h_obs.numpy(), h_rew.numpy(), h_done.numpy())
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return total_envs * e2e_steps / float(tt.item())
+
+    e2e_single = time_host_steps(env.step_host)
+    from ccbs_b200.host_pipeline import ShardedHostEnv
+    penv = ShardedHostEnv(specs, weights, cfg, num_envs=B, shards=args.host_shards, device=local_rank, seed=7,
+                          global_env_offset=rank * B, auto_reset=True, decode_gemm=args.decode_gemm)
+    penv.reset()
+    for i in range(64):      # bring the episodes to their steady-state mix before timing
+        for (lo, hi), e in zip(penv.bounds, penv.envs):
+            e.step(ring[i % R][lo:hi], None, want_info=False)
+    penv.sync()
+    e2e_value = time_host_steps(penv.step_host)
+    e2e_launches_per_step = 3 * len(penv.envs)
+    penv.close()
     h2d = B * C.ACTION_DIM * 4
     d2h = B * ((C.OBS_DIM + 2) * 4 + 4 + 1)
 
@@ -408,7 +425,8 @@ def main():
                        "state_gb": env.state_bytes / 1e9},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "cbs_step_host (pinned host buffers)"},
+                    "steps": e2e_steps, "api": f"ShardedHostEnv.step_host: {args.host_shards} handles x cbs_step_host_async, pinned host buffers",
+                    "gpu_launches_per_step": e2e_launches_per_step, "single_handle_value": e2e_single},
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
         }

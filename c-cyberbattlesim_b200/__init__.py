@@ -16,6 +16,9 @@ def __getattr__(name):
     if name in ("BatchedCyberBattleEnv", "CbsError"):
         from . import batched_env
         return getattr(batched_env, name)
+    if name == "ShardedHostEnv":
+        from . import host_pipeline
+        return host_pipeline.ShardedHostEnv
     if name in ("CyberBattleVecEnv", "RandomSwitchEnvB200"):
         from . import vec_env
         return getattr(vec_env, name)

@@ -28,7 +28,8 @@ class BatchedCyberBattleEnv:
     def __init__(self, specs: Sequence[ScenarioSpec], gae_weights: GaeWeights, cfg: Optional[EnvConfig] = None,
                  num_envs: int = 1, device: int = 0, scenario_of_env: Optional[np.ndarray] = None, seed: int = 0,
                  global_env_offset: int = 0, auto_reset: bool = True, switch_interval: int = 0,
-                 tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None, **cfg_overrides):
+                 tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None,
+                 gae_tables=None, **cfg_overrides):
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
         self.cfg = cfg or EnvConfig()
@@ -43,7 +44,7 @@ class BatchedCyberBattleEnv:
             specs, self.cfg.isolation_filter_threshold, interest_nodes=interest_nodes if node_goal else None,
             interest_node_value=self.cfg.interest_node_value if node_goal else None)
         self.obs_dim = C.obs_dim_for_goal(self.cfg.goal)
-        self.gae_tables = fold_gae(self.tables, gae_weights)
+        self.gae_tables = gae_tables if gae_tables is not None else fold_gae(self.tables, gae_weights)
         ccfg = L.make_config(self.cfg, self.num_envs, device=device, global_env_offset=global_env_offset, seed=seed,
                              auto_reset=auto_reset, switch_interval=switch_interval, **cfg_overrides)
         self._h = ct.c_void_p()
@@ -187,6 +188,17 @@ class BatchedCyberBattleEnv:
         assert actions.dtype == np.float32 and actions.shape == (self.num_envs, C.ACTION_DIM) and actions.flags.c_contiguous
         v = lambda a: None if a is None else a.ctypes.data_as(ct.c_void_p)  # noqa: E731
         self._check(self.lib.cbs_step_host(self._h, v(actions), v(uniforms), v(obs), v(reward), v(done), v(info)))
+
+    def step_host_async(self, actions: np.ndarray, uniforms: Optional[np.ndarray], obs: np.ndarray, reward: np.ndarray,
+                        done: np.ndarray, info: Optional[np.ndarray] = None):
+        """:meth:`step_host` without the final wait (``cbs_step_host_async``); pair with :meth:`host_sync`.  The buffers
+        must stay alive, unmodified, until then."""
+        assert actions.dtype == np.float32 and actions.shape == (self.num_envs, C.ACTION_DIM) and actions.flags.c_contiguous
+        v = lambda a: None if a is None else a.ctypes.data_as(ct.c_void_p)  # noqa: E731
+        self._check(self.lib.cbs_step_host_async(self._h, v(actions), v(uniforms), v(obs), v(reward), v(done), v(info)))
+
+    def host_sync(self):
+        self._check(self.lib.cbs_host_sync(self._h))
 
     def _actions(self, actions):
         """Accepts a dense [B, 905] tensor or a [B, 905] view of a wider row-pitched buffer (stride(0) >= 905,

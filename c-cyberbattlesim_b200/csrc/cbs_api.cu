@@ -488,8 +488,8 @@ static int ensure_host_staging(cbs_handle* h) {
   return 0;
 }
 
-int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host, float* reward_host,
-                  uint8_t* done_host, int32_t* info_host) {
+int cbs_step_host_async(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host, float* reward_host,
+                        uint8_t* done_host, int32_t* info_host) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (!actions_host) return fail(h, CBS_ERR_INVALID_ARG, "cbs_step_host: actions is null");
@@ -510,8 +510,21 @@ int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniform
   if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (done_host) CK(h, cudaMemcpyAsync(done_host, h->h_done, B, cudaMemcpyDeviceToHost, st));
   if (info_host) CK(h, cudaMemcpyAsync(info_host, h->h_info, B * CBS_INFO_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(h, cudaStreamSynchronize(st));
   return CBS_OK;
+}
+
+int cbs_host_sync(cbs_handle* h) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (h->hstream) CK(h, cudaStreamSynchronize(h->hstream));
+  return CBS_OK;
+}
+
+int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host, float* reward_host,
+                  uint8_t* done_host, int32_t* info_host) {
+  int rc = cbs_step_host_async(h, actions_host, uniforms_host, obs_host, reward_host, done_host, info_host);
+  if (rc) return rc;
+  return cbs_host_sync(h);
 }
 
 static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {

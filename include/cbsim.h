@@ -221,6 +221,14 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
 int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host,
                   float* reward_host, uint8_t* done_host, int32_t* info_host);
 
+/* The same step enqueued on the handle's own stream WITHOUT the final synchronisation, and the wait for it.  Several
+ * handles that each hold a slice of one env batch on the same GPU can be stepped as a pipeline: handle k+1's
+ * host-to-device copy runs under handle k's kernels and device-to-host copies (ccbs_b200.host_pipeline.ShardedHostEnv).
+ * The host buffers must stay valid (and should be pinned) until cbs_host_sync returns. */
+int cbs_step_host_async(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host,
+                        float* reward_host, uint8_t* done_host, int32_t* info_host);
+int cbs_host_sync(cbs_handle* h);
+
 /* ---- introspection (parity tests, statistics) ----------------------------------------------------- */
 typedef enum {
   CBS_F_MASKS = 0,        /* uint32 [B][mask_pitch]: plane p, word w of env b at b * mask_pitch + p * words + w */

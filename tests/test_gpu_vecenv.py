@@ -98,3 +98,40 @@ def test_device_vec_normalize_runs():
     assert obs.shape == (128, 194) and torch.isfinite(obs).all() and obs.abs().max() <= 10.0
     assert torch.isfinite(rew).all() and rew.abs().max() <= 10.0 and float(vn.ret_rms.count) > 2000
     env.close()
+
+
+def test_sharded_host_env_matches_single_handle():
+    """K handles stepped as a host pipeline give exactly what one handle holding the whole batch gives."""
+    import torch
+    import ccbs_b200 as cb
+    specs = [cb.synthetic_spec(800 + k, 11) for k in range(3)]
+    w, cfg = cb.GaeWeights.random(2), cb.EnvConfig()
+    B, T = 50, 45
+    rng = np.random.default_rng(5)
+    actions = rng.uniform(-4, 4, size=(T, B, 905)).astype(np.float32)
+
+    def run(env):
+        env.reset()
+        env.sync()
+        pin = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt).pin_memory()  # noqa: E731
+        a, obs, rew, done, info = pin(B, 905), pin(B, 194), pin(B), pin(B, dt=torch.uint8), pin(B, 8, dt=torch.int32)
+        out = []
+        for t in range(T):
+            a.numpy()[...] = actions[t]
+            env.step_host(a.numpy(), None, obs.numpy(), rew.numpy(), done.numpy(), info.numpy())
+            out.append((obs.numpy().copy(), rew.numpy().copy(), done.numpy().copy(), info.numpy().copy()))
+        return out, env.terminal_obs(), env.last_stats(), env.stat_accum()
+
+    one = cb.BatchedCyberBattleEnv(specs, w, cfg, num_envs=B, seed=41)
+    ref, ref_term, ref_stats, ref_acc = run(one)
+    one.close()
+    for shards in (3, 4):
+        env = cb.ShardedHostEnv(specs, w, cfg, num_envs=B, shards=shards, seed=41)
+        assert [hi - lo for lo, hi in env.bounds] == [len(x) for x in np.array_split(np.arange(B), shards)]
+        got, term, stats, acc = run(env)
+        env.close()
+        for t in range(T):
+            for x, y in zip(got[t], ref[t]):
+                assert np.array_equal(x, y), f"shards {shards} step {t}"
+        assert np.array_equal(term, ref_term) and np.array_equal(stats, ref_stats)
+        assert acc["episodes"] == ref_acc["episodes"] > B and abs(acc["return_sum"] - ref_acc["return_sum"]) < 1e-6 * abs(ref_acc["return_sum"])
