@@ -23,13 +23,15 @@ namespace cbs {
 
 namespace {
 
-constexpr int BM = 128;        // envs per CTA (UMMA M)
+// envs per CTA = UMMA M: 128, or 64 when 128-row tiles would leave more than half of the SMs without a CTA (8192 envs:
+// 64 tiles of 128 on 148 SMs).  The kernel is bound by staging the A slab per CTA, so twice as many half-height tiles
+// roughly halve its duration.  With M = 64 the accumulator occupies lanes 0-15 of each warp's 32-lane TMEM
+// sub-partition: tile row r lives in lane (r / 16) * 32 + r % 16.
 constexpr int BK = 32;         // floats per K slab = 128 bytes = one SWIZZLE_128B row
 constexpr int UMMA_K = 8;      // tf32: 32 bytes per instruction
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;   // ring depth is chosen per launch: as many stages as fit in shared memory
 constexpr int NT_MAX = 256;    // UMMA N limit
 constexpr int TMEM_COLS = 256;
-constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,14 +97,15 @@ __global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restri
 //            the A slab with 4-byte cp.async straight into the 128-byte-swizzled layout the UMMA descriptor expects
 //            (16-byte chunk c of row r lands at chunk c ^ (r & 7)) and arrive on the stage's full barrier when their
 //            copies land (cp.async.mbarrier.arrive.noinc); no repack pass over HBM.  256 threads.
-template <bool LDGSTS_A>
+template <bool LDGSTS_A, int BM>
 __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                                  const float* __restrict__ actions, int act_stride,
                                                                                  float* __restrict__ vt, int B, int Upad, int nt_box,
-                                                                                 int vt_stride, int32_t* errflag, int direct) {
+                                                                                 int vt_stride, int32_t* errflag, int direct, int STAGES) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB / 8 KB
   const int stage_bytes = A_STAGE_BYTES + nt_box * BK * 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
@@ -184,10 +187,12 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
   }
   __syncwarp();
 
-  // ---- epilogue: TMEM -> registers -> global (every warp owns TMEM lanes [32w, 32w+32) = tile rows) ----
+  // ---- epilogue: TMEM -> registers -> global.  Every warp owns TMEM lanes [32w, 32w+32): tile rows 32w + lane
+  //      (M = 128) or rows 16w + lane on its lanes 0-15 (M = 64) ----
   const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const int row = m0 + warp * 32 + lane;
+  const bool lane_has_row = BM == 128 || lane < 16;
+  const int row = lane_has_row ? m0 + warp * (BM / 4) + lane : B;
   if (ready) {
     for (int c0 = 0; c0 < nt; c0 += 32) {
       uint32_t r[32];
@@ -266,27 +271,42 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
   static const bool force_pack = getenv("CBS_TMA_PACK") != nullptr;
   const bool direct = (act_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(actions) & 15) == 0);
   const bool ldgsts = !direct && !force_pack;
+  if (!make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box)) return cudaErrorInvalidValue;
+  const int ntiles_n = (Upad + NT_MAX - 1) / NT_MAX;
+  int num_sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static const bool force128 = getenv("CBS_GEMM_M128") != nullptr;   // A/B switch for the measurements in DESIGN.md
+  const bool half = !force128 && 2 * ((B + 127) / 128) * ntiles_n <= num_sms + num_sms / 4;   // half-height tiles still fit (about) one wave
+  const int bm = half ? 64 : 128;
   if (direct) {
-    if (!make_map(&map_a, actions, (uint64_t)B, BM, (uint64_t)act_stride, (uint64_t)ACTION_DIM)) return cudaErrorInvalidValue;
+    if (!make_map(&map_a, actions, (uint64_t)B, bm, (uint64_t)act_stride, (uint64_t)ACTION_DIM)) return cudaErrorInvalidValue;
   } else {
-    if (!make_map(&map_a, a_packed, (uint64_t)B, BM)) return cudaErrorInvalidValue;
+    if (!make_map(&map_a, a_packed, (uint64_t)B, bm)) return cudaErrorInvalidValue;
     if (!ldgsts) pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B, act_stride);
   }
-  if (!make_map(&map_b, vemb, (uint64_t)Ug, (uint32_t)nt_box)) return cudaErrorInvalidValue;
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + (size_t)nt_box * BK * 4) + 1024 + 256;
-  static size_t attr[2] = {0, 0};
-  if (smem > attr[ldgsts]) {
-    cudaError_t e = ldgsts ? cudaFuncSetAttribute(decode_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(decode_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t stage_bytes = (size_t)bm * BK * 4 + (size_t)nt_box * BK * 4;
+  int stages = (int)((225 * 1024 - 1024 - 256) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  static const char* stages_env = getenv("CBS_GEMM_STAGES");
+  if (stages_env && atoi(stages_env) >= 2 && atoi(stages_env) < stages) stages = atoi(stages_env);
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const float*, int, float*, int, int, int, int, int32_t*, int, int);
+  const int which = (ldgsts ? 1 : 0) | (half ? 2 : 0);
+  const KernelFn kernels[4] = {decode_gemm_tc_kernel<false, 128>, decode_gemm_tc_kernel<true, 128>,
+                               decode_gemm_tc_kernel<false, 64>, decode_gemm_tc_kernel<true, 64>};
+  static size_t attr[4] = {0, 0, 0, 0};
+  if (smem > attr[which]) {
+    cudaError_t e = cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr[ldgsts] = smem;
+    attr[which] = smem;
   }
-  dim3 grid((B + BM - 1) / BM, (Upad + NT_MAX - 1) / NT_MAX);
-  if (ldgsts)
-    decode_gemm_tc_kernel<true><<<grid, 256, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag, 0);
-  else
-    decode_gemm_tc_kernel<false><<<grid, 128, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag,
-                                                             direct ? 1 : 0);
+  dim3 grid((B + bm - 1) / bm, ntiles_n);
+  kernels[which]<<<grid, ldgsts ? 256 : 128, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag,
+                                                            direct ? 1 : 0, stages);
   return cudaGetLastError();
 }
 
