@@ -245,9 +245,11 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
       r[1] = (uint32_t)t->vi_kinds_any[i] | ((uint32_t)t->vi_kinds_remote[i] << 16);
       // the port's outgoing-firewall node mask itself when a plane is one word, else the port index into `outblock`
       r[2] = t->words == 1 ? t->outblock[(size_t)(inst_port_off[i] + t->vi_port[i])] : (uint32_t)t->vi_port[i];
-      r[3] = (uint32_t)rp.size();
+      r[3] = (uint32_t)rp.size();           // both lists start on an 8-byte boundary (the transition reads 8 ids per load)
       rp.insert(rp.end(), t->recon_nodes + oa, t->recon_nodes + oa + la);
+      rp.resize((rp.size() + 7) & ~size_t(7), 0);
       rp.insert(rp.end(), t->recon_nodes + orr, t->recon_nodes + orr + lr);
+      rp.resize((rp.size() + 7) & ~size_t(7), 0);
       memcpy(&r[4], &t->vi_success[i], 8);
       memcpy(&r[6], &t->vi_cost[i], 8);
     }

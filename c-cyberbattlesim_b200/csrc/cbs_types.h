@@ -101,7 +101,7 @@ struct Tables {  // immutable, device pointers
   const uint4* vi_pack;        // [I][2]  { vi_flags | len_any << 8 | len_remote << 16, kinds_any | kinds_remote << 16,
                                //           port (words > 1) or the port's outgoing-firewall node mask itself (words == 1), recon offset }
                                //         { success rate (float64), cost (float64) }
-  const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list directly followed by the "REMOTE only" one
+  const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list, then the "REMOTE only" one, each padded to 8 bytes
   // GAE
   const float *node_static, *dyn_proj, *vuln_h, *nn0_b, *bn1_scale, *bn1_shift, *gcn_wt, *bn2_scale, *bn2_shift;
 };

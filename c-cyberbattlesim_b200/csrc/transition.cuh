@@ -310,14 +310,19 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
         else { M.set(M_EVASION, t); total += P.rew[R_EVASION]; }
         break;
       case K_RECON: {
-        // the instance's two Reconnaissance lists sit back to back in recon_pack: "any type" first, then "REMOTE only"
+        // the instance's two Reconnaissance lists sit in recon_pack, each starting on an 8-byte boundary: "any type"
+        // first, then "REMOTE only".  Eight node ids per load; a node already discovered costs three instructions.
         const int len_any = (vf >> 8) & 0xFF, len_remote = (vf >> 16) & 0xFF;
-        const int off = (int)vp0.w + (local ? 0 : len_any), len = local ? len_any : len_remote;
+        const int off = (int)vp0.w + (local ? 0 : ((len_any + 7) & ~7)), len = local ? len_any : len_remote;
         int n_disc = DEF ? SC(S_N_DISC) : n_disc_w, fresh = 0;
         uint8_t* order = S.disc_order + (size_t)b * P.ncap;
-        for (int i = 0; i < len; ++i) {                     // :291-296 + cyberbattle_env.py:398-407
-          const int node = T.recon_pack[off + i];
-          if (!M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
+        for (int i0 = 0; i0 < len; i0 += 8) {               // :291-296 + cyberbattle_env.py:398-407
+          const uint2 ch = *reinterpret_cast<const uint2*>(T.recon_pack + off + i0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int node = (int)(((j < 4 ? ch.x : ch.y) >> (8 * (j & 3))) & 0xFFu);
+            if (i0 + j < len && !M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
+          }
         }
         if (DEF) { SC(S_N_DISC) = n_disc; SC(S_DISC_AMOUNT) += fresh; }
         else { n_disc_w = n_disc; disc_amount_w += fresh; }
