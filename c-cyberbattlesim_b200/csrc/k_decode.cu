@@ -97,6 +97,9 @@ __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, i
 // Narrower per-env tiles were tried (4 / 8 / 16 lanes: 428 / 212 / 121 us against 83 us for a full warp): lanes per
 // env matter more than envs in flight.
 // ------------------------------------------------------------------------------------------------
+#ifndef CBS_SEL_MINB
+#define CBS_SEL_MINB 5   // 96 registers, 20 warps per SM: measured best (4: 78 us, 5: 76, 6: 84, 7: 94, 8: 104; no bound = 215 registers: 117)
+#endif
 constexpr int SEL_WARPS = 4;
 constexpr int SEL_THREADS = SEL_WARPS * 32;
 constexpr int CAND_CAP = 4;
@@ -220,7 +223,7 @@ struct FusedTransition {
 
 // W1: one-word mask planes and no defender -> the fused transition stages the env's records in registers
 template <bool FUSE, bool DEF, bool W1>
-__global__ void __launch_bounds__(SEL_THREADS) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
+__global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
                                                                    int vt_stride, int vt_cached, int sched_buf, FusedTransition ft,
                                                                    int32_t* __restrict__ sel_out, double* __restrict__ dist_out,
                                                                    long long* __restrict__ trace) {
