@@ -288,24 +288,11 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     na = sqrt(warp_sum(n0 + n1));
   }
   __syncthreads();
-  if (!in_range) { sched_done(S, sched_buf); return; }
-  if (flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET)) {
-    if (lane == 0) {
-      reinterpret_cast<int4*>(S.sel)[b] = make_int4(0, 0, 0, 0);
-      S.dist[b] = 0.0;
-      if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = make_int4(0, 0, 0, 0);
-      if (dist_out) dist_out[b] = 0.0;
-      if (FUSE) {
-        TransitionIn<W1> tin;
-        tin.issue(P, S, b, ft.uniforms);
-        tin.sl = make_int4(0, 0, 0, 0); tin.dist = 0.0;
-        transition_env<DEF, true, W1>(T, P, S, b, tin, T.sc_pack, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
-        tin.store_hot(S, b);
-      }
-    }
-    sched_done(S, sched_buf);
-    return;
-  }
+  // a finished env (the reference raises there, cyberbattle_env.py:300-302) decodes to zeros
+  const bool active = in_range && !(flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET));
+  int4 out = make_int4(0, 0, 0, 0);      // lane 0 holds the env's result
+  double d = 0.0;
+  if (active) {
   const uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
   const float* vt_g = S.vt + (size_t)b * vt_stride;
   const float margin_s = P.margin * (float)na;
@@ -448,29 +435,42 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   n_exact += ncand;
   flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best);
   if (lane == 0) {
-    int4 out = make_int4(starter, starter, 0, 0);
-    double d = 1.0;
+    out = make_int4(starter, starter, 0, 0);
+    d = 1.0;
     if (best.r >= 0) {
       out = make_int4(best.s, best.t, T.row_ulocal[best.r], (int)((best.packed >> 20) & 15));
       d = best.d;
     } else {
       atomicExch(S.errflag, 3);   // empty action table: outside the reference's domain (cdist would raise)
     }
-    reinterpret_cast<int4*>(S.sel)[b] = out;
-    S.dist[b] = d;
-    if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = out;
-    if (dist_out) dist_out[b] = d;
     if (trace) {
       long long* tr = trace + (size_t)b * 6;
       tr[0] = clock64() - t_begin; tr[1] = n_rows; tr[2] = n_live; tr[3] = n_exact; tr[4] = combos; tr[5] = t_begin;
     }
-    // fused step: the transition of this env runs here, on one lane, while the other warps are still scanning
-    if (FUSE) {
+  }
+  }   // active
+  if (in_range && lane == 0) {
+    reinterpret_cast<int4*>(S.sel)[b] = out;
+    S.dist[b] = d;
+    if (sel_out) reinterpret_cast<int4*>(sel_out)[b] = out;
+    if (dist_out) dist_out[b] = d;
+  }
+  // fused step: the CTA's transitions run together on the first lanes of warp 0 once all its warps have decoded.  One
+  // lane per warp right after its decode cost the same ~700 instructions per ENV at 1/32 lane utilisation — a fifth of
+  // the kernel's issue slots; the CTA's resources are held until its slowest warp is done either way.
+  if (FUSE) {
+    __shared__ int4 sh_out[SEL_WARPS];
+    __shared__ double sh_d[SEL_WARPS];
+    __shared__ int sh_b[SEL_WARPS];
+    if (lane == 0) { sh_out[warp] = out; sh_d[warp] = d; sh_b[warp] = in_range ? b : -1; }
+    __syncthreads();
+    if (warp == 0 && lane < SEL_WARPS && sh_b[lane] >= 0) {
+      const int bb = sh_b[lane];
       TransitionIn<W1> tin;
-      tin.issue(P, S, b, ft.uniforms);
-      tin.sl = out; tin.dist = d;
-      transition_env<DEF, true, W1>(T, P, S, b, tin, T.sc_pack, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
-      tin.store_hot(S, b);
+      tin.issue(P, S, bb, ft.uniforms);
+      tin.sl = sh_out[lane]; tin.dist = sh_d[lane];
+      transition_env<DEF, true, W1>(T, P, S, bb, tin, T.sc_pack, ft.uniforms != nullptr, false, sched_buf ^ 1, ft.reward, ft.done, nullptr, nullptr);
+      tin.store_hot(S, bb);
     }
   }
   sched_done(S, sched_buf);
