@@ -100,7 +100,10 @@ __device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, i
 #ifndef CBS_SEL_MINB
 #define CBS_SEL_MINB 5   // 96 registers, 20 warps per SM: measured best (4: 78 us, 5: 76, 6: 84, 7: 94, 8: 104; no bound = 215 registers: 117)
 #endif
-constexpr int SEL_WARPS = 4;
+#ifndef CBS_SEL_WARPS
+#define CBS_SEL_WARPS 4
+#endif
+constexpr int SEL_WARPS = CBS_SEL_WARPS;
 constexpr int SEL_THREADS = SEL_WARPS * 32;
 constexpr int CAND_CAP = 4;
 constexpr int RPL = 4;          // rows per lane per trip
