@@ -73,6 +73,9 @@ class EnvConfig:
     scan_frequency: int = 3               # :43-44
     # compressed:455-462: when set, every step whose DESIRED outcome is a success class re-encodes the graph - i.e. every step
     precise_graph_encoding: bool = False
+    # compressed:86,419-427,498-506: every table-maintaining encode also refreshes the rows of the (source, target) pairs
+    # from which the action's source or target node can be reached in the visible graph (their embeddings may have changed)
+    precise_action_space_positions: bool = False
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
 
@@ -91,6 +94,9 @@ class EnvConfig:
                 raise ValueError(f"scan_capacity must be in 1..{C.MAX_SCAN_CAPACITY}")
             if int(self.scan_frequency) < 1:
                 raise ValueError("scan_frequency must be >= 1")
+            if self.precise_action_space_positions:
+                raise ValueError("precise_action_space_positions is not implemented together with a static defender "
+                                 "(the reference then refreshes around `changed_nodes`, compressed:423-427)")
 
     @classmethod
     def from_reference_dicts(cls, train_config: dict, rewards_config: dict, goal: str = "control") -> "EnvConfig":
@@ -152,4 +158,5 @@ class EnvConfig:
                     random_starter_node=self.random_starter_node, rewards_dict=dict(self.rewards_dict),
                     interest_node_value=self.interest_node_value, switch_interest_node_interval=1,
                     penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None,
-                    precise_graph_encoding=self.precise_graph_encoding)
+                    precise_graph_encoding=self.precise_graph_encoding,
+                    precise_action_space_positions=self.precise_action_space_positions)

@@ -137,6 +137,8 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
     return fail(nullptr, CBS_ERR_INVALID_ARG, "static_defender must be 0 (none) or 1 (scan and re-image)");
   if (cfg->static_defender && (cfg->scan_capacity < 1 || cfg->scan_capacity > MAX_SCAN_CAPACITY || cfg->scan_frequency < 1))
     return fail(nullptr, CBS_ERR_INVALID_ARG, "scan_capacity must be in 1..%d and scan_frequency >= 1", MAX_SCAN_CAPACITY);
+  if (cfg->precise_action_space_positions && cfg->static_defender)
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "precise_action_space_positions is not implemented together with a static defender");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CBS_ERR_NO_DEVICE, "no CUDA device available (libcbsim has no CPU fallback)");
@@ -171,6 +173,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.scan_frequency = cfg->scan_frequency;
   P.detect_prob = cfg->detect_probability;
   P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
+  P.precise_positions = cfg->precise_action_space_positions ? 1 : 0;
   *out = h;
   return CBS_OK;
 }
@@ -279,7 +282,13 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   // re-imaging with pairs still missing
   int slots = (h->cfg.static_defender ? 4 : 2) * t->max_nodes - 1;
   if (max_steps + 1 < slots) slots = max_steps + 1;
-  if (slots > 255) slots = 255;
+  if (P.precise_positions) slots = max_steps + 1;   // every table-maintaining encode may refresh rows: one snapshot per step
+  if (slots > 255) {
+    if (P.precise_positions && h->cfg.max_slots <= 0)
+      return fail(h, CBS_ERR_INVALID_ARG, "precise_action_space_positions needs one snapshot slot per episode step: episodes of up to %d "
+                                          "steps exceed the 255-slot limit", max_steps);
+    slots = 255;
+  }
   P.slots = h->cfg.max_slots > 0 ? h->cfg.max_slots : slots;
   if (P.slots > 255) return fail(h, CBS_ERR_INVALID_ARG, "max_slots must be <= 255");
   int ecap = t->max_nodes * t->max_nodes;
@@ -302,6 +311,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   P.ocap = 2 * P.ncap;
   if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
   else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
+  AL(pair_epoch, P.precise_positions ? B * P.ncap * P.ncap : 1);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
   AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);

@@ -123,6 +123,7 @@ struct Params {  // configuration, by value
   int always_encode;   // defender or precise_graph_encoding: every step re-encodes (compressed:401,455-462)
   int ocap;            // capacity of owned_raw
   int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
+  int precise_positions;   // precise_action_space_positions (compressed:419-427,498-506): table rows are refreshed, see build_table
 };
 
 struct State {  // mutable, device pointers
@@ -138,6 +139,9 @@ struct State {  // mutable, device pointers
                          //            stays the append-only list of every node that ever was a source of table rows
   uint8_t* reimage_left; // [B][ncap]  node_reimaging_progress (static_defender_actions.py:23)
   uint8_t* pair_opos;    // [B][ncap*ncap]  position of the source in owned_raw when the pair entered the table (tie order)
+  // precise_action_space_positions only (1-byte dummy otherwise):
+  uint8_t* pair_epoch;   // [B][ncap*ncap]  slot at which the pair FIRST entered the table: its place in the insertion order;
+                         //                 pair_slot then names the snapshot its rows currently carry (refreshed over time)
   const int32_t* def_nodes;     // [B][scan_capacity] test override of the scan draws (random.choices), or nullptr -> Philox
   const float* def_uniforms;    // [B][scan_capacity] test override of the detection uniforms, consumed in call order
   float* z_hist;         // [B][slots][ncap][64]  node embeddings of the encode that created the slot

@@ -114,10 +114,11 @@ struct SelWarp {
   float a_o[16];
   float p_st[32], p_n2[32];   // per staged pair: a_s.z_s + a_t.z_t (from the fp16 snapshots), |z_s|^2 + |z_t|^2 + 1
   int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
-  uint32_t p_key[32];         // slot << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
+  uint32_t p_key[32];         // insertion epoch << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
+  int p_slot[32];             // snapshot slot the pair's rows carry (== the epoch unless precise_action_space_positions refreshed them)
   float c_score[CAND_CAP];    // rows still within `margin` of the running maximum, waiting for the float64 re-score
   uint32_t c_key[CAND_CAP], c_packed[CAND_CAP];
-  int c_row[CAND_CAP];
+  int c_row[CAND_CAP], c_slot[CAND_CAP];
   uint8_t oorder[MAX_NODES], dorder[MAX_NODES];
 };
 
@@ -191,7 +192,7 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
     if (sh.c_score[i] < threshold) continue;               // NaN scores are kept (comparison false)
     const uint32_t k = sh.c_key[i];
     const int r = sh.c_row[i];
-    const int slot = (int)(k >> 24), s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
+    const int slot = sh.c_slot[i], s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
     const unsigned long long key = ((unsigned long long)k << 32) | (unsigned long long)(unsigned)r;
     const double d = exact_distance(T, P, S, act, b, s, t, slot, sh.c_packed[i], na, lane);
     // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     const int c = cbase + lane;
     bool live = false;
     float st = 0.f, n2 = 0.f;
-    int r0 = 0, cnt = 0;
+    int r0 = 0, cnt = 0, slot_of_pair = 0;
     uint32_t key = 0;
     if (c < combos) {
       const int op = c / n_disc, dp = c - op * n_disc;
@@ -337,7 +338,9 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
         // exact ties resolve in table-insertion order: slot, then the source's position in owned_nodes WHEN the pair was
         // added (== its current position unless a defender removed nodes from the list), then the target's position
         const int opk = DEF ? (int)S.pair_opos[(size_t)b * P.ncap * P.ncap + s * P.ncap + t] : op;
-        key = ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)op;
+        const int epoch = P.precise_positions ? (int)S.pair_epoch[(size_t)b * P.ncap * P.ncap + s * P.ncap + t] : slot;
+        key = ((uint32_t)epoch << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)op;
+        slot_of_pair = slot;
         live = cnt > 0;
       }
     }
@@ -346,7 +349,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     n_live += npairs;
     if (npairs == 0) continue;
     const int idx = __popc(lmask & ((1u << lane) - 1u));
-    if (live) { sh.p_st[idx] = st; sh.p_n2[idx] = n2; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_pre[idx + 1] = cnt; }
+    if (live) { sh.p_st[idx] = st; sh.p_n2[idx] = n2; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_slot[idx] = slot_of_pair; sh.p_pre[idx + 1] = cnt; }
     if (lane == 0) sh.p_pre[0] = 0;
     __syncwarp();
     int run = (lane < npairs) ? sh.p_pre[lane + 1] : 0;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
           const int cpi = __shfl_sync(0xFFFFFFFFu, pp[q], src);
           const int cr = __shfl_sync(0xFFFFFFFFu, rr[q], src);
           const uint32_t cp = __shfl_sync(0xFFFFFFFFu, packed[q], src);
-          if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp; }
+          if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_slot[ncand] = sh.p_slot[cpi]; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp; }
           ++ncand;
           __syncwarp();
         }

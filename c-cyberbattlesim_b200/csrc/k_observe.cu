@@ -19,6 +19,9 @@ namespace cbs {
 #ifndef CBS_OBS_WARPS
 #define CBS_OBS_WARPS 8
 #endif
+#ifndef CBS_OBS_MINB
+#define CBS_OBS_MINB 1
+#endif
 constexpr int OBS_WARPS = CBS_OBS_WARPS;          // warps per CTA (one CTA per SM)
 constexpr int SMEM_NODES = CBS_OBS_SMEM_NODES;    // graphs up to this many nodes keep their embeddings in shared memory
 
@@ -290,9 +293,39 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 
 // ---- create_continuous_action_space (compressed:487-523): new (source,target) pairs freeze the embeddings
 //      of THIS encode; they are stored once per table-growing encode in a snapshot slot ----
-__device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane) {
+// `refresh`: precise_action_space_positions and this encode follows a step (compressed:419-422,498-506): pairs whose source
+//      or target can reach the action's source or target node in the visible graph (nx.has_path on the DiGraph; a node
+//      reaches itself) take the CURRENT embeddings — they move to this encode's snapshot slot while pair_epoch keeps their
+//      place in the table's insertion order.
+template <bool PRECISE>
+__device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg) {
+  const bool refresh = PRECISE && refresh_arg;
   const int node_off_bt = scalar(S, P, S_NODE_OFF, b);
   int new_rows = 0;
+  uint32_t reach[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
+  if (PRECISE && refresh) {
+    const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
+    reach[sl.x >> 5] |= 1u << (sl.x & 31);
+    reach[sl.y >> 5] |= 1u << (sl.y & 31);
+    const int E = scalar(S, P, S_N_EDGES, b);
+    const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
+    const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
+    for (bool changed = true; changed;) {       // backward closure over the edge list: at most one pass per graph node
+      uint32_t add[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
+      for (int e = lane; e < E; e += 32) {
+        const int s = es[e], t = ed[e];
+        if (((reach[t >> 5] >> (t & 31)) & 1u) && !((reach[s >> 5] >> (s & 31)) & 1u)) add[s >> 5] |= 1u << (s & 31);
+      }
+      changed = false;
+#pragma unroll
+      for (int w = 0; w < MAX_NODES / 32; ++w) {
+        const uint32_t a = __reduce_or_sync(0xFFFFFFFFu, add[w]);
+        changed |= a != 0u;
+        reach[w] |= a;
+      }
+    }
+  }
+  auto in_reach = [&](int n) { return ((reach[n >> 5] >> (n & 31)) & 1u) != 0u; };
   // sources: env.owned_nodes.  Under a defender that is the exact list (removals, duplicates: the dict comprehension of
   // compressed:491-492 keeps the first occurrence); otherwise the append-only list.
   const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);
@@ -300,6 +333,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   const uint8_t* oorder = P.defender ? S.owned_raw + (size_t)b * P.ocap : S.owned_order + (size_t)b * P.ncap;
   uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
   uint8_t* po = S.pair_opos + (size_t)b * P.ncap * P.ncap;
+  uint8_t* pe = S.pair_epoch + (size_t)b * P.ncap * P.ncap;
   const int slot = scalar(S, P, S_N_SLOTS, b);
   bool any_new = false;
   uint32_t seen[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
@@ -315,12 +349,16 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
       bool fresh = false;
       if (dp < n_disc) {
         const int t = dorder[dp];
-        fresh = (W.dynb[dp] & 0x80) && ps[s * P.ncap + t] == 0xFF;
+        const bool is_new = ps[s * P.ncap + t] == 0xFF;
+        fresh = (W.dynb[dp] & 0x80) && (is_new || (PRECISE && refresh && (in_reach(s) || in_reach(t))));
         if (fresh && slot < P.slots) {
           ps[s * P.ncap + t] = (uint8_t)slot;
-          if (P.defender) po[s * P.ncap + t] = (uint8_t)op;   // insertion order inside the slot (exact-tie order of the decode)
-          const int g = node_off_bt + t;
-          new_rows += T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g + (s == t ? 0 : 1)];
+          if (is_new) {
+            if (P.defender) po[s * P.ncap + t] = (uint8_t)op;   // insertion order inside the slot (exact-tie order of the decode)
+            if (PRECISE) pe[s * P.ncap + t] = (uint8_t)slot;
+            const int g = node_off_bt + t;
+            new_rows += T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g + (s == t ? 0 : 1)];
+          }
         }
       }
       any_new |= __any_sync(0xFFFFFFFFu, fresh);
@@ -480,7 +518,7 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
 
 // BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
 template <bool BIG_GRAPHS>
-__global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Params P, State S,
+__global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(Tables T, Params P, State S,
                                                                 const uint8_t* __restrict__ reset_mask, int mode,
                                                                 long long* __restrict__ trace) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -569,7 +607,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       if (flags & FL_REENCODE) {
         encode_env(T, P, S, SW, W, b, lane);
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
-        build_table(T, P, S, W, b, lane);
+        if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true);
+        else build_table<false>(T, P, S, W, b, lane, false);
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
         keep &= ~FL_DIRTY;
         if (is_node_goal(P)) keep |= FL_INTEREST_IN_GRAPH;
@@ -590,7 +629,8 @@ __global__ void __launch_bounds__(OBS_WARPS * 32) observe_kernel(Tables T, Param
       W.g = W.ysm + SMEM_NODES * NODE_EMB;
       encode_env(T, P, S, SW, W, b, lane);
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[4])); }
-      build_table(T, P, S, W, b, lane);
+      if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
+      else build_table<false>(T, P, S, W, b, lane, false);
       // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even
       // if nothing else changes
       if (is_node_goal(P) && lane == 0) scalar(S, P, S_FLAGS, b) = FL_DIRTY | FL_INTEREST_IN_GRAPH;

@@ -482,7 +482,9 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   // the target or the discovered set; reward > 0 adds / updates an edge).
   const bool dirty = (flags & FL_DIRTY) || code < 16 || add_edge || def_event;
   const int sticky = flags & FL_INTEREST_IN_GRAPH;          // survives until the episode's reset
-  const bool encode_now = reencode && dirty;
+  // (not with precise_action_space_positions: a re-encode of an unchanged graph still hands the current embeddings to
+  // the pairs around THIS action's nodes, which an earlier refresh may have passed over)
+  const bool encode_now = reencode && (dirty || P.precise_positions);
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
   M.close();

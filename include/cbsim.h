@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CBS_ABI_VERSION 3
+#define CBS_ABI_VERSION 4
 
 /* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
  * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
@@ -84,6 +84,10 @@ typedef struct {
   int32_t scan_frequency;       /* >= 1 */
   int32_t precise_graph_encoding; /* compressed:455-462: re-encode the visible graph on every step */
   double detect_probability;
+  /* compressed:86,419-427,498-506: at every table-maintaining encode of a step, the rows of the (source, target) pairs
+   * from which the action's source or target node can be reached in the visible graph are overwritten with the current
+   * node embeddings (their place in the table's insertion order is kept).  Not available with a static defender. */
+  int32_t precise_action_space_positions;
 } cbs_config;
 
 /* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the

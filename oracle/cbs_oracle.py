@@ -113,6 +113,7 @@ class OracleEnv:
         # ScanAndReimageCompromisedMachines (_env/static_defender.py:27-60); None -> no defender
         self.defender = getattr(cfg, "static_defender_agent", None) == "reimage"
         self.always_encode = self.defender or bool(getattr(cfg, "precise_graph_encoding", False))   # compressed:401,455-462
+        self.precise_positions = bool(getattr(cfg, "precise_action_space_positions", False))        # compressed:86,419-427
         self.proportional_cutoff_coefficient = cfg.proportional_cutoff_coefficient
         # create_vulnerabilities_embeddings (compressed:614-618)
         self.vuln_emb = {k: np.asarray(v, dtype=np.float64) for k, v in spec.vuln_emb.items()}
@@ -248,6 +249,7 @@ class OracleEnv:
         self.graph_edges = {}            # src -> {tgt: float64[768]}
         self._add_graph_node(self.starter)
         self.action_keys, self.action_rows = [], []
+        self._row_of_key = {}            # the reference's table is a dict: re-adding a key overwrites its row in place
         self._rows_cache = None
         self.exploited = {}
         self.node_embeddings, emb = self.encode()
@@ -624,17 +626,33 @@ class OracleEnv:
     def _discrete_features(self):
         return np.array([len(self.discovered_nodes), len(self.owned_nodes)])               # :309-316
 
-    def create_continuous_action_space(self):
-        """compressed:487-523 (+ :526-550) with sample_subset_samples=False."""
+    def _reaches(self, targets):
+        """Nodes of the evolving visible graph (a DiGraph) from which some node of `targets` can be reached
+        (nx.has_path(G, n, target); a node reaches itself)."""
+        reach = set(targets)
+        changed = True
+        while changed:
+            changed = False
+            for s, outs in self.graph_edges.items():
+                if s not in reach and any(t in reach for t in outs):
+                    reach.add(s)
+                    changed = True
+        return reach
+
+    def create_continuous_action_space(self, nodes_to_recalculate=None):
+        """compressed:487-523 (+ :526-550) with sample_subset_samples=False.  ``nodes_to_recalculate``
+        (precise_action_space_positions, :498-506): pairs whose source or target reaches one of these nodes in the
+        visible graph are processed again — their rows are overwritten in place with the current embeddings."""
         run_owned = [n for n in self.owned_nodes if self.nodes[n].status == C.ST_RUNNING]
         run_disc = [n for n in self.discovered_nodes if self.nodes[n].status == C.ST_RUNNING]
         # dict comprehension semantics (:491-494): duplicate keys collapse, first position kept
         run_owned = list(dict.fromkeys(run_owned))
         run_disc = list(dict.fromkeys(run_disc))
+        reach = self._reaches(nodes_to_recalculate) if nodes_to_recalculate else ()
         for s in run_owned:
             es = self.node_embeddings[s]
             for t in run_disc:
-                if (s, t) in self.processed_pairs:
+                if (s, t) in self.processed_pairs and not (s in reach or t in reach):
                     continue
                 et = self.node_embeddings[t]
                 if s == t:
@@ -654,8 +672,14 @@ class OracleEnv:
             if self.cfg.remove_main_obstacles and self.node_goal and self.goal != "disruption_node" and \
                     kind == C.K_DOS and t == self.interest:
                 continue                                                                   # :545-547
-            self.action_keys.append((s, t, vid, kind, vtype, ri))
-            self.action_rows.append(np.concatenate((es, et, emb)))                         # :550
+            key, row = (s, t, vid, kind, vtype, ri), np.concatenate((es, et, emb))         # :550
+            at = self._row_of_key.get(key)
+            if at is None:
+                self._row_of_key[key] = len(self.action_keys)
+                self.action_keys.append(key)
+                self.action_rows.append(row)
+            else:
+                self.action_rows[at] = row                                                 # "overwrite if changed"
             self._rows_cache = None
 
     def find_closest_action_embedding(self, action_vector):
@@ -692,7 +716,7 @@ class OracleEnv:
             self.node_embeddings, emb = self.encode()
             self.n_encodes += 1
             self.observation = {"graph_embeddings": emb, "discrete_features": self._discrete_features()}
-            self.create_continuous_action_space()
+            self.create_continuous_action_space([s, t] if self.precise_positions else None)   # :419-422
         self.reward += self.pen["distance_penalty"] * dist                                 # :430
         info = dict(source_node=s, target_node=t, vulnerability=vid, outcome_kind=kind, outcome_obtained=self.outcome,
                     vulnerability_type=self.vulnerability_type, end_episode_reason=self.end_episode_reason,

@@ -84,6 +84,13 @@ CASES = {
     # precise_graph_encoding: every step re-encodes (compressed:455-462)
     "g12_precise": dict(graph_seed=12, nodes=12, steps=500, cfg=dict(goal="control", precise_graph_encoding=True,
                                                                       proportional_cutoff_coefficient=3)),
+    # precise_action_space_positions (compressed:419-427,498-506): rows of pairs connected to the action's nodes are
+    # refreshed with the current embeddings at every table-maintaining encode
+    "g12_positions": dict(graph_seed=12, nodes=12, steps=500, cfg=dict(goal="control", precise_action_space_positions=True,
+                                                                        proportional_cutoff_coefficient=3)),
+    "p8_positions": dict(graph_seed=53, nodes=8, steps=500, policy=0.02,
+                         cfg=dict(goal="control", precise_action_space_positions=True, proportional_cutoff_coefficient=25,
+                                  episode_iterations=400)),
 }
 POOL_SEED = 1234
 GAE_SEED = 0

@@ -55,8 +55,10 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
     ("discovery_node", (8, 16), 100, 24, 60, {}),
     ("control", (6, 14), 100, 32, 90, _DEFENDER),     # re-imaging defender on its Philox streams (3.. scan, 5.. detection)
     ("discovery", (8, 16), 100, 24, 60, dict(precise_graph_encoding=True)),
+    ("control", (8, 20), 100, 24, 70, dict(precise_action_space_positions=True, proportional_cutoff_coefficient=3)),
+    ("control", (8, 14), 100, 16, 60, dict(precise_action_space_positions=True, precise_graph_encoding=True)),
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
-        "control-node", "discovery-node", "defender-philox", "precise-encoding"])
+        "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
     from scipy.spatial import distance
