@@ -587,6 +587,29 @@ void* cbs_state_ptr(cbs_handle* h, int32_t field) {
   return p;
 }
 
+int cbs_get_state(cbs_handle* h, cbs_state_view* out) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!out) return fail(h, CBS_ERR_INVALID_ARG, "cbs_get_state: null argument");
+  const Params& P = h->P;
+  const State& S = h->S;
+  out->num_envs = P.B; out->max_nodes = P.ncap; out->words = P.words; out->mask_pitch = P.mpitch; out->scalar_pitch = SCAL_PITCH;
+  out->obs_dim = P.obs_dim; out->slots = P.slots; out->num_masks = N_MASKS;
+  out->masks = S.masks; out->scalars = S.scal; out->disc_order = S.disc_order; out->owned_order = S.owned_order;
+  out->pair_slot = S.pair_slot; out->obs = S.obs; out->terminal_obs = S.term_obs; out->sel = S.sel; out->dist = S.dist;
+  out->reward64 = S.reward64; out->last_stats = S.last_stats; out->stat_accum = S.accum;
+  return CBS_OK;
+}
+
+int cbs_episode_stats(cbs_handle* h, double* out_host) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!out_host) return fail(h, CBS_ERR_INVALID_ARG, "cbs_episode_stats: null argument");
+  CK(h, cudaDeviceSynchronize());
+  CK(h, cudaMemcpy(out_host, h->S.last_stats, (size_t)h->P.B * 14 * sizeof(double), cudaMemcpyDeviceToHost));
+  return CBS_OK;
+}
+
 int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream) {
   int rc = check_ready(h);
   if (rc) return rc;

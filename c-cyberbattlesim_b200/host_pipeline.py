@@ -64,6 +64,14 @@ class ShardedHostEnv:
         for e in self.envs:
             e.host_sync()
 
+    def set_cut_off(self, cut_off: int):
+        for e in self.envs:
+            e.set_cut_off(cut_off)
+
+    def set_proportional_cutoff_coefficient(self, coefficient: float):
+        for e in self.envs:
+            e.set_proportional_cutoff_coefficient(coefficient)
+
     # ---- what CyberBattleVecEnv reads at episode ends ----
     def terminal_obs(self) -> np.ndarray:
         return np.concatenate([e.terminal_obs() for e in self.envs], axis=0)

@@ -45,6 +45,13 @@ class CbsScenarioTables(ct.Structure):
                 [("num_feasible", i32), ("sc_interest", P)] + [(n, P) for n in _SCENARIO_PTRS2])
 
 
+class CbsStateView(ct.Structure):
+    """cbs_state_view (include/cbsim.h): every state array of a handle as device pointers"""
+    _fields_ = ([(n, i32) for n in ("num_envs", "max_nodes", "words", "mask_pitch", "scalar_pitch", "obs_dim", "slots", "num_masks")] +
+                [(n, P) for n in ("masks", "scalars", "disc_order", "owned_order", "pair_slot", "obs", "terminal_obs", "sel", "dist",
+                                  "reward64", "last_stats", "stat_accum")])
+
+
 _GAE_PTRS = ["node_static", "dyn_proj", "vuln_h", "nn0_b", "bn1_scale", "bn1_shift", "gcn_wt", "bn2_scale", "bn2_shift"]
 
 
@@ -55,7 +62,7 @@ class CbsGaeTables(ct.Structure):
 # every symbol include/cbsim.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
            "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_defender_draws", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition", "cbs_observe",
-           "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_step_host_async", "cbs_host_sync", "cbs_read_state", "cbs_state_ptr", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_debug_observe_trace", "cbs_launch_count",
+           "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_step_host_async", "cbs_host_sync", "cbs_read_state", "cbs_state_ptr", "cbs_get_state", "cbs_episode_stats", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_debug_observe_trace", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
 
 # cbs_field
@@ -123,6 +130,8 @@ def load_library():
     lib.cbs_profile_step.argtypes = [H, P, P, P, P]
     lib.cbs_read_state.argtypes = [H, i32, P, i64]
     lib.cbs_read_state.restype = i64
+    lib.cbs_get_state.argtypes = [H, P]
+    lib.cbs_episode_stats.argtypes = [H, P]
     lib.cbs_state_ptr.argtypes = [H, i32]
     lib.cbs_state_ptr.restype = P
     lib.cbs_reset_stat_accum.argtypes = [H, P]

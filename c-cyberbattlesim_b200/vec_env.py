@@ -34,7 +34,10 @@ def _obs_dict(obs: np.ndarray):
 
 
 class CyberBattleVecEnv(_SB3VecEnv):
-    def __init__(self, env: BatchedCyberBattleEnv, lazy_infos: bool = False):
+    """``env``: a :class:`BatchedCyberBattleEnv`, or a :class:`~ccbs_b200.host_pipeline.ShardedHostEnv` (the same batch cut
+    into handles whose host copies and kernels overlap — the faster choice when the trainer lives on the host)."""
+
+    def __init__(self, env, lazy_infos: bool = False):
         self.env = env
         self.num_envs = env.num_envs
         self.observation_space = spaces.observation_space(env.obs_dim - 2)

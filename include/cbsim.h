@@ -259,6 +259,31 @@ typedef enum {
 #define CBS_NUM_ACCUM 20
 /* synchronous device->host copy of one state field; bytes must equal the field size (query with dst NULL). */
 int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes);
+/* All state arrays a parity test or a zero-copy consumer needs, in one call (device pointers, valid for the handle's
+ * lifetime; layouts as documented at cbs_field).  SURVEY 8(b): `cbs_get_state(h, cbs_state_view*)`. */
+typedef struct {
+  int32_t num_envs, max_nodes, words, mask_pitch, scalar_pitch, obs_dim, slots, num_masks;
+  uint32_t* masks;         /* CBS_F_MASKS */
+  int32_t* scalars;        /* CBS_F_SCALARS (sector-major) */
+  uint8_t* disc_order;     /* CBS_F_DISC_ORDER */
+  uint8_t* owned_order;    /* CBS_F_OWNED_ORDER */
+  uint8_t* pair_slot;      /* CBS_F_PAIR_SLOT */
+  float* obs;              /* CBS_F_OBS */
+  float* terminal_obs;     /* CBS_F_TERMINAL_OBS */
+  int32_t* sel;            /* CBS_F_SEL */
+  double* dist;            /* CBS_F_DIST */
+  double* reward64;        /* CBS_F_REWARD64 */
+  double* last_stats;      /* CBS_F_LAST_STATS */
+  double* stat_accum;      /* CBS_F_STAT_ACCUM */
+} cbs_state_view;
+int cbs_get_state(cbs_handle* h, cbs_state_view* out);
+
+/* get_statistics() (cyberbattle_env.py:517-524) of the last finished episode of every env, copied to the host:
+ * out_host[B][14] = owned, discovered, not_discovered, disrupted, num_nodes, ownable, discoverable, disruptable,
+ * network_availability, reimaged, num_events, discovered_amount, discoverable_amount, goal_reached.  float64 because
+ * network_availability is a ratio (SURVEY 8(b) sketched int64).  Synchronises the device. */
+int cbs_episode_stats(cbs_handle* h, double* out_host);
+
 /* device pointer of a state field (for zero-copy consumers such as an NCCL all-reduce of CBS_F_STAT_ACCUM) */
 void* cbs_state_ptr(cbs_handle* h, int32_t field);
 int cbs_reset_stat_accum(cbs_handle* h, uintptr_t stream);

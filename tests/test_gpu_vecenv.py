@@ -135,3 +135,55 @@ def test_sharded_host_env_matches_single_handle():
                 assert np.array_equal(x, y), f"shards {shards} step {t}"
         assert np.array_equal(term, ref_term) and np.array_equal(stats, ref_stats)
         assert acc["episodes"] == ref_acc["episodes"] > B and abs(acc["return_sum"] - ref_acc["return_sum"]) < 1e-6 * abs(ref_acc["return_sum"])
+
+
+def test_vec_env_over_sharded_host_env():
+    """The SB3 adapter gives the same rollout over the pipelined host env as over one handle."""
+    import ccbs_b200 as cb
+    from ccbs_b200.vec_env import CyberBattleVecEnv
+    specs = [cb.synthetic_spec(520 + k, 9) for k in range(2)]
+    w, cfg = cb.GaeWeights.random(0), cb.EnvConfig()
+    rng = np.random.default_rng(8)
+    actions = rng.uniform(-4, 4, size=(30, 20, 905)).astype(np.float32)
+
+    def rollout(venv):
+        out = [venv.reset()]
+        for a in actions:
+            obs, rew, done, infos = venv.step(a)
+            out.append((obs, rew, done, [(i["source_node"], i["target_node"], i["vulnerability"], i["outcome"], i["end_episode_reason"],
+                                          i.get("episode_stats")) for i in infos]))
+        venv.close()
+        return out
+
+    a = rollout(CyberBattleVecEnv(cb.BatchedCyberBattleEnv(specs, w, cfg, num_envs=20, seed=5)))
+    b = rollout(CyberBattleVecEnv(cb.ShardedHostEnv(specs, w, cfg, num_envs=20, shards=3, seed=5)))
+    for k in ("graph_embeddings", "discrete_features"):
+        assert np.array_equal(a[0][k], b[0][k])
+    for (oa, ra, da, ia), (ob, rb, db, ib) in zip(a[1:], b[1:]):
+        assert np.array_equal(oa["graph_embeddings"], ob["graph_embeddings"]) and np.array_equal(ra, rb) and np.array_equal(da, db)
+        assert ia == ib
+
+
+def test_state_view_and_episode_stats_calls():
+    """cbs_get_state hands out the same device pointers as cbs_state_ptr; cbs_episode_stats copies the 14-tuples."""
+    import ctypes as ct
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200 import lib as L
+    env = cb.BatchedCyberBattleEnv([cb.synthetic_spec(31, 10)], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=12, seed=4)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+    for _ in range(25):
+        env.step(torch.rand(12, 905, device="cuda", generator=g) * 8 - 4, None)
+    env.sync()
+    view = L.CbsStateView()
+    assert env.lib.cbs_get_state(env._h, ct.byref(view)) == 0
+    assert (view.num_envs, view.words, view.obs_dim, view.num_masks) == (12, 1, 194, cb.constants.N_MASKS)
+    for name, field in (("masks", L.F_MASKS), ("scalars", L.F_SCALARS), ("obs", L.F_OBS), ("sel", L.F_SEL), ("dist", L.F_DIST),
+                        ("last_stats", L.F_LAST_STATS), ("stat_accum", L.F_STAT_ACCUM), ("pair_slot", L.F_PAIR_SLOT)):
+        assert getattr(view, name) == env.lib.cbs_state_ptr(env._h, field), name
+    stats = np.empty((12, 14), np.float64)
+    assert env.lib.cbs_episode_stats(env._h, stats.ctypes.data_as(ct.c_void_p)) == 0
+    assert np.array_equal(stats, env.last_stats()) and stats[:, 4].max() == 10
+    env.close()
