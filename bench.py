@@ -365,6 +365,19 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return total_envs * e2e_steps / float(tt.item())
 
+    # what the link alone allows: the same pinned action buffer copied to the device, nothing else (CUDA events)
+    d_probe = torch.empty(B, C.ACTION_DIM, dtype=torch.float32, device=dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        d_probe.copy_(h_ring[0], non_blocking=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(20):
+        d_probe.copy_(h_ring[k % 2], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_ms = ev0.elapsed_time(ev1) / 20
+    del d_probe
     e2e_single = time_host_steps(env.step_host)
     from ccbs_b200.host_pipeline import ShardedHostEnv
     penv = ShardedHostEnv(specs, weights, cfg, num_envs=B, shards=args.host_shards, device=local_rank, seed=7,
@@ -426,7 +439,10 @@ def main():
             "clocks": sampler.summary(), "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": f"ShardedHostEnv.step_host: {args.host_shards} handles x cbs_step_host_async, pinned host buffers",
-                    "gpu_launches_per_step": e2e_launches_per_step, "single_handle_value": e2e_single},
+                    "gpu_launches_per_step": e2e_launches_per_step, "single_handle_value": e2e_single,
+                    "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
+                    "pcie_bound_value": total_envs / (h2d_ms * 1e-3),   # env-steps/s if a step cost only its action copy
+                    "frac_of_pcie_bound": e2e_value / (total_envs / (h2d_ms * 1e-3))},
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
         }
