@@ -313,7 +313,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
   AL(pair_epoch, P.precise_positions ? B * P.ncap * P.ncap : 1);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
-  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, 3 * B); AL(work_ctr, 8); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
+  AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, (size_t)OBS_CLASSES * B); AL(work_ctr, 4 + OBS_CLASSES + 2); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * P.obs_dim); AL(term_obs, B * P.obs_dim); AL(sel, B * 4); AL(dist, B); AL(reward64, B);

@@ -21,6 +21,8 @@ constexpr int MAX_NODES = 128;
 #define CBS_OBS_SMEM_NODES 32   // visible graphs up to this many nodes keep their embeddings in shared memory (k_observe.cu)
 #endif
 constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: four sectors of 8 words
+constexpr int OBS_CLASSES = 6;  // observe work classes, heaviest first (transition.cuh): the observe kernel's duration is set by its
+                                // longest items (an episode end behind a 30-node re-encode), so they must be claimed first
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 
 // outcome kinds (simulation/model.py:66-193)
@@ -163,8 +165,8 @@ struct State {  // mutable, device pointers
   float* vt;             // [B][Ug]  action x vulnerability-embedding products (decode GEMM output)
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   int32_t* errflag;      // [1]
-  int32_t* worklist;     // [3][B] envs whose step needs graph work, by cost class (episode end / re-encode / edge only)
-  int32_t* work_ctr;     // [0] worklist length, [1] finished-warp counter, [2] next item (dynamic scheduling), [4..6] class list lengths
+  int32_t* worklist;     // [OBS_CLASSES][B] envs whose step needs graph work, by cost class
+  int32_t* work_ctr;     // [1] finished-warp counter, [2] next item (dynamic scheduling), [4 .. 4 + OBS_CLASSES) class list lengths
   int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)
   int32_t* bin_cnt;      // [2][SCHED_BINS + 1] envs per cost bin (double buffered; filled by the transition for the next decode), [SCHED_BINS] = finished-warp counter
   int32_t* bin_list;     // [2][SCHED_BINS][B] env ids per bin

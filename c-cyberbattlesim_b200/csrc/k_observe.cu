@@ -572,9 +572,11 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
 
   // mode 1 (cbs_reset): every env, optionally masked.  mode 0 (after a transition): only the envs the
   // transition kernel put on the worklist — the others keep their cached observation untouched.
-  // mode 0: three class lists (episode end, re-encode, edge only) are consumed as one sequence, heaviest class first
-  const int c0 = (mode == 1) ? P.B : S.work_ctr[4], c1 = (mode == 1) ? 0 : S.work_ctr[5], c2 = (mode == 1) ? 0 : S.work_ctr[6];
-  const int count = c0 + c1 + c2;
+  // mode 0: the OBS_CLASSES class lists are consumed as one sequence, heaviest class first
+  int cls_end[OBS_CLASSES];                     // exclusive end of every class in the concatenated item sequence
+  int count = 0;
+#pragma unroll
+  for (int k = 0; k < OBS_CLASSES; ++k) { count += (mode == 1) ? (k == 0 ? P.B : 0) : S.work_ctr[4 + k]; cls_end[k] = count; }
   int i = gw;                                   // mode 1: static stride.  mode 0: items are claimed one at a time
   for (;;) {
     if (mode == 0) {
@@ -584,9 +586,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
     if (i >= count) break;
     int b = i;
     if (mode == 0) {
-      if (i < c0) b = S.worklist[i];
-      else if (i < c0 + c1) b = S.worklist[(size_t)P.B + (i - c0)];
-      else b = S.worklist[(size_t)2 * P.B + (i - c0 - c1)];
+      int k = 0, first = 0;
+#pragma unroll
+      for (int q = 0; q < OBS_CLASSES - 1; ++q) if (i >= cls_end[q]) { k = q + 1; first = cls_end[q]; }
+      b = S.worklist[(size_t)k * P.B + (i - first)];
     }
     // node-embedding buffers: shared memory while the env's visible graph has <= 32 nodes (always, when the
     // scenarios have <= 32 nodes), its slab of the L2-resident scratch otherwise.  A reset shrinks the graph to 1 node.
@@ -659,7 +662,9 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
   if (mode == 0 && lane == 0) {   // the last warp to run dry clears the counters for the next transition
     __threadfence();
     if (atomicAdd(&S.work_ctr[1], 1) == total_warps - 1) {
-      S.work_ctr[0] = 0; S.work_ctr[1] = 0; S.work_ctr[2] = 0; S.work_ctr[4] = 0; S.work_ctr[5] = 0; S.work_ctr[6] = 0;
+      S.work_ctr[1] = 0; S.work_ctr[2] = 0;
+#pragma unroll
+      for (int k = 0; k < OBS_CLASSES; ++k) S.work_ctr[4 + k] = 0;
       __threadfence();
     }
   }

@@ -14,13 +14,13 @@ namespace cbs {
 constexpr int TR_THREADS = CBS_TR_THREADS;
 constexpr int TR_SC_SMEM = 64;   // scenario records kept in shared memory (larger sets are read through L2)
 
-// Appends every thread's env to one of the SCHED_BINS decode cost bins (`bin` < 0: none) and to one of the three observe
+// Appends every thread's env to one of the SCHED_BINS decode cost bins (`bin` < 0: none) and to one of the OBS_CLASSES observe
 // class lists (`cls` < 0: none) with ONE global atomic per list and CTA: positions inside the CTA come from shared-memory
 // counters, the CTA's range from a single atomicAdd on the list's counter.
 __device__ __forceinline__ void cta_append2(int bin, int cls, int b, int32_t* __restrict__ bin_cnt, int32_t* __restrict__ bin_list,
                                             int32_t* __restrict__ cls_cnt, int32_t* __restrict__ cls_list, int cap, int32_t* errflag,
                                             int* sh_cnt, int* sh_base) {
-  constexpr int NL = SCHED_BINS + 3;
+  constexpr int NL = SCHED_BINS + OBS_CLASSES;
   if (threadIdx.x < NL) sh_cnt[threadIdx.x] = 0;
   __syncthreads();
   int pos_bin = 0, pos_cls = 0;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(TR_THREADS, DEF ? 1 : CBS_TR_MINB)
 transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_in, const double* __restrict__ dist_in,
                   const float* __restrict__ uniforms, int sched_out, float* __restrict__ reward_out, uint8_t* __restrict__ done_out,
                   uint8_t* __restrict__ trunc_out, uint8_t* __restrict__ outcome_out) {
-  __shared__ int sh_cnt[SCHED_BINS + 3], sh_base[SCHED_BINS + 3];
+  __shared__ int sh_cnt[SCHED_BINS + OBS_CLASSES], sh_base[SCHED_BINS + OBS_CLASSES];
   __shared__ int4 sh_sc[2 * TR_SC_SMEM];
   const int b = blockIdx.x * TR_THREADS + threadIdx.x;
   const bool live = b < P.B;
@@ -76,7 +76,7 @@ transition_kernel(Tables T, Params P, State S, const int32_t* __restrict__ sel_i
                                           reward_out, done_out, trunc_out, outcome_out);
     in.store_hot(S, b);
   }
-  // cost-binned env list for the next decode (longest tables first) and the observe kernel's three class lists: the
+  // cost-binned env list for the next decode (longest tables first) and the observe kernel's class lists: the
   // two appends share their barriers
   cta_append2(live ? sched_bin(west) : -1, cls, b, S.bin_cnt + sched_out * (SCHED_BINS + 1),
               S.bin_list + (size_t)sched_out * SCHED_BINS * P.B, S.work_ctr + 4, S.worklist, P.B, S.errflag, sh_cnt, sh_base);

@@ -184,7 +184,7 @@ struct TransitionIn {
 // counts) come from the scenario tables, so sectors 2-3 of the record are never touched and sector 1 only when a list
 // changes.  Table look-ups go level by level (scenario record -> instance index / node values -> instance record ->
 // firewall word), every level's loads issued together and ahead of the validity chain that consumes them.
-// Returns the env's observe work class (0 episode end, 1 re-encode, 2 edge only) or -1.
+// Returns the env's observe work class (0 .. OBS_CLASSES-1, heaviest first) or -1.
 template <bool DEF, bool ENQ = true, bool REG = false>
 static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, TransitionIn<REG>& in,
                                             const int4* __restrict__ sc_pack, bool have_uniform, bool write_sel, int sched_out,
@@ -500,8 +500,11 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   }
   int cls = -1;
   if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
-    // three cost classes, claimed heaviest first: episode end (statistics + reset + encode + table), re-encode, edge only
-    cls = (flags & FL_FINISHED_THIS_STEP) ? 0 : ((flags & FL_REENCODE) ? 1 : 2);
+    // OBS_CLASSES cost classes, claimed heaviest first.  An item costs about (re-encode ? 6 + 1.1 n : 0) + (episode end:
+    // statistics + reset + encode + table ? 18 : 0) + 2 us with n = discovered nodes; the kernel ends with its longest item.
+    const int n = DEF ? SC(S_N_DISC) : n_disc_w;
+    const bool fin = flags & FL_FINISHED_THIS_STEP, enc = flags & FL_REENCODE;
+    cls = fin ? (enc ? 0 : 2) : (enc ? (n > 20 ? 1 : (n > 10 ? 3 : 4)) : 5);
     if (ENQ) {
       const int slot = atomicAdd(&S.work_ctr[4 + cls], 1);
       if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);
