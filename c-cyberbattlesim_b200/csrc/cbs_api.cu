@@ -312,6 +312,8 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
   else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
   AL(pair_epoch, P.precise_positions ? B * P.ncap * P.ncap : 1);
+  static_assert(OBS_DIM + NODE_EMB <= RC_Z, "reset-cache entry too small for the observation");
+  AL(reset_cache, (size_t)Nn * RC_PITCH); AL(reset_cache_flag, Nn);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
   AL(z16_hist, B * P.slots * P.ncap * NODE_EMB); AL(worklist, (size_t)OBS_CLASSES * B); AL(work_ctr, 4 + OBS_CLASSES + 2); AL(work_est, B); AL(bin_cnt, 2 * (SCHED_BINS + 1)); AL(bin_list, (size_t)2 * SCHED_BINS * B);
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);

@@ -21,6 +21,10 @@ constexpr int MAX_NODES = 128;
 #define CBS_OBS_SMEM_NODES 32   // visible graphs up to this many nodes keep their embeddings in shared memory (k_observe.cu)
 #endif
 constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: four sectors of 8 words
+// reset cache: what the first encode of an episode produces depends on (scenario, starter) only — one entry per scenario node
+constexpr int RC_Z = 264;       // floats [0, obs_dim) observation, [RC_Z, RC_Z + 64) the starter's embedding, [RC_N2] its squared norm
+constexpr int RC_N2 = RC_Z + NODE_EMB;
+constexpr int RC_PITCH = 336;
 constexpr int OBS_CLASSES = 6;  // observe work classes, heaviest first (transition.cuh): the observe kernel's duration is set by its
                                 // longest items (an episode end behind a 30-node re-encode), so they must be claimed first
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
@@ -164,6 +168,8 @@ struct State {  // mutable, device pointers
   int32_t* starter_queue;  // [B][qlen] or nullptr
   float* vt;             // [B][Ug]  action x vulnerability-embedding products (decode GEMM output)
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
+  float* reset_cache;          // [total scenario nodes][RC_PITCH], filled by the first reset from each (scenario, starter)
+  int32_t* reset_cache_flag;   // [total scenario nodes] 1 = entry valid
   int32_t* errflag;      // [1]
   int32_t* worklist;     // [OBS_CLASSES][B] envs whose step needs graph work, by cost class
   int32_t* work_ctr;     // [1] finished-warp counter, [2] next item (dynamic scheduling), [4 .. 4 + OBS_CLASSES) class list lengths

@@ -452,7 +452,7 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
 }
 
 // ---- reset (cyberbattle_env.py:134-186,189-296 ; compressed:158-189 ; switch.py:151-167,218-220) ----
-__device__ void reset_env(const Tables& T, const Params& P, const State& S, int b, int lane) {
+__device__ int2 reset_env(const Tables& T, const Params& P, const State& S, int b, int lane) {
   const uint64_t genv = (uint64_t)(P.global_env_offset + b);
   const int episodes = scalar(S, P, S_EPISODES, b);
   int sc = scalar(S, P, S_SCENARIO, b);
@@ -514,6 +514,49 @@ __device__ void reset_env(const Tables& T, const Params& P, const State& S, int 
     *reinterpret_cast<double*>(&scalar(S, P, S_EP_RETURN, b)) = 0.0;
   }
   __syncwarp();
+  return make_int2(sc, starter);
+}
+
+// ---- first observation of an episode.  The visible graph is the starter alone, so encode + table depend on (scenario,
+//      starter) only: the first reset from a pair runs the generic code and publishes its result (observation, the
+//      starter's embedding and squared norm); every later one copies the entry and writes the one-pair table directly.
+//      The entry holds what the generic path computed, bit for bit, so results do not depend on who filled it. ----
+__device__ bool reset_from_cache(const Tables& T, const Params& P, const State& S, int b, int lane, int sc, int starter) {
+  const int g = T.sc_node_off[sc] + starter;
+  int hit = 0;
+  if (lane == 0) hit = *reinterpret_cast<volatile const int32_t*>(S.reset_cache_flag + g);
+  hit = __shfl_sync(0xFFFFFFFFu, hit, 0);
+  if (!hit) return false;
+  const float* rc = S.reset_cache + (size_t)g * RC_PITCH;
+  for (int idx = lane; idx < P.obs_dim; idx += 32) S.obs[(size_t)b * P.obs_dim + idx] = __ldcg(rc + idx);
+  const float2 z = __ldcg(reinterpret_cast<const float2*>(rc + RC_Z) + lane);
+  const size_t slab = (size_t)b * P.slots * P.ncap;         // snapshot slot 0 of this env
+  reinterpret_cast<float2*>(S.z_hist + (slab + starter) * NODE_EMB)[lane] = z;
+  reinterpret_cast<__half2*>(S.z16_hist + (slab + starter) * NODE_EMB)[lane] = __floats2half2_rn(z.x, z.y);
+  if (lane == 0) {
+    S.zn2_hist[slab + starter] = __ldcg(rc + RC_N2);
+    const size_t pp = (size_t)b * P.ncap * P.ncap + (size_t)starter * P.ncap + starter;   // the (starter, starter) pair
+    S.pair_slot[pp] = 0;
+    if (P.defender) S.pair_opos[pp] = 0;
+    if (P.precise_positions) S.pair_epoch[pp] = 0;
+    S.work_est[b] = T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g];      // local + remote candidate rows of the starter
+    scalar(S, P, S_N_SLOTS, b) = 1;
+    scalar(S, P, S_N_ENCODES, b) += 1;
+  }
+  __syncwarp();
+  return true;
+}
+__device__ void reset_cache_publish(const Tables& T, const Params& P, const State& S, const WarpScratch& W, int b, int lane, int sc,
+                                    int starter) {
+  const int g = T.sc_node_off[sc] + starter;
+  float* rc = S.reset_cache + (size_t)g * RC_PITCH;
+  __syncwarp();
+  for (int idx = lane; idx < P.obs_dim; idx += 32) rc[idx] = S.obs[(size_t)b * P.obs_dim + idx];
+  reinterpret_cast<float2*>(rc + RC_Z)[lane] = reinterpret_cast<const float2*>(W.y)[lane];      // position 0 = the starter
+  if (lane == 0) rc[RC_N2] = S.zn2_hist[(size_t)b * P.slots * P.ncap + starter];
+  __threadfence();
+  __syncwarp();
+  if (lane == 0) atomicExch(S.reset_cache_flag + g, 1);
 }
 
 // BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
@@ -626,14 +669,17 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       __syncwarp();
     }
     if (do_reset) {
-      reset_env(T, P, S, b, lane);
+      const int2 ss = reset_env(T, P, S, b, lane);
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[3])); }
-      W.y = W.ysm;                               // a fresh episode's graph is one node
-      W.g = W.ysm + SMEM_NODES * NODE_EMB;
-      encode_env(T, P, S, SW, W, b, lane);
+      if (!reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
+        W.y = W.ysm;                               // a fresh episode's graph is one node
+        W.g = W.ysm + SMEM_NODES * NODE_EMB;
+        encode_env(T, P, S, SW, W, b, lane);
+        if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
+        else build_table<false>(T, P, S, W, b, lane, false);
+        reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
+      }
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[4])); }
-      if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
-      else build_table<false>(T, P, S, W, b, lane, false);
       // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even
       // if nothing else changes
       if (is_node_goal(P) && lane == 0) scalar(S, P, S_FLAGS, b) = FL_DIRTY | FL_INTEREST_IN_GRAPH;
