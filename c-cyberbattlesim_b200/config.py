@@ -76,6 +76,8 @@ class EnvConfig:
     # compressed:86,419-427,498-506: every table-maintaining encode also refreshes the rows of the (source, target) pairs
     # from which the action's source or target node can be reached in the visible graph (their embeddings may have changed)
     precise_action_space_positions: bool = False
+    # compressed:82,570-590: metric of the nearest-row decode: 'cosine' (scipy cdist, default), 'l1', 'l2', 'inf' (np.linalg.norm)
+    distance_metric: str = "cosine"
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
 
@@ -83,6 +85,8 @@ class EnvConfig:
         self.goal = self.goal.lower()
         if self.goal not in C.GOALS:
             raise ValueError(f"goal '{self.goal}' is not supported by the batched env (supported: {sorted(C.GOALS)})")
+        if self.distance_metric not in C.METRICS:
+            raise ValueError(f"Unsupported metric '{self.distance_metric}'. Use 'l1', 'l2', 'inf', or 'cosine'.")   # compressed:578-579
         if not self.rewards_dict:
             self.rewards_dict = dict(DEFAULT_REWARDS[self.goal])
         if not self.penalties_dict:
@@ -121,8 +125,6 @@ class EnvConfig:
                 if k not in train_config and f"{k}_min" in train_config:
                     mid = (train_config[f"{k}_min"] + train_config[f"{k}_max"]) / 2
                     train_config[k] = mid if k == "detect_probability" else int(round(mid))
-        if train_config.get("distance_metric", "cosine") != "cosine":
-            raise ValueError("only the cosine decode metric is implemented")
         if train_config.get("sample_subset_samples"):
             import warnings
             warnings.warn("sample_subset_samples is ignored: the batched decode always scans the full action table "
@@ -159,4 +161,5 @@ class EnvConfig:
                     interest_node_value=self.interest_node_value, switch_interest_node_interval=1,
                     penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None,
                     precise_graph_encoding=self.precise_graph_encoding,
-                    precise_action_space_positions=self.precise_action_space_positions)
+                    precise_action_space_positions=self.precise_action_space_positions,
+                    distance_metric=self.distance_metric)

@@ -110,6 +110,9 @@ ST_STOPPED, ST_RUNNING, ST_IMAGING = 0, 1, 2
 # per scenario; the observation then carries that node's embedding as 64 extra floats, compressed:119-125)
 GOAL_CONTROL, GOAL_DISCOVERY, GOAL_DISRUPTION = 0, 1, 2
 GOAL_CONTROL_NODE, GOAL_DISCOVERY_NODE, GOAL_DISRUPTION_NODE = 3, 4, 5
+# decode metrics of find_closest_action_embedding (compressed:571-576); the values are cbs_config.distance_metric
+METRIC_COSINE, METRIC_L1, METRIC_L2, METRIC_INF = 0, 1, 2, 3
+METRICS = {"cosine": METRIC_COSINE, "l1": METRIC_L1, "l2": METRIC_L2, "inf": METRIC_INF}
 GOALS = {"control": GOAL_CONTROL, "discovery": GOAL_DISCOVERY, "disruption": GOAL_DISRUPTION,
          "control_node": GOAL_CONTROL_NODE, "discovery_node": GOAL_DISCOVERY_NODE, "disruption_node": GOAL_DISRUPTION_NODE}
 

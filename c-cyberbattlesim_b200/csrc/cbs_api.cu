@@ -14,6 +14,7 @@ cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float
 bool decode_gemm_tc_available();
 cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int, int, const float*, float*, uint8_t*,
                                  int32_t*, double*, cudaStream_t);
+cudaError_t launch_decode_metric(const Tables&, const Params&, const State&, const float*, double*, int, int, int32_t*, double*, cudaStream_t);
 cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, int, int, cudaStream_t);
 cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, int, float*,
                               uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
@@ -57,6 +58,7 @@ struct cbs_handle {
   int sched_buf = 0;     // cost-bin buffer the next decode reads (the transitions of that step fill the other one)
   int num_sms = 148;
   float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
+  double* vt64 = nullptr;      // [B][Ug] vulnerability part of the l1 / l2 / inf distances (distance_metric != cosine only)
   // host-step staging
   cudaStream_t hstream = nullptr;
   float *h_actions = nullptr, *h_uniforms = nullptr, *h_reward = nullptr;
@@ -139,6 +141,8 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
     return fail(nullptr, CBS_ERR_INVALID_ARG, "scan_capacity must be in 1..%d and scan_frequency >= 1", MAX_SCAN_CAPACITY);
   if (cfg->precise_action_space_positions && cfg->static_defender)
     return fail(nullptr, CBS_ERR_INVALID_ARG, "precise_action_space_positions is not implemented together with a static defender");
+  if (cfg->distance_metric < METRIC_COSINE || cfg->distance_metric > METRIC_INF)
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "Unsupported metric %d. Use 0 cosine, 1 l1, 2 l2 or 3 inf", cfg->distance_metric);   // compressed:578-579
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(nullptr, CBS_ERR_NO_DEVICE, "no CUDA device available (libcbsim has no CPU fallback)");
@@ -174,6 +178,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.detect_prob = cfg->detect_probability;
   P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
   P.precise_positions = cfg->precise_action_space_positions ? 1 : 0;
+  P.metric = cfg->distance_metric;
   *out = h;
   return CBS_OK;
 }
@@ -325,6 +330,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if ((rc = dalloc(h, h->state_allocs, &h->d_sel, B * 4))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->d_dist, B))) return rc;
   if (h->use_tc && (rc = dalloc(h, h->state_allocs, &h->a_packed, B * VULN_EMB))) return rc;
+  if (P.metric != METRIC_COSINE && (rc = dalloc(h, h->state_allocs, &h->vt64, B * (size_t)h->Ug, false))) return rc;
   init_flags_kernel<<<(P.B + 255) / 256, 256>>>(S.scal, P.B);
   CK(h, cudaGetLastError());
   CK(h, cudaDeviceSynchronize());
@@ -405,6 +411,11 @@ int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double
   if (rc) return rc;
   if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_decode: actions is null");
   cudaStream_t st = (cudaStream_t)stream;
+  if (h->P.metric != METRIC_COSINE) {
+    CK(h, launch_decode_metric(h->T, h->P, h->S, actions_dev, h->vt64, h->Ug, h->sched_buf, sel_dev, dist_dev, st));
+    h->launches += 2;
+    return CBS_OK;
+  }
   if ((rc = launch_gemm(h, actions_dev, st))) return rc;
   CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, sel_dev, dist_dev, st));
   h->launches += 1;
@@ -449,12 +460,20 @@ int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev,
   if (rc) return rc;
   if (!actions_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_step: actions is null");
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = launch_gemm(h, actions_dev, st))) return rc;
-  // fused: every warp runs the transition of its env right after decoding it (no separate transition launch)
-  CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 1, uniforms_dev, reward_dev, done_dev,
-                             nullptr, nullptr, st));
-  h->sched_buf ^= 1;
-  h->launches += 1;
+  if (h->P.metric != METRIC_COSINE) {
+    // l1 / l2 / inf decode (k_decode_metric.cu), then the transition as its own launch on the handle's own sel / dist
+    CK(h, launch_decode_metric(h->T, h->P, h->S, actions_dev, h->vt64, h->Ug, h->sched_buf, nullptr, nullptr, st));
+    CK(h, launch_transition(h->T, h->P, h->S, h->S.sel, h->S.dist, uniforms_dev, h->sched_buf ^ 1, reward_dev, done_dev, nullptr, nullptr, st));
+    h->sched_buf ^= 1;
+    h->launches += 3;
+  } else {
+    if ((rc = launch_gemm(h, actions_dev, st))) return rc;
+    // fused: every warp runs the transition of its env right after decoding it (no separate transition launch)
+    CK(h, launch_decode_select(h->T, h->P, h->S, actions_dev, h->vt_stride, h->sched_buf, 1, uniforms_dev, reward_dev, done_dev,
+                               nullptr, nullptr, st));
+    h->sched_buf ^= 1;
+    h->launches += 1;
+  }
   if (info_dev) {   // before observe: an auto-reset clears the per-step flags
     info_kernel<<<(h->P.B + 255) / 256, 256, 0, st>>>(h->P, h->S, info_dev);
     CK(h, cudaGetLastError());
@@ -469,6 +488,7 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
   int rc = check_ready(h);
   if (rc) return rc;
   if (!actions_dev || !out_ms) return fail(h, CBS_ERR_INVALID_ARG, "cbs_profile_step: null argument");
+  if (h->P.metric != METRIC_COSINE) return fail(h, CBS_ERR_INVALID_ARG, "cbs_profile_step times the cosine decode's kernels only");
   cudaStream_t st = (cudaStream_t)stream;
   cudaEvent_t ev[4];
   for (auto& e : ev) CK(h, cudaEventCreate(&e));

@@ -18,6 +18,16 @@ __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int 
 __device__ __forceinline__ bool is_node_goal(const Params& P) { return P.goal >= GOAL_CONTROL_NODE; }
 __device__ __forceinline__ int base_goal(const Params& P) { return is_node_goal(P) ? P.goal - GOAL_CONTROL_NODE : P.goal; }
 
+// rows that create_continuous_action_space never adds to the action table (compressed:532-547)
+__device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter, int interest) {
+  if ((s == t && kind == K_LATERAL) || kind == K_CREDACCESS) return true;                         // compressed:532
+  if (kind != K_DOS) return false;
+  if (P.remove_all && P.goal != GOAL_DISRUPTION && P.goal != GOAL_DISRUPTION_NODE) return true;    // :536-538
+  if (P.remove_main && t == starter) return true;                                                 // :541-543
+  if (P.remove_main && interest >= 0 && P.goal != GOAL_DISRUPTION_NODE && t == interest) return true;   // :545-547
+  return false;
+}
+
 // cost bin of an env for the longest-first decode schedule
 __device__ __forceinline__ int sched_bin(int rows) {
   const int b = 31 - __clz((rows >> 5) | 1);   // rows < 64 -> 0, < 128 -> 1, ...

@@ -36,6 +36,7 @@ enum Kind : int { K_DOS = 0, K_DISCOVERY, K_COLLECTION, K_EXFILTRATION, K_RECON,
 enum Code : int { OC_INVALID_SRC_NOT_OWNED = 16, OC_INVALID_TGT_NOT_DISCOVERED, OC_SRC_NOT_RUNNING, OC_TGT_NOT_RUNNING,
                   OC_NO_VULNERABILITY, OC_NO_PRIVILEGE, OC_OUTCOME_NOT_PRESENT, OC_PORT_NOT_LISTENING, OC_FW_OUTGOING,
                   OC_FW_INCOMING, OC_UNSUCCESSFUL, OC_NO_NEEDED, OC_REPEATED, OC_REMOTE_OUTCOME_LOCAL };
+enum Metric : int { METRIC_COSINE = 0, METRIC_L1 = 1, METRIC_L2 = 2, METRIC_INF = 3 };   // cbs_config.distance_metric (compressed:571-576)
 enum Goal : int { GOAL_CONTROL = 0, GOAL_DISCOVERY = 1, GOAL_DISRUPTION = 2, GOAL_CONTROL_NODE = 3, GOAL_DISCOVERY_NODE = 4,
                   GOAL_DISRUPTION_NODE = 5 };
 enum Mask : int { M_OWNED = 0, M_DISCOVERED, M_VISIBLE, M_HAS_DATA, M_COLLECTED, M_EXFILTRATED, M_PERSISTENCE,
@@ -130,6 +131,7 @@ struct Params {  // configuration, by value
   int ocap;            // capacity of owned_raw
   int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
   int precise_positions;   // precise_action_space_positions (compressed:419-427,498-506): table rows are refreshed, see build_table
+  int metric;              // enum Metric; != METRIC_COSINE: k_decode_metric.cu decodes, the transition runs as its own launch
 };
 
 struct State {  // mutable, device pointers

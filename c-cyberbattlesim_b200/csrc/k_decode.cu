@@ -76,14 +76,7 @@ cudaError_t launch_decode_gemm_simt(const float* actions, int act_stride, const 
 // ------------------------------------------------------------------------------------------------
 // candidate scan + float64 re-score + argmin
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool row_filtered(const Params& P, int kind, int s, int t, int starter, int interest) {
-  if ((s == t && kind == K_LATERAL) || kind == K_CREDACCESS) return true;                         // compressed:532
-  if (kind != K_DOS) return false;
-  if (P.remove_all && P.goal != GOAL_DISRUPTION && P.goal != GOAL_DISRUPTION_NODE) return true;    // :536-538
-  if (P.remove_main && t == starter) return true;                                                 // :541-543
-  if (P.remove_main && interest >= 0 && P.goal != GOAL_DISRUPTION_NODE && t == interest) return true;   // :545-547
-  return false;
-}
+// row_filtered(): cbs_device.cuh
 
 // ------------------------------------------------------------------------------------------------
 // decode_select: one warp per env.  Measured with a per-env cycle trace (tools/select_trace.py): the kernel is a

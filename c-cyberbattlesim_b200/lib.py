@@ -13,7 +13,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("CBS_LIB", "libcbsim.so"))
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 i32, i64, u64, f32, f64 = ct.c_int32, ct.c_int64, ct.c_uint64, ct.c_float, ct.c_double
 P = ct.c_void_p
@@ -27,7 +27,7 @@ class CbsConfig(ct.Structure):
                 ("rewards", f64 * 10), ("penalties", f64 * 18), ("max_slots", i32), ("max_edges", i32),
                 ("decode_margin", f32), ("decode_gemm", i32),
                 ("static_defender", i32), ("scan_capacity", i32), ("scan_frequency", i32), ("precise_graph_encoding", i32),
-                ("detect_probability", f64), ("precise_action_space_positions", i32)]
+                ("detect_probability", f64), ("precise_action_space_positions", i32), ("distance_metric", i32)]
 
 
 _SCENARIO_PTRS = ["sc_num_nodes", "sc_node_off", "sc_port_off", "sc_uvuln_off", "sc_num_uvuln", "sc_instof_off",
@@ -230,4 +230,5 @@ def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0,
     c.detect_probability = float(cfg.detect_probability)
     c.precise_graph_encoding = int(bool(cfg.precise_graph_encoding))
     c.precise_action_space_positions = int(bool(getattr(cfg, "precise_action_space_positions", False)))
+    c.distance_metric = C.METRICS[getattr(cfg, "distance_metric", "cosine")]
     return c

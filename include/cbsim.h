@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CBS_ABI_VERSION 4
+#define CBS_ABI_VERSION 5
 
 /* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
  * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
@@ -88,6 +88,10 @@ typedef struct {
    * from which the action's source or target node can be reached in the visible graph are overwritten with the current
    * node embeddings (their place in the table's insertion order is kept).  Not available with a static defender. */
   int32_t precise_action_space_positions;
+  /* compressed:82,570-590 `distance_metric` of find_closest_action_embedding: 0 'cosine' (scipy cdist, the reference's default),
+   * 1 'l1', 2 'l2', 3 'inf' (np.linalg.norm(action - rows, ord, axis=1), :571-576).  Anything else is rejected like the
+   * reference's ValueError (:578-579).  1..3 decode in float64 (k_decode_metric.cu) and run the transition as its own launch. */
+  int32_t distance_metric;
 } cbs_config;
 
 /* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the
@@ -184,9 +188,10 @@ int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double proportion
  * obs_dev (optional): [num_envs][obs_len] float32 (obs_len = 194, or 258 for *_node goals), written for every env. */
 int cbs_reset(cbs_handle* h, const uint8_t* env_mask_dev, float* obs_dev, uintptr_t stream);
 
-/* replaces find_closest_action_embedding (compressed:570-590, scipy cdist 'cosine' + argmin over the action
- * table).  actions_dev: [num_envs][905] float32.  sel_dev: [num_envs][4] = source node, target node,
- * scenario-local vulnerability index, outcome kind.  dist_dev: [num_envs] float64 cosine distance. */
+/* replaces find_closest_action_embedding (compressed:570-590: scipy cdist 'cosine', or np.linalg.norm with ord 1 / 2 / inf
+ * for cbs_config.distance_metric 1..3, + argmin over the action table).  actions_dev: [num_envs][905] float32.
+ * sel_dev: [num_envs][4] = source node, target node, scenario-local vulnerability index, outcome kind.
+ * dist_dev: [num_envs] float64 distance in the configured metric. */
 int cbs_decode(cbs_handle* h, const float* actions_dev, int32_t* sel_dev, double* dist_dev, uintptr_t stream);
 
 /* replaces CyberBattleEnv.step_attacker_env (cyberbattle_env.py:299-394) incl.

@@ -113,6 +113,7 @@ class OracleEnv:
         # ScanAndReimageCompromisedMachines (_env/static_defender.py:27-60); None -> no defender
         self.defender = getattr(cfg, "static_defender_agent", None) == "reimage"
         self.always_encode = self.defender or bool(getattr(cfg, "precise_graph_encoding", False))   # compressed:401,455-462
+        self.distance_metric = getattr(cfg, "distance_metric", "cosine")                            # compressed:82,100
         self.precise_positions = bool(getattr(cfg, "precise_action_space_positions", False))        # compressed:86,419-427
         self.proportional_cutoff_coefficient = cfg.proportional_cutoff_coefficient
         # create_vulnerabilities_embeddings (compressed:614-618)
@@ -682,12 +683,19 @@ class OracleEnv:
                 self.action_rows[at] = row                                                 # "overwrite if changed"
             self._rows_cache = None
 
-    def find_closest_action_embedding(self, action_vector):
-        """compressed:570-590 with distance_metric='cosine'."""
+    def all_distances(self, action_vector):
+        """Distances of the action to every table row, in table order — compressed:571-584: scipy's cosine cdist, or
+        np.linalg.norm of (action - rows) with ord 1 / 2 / inf; the action is cast to float32 first (:582)."""
         if self._rows_cache is None:
             self._rows_cache = np.array(self.action_rows)
         seg = np.atleast_2d(np.array(action_vector, dtype=np.float32))
-        d = _sp_distance.cdist(seg, self._rows_cache, "cosine").flatten()
+        if self.distance_metric == "cosine":
+            return _sp_distance.cdist(seg, self._rows_cache, "cosine").flatten()
+        return np.linalg.norm(seg - self._rows_cache, ord={"l1": 1, "l2": 2, "inf": np.inf}[self.distance_metric], axis=1)
+
+    def find_closest_action_embedding(self, action_vector):
+        """compressed:570-590."""
+        d = self.all_distances(action_vector)
         i = int(np.argmin(d))
         s, t, vid, kind, vtype, ri = self.action_keys[i]
         return s, t, vid, kind, d[i], i

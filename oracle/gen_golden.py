@@ -45,6 +45,11 @@ CASES = {
     # 100-node "default-like" scenario (configs[0]); >64 nodes exercises 4-word masks
     "g100_control": dict(graph_seed=16, nodes=100, steps=1200, pool_size=560, services_range=(1, 4),
                          vulns_per_service_range=(8, 18), cfg=dict(goal="control")),
+    # BASELINE configs[0] at its stated length: 10 000 steps of one default-like 100-node env with random actions.  Oracle-only
+    # fixture (the CUDA replay of 10 k single steps through the split calls would take minutes; tests/test_gpu_golden.py skips it,
+    # the same scenario class is replayed on the GPU by g100_control)
+    "g100_10k": dict(graph_seed=17, nodes=100, steps=10000, pool_size=560, services_range=(1, 4),
+                     vulns_per_service_range=(8, 18), cfg=dict(goal="control")),
     # every DoS row filtered out of the action table (compressed:536-538), non-default reward scale, stricter isolation filter
     "g14_removeall": dict(graph_seed=19, nodes=14, steps=600,
                           cfg=dict(goal="discovery", remove_all_obstacles=True, remove_main_obstacles=False, winning_reward=300,
@@ -91,6 +96,16 @@ CASES = {
     "p8_positions": dict(graph_seed=53, nodes=8, steps=500, policy=0.02,
                          cfg=dict(goal="control", precise_action_space_positions=True, proportional_cutoff_coefficient=25,
                                   episode_iterations=400)),
+    # decode metrics other than cosine (compressed:571-576: np.linalg.norm of action - rows, ord 1 / 2 / inf)
+    "g12_l1": dict(graph_seed=12, nodes=12, steps=500, cfg=dict(goal="control", distance_metric="l1", proportional_cutoff_coefficient=3)),
+    "g16_l2": dict(graph_seed=13, nodes=16, steps=500, cfg=dict(goal="control", distance_metric="l2", proportional_cutoff_coefficient=3)),
+    "g12_inf": dict(graph_seed=12, nodes=12, steps=500, cfg=dict(goal="discovery", distance_metric="inf", proportional_cutoff_coefficient=3)),
+    "p8_l2": dict(graph_seed=53, nodes=8, steps=500, policy=0.02,
+                  cfg=dict(goal="control", distance_metric="l2", proportional_cutoff_coefficient=25, episode_iterations=400)),
+    "p8_inf": dict(graph_seed=53, nodes=8, steps=400, policy=0.02,
+                   cfg=dict(goal="control", distance_metric="inf", proportional_cutoff_coefficient=25, episode_iterations=400)),
+    "p6_l1": dict(graph_seed=30, nodes=6, steps=400, policy=0.02,
+                  cfg=dict(goal="control", distance_metric="l1", proportional_cutoff_coefficient=25, episode_iterations=400)),
 }
 POOL_SEED = 1234
 GAE_SEED = 0

@@ -221,6 +221,28 @@ def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=N
     return rec
 
 
+def window(rec, actions, uniforms, starters, first_episode, max_steps):
+    """Cut a recorded trace at an episode boundary: the steps of episodes ``first_episode``.. (at most ``max_steps`` of
+    them) with the matching inputs, as a self-contained (record, actions, uniforms, starters).  Episodes are independent
+    given their starter, so a replay of the window must reproduce it exactly (random-action traces without a defender)."""
+    t0 = int(np.argmax(rec["episode"] >= first_episode))
+    if rec["episode"][t0] != first_episode:
+        raise ValueError("first_episode is beyond the trace")
+    t1 = min(len(rec["episode"]), t0 + int(max_steps))
+    out = {}
+    for k, v in rec.items():
+        if k in ("reset_obs", "reset_masks", "stats", "num_episodes"):
+            continue
+        out[k] = np.array(v[t0:t1], copy=True)
+    out["episode"] = out["episode"] - first_episode
+    k = int(np.count_nonzero(out["done"] | out["truncated"]))
+    out["reset_obs"] = rec["reset_obs"][first_episode:first_episode + k + 1]
+    out["reset_masks"] = rec["reset_masks"][first_episode:first_episode + k + 1]
+    out["stats"] = rec["stats"][first_episode:first_episode + k]
+    out["num_episodes"] = np.array(k + 1, np.int32)
+    return out, actions[t0:t1], uniforms[t0:t1], starters[first_episode:]
+
+
 INT_KEYS = ("sel", "code", "done", "truncated", "reason", "masks", "disc_order", "owned_order", "counters",
             "episode", "reset_masks", "num_episodes")   # "policy_rows" is an input, not compared
 

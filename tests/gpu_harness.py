@@ -34,9 +34,7 @@ class TieFollower:
         self._forced = (s, t, vid, kind, d)
         if tuple(int(x) for x in gpu_sel) == want:
             return None
-        rows = self.env._rows_cache
-        from scipy.spatial import distance
-        dd = distance.cdist(np.atleast_2d(np.asarray(action, np.float32)), rows, "cosine").flatten()
+        dd = self.env.all_distances(action)
         cand = [i for i, k in enumerate(self.env.action_keys)
                 if (k[0], k[1], self.vidx[k[2]], k[3]) == tuple(int(x) for x in gpu_sel)]
         assert cand, f"CUDA decode chose {tuple(gpu_sel)} which is not in the oracle's action table (oracle: {want})"

@@ -74,3 +74,11 @@ def test_rejects_bad_arguments(lib):
     assert lib.cbs_create(None, ct.byref(h)) == -1
     with pytest.raises(ValueError):
         cb.EnvConfig(goal="conquer")
+    # compressed:578-579: an unknown decode metric is a ValueError in the reference
+    with pytest.raises(ValueError, match="Unsupported metric"):
+        cb.EnvConfig(distance_metric="l3")
+    cfg = L.make_config(cb.EnvConfig(distance_metric="inf"), num_envs=4)
+    assert cfg.distance_metric == 3
+    cfg.distance_metric = 7
+    assert lib.cbs_create(ct.byref(cfg), ct.byref(h)) == -1
+    assert b"metric" in lib.cbs_last_error(None)

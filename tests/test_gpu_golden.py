@@ -8,8 +8,10 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-CASES = sorted(os.path.splitext(os.path.basename(p))[0]
-               for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+# g100_10k (BASELINE configs[0] at its full 10 000 steps) is an oracle-only fixture: replaying 10 k single steps through the split
+# calls with a host round trip each would take minutes of GPU time; the same scenario class runs here as g100_control
+CASES = sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
+                           for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))) if n != "g100_10k")
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -57,11 +57,16 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
     ("discovery", (8, 16), 100, 24, 60, dict(precise_graph_encoding=True)),
     ("control", (8, 20), 100, 24, 70, dict(precise_action_space_positions=True, proportional_cutoff_coefficient=3)),
     ("control", (8, 14), 100, 16, 60, dict(precise_action_space_positions=True, precise_graph_encoding=True)),
+    # decode metrics other than cosine (compressed:571-576): k_decode_metric.cu + the transition as its own launch inside cbs_step
+    ("control", (8, 24), 120, 40, 60, dict(distance_metric="l1")),
+    ("discovery", (8, 20), 330, 33, 60, dict(distance_metric="l2")),        # Ug > 256: several tiles of the vulnerability part
+    ("control", (20, 40), 120, 24, 50, dict(distance_metric="inf")),
+    ("control", (6, 14), 100, 24, 60, dict(_DEFENDER, distance_metric="l2")),
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
-        "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both"])
+        "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both",
+        "metric-l1", "metric-l2", "metric-inf", "metric-l2-defender"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
-    from scipy.spatial import distance
     import ccbs_b200 as cb
     from ccbs_b200 import lib as L
     from ccbs_b200.batched_env import BatchedCyberBattleEnv
@@ -131,7 +136,7 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
             if got != want:
                 # accepted only as a genuine near-tie of the ORACLE's float64 distances (two table rows whose
                 # node embeddings agree to the last float32 bit or so); the oracle then follows the CUDA pick
-                dd = distance.cdist(np.atleast_2d(actions[t, b]), o._rows_cache, "cosine").flatten()
+                dd = o.all_distances(actions[t, b])
                 cand = [i for i, k in enumerate(o.action_keys) if (k[0], k[1], vidx[b][k[2]], k[3]) == got]
                 assert cand, f"step {t} env {b}: decode {got} is not in the oracle's table (oracle {want})"
                 i = min(cand, key=lambda j: dd[j])

@@ -21,6 +21,16 @@ def test_fixtures_present():
 def test_oracle_replays_reference_trace(name, golden_dir):
     case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
     env = OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"])
+    if name == "g100_10k" and not os.environ.get("CBS_FULL_GOLDEN"):
+        # BASELINE configs[0] at its stated 10 000 steps: the full replay takes ~5 min of oracle time (CBS_FULL_GOLDEN=1; it
+        # passes).  The default suite replays three windows cut at episode boundaries — start, middle, end of the trace.
+        n_ep = int(case["trace"]["num_episodes"])
+        for ep0 in (0, n_ep // 2, max(0, n_ep - 8)):
+            want, a, u, st = tr.window(case["trace"], case["actions"], case["uniforms"], case["starters"], ep0, 600)
+            rec = tr.record(tr.OracleAdapter(env, case["spec"]), a, u, st)
+            report = tr.compare(rec, want, rtol=1e-5, atol=1e-6, label=f"{name}@episode{ep0}")
+            assert report["obs"] <= 1e-5
+        return
     rec = tr.record(tr.OracleAdapter(env, case["spec"]), case["actions"], case["uniforms"], case["starters"],
                     policy_seed=case["policy_seed"], policy_rows=case["policy_rows"], defender_draws=case["defender_draws"])
     report = tr.compare(rec, case["trace"], rtol=1e-5, atol=1e-6, label=name)

@@ -64,8 +64,9 @@ def test_unsupported_reference_options_are_not_silently_dropped():
     assert cfg.static_defender_agent == "reimage" and abs(cfg.detect_probability - 0.1) < 1e-12
     assert (cfg.scan_capacity, cfg.scan_frequency) == (3, 3)
     assert cb.EnvConfig.from_reference_dicts({"static_defender_agent": None}, rewards).static_defender_agent is None
-    with pytest.raises(ValueError):
-        cb.EnvConfig.from_reference_dicts({"distance_metric": "l2"}, rewards)
+    assert cb.EnvConfig.from_reference_dicts({"distance_metric": "l2"}, rewards).distance_metric == "l2"
+    with pytest.raises(ValueError):                                    # compressed:578-579
+        cb.EnvConfig.from_reference_dicts({"distance_metric": "chebyshev"}, rewards)
     with pytest.warns(UserWarning):
         cfg = cb.EnvConfig.from_reference_dicts({"sample_subset_samples": 100, "episode_iterations": 77}, rewards)
     assert cfg.episode_iterations == 77
