@@ -22,6 +22,8 @@ def test_cuda_replays_reference_trace(name, gemm, golden_dir):
     from oracle.cbs_oracle import OracleEnv
     from tests.gpu_harness import replay, TieFollower
     case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
+    if gemm == 1 and case["cfg"].distance_metric != "cosine":
+        pytest.skip("the l1 / l2 / inf decode does not use the contraction the gemm switch selects")
     B = 5
     interest = None if case["interest"] is None else [case["interest"]]
     env = BatchedCyberBattleEnv([case["spec"]], case["weights"], case["cfg"], num_envs=B, auto_reset=True,
