@@ -16,15 +16,24 @@ def masks_to_u64(m, b):
     return out
 
 
+def near_tie_tolerance(metric):
+    """Largest gap between the ORACLE's own float64 distances of two table rows that still counts as a near-tie decided by
+    float32 rounding of the node embeddings.  cosine / l2 / inf: 1e-6.  l1 adds the |rounding differences| of all 128 node-
+    embedding elements instead of letting them cancel (observed 1.006e-6 on p6_l1 between two sources with mathematically
+    equal embeddings, i.e. ~1e-8 per element, below one float32 ulp): 2e-5 = 128 elements x 1.5e-7."""
+    return 2e-5 if metric == "l1" else 1e-6
+
+
 class TieFollower:
     """Runs the oracle in lockstep.  When the CUDA decode picks a different table row than the oracle, the
     pick is accepted only if the ORACLE's own float64 distances of the two rows differ by < tol (a genuine
     near-tie, decided by float32 rounding of the node embeddings); the step then continues with the oracle's
     choice on both sides so that the rest of the trace stays comparable.  Every such event is counted."""
 
-    def __init__(self, oracle_env, spec, starters, tol=1e-6):
+    def __init__(self, oracle_env, spec, starters, tol=None):
         from oracle import trace as tr
-        self.env, self.vidx, self.starters, self.tol = oracle_env, tr.vuln_index(spec), starters, tol
+        self.env, self.vidx, self.starters = oracle_env, tr.vuln_index(spec), starters
+        self.tol = near_tie_tolerance(oracle_env.distance_metric) if tol is None else tol
         self.ep, self.flips, self.max_gap = 0, 0, 0.0
         self.env.reset(starter=int(starters[0]))
 
