@@ -30,25 +30,45 @@ class TieFollower:
     near-tie, decided by float32 rounding of the node embeddings); the step then continues with the oracle's
     choice on both sides so that the rest of the trace stays comparable.  Every such event is counted."""
 
-    def __init__(self, oracle_env, spec, starters, tol=None):
+    def __init__(self, oracle_env, spec, starters, tol=None, golden_sel=None):
         from oracle import trace as tr
         self.env, self.vidx, self.starters = oracle_env, tr.vuln_index(spec), starters
         self.tol = near_tie_tolerance(oracle_env.distance_metric) if tol is None else tol
-        self.ep, self.flips, self.max_gap = 0, 0, 0.0
+        # decoded actions of the recorded reference trace, [T, 4].  The oracle's own torch-CPU rounding differs from machine to
+        # machine, so on a near-tie the oracle running HERE may pick the other row than the recorded reference did (seen on
+        # p6_l1: the oracle picks source 4 like the record in the build container and source 3 on the GPU box, gap 1.0e-6).
+        # Such a step follows the record — under the same near-tie test — so that the rest of the trace stays comparable.
+        self.golden_sel = golden_sel
+        self.ep, self.flips, self.oracle_flips, self.max_gap = 0, 0, 0, 0.0
         self.env.reset(starter=int(starters[0]))
 
-    def resolve(self, action, gpu_sel):
-        s, t, vid, kind, d, _ = self.env.find_closest_action_embedding(action)
-        want = (s, t, self.vidx[vid], kind)
-        self._forced = (s, t, vid, kind, d)
-        if tuple(int(x) for x in gpu_sel) == want:
-            return None
+    def _rows_of(self, sel):
+        return [i for i, k in enumerate(self.env.action_keys) if (k[0], k[1], self.vidx[k[2]], k[3]) == sel]
+
+    def resolve(self, action, gpu_sel, t=None):
         dd = self.env.all_distances(action)
-        cand = [i for i, k in enumerate(self.env.action_keys)
-                if (k[0], k[1], self.vidx[k[2]], k[3]) == tuple(int(x) for x in gpu_sel)]
-        assert cand, f"CUDA decode chose {tuple(gpu_sel)} which is not in the oracle's action table (oracle: {want})"
-        gap = float(min(dd[i] for i in cand) - d)
-        assert gap < self.tol, f"CUDA decode chose {tuple(gpu_sel)} (d gap {gap:.3e}) instead of {want}"
+        i0 = int(np.argmin(dd))
+        d0 = float(dd[i0])
+        s, t_, vid, kind = self.env.action_keys[i0][:4]
+        want, d = (s, t_, self.vidx[vid], kind), dd[i0]
+        if self.golden_sel is not None and t is not None:
+            g = tuple(int(x) for x in self.golden_sel[t])
+            cand = self._rows_of(g) if g != want else []
+            if cand:
+                i = min(cand, key=lambda j: dd[j])
+                if float(dd[i]) - d0 < self.tol:
+                    self.oracle_flips += 1
+                    self.max_gap = max(self.max_gap, float(dd[i]) - d0)
+                    s, t_, vid, kind = self.env.action_keys[i][:4]
+                    want, d = g, dd[i]
+        self._forced = (s, t_, vid, kind, d)
+        gpu = tuple(int(x) for x in gpu_sel)
+        if gpu == want:
+            return None
+        cand = self._rows_of(gpu)
+        assert cand, f"CUDA decode chose {gpu} which is not in the oracle's action table (oracle: {want})"
+        gap = float(min(dd[i] for i in cand)) - d0
+        assert gap < self.tol, f"CUDA decode chose {gpu} (d gap {gap:.3e}) instead of {want}"
         self.flips += 1
         self.max_gap = max(self.max_gap, gap)
         return np.array(want, np.int32), d
@@ -95,7 +115,7 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
         sel, dist = env.decode(a)
         if follower is not None:
             env.sync()
-            fix = follower.resolve(actions[t], sel[check_env].cpu().numpy())
+            fix = follower.resolve(actions[t], sel[check_env].cpu().numpy(), t)
             if fix is not None:
                 sel = torch.from_numpy(fix[0]).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
                 dist = torch.full((B,), fix[1], dtype=torch.float64, device=env.device)
