@@ -30,9 +30,12 @@ class BatchedCyberBattleEnv:
                  global_env_offset: int = 0, auto_reset: bool = True, switch_interval: int = 0,
                  tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None,
                  gae_tables=None, **cfg_overrides):
+        self.cfg = cfg or EnvConfig()
+        if getattr(self.cfg, "sample_subset_samples", 0):
+            raise NotImplementedError("sample_subset_samples (compressed:553-567) is restated by the oracle only so far; the CUDA "
+                                      "decode scans the whole action table (DESIGN.md §5)")
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
-        self.cfg = cfg or EnvConfig()
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", device)
         self.lib = L.load_library()

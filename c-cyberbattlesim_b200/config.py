@@ -78,6 +78,11 @@ class EnvConfig:
     precise_action_space_positions: bool = False
     # compressed:82,570-590: metric of the nearest-row decode: 'cosine' (scipy cdist, default), 'l1', 'l2', 'inf' (np.linalg.norm)
     distance_metric: str = "cosine"
+    # compressed:83,521-522,553-567: keep at most this many action-table rows per outcome class (0 / False = the whole table).
+    # Restated by the oracle with a Philox-keyed subset rule (ccbs_b200.philox.subset_keep) and pinned against the reference
+    # fed the same rule; NOT implemented by the CUDA path yet: BatchedCyberBattleEnv refuses it (from_reference_dicts drops it
+    # with a warning, as before).
+    sample_subset_samples: int = 0
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
 
@@ -126,6 +131,7 @@ class EnvConfig:
                     mid = (train_config[f"{k}_min"] + train_config[f"{k}_max"]) / 2
                     train_config[k] = mid if k == "detect_probability" else int(round(mid))
         if train_config.get("sample_subset_samples"):
+            train_config["sample_subset_samples"] = 0
             import warnings
             warnings.warn("sample_subset_samples is ignored: the batched decode always scans the full action table "
                           "(the reference sub-samples it with np.random.choice to bound cdist time)", stacklevel=2)
@@ -159,7 +165,8 @@ class EnvConfig:
                     remove_main_obstacles=self.remove_main_obstacles, remove_all_obstacles=self.remove_all_obstacles,
                     random_starter_node=self.random_starter_node, rewards_dict=dict(self.rewards_dict),
                     interest_node_value=self.interest_node_value, switch_interest_node_interval=1,
-                    penalties_dict=pen, sample_subset_samples=False, static_defender_agent=None,
+                    penalties_dict=pen, sample_subset_samples=int(self.sample_subset_samples or 0) or False,
+                    static_defender_agent=None,
                     precise_graph_encoding=self.precise_graph_encoding,
                     precise_action_space_positions=self.precise_action_space_positions,
                     distance_metric=self.distance_metric)

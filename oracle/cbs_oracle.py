@@ -98,8 +98,17 @@ class OracleEnv:
     with the success-rate draw replaced by the supplied uniform (consumed only where the reference
     calls ``random.random()``, attacker_actions.py:190,409)."""
 
-    def __init__(self, spec, gae_weights, cfg, interest_node=None):
+    def __init__(self, spec, gae_weights, cfg, interest_node=None, philox_seed=0, env_index=0):
         self.spec, self.cfg = spec, cfg
+        # sample_subset_samples (compressed:83,105,521-522,553-567): rows kept per outcome class, 0 = off.  The reference draws
+        # the subset with np.random.choice; here (and in the golden generator, which hands the same function to the reference)
+        # it is ccbs_b200.philox.subset_keep keyed by (philox_seed, env_index, lifetime balance counter, row identity).
+        self.sample_subset_samples = int(getattr(cfg, "sample_subset_samples", 0) or 0)
+        self.philox_seed, self.env_index, self.balance_calls, self.rows_dropped = int(philox_seed), int(env_index), 0, 0
+        self._vloc = {}
+        for nd in spec.nodes:
+            for v in nd.vulns:
+                self._vloc.setdefault(v.vid, len(self._vloc))
         self.node_goal = cfg.goal.endswith("node")
         self.interest = None if interest_node is None else int(interest_node)      # cyberbattle_env.py:127-131 (fixed per env object)
         if self.node_goal and self.interest is None:
@@ -641,7 +650,7 @@ class OracleEnv:
         return reach
 
     def create_continuous_action_space(self, nodes_to_recalculate=None):
-        """compressed:487-523 (+ :526-550) with sample_subset_samples=False.  ``nodes_to_recalculate``
+        """compressed:487-523 (+ :526-550).  ``nodes_to_recalculate``
         (precise_action_space_positions, :498-506): pairs whose source or target reaches one of these nodes in the
         visible graph are processed again — their rows are overwritten in place with the current embeddings."""
         run_owned = [n for n in self.owned_nodes if self.nodes[n].status == C.ST_RUNNING]
@@ -660,6 +669,32 @@ class OracleEnv:
                     self._add_rows(s, es, t, et, 0)
                 self._add_rows(s, es, t, et, 1)
                 self.processed_pairs.add((s, t))
+        if self.sample_subset_samples:                                                     # :521-522
+            self._balance_action_space_by_outcome()
+
+    def _balance_action_space_by_outcome(self):
+        """compressed:553-567: group the table's keys by outcome class in first-appearance order; a class with more than
+        ``sample_subset_samples`` rows keeps that many (np.random.choice there, philox.subset_keep here: a uniform subset that
+        keeps its table order); the table becomes the concatenation of the groups.  Dropped rows are gone for good: their pair
+        stays in processed_pairs (only precise_action_space_positions re-adds rows, at the end of the table)."""
+        from ccbs_b200.philox import subset_keep, row_identity
+        groups = {}
+        for i, key in enumerate(self.action_keys):
+            groups.setdefault(key[3], []).append(i)
+        order = []
+        for kind, idx in groups.items():
+            if len(idx) > self.sample_subset_samples:
+                ks = [self.action_keys[i] for i in idx]
+                ident = row_identity([k[0] for k in ks], [k[1] for k in ks], [kind] * len(ks), [self._vloc[k[2]] for k in ks])
+                keep = subset_keep(self.philox_seed, self.env_index, self.balance_calls, ident, self.sample_subset_samples)
+                self.rows_dropped += len(idx) - len(keep)
+                idx = [idx[j] for j in keep]
+            order.extend(idx)
+        self.action_keys = [self.action_keys[i] for i in order]
+        self.action_rows = [self.action_rows[i] for i in order]
+        self._row_of_key = {k: i for i, k in enumerate(self.action_keys)}
+        self._rows_cache = None
+        self.balance_calls += 1
 
     def _add_rows(self, s, es, t, et, vtype):
         for vid, ri, kind, emb in self.per_node_type[t][vtype]:

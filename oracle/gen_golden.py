@@ -104,6 +104,17 @@ CASES = {
                   cfg=dict(goal="control", distance_metric="l2", proportional_cutoff_coefficient=25, episode_iterations=400)),
     "p8_inf": dict(graph_seed=53, nodes=8, steps=400, policy=0.02,
                    cfg=dict(goal="control", distance_metric="inf", proportional_cutoff_coefficient=25, episode_iterations=400)),
+    # sample_subset_samples (compressed:553-567): at most k rows per outcome class stay in the table after every table-
+    # maintaining encode; np.random.choice replaced on both sides by ccbs_b200.philox.subset_keep.  ORACLE-ONLY fixtures (s*):
+    # the CUDA path does not implement the sub-sampling yet
+    "s16_subset_random": dict(graph_seed=13, nodes=16, steps=600, philox_seed=77,
+                              cfg=dict(goal="control", sample_subset_samples=12, proportional_cutoff_coefficient=3)),
+    "s8_subset_policy": dict(graph_seed=53, nodes=8, steps=500, policy=0.02, philox_seed=78,
+                             cfg=dict(goal="control", sample_subset_samples=25, proportional_cutoff_coefficient=25,
+                                      episode_iterations=400)),
+    "s12_subset_positions": dict(graph_seed=12, nodes=12, steps=400, philox_seed=79,
+                                 cfg=dict(goal="control", sample_subset_samples=10, precise_action_space_positions=True,
+                                          proportional_cutoff_coefficient=3)),
     "p6_l1": dict(graph_seed=30, nodes=6, steps=400, policy=0.02,
                   cfg=dict(goal="control", distance_metric="l1", proportional_cutoff_coefficient=25, episode_iterations=400)),
 }
@@ -150,7 +161,8 @@ def generate(name):
     assert feasible, "no feasible starter for this case"
     actions, uniforms = make_case_inputs(p)
     starters = tr.make_starters(p["graph_seed"] * 1000 + 2, feasible, p["steps"] + 2)
-    runner = rb.ReferenceRunner(model, weights, cfg, interest_node=interest)
+    runner = rb.ReferenceRunner(model, weights, cfg, interest_node=interest, subset_vuln_index=tr.vuln_index(spec),
+                                philox_seed=p.get("philox_seed", 0))
     rec = tr.record(tr.ReferenceAdapter(runner, spec), actions, uniforms, starters,
                     policy_seed=(p["graph_seed"] * 1000 + 3) if "policy" in p else None,
                     defender_draws=make_case_defender_draws(p, cfg), p_persist=p.get("p_persist", 0.0))
@@ -197,7 +209,7 @@ def load_case(path):
     rec["obs"] = z["obs_rows"][z["obs_idx"]]
     return dict(meta=meta, spec=spec, cfg=cfg, weights=weights, actions=actions, uniforms=uniforms,
                 starters=z["starters"], trace=rec, policy_seed=0 if "policy" in p else None,
-                policy_rows=rec.get("policy_rows"), interest=p.get("interest"),
+                policy_rows=rec.get("policy_rows"), interest=p.get("interest"), philox_seed=p.get("philox_seed", 0),
                 defender_draws=make_case_defender_draws(p, cfg))
 
 

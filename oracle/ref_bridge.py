@@ -107,7 +107,7 @@ def _fake_numpy_random(fake):
 class ReferenceRunner:
     """One reference ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv])`` with controlled randomness."""
 
-    def __init__(self, model, gae_weights, cfg, interest_node=None):
+    def __init__(self, model, gae_weights, cfg, interest_node=None, subset_vuln_index=None, philox_seed=0, env_index=0):
         import torch
         ref = import_reference()
         self.ref = ref
@@ -138,9 +138,50 @@ class ReferenceRunner:
         env.set_graph_encoder(enc)
         env.set_pca_components(768)
         self.env = env
+        if getattr(cfg, "sample_subset_samples", 0):
+            self._install_subset_rule(ref["compressed"], subset_vuln_index, int(philox_seed), int(env_index))
         self.ids = list(model.network.nodes)
         self.index = {n: i for i, n in enumerate(self.ids)}
         self.wrapper = None
+
+    def _install_subset_rule(self, module, vuln_index, seed, env_index):
+        """__balance_action_space_by_outcome (compressed:553-567) draws its subset with ``np.random.choice(len(actions), k,
+        replace=False)``.  The module-level name ``np`` is replaced by a proxy whose ``random.choice`` applies the documented
+        rule (ccbs_b200.philox.subset_keep) to the caller's ``actions`` list; the lifetime balance counter comes from a counting
+        wrapper around the (name-mangled) method on the env instance.  Everything else of the method runs unmodified."""
+        from ccbs_b200.philox import subset_keep, row_identity
+        from ccbs_b200.scenario import _KIND_BY_CLASSNAME
+        if vuln_index is None:
+            raise ValueError("sample_subset_samples needs subset_vuln_index (oracle.trace.vuln_index(spec))")
+        runner, env = self, self.env
+        self.balance_calls = 0
+        name = "_CyberBattleCompressedEnv__balance_action_space_by_outcome"
+        original = getattr(env, name)
+
+        def counted():
+            original()
+            runner.balance_calls += 1
+        setattr(env, name, counted)
+
+        class _Random:
+            @staticmethod
+            def choice(n, size, replace=False):
+                assert replace is False
+                actions = sys._getframe(1).f_locals["actions"]
+                assert len(actions) == n
+                ident = row_identity([runner.index[a[0]] for a in actions], [runner.index[a[1]] for a in actions],
+                                     [_KIND_BY_CLASSNAME[type(a[3]).__name__] for a in actions], [vuln_index[a[2]] for a in actions])
+                return subset_keep(seed, env_index, runner.balance_calls, ident, size)
+
+            def __getattr__(self, attr):
+                return getattr(np.random, attr)
+
+        class _Numpy:
+            random = _Random()
+
+            def __getattr__(self, attr):
+                return getattr(np, attr)
+        module.np = _Numpy()
 
     def reset(self, starter: int):
         self.fake.next_starter = int(starter)

@@ -20,7 +20,7 @@ def test_fixtures_present():
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_replays_reference_trace(name, golden_dir):
     case = gg.load_case(os.path.join(golden_dir, name + ".npz"))
-    env = OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"])
+    env = OracleEnv(case["spec"], case["weights"], case["cfg"], interest_node=case["interest"], philox_seed=case["philox_seed"])
     if name == "g100_10k" and not os.environ.get("CBS_FULL_GOLDEN"):
         # BASELINE configs[0] at its stated 10 000 steps: the full replay takes ~5 min of oracle time (CBS_FULL_GOLDEN=1; it
         # passes).  The default suite replays three windows cut at episode boundaries — start, middle, end of the trace.
@@ -43,6 +43,10 @@ def test_oracle_replays_reference_trace(name, golden_dir):
         st = case["trace"]["stats"]
         assert st[:, 9].sum() >= 5 and np.array_equal(st[:, 9], st[:, 10])
         assert np.any(case["trace"]["masks"][:, 11])      # some node was Imaging at some step
+    elif name.startswith("s"):                            # sample_subset_samples: the table really is thinned, class by class
+        k = int(case["cfg"].sample_subset_samples)
+        per_kind = np.bincount([key[3] for key in env.action_keys], minlength=16)
+        assert env.balance_calls > int(case["trace"]["num_episodes"]) and env.rows_dropped > 100 and per_kind.max() <= k
     elif name.startswith("n"):                            # node-goal cases: short episodes, most success kinds
         assert len(codes & {0, 1, 2, 3, 4, 5, 6, 7, 9}) >= 7 and case["trace"]["obs"].shape[1] == 258
     else:
