@@ -157,7 +157,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
             assert tuple(obs_h[b, G:]) == tuple(float(x) for x in ob["discrete_features"])
             assert np.array_equal(masks_to_u64(m, b), tr.masks_to_array(o.masks())), f"step {t} env {b}: masks differ"
     sc = env.scalars()
-    assert flips <= max(1, B * T // 200), f"{flips} near-tie flips in {B * T} env-steps"
+    # l1 sums the float32 rounding differences of equal embeddings instead of cancelling them: wider near-tie window, more of them
+    assert flips <= max(1, B * T // (50 if cfg.distance_metric == "l1" else 200)), f"{flips} near-tie flips in {B * T} env-steps"
     assert np.array_equal(sc[L.S_EPISODES], np.array(episodes))
     assert sum(episodes) >= (B if sizes[1] < 100 else 1), "test too short to exercise auto-reset"
     if pool_size > 256:
