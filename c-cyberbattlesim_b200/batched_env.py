@@ -34,6 +34,9 @@ class BatchedCyberBattleEnv:
         if getattr(self.cfg, "sample_subset_samples", 0):
             raise NotImplementedError("sample_subset_samples (compressed:553-567) is restated by the oracle only so far; the CUDA "
                                       "decode scans the whole action table (DESIGN.md §5)")
+        if getattr(self.cfg, "static_defender_agent", None) == "events":
+            raise NotImplementedError("the 'events' static defender (ExternalRandomEvents, _env/static_defender.py:63-161) is restated by "
+                                      "the oracle only so far (DESIGN.md §5)")
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
         self.num_envs = int(num_envs)

@@ -66,8 +66,11 @@ class EnvConfig:
     random_starter_node: bool = True
     switch_interval: int = 5
     interest_node_value: int = 200        # agents/config/train_config.yaml:16 (value of the node of interest, *_node goals)
-    # static defender (_env/static_defender.py): None or "reimage" (ScanAndReimageCompromisedMachines, :27-60)
+    # static defender (_env/static_defender.py): None, "reimage" (ScanAndReimageCompromisedMachines, :27-60) or "events"
+    # (ExternalRandomEvents, :63-161: per node and step one of start / stop a service, add / remove a firewall rule, each with
+    # random_event_probability).  "events" is restated by the oracle only so far: BatchedCyberBattleEnv refuses it.
     static_defender_agent: Optional[str] = None
+    random_event_probability: float = 0.0075   # agents/multi_env/config/train_config.yaml:37-38 (midpoint of [min, max])
     detect_probability: float = 0.05      # train_config.yaml:39-40
     scan_capacity: int = 3                # :41-42
     scan_frequency: int = 3               # :43-44
@@ -96,9 +99,12 @@ class EnvConfig:
             self.rewards_dict = dict(DEFAULT_REWARDS[self.goal])
         if not self.penalties_dict:
             self.penalties_dict = dict(DEFAULT_PENALTIES[self.goal])
-        if self.static_defender_agent not in (None, "reimage"):
-            raise ValueError("static_defender_agent must be None or 'reimage' (the 'events' defender is not implemented, DESIGN.md §5)")
-        if self.static_defender_agent:
+        if self.static_defender_agent not in (None, "reimage", "events"):
+            raise ValueError("static_defender_agent must be None, 'reimage' or 'events'")
+        if self.static_defender_agent == "events" and self.precise_action_space_positions:
+            raise ValueError("precise_action_space_positions is not implemented together with a static defender "
+                             "(the reference then refreshes around `changed_nodes`, compressed:423-427)")
+        if self.static_defender_agent == "reimage":
             if not (1 <= int(self.scan_capacity) <= C.MAX_SCAN_CAPACITY):
                 raise ValueError(f"scan_capacity must be in 1..{C.MAX_SCAN_CAPACITY}")
             if int(self.scan_frequency) < 1:

@@ -36,7 +36,7 @@ _REFRESH_KINDS = (C.K_DISCOVERY, C.K_COLLECTION, C.K_PERSISTENCE, C.K_PRIVESC, C
 class _Node:
     """Mutable NodeInfo fields (model.py:294-338) over an immutable NodeSpec."""
     __slots__ = ("spec", "agent_installed", "privilege_level", "status", "has_data", "data_collected",
-                 "data_exfiltrated", "visible", "persistence", "defense_evasion", "vulns")
+                 "data_exfiltrated", "visible", "persistence", "defense_evasion", "vulns", "fw_in", "fw_out", "running")
 
     def __init__(self, spec):
         self.spec = spec
@@ -50,6 +50,10 @@ class _Node:
         self.persistence = False
         self.defense_evasion = False
         self.vulns = {v.vid: v for v in spec.vulns}
+        # mutable only under the ExternalRandomEvents defender (static_defender_actions.py:96-168)
+        self.fw_in = [(int(p), int(q)) for p, q in spec.fw_in]
+        self.fw_out = [(int(p), int(q)) for p, q in spec.fw_out]
+        self.running = [bool(sv.running) for sv in spec.services]
 
 
 class GaeOracle:
@@ -121,7 +125,10 @@ class OracleEnv:
         self.episode_iterations = cfg.episode_iterations
         # ScanAndReimageCompromisedMachines (_env/static_defender.py:27-60); None -> no defender
         self.defender = getattr(cfg, "static_defender_agent", None) == "reimage"
-        self.always_encode = self.defender or bool(getattr(cfg, "precise_graph_encoding", False))   # compressed:401,455-462
+        # ExternalRandomEvents (_env/static_defender.py:63-161)
+        self.events_defender = getattr(cfg, "static_defender_agent", None) == "events"
+        self.always_encode = self.defender or self.events_defender or \
+            bool(getattr(cfg, "precise_graph_encoding", False))                                     # compressed:401,455-462
         self.distance_metric = getattr(cfg, "distance_metric", "cosine")                            # compressed:82,100
         self.precise_positions = bool(getattr(cfg, "precise_action_space_positions", False))        # compressed:86,419-427
         self.proportional_cutoff_coefficient = cfg.proportional_cutoff_coefficient
@@ -313,11 +320,11 @@ class OracleEnv:
         res = next((r for r in v.results if r.vtype == 1 and r.kind == kind), None)       # :149-152
         if res is None:
             return P["invalid_action"], C.OC_OUTCOME_NOT_PRESENT, None                    # :153
-        if v.port not in [sv.port for sv in tgt.spec.services if sv.running]:
+        if v.port not in [sv.port for sv, up in zip(tgt.spec.services, tgt.running) if up]:
             return P["scanning_unopen_port"], C.OC_PORT_NOT_LISTENING, None               # :161
-        if not src.defense_evasion and not self._passing(src.spec.fw_out, v.port):
+        if not src.defense_evasion and not self._passing(src.fw_out, v.port):
             return P["blocked_by_local_firewall"], C.OC_FW_OUTGOING, None                 # :170
-        if not tgt.defense_evasion and not self._passing(tgt.spec.fw_in, v.port):
+        if not tgt.defense_evasion and not self._passing(tgt.fw_in, v.port):
             return P["blocked_by_remote_firewall"], C.OC_FW_INCOMING, None                # :180
         if u >= v.success_rate:
             return P["success_rate_failed"], C.OC_UNSUCCESSFUL, None                      # :190
@@ -443,6 +450,54 @@ class OracleEnv:
             if nd.agent_installed and nd.status == C.ST_RUNNING and n not in self.owned_nodes:
                 self.owned_nodes.append(n)
 
+    def events_defender_step(self, draws):
+        """cyberbattle_env.py:416-419,431 static_defender_step with ExternalRandomEvents (_env/static_defender.py:76-161).
+        ``draws[n]`` = (f, u_event, u_pick, u_side) for node n: f indexes random.choice(["start service", "firewall remove",
+        "stop service", "firewall add"]) (:80), u_event is the numpy.random.random() compared with the probability, u_pick
+        picks the service / port (random.choice -> floor(u_pick * len)), u_side <= 0.5 means an incoming rule.  A node with
+        defense evasion consumes only f (:100,:112,:124,:149)."""
+        draws = draws[0] if isinstance(draws, tuple) else draws
+        events = 0
+        p = float(self.cfg.random_event_probability)
+        for n in range(self.N):                                                            # environment.get_nodes() order
+            f, u_event, u_pick, u_side = int(draws[n][0]), float(draws[n][1]), float(draws[n][2]), float(draws[n][3])
+            nd = self.nodes[n]
+            if nd.defense_evasion or not u_event <= p:
+                continue
+            services = nd.spec.services
+            if f in (0, 2):                                                                # start / stop a service (:98-119)
+                if len(services) == 0:
+                    continue
+                port = services[min(int(u_pick * len(services)), len(services) - 1)].port
+                if nd.status == C.ST_RUNNING:                                              # static_defender_actions.py:150,161
+                    for i, sv in enumerate(services):
+                        if sv.port == port:
+                            nd.running[i] = (f == 0)
+                events += 1                                                                # counted even when the node is not Running
+            else:                                                                          # firewall remove (ALLOW) / add (BLOCK) (:122-161)
+                if len(services) == 0:
+                    raise IndexError("Cannot choose from an empty sequence")              # random.choice([]) in the reference
+                port = services[min(int(u_pick * len(services)), len(services) - 1)].port
+                perm = 1 if f == 3 else 0
+                if (port, perm) in nd.fw_in:                                               # BOTH sides test firewall.incoming (:135,138 / :158,161)
+                    continue
+                rules = nd.fw_in if u_side <= 0.5 else nd.fw_out
+                patched, seen = [], False                                                  # override_firewall_rule (static_defender_actions.py:96-128)
+                for q, perm_q in rules:
+                    if q == port:
+                        seen = True
+                        patched.append((q, perm))
+                    else:
+                        patched.append((q, perm_q))
+                if not seen:
+                    patched.append((port, perm))
+                if u_side <= 0.5:
+                    nd.fw_in = patched
+                else:
+                    nd.fw_out = patched
+                events += 1
+        self.num_events += events                                                          # :419
+
     def step_attacker_env(self, s, t, vid, kind, u, defender_draws=None):
         """cyberbattle_env.py:299-394 step_attacker_env."""
         if self.done:
@@ -472,6 +527,8 @@ class OracleEnv:
             self.reward = 0                                                                # :322-326
         if self.defender:
             self.static_defender_step(defender_draws)                                      # :331-332
+        elif self.events_defender:
+            self.events_defender_step(defender_draws)
         # end checks (:338-370)
         self.end_episode_reason = 0
         self.truncated = False
@@ -548,11 +605,11 @@ class OracleEnv:
         ports = [s.port for s in sp.services]
         fw = [0] * (2 * M)
         if nd.visible:
-            for port, perm in sp.fw_in:
+            for port, perm in nd.fw_in:
                 i = ports.index(port) if port in ports else -1
                 if i != -1 and i < M:
                     fw[i] = perm
-            for port, perm in sp.fw_out:
+            for port, perm in nd.fw_out:
                 i = ports.index(port) if port in ports else -1
                 if i != -1 and i < M:
                     fw[M + i] = perm
@@ -563,7 +620,7 @@ class OracleEnv:
             for i, s in enumerate(sp.services):
                 if i >= M:
                     break
-                running[i] = int(s.running)
+                running[i] = int(nd.running[i])
                 acc = acc + np.asarray(s.fv, dtype=np.float64)
             if len(sp.services) > 0:
                 acc = acc / len(sp.services)
@@ -798,7 +855,7 @@ class OracleEnv:
                 m[C.M_IMAGING] |= b
             if j in self.node_x and int(self.node_x[j][C.F_STATUS]) == C.ST_IMAGING:
                 m[C.M_X_IMAGING] |= b
-            if self.defender:        # tracking planes the device only maintains under a defender
+            if self.defender or self.events_defender:        # tracking planes the device only maintains under a defender
                 if self._discovered.get(j):
                     m[C.M_EVER_OWNED] |= b
                 if j in self._stale:

@@ -115,6 +115,14 @@ CASES = {
     "s12_subset_positions": dict(graph_seed=12, nodes=12, steps=400, philox_seed=79,
                                  cfg=dict(goal="control", sample_subset_samples=10, precise_action_space_positions=True,
                                           proportional_cutoff_coefficient=3)),
+    # ExternalRandomEvents static defender (_env/static_defender.py:63-161): services stopped / started, firewall rules added /
+    # removed at random; every step re-encodes (compressed:401) over stale node features.  ORACLE-ONLY fixtures (e*)
+    "e12_events_random": dict(graph_seed=41, nodes=12, steps=600,
+                              cfg=dict(goal="control", static_defender_agent="events", random_event_probability=0.02,
+                                       proportional_cutoff_coefficient=4)),
+    "e8_events_policy": dict(graph_seed=53, nodes=8, steps=600, policy=0.02,
+                             cfg=dict(goal="control", static_defender_agent="events", random_event_probability=0.03,
+                                      proportional_cutoff_coefficient=25, episode_iterations=300)),
     "p6_l1": dict(graph_seed=30, nodes=6, steps=400, policy=0.02,
                   cfg=dict(goal="control", distance_metric="l1", proportional_cutoff_coefficient=25, episode_iterations=400)),
 }
@@ -147,6 +155,8 @@ def make_case_inputs(p):
 def make_case_defender_draws(p, cfg):
     if cfg.static_defender_agent is None:
         return None
+    if cfg.static_defender_agent == "events":
+        return tr.make_events_draws(p["graph_seed"] * 1000 + 5, p["steps"], p["nodes"], float(cfg.random_event_probability))
     return tr.make_defender_draws(p["graph_seed"] * 1000 + 5, p["steps"], p["nodes"], int(cfg.scan_capacity))
 
 

@@ -104,6 +104,51 @@ def _fake_numpy_random(fake):
     return _N()
 
 
+class _FakeEvents:
+    """Stands in for ``random`` and ``numpy`` inside _env/static_defender.py under ExternalRandomEvents (:76-161): per node the
+    reference calls random.choice(<4 function names>) (:80), then — unless the node has defense evasion — numpy.random.random()
+    for the event test, random.choice(services / ports) and, for firewall events, numpy.random.random() for the side."""
+    FUNCTIONS = ["start service", "firewall remove", "stop service", "firewall add"]
+
+    def __init__(self):
+        self.draws, self.node, self.calls = None, -1, 0
+
+    def begin_step(self, draws):
+        self.draws, self.node, self.calls = np.asarray(draws, np.float64), -1, 0
+
+    def choice(self, seq):
+        if list(seq) == self.FUNCTIONS:
+            self.node += 1
+            self.calls = 0
+            return seq[int(self.draws[self.node][0])]
+        if len(seq) == 0:
+            raise IndexError("Cannot choose from an empty sequence")
+        return seq[min(int(float(self.draws[self.node][2]) * len(seq)), len(seq) - 1)]
+
+    def numpy_random(self):
+        u = float(self.draws[self.node][1 if self.calls == 0 else 3])
+        self.calls += 1
+        return u
+
+    def numpy_proxy(self):
+        outer = self
+
+        class _R:
+            @staticmethod
+            def random():
+                return outer.numpy_random()
+
+        class _N:
+            random = _R()
+
+            def __getattr__(self, name):
+                return getattr(np, name)
+        return _N()
+
+    def __getattr__(self, name):
+        return getattr(_py_random, name)
+
+
 class ReferenceRunner:
     """One reference ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv])`` with controlled randomness."""
 
@@ -134,6 +179,12 @@ class ReferenceRunner:
             sd.numpy = _fake_numpy_random(self.fake)
             kw["static_defender_agent"] = sd.ScanAndReimageCompromisedMachines(
                 cfg.detect_probability, int(cfg.scan_capacity), int(cfg.scan_frequency), logger=logger, verbose=0)
+        if getattr(cfg, "static_defender_agent", None) == "events":
+            import cyberbattle._env.static_defender as sd
+            self.events = _FakeEvents()
+            sd.random = self.events
+            sd.numpy = self.events.numpy_proxy()
+            kw["static_defender_agent"] = sd.ExternalRandomEvents(float(cfg.random_event_probability), logger=logger, verbose=0)
         env = ref["compressed"].CyberBattleCompressedEnv(initial_environment=model, logger=logger, verbose=0, **kw)
         env.set_graph_encoder(enc)
         env.set_pca_components(768)
@@ -194,7 +245,9 @@ class ReferenceRunner:
 
     def step(self, action, uniform, defender_draws=None):
         self.fake.next_uniform = float(uniform)
-        if defender_draws is not None:
+        if defender_draws is not None and len(defender_draws) == 1:        # ExternalRandomEvents: (f, u_event, u_pick, u_side) per node
+            self.events.begin_step(defender_draws[0])
+        elif defender_draws is not None:
             self.fake.next_scan_nodes, self.fake.next_scan_uniforms = defender_draws
             self.fake.scan_pos = 0
         self.fake.uniform_consumed = False

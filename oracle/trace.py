@@ -30,6 +30,20 @@ def make_defender_draws(seed: int, steps: int, num_nodes: int, capacity: int):
             rng.random((steps, capacity), dtype=np.float32))
 
 
+def make_events_draws(seed: int, steps: int, num_nodes: int, p_event: float, boost: float = 8.0):
+    """ExternalRandomEvents draws, one row (f, u_event, u_pick, u_side) per step and node (see OracleEnv.events_defender_step).
+    u_event is skewed towards the event probability (a fraction ``boost * p_event`` of the draws fall below it) so that a short
+    trace sees many events; the defender itself is unchanged."""
+    rng = np.random.default_rng(seed)
+    ev = np.zeros((steps, num_nodes, 4), np.float64)
+    ev[..., 0] = rng.integers(0, 4, size=(steps, num_nodes))
+    hit = rng.random((steps, num_nodes)) < min(1.0, boost * p_event)
+    ev[..., 1] = np.where(hit, rng.random((steps, num_nodes)) * p_event, p_event + (1 - p_event) * (0.001 + 0.999 * rng.random((steps, num_nodes))))
+    ev[..., 2] = rng.random((steps, num_nodes))
+    ev[..., 3] = rng.random((steps, num_nodes))
+    return (ev,)
+
+
 def make_starters(seed: int, feasible, count: int):
     rng = np.random.default_rng(seed)
     feasible = np.asarray(feasible)
@@ -194,7 +208,7 @@ def record(adapter, actions, uniforms, starters, policy_seed=None, policy_rows=N
             else:
                 chosen_rows[t] = policy_rows[t]
             action = (adapter.table_row(int(chosen_rows[t])) + actions[t].astype(np.float64)).astype(np.float32)
-        dd = None if defender_draws is None else (defender_draws[0][t], defender_draws[1][t])
+        dd = None if defender_draws is None else tuple(x[t] for x in defender_draws)
         obs, r, done, trunc, sel, code, reason, dist = adapter.step(action, uniforms[t], defender_draws=dd)
         rec["sel"][t], rec["code"][t], rec["reward"][t] = sel, code, r
         rec["done"][t], rec["truncated"][t], rec["reason"][t], rec["dist"][t] = done, trunc, reason, dist

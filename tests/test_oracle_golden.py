@@ -43,6 +43,11 @@ def test_oracle_replays_reference_trace(name, golden_dir):
         st = case["trace"]["stats"]
         assert st[:, 9].sum() >= 5 and np.array_equal(st[:, 9], st[:, 10])
         assert np.any(case["trace"]["masks"][:, 11])      # some node was Imaging at some step
+    elif name.startswith("e"):                            # ExternalRandomEvents: many events, stopped services and new BLOCK rules bite
+        import ccbs_b200.constants as C
+        n_codes = np.bincount(case["trace"]["code"], minlength=32)
+        assert case["trace"]["stats"][:, 10].min() >= 50 and case["trace"]["stats"][:, 9].sum() == 0
+        assert n_codes[C.OC_PORT_NOT_LISTENING] >= 20 and n_codes[C.OC_FW_INCOMING] >= 20
     elif name.startswith("s"):                            # sample_subset_samples: the table really is thinned, class by class
         k = int(case["cfg"].sample_subset_samples)
         per_kind = np.bincount([key[3] for key in env.action_keys], minlength=16)
