@@ -37,6 +37,9 @@ class BatchedCyberBattleEnv:
         if getattr(self.cfg, "static_defender_agent", None) == "events":
             raise NotImplementedError("the 'events' static defender (ExternalRandomEvents, _env/static_defender.py:63-161) is restated by "
                                       "the oracle only so far (DESIGN.md §5)")
+        if self.cfg.static_defender_agent and self.cfg.precise_action_space_positions:
+            raise NotImplementedError("precise_action_space_positions together with a static defender (the reference then refreshes "
+                                      "around `changed_nodes`, compressed:423-427) is restated by the oracle only so far")
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
         self.num_envs = int(num_envs)

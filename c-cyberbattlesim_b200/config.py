@@ -102,16 +102,14 @@ class EnvConfig:
         if self.static_defender_agent not in (None, "reimage", "events"):
             raise ValueError("static_defender_agent must be None, 'reimage' or 'events'")
         if self.static_defender_agent == "events" and self.precise_action_space_positions:
-            raise ValueError("precise_action_space_positions is not implemented together with a static defender "
-                             "(the reference then refreshes around `changed_nodes`, compressed:423-427)")
+            raise ValueError("precise_action_space_positions cannot be used with the 'events' defender: the reference raises "
+                             "networkx.NodeNotFound as soon as an event changes a node that is not in the visible graph "
+                             "(nx.has_path on `changed_nodes`, compressed:423-427,498-500)")
         if self.static_defender_agent == "reimage":
             if not (1 <= int(self.scan_capacity) <= C.MAX_SCAN_CAPACITY):
                 raise ValueError(f"scan_capacity must be in 1..{C.MAX_SCAN_CAPACITY}")
             if int(self.scan_frequency) < 1:
                 raise ValueError("scan_frequency must be >= 1")
-            if self.precise_action_space_positions:
-                raise ValueError("precise_action_space_positions is not implemented together with a static defender "
-                                 "(the reference then refreshes around `changed_nodes`, compressed:423-427)")
 
     @classmethod
     def from_reference_dicts(cls, train_config: dict, rewards_config: dict, goal: str = "control") -> "EnvConfig":

@@ -257,6 +257,7 @@ class OracleEnv:
         self._discovered = {}                                        # node -> last_owned (bool) tracking
         self._stale = set()                                          # nodes re-imaged after they were last owned
         self.reimaging = {}                                          # StaticDefenderAgentActions.node_reimaging_progress (:23)
+        self.changed_nodes = []
         self.overall_reimaged, self.num_events = [], 0               # cyberbattle_env.py:160-161
         self._mark_owned(self.starter, self.nodes[self.starter].spec.level_at_access)
         # compressed:167-188
@@ -441,6 +442,7 @@ class OracleEnv:
                         nd.status = C.ST_IMAGING
                         self._stale.add(int(n))                                  # last_reimaging = now
                         changed.append(int(n))
+        self.changed_nodes = changed                                              # :418
         self.num_events += len(changed)                                           # :419
         self.overall_reimaged.extend(changed)                                     # :422
         for n in changed:
@@ -458,6 +460,7 @@ class OracleEnv:
         defense evasion consumes only f (:100,:112,:124,:149)."""
         draws = draws[0] if isinstance(draws, tuple) else draws
         events = 0
+        self.changed_nodes = []                                                            # nodes_changed (:78,:93-94)
         p = float(self.cfg.random_event_probability)
         for n in range(self.N):                                                            # environment.get_nodes() order
             f, u_event, u_pick, u_side = int(draws[n][0]), float(draws[n][1]), float(draws[n][2]), float(draws[n][3])
@@ -474,6 +477,7 @@ class OracleEnv:
                         if sv.port == port:
                             nd.running[i] = (f == 0)
                 events += 1                                                                # counted even when the node is not Running
+                self.changed_nodes.append(n)
             else:                                                                          # firewall remove (ALLOW) / add (BLOCK) (:122-161)
                 if len(services) == 0:
                     raise IndexError("Cannot choose from an empty sequence")              # random.choice([]) in the reference
@@ -496,6 +500,7 @@ class OracleEnv:
                 else:
                     nd.fw_out = patched
                 events += 1
+                self.changed_nodes.append(n)
         self.num_events += events                                                          # :419
 
     def step_attacker_env(self, s, t, vid, kind, u, defender_draws=None):
@@ -816,7 +821,11 @@ class OracleEnv:
             self.node_embeddings, emb = self.encode()
             self.n_encodes += 1
             self.observation = {"graph_embeddings": emb, "discrete_features": self._discrete_features()}
-            self.create_continuous_action_space([s, t] if self.precise_positions else None)   # :419-422
+            nodes = None
+            if self.precise_positions:                                                     # :419-427
+                changes = kind in _REENCODE_KINDS or bool(getattr(self.cfg, "precise_graph_encoding", False))
+                nodes = [s, t] if changes else list(self.changed_nodes)                    # defender: around what it changed
+            self.create_continuous_action_space(nodes)
         self.reward += self.pen["distance_penalty"] * dist                                 # :430
         info = dict(source_node=s, target_node=t, vulnerability=vid, outcome_kind=kind, outcome_obtained=self.outcome,
                     vulnerability_type=self.vulnerability_type, end_episode_reason=self.end_episode_reason,

@@ -123,6 +123,12 @@ CASES = {
     "e8_events_policy": dict(graph_seed=53, nodes=8, steps=600, policy=0.02,
                              cfg=dict(goal="control", static_defender_agent="events", random_event_probability=0.03,
                                       proportional_cutoff_coefficient=25, episode_iterations=300)),
+    # precise_action_space_positions under the re-imaging defender: rows refreshed around `changed_nodes` = the nodes re-imaged in
+    # this step (compressed:423-427).  ORACLE-ONLY.  (With the events defender the reference raises NodeNotFound, see EnvConfig.)
+    "x8_reimage_positions": dict(graph_seed=53, nodes=8, steps=500, policy=0.02, p_persist=0.25,
+                                 cfg=dict(goal="control", static_defender_agent="reimage", detect_probability=0.25, scan_capacity=3,
+                                          scan_frequency=3, precise_action_space_positions=True, proportional_cutoff_coefficient=25,
+                                          episode_iterations=300)),
     "p6_l1": dict(graph_seed=30, nodes=6, steps=400, policy=0.02,
                   cfg=dict(goal="control", distance_metric="l1", proportional_cutoff_coefficient=25, episode_iterations=400)),
 }
