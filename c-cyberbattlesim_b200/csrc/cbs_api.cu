@@ -490,8 +490,12 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
   if (!actions_dev || !out_ms) return fail(h, CBS_ERR_INVALID_ARG, "cbs_profile_step: null argument");
   if (h->P.metric != METRIC_COSINE) return fail(h, CBS_ERR_INVALID_ARG, "cbs_profile_step times the cosine decode's kernels only");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaEvent_t ev[4];
-  for (auto& e : ev) CK(h, cudaEventCreate(&e));
+  struct Events {   // destroyed on every return path (CK returns early on a CUDA error)
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    ~Events() { for (cudaEvent_t x : e) if (x) cudaEventDestroy(x); }
+  } evs;
+  cudaEvent_t* ev = evs.e;
+  for (int i = 0; i < 4; ++i) CK(h, cudaEventCreate(&ev[i]));
   CK(h, cudaEventRecord(ev[0], st));
   if ((rc = launch_gemm(h, actions_dev, st))) return rc;
   CK(h, cudaEventRecord(ev[1], st));
@@ -504,7 +508,6 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
   CK(h, cudaStreamSynchronize(st));
   for (int i = 0; i < 3; ++i) CK(h, cudaEventElapsedTime(&out_ms[i], ev[i], ev[i + 1]));
   out_ms[3] = out_ms[4] = 0.f;
-  for (auto& e : ev) cudaEventDestroy(e);
   h->launches += 2;
   return CBS_OK;
 }
