@@ -1,5 +1,5 @@
-"""Debug aid: replay a golden case on the GPU next to the oracle and dump both states at the first divergence.
-    python tools/debug_golden.py d12_reimage_random 1"""
+"""TEST INFRASTRUCTURE (not collected by pytest) - debug aid: replay a golden case on the GPU next to the oracle and dump both states at the first divergence.
+    python tests/debug_golden.py d12_reimage_random 1"""
 import os
 import sys
 
