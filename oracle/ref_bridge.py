@@ -315,3 +315,53 @@ class ReferenceRunner:
                 "OutcomeNonPresent": C.OC_OUTCOME_NOT_PRESENT, "NonListeningPort": C.OC_PORT_NOT_LISTENING,
                 "UnsuccessfulAction": C.OC_UNSUCCESSFUL, "NoNeededAction": C.OC_NO_NEEDED,
                 "RepeatedResult": C.OC_REPEATED, "RemoteOutcomeInLocalNode": C.OC_REMOTE_OUTCOME_LOCAL}[name]
+
+
+def reference_switch_sequence(models, gae_weights, cfg, switch_interval, picks, n_episodes, seed=0):
+    """Scenario index in force during each of the first ``n_episodes`` episodes of the reference's own
+    ``RandomSwitchEnv(envs_list=[...], switch_interval=...)`` over several CyberBattleCompressedEnv objects, with
+    ``np.random.choice(envs_ids)`` (cyberbattle_env_switch.py:103) answering from ``picks`` in call order.  Also returns how
+    many picks were consumed.  Random actions; starters: the first feasible node (rejection loop over randrange)."""
+    ref = import_reference()
+    runners = [ReferenceRunner(m, gae_weights, cfg) for m in models]
+    state = {"i": 0}
+
+    class _Random:
+        @staticmethod
+        def choice(ids):
+            v = ids[int(picks[state["i"]])]
+            state["i"] += 1
+            return v
+
+        def __getattr__(self, attr):
+            return getattr(np.random, attr)
+
+    class _Numpy:
+        random = _Random()
+
+        def __getattr__(self, attr):
+            return getattr(np, attr)
+    module = ref["switch"]
+    saved = module.np
+    module.np = _Numpy()
+    try:
+        fake = runners[0].fake                     # the module-level fakes of the LAST runner built serve every env
+        for r in runners:
+            fake = r.fake
+        tries = {"n": 0}
+        fake.randrange = lambda n: (tries.__setitem__("n", tries["n"] + 1) or tries["n"]) % n     # walks the nodes until one passes
+        wrapper = module.RandomSwitchEnv(envs_ids=list(range(len(models))), switch_interval=switch_interval,
+                                         envs_list=[r.env for r in runners], verbose=0)
+        rng = np.random.default_rng(seed)
+        seq = []
+        for _ in range(n_episodes):
+            wrapper.reset()
+            seq.append(int(wrapper.current_env_index))
+            for _ in range(10000):
+                fake.next_uniform = float(rng.random())
+                _, _, done, truncated, _ = wrapper.step(rng.uniform(-4, 4, 905).astype(np.float32))
+                if done or truncated:
+                    break
+        return seq, state["i"]
+    finally:
+        module.np = saved

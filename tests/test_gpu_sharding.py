@@ -67,7 +67,7 @@ def test_scenario_switch_cadence():
         for b in np.nonzero(d)[0]:
             episodes[b] += 1
             # _check_switch: (episode_count + 1) % (switch_interval + 1) == 0 -> new scenario (uniform choice)
-            if (episodes[b] + 1) % (interval + 1) == 0:
+            if cb.constants.switch_due(episodes[b], interval):
                 want[b] = philox_pick(seed, b, int(episodes[b]), 2, len(specs))
         sc = env.scalars()
         assert np.array_equal(sc[L.S_SCENARIO], want), f"step {t}"
