@@ -39,3 +39,23 @@ def test_reference_switcher_follows_switch_due(interval):
         want.append(cur)
     assert seq == want and used == i
     assert len(set(seq)) > 1
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
+def test_csv_header_is_the_reference_header(tmp_path):
+    """ccbs_b200.trace_csv.HEADER against the header row the reference's own switcher writes (switch.py:223-243, the variant
+    without embeddings)."""
+    import csv
+    from ccbs_b200.trace_csv import HEADER
+    from oracle import ref_bridge as rb
+    graph = cb.synthetic_input_graph(310, 5, pool=cb.synthetic_vuln_pool(7, 40))
+    model = rb.reference_model_from_input_graph(graph, seed=310)
+    runner = rb.ReferenceRunner(model, cb.GaeWeights.random(0), cb.EnvConfig(isolation_filter_threshold=0.0))
+    runner.fake.next_starter = 0
+    wrapper = runner.ref["switch"].RandomSwitchEnv(envs_ids=[0], switch_interval=10 ** 9, envs_list=[runner.env], verbose=0,
+                                                   save_to_csv=True, csv_folder=str(tmp_path), save_embeddings=False)
+    wrapper.file.flush()
+    with open(os.path.join(str(tmp_path), "logs.csv"), newline="") as f:
+        assert next(csv.reader(f)) == HEADER
+    wrapper.file.close()
