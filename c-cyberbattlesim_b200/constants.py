@@ -51,6 +51,10 @@ N_KINDS = 11
 KIND_NAMES = ["DenialOfService", "Discovery", "Collection", "Exfiltration", "Reconnaissance",
               "DefenseEvasion", "Persistence", "PrivilegeEscalation", "CredentialAccess", "LateralMove",
               "Execution"]
+# PredictedResult.outcome_str: the classifier labels the generator maps to outcome classes (utils/encoding_utils.py:129-147,
+# simulation/generate_network.py:160-207); printed by RandomSwitchEnv.get_str_info (switch.py:331-333)
+KIND_LABELS = ["DOS", "discovery", "collection", "exfiltration", "reconnaissance", "defense evasion", "persistence",
+               "privilege escalation", "credential access", "lateral move", "execution"]
 # utils/encoding_utils.py:40-62 map_outcome_to_string (info['outcome'])
 KIND_INFO_STR = ["DenialOfService", "Discovery", "Collection", "Exfiltration", "Reconnaissance",
                  "DefenseEvasion", "Persistence", "PrivilegeEscalation", "LateralMove-Credential",

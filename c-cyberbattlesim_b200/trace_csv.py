@@ -3,7 +3,11 @@
 
 The reference writes one row per step from Python object state; here the integer state of the traced envs is read back from
 the device before and after each step (a debugging aid: it synchronises, keep the traced subset small).  Node detail
-strings follow get_str_info (switch.py:307-334)."""
+strings follow get_str_info (switch.py:307-334) character for character (tests/test_switch_rule.py compares them with the
+reference's own on a scripted-attacker trace); "Iteration" is the 0-based step of the episode (the reference writes the row before
+it increments steps_in_current_episode, switch.py:124-134).  Deliberate differences: the two outcome columns hold class names
+where the reference prints object reprs with memory addresses (switch.py:259-264,276), and every step of the traced envs is
+written, whereas the reference skips episode 0 and writes every save_to_csv_interval-th episode (switch.py:124)."""
 from __future__ import annotations
 
 import csv
@@ -17,7 +21,8 @@ from . import lib as L
 HEADER = ["Environment", "Episode", "Iteration", "Discovered Nodes", "Owned Nodes", "Alive nodes", "Source node",
           "Target node", "Vulnerability ID", "Outcome Mapped", "Reward", "Outcome", "Done", "Source Node Details",
           "Target Node Details", "Previous Source Node Details", "Previous Target Node Details", "Edges"]
-_PRIV = {0: "PrivilegeLevel.NoAccess", 1: "PrivilegeLevel.LocalUser", 3: "PrivilegeLevel.ROOT"}
+# PrivilegeLevel is an IntEnum: str() is the bare integer under the reference's Python (3.12, environment.yml:22)
+_PRIV = {0: "0", 1: "1", 3: "3"}
 
 
 class TraceCsvWriter:
@@ -51,7 +56,7 @@ class TraceCsvWriter:
             s += f"{svc.port} {svc.running} {fin} {fout} "
         s += " / vulnerabilities : "
         for v in nd.vulns:
-            s += f"{v.vid}  " + "".join(f"{'remote' if r.vtype else 'local'}--{C.KIND_NAMES[r.kind]}  " for r in v.results)
+            s += f"{v.vid}  " + "".join(f"{'remote' if r.vtype else 'local'}--{C.KIND_LABELS[r.kind]}  " for r in v.results)
         return s
 
     def _lists(self, snap, b):
@@ -83,7 +88,7 @@ class TraceCsvWriter:
             tgt_now = self._node_str(after, b, tg) if int(after["scal"][L.S_SCENARIO, b]) == sc else ""
             if float(reward[b]) > 0 and not finished:    # an edge is added when the step's reward is positive (compressed:483)
                 self.edges[b].append(f"{ids[s]}:{ids[tg]}:{t.vuln_ids[sc][u]}")
-            self.writer.writerow([sc, int(before["scal"][L.S_EPISODES, b]), step_count, disc, owned, alive, ids[s], ids[tg],
+            self.writer.writerow([sc, int(before["scal"][L.S_EPISODES, b]), step_count - 1, disc, owned, alive, ids[s], ids[tg],
                                   t.vuln_ids[sc][u], C.KIND_NAMES[kind], float(reward[b]),
                                   C.KIND_NAMES[code] if code < 16 else C.OC_NAMES.get(code), finished, src_now, tgt_now,
                                   self._node_str(before, b, s), self._node_str(before, b, tg), ",".join(self.edges[b])])

@@ -59,3 +59,50 @@ def test_csv_header_is_the_reference_header(tmp_path):
     with open(os.path.join(str(tmp_path), "logs.csv"), newline="") as f:
         assert next(csv.reader(f)) == HEADER
     wrapper.file.close()
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
+def test_node_detail_strings_match_get_str_info():
+    """TraceCsvWriter._node_str (fed a state snapshot in the device's mask layout) against the reference's own
+    RandomSwitchEnv.get_str_info (switch.py:307-334) for every node after every step of a scripted-attacker trace: status,
+    privilege (IntEnum -> bare integer under the reference's Python 3.12), data / persistence / evasion flags, services with
+    their firewall flags, vulnerabilities with the generator's outcome labels."""
+    import ccbs_b200.constants as C
+    from ccbs_b200 import lib as L
+    from ccbs_b200.trace_csv import TraceCsvWriter
+    from oracle import gen_golden as gg, trace as tr, ref_bridge as rb
+    from oracle.cbs_oracle import OracleEnv
+    name = "p6_control_win"
+    p, graph, model, spec, cfg, weights = gg.build_case(name)
+    case = gg.load_case(os.path.join(os.path.dirname(__file__), "golden", name + ".npz"))
+    runner, oracle = rb.ReferenceRunner(model, weights, cfg), OracleEnv(spec, weights, cfg)
+
+    class _Env:
+        tables = cb.compile_scenarios([spec], cfg.isolation_filter_threshold)
+    writer = TraceCsvWriter.__new__(TraceCsvWriter)
+    writer.env = _Env()
+
+    def snapshot():
+        m64 = tr.masks_to_array(oracle.masks())                      # [N_MASKS, 2] uint64 -> the device's [N_MASKS, words, B] uint32
+        masks = np.zeros((C.N_MASKS, 4, 1), np.uint32)
+        for w in range(4):
+            masks[:, w, 0] = (m64[:, w // 2] >> np.uint64(32 * (w % 2))) & np.uint64(0xFFFFFFFF)
+        return dict(masks=masks, scal=np.zeros((L.NUM_SCALARS, 1), np.int32))
+
+    starter = int(case["starters"][0])
+    runner.reset(starter)
+    oracle.reset(starter=starter)
+    seen = set()
+    for t in range(80):
+        a = (np.asarray(oracle.action_rows[int(case["policy_rows"][t])], np.float64) + case["actions"][t].astype(np.float64)).astype(np.float32)
+        runner.step(a, case["uniforms"][t])
+        oracle.step(a, case["uniforms"][t])
+        if oracle.done or oracle.truncated:
+            break
+        snap = snapshot()
+        for j, nid in enumerate(runner.ids):
+            want = runner.wrapper.get_str_info(runner.env.get_node(nid))
+            assert writer._node_str(snap, 0, j) == want, (t, j)
+            seen.add(want.split(" / tag")[0] + want.split("privilege level : ")[1][:1])
+    assert t >= 40 and len(seen) >= 3          # Running / Stopped nodes and several privilege levels were compared
