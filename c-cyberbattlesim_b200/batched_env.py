@@ -276,6 +276,10 @@ class BatchedCyberBattleEnv:
     def reward64(self) -> np.ndarray:
         return self.read(L.F_REWARD64, np.float64, (self.num_envs,))
 
+    def distances(self) -> np.ndarray:
+        """float64[B]: distance of the last decoded action to its table row (info['min_distance_action'], compressed:449)."""
+        return self.read(L.F_DIST, np.float64, (self.num_envs,))
+
     def stat_accum(self) -> dict:
         a = self.read(L.F_STAT_ACCUM, np.float64, (L.NUM_ACCUM,))
         return dict(zip(L.ACCUM_NAMES, a.tolist()))

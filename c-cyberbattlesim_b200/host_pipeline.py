@@ -79,6 +79,9 @@ class ShardedHostEnv:
     def last_stats(self) -> np.ndarray:
         return np.concatenate([e.last_stats() for e in self.envs], axis=0)
 
+    def distances(self) -> np.ndarray:
+        return np.concatenate([e.distances() for e in self.envs], axis=0)
+
     def stat_accum(self) -> dict:
         out: dict = {}
         for e in self.envs:

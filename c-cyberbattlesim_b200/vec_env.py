@@ -86,11 +86,16 @@ class CyberBattleVecEnv(_SB3VecEnv):
             term = env.terminal_obs()
             stats = env.last_stats()
         infos: List[dict] = []
+        dist = None
         for b in range(self.num_envs):
             if self.lazy_infos and not done[b]:
                 infos.append(self._empty)
                 continue
-            infos.append(self._info_dict(b, info[b]))
+            d = self._info_dict(b, info[b])
+            if dist is None:
+                dist = env.distances()                       # one read per step, and only when some info dict is built
+            d["min_distance_action"] = float(dist[b])        # compressed:449; callbacks_multi_env.py:89-90 reads it
+            infos.append(d)
         for b in finished:
             d = infos[b]
             d["terminal_observation"] = {"graph_embeddings": term[b, :-2].astype(np.float64),
@@ -116,6 +121,7 @@ class CyberBattleVecEnv(_SB3VecEnv):
         s, tg, u, kind, code, reason, step_count, _ = (int(x) for x in row)
         nodes, vulns = t.node_ids[sc], t.vuln_ids[sc]
         return {
+            "description": "CyberBattleEnvCompressed step info",                               # compressed:436
             "source_node": nodes[s] if 0 <= s < len(nodes) else None,
             "target_node": nodes[tg] if 0 <= tg < len(nodes) else None,
             "source_node_tag": t.specs[sc].nodes[s].tag if t.specs and 0 <= s < len(nodes) else "",
@@ -209,7 +215,7 @@ class RandomSwitchEnvB200:
         self.truncated = bool(row[7])
         o = _obs_dict(obs.cpu().numpy())
         d = CyberBattleVecEnv._info_dict(self, 0, row)
-        d["min_distance_action"] = float(self.env.read(9, np.float64, (1,))[0])
+        d["min_distance_action"] = float(self.env.distances()[0])
         return {k: v[0] for k, v in o.items()}, float(self.env.reward64()[0]), self.done, self.truncated, d
 
     def get_statistics(self):
