@@ -70,3 +70,27 @@ def test_unsupported_reference_options_are_not_silently_dropped():
     with pytest.warns(UserWarning):
         cfg = cb.EnvConfig.from_reference_dicts({"sample_subset_samples": 100, "episode_iterations": 77}, rewards)
     assert cfg.episode_iterations == 77
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
+def test_every_reference_train_config_parses():
+    """EnvConfig.from_reference_dicts over the reference's own YAML files (agents/*/config/train_config.yaml +
+    rewards_config.yaml) for all six goals: the defaults of every trainer are accepted (sample_subset_samples with its warning)."""
+    import glob
+    import warnings
+    import yaml
+    paths = glob.glob("/root/reference/cyberbattle/agents/**/config/train_config.yaml", recursive=True)
+    assert len(paths) >= 3
+    for tcp in paths:
+        tc = yaml.safe_load(open(tcp))
+        rcp = os.path.join(os.path.dirname(tcp), "rewards_config.yaml")
+        rc = yaml.safe_load(open(rcp if os.path.exists(rcp) else "/root/reference/cyberbattle/agents/config/rewards_config.yaml"))
+        assert set(rc["rewards_dict"]) == set(cb.constants.GOALS)
+        for goal in rc["rewards_dict"]:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                cfg = cb.EnvConfig.from_reference_dicts(tc, rc, goal=goal)
+            assert cfg.goal == goal and cfg.distance_metric == tc["distance_metric"] and cfg.sample_subset_samples == 0
+            assert cfg.episode_iterations == tc["episode_iterations"]
+            assert len(cfg.reward_vector()) == 10 and len(cfg.penalty_vector()) == 18
