@@ -82,9 +82,8 @@ class EnvConfig:
     # compressed:82,570-590: metric of the nearest-row decode: 'cosine' (scipy cdist, default), 'l1', 'l2', 'inf' (np.linalg.norm)
     distance_metric: str = "cosine"
     # compressed:83,521-522,553-567: keep at most this many action-table rows per outcome class (0 / False = the whole table).
-    # Restated by the oracle with a Philox-keyed subset rule (ccbs_b200.philox.subset_keep) and pinned against the reference
-    # fed the same rule; NOT implemented by the CUDA path yet: BatchedCyberBattleEnv refuses it (from_reference_dicts drops it
-    # with a warning, as before).
+    # The reference draws the subset with np.random.choice; the oracle and the CUDA path both use the Philox-keyed rule
+    # ccbs_b200.philox.subset_keep (pinned against the reference fed the same rule, fixtures s*).
     sample_subset_samples: int = 0
     rewards_dict: Dict[str, float] = field(default_factory=dict)
     penalties_dict: Dict[str, float] = field(default_factory=dict)
@@ -105,6 +104,11 @@ class EnvConfig:
             raise ValueError("precise_action_space_positions cannot be used with the 'events' defender: the reference raises "
                              "networkx.NodeNotFound as soon as an event changes a node that is not in the visible graph "
                              "(nx.has_path on `changed_nodes`, compressed:423-427,498-500)")
+        if not self.random_starter_node:
+            # cyberbattle_env.py:190-191 takes node 0 and skips the block that computes ownable / discoverable / disruptable
+            # counts (:205-217), so the reference's own goal test (:470) raises AttributeError on the first step
+            raise ValueError("random_starter_node=False is not supported: the reference never computes the reachable-node "
+                             "counts on that branch (cyberbattle_env.py:190-191 vs :205-217) and fails at its first goal test")
         if self.static_defender_agent == "reimage":
             if not (1 <= int(self.scan_capacity) <= C.MAX_SCAN_CAPACITY):
                 raise ValueError(f"scan_capacity must be in 1..{C.MAX_SCAN_CAPACITY}")
@@ -126,19 +130,14 @@ class EnvConfig:
                 if hasattr(obj, k_obj):
                     train_config[k_cfg] = getattr(obj, k_obj)
         train_config["static_defender_agent"] = sda or None
-        if sda and sda != "reimage":
-            raise ValueError("only the 'reimage' static defender is implemented by the batched env (DESIGN.md §5)")
+        if sda and sda not in ("reimage", "events"):
+            raise ValueError(f"unknown static defender {sda!r} (the reference has 'reimage' and 'events', _env/static_defender.py)")
         if sda:
             # train_agent.py:395-397 draws the three parameters once per run from [min, max]; the midpoint is used here
             for k in ("detect_probability", "scan_capacity", "scan_frequency"):
                 if k not in train_config and f"{k}_min" in train_config:
                     mid = (train_config[f"{k}_min"] + train_config[f"{k}_max"]) / 2
                     train_config[k] = mid if k == "detect_probability" else int(round(mid))
-        if train_config.get("sample_subset_samples"):
-            train_config["sample_subset_samples"] = 0
-            import warnings
-            warnings.warn("sample_subset_samples is ignored: the batched decode always scans the full action table "
-                          "(the reference sub-samples it with np.random.choice to bound cdist time)", stacklevel=2)
         if train_config.get("pca_components") not in (None, False, 768):
             raise ValueError("only 768-dimensional vulnerability embeddings are implemented")
         kw = {k: v for k, v in train_config.items() if k in keys}

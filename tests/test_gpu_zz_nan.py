@@ -3,15 +3,14 @@ returns the FIRST NaN row, i.e. the first row of the insertion-ordered table; th
 decode_select keeps np.argmin's NaN rule in its float64 re-score (k_decode.cu flush_candidates); the l1 / l2 / inf kernels
 never produce NaN from finite inputs and must simply agree with the oracle.
 
-Written after the round's GPU budget was spent: not yet run on a B200, hence the non-strict xfail marker (an XPASS is the
-expected outcome; remove the marker once seen)."""
+Distances are compared at the golden replay's float tolerance (rtol 1e-5: the node embeddings come from two different fp32
+encoders, torch-CPU in the oracle and the observe kernel here); the decoded row, the NaN-ness and "row 0 wins" are exact."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="not yet run on a GPU (written after the round's GPU budget was spent)")
 @pytest.mark.parametrize("metric", ["cosine", "l2"])
 def test_zero_action_decodes_like_np_argmin(metric):
     import warnings
@@ -41,7 +40,7 @@ def test_zero_action_decodes_like_np_argmin(metric):
         if np.isnan(d):
             assert metric == "cosine" and row == 0 and np.all(np.isnan(gd))
         else:
-            np.testing.assert_allclose(gd, d, rtol=1e-9)
+            np.testing.assert_allclose(gd, d, rtol=1e-5)
         u = torch.full((3,), 0.37, dtype=torch.float32, device=env.device)
         env.transition(sel, dist, u)
         env.observe()
