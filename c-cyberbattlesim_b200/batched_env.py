@@ -27,13 +27,13 @@ class CbsError(RuntimeError):
 class BatchedCyberBattleEnv:
     def __init__(self, specs: Sequence[ScenarioSpec], gae_weights: GaeWeights, cfg: Optional[EnvConfig] = None,
                  num_envs: int = 1, device: int = 0, scenario_of_env: Optional[np.ndarray] = None, seed: int = 0,
-                 global_env_offset: int = 0, auto_reset: bool = True, switch_interval: int = 0,
+                 global_env_offset: int = 0, auto_reset: bool = True, switch_interval: Optional[int] = None,
                  tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None,
                  gae_tables=None, **cfg_overrides):
         self.cfg = cfg or EnvConfig()
-        if getattr(self.cfg, "sample_subset_samples", 0):
-            raise NotImplementedError("sample_subset_samples (compressed:553-567) is restated by the oracle only so far; the CUDA "
-                                      "decode scans the whole action table (DESIGN.md §5)")
+        if getattr(self.cfg, "sample_subset_samples", 0) and self.cfg.distance_metric != "cosine":
+            raise NotImplementedError("sample_subset_samples together with the l1 / l2 / inf decode metrics is not implemented "
+                                      "(the sub-sampled table is scanned by the cosine decode only)")
         if getattr(self.cfg, "static_defender_agent", None) == "events":
             raise NotImplementedError("the 'events' static defender (ExternalRandomEvents, _env/static_defender.py:63-161) is restated by "
                                       "the oracle only so far (DESIGN.md §5)")
@@ -279,6 +279,10 @@ class BatchedCyberBattleEnv:
     def distances(self) -> np.ndarray:
         """float64[B]: distance of the last decoded action to its table row (info['min_distance_action'], compressed:449)."""
         return self.read(L.F_DIST, np.float64, (self.num_envs,))
+
+    def divergence_count(self) -> int:
+        """Env-steps so far at which the reference itself would have raised (see CBS_F_DIVERGENCE in include/cbsim.h)."""
+        return int(self.read(L.F_DIVERGENCE, np.int32, (1,))[0])
 
     def stat_accum(self) -> dict:
         a = self.read(L.F_STAT_ACCUM, np.float64, (L.NUM_ACCUM,))

@@ -64,7 +64,10 @@ class EnvConfig:
     remove_main_obstacles: bool = True
     remove_all_obstacles: bool = False
     random_starter_node: bool = True
-    switch_interval: int = 5
+    # RandomSwitchEnv.switch_interval (cyberbattle_env_switch.py:218-220; 5 in agents/config/train_config.yaml, filled in by
+    # from_reference_dicts): a reset draws a new scenario when (episodes finished + 1) % (switch_interval + 1) == 0.
+    # None = never switch (every env keeps its scenario); BatchedCyberBattleEnv(switch_interval=...) overrides it.
+    switch_interval: Optional[int] = None
     interest_node_value: int = 200        # agents/config/train_config.yaml:16 (value of the node of interest, *_node goals)
     # static defender (_env/static_defender.py): None, "reimage" (ScanAndReimageCompromisedMachines, :27-60) or "events"
     # (ExternalRandomEvents, :63-161: per node and step one of start / stop a service, add / remove a firewall rule, each with

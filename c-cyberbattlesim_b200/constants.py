@@ -171,5 +171,5 @@ MAX_NODES = 128  # 4 mask words; config 4 tops out at 100 nodes
 def switch_due(episodes_finished: int, switch_interval: int) -> bool:
     """RandomSwitchEnv._check_switch (cyberbattle_env_switch.py:218-220), evaluated by reset() after ``episodes_finished``
     episodes have ended: a new scenario is drawn when ``(episode_count + 1) % (switch_interval + 1) == 0``.  The device applies
-    the same test when it resets a finished env in place (k_observe.cu reset_env; ``switch_interval <= 0`` = never there)."""
+    the same test when it resets a finished env in place (k_observe.cu reset_env; ``switch_interval < 0`` = never there)."""
     return (int(episodes_finished) + 1) % (int(switch_interval) + 1) == 0

@@ -30,7 +30,7 @@ __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
   o[4] = sc[S_OUTCOME];
   o[5] = (flags >> FL_REASON_SHIFT) & 3;
   o[6] = sc[S_STEPCOUNT];
-  o[7] = (flags & FL_TRUNC) ? 1 : 0;
+  o[7] = ((flags & FL_TRUNC) ? 1 : 0) | ((sc[S_SCST] >> 8) << 8);   // bit 0 truncated, bits 8.. the scenario in force during the step
 }
 
 __global__ void init_flags_kernel(int32_t* scal, int B) {
@@ -43,6 +43,9 @@ using namespace cbs;
 namespace cbs { extern long long* g_sel_trace; extern long long* g_obs_trace; }
 
 static thread_local std::string g_create_error;
+static const char* const kErrflagMessage =
+    "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 5 owned-node list, "
+    "6 sub-sampled action table, 7 removal of an absent owned node (the reference raises ValueError there), 9 tensor-core pipeline timeout)";
 
 struct cbs_handle {
   cbs_config cfg{};
@@ -64,6 +67,7 @@ struct cbs_handle {
   float *h_actions = nullptr, *h_uniforms = nullptr, *h_reward = nullptr;
   uint8_t* h_done = nullptr;
   int32_t* h_info = nullptr;
+  int32_t* h_errflag = nullptr;   // pinned host copy of State::errflag, refreshed by every cbs_step_host_async
   // io scratch for cbs_step
   int32_t* d_sel = nullptr;
   double* d_dist = nullptr;
@@ -124,6 +128,27 @@ static std::vector<int32_t> instance_port_offsets(const cbs_scenario_tables* t) 
   return off;
 }
 
+
+// Per-env capacities an episode of the given cut-offs can need (snapshot slots = table-growing encodes, visible-graph edges)
+static void derive_capacities(int max_nodes, int episode_iterations, double prop_coeff, bool defender, bool precise, int* slots_out,
+                              int* ecap_out, int* max_steps_out) {
+  int max_steps = episode_iterations;
+  if (prop_coeff > 0) {
+    const double lim = (double)(max_nodes - 1) * prop_coeff;
+    const int l = (int)lim + ((double)(int)lim < lim ? 1 : 0);
+    if (l < max_steps) max_steps = l;
+  }
+  max_steps += 1;   // the cut-offs test the pre-increment counter (cyberbattle_env.py:361-366, :394)
+  // table-growing encodes: each adds an owned or a discovered node ... or, under a defender, sees a node come back from
+  // re-imaging with pairs still missing
+  int slots = (defender ? 4 : 2) * max_nodes - 1;
+  if (max_steps + 1 < slots) slots = max_steps + 1;
+  if (precise) slots = max_steps + 1;   // every table-maintaining encode may refresh rows: one snapshot per step
+  int ecap = max_nodes * max_nodes;
+  if (max_steps < ecap) ecap = max_steps;
+  *slots_out = slots; *ecap_out = ecap; *max_steps_out = max_steps;
+}
+
 extern "C" {
 
 int cbs_abi_version(void) { return CBS_ABI_VERSION; }
@@ -179,6 +204,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
   P.precise_positions = cfg->precise_action_space_positions ? 1 : 0;
   P.metric = cfg->distance_metric;
+  P.subset_k = cfg->sample_subset_samples > 0 ? cfg->sample_subset_samples : 0;
   *out = h;
   return CBS_OK;
 }
@@ -190,6 +216,7 @@ void cbs_destroy(cbs_handle* h) {
   for (void* p : h->table_allocs) cudaFree(p);
   for (void* p : h->state_allocs) cudaFree(p);
   if (h->hstream) cudaStreamDestroy(h->hstream);
+  if (h->h_errflag) cudaFreeHost(h->h_errflag);
   delete h;
 }
 
@@ -198,6 +225,15 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if (h->loaded) return fail(h, CBS_ERR_INVALID_ARG, "scenarios already loaded (create a new handle)");
   if (t->max_nodes < 1 || t->max_nodes > CBS_MAX_NODES) return fail(h, CBS_ERR_INVALID_ARG, "max_nodes %d out of range", t->max_nodes);
   if (t->words != (t->max_nodes + 31) / 32) return fail(h, CBS_ERR_INVALID_ARG, "words does not match max_nodes");
+  if (h->P.subset_k) {   // limits of the explicit table's 32-bit row entries and of the Philox row identity (subset.cuh)
+    for (int n = 0; n < t->num_nodes_total; ++n)
+      if (t->nd_row_off[2 * n + 2] - t->nd_row_off[2 * n] > SUB_MAX_ROWS_PER_PAIR)
+        return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples: node %d has more than %d candidate rows", n, SUB_MAX_ROWS_PER_PAIR);
+    for (int s = 0; s < t->num_scenarios; ++s)
+      if (t->sc_num_uvuln[s] > 4096) return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples: scenario %d has more than 4096 vulnerabilities", s);
+    if (h->cfg.distance_metric != METRIC_COSINE)
+      return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples is implemented for the cosine decode only");
+  }
   CK(h, cudaSetDevice(h->cfg.device));
   Tables& T = h->T;
   Params& P = h->P;
@@ -276,18 +312,9 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   // capacities
   P.ncap = ((t->max_nodes + 3) / 4) * 4;
   P.words = t->words;
-  int max_steps = h->cfg.episode_iterations;
-  if (P.prop_coeff > 0) {
-    const double lim = (double)(t->max_nodes - 1) * P.prop_coeff;
-    const int l = (int)lim + ((double)(int)lim < lim ? 1 : 0);
-    if (l < max_steps) max_steps = l;
-  }
-  max_steps += 1;   // the cut-offs test the pre-increment counter (cyberbattle_env.py:361-366, :394)
-  // table-growing encodes: each adds an owned or a discovered node ... or, under a defender, sees a node come back from
-  // re-imaging with pairs still missing
-  int slots = (h->cfg.static_defender ? 4 : 2) * t->max_nodes - 1;
-  if (max_steps + 1 < slots) slots = max_steps + 1;
-  if (P.precise_positions) slots = max_steps + 1;   // every table-maintaining encode may refresh rows: one snapshot per step
+  int slots = 0, ecap = 0, max_steps = 0;
+  derive_capacities(t->max_nodes, h->cfg.episode_iterations, P.prop_coeff, h->cfg.static_defender != 0, P.precise_positions != 0, &slots, &ecap,
+                    &max_steps);
   if (slots > 255) {
     if (P.precise_positions && h->cfg.max_slots <= 0)
       return fail(h, CBS_ERR_INVALID_ARG, "precise_action_space_positions needs one snapshot slot per episode step: episodes of up to %d "
@@ -296,8 +323,6 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   }
   P.slots = h->cfg.max_slots > 0 ? h->cfg.max_slots : slots;
   if (P.slots > 255) return fail(h, CBS_ERR_INVALID_ARG, "max_slots must be <= 255");
-  int ecap = t->max_nodes * t->max_nodes;
-  if (max_steps < ecap) ecap = max_steps;
   P.ecap = h->cfg.max_edges > 0 ? h->cfg.max_edges : ecap;
   h->Ug = t->num_global_vulns;
   h->vt_stride = ((h->Ug + 63) / 64) * 64;
@@ -324,8 +349,11 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * P.obs_dim); AL(term_obs, B * P.obs_dim); AL(sel, B * 4); AL(dist, B); AL(reward64, B);
-  AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 1);
+  AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 2);
   AL(scratch, P.ncap > CBS_OBS_SMEM_NODES ? B * 2 * P.ncap * NODE_EMB : 1);   // only graphs beyond the shared-memory buffers use it
+  AL(sub_rows, P.subset_k ? B * SUB_CLASSES * P.subset_k : 1); AL(sub_meta, P.subset_k ? B * SUB_META : 1);
+  AL(sub_alive, (P.subset_k && P.precise_positions) ? B * P.ncap * P.ncap * (SUB_MAX_ROWS_PER_PAIR / 32) : 1);
+  AL(sub_newp, (P.subset_k && P.ncap > CBS_OBS_SMEM_NODES) ? B * P.ncap * P.ncap : 1);
 #undef AL
   if ((rc = dalloc(h, h->state_allocs, &h->d_sel, B * 4))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->d_dist, B))) return rc;
@@ -382,6 +410,15 @@ int cbs_set_defender_draws(cbs_handle* h, const int32_t* scan_nodes_dev, const f
 
 int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double prop) {
   if (!h) return CBS_ERR_INVALID_ARG;
+  if (h->loaded) {   // the per-env buffers were sized from the cut-offs in force at load time: longer episodes must still fit
+    int slots = 0, ecap = 0, max_steps = 0;
+    derive_capacities(h->T.max_nodes, episode_iterations, prop, h->P.defender != 0, h->P.precise_positions != 0, &slots, &ecap, &max_steps);
+    if (slots > 255) slots = 255;
+    if (slots > h->P.slots || ecap > h->P.ecap)
+      return fail(h, CBS_ERR_CAPACITY, "cut-offs (%d iterations, coefficient %g) allow episodes of %d steps, which need %d snapshot slots and "
+                  "%d edges per env; this handle was created with %d / %d.  Create it with cbs_config.max_slots / max_edges (or the "
+                  "larger cut-offs) instead", episode_iterations, prop, max_steps, slots, ecap, h->P.slots, h->P.ecap);
+  }
   h->P.episode_iterations = episode_iterations;
   h->P.prop_coeff = prop;
   return CBS_OK;
@@ -522,6 +559,8 @@ static int ensure_host_staging(cbs_handle* h) {
   if ((rc = dalloc(h, h->state_allocs, &h->h_reward, B, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_done, B, false))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->h_info, B * CBS_INFO_INTS, false))) return rc;
+  CK(h, cudaMallocHost(&h->h_errflag, sizeof(int32_t)));
+  *h->h_errflag = 0;
   return 0;
 }
 
@@ -547,6 +586,7 @@ int cbs_step_host_async(cbs_handle* h, const float* actions_host, const float* u
   if (reward_host) CK(h, cudaMemcpyAsync(reward_host, h->h_reward, B * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (done_host) CK(h, cudaMemcpyAsync(done_host, h->h_done, B, cudaMemcpyDeviceToHost, st));
   if (info_host) CK(h, cudaMemcpyAsync(info_host, h->h_info, B * CBS_INFO_INTS * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(h, cudaMemcpyAsync(h->h_errflag, h->S.errflag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));   // checked by cbs_host_sync
   return CBS_OK;
 }
 
@@ -554,6 +594,7 @@ int cbs_host_sync(cbs_handle* h) {
   int rc = check_ready(h);
   if (rc) return rc;
   if (h->hstream) CK(h, cudaStreamSynchronize(h->hstream));
+  if (h->h_errflag && *h->h_errflag) return fail(h, CBS_ERR_CAPACITY, kErrflagMessage, *h->h_errflag);
   return CBS_OK;
 }
 
@@ -585,6 +626,7 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_REWARD64: *p = S.reward64; *bytes = B * 8; break;
     case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
     case CBS_F_SEL: *p = S.sel; *bytes = B * 16; break;
+    case CBS_F_DIVERGENCE: *p = S.errflag + 1; *bytes = 4; break;
     case CBS_F_VT: *p = S.vt; *bytes = B * h->vt_stride * 4; break;
     default: return fail(h, CBS_ERR_INVALID_ARG, "unknown state field %d", field);
   }
@@ -662,7 +704,7 @@ int cbs_sync(cbs_handle* h) {
   CK(h, cudaDeviceSynchronize());
   int flag = 0;
   CK(h, cudaMemcpy(&flag, h->S.errflag, 4, cudaMemcpyDeviceToHost));
-  if (flag) return fail(h, CBS_ERR_CAPACITY, "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 5 owned-node list, 9 tensor-core pipeline timeout)", flag);
+  if (flag) return fail(h, CBS_ERR_CAPACITY, kErrflagMessage, flag);
   return CBS_OK;
 }
 

@@ -27,6 +27,10 @@ constexpr int RC_N2 = RC_Z + NODE_EMB;
 constexpr int RC_PITCH = 336;
 constexpr int OBS_CLASSES = 6;  // observe work classes, heaviest first (transition.cuh): the observe kernel's duration is set by its
                                 // longest items (an episode end behind a 30-node re-encode), so they must be claimed first
+constexpr int SUB_CLASSES = 10;   // outcome kinds that can have action-table rows (K_DOS .. K_LATERAL; Execution never does)
+constexpr int SUB_META = 16;      // int32 per env in State::sub_meta: [0, 10) rows alive per class, [10] classes ranked so far, [11], [12] the
+                                  // classes' first-appearance rank (4 bits per kind, 15 = not in the table yet), [13] lifetime count of balance calls
+constexpr int SUB_MAX_ROWS_PER_PAIR = 256;   // candidate rows of one (source, target) pair addressable by a list entry
 constexpr int SCHED_BINS = 8;   // decode cost bins: rows < 64, < 128, ..., >= 4096 (longest-first scheduling)
 
 // outcome kinds (simulation/model.py:66-193)
@@ -132,6 +136,7 @@ struct Params {  // configuration, by value
   int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
   int precise_positions;   // precise_action_space_positions (compressed:419-427,498-506): table rows are refreshed, see build_table
   int metric;              // enum Metric; != METRIC_COSINE: k_decode_metric.cu decodes, the transition runs as its own launch
+  int subset_k;            // sample_subset_samples (compressed:521-522,553-567): rows kept per outcome class, 0 = the whole table
 };
 
 struct State {  // mutable, device pointers
@@ -172,12 +177,17 @@ struct State {  // mutable, device pointers
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   float* reset_cache;          // [total scenario nodes][RC_PITCH], filled by the first reset from each (scenario, starter)
   int32_t* reset_cache_flag;   // [total scenario nodes] 1 = entry valid
-  int32_t* errflag;      // [1]
+  int32_t* errflag;      // [2]  [0] capacity / domain error code (cbs_sync), [1] steps at which the reference itself would have raised (CBS_F_DIVERGENCE)
   int32_t* worklist;     // [OBS_CLASSES][B] envs whose step needs graph work, by cost class
   int32_t* work_ctr;     // [1] finished-warp counter, [2] next item (dynamic scheduling), [4 .. 4 + OBS_CLASSES) class list lengths
   int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)
   int32_t* bin_cnt;      // [2][SCHED_BINS + 1] envs per cost bin (double buffered; filled by the transition for the next decode), [SCHED_BINS] = finished-warp counter
   int32_t* bin_list;     // [2][SCHED_BINS][B] env ids per bin
+  // sample_subset_samples only (1-element dummies otherwise): the action table is then EXPLICIT, at most subset_k rows per outcome class
+  uint32_t* sub_rows;    // [B][SUB_CLASSES][subset_k]  source | target << 7 | row within the pair << 14 | insertion epoch << 22
+  int32_t* sub_meta;     // [B][SUB_META]
+  uint32_t* sub_alive;   // [B][ncap*ncap][8]  with precise_action_space_positions: which rows of a pair are in the lists
+  uint16_t* sub_newp;    // [B][ncap*ncap]     scratch (graphs beyond the shared-memory buffers): the pairs one table build touches
 };
 
 

@@ -14,6 +14,7 @@
 #include <cstdlib>
 
 #include "transition.cuh"
+#include "subset.cuh"
 
 namespace cbs {
 
@@ -110,8 +111,9 @@ struct SelWarp {
   uint32_t p_key[32];         // insertion epoch << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
   int p_slot[32];             // snapshot slot the pair's rows carry (== the epoch unless precise_action_space_positions refreshed them)
   float c_score[CAND_CAP];    // rows still within `margin` of the running maximum, waiting for the float64 re-score
-  uint32_t c_key[CAND_CAP], c_packed[CAND_CAP];
-  int c_row[CAND_CAP], c_slot[CAND_CAP];
+  unsigned long long c_key[CAND_CAP];   // place in the table's order (np.argmin takes the first of equal distances)
+  uint32_t c_packed[CAND_CAP];
+  int c_row[CAND_CAP], c_slot[CAND_CAP], c_st[CAND_CAP];   // c_st: source | target << 8
   uint8_t oorder[MAX_NODES], dorder[MAX_NODES];
 };
 
@@ -183,10 +185,9 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
                                                  int& ncand, float threshold, int b, double na, int lane, Best& best) {
   for (int i = 0; i < ncand; ++i) {
     if (sh.c_score[i] < threshold) continue;               // NaN scores are kept (comparison false)
-    const uint32_t k = sh.c_key[i];
+    const unsigned long long key = sh.c_key[i];
     const int r = sh.c_row[i];
-    const int slot = sh.c_slot[i], s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
-    const unsigned long long key = ((unsigned long long)k << 32) | (unsigned long long)(unsigned)r;
+    const int slot = sh.c_slot[i], s = sh.c_st[i] & 0xFF, t = sh.c_st[i] >> 8;
     const double d = exact_distance(T, P, S, act, b, s, t, slot, sh.c_packed[i], na, lane);
     // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
     const bool dn = d != d, bn = best.d != best.d;
@@ -219,7 +220,8 @@ struct FusedTransition {
 };
 
 // W1: one-word mask planes and no defender -> the fused transition stages the env's records in registers
-template <bool FUSE, bool DEF, bool W1>
+// SUBSET: sample_subset_samples — the table is the env's explicit per-class row lists (subset.cuh), scanned one row per lane
+template <bool FUSE, bool DEF, bool W1, bool SUBSET>
 __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kernel(Tables T, Params P, State S, const float* __restrict__ actions,
                                                                    int vt_stride, int vt_cached, int sched_buf, FusedTransition ft,
                                                                    int32_t* __restrict__ sel_out, double* __restrict__ dist_out,
@@ -299,7 +301,89 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   Best best{INFINITY, ~0ull, 0, 0, -1, 0u};
   int ncand = 0, n_rows = 0, n_live = 0, n_exact = 0;
 
-  const int combos = n_owned * n_disc;
+  const int combos = SUBSET ? 0 : n_owned * n_disc;
+  if constexpr (SUBSET) {
+    // ---- the explicit table: at most SUB_CLASSES x subset_k rows.  Lane-per-row: entry -> snapshot rows of its pair (half
+    //      precision) -> two 64-wide dots, the row template, score; candidates are parked for the float64 re-score as below ----
+    const int K = P.subset_k;
+    const uint32_t* lists = S.sub_rows + (size_t)b * SUB_CLASSES * K;
+    const int32_t* meta = S.sub_meta + (size_t)b * SUB_META;
+    int cls_end[SUB_CLASSES];
+    int total = 0;
+#pragma unroll
+    for (int c = 0; c < SUB_CLASSES; ++c) { total += meta[c]; cls_end[c] = total; }
+    const uint32_t rank_lo = (uint32_t)meta[11], rank_hi = (uint32_t)meta[12];
+    // positions of the nodes in the two order lists (tie order); p_st / p_n2 double as byte arrays here
+    uint8_t* dpos = reinterpret_cast<uint8_t*>(sh.p_st);
+    uint8_t* opos = reinterpret_cast<uint8_t*>(sh.p_n2);
+    for (int i = lane; i < n_disc; i += 32) dpos[sh.dorder[i]] = (uint8_t)i;
+    if (!DEF) for (int i = lane; i < n_owned; i += 32) opos[sh.oorder[i]] = (uint8_t)i;
+    __syncwarp();
+    n_rows = total;
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      float score = -INFINITY;
+      bool valid = false;
+      int s = 0, t = 0, slot = 0, r = 0;
+      uint32_t packed = 0u;
+      unsigned long long key = 0ull;
+      if (j < total) {
+        int c = 0, first = 0;
+#pragma unroll
+        for (int q = 0; q < SUB_CLASSES - 1; ++q) if (j >= cls_end[q]) { c = q + 1; first = cls_end[q]; }
+        const uint32_t e = lists[c * K + (j - first)];
+        s = e & 127; t = (e >> 7) & 127;
+        const int rip = (e >> 14) & 255, epoch = (int)(e >> 22);
+        slot = ps[s * P.ncap + t];
+        const int g = node_off + t;
+        r = T.nd_row_off[2 * g + (s == t ? 0 : 1)] + rip;
+        packed = T.row_packed[r];
+        const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
+        const uint4* zs = reinterpret_cast<const uint4*>(S.z16_hist + (zbase + s) * NODE_EMB);
+        const uint4* zt = reinterpret_cast<const uint4*>(S.z16_hist + (zbase + t) * NODE_EMB);
+        uint4 hs[NODE_EMB / 8], ht[NODE_EMB / 8];
+#pragma unroll
+        for (int i = 0; i < NODE_EMB / 8; ++i) { hs[i] = zs[i]; ht[i] = zt[i]; }
+        const float n2 = S.zn2_hist[zbase + s] + S.zn2_hist[zbase + t] + 1.f;
+        float st = 0.f;
+#pragma unroll
+        for (int i = 0; i < NODE_EMB / 8; ++i) {
+          st += dot8(hs[i], sh.a_st + 8 * i);
+          st += dot8(ht[i], sh.a_st + NODE_EMB + 8 * i);
+        }
+        const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
+        const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
+        const float vn2 = u < vt_cached ? vn2_sh[u] : (float)T.vnorm2[u];
+        score = (st + vtu + sh.a_o[oh]) * rsqrtf(n2 + vn2);
+        valid = true;
+        // table order: the classes in first-appearance order, inside a class the insertion order
+        const uint32_t rank = ((c < 8 ? rank_lo : rank_hi) >> (4 * (c & 7))) & 15u;
+        const int opk = DEF ? (int)S.pair_opos[(size_t)b * P.ncap * P.ncap + s * P.ncap + t] : (int)opos[s];
+        key = ((unsigned long long)rank << 32) |
+              (((unsigned long long)epoch << 24) | ((unsigned long long)opk << 16) | ((unsigned long long)dpos[t] << 8) | (unsigned long long)rip);
+      }
+      float cmax = score;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+      run_max = fmaxf(run_max, cmax);
+      unsigned cand = __ballot_sync(0xFFFFFFFFu, valid && !(score < run_max - margin_s));
+      while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        if (ncand == CAND_CAP) { n_exact += ncand; flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best); }
+        const float cs = __shfl_sync(0xFFFFFFFFu, score, src);
+        const int cst = __shfl_sync(0xFFFFFFFFu, s | (t << 8), src);
+        const int cslot = __shfl_sync(0xFFFFFFFFu, slot, src);
+        const int cr = __shfl_sync(0xFFFFFFFFu, r, src);
+        const uint32_t cp = __shfl_sync(0xFFFFFFFFu, packed, src);
+        const unsigned long long ck = __shfl_sync(0xFFFFFFFFu, key, src);
+        if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = ck; sh.c_st[ncand] = cst; sh.c_slot[ncand] = cslot; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp; }
+        ++ncand;
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+  }
   for (int cbase = 0; cbase < combos; cbase += 32) {
     // ---- phase A: one (source, target) combination per lane ----
     const int c = cbase + lane;
@@ -423,7 +507,12 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
           const int cpi = __shfl_sync(0xFFFFFFFFu, pp[q], src);
           const int cr = __shfl_sync(0xFFFFFFFFu, rr[q], src);
           const uint32_t cp = __shfl_sync(0xFFFFFFFFu, packed[q], src);
-          if (lane == 0) { sh.c_score[ncand] = cs; sh.c_key[ncand] = sh.p_key[cpi]; sh.c_slot[ncand] = sh.p_slot[cpi]; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp; }
+          if (lane == 0) {
+            const uint32_t pk = sh.p_key[cpi];
+            sh.c_score[ncand] = cs; sh.c_key[ncand] = ((unsigned long long)pk << 32) | (unsigned long long)(unsigned)cr;
+            sh.c_st[ncand] = (int)sh.oorder[pk & 0xFF] | ((int)sh.dorder[(pk >> 8) & 0xFF] << 8);
+            sh.c_slot[ncand] = sh.p_slot[cpi]; sh.c_row[ncand] = cr; sh.c_packed[ncand] = cp;
+          }
           ++ncand;
           __syncwarp();
         }
@@ -483,12 +572,15 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
   const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
   const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
-  static size_t attr[6] = {0, 0, 0, 0, 0, 0};
-  const int which = (fuse_transition ? 1 : 0) | (P.defender ? 2 : (P.words == 1 ? 4 : 0));
+  static size_t attr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const int which = ((fuse_transition ? 1 : 0) | (P.defender ? 2 : (P.words == 1 ? 4 : 0))) + (P.subset_k ? 6 : 0);
   using KernelFn = void (*)(Tables, Params, State, const float*, int, int, int, FusedTransition, int32_t*, double*, long long*);
-  const KernelFn kernels[6] = {decode_select_kernel<false, false, false>, decode_select_kernel<true, false, false>,
-                               decode_select_kernel<false, true, false>,  decode_select_kernel<true, true, false>,
-                               decode_select_kernel<false, false, true>,  decode_select_kernel<true, false, true>};
+  const KernelFn kernels[12] = {decode_select_kernel<false, false, false, false>, decode_select_kernel<true, false, false, false>,
+                                decode_select_kernel<false, true, false, false>,  decode_select_kernel<true, true, false, false>,
+                                decode_select_kernel<false, false, true, false>,  decode_select_kernel<true, false, true, false>,
+                                decode_select_kernel<false, false, false, true>,  decode_select_kernel<true, false, false, true>,
+                                decode_select_kernel<false, true, false, true>,   decode_select_kernel<true, true, false, true>,
+                                decode_select_kernel<false, false, true, true>,   decode_select_kernel<true, false, true, true>};
   const KernelFn kern = kernels[which];
   if (smem > 48 * 1024 && smem > attr[which]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

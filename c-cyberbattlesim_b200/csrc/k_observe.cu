@@ -13,6 +13,7 @@
 // embeddings of one env live in shared memory (<= 32 nodes) or in an L2-resident scratch slab (<= 128 nodes).
 #include "cbs_device.cuh"
 #include "philox.cuh"
+#include "subset.cuh"
 
 namespace cbs {
 
@@ -297,9 +298,17 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 //      or target can reach the action's source or target node in the visible graph (nx.has_path on the DiGraph; a node
 //      reaches itself) take the CURRENT embeddings — they move to this encode's snapshot slot while pair_epoch keeps their
 //      place in the table's insertion order.
+// With sample_subset_samples the pairs this build touches are also listed in the warp's scratch and handed to subset_update
+// (subset.cuh), which keeps the explicit, sub-sampled table.
 template <bool PRECISE>
 __device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg) {
   const bool refresh = PRECISE && refresh_arg;
+  SubScratch sub;
+  int n_newp = 0;
+  if (P.subset_k) {
+    const bool in_smem = W.g == W.ysm + SMEM_NODES * NODE_EMB;   // the projection buffer of a small graph; free once the encode is done
+    sub.carve(reinterpret_cast<unsigned char*>(W.ysm + SMEM_NODES * NODE_EMB), in_smem ? nullptr : S.sub_newp + (size_t)b * P.ncap * P.ncap);
+  }
   const int node_off_bt = scalar(S, P, S_NODE_OFF, b);
   int new_rows = 0;
   uint32_t reach[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
@@ -346,10 +355,11 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
     if (!(W.dynb[W.pos[s]] & 0x80)) continue;               // stopped sources add no rows (compressed:491-492)
     for (int base = 0; base < n_disc; base += 32) {
       const int dp = base + lane;
-      bool fresh = false;
+      bool fresh = false, fresh_refresh_only = false;
       if (dp < n_disc) {
         const int t = dorder[dp];
         const bool is_new = ps[s * P.ncap + t] == 0xFF;
+        fresh_refresh_only = !is_new;
         fresh = (W.dynb[dp] & 0x80) && (is_new || (PRECISE && refresh && (in_reach(s) || in_reach(t))));
         if (fresh && slot < P.slots) {
           ps[s * P.ncap + t] = (uint8_t)slot;
@@ -361,13 +371,22 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
           }
         }
       }
-      any_new |= __any_sync(0xFFFFFFFFu, fresh);
+      const unsigned fm = __ballot_sync(0xFFFFFFFFu, fresh);
+      any_new |= fm != 0u;
+      if (P.subset_k && fm && slot < P.slots) {
+        if (fresh) sub.newp[n_newp + __popc(fm & ((1u << lane) - 1u))] = (uint16_t)(dp | (op << 7) | (fresh_refresh_only ? 0x8000 : 0));
+        n_newp += __popc(fm);
+      }
     }
   }
-  if (!any_new) return;
+  if (!any_new) {
+    // the reference still balances (and draws from its generator) at the end of this create_continuous_action_space
+    if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos);
+    return;
+  }
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
   new_rows = (int)warp_sum((float)new_rows);
-  if (lane == 0) S.work_est[b] += new_rows;
+  if (lane == 0 && !P.subset_k) S.work_est[b] += new_rows;
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
@@ -382,6 +401,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
   __syncwarp();
+  if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos);
 }
 
 // ---- get_statistics (cyberbattle_env.py:517-524) + episode accumulators ----
@@ -456,7 +476,7 @@ __device__ int2 reset_env(const Tables& T, const Params& P, const State& S, int 
   const uint64_t genv = (uint64_t)(P.global_env_offset + b);
   const int episodes = scalar(S, P, S_EPISODES, b);
   int sc = scalar(S, P, S_SCENARIO, b);
-  if (P.switch_interval > 0 && episodes > 0 && (episodes + 1) % (P.switch_interval + 1) == 0) {   // _check_switch
+  if (P.switch_interval >= 0 && (episodes + 1) % (P.switch_interval + 1) == 0) {   // _check_switch (switch.py:218-220); < 0 = never
     const Philox4 r = philox4x32_10(P.seed, genv, (uint32_t)episodes, 2u);
     sc = (int)(((uint64_t)r.x * (uint64_t)T.num_scenarios) >> 32);
   }
@@ -482,6 +502,14 @@ __device__ int2 reset_env(const Tables& T, const Params& P, const State& S, int 
   }
   uint32_t* ps = reinterpret_cast<uint32_t*>(S.pair_slot + (size_t)b * P.ncap * P.ncap);
   for (int i = lane; i < P.ncap * P.ncap / 4; i += 32) ps[i] = 0xFFFFFFFFu;
+  if (P.subset_k) {   // empty table; the lifetime balance counter ([13]) goes on
+    int32_t* meta = S.sub_meta + (size_t)b * SUB_META;
+    if (lane < 13) meta[lane] = (lane == 11 || lane == 12) ? -1 : 0;
+    if (P.precise_positions) {
+      uint32_t* al = S.sub_alive + (size_t)b * P.ncap * P.ncap * (SUB_MAX_ROWS_PER_PAIR / 32);
+      for (int i = lane; i < P.ncap * P.ncap * (SUB_MAX_ROWS_PER_PAIR / 32); i += 32) al[i] = 0u;
+    }
+  }
   if (lane == 0) {
     scalar(S, P, S_SCENARIO, b) = sc;
     scalar(S, P, S_NODE_OFF, b) = T.sc_node_off[sc];
@@ -671,13 +699,14 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
     if (do_reset) {
       const int2 ss = reset_env(T, P, S, b, lane);
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[3])); }
-      if (!reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
+      // (the sub-sampled table is rebuilt through the generic path: its balance step is per env, not per (scenario, starter))
+      if (P.subset_k || !reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
         encode_env(T, P, S, SW, W, b, lane);
         if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
         else build_table<false>(T, P, S, W, b, lane, false);
-        reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
+        if (!P.subset_k) reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
       }
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[4])); }
       // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even

@@ -121,6 +121,9 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
         int k = 0;                                // owned_nodes.remove(node): first occurrence (cyberbattle_env.py:425)
         while (k < n_raw && raw[k] != n) ++k;
         if (k < n_raw) { for (; k + 1 < n_raw; ++k) raw[k] = raw[k + 1]; --n_raw; }
+        // a persistent node that came back in this very step is not in the list yet (the re-own loop runs after the removals,
+        // cyberbattle_env.py:425 vs :427-430): the reference raises ValueError here; counted, then treated as a no-op
+        else atomicAdd(P.errflag + 1, 1);
         event = true;
       }
     }
@@ -484,7 +487,8 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const int sticky = flags & FL_INTEREST_IN_GRAPH;          // survives until the episode's reset
   // (not with precise_action_space_positions: a re-encode of an unchanged graph still hands the current embeddings to
   // the pairs around THIS action's nodes, which an earlier refresh may have passed over)
-  const bool encode_now = reencode && (dirty || P.precise_positions);
+  // (nor with sample_subset_samples: every create_continuous_action_space advances the env's balance counter)
+  const bool encode_now = reencode && (dirty || P.precise_positions || P.subset_k);
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
   M.close();

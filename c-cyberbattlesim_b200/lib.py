@@ -5,6 +5,7 @@ from __future__ import annotations
 import ctypes as ct
 import os
 import subprocess
+from typing import Optional
 
 import numpy as np
 
@@ -13,7 +14,7 @@ from . import constants as C
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, os.environ.get("CBS_LIB", "libcbsim.so"))
 CSRC = os.path.join(_HERE, "csrc")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 i32, i64, u64, f32, f64 = ct.c_int32, ct.c_int64, ct.c_uint64, ct.c_float, ct.c_double
 P = ct.c_void_p
@@ -27,7 +28,8 @@ class CbsConfig(ct.Structure):
                 ("rewards", f64 * 10), ("penalties", f64 * 18), ("max_slots", i32), ("max_edges", i32),
                 ("decode_margin", f32), ("decode_gemm", i32),
                 ("static_defender", i32), ("scan_capacity", i32), ("scan_frequency", i32), ("precise_graph_encoding", i32),
-                ("detect_probability", f64), ("precise_action_space_positions", i32), ("distance_metric", i32)]
+                ("detect_probability", f64), ("precise_action_space_positions", i32), ("distance_metric", i32),
+                ("sample_subset_samples", i32)]
 
 
 _SCENARIO_PTRS = ["sc_num_nodes", "sc_node_off", "sc_port_off", "sc_uvuln_off", "sc_num_uvuln", "sc_instof_off",
@@ -67,7 +69,7 @@ SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cb
 
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
-    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL = range(17)
+    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE = range(18)
 NUM_SCALARS, NUM_ACCUM = 25, 20
 # per-env scalar record (csrc/cbs_types.h enum Scalar): four 32-byte sectors — rewritten every step | list lengths and
 # counters | episode constants | misc
@@ -208,7 +210,7 @@ def make_gae_struct(gt):
 
 
 def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0, seed: int = 0, auto_reset: bool = True,
-                switch_interval: int = 0, max_slots: int = 0, max_edges: int = 0, decode_margin: float = 0.0,
+                switch_interval: Optional[int] = None, max_slots: int = 0, max_edges: int = 0, decode_margin: float = 0.0,
                 decode_gemm: int = 0) -> CbsConfig:
     c = CbsConfig()
     c.abi_version, c.device, c.num_envs = ABI_VERSION, device, num_envs
@@ -219,7 +221,9 @@ def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0,
     c.winning_reward, c.losing_reward = float(cfg.winning_reward), float(cfg.losing_reward)
     c.absolute_reward, c.stop_at_goal_reached = int(cfg.absolute_reward), int(cfg.stop_at_goal_reached)
     c.remove_main_obstacles, c.remove_all_obstacles = int(cfg.remove_main_obstacles), int(cfg.remove_all_obstacles)
-    c.switch_interval, c.auto_reset = int(switch_interval), int(auto_reset)
+    if switch_interval is None:          # not given: the config's (None there = never switch)
+        switch_interval = getattr(cfg, "switch_interval", None)
+    c.switch_interval, c.auto_reset = (-1 if switch_interval is None else int(switch_interval)), int(auto_reset)
     for i, v in enumerate(cfg.reward_vector()):
         c.rewards[i] = v
     for i, v in enumerate(cfg.penalty_vector()):
@@ -231,4 +235,5 @@ def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0,
     c.precise_graph_encoding = int(bool(cfg.precise_graph_encoding))
     c.precise_action_space_positions = int(bool(getattr(cfg, "precise_action_space_positions", False)))
     c.distance_metric = C.METRICS[getattr(cfg, "distance_metric", "cosine")]
+    c.sample_subset_samples = int(getattr(cfg, "sample_subset_samples", 0) or 0)
     return c

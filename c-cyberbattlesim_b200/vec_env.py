@@ -85,17 +85,21 @@ class CyberBattleVecEnv(_SB3VecEnv):
         if len(finished):
             term = env.terminal_obs()
             stats = env.last_stats()
-        infos: List[dict] = []
-        dist = None
-        for b in range(self.num_envs):
-            if self.lazy_infos and not done[b]:
-                infos.append(self._empty)
-                continue
-            d = self._info_dict(b, info[b])
-            if dist is None:
-                dist = env.distances()                       # one read per step, and only when some info dict is built
-            d["min_distance_action"] = float(dist[b])        # compressed:449; callbacks_multi_env.py:89-90 reads it
-            infos.append(d)
+        # info dicts: every env, or (lazy_infos) only the envs that finished — the others share one empty dict, so the
+        # Python work per step is proportional to the number of episode ends, not to num_envs
+        if self.lazy_infos:
+            infos: List[dict] = [self._empty] * self.num_envs
+            built = finished.tolist()
+        else:
+            infos = [None] * self.num_envs
+            built = range(self.num_envs)
+        if len(built):
+            dist = env.distances().tolist()                  # one read per step, and only when some info dict is built
+            rows = info.tolist()
+            for b in built:
+                d = self._info_dict(b, rows[b])
+                d["min_distance_action"] = dist[b]           # compressed:449; callbacks_multi_env.py:89-90 reads it
+                infos[b] = d
         for b in finished:
             d = infos[b]
             d["terminal_observation"] = {"graph_embeddings": term[b, :-2].astype(np.float64),
@@ -103,7 +107,7 @@ class CyberBattleVecEnv(_SB3VecEnv):
             # the reference reports done|truncated as `terminated` (compressed:451 via switch.py:121,148), so SB3 never
             # bootstraps at a cut-off; kept identical here
             d["TimeLimit.truncated"] = False
-            d["truncated"] = bool(info[b, 7])
+            d["truncated"] = bool(info[b, 7] & 1)
             d["episode"] = {"r": float(self._ep_return[b]), "l": int(self._ep_len[b]), "t": round(time.time() - self._t0, 6)}
             d["episode_stats"] = tuple(stats[b].tolist()[:13]) + (bool(stats[b, 13]),)   # callbacks_multi_env.py:20-32
             d["env_id"] = int(b)
@@ -115,10 +119,10 @@ class CyberBattleVecEnv(_SB3VecEnv):
         self.step_async(actions)
         return self.step_wait()
 
-    def _info_dict(self, b: int, row: np.ndarray) -> dict:
+    def _info_dict(self, b: int, row) -> dict:
         t = self.env.tables
-        sc = int(self.env.scenario_of_env[b])
-        s, tg, u, kind, code, reason, step_count, _ = (int(x) for x in row)
+        s, tg, u, kind, code, reason, step_count, last = (int(x) for x in row)
+        sc = last >> 8      # the scenario in force during the step (the device switches scenarios on its own, switch.py:218-220)
         nodes, vulns = t.node_ids[sc], t.vuln_ids[sc]
         return {
             "description": "CyberBattleEnvCompressed step info",                               # compressed:436
@@ -187,7 +191,7 @@ class RandomSwitchEnvB200:
     truncated, info), get_statistics(), set_cut_off(), set_proportional_cutoff_coefficient()
     (_env/cyberbattle_env_switch.py:109-167,194-203).  auto_reset is off: the caller resets, as gymnasium expects."""
 
-    def __init__(self, specs, gae_weights, cfg=None, device: int = 0, switch_interval: int = 0, seed: int = 0,
+    def __init__(self, specs, gae_weights, cfg=None, device: int = 0, switch_interval: Optional[int] = None, seed: int = 0,
                  interest_nodes=None):
         self.env = BatchedCyberBattleEnv(specs, gae_weights, cfg, num_envs=1, device=device, auto_reset=False,
                                          switch_interval=switch_interval, seed=seed, interest_nodes=interest_nodes)
@@ -212,7 +216,7 @@ class RandomSwitchEnvB200:
         self.env.sync()
         row = info.cpu().numpy()[0]
         self.done = bool(done.item())
-        self.truncated = bool(row[7])
+        self.truncated = bool(row[7] & 1)
         o = _obs_dict(obs.cpu().numpy())
         d = CyberBattleVecEnv._info_dict(self, 0, row)
         d["min_distance_action"] = float(self.env.distances()[0])

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define CBS_ABI_VERSION 5
+#define CBS_ABI_VERSION 6
 
 /* dimensions fixed by the reference's defaults (agents/config/train_config.yaml:19,32;
  * gae/config/train_config.yaml:8,11; _env/cyberbattle_env_compressed.py:112-142) */
@@ -67,7 +67,8 @@ typedef struct {
   int32_t absolute_reward;      /* cyberbattle_env.py:379 */
   int32_t stop_at_goal_reached; /* cyberbattle_env.py:348 */
   int32_t remove_main_obstacles, remove_all_obstacles; /* compressed:536-543 */
-  int32_t switch_interval;      /* episodes between scenario switches (cyberbattle_env_switch.py:218-220); <=0 = never */
+  int32_t switch_interval;      /* RandomSwitchEnv.switch_interval (cyberbattle_env_switch.py:218-220): a reset draws a new scenario when
+                                   (episodes finished + 1) % (switch_interval + 1) == 0, so 0 = at every reset; < 0 = never */
   int32_t auto_reset;           /* 1: cbs_observe resets finished envs in place (DummyVecEnv semantics) */
   double rewards[CBS_NUM_REWARDS];
   double penalties[CBS_NUM_PENALTIES];
@@ -92,6 +93,12 @@ typedef struct {
    * 1 'l1', 2 'l2', 3 'inf' (np.linalg.norm(action - rows, ord, axis=1), :571-576).  Anything else is rejected like the
    * reference's ValueError (:578-579).  1..3 decode in float64 (k_decode_metric.cu) and run the transition as its own launch. */
   int32_t distance_metric;
+  /* compressed:83,521-522,553-567 `sample_subset_samples` (100 in agents/config/train_config.yaml:29): after every table-maintaining
+   * encode at most this many action-table rows per outcome class stay in the table; 0 = the whole table.  The reference draws
+   * the subset with np.random.choice; here row i of an over-full class gets the key philox(seed, global env index, c, identity_i).x
+   * with c = the env's lifetime count of balance calls and identity = 0x80000000 | source << 23 | target << 16 | kind << 12 |
+   * scenario-local vulnerability index, and the k smallest (key, table position) stay (ccbs_b200.philox.subset_keep). */
+  int32_t sample_subset_samples;
 } cbs_config;
 
 /* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the
@@ -256,8 +263,11 @@ typedef enum {
   CBS_F_OWNED_RAW = 13,   /* uint8 [B][2*max_nodes] env.owned_nodes as the reference holds it under a defender (removals, duplicates) */
   CBS_F_REIMAGE_LEFT = 14,/* uint8 [B][max_nodes] node_reimaging_progress of nodes whose Imaging bit is set */
   CBS_F_Z_HIST = 15,      /* float32 [B][slots][max_nodes][64] node-embedding snapshots the action-table rows refer to (cbs_capacities: slots) */
-  CBS_F_SEL = 16          /* int32 [B][4] last decoded / applied action (source, target, vulnerability, outcome kind); a caller that
+  CBS_F_SEL = 16,         /* int32 [B][4] last decoded / applied action (source, target, vulnerability, outcome kind); a caller that
                              hands this very buffer to cbs_transition saves the copy */
+  CBS_F_DIVERGENCE = 17   /* int32 [1] number of env-steps at which the reference itself raises and this library goes on: the re-imaging
+                             defender detecting a persistent node in the very step it comes back (owned_nodes.remove of an absent
+                             node, cyberbattle_env.py:425 -> ValueError); the removal is a no-op here */
 } cbs_field;
 #define CBS_NUM_MASKS 15
 #define CBS_NUM_SCALARS 25

@@ -80,9 +80,11 @@ class TieFollower:
             self.env.reset(starter=int(self.starters[self.ep]))
 
 
-def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_rows=None, defender_draws=None):
+def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_rows=None, defender_draws=None, lockstep_batch=True):
     """Step every env of `env` with the same action/uniform sequence; returns a trace record for env
-    `check_env` plus the per-step cross-env consistency flag."""
+    `check_env` plus the per-step cross-env consistency flag.  `lockstep_batch=False`: the other envs are expected to go their
+    own way (sub-sampled action tables are keyed by the env index) — they still get the same inputs, but a near-tie correction is
+    applied to `check_env` alone and the consistency flag is not evaluated."""
     B, T = env.num_envs, len(actions)
     defender = defender_draws is not None
     OW = 2 * n_nodes if defender else n_nodes   # under a defender the record holds env.owned_nodes itself (duplicates possible)
@@ -116,9 +118,13 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
         if follower is not None:
             env.sync()
             fix = follower.resolve(actions[t], sel[check_env].cpu().numpy(), t)
-            if fix is not None:
+            if fix is not None and lockstep_batch:
                 sel = torch.from_numpy(fix[0]).to(env.device).unsqueeze(0).repeat(B, 1).contiguous()
                 dist = torch.full((B,), fix[1], dtype=torch.float64, device=env.device)
+            elif fix is not None:
+                sel, dist = sel.clone(), dist.clone()
+                sel[check_env] = torch.from_numpy(fix[0]).to(env.device)
+                dist[check_env] = float(fix[1])
             follower.advance(actions[t], uniforms[t],
                              (defender_draws[0][t], defender_draws[1][t]) if defender else None)
         if defender:
@@ -130,7 +136,7 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
         m, sc = env.masks(), env.scalars()
         do, oo = env.disc_order(), (env.owned_raw() if defender else env.owned_order())
         r64 = env.reward64()
-        consistent &= bool((sel_h == sel_h[0]).all() and (m == m[:, :, :1]).all())
+        consistent &= (not lockstep_batch) or bool((sel_h == sel_h[0]).all() and (m == m[:, :, :1]).all())
         flags = int(sc[L.S_FLAGS, b])
         rec["sel"][t] = sel_h[b]
         rec["code"][t] = int(outcome[b])

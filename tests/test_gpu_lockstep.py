@@ -62,9 +62,18 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
     ("discovery", (8, 20), 330, 33, 60, dict(distance_metric="l2")),        # Ug > 256: several tiles of the vulnerability part
     ("control", (20, 40), 120, 24, 50, dict(distance_metric="inf")),
     ("control", (6, 14), 100, 24, 60, dict(_DEFENDER, distance_metric="l2")),
+    # sample_subset_samples (compressed:553-567): the reference's training default k = 100 on 32-node scenarios, a k small enough
+    # to thin every class at every build, and the option together with the defender / precise_action_space_positions
+    ("control", (28, 32), 120, 24, 70, dict(sample_subset_samples=100, proportional_cutoff_coefficient=2)),
+    ("control", (8, 20), 100, 32, 70, dict(sample_subset_samples=6, proportional_cutoff_coefficient=3)),
+    ("control", (6, 14), 100, 24, 80, dict(_DEFENDER, sample_subset_samples=10)),
+    ("control", (8, 16), 100, 24, 70, dict(sample_subset_samples=8, precise_action_space_positions=True, proportional_cutoff_coefficient=3)),
+    # BASELINE configs[3] (bench workload c4): mixed 10-100-node scenarios in one padded batch, pool of 600 vulnerabilities
+    ("control", (10, 100), 600, 18, 60, {}),
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
         "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both",
-        "metric-l1", "metric-l2", "metric-inf", "metric-l2-defender"])
+        "metric-l1", "metric-l2", "metric-inf", "metric-l2-defender", "subset-k100-32-nodes", "subset-k6", "subset-defender",
+        "subset-positions", "c4-mixed-10-100"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
     import ccbs_b200 as cb
@@ -77,9 +86,13 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
 
     rng = np.random.default_rng(5)
     pool = cb.synthetic_vuln_pool(99, pool_size)
-    S, seed, offset = (6 if sizes[1] < 100 else 2), 12345, 1000
+    S, seed, offset = (6 if (sizes[1] < 100 or sizes[0] < 50) else 2), 12345, 1000
     gkw = dict(vulns_per_service_range=(6, 14)) if pool_size > 256 else {}
-    specs = [cb.synthetic_spec(200 + k, int(rng.integers(sizes[0], sizes[1] + 1)), pool=pool, **gkw) for k in range(S)]
+    if sizes == (10, 100):      # the mixed batch: both ends of the range are present
+        ns = [10, 100] + [int(x) for x in rng.integers(sizes[0], sizes[1] + 1, size=S - 2)]
+    else:
+        ns = [int(rng.integers(sizes[0], sizes[1] + 1)) for _ in range(S)]
+    specs = [cb.synthetic_spec(200 + k, ns[k], pool=pool, **gkw) for k in range(S)]
     cfg = cb.EnvConfig(goal=goal, **extra)
     defender = cfg.static_defender_agent is not None
     w = GaeWeights.random(3)
@@ -100,8 +113,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     tables = env.tables
     g = cb.constants.GOALS[goal]
     G = env.obs_dim - 2
-    oracles = [OracleEnv(specs[sc_of_env[b]], w, cfg, interest_node=None if interest is None else interest[sc_of_env[b]])
-               for b in range(B)]
+    oracles = [OracleEnv(specs[sc_of_env[b]], w, cfg, interest_node=None if interest is None else interest[sc_of_env[b]],
+                         philox_seed=seed, env_index=offset + b) for b in range(B)]
     vidx = [tr.vuln_index(specs[sc_of_env[b]]) for b in range(B)]
     episodes = [0] * B
     total_steps = [0] * B
@@ -161,6 +174,11 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     assert flips <= max(1, B * T // (50 if cfg.distance_metric == "l1" else 200)), f"{flips} near-tie flips in {B * T} env-steps"
     assert np.array_equal(sc[L.S_EPISODES], np.array(episodes))
     assert sum(episodes) >= (B if sizes[1] < 100 else 1), "test too short to exercise auto-reset"
+    if cfg.sample_subset_samples:
+        dropped = sum(o.rows_dropped for o in oracles)
+        print("rows dropped by the sub-sampling:", dropped, "balance calls:", sum(o.balance_calls for o in oracles))
+        assert dropped > 0, "the sub-sampling never thinned a class: k too large for this case"
+    print(f"near-tie flips: {flips} in {B * T} env-steps")
     if pool_size > 256:
         assert tables.vemb32.shape[0] > 256
     acc = env.stat_accum()

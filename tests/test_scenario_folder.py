@@ -56,7 +56,7 @@ def test_unsupported_reference_options_are_not_silently_dropped():
     rewards = {"rewards_dict": {"control": cb.config.DEFAULT_REWARDS["control"]},
                "penalties_dict": {"control": cb.config.DEFAULT_PENALTIES["control"]}}
     with pytest.raises(ValueError):
-        cb.EnvConfig.from_reference_dicts({"static_defender_agent": "events"}, rewards)
+        cb.EnvConfig.from_reference_dicts({"static_defender_agent": "honeypot"}, rewards)
     # the re-imaging defender is implemented; its parameters come from the [min, max] ranges of train_config.yaml:39-44
     cfg = cb.EnvConfig.from_reference_dicts({"static_defender_agent": "reimage", "detect_probability_min": 0.05,
                                              "detect_probability_max": 0.15, "scan_capacity_min": 3, "scan_capacity_max": 3,
@@ -67,16 +67,22 @@ def test_unsupported_reference_options_are_not_silently_dropped():
     assert cb.EnvConfig.from_reference_dicts({"distance_metric": "l2"}, rewards).distance_metric == "l2"
     with pytest.raises(ValueError):                                    # compressed:578-579
         cb.EnvConfig.from_reference_dicts({"distance_metric": "chebyshev"}, rewards)
-    with pytest.warns(UserWarning):
-        cfg = cb.EnvConfig.from_reference_dicts({"sample_subset_samples": 100, "episode_iterations": 77}, rewards)
-    assert cfg.episode_iterations == 77
+    # sample_subset_samples (compressed:553-567, the reference's training default) is carried through, not dropped, and the
+    # caller's dict is left alone
+    tc = {"sample_subset_samples": 100, "episode_iterations": 77, "static_defender_agent": None}
+    before = dict(tc)
+    cfg = cb.EnvConfig.from_reference_dicts(tc, rewards)
+    assert cfg.episode_iterations == 77 and cfg.sample_subset_samples == 100 and tc == before
+    assert cb.EnvConfig.from_reference_dicts({"static_defender_agent": "events"}, rewards).static_defender_agent == "events"
+    assert cb.EnvConfig.from_reference_dicts({"switch_interval": 5}, rewards).switch_interval == 5
+    assert cb.EnvConfig().switch_interval is None
 
 
 @pytest.mark.reference
 @pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
 def test_every_reference_train_config_parses():
     """EnvConfig.from_reference_dicts over the reference's own YAML files (agents/*/config/train_config.yaml +
-    rewards_config.yaml) for all six goals: the defaults of every trainer are accepted (sample_subset_samples with its warning)."""
+    rewards_config.yaml) for all six goals: the defaults of every trainer are accepted, sample_subset_samples included."""
     import glob
     import warnings
     import yaml
@@ -91,6 +97,8 @@ def test_every_reference_train_config_parses():
             with warnings.catch_warnings():
                 warnings.simplefilter("ignore")
                 cfg = cb.EnvConfig.from_reference_dicts(tc, rc, goal=goal)
-            assert cfg.goal == goal and cfg.distance_metric == tc["distance_metric"] and cfg.sample_subset_samples == 0
+            assert cfg.goal == goal and cfg.distance_metric == tc["distance_metric"]
+            assert int(cfg.sample_subset_samples or 0) == int(tc.get("sample_subset_samples") or 0)
+            assert cfg.switch_interval == tc.get("switch_interval")
             assert cfg.episode_iterations == tc["episode_iterations"]
             assert len(cfg.reward_vector()) == 10 and len(cfg.penalty_vector()) == 18

@@ -28,9 +28,9 @@ class _FakeBatchedEnv:
         reward[...] = np.arange(self.num_envs) - 1.5
         done[...] = [(b + self.t) % 3 == 0 for b in range(self.num_envs)]
         for b in range(self.num_envs):
-            # source, target, local vulnerability, desired kind, obtained code, end reason, step count, truncated
+            # source, target, local vulnerability, desired kind, obtained code, end reason, step count, truncated | scenario << 8
             info[b] = [0, 1 % self.tables.specs[self.scenario_of_env[b]].num_nodes, 0, C.K_RECON, C.OC_REPEATED,
-                       3 if done[b] else 0, self.t, int(done[b])]
+                       3 if done[b] else 0, self.t, int(done[b]) | (int(self.scenario_of_env[b]) << 8)]
 
     def distances(self):
         return 0.25 + np.arange(self.num_envs, dtype=np.float64)
