@@ -14,12 +14,22 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("CBS_REFERENCE_ROOT", "/root/reference")
-_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SHIMS = os.path.join(_HERE, "shims")
+# the reference tree itself (build container), else the bytecode oracle/build_ref.py compiled from it (travels to the GPU box)
+COMPILED_ROOT = os.path.join(_HERE, "_ref")
+REFERENCE_ROOT = os.environ.get("CBS_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/cyberbattle") else COMPILED_ROOT)
 
 
 def reference_available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "cyberbattle"))
+
+
+def reference_kind() -> str:
+    """'source' (the read-only tree), 'compiled' (oracle/_ref bytecode of the same files) or 'absent'."""
+    if not reference_available():
+        return "absent"
+    return "compiled" if os.path.abspath(REFERENCE_ROOT) == os.path.abspath(COMPILED_ROOT) else "source"
 
 
 def import_reference():
@@ -315,6 +325,27 @@ class ReferenceRunner:
                 "OutcomeNonPresent": C.OC_OUTCOME_NOT_PRESENT, "NonListeningPort": C.OC_PORT_NOT_LISTENING,
                 "UnsuccessfulAction": C.OC_UNSUCCESSFUL, "NoNeededAction": C.OC_NO_NEEDED,
                 "RepeatedResult": C.OC_REPEATED, "RemoteOutcomeInLocalNode": C.OC_REMOTE_OUTCOME_LOCAL}[name]
+
+
+def make_unpatched_env(model, gae_weights, cfg, seed=0):
+    """The reference's own ``RandomSwitchEnv(envs_list=[CyberBattleCompressedEnv])`` exactly as agents/train_agent.py:67 builds
+    it — NO randomness is replaced (global ``random`` / ``numpy.random`` seeded like utils/math_utils.py:73-80 set_seeds): the
+    thing bench.py times as the CPU reference arm."""
+    import torch
+    ref = import_reference()
+    logger = logging.getLogger("cbs_ref")
+    logger.setLevel(logging.CRITICAL)
+    _py_random.seed(seed)
+    np.random.seed(seed)
+    layers = [dict(type="NNConv", NN_channels=16, out_channels=64, activation="ReLU"),
+              dict(type="GCNConv", out_channels=64, activation="ReLU")]
+    enc = ref["gae"].GAEEncoder(1576, layers, 768)
+    enc.load_state_dict(gae_weights.state_dict())
+    enc.eval()
+    env = ref["compressed"].CyberBattleCompressedEnv(initial_environment=model, logger=logger, verbose=0, **cfg.reference_kwargs())
+    env.set_graph_encoder(enc)
+    env.set_pca_components(768)
+    return ref["switch"].RandomSwitchEnv(envs_ids=[0], switch_interval=10 ** 9, envs_list=[env], verbose=0)
 
 
 def reference_switch_sequence(models, gae_weights, cfg, switch_interval, picks, n_episodes, seed=0):
