@@ -198,49 +198,105 @@ def ncu_traffic(kernel):
         return json.load(f).get(kernel)
 
 
-def transition_roofline(specs, weights, device_index, n_envs, n_steps=4, seed=11):
-    """Large-batch leg for the transition kernel (at 8192 envs a launch moves 1.8 MB and is latency bound; the
-    HBM roofline is only meaningful at >= 1e6 env-steps per launch).  The same scenario set with `n_envs` envs on one GPU,
-    driven through the split C-ABI calls decode -> transition -> observe from a fresh reset; only `cbs_transition` is
-    timed (CUDA events on the launching stream).  Snapshot capacity is cut to 4 slots so that the state fits HBM; envs
-    that would need more stop growing their tables (flagged, harmless for this measurement).  Returns a dict."""
+def transition_roofline(specs, weights, device_index, n_envs, n_steps=8, seed=11, blocked=None):
+    """Large-batch legs for the transition kernel (at 8192 envs a launch moves 1.8 MB and is latency bound; the
+    HBM roofline is only meaningful at >= 1e6 env-steps per launch).  The same scenario set with `n_envs` envs on one GPU.
+    (1) per-step launch: the split C-ABI calls decode -> transition -> observe from a fresh reset, only `cbs_transition` timed
+    (CUDA events on the launching stream).  (2) K-step persistent launch: the decoded actions, distances and uniforms of those
+    very steps are replayed from the same reset state by ONE `cbs_transition_ksteps` launch (records in registers across the
+    steps, written back once).  Snapshot capacity is cut to 4 slots so that the state fits HBM; envs that would need more stop
+    growing their tables (flagged, harmless for this measurement).  Returns a dict."""
     import torch
     import ccbs_b200 as cb
     from ccbs_b200 import constants as C
     from ccbs_b200.batched_env import BatchedCyberBattleEnv
     dev = torch.device("cuda", device_index)
+    sc_of_env = None
+    if blocked if blocked is not None else bool(int(os.environ.get("CBS_BLOCKED", "0"))):
+        sc_of_env = ((np.arange(n_envs, dtype=np.int64) * len(specs)) // n_envs).astype(np.int32)
     env = BatchedCyberBattleEnv(specs, weights, cb.EnvConfig(), num_envs=n_envs, device=device_index, seed=seed,
-                                auto_reset=True, max_slots=4, max_edges=8)
+                                auto_reset=True, max_slots=4, max_edges=8, scenario_of_env=sc_of_env)
+    # every episode of env b starts from the first feasible starter of its scenario: a reset reproduces the same state
+    g = C.GOALS["control"]
+    t = env.tables
+    first = np.asarray(t.feasible_starters[g])[np.asarray(t.sc_feasible_off[g])[:-1]]
+    env.set_starter_queue(first[env.scenario_of_env][:, None].astype(np.int32))
     gen = torch.Generator(device=dev)
     gen.manual_seed(99)
     actions = torch.empty(n_envs, C.ACTION_DIM, device=dev)
+    K = int(n_steps)
+    sel_all = torch.empty(K, n_envs, 4, dtype=torch.int32, device=dev)
+    dist_all = torch.empty(K, n_envs, dtype=torch.float64, device=dev)
+    uni_all = torch.rand(K, n_envs, device=dev, generator=gen)
+    rew_all = torch.empty(K, n_envs, dtype=torch.float32, device=dev)
     env.reset()
     torch.cuda.synchronize(dev)
     times, ok_frac = [], []
-    for k in range(n_steps + 1):            # step 0 is the warm-up launch
+    alive = torch.ones(n_envs, dtype=torch.bool, device=dev)     # envs whose first episode is still running
+    alive_frac = []
+    for k in range(K):            # step 0 is the warm-up launch
         actions.uniform_(-4.0, 4.0, generator=gen)
         sel, dist = env.decode(actions)
+        sel_all[k].copy_(sel)
+        dist_all[k].copy_(dist)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _, _, _, outcome = env.transition(sel, dist, None)
+        reward, done, _, outcome = env.transition(sel, dist, uni_all[k])
         e1.record()
+        rew_all[k].copy_(reward)
         env.observe()
         torch.cuda.synchronize(dev)
+        alive_frac.append(float(alive.float().mean().item()))
+        alive &= done == 0
         if k:
             times.append(e0.elapsed_time(e1))
             ok_frac.append(float((outcome < 16).float().mean().item()))
     state_gb = env.state_bytes / 1e9
-    env.close()
-    del actions
-    torch.cuda.empty_cache()
     ms = float(np.mean(times))
     peak, peak_src = measured_peaks()
     alg = 220.0 * n_envs                    # SURVEY 8(d): ~220 B of per-env state and I/O per transition
-    return {"kernel": "transition (split call cbs_transition, large batch)", "envs_per_launch": int(n_envs), "launches_timed": len(times),
-            "ms_per_launch": ms, "ms_all": times, "bytes_per_env_step": 220, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
-            "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
-            "traffic": ncu_traffic("transition_large"), "successful_outcomes": float(np.mean(ok_frac)),
-            "state_gb": state_gb, "env_steps_per_s": n_envs / (ms * 1e-3)}
+    out = {"kernel": "transition (split call cbs_transition, large batch)", "envs_per_launch": int(n_envs), "launches_timed": len(times),
+           "ms_per_launch": ms, "ms_all": times, "bytes_per_env_step": 220, "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+           "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "peak_source": peak_src,
+           "traffic": ncu_traffic("transition_large"), "successful_outcomes": float(np.mean(ok_frac)),
+           "state_gb": state_gb, "env_steps_per_s": n_envs / (ms * 1e-3)}
+    # ---- (2) the same K steps as one persistent launch ----
+    try:
+        kms = []
+        same = None
+        for rep in range(3):
+            env.reset()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rk, dk = env.transition_ksteps(sel_all, dist_all, uni_all)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if rep:
+                kms.append(e0.elapsed_time(e1))
+            else:   # while an env's first episode runs, the persistent launch must reproduce the per-step launches bit for bit
+                running = torch.ones(n_envs, dtype=torch.bool, device=dev)
+                same = True
+                for k in range(K):
+                    same = same and bool(torch.equal(rk[k][running], rew_all[k][running]))
+                    running &= dk[k] == 0
+        kms_mean = float(np.mean(kms))
+        # physical bytes the launch needs per env: records once (hot sector 32 in + 32 out, list lengths 16, masks 64 in + changed
+        # words out) + per step sel 16 + dist 8 + uniform 4 + reward 4 + done 1
+        phys = 150.0 + 33.0 * K
+        out["ksteps"] = {"kernel": "transition_ksteps (K steps per launch, records in registers)", "k_steps": K, "envs_per_launch": int(n_envs),
+                         "ms_per_launch": kms_mean, "ms_all": kms, "env_steps_per_s": n_envs * K / (kms_mean * 1e-3),
+                         "bytes_per_env_step": 220, "achieved": alg * K / (kms_mean * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg * K / (kms_mean * 1e-3) / 1e9 / peak,
+                         "physical_bytes_per_env_step_model": phys / K, "physical_gbs_model": phys * n_envs / (kms_mean * 1e-3) / 1e9,
+                         "matches_per_step_launches": same, "envs_running_at_step": alive_frac,
+                         "traffic": ncu_traffic("transition_ksteps")}
+    except Exception as exc:  # noqa: BLE001
+        out["ksteps"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    env.close()
+    del actions, sel_all, dist_all, uni_all, rew_all
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args, wl_key, rank, emit):

@@ -170,6 +170,22 @@ class BatchedCyberBattleEnv:
                                             self._p(self.done), self._p(self.truncated), self._p(self.outcome), self._stream()))
         return self.reward, self.done, self.truncated, self.outcome
 
+    def transition_ksteps(self, sel: torch.Tensor, dist: Optional[torch.Tensor] = None, uniforms: Optional[torch.Tensor] = None):
+        """``cbs_transition_ksteps``: K pre-decoded actions per env in one launch (sel int32[K, B, 4], dist float64[K, B],
+        uniforms float32[K, B] or None for Philox).  Returns (reward float32[K, B], done uint8[K, B]).  The visible graph / action
+        table are not advanced (no observe between the steps): reset() before stepping normally again."""
+        K = int(sel.shape[0])
+        assert sel.shape == (K, self.num_envs, 4) and sel.dtype == torch.int32 and sel.is_contiguous() and sel.device == self.device
+        if dist is not None:
+            assert dist.shape == (K, self.num_envs) and dist.dtype == torch.float64 and dist.is_contiguous()
+        if uniforms is not None:
+            assert uniforms.shape == (K, self.num_envs) and uniforms.dtype == torch.float32 and uniforms.is_contiguous()
+        reward = torch.empty(K, self.num_envs, dtype=torch.float32, device=self.device)
+        done = torch.empty(K, self.num_envs, dtype=torch.uint8, device=self.device)
+        self._check(self.lib.cbs_transition_ksteps(self._h, self._p(sel), self._p(dist), self._p(uniforms), K, self._p(reward),
+                                                   self._p(done), self._stream()))
+        return reward, done
+
     def observe(self) -> torch.Tensor:
         self._check(self.lib.cbs_observe(self._h, None, self._stream()))
         return self.obs

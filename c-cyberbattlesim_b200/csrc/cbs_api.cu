@@ -17,7 +17,9 @@ cudaError_t launch_decode_select(const Tables&, const Params&, const State&, con
 cudaError_t launch_decode_metric(const Tables&, const Params&, const State&, const float*, double*, int, int, int32_t*, double*, cudaStream_t);
 cudaError_t launch_observe(const Tables&, const Params&, const State&, const uint8_t*, int, int, cudaStream_t);
 cudaError_t launch_transition(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, int, float*,
-                              uint8_t*, uint8_t*, uint8_t*, cudaStream_t);
+                              uint8_t*, uint8_t*, uint8_t*, int, cudaStream_t);
+cudaError_t launch_transition_ksteps(const Tables&, const Params&, const State&, const int32_t*, const double*, const float*, int, float*,
+                                     uint8_t*, cudaStream_t);
 
 __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -279,6 +281,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
     std::vector<uint32_t> vp((size_t)(I > 0 ? I : 1) * 8, 0u);
     const std::vector<int32_t> inst_port_off = instance_port_offsets(t);
     std::vector<uint8_t> rp;
+    std::vector<uint32_t> rmask((size_t)(I > 0 ? I : 1) * 2, 0u);
     for (int i = 0; i < I; ++i) {
       uint32_t* r = &vp[(size_t)i * 8];
       const int oa = t->vi_recon_any[2 * i], la = t->vi_recon_any[2 * i + 1];
@@ -290,6 +293,10 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
       // the port's outgoing-firewall node mask itself when a plane is one word, else the port index into `outblock`
       r[2] = t->words == 1 ? t->outblock[(size_t)(inst_port_off[i] + t->vi_port[i])] : (uint32_t)t->vi_port[i];
       r[3] = (uint32_t)rp.size();           // both lists start on an 8-byte boundary (the transition reads 8 ids per load)
+      if (t->words == 1) {
+        for (int k = 0; k < la; ++k) rmask[2 * (size_t)i] |= 1u << (t->recon_nodes[oa + k] & 31);
+        for (int k = 0; k < lr; ++k) rmask[2 * (size_t)i + 1] |= 1u << (t->recon_nodes[orr + k] & 31);
+      }
       rp.insert(rp.end(), t->recon_nodes + oa, t->recon_nodes + oa + la);
       rp.resize((rp.size() + 7) & ~size_t(7), 0);
       rp.insert(rp.end(), t->recon_nodes + orr, t->recon_nodes + orr + lr);
@@ -299,6 +306,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
     }
     if ((rc = upload(h, reinterpret_cast<const uint32_t**>(&T.vi_pack), vp.data(), vp.size()))) return rc;
     if ((rc = upload(h, &T.recon_pack, rp.data(), rp.size()))) return rc;
+    if ((rc = upload(h, reinterpret_cast<const uint32_t**>(&T.recon_mask), rmask.data(), rmask.size()))) return rc;
   }
   UP(vemb32, (size_t)t->num_global_vulns * VULN_EMB); UP(vemb64, (size_t)t->num_global_vulns * VULN_EMB);
   UP(vnorm2, t->num_global_vulns);
@@ -465,8 +473,20 @@ int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev
   if (rc) return rc;
   if (!sel_dev) return fail(h, CBS_ERR_INVALID_ARG, "cbs_transition: sel is null");
   CK(h, launch_transition(h->T, h->P, h->S, sel_dev, dist_dev, uniforms_dev, h->sched_buf ^ 1, reward_dev, done_dev, truncated_dev,
-                          outcome_dev, (cudaStream_t)stream));
+                          outcome_dev, h->num_sms, (cudaStream_t)stream));
   h->sched_buf ^= 1;
+  h->launches += 1;
+  return CBS_OK;
+}
+
+int cbs_transition_ksteps(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev, const float* uniforms_dev, int32_t k_steps,
+                          float* reward_dev, uint8_t* done_dev, uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!sel_dev || k_steps < 1) return fail(h, CBS_ERR_INVALID_ARG, "cbs_transition_ksteps: sel is null or k_steps < 1");
+  if (h->P.defender || h->P.words != 1)
+    return fail(h, CBS_ERR_INVALID_ARG, "cbs_transition_ksteps keeps an env's record in registers: scenarios of <= 32 nodes, no static defender");
+  CK(h, launch_transition_ksteps(h->T, h->P, h->S, sel_dev, dist_dev, uniforms_dev, k_steps, reward_dev, done_dev, (cudaStream_t)stream));
   h->launches += 1;
   return CBS_OK;
 }
@@ -500,7 +520,7 @@ int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev,
   if (h->P.metric != METRIC_COSINE) {
     // l1 / l2 / inf decode (k_decode_metric.cu), then the transition as its own launch on the handle's own sel / dist
     CK(h, launch_decode_metric(h->T, h->P, h->S, actions_dev, h->vt64, h->Ug, h->sched_buf, nullptr, nullptr, st));
-    CK(h, launch_transition(h->T, h->P, h->S, h->S.sel, h->S.dist, uniforms_dev, h->sched_buf ^ 1, reward_dev, done_dev, nullptr, nullptr, st));
+    CK(h, launch_transition(h->T, h->P, h->S, h->S.sel, h->S.dist, uniforms_dev, h->sched_buf ^ 1, reward_dev, done_dev, nullptr, nullptr, h->num_sms, st));
     h->sched_buf ^= 1;
     h->launches += 3;
   } else {

@@ -113,6 +113,7 @@ struct Tables {  // immutable, device pointers
                                //           port (words > 1) or the port's outgoing-firewall node mask itself (words == 1), recon offset }
                                //         { success rate (float64), cost (float64) }
   const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list, then the "REMOTE only" one, each padded to 8 bytes
+  const uint2* recon_mask;     // [I] node sets of those two lists as bitmasks (scenarios of <= 32 nodes; zeros otherwise)
   // GAE
   const float *node_static, *dyn_proj, *vuln_h, *nn0_b, *bn1_scale, *bn1_shift, *gcn_wt, *bn2_scale, *bn2_shift;
 };

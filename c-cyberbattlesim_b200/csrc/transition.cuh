@@ -24,6 +24,9 @@ struct EnvBits {
   __device__ bool get(int plane, int node) const { return (word(plane, node >> 5) >> (node & 31)) & 1u; }
   __device__ void set(int plane, int node) { masks[plane * words + (node >> 5)] |= (1u << (node & 31)); }
   __device__ void clr(int plane, int node) { masks[plane * words + (node >> 5)] &= ~(1u << (node & 31)); }
+  __device__ void set_if(int plane, int node, bool c) { if (c) set(plane, node); }
+  __device__ void clr_if(int plane, int node, bool c) { if (c) clr(plane, node); }
+  __device__ void or_word(int plane, uint32_t bits) { masks[plane * words] |= bits; }
 };
 
 // Scenarios of <= 32 nodes (one word per plane): the whole 64-byte record is fetched with four 128-bit loads when the
@@ -53,6 +56,19 @@ struct EnvBitsReg {
   __device__ __forceinline__ void clr(int plane, int node) {
     const uint32_t v = m[plane] & ~(1u << (node & 31));
     if (v != m[plane]) { m[plane] = v; dirty |= 1u << plane; }
+  }
+  // predicated forms: straight-line selects, no branch (the caller's condition implies that the bit really changes)
+  __device__ __forceinline__ void set_if(int plane, int node, bool c) {
+    m[plane] |= c ? (1u << (node & 31)) : 0u;
+    dirty |= c ? (1u << plane) : 0u;
+  }
+  __device__ __forceinline__ void clr_if(int plane, int node, bool c) {
+    m[plane] &= c ? ~(1u << (node & 31)) : 0xFFFFFFFFu;
+    dirty |= c ? (1u << plane) : 0u;
+  }
+  __device__ __forceinline__ void or_word(int plane, uint32_t bits) {
+    m[plane] |= bits;
+    dirty |= bits ? (1u << plane) : 0u;
   }
 };
 static_assert(N_MASKS <= 16, "EnvBitsReg holds one 64-byte record");
@@ -188,7 +204,10 @@ struct TransitionIn {
 // changes.  Table look-ups go level by level (scenario record -> instance index / node values -> instance record ->
 // firewall word), every level's loads issued together and ahead of the validity chain that consumes them.
 // Returns the env's observe work class (0 .. OBS_CLASSES-1, heaviest first) or -1.
-template <bool DEF, bool ENQ = true, bool REG = false>
+// PERSIST: the caller keeps the env's records in registers across several steps (transition_ksteps_kernel): nothing of the
+//      record is written here — mask words, list lengths and the hot sector all go back once, after the last step — and the
+//      observe / decode work lists are not fed (no observe runs between those steps).
+template <bool DEF, bool ENQ = true, bool REG = false, bool PERSIST = false>
 static __device__ __forceinline__ int transition_env(const Tables& T, const Params& P, const State& S, int b, TransitionIn<REG>& in,
                                             const int4* __restrict__ sc_pack, bool have_uniform, bool write_sel, int sched_out,
                                             float* __restrict__ reward_out,
@@ -247,6 +266,8 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const int insti = inst >= 0 ? inst : 0;
   const uint4 vp0 = T.vi_pack[2 * insti], vp1 = T.vi_pack[2 * insti + 1];
   const uint32_t vf = vp0.x;
+  uint2 recon_m = make_uint2(0u, 0u);      // node sets of the instance's two Reconnaissance lists (one-word planes only)
+  if constexpr (REG) recon_m = T.recon_mask[insti];
   const double v_success = __hiloint2double((int)vp1.y, (int)vp1.x), v_cost = __hiloint2double((int)vp1.w, (int)vp1.z);
   // ---- outgoing-firewall word of (port, source): with one-word planes the instance record carries it ----
   const uint32_t fw_out = P.words == 1 ? vp0.z : T.outblock[(size_t)(port_off + (int)vp0.z) * P.words + (ss >> 5)];
@@ -254,77 +275,97 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   double reward = 0.0;
   int code = -1;
 
-  // ---- validity chain (attacker_actions.py:109-197 remote, :363-416 local) ----
-  if (!idx_ok || !M.get(M_OWNED, s)) {
-    reward = P.pen[P_INVALID_ACTION]; code = OC_INVALID_SRC_NOT_OWNED;
-  } else if (!local && !M.get(M_DISCOVERED, t)) {
-    reward = P.pen[P_INVALID_ACTION]; code = OC_INVALID_TGT_NOT_DISCOVERED;
-  } else if (M.get(M_STOPPED, s) || (DEF && M.get(M_IMAGING, s))) {
-    reward = P.pen[P_INVALID_ACTION]; code = OC_SRC_NOT_RUNNING;
-  } else if (!local && (M.get(M_STOPPED, t) || (DEF && M.get(M_IMAGING, t)))) {
-    reward = P.pen[P_INVALID_ACTION]; code = OC_TGT_NOT_RUNNING;
-  } else if (inst < 0) {
-    reward = P.pen[P_NO_VULN]; code = OC_NO_VULNERABILITY;
-  } else {
+  // The validity chain and the per-outcome mutations below are written as straight-line selects wherever an arm is a bit test
+  // plus a bit set: measured on the large-batch launch (ncu source view, round 2) the branchy version spent 50 % of the
+  // kernel's warp instructions in these two sections at ~3 active lanes per warp (every lane of a warp wants another arm).
+  // Only the arms with real work of their own (Reconnaissance list walk, privilege escalation, lateral move) stay branches.
+  const bool own_s = M.get(M_OWNED, ss), disc_t = M.get(M_DISCOVERED, tt);
+  const bool down_s = M.get(M_STOPPED, ss) || (DEF && M.get(M_IMAGING, ss));
+  const bool down_t = M.get(M_STOPPED, tt) || (DEF && M.get(M_IMAGING, tt));
+  const bool eva_s = M.get(M_EVASION, ss), eva_t = M.get(M_EVASION, tt);
+  const bool root_t = M.get(M_PRIV_ROOT, tt), user_t = M.get(M_PRIV_USER, tt);
+  const int level_t = root_t ? 3 : (user_t ? 1 : 0);
+  {
+    // ---- validity chain (attacker_actions.py:109-197 remote, :363-416 local): the FIRST failing test decides, so the tests
+    //      are applied last to first and an earlier one overwrites a later one ----
     const int privreq = (vf >> VI_PRIVREQ_SHIFT) & 3;
-    const int level = M.get(M_PRIV_ROOT, t) ? 3 : (M.get(M_PRIV_USER, t) ? 1 : 0);
     const uint32_t kinds = local ? (vp0.y & 0xFFFFu) : (vp0.y >> 16);
-    if (privreq && level < privreq) {
-      reward = P.pen[P_NO_PRIV]; code = OC_NO_PRIVILEGE;
-    } else if (kind < 0 || kind >= N_KINDS || !((kinds >> kind) & 1u)) {
-      reward = P.pen[P_INVALID_ACTION]; code = OC_OUTCOME_NOT_PRESENT;
-    } else if (!local && !(vf & VI_LISTENING)) {
-      reward = P.pen[P_UNOPEN_PORT]; code = OC_PORT_NOT_LISTENING;
-    } else if (!local && !M.get(M_EVASION, s) && ((fw_out >> (s & 31)) & 1u)) {
-      reward = P.pen[P_FW_LOCAL]; code = OC_FW_OUTGOING;
-    } else if (!local && !M.get(M_EVASION, t) && !(vf & VI_IN_ALLOWED)) {
-      reward = P.pen[P_FW_REMOTE]; code = OC_FW_INCOMING;
-    } else if ((double)uf >= v_success) {                  // :190 / :409
-      reward = P.pen[P_SUCCESS_FAILED]; code = OC_UNSUCCESSFUL;
-    }
+    int pidx = 0;
+    if ((double)uf >= v_success) { code = OC_UNSUCCESSFUL; pidx = P_SUCCESS_FAILED; }                                    // :190 / :409
+    if (!local && !eva_t && !(vf & VI_IN_ALLOWED)) { code = OC_FW_INCOMING; pidx = P_FW_REMOTE; }
+    if (!local && !eva_s && ((fw_out >> (ss & 31)) & 1u)) { code = OC_FW_OUTGOING; pidx = P_FW_LOCAL; }
+    if (!local && !(vf & VI_LISTENING)) { code = OC_PORT_NOT_LISTENING; pidx = P_UNOPEN_PORT; }
+    if (kind < 0 || kind >= N_KINDS || !((kinds >> (kind & 15)) & 1u)) { code = OC_OUTCOME_NOT_PRESENT; pidx = P_INVALID_ACTION; }
+    if (privreq && level_t < privreq) { code = OC_NO_PRIVILEGE; pidx = P_NO_PRIV; }
+    if (inst < 0) { code = OC_NO_VULNERABILITY; pidx = P_NO_VULN; }
+    if (!local && down_t) { code = OC_TGT_NOT_RUNNING; pidx = P_INVALID_ACTION; }
+    if (down_s) { code = OC_SRC_NOT_RUNNING; pidx = P_INVALID_ACTION; }
+    if (!local && !disc_t) { code = OC_INVALID_TGT_NOT_DISCOVERED; pidx = P_INVALID_ACTION; }
+    if (!idx_ok || !own_s) { code = OC_INVALID_SRC_NOT_OWNED; pidx = P_INVALID_ACTION; }
+    if (code >= 0) reward = P.pen[pidx];
   }
 
   // ---- per-outcome mutation + reward (attacker_actions.py:199-351 / :418-547) ----
   if (code < 0) {
     double total = 0.0;
     bool ok = true;
-    switch (kind) {
-      case K_COLLECTION:
-        if (M.get(M_HAS_DATA, t)) { M.clr(M_HAS_DATA, t); M.set(M_COLLECTED, t); total += P.rew[R_COLLECTED]; }
-        else { reward = P.pen[P_NO_DATA_COLLECT]; code = OC_NO_NEEDED; ok = false; }
-        break;
-      case K_PERSISTENCE:
-        if (M.get(M_PERSISTENCE, t)) { reward = P.pen[P_ALREADY_PERSISTENT]; code = OC_REPEATED; ok = false; }
-        else { M.set(M_PERSISTENCE, t); total += P.rew[R_PERSISTENCE]; }
-        break;
-      case K_DOS:  // a stopped target never gets here (:127), a local DoS has no such test (:450)
-        M.set(M_STOPPED, t); total += P.rew[R_DOS] * (double)t_value;
-        break;
-      case K_DISCOVERY:
-        if (M.get(M_VISIBLE, t)) { reward = P.pen[P_ALREADY_VISIBLE]; code = OC_REPEATED; ok = false; }
-        else { M.set(M_VISIBLE, t); total += P.rew[R_VISIBILITY]; }
-        break;
-      case K_EXFILTRATION:
-        if (M.get(M_COLLECTED, t) && !M.get(M_EXFILTRATED, t)) { M.set(M_EXFILTRATED, t); total += P.rew[R_EXFILTRATED]; }
-        else { reward = P.pen[P_NO_DATA_EXFIL]; code = OC_NO_NEEDED; ok = false; }
-        break;
-      case K_EVASION:
-        if (M.get(M_EVASION, t)) { reward = P.pen[P_ALREADY_EVASION]; code = OC_REPEATED; ok = false; }
-        else { M.set(M_EVASION, t); total += P.rew[R_EVASION]; }
-        break;
+    // the six outcomes that are "test a bit of the target, set a bit of the target" (t == tt here: the indices passed the chain)
+    const bool kC = kind == K_COLLECTION, kP = kind == K_PERSISTENCE, kD = kind == K_DOS, kV = kind == K_DISCOVERY,
+               kX = kind == K_EXFILTRATION, kE = kind == K_EVASION;
+    if (kC | kP | kD | kV | kX | kE) {
+      const bool okC = kC && M.get(M_HAS_DATA, t);
+      const bool okP = kP && !M.get(M_PERSISTENCE, t);
+      const bool okV = kV && !M.get(M_VISIBLE, t);
+      const bool okX = kX && M.get(M_COLLECTED, t) && !M.get(M_EXFILTRATED, t);
+      const bool okE = kE && !eva_t;
+      // a stopped target never gets here (:127), a local DoS has no such test (:450): DoS always succeeds
+      M.clr_if(M_HAS_DATA, t, okC); M.set_if(M_COLLECTED, t, okC);
+      M.set_if(M_PERSISTENCE, t, okP);
+      M.set_if(M_STOPPED, t, kD);
+      M.set_if(M_VISIBLE, t, okV);
+      M.set_if(M_EXFILTRATED, t, okX);
+      M.set_if(M_EVASION, t, okE);
+      ok = okC | okP | kD | okV | okX | okE;
+      if (ok) {
+        const int ridx = kC ? R_COLLECTED : (kP ? R_PERSISTENCE : (kD ? R_DOS : (kV ? R_VISIBILITY : (kX ? R_EXFILTRATED : R_EVASION))));
+        total += kD ? P.rew[R_DOS] * (double)t_value : P.rew[ridx];
+      } else {
+        const int pidx = kC ? P_NO_DATA_COLLECT : (kP ? P_ALREADY_PERSISTENT : (kV ? P_ALREADY_VISIBLE : (kX ? P_NO_DATA_EXFIL : P_ALREADY_EVASION)));
+        reward = P.pen[pidx];
+        code = (kC | kX) ? OC_NO_NEEDED : OC_REPEATED;
+      }
+    } else switch (kind) {
       case K_RECON: {
         // the instance's two Reconnaissance lists sit in recon_pack, each starting on an 8-byte boundary: "any type"
-        // first, then "REMOTE only".  Eight node ids per load; a node already discovered costs three instructions.
+        // first, then "REMOTE only".
         const int len_any = (vf >> 8) & 0xFF, len_remote = (vf >> 16) & 0xFF;
         const int off = (int)vp0.w + (local ? 0 : ((len_any + 7) & ~7)), len = local ? len_any : len_remote;
         int n_disc = DEF ? SC(S_N_DISC) : n_disc_w, fresh = 0;
         uint8_t* order = S.disc_order + (size_t)b * P.ncap;
-        for (int i0 = 0; i0 < len; i0 += 8) {               // :291-296 + cyberbattle_env.py:398-407
-          const uint2 ch = *reinterpret_cast<const uint2*>(T.recon_pack + off + i0);
+        if constexpr (REG) {
+          // one-word planes: the list's node set comes with the instance (recon_mask), so the nodes that are new are known
+          // before the list is touched — most Reconnaissance outcomes discover nothing new and skip the walk; the others walk
+          // it only until their last new node is appended (list order = the order of env.discovered_nodes, :291-296 +
+          // cyberbattle_env.py:398-407)
+          uint32_t todo = (local ? recon_m.x : recon_m.y) & ~M.word(M_DISCOVERED, 0);
+          fresh = __popc(todo);
+          M.or_word(M_DISCOVERED, todo);
+          for (int i0 = 0; todo != 0u && i0 < len; i0 += 8) {
+            const uint2 ch = *reinterpret_cast<const uint2*>(T.recon_pack + off + i0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int node = (int)(((j < 4 ? ch.x : ch.y) >> (8 * (j & 3))) & 0xFFu);
-            if (i0 + j < len && !M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
+            for (int j = 0; j < 8; ++j) {
+              const int node = (int)(((j < 4 ? ch.x : ch.y) >> (8 * (j & 3))) & 0xFFu);
+              if (i0 + j < len && ((todo >> (node & 31)) & 1u)) { todo &= ~(1u << (node & 31)); order[n_disc++] = (uint8_t)node; }
+            }
+          }
+        } else {
+          for (int i0 = 0; i0 < len; i0 += 8) {               // eight node ids per load; a node already discovered costs three instructions
+            const uint2 ch = *reinterpret_cast<const uint2*>(T.recon_pack + off + i0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int node = (int)(((j < 4 ? ch.x : ch.y) >> (8 * (j & 3))) & 0xFFu);
+              if (i0 + j < len && !M.get(M_DISCOVERED, node)) { M.set(M_DISCOVERED, node); order[n_disc++] = (uint8_t)node; ++fresh; }
+            }
           }
         }
         if (DEF) { SC(S_N_DISC) = n_disc; SC(S_DISC_AMOUNT) += fresh; }
@@ -334,7 +375,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
       }
       case K_PRIVESC: {
         const int lvl = (vf >> (local ? VI_LEVEL_ANY_SHIFT : VI_LEVEL_REMOTE_SHIFT)) & 3;
-        const int cur = M.get(M_PRIV_ROOT, t) ? 3 : (M.get(M_PRIV_USER, t) ? 1 : 0);
+        const int cur = level_t;
         if (!local && cur == 0) { reward = P.pen[P_PRIVESC_NOT_OWNED]; code = OC_NO_PRIVILEGE; ok = false; }
         else if (cur >= lvl) { reward = P.pen[P_PRIVESC_ALREADY]; code = OC_REPEATED; ok = false; }
         else {                                              // __mark_node_as_owned(t, level) :70-89
@@ -389,7 +430,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
       total -= P.rew[R_COST] * v_cost;             // :348 / :544
       reward = total;
       code = kind;
-      if (kind == K_COLLECTION || kind == K_EXFILTRATION || kind == K_DISCOVERY) {                      // env:411-412
+      if (kC | kX | kV) {                                                                              // env:411-412
         if (DEF) SC(S_DISC_AMOUNT) += 1; else disc_amount_w += 1;
       }
     }
@@ -491,19 +532,20 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const bool encode_now = reencode && (dirty || P.precise_positions || P.subset_k);
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
           (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
-  M.close();
-  if (!DEF) {   // changed list lengths go back word by word (fire and forget)
+  if (!PERSIST) M.close();
+  if (!DEF && !PERSIST) {   // changed list lengths go back word by word (fire and forget)
     if (n_disc_w != in.c0.x) SC(S_N_DISC) = n_disc_w;
     if (n_owned_w != in.c0.y) SC(S_N_OWNED) = n_owned_w;
     if (disc_amount_w != in.c0.z) SC(S_DISC_AMOUNT) = disc_amount_w;
   }
+  if (PERSIST) { in.c0.x = n_disc_w; in.c0.y = n_owned_w; in.c0.z = disc_amount_w; }
   {   // the new hot sector (num_iterations += 1 is :394); the caller stores it
     const double ep = __hiloint2double(h1.w, h1.z) + reward;
     in.h0 = make_int4(flags, stepcount, num_iter + 1, total_steps + 1);
     in.h1 = make_int4(code, h1.y, __double2loint(ep), __double2hiint(ep));
   }
   int cls = -1;
-  if (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP)) {   // the observe kernel only visits these envs
+  if (!PERSIST && (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP))) {   // the observe kernel only visits these envs
     // OBS_CLASSES cost classes, claimed heaviest first.  An item costs about (re-encode ? 6 + 1.1 n : 0) + (episode end:
     // statistics + reset + encode + table ? 18 : 0) + 2 us with n = discovered nodes; the kernel ends with its longest item.
     const int n = DEF ? SC(S_N_DISC) : n_disc_w;
@@ -514,7 +556,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
       if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);
     }
   }
-  S.reward64[b] = reward;
+  if (!PERSIST) S.reward64[b] = reward;
   if (reward_out) reward_out[b] = (float)reward;
   if (done_out) done_out[b] = (done || trunc) ? 1 : 0;
   if (trunc_out) trunc_out[b] = trunc ? 1 : 0;

@@ -213,6 +213,16 @@ int cbs_transition(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev
                    float* reward_dev, uint8_t* done_dev, uint8_t* truncated_dev, uint8_t* outcome_dev,
                    uintptr_t stream);
 
+/* K transitions per env in one launch ("K-step persistent kernel over fixed action traces"): sel_dev [k_steps][num_envs][4],
+ * dist_dev [k_steps][num_envs] or NULL, uniforms_dev [k_steps][num_envs] or NULL (Philox), reward_dev / done_dev [k_steps][num_envs]
+ * or NULL.  Step k of env b applies sel_dev[k][b] exactly like cbs_transition (same code), but the env's record stays in
+ * registers between the steps and is written back once.  No cbs_observe runs between those steps: the visible graph, the action
+ * table and the observation are NOT advanced and an env that finishes stays finished (reward 0, done 1) — this is
+ * CyberBattleEnv.step_attacker_env (cyberbattle_env.py:299-394) alone, for pre-decoded traces and for the transition roofline.
+ * Scenarios of <= 32 nodes, no static defender.  Follow it with cbs_reset before stepping the envs normally again. */
+int cbs_transition_ksteps(cbs_handle* h, const int32_t* sel_dev, const double* dist_dev, const float* uniforms_dev, int32_t k_steps,
+                          float* reward_dev, uint8_t* done_dev, uintptr_t stream);
+
 /* replaces update_evolving_visible_graph_after_step + encode + create_continuous_action_space
  * (compressed:399-428, 465-550) and, with auto_reset, the VecEnv reset of finished envs.
  * obs_dev: [num_envs][CBS_OBS_DIM] float32, or NULL: the observation cache itself is addressable through
