@@ -299,6 +299,48 @@ def transition_roofline(specs, weights, device_index, n_envs, n_steps=8, seed=11
     return out
 
 
+def configs4_leg(device_index, n_envs=4096, steps=40):
+    """BASELINE configs[4] (SB3 PPO with the GPU env in the loop).  stable_baselines3 is not in this image, so two things are timed:
+    (1) the SB3 boundary itself — ``CyberBattleVecEnv.step(numpy actions) -> (dict obs, rewards, dones, infos)``, the call
+    SB3's collect_rollouts makes (agents/train_agent.py:113) — with full and with lazy info dicts; (2) the in-repo PPO loop of
+    examples/train_ppo_b200.py (rollout + update on the same GPU): env-steps/s and wall-clock per update.  The reference's
+    figure for the same boundary is the CPU arm's env-steps/s (one DummyVecEnv env per process)."""
+    import importlib.util
+    import ccbs_b200 as cb
+    from ccbs_b200 import constants as C
+    from ccbs_b200.vec_env import CyberBattleVecEnv
+    wl = WORKLOADS["c1"]
+    specs = build_specs(wl)
+    weights = cb.GaeWeights.random(GAE_SEED)
+    out = {"envs": n_envs, "workload": wl["name"], "steps": steps}
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-4, 4, size=(n_envs, C.ACTION_DIM)).astype(np.float32)
+    for lazy in (False, True):
+        venv = CyberBattleVecEnv(cb.BatchedCyberBattleEnv(specs, weights, cb.EnvConfig(), num_envs=n_envs, device=device_index, seed=3),
+                                 lazy_infos=lazy)
+        venv.reset()
+        for _ in range(5):
+            venv.step(a)
+        t0 = time.perf_counter()
+        n_done = 0
+        for _ in range(steps):
+            _, _, dones, _ = venv.step(a)
+            n_done += int(dones.sum())
+        dt = time.perf_counter() - t0
+        out["vecenv_step_lazy_infos" if lazy else "vecenv_step_full_infos"] = {
+            "env_steps_per_s": n_envs * steps / dt, "ms_per_step": 1e3 * dt / steps, "episode_ends": n_done}
+        venv.close()
+    spec = importlib.util.spec_from_file_location("train_ppo_b200", os.path.join(ROOT, "examples", "train_ppo_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    log = mod.main(["--envs", str(n_envs), "--updates", "4", "--n-steps", "32"], quiet=True)
+    last = log[-1]
+    out["ppo_in_repo"] = {"rollout_env_steps_per_s": last["rollout_env_steps_per_s"], "train_env_steps_per_s": last["train_env_steps_per_s"],
+                          "seconds_per_update": last["seconds_per_update"], "env_steps_per_update": 32 * n_envs,
+                          "policy": "MLP [256,128,64] actor + critic, 4 epochs x 16384-sample minibatches, same GPU"}
+    return out
+
+
 def run_reference(args, wl_key, rank, emit):
     """--impl reference: the CPU restatement of the same path on all host cores (rank 0 only)."""
     if rank != 0:
@@ -341,6 +383,10 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time plain per-step launches instead of CUDA-graph replays")
+    ap.add_argument("--presteps", type=int, default=64, help="untimed steps before the warm-up: episodes reach their steady-state mix")
+    ap.add_argument("--subset", type=int, default=0, help="side measurement: sample_subset_samples=K (the reference's training default is 100)")
+    ap.add_argument("--no-vecenv", action="store_true", help="skip the configs[4] leg (CyberBattleVecEnv.step and the PPO loop)")
     ap.add_argument("--decode-gemm", type=int, default=0)
     ap.add_argument("--defender", action="store_true",
                     help="side measurement: the same workload with the re-imaging static defender of train_config.yaml:39-44 "
@@ -402,11 +448,20 @@ def main():
     B = wl["envs_per_gpu"]
     specs = build_specs(wl)
     weights = GaeWeights.random(GAE_SEED)
-    cfg = cb.EnvConfig(static_defender_agent="reimage") if args.defender else cb.EnvConfig()
+    cfg = cb.EnvConfig(static_defender_agent="reimage") if args.defender else cb.EnvConfig(sample_subset_samples=args.subset)
     env = BatchedCyberBattleEnv(specs, weights, cfg, num_envs=B, device=local_rank, seed=7, global_env_offset=rank * B,
                                 auto_reset=True, decode_gemm=args.decode_gemm)
-    # action ring: R batches of [B, 905] float32, together larger than the 126 MB L2
+    # action ring: R batches of [B, 905] float32, together larger than the 126 MB L2.  The timed steps are replayed from a CUDA
+    # graph of G consecutive steps when --steps has an even divisor G in [R, 32] (the driver's 20 steps: G = 10); the ring is
+    # then G batches long, so that one replay still walks more than L2's worth of actions
     R = max(2, int(np.ceil(160e6 / (B * C.ACTION_DIM * 4))))
+    G = 0
+    if not args.no_graph:
+        for cand in range(min(32, args.steps), R - 1, -1):
+            if cand % 2 == 0 and args.steps % cand == 0 and cand * B * C.ACTION_DIM * 4 <= 2.5e9:
+                G = cand
+                break
+    R = max(R, G)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     ring = (torch.rand(R, B, args.action_pitch, device=dev, generator=gen) * 8.0 - 4.0).contiguous()[:, :, :C.ACTION_DIM]
@@ -418,27 +473,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from here on: the pre-steps below are the same load as the (possibly very short) timed window
+    sampler = ClockSampler(local_rank, period=0.002)
+    sampler.start()
+    sampler.ready.wait(10)
+    sampler.armed = True
+    # bring the episodes to their steady-state mix before anything is timed (a window that starts right after a cold reset
+    # of all envs holds no episode end and no in-place reset), then the W warm-up steps of the contract
+    for i in range(args.presteps):
+        env.step(ring[i % R], None, want_info=False)
+    env.sync()
+    env.reset_stat_accum()
     for i in range(args.warmup):
         env.step(ring[i % R], None, want_info=False)
     env.sync()
+    graph = None
+    if G:
+        try:      # G steps of the same three launches each, captured once on a side stream, replayed steps / G times
+            gstream = torch.cuda.Stream(device=dev)
+            gstream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(gstream):
+                for i in range(2):                       # untimed: nothing lazy (function attributes, tensor maps) is left for the capture
+                    env.step(ring[i % R], None, want_info=False)
+            torch.cuda.current_stream().wait_stream(gstream)
+            torch.cuda.synchronize()
+            l_before = env.launch_count
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=gstream):
+                for i in range(G):
+                    env.step(ring[i % R], None, want_info=False)
+            launches_per_replay = env.launch_count - l_before
+            graph.replay()                               # one untimed replay
+            env.sync()
+        except Exception as exc:  # noqa: BLE001  (a failed capture must not cost the measurement: plain launches instead)
+            print(f"[bench] CUDA graph capture failed ({type(exc).__name__}: {exc}); timing plain launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
 
     # ---- timed region: device-resident inputs ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    sampler.ready.wait(10)
     barrier()
-    sampler.armed = True
     l0 = env.launch_count
+    launches_per_replay = 0 if graph is None else launches_per_replay
+    side = torch.cuda.Stream(device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
-        env.step(ring[(args.warmup + i) % R], None, want_info=False)
-    acc_all = env.stat_accum_tensor().clone()
-    if world > 1:   # the only collective: episode statistics, once per logging interval
-        dist.all_reduce(acc_all)
+    if graph is not None:
+        for _ in range(args.steps // G):
+            graph.replay()
+    else:
+        for i in range(args.steps):
+            env.step(ring[(args.warmup + i) % R], None, want_info=False)
     e1.record()
+    # the only collective: episode statistics, once per logging interval — issued on a side stream behind the window's last
+    # step, where a trainer overlaps it with the next interval's steps
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        acc_all = env.stat_accum_tensor().clone()
+        if world > 1:
+            dist.all_reduce(acc_all)
+    torch.cuda.current_stream().wait_stream(side)
     barrier()
-    launches = env.launch_count - l0
+    launches = (args.steps // G) * launches_per_replay if graph is not None else env.launch_count - l0
     ms = e0.elapsed_time(e1)
     sampler.stop_flag = True
     sampler.join()
@@ -533,21 +628,29 @@ def main():
             # action read + VT row read + per pair two half-precision snapshot rows + norms, per row 16 B of table,
             # plus the transition's 220 B of per-env state
             "decode_select_transition": B * (C.ACTION_DIM * 4 + 4 * Ug + pairs * (2 * 128 + 9) + rows * 16 + 28 + 220.0),
-            "observe": B * 0.45 * 10240.0,
         }
-        dom = max(kern, key=kern.get)
+        dom = max((k for k in kern if k in alg), key=kern.get)
+        # (observe has no algorithmic-bytes model worth the name — its items are latency chains over L2-resident tables — so
+        # its figure is the DRAM traffic ncu measured for one launch, profiles/traffic.json, over the live duration)
+        gbs = {k: alg[k] / (kern[k] * 1e-3) / 1e9 for k in kern if k in alg}
+        if ncu_traffic("observe"):
+            gbs["observe_dram_ncu"] = ncu_traffic("observe") / (kern["observe"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": alg[dom] / (kern[dom] * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "peak_source": peak_src, "traffic": ncu_traffic(dom),
-                "kernels_ms": kern, "kernels_gbs": {k: alg[k] / (kern[k] * 1e-3) / 1e9 for k in kern}}
+                "kernels_ms": kern, "kernels_gbs": gbs}
         roof["frac"] = roof["achieved"] / peak
         acc = dict(zip(_L.ACCUM_NAMES, acc_all.cpu().tolist()))   # summed over all ranks, timed-region episodes + warm-up
         out = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 bitmasks + f32 GAE + f64 decode re-score", "data": "synthetic",
-            "config": {"workload": wl["name"] + (" + static defender (reimage 0.05/3/3)" if args.defender else ""), "envs_per_gpu": B, "scenarios": wl["scenarios"], "global_vulns": int(Ug),
+            "config": {"workload": wl["name"] + (" + static defender (reimage 0.05/3/3)" if args.defender else "") +
+                       (f" + sample_subset_samples={args.subset}" if args.subset else ""), "envs_per_gpu": B, "scenarios": wl["scenarios"], "global_vulns": int(Ug),
                        "action_pitch_floats": args.action_pitch,
                        "actions": f"ring of {R} x [{B},905] f32 batches = {R * B * 905 * 4 / 1e6:.0f} MB (> 126 MB L2), no L2 flush",
+                       "launch": (f"CUDA graph of {G} steps replayed {args.steps // G}x" if graph is not None else "plain launches"),
+                       "presteps": args.presteps, "stats_allreduce": "side stream, behind the window's last step",
+                       "sample_subset_samples": args.subset,
                        "decode_gemm": "tcgen05-tf32" if env.tensor_core_decode else "simt-f32",
                        "state_gb": env.state_bytes / 1e9},
             "clocks": sampler.summary(), "gpu_launches": int(launches),
@@ -560,6 +663,11 @@ def main():
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
         }
         env.close()
+        if world == 1 and not args.no_vecenv:
+            try:
+                out["configs4"] = configs4_leg(local_rank)
+            except Exception as exc:  # noqa: BLE001
+                out["configs4"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if world == 1 and args.transition_envs > 0:
             try:    # a side measurement must never cost the headline line (e.g. 60 GB of state not available on this box)
                 out["transition_roofline"] = transition_roofline(specs, weights, local_rank, args.transition_envs)

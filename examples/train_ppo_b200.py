@@ -49,7 +49,7 @@ class ActorCritic(nn.Module):
         return self.v(self.vf(obs * self.obs_scale)).squeeze(-1)
 
 
-def main():
+def main(argv=None, quiet=False):
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--nodes", type=int, default=20)
@@ -60,7 +60,7 @@ def main():
     ap.add_argument("--minibatch", type=int, default=16384)
     ap.add_argument("--lr", type=float, default=3e-4)
     ap.add_argument("--seed", type=int, default=0)
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     torch.manual_seed(args.seed)
     dev = torch.device("cuda", 0)
     pool = cb.synthetic_vuln_pool(1234, 200)
@@ -128,7 +128,8 @@ def main():
                    seconds_per_update=t_all, ep_rew_mean=st["ep_rew_mean"], ep_len_mean=st["ep_len_mean"],
                    episodes=st["episodes"], owned_mean=st["stat0"] / max(st["episodes"], 1), win_rate=st["win_rate"])
         log.append(row)
-        print(json.dumps(row))
+        if not quiet:
+            print(json.dumps(row))
     env.sync()
     env.close()
     return log

@@ -17,12 +17,12 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SHIMS = os.path.join(_HERE, "shims")
 # the reference tree itself (build container), else the bytecode oracle/build_ref.py compiled from it (travels to the GPU box)
-COMPILED_ROOT = os.path.join(_HERE, "_ref")
+COMPILED_ROOT = os.path.join(_HERE, "_ref", "cyberbattle_ref.zip")
 REFERENCE_ROOT = os.environ.get("CBS_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/cyberbattle") else COMPILED_ROOT)
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "cyberbattle"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "cyberbattle")) or (REFERENCE_ROOT.endswith(".zip") and os.path.isfile(REFERENCE_ROOT))
 
 
 def reference_kind() -> str:

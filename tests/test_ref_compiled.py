@@ -19,7 +19,7 @@ assert rb.reference_kind() == "compiled", rb.reference_kind()
 g = cb.synthetic_input_graph(5, 8, pool=cb.synthetic_vuln_pool(1234, 60))
 env = rb.make_unpatched_env(rb.reference_model_from_input_graph(g, seed=5), GaeWeights.random(0), cb.EnvConfig(), seed=3)
 import cyberbattle._env.cyberbattle_env_switch as sw
-assert sw.__file__.endswith(".pyc") and "/oracle/_ref/" in sw.__file__, sw.__file__
+assert sw.__file__.endswith(".pyc") and "/oracle/_ref/cyberbattle_ref.zip/" in sw.__file__, sw.__file__
 obs, _ = env.reset()
 assert obs["graph_embeddings"].shape == (192,)
 n = 0
@@ -36,11 +36,11 @@ print("OK", n)
 @pytest.mark.skipif(not os.path.isdir("/root/reference/cyberbattle"), reason="reference tree not mounted")
 def test_compiled_reference_steps_without_the_source_tree():
     from oracle import build_ref
-    build_ref.build(verbose=False)
-    listed = {m[:-3] + ".pyc" for m in build_ref.MODULES}
-    found = {os.path.relpath(os.path.join(d, f), build_ref.OUT) for d, _, fs in os.walk(build_ref.OUT) for f in fs if f.endswith(".pyc")}
-    assert found == listed
-    assert not any(f.endswith(".py") for _, _, fs in os.walk(build_ref.OUT) for f in fs), "no reference source may be staged"
-    env = dict(os.environ, CBS_REFERENCE_ROOT=build_ref.OUT, PYTHONDONTWRITEBYTECODE="1")
+    import zipfile
+    archive = build_ref.build(verbose=False)
+    names = set(zipfile.ZipFile(archive).namelist())
+    assert names == {m[:-3] + ".pyc" for m in build_ref.MODULES} | {"cyberbattle/utils/__init__.pyc"}, \
+        "bytecode only: no reference source may be staged"
+    env = dict(os.environ, CBS_REFERENCE_ROOT=archive, PYTHONDONTWRITEBYTECODE="1")
     res = subprocess.run([sys.executable, "-c", _PROBE % ROOT], capture_output=True, text=True, env=env, timeout=600)
     assert res.returncode == 0 and "OK 30" in res.stdout, res.stderr[-2000:]
