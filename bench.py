@@ -383,6 +383,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ring", type=int, default=0, help="minimum number of action batches in the device-resident ring")
     ap.add_argument("--no-graph", action="store_true", help="time plain per-step launches instead of CUDA-graph replays")
     ap.add_argument("--presteps", type=int, default=64, help="untimed steps before the warm-up: episodes reach their steady-state mix")
     ap.add_argument("--subset", type=int, default=0, help="side measurement: sample_subset_samples=K (the reference's training default is 100)")
@@ -451,17 +452,18 @@ def main():
     cfg = cb.EnvConfig(static_defender_agent="reimage") if args.defender else cb.EnvConfig(sample_subset_samples=args.subset)
     env = BatchedCyberBattleEnv(specs, weights, cfg, num_envs=B, device=local_rank, seed=7, global_env_offset=rank * B,
                                 auto_reset=True, decode_gemm=args.decode_gemm)
-    # action ring: R batches of [B, 905] float32, together larger than the 126 MB L2.  The timed steps are replayed from a CUDA
-    # graph of G consecutive steps when --steps has an even divisor G in [R, 32] (the driver's 20 steps: G = 10); the ring is
-    # then G batches long, so that one replay still walks more than L2's worth of actions
-    R = max(2, int(np.ceil(160e6 / (B * C.ACTION_DIM * 4))))
+    # action ring: R batches of [B, 905] float32, together larger than the 126 MB L2 (step i reads batch i % R).  The timed steps
+    # are replayed from a CUDA graph of G consecutive steps when --steps has an even divisor G in [R, 32] (the driver's 20
+    # steps: one graph of 20), so that one replay walks the whole ring more than once.  (A longer ring only evicts more of the
+    # env state from L2 between steps — measured 63 / 56 / 51 M env-steps/s with 6 / 10 / 20 batches; a trainer's actions are
+    # the freshly written output of its policy network, not a ring, so the shortest ring that exceeds L2 is the one used.)
+    R = max(2, int(np.ceil(160e6 / (B * C.ACTION_DIM * 4))), args.ring)
     G = 0
     if not args.no_graph:
         for cand in range(min(32, args.steps), R - 1, -1):
-            if cand % 2 == 0 and args.steps % cand == 0 and cand * B * C.ACTION_DIM * 4 <= 2.5e9:
+            if cand % 2 == 0 and args.steps % cand == 0:
                 G = cand
                 break
-    R = max(R, G)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     ring = (torch.rand(R, B, args.action_pitch, device=dev, generator=gen) * 8.0 - 4.0).contiguous()[:, :, :C.ACTION_DIM]
