@@ -200,6 +200,60 @@ class BatchedCyberBattleEnv:
                                       self._p(self.done), self._p(self.info) if want_info else None, self._stream()))
         return self.obs, self.reward, self.done, self.info
 
+    def replay(self, actions: torch.Tensor, uniforms: Optional[torch.Tensor] = None, log_envs: Optional[slice] = None,
+               forced: Optional[dict] = None) -> dict:
+        """``cbs_replay``: T whole steps over pre-staged inputs (actions float32[T, B, 905], uniforms float32[T, B] or None for
+        Philox) without a host round trip per step; every step's decoded action, outcome, reward, distance, state records and
+        observation of the envs in ``log_envs`` (default: all) go to a device log, returned as a dict of numpy arrays
+        [T, n_logged, ...] after ONE synchronisation.  Keys: sel, code, done, truncated, reason, step_count, episode, reward,
+        dist, masks (uint32 [T, n, N_MASKS, words]), disc_order, owned_order, counters, n_disc, n_owned, obs, reset_obs,
+        reset_masks, stats.  ``forced`` = {step: (sel[4], distance)}: at those steps EVERY env takes that decoded action instead
+        of its own (parity tests following a verified near-tie)."""
+        T = int(actions.shape[0])
+        assert actions.shape == (T, self.num_envs, C.ACTION_DIM) and actions.dtype == torch.float32 and actions.is_contiguous()
+        assert actions.device == self.device
+        if self._act_stride != C.ACTION_DIM:
+            self._act_stride = C.ACTION_DIM
+            self._check(self.lib.cbs_set_action_stride(self._h, self._act_stride))
+        if uniforms is not None:
+            assert uniforms.shape == (T, self.num_envs) and uniforms.dtype == torch.float32 and uniforms.is_contiguous()
+        lo, hi, _ = (log_envs or slice(None)).indices(self.num_envs)
+        n = hi - lo
+        defender = bool(self.cfg.static_defender_agent)
+        olen = (2 if defender else 1) * self.ncap
+        z = lambda *shape, dtype: torch.zeros(T, n, *shape, dtype=dtype, device=self.device)   # noqa: E731
+        bufs = dict(sel=z(4, dtype=torch.int32), meta=z(4, dtype=torch.int32), reward=z(dtype=torch.float64), dist=z(dtype=torch.float64),
+                    masks=z(self._mask_pitch, dtype=torch.int32), disc_order=z(self.ncap, dtype=torch.uint8),
+                    owned_order=z(olen, dtype=torch.uint8), counters=z(8, dtype=torch.int32), obs=z(self.obs_dim, dtype=torch.float32),
+                    reset_obs=z(self.obs_dim, dtype=torch.float32), reset_masks=z(self._mask_pitch, dtype=torch.int32),
+                    stats=z(14, dtype=torch.float64))
+        log = L.CbsReplayLog()
+        log.first_env, log.num_logged = lo, n
+        for k, v in bufs.items():
+            setattr(log, k, v.data_ptr())
+        if forced:
+            f_sel = torch.full((T, self.num_envs, 4), -1, dtype=torch.int32)
+            f_dist = torch.zeros(T, self.num_envs, dtype=torch.float64)
+            steps = np.zeros(T, dtype=np.uint8)
+            for t, (sel4, d) in forced.items():
+                f_sel[t] = torch.as_tensor(np.asarray(sel4, np.int32))
+                f_dist[t] = float(d)
+                steps[t] = 1
+            f_sel, f_dist = f_sel.to(self.device), f_dist.to(self.device)
+            log.force_sel, log.force_dist, log.force_steps_host = f_sel.data_ptr(), f_dist.data_ptr(), steps.ctypes.data
+        self._check(self.lib.cbs_replay(self._h, self._p(actions), self._p(uniforms), T, ct.byref(log), self._stream()))
+        self.sync()
+        out = {k: v.cpu().numpy() for k, v in bufs.items()}
+        w = self.tables.words
+        meta, cnt = out.pop("meta"), out["counters"]
+        unpack = lambda m: np.ascontiguousarray(m.view(np.uint32)[..., :C.N_MASKS * w].reshape(T, n, C.N_MASKS, w))   # noqa: E731
+        out["masks"], out["reset_masks"] = unpack(out["masks"]), unpack(out["reset_masks"])
+        out["code"], flags, out["step_count"], out["episode"] = meta[..., 0], meta[..., 1], meta[..., 2], meta[..., 3]
+        out["done"], out["truncated"], out["reason"] = flags & 1, (flags >> 1) & 1, (flags >> 2) & 3
+        out["n_disc"], out["n_owned"] = cnt[..., 7] & 0xFFFF, cnt[..., 7] >> 16
+        out["counters"] = cnt[..., :7]
+        return out
+
     def profile_step(self, actions: torch.Tensor) -> dict:
         """One step with CUDA events between the launches; returns milliseconds per kernel group."""
         actions = self._actions(actions)

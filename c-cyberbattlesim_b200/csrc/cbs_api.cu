@@ -35,6 +35,59 @@ __global__ void info_kernel(Params P, State S, int32_t* __restrict__ info) {
   o[7] = ((flags & FL_TRUNC) ? 1 : 0) | ((sc[S_SCST] >> 8) << 8);   // bit 0 truncated, bits 8.. the scenario in force during the step
 }
 
+// cbs_replay: one warp per logged env copies the env's records into row (t, e) of the log.  phase 0 = after the transition,
+// phase 1 = after the observe.
+__global__ void replay_log_kernel(Params P, State S, cbs_replay_log L, int t, int phase, int owned_len) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= L.num_logged) return;
+  const int b = L.first_env + e;
+  const size_t row = (size_t)t * L.num_logged + e;
+  auto sc = [&](int plane) { return S.scal[((size_t)(plane >> 3) * P.B + b) * 8 + (plane & 7)]; };
+  if (phase == 0) {
+    const int flags = sc(S_FLAGS);
+    if (lane < 4) {
+      if (L.sel) L.sel[row * 4 + lane] = S.sel[(size_t)b * 4 + lane];
+      if (L.meta) L.meta[row * 4 + lane] = lane == 0 ? sc(S_OUTCOME) : (lane == 1 ? (flags & 15) : (lane == 2 ? sc(S_STEPCOUNT) : sc(S_EPISODES)));
+    }
+    if (lane == 0) {
+      if (L.reward) L.reward[row] = S.reward64[b];
+      if (L.dist) L.dist[row] = S.dist[b];
+    }
+    if (L.masks) for (int i = lane; i < P.mpitch; i += 32) L.masks[row * P.mpitch + i] = S.masks[(size_t)b * P.mpitch + i];
+    if (L.disc_order) for (int i = lane; i < P.ncap; i += 32) L.disc_order[row * P.ncap + i] = S.disc_order[(size_t)b * P.ncap + i];
+    if (L.owned_order)
+      for (int i = lane; i < owned_len; i += 32)
+        L.owned_order[row * owned_len + i] = P.defender ? S.owned_raw[(size_t)b * P.ocap + i] : S.owned_order[(size_t)b * P.ncap + i];
+    if (L.counters && lane < 8) {
+      const int planes[8] = {S_STEPCOUNT, S_NUM_ITER, S_DISC_AMOUNT, S_OWNABLE, S_DISCOVERABLE, S_DISRUPTABLE, S_DISCOVERABLE_AMOUNT, S_N_DISC};
+      int v = sc(planes[lane]);
+      if (lane == 7) v |= sc(P.defender ? S_N_OWNED_RAW : S_N_OWNED) << 16;
+      L.counters[row * 8 + lane] = v;
+    }
+  } else {
+    // the step's own done flag was logged in phase 0 (an in-place reset has cleared it by now)
+    const bool finished = L.meta ? (L.meta[row * 4 + 1] & 3) != 0 : false;
+    for (int i = lane; i < P.obs_dim; i += 32) {
+      const float cur = S.obs[(size_t)b * P.obs_dim + i];
+      if (L.obs) L.obs[row * P.obs_dim + i] = finished ? S.term_obs[(size_t)b * P.obs_dim + i] : cur;
+      if (L.reset_obs) L.reset_obs[row * P.obs_dim + i] = finished ? cur : 0.f;
+    }
+    if (finished) {
+      if (L.reset_masks) for (int i = lane; i < P.mpitch; i += 32) L.reset_masks[row * P.mpitch + i] = S.masks[(size_t)b * P.mpitch + i];
+      if (L.stats && lane < 14) L.stats[row * 14 + lane] = S.last_stats[(size_t)b * 14 + lane];
+    }
+  }
+}
+
+__global__ void replay_force_kernel(Params P, State S, const int32_t* __restrict__ force_sel, const double* __restrict__ force_dist) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const int4 f = reinterpret_cast<const int4*>(force_sel)[b];
+  if (f.x < 0) return;
+  reinterpret_cast<int4*>(S.sel)[b] = f;
+  S.dist[b] = force_dist[b];
+}
+
 __global__ void init_flags_kernel(int32_t* scal, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) scal[(size_t)b * 8 + S_FLAGS] = FL_NEEDS_RESET;   // sector 0
@@ -537,6 +590,61 @@ int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev,
     h->launches += 1;
   }
   return cbs_observe(h, obs_dev, stream);
+}
+
+int cbs_replay(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, int32_t num_steps, const cbs_replay_log* log,
+               uintptr_t stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!actions_dev || num_steps < 1) return fail(h, CBS_ERR_INVALID_ARG, "cbs_replay: actions is null or num_steps < 1");
+  if (log && (log->first_env < 0 || log->num_logged < 0 || log->first_env + log->num_logged > h->P.B))
+    return fail(h, CBS_ERR_INVALID_ARG, "cbs_replay: logged env range [%d, %d) outside the handle's %d envs", log->first_env,
+                log->first_env + log->num_logged, h->P.B);
+  if (log && log->num_logged > 0 && !log->meta && (log->obs || log->reset_obs || log->reset_masks || log->stats))
+    return fail(h, CBS_ERR_INVALID_ARG, "cbs_replay: the post-observe log fields need `meta` (it carries the step's done flag)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = h->P.B;
+  const int owned_len = h->P.defender ? h->P.ocap : h->P.ncap;
+  const bool logging = log && log->num_logged > 0;
+  const int lgrid = logging ? (log->num_logged + 3) / 4 : 0;
+  for (int t = 0; t < num_steps; ++t) {
+    const float* a = actions_dev + (size_t)t * B * h->P.act_stride;
+    const float* u = uniforms_dev ? uniforms_dev + (size_t)t * B : nullptr;
+    const bool forced = log && log->force_steps_host && log->force_sel && log->force_dist && log->force_steps_host[t];
+    if (h->P.metric != METRIC_COSINE || forced) {
+      if (h->P.metric != METRIC_COSINE) {
+        CK(h, launch_decode_metric(h->T, h->P, h->S, a, h->vt64, h->Ug, h->sched_buf, nullptr, nullptr, st));
+        h->launches += 2;
+      } else {
+        if ((rc = launch_gemm(h, a, st))) return rc;
+        CK(h, launch_decode_select(h->T, h->P, h->S, a, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+        h->launches += 1;
+      }
+      if (forced) {
+        replay_force_kernel<<<(h->P.B + 255) / 256, 256, 0, st>>>(h->P, h->S, log->force_sel + (size_t)t * B * 4, log->force_dist + (size_t)t * B);
+        h->launches += 1;
+      }
+      CK(h, launch_transition(h->T, h->P, h->S, h->S.sel, h->S.dist, u, h->sched_buf ^ 1, nullptr, nullptr, nullptr, nullptr, h->num_sms, st));
+      h->launches += 1;
+    } else {
+      if ((rc = launch_gemm(h, a, st))) return rc;
+      CK(h, launch_decode_select(h->T, h->P, h->S, a, h->vt_stride, h->sched_buf, 1, u, nullptr, nullptr, nullptr, nullptr, st));
+      h->launches += 1;
+    }
+    h->sched_buf ^= 1;
+    if (logging) {
+      replay_log_kernel<<<lgrid, 128, 0, st>>>(h->P, h->S, *log, t, 0, owned_len);
+      h->launches += 1;
+    }
+    CK(h, launch_observe(h->T, h->P, h->S, nullptr, 0, h->num_sms, st));
+    h->launches += 1;
+    if (logging) {
+      replay_log_kernel<<<lgrid, 128, 0, st>>>(h->P, h->S, *log, t, 1, owned_len);
+      h->launches += 1;
+    }
+    CK(h, cudaGetLastError());
+  }
+  return CBS_OK;
 }
 
 int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* out_ms, uintptr_t stream) {

@@ -54,6 +54,13 @@ class CbsStateView(ct.Structure):
                                   "reward64", "last_stats", "stat_accum")])
 
 
+class CbsReplayLog(ct.Structure):
+    """cbs_replay_log (include/cbsim.h)"""
+    _fields_ = ([("first_env", i32), ("num_logged", i32)] +
+                [(n, P) for n in ("sel", "meta", "reward", "dist", "masks", "disc_order", "owned_order", "counters", "obs", "reset_obs",
+                                  "reset_masks", "stats", "force_sel", "force_dist", "force_steps_host")])
+
+
 _GAE_PTRS = ["node_static", "dyn_proj", "vuln_h", "nn0_b", "bn1_scale", "bn1_shift", "gcn_wt", "bn2_scale", "bn2_shift"]
 
 
@@ -65,7 +72,7 @@ class CbsGaeTables(ct.Structure):
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
            "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_defender_draws", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition",
            "cbs_transition_ksteps", "cbs_observe",
-           "cbs_step", "cbs_profile_step", "cbs_step_host", "cbs_step_host_async", "cbs_host_sync", "cbs_read_state", "cbs_state_ptr", "cbs_get_state", "cbs_episode_stats", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_debug_observe_trace", "cbs_launch_count",
+           "cbs_step", "cbs_replay", "cbs_profile_step", "cbs_step_host", "cbs_step_host_async", "cbs_host_sync", "cbs_read_state", "cbs_state_ptr", "cbs_get_state", "cbs_episode_stats", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_debug_observe_trace", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
 
 # cbs_field
@@ -128,6 +135,7 @@ def load_library():
     lib.cbs_transition_ksteps.argtypes = [H, P, P, P, i32, P, P, P]
     lib.cbs_observe.argtypes = [H, P, P]
     lib.cbs_step.argtypes = [H, P, P, P, P, P, P, P]
+    lib.cbs_replay.argtypes = [H, P, P, i32, ct.POINTER(CbsReplayLog), P]
     lib.cbs_step_host.argtypes = [H, P, P, P, P, P, P]
     lib.cbs_step_host_async.argtypes = [H, P, P, P, P, P, P]
     lib.cbs_host_sync.argtypes = [H]

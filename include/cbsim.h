@@ -242,6 +242,35 @@ int cbs_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev,
  * stream.  Measurement aid for bench.py. */
 int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, float* out_ms, uintptr_t stream);
 
+/* ---- K-step replay (BASELINE configs[0]: one env, 10 000 steps, parity trace) -------------------------------------------------
+ * T whole steps (decode -> transition -> observe with in-place resets, exactly the launches of cbs_step) over pre-staged inputs,
+ * with every step's decoded action, outcome, reward, distance, state records and observation written to a device log — no host
+ * round trip between the steps, one synchronisation (the caller's) at the end.  actions_dev [T][num_envs][905] float32,
+ * uniforms_dev [T][num_envs] float32 or NULL (Philox).  Starters come from cbs_set_starter_queue (or Philox).  The log covers envs
+ * [first_env, first_env + num_logged); every pointer is device memory, [T][num_logged][...], and may be NULL to skip the field:
+ *   after the transition, before the observe (i.e. before an in-place reset):
+ *     sel int32[4] · meta int32[4] = { obtained outcome code, flags (bit0 done, bit1 truncated, bits2-3 end reason), step count,
+ *     episodes finished before this step } · reward, dist float64 · masks uint32[mask_pitch] · disc_order uint8[max_nodes] ·
+ *     owned_order uint8[owned_len] (owned_len = 2 * max_nodes under a static defender: env.owned_nodes itself, else max_nodes) ·
+ *     counters int32[8] = { stepcount, num_iterations, discovered_amount, ownable, discoverable, disruptable, discoverable_amount,
+ *     n_discovered | n_owned << 16 }
+ *   after the observe:
+ *     obs float32[obs_len] (the terminal observation when the episode ended in this step) · and, only meaningful when it did:
+ *     reset_obs float32[obs_len], reset_masks uint32[mask_pitch] (first observation / masks of the next episode), stats float64[14]
+ * Forced decodes (parity tests: follow the recorded pick on a verified near-tie of two table rows): at every step t with
+ * force_steps_host[t] != 0 (host array [num_steps]) the decode and the transition run as separate launches and, in between, every
+ * env b with force_sel[t][b][0] >= 0 (device, int32 [num_steps][num_envs][4]) takes that action and force_dist[t][b] (device,
+ * float64) instead of its own decode.  All three NULL = no forcing.
+ * replaces: the reference's own per-step loop `for t: env.step(action[t])` (agents/test_agent.py, utils/test_utils.py:78-140). */
+typedef struct {
+  int32_t first_env, num_logged;
+  int32_t* sel; int32_t* meta; double* reward; double* dist; uint32_t* masks; uint8_t* disc_order; uint8_t* owned_order;
+  int32_t* counters; float* obs; float* reset_obs; uint32_t* reset_masks; double* stats;
+  const int32_t* force_sel; const double* force_dist; const uint8_t* force_steps_host;
+} cbs_replay_log;
+int cbs_replay(cbs_handle* h, const float* actions_dev, const float* uniforms_dev, int32_t num_steps, const cbs_replay_log* log,
+               uintptr_t stream);
+
 /* Same through HOST buffers (pinned memory recommended): copies actions in, runs the step, copies
  * obs / reward / done (/ info) out, and synchronises.  This is the call the VecEnv adapter makes. */
 int cbs_step_host(cbs_handle* h, const float* actions_host, const float* uniforms_host, float* obs_host,

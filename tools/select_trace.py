@@ -25,3 +25,8 @@ for b in order: print("   ", cyc[b], rows[b], live[b], nex[b], combos[b])
 print("corr(cycles, rows) =", np.corrcoef(cyc, rows)[0,1], " corr(cycles, rescored) =", np.corrcoef(cyc, nex)[0,1], "corr(cycles, combos)=", np.corrcoef(cyc, combos)[0,1])
 # start-time distribution: when did the last warp START?
 print("last start at (us):", (t0.max() - t0.min()) / 1900, " mean start:", (t0.mean() - t0.min())/1900)
+# least-squares model of the per-env cost: cycles ~ a + b * rows + c * ceil(combos / 32) + d * rescored
+X = np.stack([np.ones(B), rows, np.ceil(combos / 32.0), nex], axis=1).astype(np.float64)
+coef, *_ = np.linalg.lstsq(X, cyc.astype(np.float64), rcond=None)
+print("fit: cycles = %.0f + %.2f * rows + %.0f * pair-blocks + %.0f * rescored" % tuple(coef))
+print("shares of the mean: const %.0f%% rows %.0f%% blocks %.0f%% rescore %.0f%%" % tuple(100 * coef * X.mean(0) / cyc.mean()))
