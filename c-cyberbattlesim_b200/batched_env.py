@@ -35,8 +35,9 @@ class BatchedCyberBattleEnv:
             raise NotImplementedError("sample_subset_samples together with the l1 / l2 / inf decode metrics is not implemented "
                                       "(the sub-sampled table is scanned by the cosine decode only)")
         if getattr(self.cfg, "static_defender_agent", None) == "events":
-            raise NotImplementedError("the 'events' static defender (ExternalRandomEvents, _env/static_defender.py:63-161) is restated by "
-                                      "the oracle only so far (DESIGN.md §5)")
+            from .scenario import check_events_compatible
+            for sp in (tables.specs if tables is not None else specs):
+                check_events_compatible(sp)
         if self.cfg.static_defender_agent and self.cfg.precise_action_space_positions:
             raise NotImplementedError("precise_action_space_positions together with a static defender (the reference then refreshes "
                                       "around `changed_nodes`, compressed:423-427) is restated by the oracle only so far")
@@ -127,7 +128,14 @@ class BatchedCyberBattleEnv:
         """Test hook: replace the static defender's random draws (static_defender.py:48,53) by device tensors
         scan_nodes int32[B, scan_capacity] / detect_uniforms float32[B, scan_capacity]; the tensors are read by every
         following step (update them in place), ``None, None`` restores the Philox streams."""
-        if scan_nodes is None:
+        if self.cfg.static_defender_agent == "events" and detect_uniforms is not None:
+            # ExternalRandomEvents: detect_uniforms = float32[B, max_nodes, 4] per node (function index, event / pick / side uniform)
+            assert detect_uniforms.shape == (self.num_envs, self.ncap, 4) and detect_uniforms.dtype == torch.float32
+            assert detect_uniforms.is_contiguous() and detect_uniforms.device == self.device
+            self._def_draws = (detect_uniforms,)
+            self._check(self.lib.cbs_set_defender_draws(self._h, None, self._p(detect_uniforms)))
+            return
+        if scan_nodes is None and detect_uniforms is None:
             self._def_draws = None
             self._check(self.lib.cbs_set_defender_draws(self._h, None, None))
             return
@@ -349,6 +357,11 @@ class BatchedCyberBattleEnv:
     def distances(self) -> np.ndarray:
         """float64[B]: distance of the last decoded action to its table row (info['min_distance_action'], compressed:449)."""
         return self.read(L.F_DIST, np.float64, (self.num_envs,))
+
+    def events_state(self, cached: bool = False) -> np.ndarray:
+        """Events defender: uint16[B, max_nodes, 4] = per node the { running services, incoming BLOCK, outgoing BLOCK, - } bit sets
+        over the node's service slots; ``cached`` = as held by the node's feature vector in the visible graph."""
+        return self.read(L.F_EV_X if cached else L.F_EV_CUR, np.uint16, (self.num_envs, self.ncap, 4))
 
     def divergence_count(self) -> int:
         """Env-steps so far at which the reference itself would have raised (see CBS_F_DIVERGENCE in include/cbsim.h)."""

@@ -215,9 +215,11 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   if (cfg->abi_version != CBS_ABI_VERSION) return fail(nullptr, CBS_ERR_INVALID_ARG, "ABI version mismatch (%d vs %d)", cfg->abi_version, CBS_ABI_VERSION);
   if (cfg->num_envs <= 0) return fail(nullptr, CBS_ERR_INVALID_ARG, "num_envs must be positive");
   if (cfg->goal < 0 || cfg->goal > 5) return fail(nullptr, CBS_ERR_INVALID_ARG, "unsupported goal %d", cfg->goal);
-  if (cfg->static_defender != 0 && cfg->static_defender != 1)
-    return fail(nullptr, CBS_ERR_INVALID_ARG, "static_defender must be 0 (none) or 1 (scan and re-image)");
-  if (cfg->static_defender && (cfg->scan_capacity < 1 || cfg->scan_capacity > MAX_SCAN_CAPACITY || cfg->scan_frequency < 1))
+  if (cfg->static_defender < 0 || cfg->static_defender > 2)
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "static_defender must be 0 (none), 1 (scan and re-image) or 2 (external random events)");
+  if (cfg->static_defender == 2 && !(cfg->random_event_probability >= 0.0 && cfg->random_event_probability <= 1.0))
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "random_event_probability must be in [0, 1]");
+  if (cfg->static_defender == 1 && (cfg->scan_capacity < 1 || cfg->scan_capacity > MAX_SCAN_CAPACITY || cfg->scan_frequency < 1))
     return fail(nullptr, CBS_ERR_INVALID_ARG, "scan_capacity must be in 1..%d and scan_frequency >= 1", MAX_SCAN_CAPACITY);
   if (cfg->precise_action_space_positions && cfg->static_defender)
     return fail(nullptr, CBS_ERR_INVALID_ARG, "precise_action_space_positions is not implemented together with a static defender");
@@ -256,6 +258,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.scan_capacity = cfg->scan_capacity;
   P.scan_frequency = cfg->scan_frequency;
   P.detect_prob = cfg->detect_probability;
+  P.event_prob = cfg->random_event_probability;
   P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
   P.precise_positions = cfg->precise_action_space_positions ? 1 : 0;
   P.metric = cfg->distance_metric;
@@ -310,7 +313,13 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if (h->cfg.static_defender) {
     if (!t->nd_reimageable) return fail(h, CBS_ERR_INVALID_ARG, "the static defender needs nd_reimageable");
     UP(nd_reimageable, Nn);
-  } UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
+  }
+  if (h->cfg.static_defender == 2) {
+    if (!t->nd_ev_init || !t->vi_svc_slot || !t->out_slot || !g->ev_proj)
+      return fail(h, CBS_ERR_INVALID_ARG, "the events defender needs nd_ev_init, vi_svc_slot, out_slot and the folded ev_proj");
+    UP(nd_ev_init, (size_t)Nn * 4); UP(out_slot, (size_t)t->num_ports_total * t->max_nodes);
+  }
+  UP(nd_ownable, Nn); UP(nd_discoverable, Nn); UP(nd_disruptable, Nn);
   UP(nd_row_off, 2 * (size_t)Nn + 1); UP(outblock, (size_t)t->num_ports_total * t->words);
   UP(uvuln_global, t->num_uvuln_total); UP(inst_of, t->num_instof);
   UP(vi_port, I); UP(vi_flags, I); UP(vi_kinds_any, I); UP(vi_kinds_remote, I); UP(vi_success, I); UP(vi_cost, I);
@@ -339,12 +348,13 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
       uint32_t* r = &vp[(size_t)i * 8];
       const int oa = t->vi_recon_any[2 * i], la = t->vi_recon_any[2 * i + 1];
       const int orr = t->vi_recon_remote[2 * i], lr = t->vi_recon_remote[2 * i + 1];
-      if (la < 0 || la > CBS_MAX_NODES || lr < 0 || lr > CBS_MAX_NODES || (t->vi_flags[i] >> 8))
+      if (la < 0 || la > CBS_MAX_NODES || lr < 0 || lr > CBS_MAX_NODES || (t->vi_flags[i] >> 8))   // (list lengths <= 128 < 256: bits 8..23)
         return fail(h, CBS_ERR_INVALID_ARG, "vulnerability instance %d: malformed flags / reconnaissance list", i);
-      r[0] = t->vi_flags[i] | ((uint32_t)la << 8) | ((uint32_t)lr << 16);
+      r[0] = t->vi_flags[i] | ((uint32_t)la << 8) | ((uint32_t)lr << 16) |
+             ((uint32_t)(h->cfg.static_defender == 2 ? t->vi_svc_slot[i] : 0xFF) << 24);   // events defender: the target's service slot of the port
       r[1] = (uint32_t)t->vi_kinds_any[i] | ((uint32_t)t->vi_kinds_remote[i] << 16);
       // the port's outgoing-firewall node mask itself when a plane is one word, else the port index into `outblock`
-      r[2] = t->words == 1 ? t->outblock[(size_t)(inst_port_off[i] + t->vi_port[i])] : (uint32_t)t->vi_port[i];
+      r[2] = (t->words == 1 && h->cfg.static_defender != 2) ? t->outblock[(size_t)(inst_port_off[i] + t->vi_port[i])] : (uint32_t)t->vi_port[i];
       r[3] = (uint32_t)rp.size();           // both lists start on an 8-byte boundary (the transition reads 8 ids per load)
       if (t->words == 1) {
         for (int k = 0; k < la; ++k) rmask[2 * (size_t)i] |= 1u << (t->recon_nodes[oa + k] & 31);
@@ -368,6 +378,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   UPG(node_static, (size_t)Nn * 2 * PROJ_ROWS * NODE_EMB); UPG(dyn_proj, NUM_DYN * PROJ_ROWS * NODE_EMB);
   UPG(vuln_h, (size_t)t->num_global_vulns * NN_CH); UPG(nn0_b, NN_CH); UPG(bn1_scale, NODE_EMB); UPG(bn1_shift, NODE_EMB);
   UPG(gcn_wt, NODE_EMB * NODE_EMB); UPG(bn2_scale, NODE_EMB); UPG(bn2_shift, NODE_EMB);
+  if (h->cfg.static_defender == 2) UPG(ev_proj, 30 * PROJ_ROWS * NODE_EMB);
 #undef UPG
 
   // capacities
@@ -403,6 +414,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
   else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
   AL(pair_epoch, P.precise_positions ? B * P.ncap * P.ncap : 1);
+  AL(ev_cur, P.defender == 2 ? B * P.ncap * 4 : 1); AL(ev_x, P.defender == 2 ? B * P.ncap * 4 : 1);
   static_assert(OBS_DIM + NODE_EMB <= RC_Z, "reset-cache entry too small for the observation");
   AL(reset_cache, (size_t)Nn * RC_PITCH); AL(reset_cache_flag, Nn);
   AL(z_hist, B * P.slots * P.ncap * NODE_EMB); AL(zn2_hist, B * P.slots * P.ncap);
@@ -755,6 +767,8 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
     case CBS_F_SEL: *p = S.sel; *bytes = B * 16; break;
     case CBS_F_DIVERGENCE: *p = S.errflag + 1; *bytes = 4; break;
+    case CBS_F_EV_CUR: *p = S.ev_cur; *bytes = P.defender == 2 ? B * P.ncap * 8 : 2; break;
+    case CBS_F_EV_X: *p = S.ev_x; *bytes = P.defender == 2 ? B * P.ncap * 8 : 2; break;
     case CBS_F_VT: *p = S.vt; *bytes = B * h->vt_stride * 4; break;
     default: return fail(h, CBS_ERR_INVALID_ARG, "unknown state field %d", field);
   }

@@ -114,6 +114,10 @@ struct Tables {  // immutable, device pointers
                                //         { success rate (float64), cost (float64) }
   const uint8_t* recon_pack;   // per instance: the "any type" Reconnaissance node list, then the "REMOTE only" one, each padded to 8 bytes
   const uint2* recon_mask;     // [I] node sets of those two lists as bitmasks (scenarios of <= 32 nodes; zeros otherwise)
+  // ExternalRandomEvents defender
+  const uint16_t* nd_ev_init;  // [Nn][4] running | incoming BLOCK | outgoing BLOCK bits per service slot, service count
+  const uint8_t* out_slot;     // [ports][max_nodes] node's service slot of a scenario port (0xFF none)
+  const float* ev_proj;        // [30][18][64] folded firewall / running feature columns
   // GAE
   const float *node_static, *dyn_proj, *vuln_h, *nn0_b, *bn1_scale, *bn1_shift, *gcn_wt, *bn2_scale, *bn2_shift;
 };
@@ -137,6 +141,7 @@ struct Params {  // configuration, by value
   int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
   int precise_positions;   // precise_action_space_positions (compressed:419-427,498-506): table rows are refreshed, see build_table
   int metric;              // enum Metric; != METRIC_COSINE: k_decode_metric.cu decodes, the transition runs as its own launch
+  double event_prob;       // defender == 2: random_event_probability
   int subset_k;            // sample_subset_samples (compressed:521-522,553-567): rows kept per outcome class, 0 = the whole table
 };
 
@@ -156,8 +161,13 @@ struct State {  // mutable, device pointers
   // precise_action_space_positions only (1-byte dummy otherwise):
   uint8_t* pair_epoch;   // [B][ncap*ncap]  slot at which the pair FIRST entered the table: its place in the insertion order;
                          //                 pair_slot then names the snapshot its rows currently carry (refreshed over time)
+  // events defender only: per node { running services, incoming BLOCK, outgoing BLOCK, unused } bit sets over the node's
+  // service slots — the live ones and the ones the node's CACHED feature vector in the visible graph was built from
+  uint16_t* ev_cur;      // [B][ncap][4]
+  uint16_t* ev_x;        // [B][ncap][4]
   const int32_t* def_nodes;     // [B][scan_capacity] test override of the scan draws (random.choices), or nullptr -> Philox
   const float* def_uniforms;    // [B][scan_capacity] test override of the detection uniforms, consumed in call order
+                                //   (events defender: [B][ncap][4] = function index, event / pick / side uniforms per node)
   float* z_hist;         // [B][slots][ncap][64]  node embeddings of the encode that created the slot
   float* zn2_hist;       // [B][slots][ncap]      their squared norms
   __half* z16_hist;      // [B][slots][ncap][64]  half-precision copy read by the approximate decode scan

@@ -71,6 +71,27 @@ __device__ __forceinline__ void node_dyn(uint8_t d, uint8_t xstatus, float& vis,
   x[5] = (float)xstatus;
 }
 
+// ---- ExternalRandomEvents defender: the firewall-in / firewall-out / service-running columns of a VISIBLE node's cached feature
+//      vector (compressed:365-370) are per-env state; node_static holds the scenario's initial values, so the columns that
+//      differ are added (or removed) here.  `evx` / `init` = the node's { running, incoming BLOCK, outgoing BLOCK } bit sets as
+//      cached in the graph / as compiled; only the first MAX_SERVICES slots are features.  Returns the correction of channel c
+//      of folded row k. ----
+__device__ __forceinline__ float ev_delta(const float* __restrict__ ev_proj, const uint16_t* evx, const uint16_t* init, int k, int c) {
+  float acc = 0.f;
+  const int col0[3] = {20, 0, 10};          // word 0 running -> F_SVC_RUNNING, word 1 incoming -> F_FW_IN, word 2 outgoing -> F_FW_OUT
+#pragma unroll
+  for (int w = 0; w < 3; ++w) {
+    uint32_t diff = (uint32_t)(evx[w] ^ init[w]) & 0x3FFu;
+    while (diff) {
+      const int i = __ffs(diff) - 1;
+      diff &= diff - 1;
+      const float v = ev_proj[((size_t)(col0[w] + i) * PROJ_ROWS + k) * NODE_EMB + c];
+      acc += ((evx[w] >> i) & 1) ? v : -v;
+    }
+  }
+  return acc;
+}
+
 // ---- add_edge_evolving_visible_graph (compressed:214-246), mean aggregation, in the W1-projected space ----
 __device__ void edge_update(const Tables& T, const Params& P, const State& S, int b, int lane) {
   const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
@@ -167,6 +188,12 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
         a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
         a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
       }
+      if (P.defender == 2 && vis != 0.f) {
+        const uint16_t* evx = S.ev_x + ((size_t)b * P.ncap + order[i]) * 4;
+        const uint16_t* ini = T.nd_ev_init + (size_t)(node_off + order[i]) * 4;
+        a0 += ev_delta(T.ev_proj, evx, ini, 17, c0);
+        a1 += ev_delta(T.ev_proj, evx, ini, 17, c1);
+      }
       W.y[i * NODE_EMB + c0] = a0;
       W.y[i * NODE_EMB + c1] = a1;
     }
@@ -185,6 +212,10 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     float vis, x[NUM_DYN];
     node_dyn(W.dynb[is], W.xst[is], vis, x);
     const float* ns = T.node_static + ((size_t)(node_off + js) * 2 + (vis != 0.f ? 1 : 0)) * ROW;   // visible / not-visible variant
+    const bool evd = P.defender == 2 && vis != 0.f;
+    const uint16_t* evx = evd ? S.ev_x + ((size_t)b * P.ncap + js) * 4 : nullptr;
+    const uint16_t* ini = evd ? T.nd_ev_init + (size_t)(node_off + js) * 4 : nullptr;
+    const bool ev_any = evd && (((evx[0] ^ ini[0]) | (evx[1] ^ ini[1]) | (evx[2] ^ ini[2])) & 0x3FF) != 0;
     float m0 = 0.f, m1 = 0.f;
 #pragma unroll
     for (int k = 0; k < NN_CH + 1; ++k) {
@@ -196,6 +227,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
         t0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c0], t0);
         t1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c1], t1);
       }
+      if (ev_any) { t0 += ev_delta(T.ev_proj, evx, ini, k, c0); t1 += ev_delta(T.ev_proj, evx, ini, k, c1); }
       m0 = fmaf(hk, t0, m0);
       m1 = fmaf(hk, t1, m1);
     }
@@ -446,7 +478,8 @@ __device__ void finish_episode(const Tables& T, const Params& P, const State& S,
   st[0] = owned; st[1] = n_disc; st[2] = N - n_disc; st[3] = disrupted; st[4] = N;
   st[5] = sc_of(2); st[6] = sc_of(3); st[7] = sc_of(4);
   st[8] = (double)running / (double)n_disc;
-  st[9] = st[10] = P.defender ? sc_of(8) : 0;          // len(overall_reimaged), num_events
+  st[10] = P.defender ? sc_of(8) : 0;                  // num_events (cyberbattle_env.py:419)
+  st[9] = P.defender == 1 ? st[10] : 0.0;              // len(overall_reimaged): only the re-imaging defender fills it (:420-422)
   st[11] = sc_of(5); st[12] = sc_of(6);
   // attacker_goal_reached() at the end of an episode: the goal test comes first in the end-of-step chain
   // (cyberbattle_env.py:343-370), so it holds exactly when the episode's last step reported reason 1
@@ -502,6 +535,13 @@ __device__ int2 reset_env(const Tables& T, const Params& P, const State& S, int 
   }
   uint32_t* ps = reinterpret_cast<uint32_t*>(S.pair_slot + (size_t)b * P.ncap * P.ncap);
   for (int i = lane; i < P.ncap * P.ncap / 4; i += 32) ps[i] = 0xFFFFFFFFu;
+  if (P.defender == 2) {      // pristine services / firewall rules (the reference's deepcopy of the scenario, cyberbattle_env.py:145)
+    const int N = T.sc_num_nodes[sc];
+    const uint2* ini = reinterpret_cast<const uint2*>(T.nd_ev_init + (size_t)T.sc_node_off[sc] * 4);
+    uint2* cur = reinterpret_cast<uint2*>(S.ev_cur + (size_t)b * P.ncap * 4);
+    uint2* evx = reinterpret_cast<uint2*>(S.ev_x + (size_t)b * P.ncap * 4);
+    for (int i = lane; i < N; i += 32) { cur[i] = ini[i]; evx[i] = ini[i]; }
+  }
   if (P.subset_k) {   // empty table; the lifetime balance counter ([13]) goes on
     int32_t* meta = S.sub_meta + (size_t)b * SUB_META;
     if (lane < 13) meta[lane] = (lane == 11 || lane == 12) ? -1 : 0;

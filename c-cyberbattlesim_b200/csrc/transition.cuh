@@ -167,6 +167,56 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
   return event;
 }
 
+// ---- static defender step with ExternalRandomEvents (_env/static_defender.py:76-161): every node, in node order, draws one of
+//      { start service, firewall remove, stop service, firewall add } and suffers it with probability `event_prob` unless it has
+//      defense evasion.  Service events pick one of the node's services and (only while the node is Running) set its running
+//      flag, but count as an event either way (static_defender_actions.py:150,161); firewall events pick one of the node's
+//      ports, do nothing if an INCOMING rule (port, wanted permission) already exists — both sides test firewall.incoming,
+//      :135-141 / :158-164 — else patch the rule of the drawn side (override_firewall_rule :96-128).  The device keeps one bit
+//      per (node, service slot): running, incoming BLOCK, outgoing BLOCK (ev[node][0..2]).  Returns the number of events. ----
+struct EventsCtx {
+  uint16_t* ev;                 // this env's [ncap][4]
+  const uint16_t* init;         // this scenario's nd_ev_init rows (service counts in [3])
+  const float* draws;           // this env's [ncap][4] test override or nullptr
+  uint64_t seed, genv;
+  double prob;
+};
+__device__ __noinline__ int events_step(EventsCtx E, EnvBits M, int N, int total_steps) {
+  int events = 0;
+  for (int n = 0; n < N; ++n) {
+    int f;
+    float u_event, u_pick, u_side;
+    if (E.draws) {
+      const float4 d = reinterpret_cast<const float4*>(E.draws)[n];
+      f = (int)d.x; u_event = d.y; u_pick = d.z; u_side = d.w;
+    } else {      // Philox stream 16 + node: { function, event uniform, pick uniform, side uniform }
+      const Philox4 r = philox4x32_10(E.seed, E.genv, (uint32_t)total_steps, 16u + (uint32_t)n);
+      f = (int)(r.x >> 30);
+      u_event = (float)(r.y >> 8) * (1.0f / 16777216.0f);
+      u_pick = (float)(r.z >> 8) * (1.0f / 16777216.0f);
+      u_side = (float)(r.w >> 8) * (1.0f / 16777216.0f);
+    }
+    if (M.get(M_EVASION, n) || !((double)u_event <= E.prob)) continue;
+    const int ns = E.init[4 * n + 3];
+    if (ns == 0) continue;                 // (the reference raises on a firewall event here; such scenarios are rejected up front)
+    int slot = (int)(u_pick * (float)ns);
+    if (slot > ns - 1) slot = ns - 1;
+    uint16_t* w = E.ev + 4 * n;
+    const uint16_t bit = (uint16_t)(1u << slot);
+    if (f == 0 || f == 2) {
+      if (!M.get(M_STOPPED, n) && !M.get(M_IMAGING, n)) w[0] = f == 0 ? (uint16_t)(w[0] | bit) : (uint16_t)(w[0] & ~bit);
+      ++events;
+    } else {
+      const bool block = f == 3;
+      if (((w[1] & bit) != 0) == block) continue;          // (port, permission) already among the incoming rules
+      uint16_t& side = (double)u_side <= 0.5 ? w[1] : w[2];
+      side = block ? (uint16_t)(side | bit) : (uint16_t)(side & ~bit);
+      ++events;
+    }
+  }
+  return events;
+}
+
 }  // namespace
 
 // Everything a transition reads from the env's own records and the call's per-env inputs, requested in ONE burst before
@@ -270,7 +320,19 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   if constexpr (REG) recon_m = T.recon_mask[insti];
   const double v_success = __hiloint2double((int)vp1.y, (int)vp1.x), v_cost = __hiloint2double((int)vp1.w, (int)vp1.z);
   // ---- outgoing-firewall word of (port, source): with one-word planes the instance record carries it ----
-  const uint32_t fw_out = P.words == 1 ? vp0.z : T.outblock[(size_t)(port_off + (int)vp0.z) * P.words + (ss >> 5)];
+  uint32_t fw_out = 0u;
+  bool listening = (vf & VI_LISTENING) != 0u, in_allowed = (vf & VI_IN_ALLOWED) != 0u;
+  if (DEF && P.defender == 2) {
+    // ExternalRandomEvents: services and firewall rules are per-env state (one bit per node and service slot)
+    const uint16_t* ev = S.ev_cur + (size_t)b * P.ncap * 4;
+    const int slot_t = (int)(vf >> 24);                                               // the target's service slot of the port
+    const int slot_s = T.out_slot[(size_t)(port_off + (int)vp0.z) * T.max_nodes + ss];  // the source's
+    listening = slot_t != 0xFF && ((ev[4 * tt] >> slot_t) & 1);
+    in_allowed = slot_t == 0xFF || !((ev[4 * tt + 1] >> slot_t) & 1);
+    fw_out = (slot_s != 0xFF && ((ev[4 * ss + 2] >> slot_s) & 1)) ? (1u << (ss & 31)) : 0u;
+  } else {
+    fw_out = P.words == 1 ? vp0.z : T.outblock[(size_t)(port_off + (int)vp0.z) * P.words + (ss >> 5)];
+  }
 
   double reward = 0.0;
   int code = -1;
@@ -292,9 +354,9 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     const uint32_t kinds = local ? (vp0.y & 0xFFFFu) : (vp0.y >> 16);
     int pidx = 0;
     if ((double)uf >= v_success) { code = OC_UNSUCCESSFUL; pidx = P_SUCCESS_FAILED; }                                    // :190 / :409
-    if (!local && !eva_t && !(vf & VI_IN_ALLOWED)) { code = OC_FW_INCOMING; pidx = P_FW_REMOTE; }
+    if (!local && !eva_t && !in_allowed) { code = OC_FW_INCOMING; pidx = P_FW_REMOTE; }
     if (!local && !eva_s && ((fw_out >> (ss & 31)) & 1u)) { code = OC_FW_OUTGOING; pidx = P_FW_LOCAL; }
-    if (!local && !(vf & VI_LISTENING)) { code = OC_PORT_NOT_LISTENING; pidx = P_UNOPEN_PORT; }
+    if (!local && !listening) { code = OC_PORT_NOT_LISTENING; pidx = P_UNOPEN_PORT; }
     if (kind < 0 || kind >= N_KINDS || !((kinds >> (kind & 15)) & 1u)) { code = OC_OUTCOME_NOT_PRESENT; pidx = P_INVALID_ACTION; }
     if (privreq && level_t < privreq) { code = OC_NO_PRIVILEGE; pidx = P_NO_PRIV; }
     if (inst < 0) { code = OC_NO_VULNERABILITY; pidx = P_NO_VULN; }
@@ -444,6 +506,29 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   //      vector is rebuilt from the post-defender state for these obtained outcomes only (compressed:472-479) ----
   bool def_event = false;
   if constexpr (DEF) {
+   if (P.defender == 2) {
+    const int n_disc_before = in.c0.x;
+    EventsCtx E;
+    E.ev = S.ev_cur + (size_t)b * P.ncap * 4;
+    E.init = T.nd_ev_init + (size_t)node_off * 4;
+    E.draws = S.def_uniforms ? S.def_uniforms + (size_t)b * P.ncap * 4 : nullptr;
+    E.seed = P.seed; E.genv = (uint64_t)(P.global_env_offset + b);
+    E.prob = P.event_prob;
+    const int ev_n = events_step(E, M, N, total_steps);
+    SC(S_N_REIMAGED) += ev_n;                      // num_events of the episode (cyberbattle_env.py:419)
+    def_event = ev_n > 0;
+    // the visible graph caches node feature vectors: a node's services / firewall columns are those of the moment it joined
+    // the graph (newly discovered nodes: after this step's events, compressed:467-469) or was last the target of a successful
+    // outcome (compressed:472-479)
+    uint16_t* evx = S.ev_x + (size_t)b * P.ncap * 4;
+    const uint8_t* order = S.disc_order + (size_t)b * P.ncap;
+    const int n_disc_now = SC(S_N_DISC);
+    for (int i = n_disc_before; i < n_disc_now; ++i) {
+      const int node = order[i];
+      *reinterpret_cast<uint2*>(evx + 4 * node) = *reinterpret_cast<const uint2*>(E.ev + 4 * node);
+    }
+    if (code < 16 && code != K_RECON) *reinterpret_cast<uint2*>(evx + 4 * t) = *reinterpret_cast<const uint2*>(E.ev + 4 * t);
+   } else {
     DefenderCtx D;
     D.left = S.reimage_left + (size_t)b * P.ncap;
     D.raw = S.owned_raw + (size_t)b * P.ocap;
@@ -459,7 +544,8 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     def_event = defender_step(D, M, N, stepcount, total_steps, code == K_PRIVESC);
     if (code < 16 && code != K_RECON) {
       if (M.get(M_IMAGING, t)) M.set(M_X_IMAGING, t); else M.clr(M_X_IMAGING, t);
-    }
+     }
+  }
   }
 
   // ---- goal / termination (cyberbattle_env.py:338-370, 438-514) ----

@@ -97,6 +97,7 @@ class GaeTables:
     gcn_wt: np.ndarray        # [64(in), 64(out)]  transposed for coalesced reads
     bn2_scale: np.ndarray     # [64]
     bn2_shift: np.ndarray     # [64]  (gcn_b - mean) * scale + beta
+    ev_proj: np.ndarray = None  # [30, 18, 64] the firewall-in | firewall-out | service-running feature columns (events defender)
 
 
 def node_feature_static(spec_node, vuln_emb) -> tuple:
@@ -161,6 +162,7 @@ def fold_gae(tables: ScenarioTables, w: GaeWeights, chunk: int = 64) -> GaeTable
         node_static[g:g + spec.num_nodes] = out
         g += spec.num_nodes
     dyn = np.stack([P[f] for f in C.DYN_FEATURES]).astype(np.float32)
+    ev_proj = np.ascontiguousarray(P[C.F_FW_IN:C.F_SVC_RUNNING + C.MAX_SERVICES].astype(np.float32))     # columns 0..29
     vuln_h = (tables.vemb64.astype(np.float32).astype(np.float64) @ w.nn0_w.astype(np.float64).T).astype(np.float32)
 
     def bn_fold(bn, conv_bias):
@@ -171,4 +173,4 @@ def fold_gae(tables: ScenarioTables, w: GaeWeights, chunk: int = 64) -> GaeTable
     s2, h2 = bn_fold(w.bn2, w.gcn_b)
     return GaeTables(node_static=node_static, dyn_proj=dyn, vuln_h=vuln_h, nn0_b=w.nn0_b.astype(np.float32),
                      bn1_scale=s1, bn1_shift=h1, gcn_wt=np.ascontiguousarray(w.gcn_w.T.astype(np.float32)),
-                     bn2_scale=s2, bn2_shift=h2)
+                     bn2_scale=s2, bn2_shift=h2, ev_proj=ev_proj)

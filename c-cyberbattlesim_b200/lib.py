@@ -29,7 +29,7 @@ class CbsConfig(ct.Structure):
                 ("decode_margin", f32), ("decode_gemm", i32),
                 ("static_defender", i32), ("scan_capacity", i32), ("scan_frequency", i32), ("precise_graph_encoding", i32),
                 ("detect_probability", f64), ("precise_action_space_positions", i32), ("distance_metric", i32),
-                ("sample_subset_samples", i32)]
+                ("sample_subset_samples", i32), ("random_event_probability", f64)]
 
 
 _SCENARIO_PTRS = ["sc_num_nodes", "sc_node_off", "sc_port_off", "sc_uvuln_off", "sc_num_uvuln", "sc_instof_off",
@@ -37,7 +37,7 @@ _SCENARIO_PTRS = ["sc_num_nodes", "sc_node_off", "sc_port_off", "sc_uvuln_off", 
 _SCENARIO_PTRS2 = ["nd_value", "nd_level_at_access", "nd_reimageable", "nd_ownable", "nd_discoverable", "nd_disruptable", "nd_row_off",
                    "outblock", "uvuln_global", "inst_of", "vi_port", "vi_flags", "vi_kinds_any", "vi_kinds_remote",
                    "vi_success", "vi_cost", "vi_recon_any", "vi_recon_remote", "vi_ulocal", "recon_nodes", "row_packed",
-                   "row_inst", "vemb32", "vemb64", "vnorm2"]
+                   "row_inst", "vemb32", "vemb64", "vnorm2", "nd_ev_init", "vi_svc_slot", "out_slot"]
 
 
 class CbsScenarioTables(ct.Structure):
@@ -61,7 +61,7 @@ class CbsReplayLog(ct.Structure):
                                   "reset_masks", "stats", "force_sel", "force_dist", "force_steps_host")])
 
 
-_GAE_PTRS = ["node_static", "dyn_proj", "vuln_h", "nn0_b", "bn1_scale", "bn1_shift", "gcn_wt", "bn2_scale", "bn2_shift"]
+_GAE_PTRS = ["node_static", "dyn_proj", "vuln_h", "nn0_b", "bn1_scale", "bn1_shift", "gcn_wt", "bn2_scale", "bn2_shift", "ev_proj"]
 
 
 class CbsGaeTables(ct.Structure):
@@ -77,7 +77,7 @@ SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cb
 
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
-    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE = range(18)
+    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE, F_EV_CUR, F_EV_X = range(20)
 NUM_SCALARS, NUM_ACCUM = 25, 20
 # per-env scalar record (csrc/cbs_types.h enum Scalar): four 32-byte sectors — rewritten every step | list lengths and
 # counters | episode constants | misc
@@ -204,7 +204,7 @@ def make_scenario_struct(tables, goal: int):
                      ("vi_success", np.float64), ("vi_cost", np.float64), ("vi_recon_any", np.int32),
                      ("vi_recon_remote", np.int32), ("vi_ulocal", np.int32), ("recon_nodes", np.uint8),
                      ("row_packed", np.uint32), ("row_inst", np.int32), ("vemb32", np.float32), ("vemb64", np.float64),
-                     ("vnorm2", np.float64)):
+                     ("vnorm2", np.float64), ("nd_ev_init", np.uint16), ("vi_svc_slot", np.uint8), ("out_slot", np.uint8)):
         setattr(t, name, arr(getattr(tables, name), dt))
     return t, keep
 
@@ -239,7 +239,8 @@ def make_config(cfg, num_envs: int, device: int = 0, global_env_offset: int = 0,
     for i, v in enumerate(cfg.penalty_vector()):
         c.penalties[i] = v
     c.max_slots, c.max_edges, c.decode_margin, c.decode_gemm = max_slots, max_edges, decode_margin, decode_gemm
-    c.static_defender = {None: 0, "reimage": 1}[getattr(cfg, "static_defender_agent", None)]
+    c.static_defender = {None: 0, "reimage": 1, "events": 2}[getattr(cfg, "static_defender_agent", None)]
+    c.random_event_probability = float(getattr(cfg, "random_event_probability", 0.0) or 0.0)
     c.scan_capacity, c.scan_frequency = int(cfg.scan_capacity), int(cfg.scan_frequency)
     c.detect_probability = float(cfg.detect_probability)
     c.precise_graph_encoding = int(bool(cfg.precise_graph_encoding))

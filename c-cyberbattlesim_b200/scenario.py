@@ -341,6 +341,23 @@ def synthetic_spec(seed: int, num_nodes: int, pool=None, pool_seed: int = 1234, 
 # --------------------------------------------------------------------------------------------
 # Compiler: specs -> SoA tables
 # --------------------------------------------------------------------------------------------
+def check_events_compatible(spec: "ScenarioSpec") -> None:
+    """The device keeps the ExternalRandomEvents defender's mutable state (static_defender_actions.py:96-168) as one bit per
+    (node, service slot): that needs distinct service ports per node, at most 16 services, and firewall rules on the node's own
+    service ports only (what the reference's generator produces, generate_network.py:222-256)."""
+    for nd in spec.nodes:
+        ports = [s.port for s in nd.services]
+        if len(ports) > 16 or len(set(ports)) != len(ports):
+            raise ValueError(f"scenario '{spec.name}', node {nd.node_id}: the events defender needs <= 16 services with distinct ports")
+        if len(ports) == 0:
+            raise ValueError(f"scenario '{spec.name}', node {nd.node_id}: a node without services makes the reference's "
+                             "ExternalRandomEvents raise (random.choice of an empty list, static_defender.py:123,150)")
+        for rules in (nd.fw_in, nd.fw_out):
+            rp = [p for p, _ in rules]
+            if any(p not in ports for p in rp) or len(set(rp)) != len(rp):
+                raise ValueError(f"scenario '{spec.name}', node {nd.node_id}: the events defender needs one firewall rule per own service port")
+
+
 def _is_passing(rules: Sequence[Tuple[int, int]], port: int) -> bool:
     """attacker_actions.py:550-559 — first rule on the port decides, default allow."""
     for p, perm in rules:
@@ -425,6 +442,12 @@ class ScenarioTables:
     nd_row_off: np.ndarray         # i32[Nn+1, 2]-> flattened [2*Nn+1]: local list then remote list per node
     # per port of a scenario: nodes whose outgoing firewall blocks it
     outblock: np.ndarray           # u32[sum ports, words]
+    # ExternalRandomEvents defender: per scenario node the initial { running services, incoming BLOCK, outgoing BLOCK } bit sets
+    # over the node's service slots and its service count; per instance the target's service slot of the vulnerability's port;
+    # per (scenario port, node) the node's service slot of that port (0xFF = the node has no service on it)
+    nd_ev_init: np.ndarray         # u16[Nn, 4]
+    vi_svc_slot: np.ndarray        # u8[I]
+    out_slot: np.ndarray           # u8[sum ports, max_nodes]
     # per unique vulnerability of a scenario
     uvuln_global: np.ndarray       # i32   row in the global embedding table
     inst_of: np.ndarray            # i32   [node j][u] -> instance index or -1, per scenario block
@@ -498,6 +521,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
     feas = [[] for _ in range(6)]
     feas_off = [[0] for _ in range(6)]
     nd_value, nd_laa, nd_own, nd_disc, nd_disr, nd_reim = [], [], [], [], [], []
+    nd_ev_init, vi_svc_slot, out_slot = [], [], []       # ExternalRandomEvents defender (mutable services / firewall rules)
     nd_row_off = [0]
     outblock = []
     uvuln_global, inst_of = [], []
@@ -521,6 +545,14 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
                 if not _is_passing(nd.fw_out, p):
                     ob[pi, j // 32] |= np.uint32(1 << (j % 32))
         outblock.append(ob)
+        # slot of port p among node j's services (first match, like get_service_index cyberbattle_env.py:547-551), 0xFF = none
+        osl = np.full((max(len(ports), 1), max_nodes), 0xFF, dtype=np.uint8)
+        for p, pi in ports.items():
+            for j, nd in enumerate(spec.nodes):
+                sp = [s.port for s in nd.services]
+                if p in sp and sp.index(p) < 16:
+                    osl[pi, j] = sp.index(p)
+        out_slot.append(osl)
         sc_num_ports.append(ob.shape[0])
         sc_port_off.append(sc_port_off[-1] + ob.shape[0])
         # unique vulnerability ids of the scenario
@@ -562,6 +594,11 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
             nd_laa.append(nd.level_at_access)
             nd_reim.append(1 if nd.reimageable else 0)
             running_ports = [s.port for s in nd.services if s.running]
+            svc_ports = [s.port for s in nd.services]
+            run_bits = sum(1 << i for i, s in enumerate(nd.services[:16]) if s.running)
+            in_bits = sum(1 << i for i, p in enumerate(svc_ports[:16]) if not _is_passing(nd.fw_in, p))
+            out_bits = sum(1 << i for i, p in enumerate(svc_ports[:16]) if not _is_passing(nd.fw_out, p))
+            nd_ev_init.append((run_bits, in_bits, out_bits, len(nd.services)))
             local_rows, remote_rows = [], []
             for v in nd.vulns:
                 inst = len(vi_port)
@@ -602,6 +639,7 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
                         dst.append((len(recon_nodes), len(lst)))
                         recon_nodes.extend(int(x) for x in lst)
                 vi_port.append(ports[v.port])
+                vi_svc_slot.append(svc_ports.index(v.port) if v.port in svc_ports and svc_ports.index(v.port) < 16 else 0xFF)
                 vi_flags.append(flags)
                 vi_ka.append(ka)
                 vi_kr.append(kr)
@@ -659,6 +697,8 @@ def compile_scenarios(specs: Sequence[ScenarioSpec], isolation_filter_threshold:
         nd_ownable=np.array(nd_own, np.int32), nd_discoverable=np.array(nd_disc, np.int32),
         nd_disruptable=np.array(nd_disr, np.int32), nd_row_off=np.array(nd_row_off, np.int32),
         outblock=np.concatenate(outblock, axis=0),
+        nd_ev_init=np.array(nd_ev_init, np.uint16).reshape(-1, 4), vi_svc_slot=np.array(vi_svc_slot, np.uint8),
+        out_slot=np.concatenate(out_slot, axis=0),
         uvuln_global=np.array(uvuln_global, np.int32), inst_of=np.concatenate(inst_of),
         vi_port=np.array(vi_port, np.int32), vi_flags=np.array(vi_flags, np.uint32),
         vi_kinds_any=np.array(vi_ka, np.uint16), vi_kinds_remote=np.array(vi_kr, np.uint16),

@@ -80,7 +80,10 @@ typedef struct {
    * (_env/static_defender.py:27-60: every scan_frequency steps scan_capacity nodes are drawn with replacement; an owned,
    * Running node without defense evasion is detected with detect_probability and, if re-imageable, goes to Imaging for
    * 15 steps, static_defender_actions.py:19,37-68).  Needs cbs_scenario_tables.nd_reimageable. */
-  int32_t static_defender;
+  int32_t static_defender;      /* 2 = ExternalRandomEvents (_env/static_defender.py:63-161): every step every node without defense
+                                   evasion suffers, with random_event_probability, one of start / stop a service, remove / add a
+                                   firewall rule (simulation/static_defender_actions.py:96-168).  Needs nd_ev_init, vi_svc_slot,
+                                   out_slot of cbs_scenario_tables and ev_proj of cbs_gae_tables. */
   int32_t scan_capacity;        /* 1..8 */
   int32_t scan_frequency;       /* >= 1 */
   int32_t precise_graph_encoding; /* compressed:455-462: re-encode the visible graph on every step */
@@ -99,6 +102,7 @@ typedef struct {
    * with c = the env's lifetime count of balance calls and identity = 0x80000000 | source << 23 | target << 16 | kind << 12 |
    * scenario-local vulnerability index, and the k smallest (key, table position) stay (ccbs_b200.philox.subset_keep). */
   int32_t sample_subset_samples;
+  double random_event_probability; /* static_defender == 2 (train_config.yaml random_event_probability_min / _max) */
 } cbs_config;
 
 /* Immutable scenario tables, produced by ccbs_b200.scenario.compile_scenarios (host arrays; copied to the
@@ -146,6 +150,10 @@ typedef struct {
   const float* vemb32;                   /* [Ug][768] */
   const double* vemb64;                  /* [Ug][768] */
   const double* vnorm2;                  /* [Ug] */
+  /* events defender only (may be NULL otherwise) */
+  const uint16_t* nd_ev_init;            /* [Nn][4] running services, incoming BLOCK, outgoing BLOCK (bit i = the node's i-th service / its port), service count */
+  const uint8_t* vi_svc_slot;            /* [I] the target node's service slot of the vulnerability's port, 0xFF = none */
+  const uint8_t* out_slot;               /* [ports][max_nodes] node's service slot of a scenario port, 0xFF = none */
 } cbs_scenario_tables;
 
 /* Folded graph-encoder tables (ccbs_b200.gae.fold_gae) for gae/model.py:25-82 GAEEncoder.forward with the
@@ -160,6 +168,7 @@ typedef struct {
   const float* gcn_wt;      /* [64][64] (in, out) */
   const float* bn2_scale;   /* [64] */
   const float* bn2_shift;   /* [64] */
+  const float* ev_proj;     /* [30][18][64] firewall-in[10] | firewall-out[10] | service-running[10] feature columns (events defender; may be NULL) */
 } cbs_gae_tables;
 
 /* ---- lifetime ---------------------------------------------------------------------------------- */
@@ -181,6 +190,9 @@ int cbs_set_starter_queue(cbs_handle* h, const int32_t* queue_host, int32_t qlen
  * that is a multiple of 4 floats the tensor-core contraction reads the tensor in place through TMA; a dense tensor
  * is repacked first (TMA cannot address 3620-byte rows). */
 int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats);
+/* (events defender: detect_uniforms_dev is float32 [num_envs][max_nodes][4] = per node { function index 0 start service / 1 firewall
+ * remove / 2 stop service / 3 firewall add, event uniform, pick uniform, side uniform } replacing random.choice /
+ * numpy.random.random of _env/static_defender.py:80-161; scan_nodes_dev is ignored.) */
 /* Test hook for the static defender's randomness: scan_nodes_dev [num_envs][scan_capacity] int32 replaces the
  * random.choices draw of _env/static_defender.py:48, detect_uniforms_dev [num_envs][scan_capacity] float32 replaces the
  * numpy.random.random() calls of :53 (consumed in call order, as the reference consumes its stream).  The pointers are
@@ -304,6 +316,9 @@ typedef enum {
   CBS_F_Z_HIST = 15,      /* float32 [B][slots][max_nodes][64] node-embedding snapshots the action-table rows refer to (cbs_capacities: slots) */
   CBS_F_SEL = 16,         /* int32 [B][4] last decoded / applied action (source, target, vulnerability, outcome kind); a caller that
                              hands this very buffer to cbs_transition saves the copy */
+  CBS_F_EV_CUR = 18,      /* uint16 [B][max_nodes][4] events defender: per node { running services, incoming BLOCK, outgoing BLOCK, - } bit
+                             sets over the node's service slots */
+  CBS_F_EV_X = 19,        /* uint16 [B][max_nodes][4] the same as cached in the node's feature vector of the visible graph */
   CBS_F_DIVERGENCE = 17   /* int32 [1] number of env-steps at which the reference itself raises and this library goes on: the re-imaging
                              defender detecting a persistent node in the very step it comes back (owned_nodes.remove of an absent
                              node, cyberbattle_env.py:425 -> ValueError); the removal is a no-op here */

@@ -87,8 +87,12 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
     applied to `check_env` alone and the consistency flag is not evaluated."""
     B, T = env.num_envs, len(actions)
     defender = defender_draws is not None
+    events = defender and len(defender_draws) == 1      # ExternalRandomEvents: one (function, event, pick, side) row per node and step
     OW = 2 * n_nodes if defender else n_nodes   # under a defender the record holds env.owned_nodes itself (duplicates possible)
-    if defender:
+    if events:
+        ev_draws = torch.zeros((B, env.ncap, 4), dtype=torch.float32, device=env.device)
+        env.set_defender_draws(None, ev_draws)
+    elif defender:
         k = defender_draws[0].shape[1]
         scan_nodes = torch.zeros((B, k), dtype=torch.int32, device=env.device)
         scan_u = torch.zeros((B, k), dtype=torch.float32, device=env.device)
@@ -126,8 +130,10 @@ def replay(env, actions, uniforms, n_nodes, check_env=0, follower=None, policy_r
                 sel[check_env] = torch.from_numpy(fix[0]).to(env.device)
                 dist[check_env] = float(fix[1])
             follower.advance(actions[t], uniforms[t],
-                             (defender_draws[0][t], defender_draws[1][t]) if defender else None)
-        if defender:
+                             ((defender_draws[0][t],) if events else (defender_draws[0][t], defender_draws[1][t])) if defender else None)
+        if events:
+            ev_draws[:, :n_nodes, :] = torch.from_numpy(defender_draws[0][t].astype(np.float32)).to(env.device)[None]
+        elif defender:
             scan_nodes.copy_(torch.from_numpy(np.tile(defender_draws[0][t][None, :], (B, 1))))
             scan_u.copy_(torch.from_numpy(np.tile(defender_draws[1][t][None, :], (B, 1))))
         reward, done, trunc, outcome = env.transition(sel, dist, u)

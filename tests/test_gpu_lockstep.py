@@ -32,6 +32,16 @@ def philox_defender_draws(seed, env, step, n_nodes, capacity):
     return nodes, us
 
 
+def philox_events_draws(seed, env, step, n_nodes):
+    """csrc/transition.cuh events_step: node n draws the four words of stream 16 + n = { function (top two bits), event uniform,
+    pick uniform, side uniform (24-bit each) }"""
+    rows = []
+    for n in range(n_nodes):
+        w = _philox_words(seed, env, step, 16 + n)
+        rows.append([w[0] >> 30] + [float(np.float32((x >> 8) * (1.0 / 16777216.0))) for x in w[1:]])
+    return (np.array(rows, np.float64),)
+
+
 def philox_u01(seed, env, step, stream):
     return np.float32((_philox_uniform(seed, env, step, stream) >> 8) * (1.0 / 16777216.0))
 
@@ -68,12 +78,14 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
     ("control", (8, 20), 100, 32, 70, dict(sample_subset_samples=6, proportional_cutoff_coefficient=3)),
     ("control", (6, 14), 100, 24, 80, dict(_DEFENDER, sample_subset_samples=10)),
     ("control", (8, 16), 100, 24, 70, dict(sample_subset_samples=8, precise_action_space_positions=True, proportional_cutoff_coefficient=3)),
+    # ExternalRandomEvents defender on its Philox streams (16 + node): services stopped / started, firewall rules added / removed
+    ("control", (6, 14), 100, 24, 90, dict(static_defender_agent="events", random_event_probability=0.05, proportional_cutoff_coefficient=4)),
     # BASELINE configs[3] (bench workload c4): mixed 10-100-node scenarios in one padded batch, pool of 600 vulnerabilities
     ("control", (10, 100), 600, 18, 60, {}),
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
         "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both",
         "metric-l1", "metric-l2", "metric-inf", "metric-l2-defender", "subset-k100-32-nodes", "subset-k6", "subset-defender",
-        "subset-positions", "c4-mixed-10-100"])
+        "subset-positions", "events-philox", "c4-mixed-10-100"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
     import ccbs_b200 as cb
@@ -156,7 +168,10 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
                 assert dd[i] - d < near_tie_tolerance(cfg.distance_metric), f"step {t} env {b}: decode {got} (gap {dd[i] - d:.3e}) vs oracle {want}"
                 flips += 1
                 forced = (got[0], got[1], o.action_keys[i][2], got[3], dd[i])
-            dd_ = philox_defender_draws(seed, offset + b, total_steps[b] - 1, o.N, int(cfg.scan_capacity)) if defender else None
+            if cfg.static_defender_agent == "events":
+                dd_ = philox_events_draws(seed, offset + b, total_steps[b] - 1, o.N)
+            else:
+                dd_ = philox_defender_draws(seed, offset + b, total_steps[b] - 1, o.N, int(cfg.scan_capacity)) if defender else None
             ob, r, dn, inf = o.step(actions[t, b], u, forced=forced, defender_draws=dd_)
             assert int(info_h[b, 4]) == o.outcome and int(info_h[b, 5]) == o.end_episode_reason
             assert bool(done_h[b]) == bool(dn)
@@ -183,6 +198,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
         assert tables.vemb32.shape[0] > 256
     acc = env.stat_accum()
     assert acc["episodes"] == sum(episodes)
-    if defender:
+    if cfg.static_defender_agent == "reimage":
         assert acc["stat9"] > 0 and acc["lost"] > 0, "the defender never re-imaged a node / never evicted the attacker"
+    if cfg.static_defender_agent == "events":
+        assert acc["stat10"] > 0 and acc["stat9"] == 0, "no external event happened"
     env.close()

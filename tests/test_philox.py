@@ -42,5 +42,3 @@ def test_cuda_env_refuses_oracle_only_options():
     import ccbs_b200 as cb
     with pytest.raises(NotImplementedError):
         cb.BatchedCyberBattleEnv([cb.synthetic_spec(0, 8)], cb.GaeWeights.random(0), cb.EnvConfig(sample_subset_samples=100, distance_metric="l1"))
-    with pytest.raises(NotImplementedError):
-        cb.BatchedCyberBattleEnv([cb.synthetic_spec(0, 8)], cb.GaeWeights.random(0), cb.EnvConfig(static_defender_agent="events"))
