@@ -38,9 +38,6 @@ class BatchedCyberBattleEnv:
             from .scenario import check_events_compatible
             for sp in (tables.specs if tables is not None else specs):
                 check_events_compatible(sp)
-        if self.cfg.static_defender_agent and self.cfg.precise_action_space_positions:
-            raise NotImplementedError("precise_action_space_positions together with a static defender (the reference then refreshes "
-                                      "around `changed_nodes`, compressed:423-427) is restated by the oracle only so far")
         if not torch.cuda.is_available():
             raise CbsError("BatchedCyberBattleEnv needs a CUDA device (there is no CPU fallback)")
         self.num_envs = int(num_envs)

@@ -221,8 +221,8 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
     return fail(nullptr, CBS_ERR_INVALID_ARG, "random_event_probability must be in [0, 1]");
   if (cfg->static_defender == 1 && (cfg->scan_capacity < 1 || cfg->scan_capacity > MAX_SCAN_CAPACITY || cfg->scan_frequency < 1))
     return fail(nullptr, CBS_ERR_INVALID_ARG, "scan_capacity must be in 1..%d and scan_frequency >= 1", MAX_SCAN_CAPACITY);
-  if (cfg->precise_action_space_positions && cfg->static_defender)
-    return fail(nullptr, CBS_ERR_INVALID_ARG, "precise_action_space_positions is not implemented together with a static defender");
+  if (cfg->precise_action_space_positions && cfg->static_defender == 2)   // the reference raises networkx.NodeNotFound there (compressed:423-427,498-500)
+    return fail(nullptr, CBS_ERR_INVALID_ARG, "precise_action_space_positions cannot be used with the events defender");
   if (cfg->distance_metric < METRIC_COSINE || cfg->distance_metric > METRIC_INF)
     return fail(nullptr, CBS_ERR_INVALID_ARG, "Unsupported metric %d. Use 0 cosine, 1 l1, 2 l2 or 3 inf", cfg->distance_metric);   // compressed:578-579
   int ndev = 0;
@@ -261,6 +261,7 @@ int cbs_create(const cbs_config* cfg, cbs_handle** out) {
   P.event_prob = cfg->random_event_probability;
   P.always_encode = (cfg->static_defender || cfg->precise_graph_encoding) ? 1 : 0;
   P.precise_positions = cfg->precise_action_space_positions ? 1 : 0;
+  P.precise_graph = cfg->precise_graph_encoding ? 1 : 0;
   P.metric = cfg->distance_metric;
   P.subset_k = cfg->sample_subset_samples > 0 ? cfg->sample_subset_samples : 0;
   *out = h;
@@ -414,6 +415,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if (P.defender) { AL(owned_raw, B * P.ocap); AL(reimage_left, B * P.ncap); AL(pair_opos, B * P.ncap * P.ncap); }
   else { AL(owned_raw, 1); AL(reimage_left, 1); AL(pair_opos, 1); }
   AL(pair_epoch, P.precise_positions ? B * P.ncap * P.ncap : 1);
+  AL(changed, (P.precise_positions && P.defender) ? B * P.words : 1);
   AL(ev_cur, P.defender == 2 ? B * P.ncap * 4 : 1); AL(ev_x, P.defender == 2 ? B * P.ncap * 4 : 1);
   static_assert(OBS_DIM + NODE_EMB <= RC_Z, "reset-cache entry too small for the observation");
   AL(reset_cache, (size_t)Nn * RC_PITCH); AL(reset_cache_flag, Nn);

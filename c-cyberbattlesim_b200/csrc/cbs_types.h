@@ -139,6 +139,7 @@ struct Params {  // configuration, by value
   int always_encode;   // defender or precise_graph_encoding: every step re-encodes (compressed:401,455-462)
   int ocap;            // capacity of owned_raw
   int mpitch;          // uint32 words per env in State::masks (N_MASKS * words rounded up to 16)
+  int precise_graph;       // precise_graph_encoding (compressed:455-462)
   int precise_positions;   // precise_action_space_positions (compressed:419-427,498-506): table rows are refreshed, see build_table
   int metric;              // enum Metric; != METRIC_COSINE: k_decode_metric.cu decodes, the transition runs as its own launch
   double event_prob;       // defender == 2: random_event_probability
@@ -159,6 +160,8 @@ struct State {  // mutable, device pointers
   uint8_t* reimage_left; // [B][ncap]  node_reimaging_progress (static_defender_actions.py:23)
   uint8_t* pair_opos;    // [B][ncap*ncap]  position of the source in owned_raw when the pair entered the table (tie order)
   // precise_action_space_positions only (1-byte dummy otherwise):
+  uint32_t* changed;     // [B][words]  defender + precise_action_space_positions: nodes the defender re-imaged in the last step
+                         //             (env.changed_nodes, cyberbattle_env.py:418: the refresh seeds of compressed:423-427)
   uint8_t* pair_epoch;   // [B][ncap*ncap]  slot at which the pair FIRST entered the table: its place in the insertion order;
                          //                 pair_slot then names the snapshot its rows currently carry (refreshed over time)
   // events defender only: per node { running services, incoming BLOCK, outgoing BLOCK, unused } bit sets over the node's

@@ -346,8 +346,15 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   uint32_t reach[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
   if (PRECISE && refresh) {
     const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
-    reach[sl.x >> 5] |= 1u << (sl.x & 31);
-    reach[sl.y >> 5] |= 1u << (sl.y & 31);
+    // compressed:419-427: around the action's nodes when its desired outcome re-encodes by itself (or precise_graph_encoding),
+    // else (the re-encode is the defender's doing) around the nodes the defender changed in this step — possibly none
+    const bool own_doing = sl.w == K_LATERAL || sl.w == K_DOS || sl.w == K_RECON || P.precise_graph || !P.defender;
+    if (own_doing) {
+      reach[sl.x >> 5] |= 1u << (sl.x & 31);
+      reach[sl.y >> 5] |= 1u << (sl.y & 31);
+    } else {
+      for (int w = 0; w < P.words; ++w) reach[w] = S.changed[(size_t)b * P.words + w];
+    }
     const int E = scalar(S, P, S_N_EDGES, b);
     const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
     const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;

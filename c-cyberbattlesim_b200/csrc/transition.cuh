@@ -86,6 +86,7 @@ __device__ __forceinline__ uint32_t philox_word(uint64_t key, uint64_t env, uint
 // would copy them to the caller's stack on the hot path.
 struct DefenderCtx {
   uint8_t *left, *raw, *oo;                 // this env's reimage_left / owned_raw / owned_order rows
+  uint32_t* changed;                        // this env's [words] "re-imaged in this step" set, or nullptr
   int32_t *n_raw, *n_owned, *n_reimaged;    // this env's scalars
   const int32_t* def_nodes;                 // this env's override rows (or nullptr)
   const float* def_uniforms;
@@ -97,6 +98,7 @@ struct DefenderCtx {
 };
 __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int stepcount, int total_steps, bool check_reown) {
   bool event = false;
+  if (P.changed) for (int w = 0; w < P.words; ++w) P.changed[w] = 0u;
   uint8_t* left = P.left;
   uint8_t* raw = P.raw;
   int32_t& n_raw = *P.n_raw;
@@ -133,6 +135,7 @@ __device__ __noinline__ bool defender_step(DefenderCtx P, EnvBits M, int N, int 
         M.clr(M_OWNED, n);
         M.set(M_IMAGING, n);
         M.set(M_OWN_STALE, n);                    // last_reimaging = now > last_owned_at
+        if (P.changed) P.changed[n >> 5] |= 1u << (n & 31);
         ++reimaged;
         int k = 0;                                // owned_nodes.remove(node): first occurrence (cyberbattle_env.py:425)
         while (k < n_raw && raw[k] != n) ++k;
@@ -533,6 +536,7 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
     D.left = S.reimage_left + (size_t)b * P.ncap;
     D.raw = S.owned_raw + (size_t)b * P.ocap;
     D.oo = S.owned_order + (size_t)b * P.ncap;
+    D.changed = P.precise_positions ? S.changed + (size_t)b * P.words : nullptr;
     D.n_raw = &SC(S_N_OWNED_RAW); D.n_owned = &SC(S_N_OWNED); D.n_reimaged = &SC(S_N_REIMAGED);
     D.def_nodes = S.def_nodes ? S.def_nodes + (size_t)b * P.scan_capacity : nullptr;
     D.def_uniforms = S.def_uniforms ? S.def_uniforms + (size_t)b * P.scan_capacity : nullptr;

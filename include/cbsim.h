@@ -90,7 +90,9 @@ typedef struct {
   double detect_probability;
   /* compressed:86,419-427,498-506: at every table-maintaining encode of a step, the rows of the (source, target) pairs
    * from which the action's source or target node can be reached in the visible graph are overwritten with the current
-   * node embeddings (their place in the table's insertion order is kept).  Not available with a static defender. */
+   * node embeddings (their place in the table's insertion order is kept).  Under the re-imaging defender a step whose desired
+   * outcome does not re-encode by itself refreshes around the nodes the defender re-imaged in that step (:423-427); with the
+   * events defender the reference itself raises (nx.has_path on nodes outside the visible graph), so that pair is rejected. */
   int32_t precise_action_space_positions;
   /* compressed:82,570-590 `distance_metric` of find_closest_action_embedding: 0 'cosine' (scipy cdist, the reference's default),
    * 1 'l1', 2 'l2', 3 'inf' (np.linalg.norm(action - rows, ord, axis=1), :571-576).  Anything else is rejected like the
