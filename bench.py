@@ -663,6 +663,9 @@ def main():
                     "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9},
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
+            # decodes of the whole run whose float64 winner sat in the outer half of the float32 re-score margin (0 = the margin
+            # was never under pressure)
+            "decode_margin_edge": env.margin_edge_count(),
         }
         env.close()
         if world == 1 and not args.no_vecenv:

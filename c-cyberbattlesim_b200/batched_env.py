@@ -360,6 +360,10 @@ class BatchedCyberBattleEnv:
         over the node's service slots; ``cached`` = as held by the node's feature vector in the visible graph."""
         return self.read(L.F_EV_X if cached else L.F_EV_CUR, np.uint16, (self.num_envs, self.ncap, 4))
 
+    def margin_edge_count(self) -> int:
+        """Decodes so far whose float64 winner sat in the outer half of the float32 re-score margin (see CBS_F_MARGIN_EDGE)."""
+        return int(self.read(L.F_MARGIN_EDGE, np.int32, (1,))[0])
+
     def divergence_count(self) -> int:
         """Env-steps so far at which the reference itself would have raised (see CBS_F_DIVERGENCE in include/cbsim.h)."""
         return int(self.read(L.F_DIVERGENCE, np.int32, (1,))[0])

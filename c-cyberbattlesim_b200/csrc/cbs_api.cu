@@ -100,7 +100,7 @@ namespace cbs { extern long long* g_sel_trace; extern long long* g_obs_trace; }
 static thread_local std::string g_create_error;
 static const char* const kErrflagMessage =
     "device reported capacity/domain error %d (1 snapshot slots, 2 edges, 3 empty action table, 4 worklist, 5 owned-node list, "
-    "6 sub-sampled action table, 7 removal of an absent owned node (the reference raises ValueError there), 9 tensor-core pipeline timeout)";
+    "6 sub-sampled action table, 8 node embedding beyond the half-precision range, 7 removal of an absent owned node (the reference raises ValueError there), 9 tensor-core pipeline timeout)";
 
 struct cbs_handle {
   cbs_config cfg{};
@@ -424,7 +424,7 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   AL(edge_src, B * P.ecap); AL(edge_dst, B * P.ecap); AL(edge_cnt, B * P.ecap);
   AL(edge_sum, B * P.ecap * NN_CH); AL(edge_m, B * P.ecap * NN_CH);
   AL(obs, B * P.obs_dim); AL(term_obs, B * P.obs_dim); AL(sel, B * 4); AL(dist, B); AL(reward64, B);
-  AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 2);
+  AL(last_stats, B * 14); AL(accum, N_ACCUM); AL(vt, B * h->vt_stride); AL(errflag, 4);
   AL(scratch, P.ncap > CBS_OBS_SMEM_NODES ? B * 2 * P.ncap * NODE_EMB : 1);   // only graphs beyond the shared-memory buffers use it
   AL(sub_rows, P.subset_k ? B * SUB_CLASSES * P.subset_k : 1); AL(sub_meta, P.subset_k ? B * SUB_META : 1);
   AL(sub_alive, (P.subset_k && P.precise_positions) ? B * P.ncap * P.ncap * (SUB_MAX_ROWS_PER_PAIR / 32) : 1);
@@ -769,6 +769,7 @@ static int field_ptr(cbs_handle* h, int32_t field, void** p, int64_t* bytes) {
     case CBS_F_ERRFLAG: *p = S.errflag; *bytes = 4; break;
     case CBS_F_SEL: *p = S.sel; *bytes = B * 16; break;
     case CBS_F_DIVERGENCE: *p = S.errflag + 1; *bytes = 4; break;
+    case CBS_F_MARGIN_EDGE: *p = S.errflag + 2; *bytes = 4; break;
     case CBS_F_EV_CUR: *p = S.ev_cur; *bytes = P.defender == 2 ? B * P.ncap * 8 : 2; break;
     case CBS_F_EV_X: *p = S.ev_x; *bytes = P.defender == 2 ? B * P.ncap * 8 : 2; break;
     case CBS_F_VT: *p = S.vt; *bytes = B * h->vt_stride * 4; break;

@@ -191,7 +191,8 @@ struct State {  // mutable, device pointers
   float* scratch;        // [B][2][ncap][64] encode scratch when ncap > 32
   float* reset_cache;          // [total scenario nodes][RC_PITCH], filled by the first reset from each (scenario, starter)
   int32_t* reset_cache_flag;   // [total scenario nodes] 1 = entry valid
-  int32_t* errflag;      // [2]  [0] capacity / domain error code (cbs_sync), [1] steps at which the reference itself would have raised (CBS_F_DIVERGENCE)
+  int32_t* errflag;      // [4]  [0] capacity / domain error code (cbs_sync), [1] steps at which the reference itself would have raised
+                         //      (CBS_F_DIVERGENCE), [2] decodes whose winner sat in the outer half of the re-score margin (CBS_F_MARGIN_EDGE)
   int32_t* worklist;     // [OBS_CLASSES][B] envs whose step needs graph work, by cost class
   int32_t* work_ctr;     // [1] finished-warp counter, [2] next item (dynamic scheduling), [4 .. 4 + OBS_CLASSES) class list lengths
   int32_t* work_est;     // [B] candidate rows in the env's action table (decode cost estimate)

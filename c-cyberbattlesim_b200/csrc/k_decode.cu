@@ -178,6 +178,7 @@ struct Best {
   unsigned long long key;
   int s, t, r;
   uint32_t packed;
+  float score32;      // the float32 scan score of the row that won the float64 re-score (margin diagnostics)
 };
 
 // re-score the pending candidates that are still within `margin` of run_max; empties the list
@@ -192,7 +193,7 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
     // np.argmin: the first NaN wins if any distance is NaN, else the first minimum (insertion order)
     const bool dn = d != d, bn = best.d != best.d;
     const bool better = best.r < 0 || (dn ? (!bn || key < best.key) : (!bn && (d < best.d || (d == best.d && key < best.key))));
-    if (better) { best.d = d; best.key = key; best.s = s; best.t = t; best.r = r; best.packed = sh.c_packed[i]; }
+    if (better) { best.d = d; best.key = key; best.s = s; best.t = t; best.r = r; best.packed = sh.c_packed[i]; best.score32 = sh.c_score[i]; }
   }
   ncand = 0;
 }
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   const int interest = is_node_goal(P) ? T.sc_interest[scalar(S, P, S_SCENARIO, b)] : -1;
 
   float run_max = -INFINITY;
-  Best best{INFINITY, ~0ull, 0, 0, -1, 0u};
+  Best best{INFINITY, ~0ull, 0, 0, -1, 0u, 0.f};
   int ncand = 0, n_rows = 0, n_live = 0, n_exact = 0;
 
   const int combos = SUBSET ? 0 : n_owned * n_disc;
@@ -528,6 +529,9 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     if (best.r >= 0) {
       out = make_int4(best.s, best.t, T.row_ulocal[best.r], (int)((best.packed >> 20) & 15));
       d = best.d;
+      // margin diagnostics: the float64 winner's float32 score sat in the outer half of the re-score window, i.e. the scan's
+      // error (TF32 operand rounding of the contraction + half-precision snapshot rows) used more than half of the margin
+      if (run_max - best.score32 > 0.5f * margin_s) atomicAdd(S.errflag + 2, 1);
     } else {
       atomicExch(S.errflag, 3);   // empty action table: outside the reference's domain (cdist would raise)
     }

@@ -136,6 +136,9 @@ __device__ void edge_update(const Tables& T, const Params& P, const State& S, in
 }
 
 // ---- encode (compressed:249-306) : returns node embeddings z in W.y (position-major) and writes S.obs ----
+// EV: the ExternalRandomEvents defender is configured (compile-time: its feature corrections sit inside the unrolled hot loops,
+// and the default instance must not carry their code)
+template <bool EV>
 __device__ void encode_env(const Tables& T, const Params& P, const State& S, const SharedWeights& SW, WarpScratch& W, int b,
                            int lane) {
   const int sc = scalar(S, P, S_SCENARIO, b);
@@ -188,7 +191,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
         a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
         a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
       }
-      if (P.defender == 2 && vis != 0.f) {
+      if (EV && vis != 0.f) {
         const uint16_t* evx = S.ev_x + ((size_t)b * P.ncap + order[i]) * 4;
         const uint16_t* ini = T.nd_ev_init + (size_t)(node_off + order[i]) * 4;
         a0 += ev_delta(T.ev_proj, evx, ini, 17, c0);
@@ -212,7 +215,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     float vis, x[NUM_DYN];
     node_dyn(W.dynb[is], W.xst[is], vis, x);
     const float* ns = T.node_static + ((size_t)(node_off + js) * 2 + (vis != 0.f ? 1 : 0)) * ROW;   // visible / not-visible variant
-    const bool evd = P.defender == 2 && vis != 0.f;
+    const bool evd = EV && vis != 0.f;
     const uint16_t* evx = evd ? S.ev_x + ((size_t)b * P.ncap + js) * 4 : nullptr;
     const uint16_t* ini = evd ? T.nd_ev_init + (size_t)(node_off + js) * 4 : nullptr;
     const bool ev_any = evd && (((evx[0] ^ ini[0]) | (evx[1] ^ ini[1]) | (evx[2] ^ ini[2])) & 0x3FF) != 0;
@@ -227,7 +230,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
         t0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c0], t0);
         t1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c1], t1);
       }
-      if (ev_any) { t0 += ev_delta(T.ev_proj, evx, ini, k, c0); t1 += ev_delta(T.ev_proj, evx, ini, k, c1); }
+      if (EV && ev_any) { t0 += ev_delta(T.ev_proj, evx, ini, k, c0); t1 += ev_delta(T.ev_proj, evx, ini, k, c1); }
       m0 = fmaf(hk, t0, m0);
       m1 = fmaf(hk, t1, m1);
     }
@@ -435,6 +438,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
     const float2 z = reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane];   // channels 2*lane, 2*lane+1
     reinterpret_cast<float2*>(zh + node * NODE_EMB)[lane] = z;
     zh16[node * (NODE_EMB / 2) + lane] = __floats2half2_rn(z.x, z.y);
+    if (fmaxf(fabsf(z.x), fabsf(z.y)) > 65504.f) atomicExch(S.errflag, 8);     // beyond half precision: the decode scan reads these copies
     const float n2 = warp_sum(z.x * z.x + z.y * z.y);
     if (lane == 0) zn[node] = n2;
   }
@@ -726,7 +730,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       int keep = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
       if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
       if (flags & FL_REENCODE) {
-        encode_env(T, P, S, SW, W, b, lane);
+        if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
         if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true);
         else build_table<false>(T, P, S, W, b, lane, false);
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       if (P.subset_k || !reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
-        encode_env(T, P, S, SW, W, b, lane);
+        if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
         if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
         else build_table<false>(T, P, S, W, b, lane, false);
         if (!P.subset_k) reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);

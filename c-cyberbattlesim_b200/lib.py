@@ -77,7 +77,7 @@ SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cb
 
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
-    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE, F_EV_CUR, F_EV_X = range(20)
+    F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE, F_EV_CUR, F_EV_X, F_MARGIN_EDGE = range(21)
 NUM_SCALARS, NUM_ACCUM = 25, 20
 # per-env scalar record (csrc/cbs_types.h enum Scalar): four 32-byte sectors — rewritten every step | list lengths and
 # counters | episode constants | misc

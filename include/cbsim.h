@@ -321,6 +321,8 @@ typedef enum {
   CBS_F_EV_CUR = 18,      /* uint16 [B][max_nodes][4] events defender: per node { running services, incoming BLOCK, outgoing BLOCK, - } bit
                              sets over the node's service slots */
   CBS_F_EV_X = 19,        /* uint16 [B][max_nodes][4] the same as cached in the node's feature vector of the visible graph */
+  CBS_F_MARGIN_EDGE = 20, /* int32 [1] decodes whose float64 winner had a float32 scan score in the outer half of the re-score margin
+                             (cbs_config.decode_margin): 0 in every test and bench run; non-zero = widen the margin */
   CBS_F_DIVERGENCE = 17   /* int32 [1] number of env-steps at which the reference itself raises and this library goes on: the re-imaging
                              defender detecting a persistent node in the very step it comes back (owned_nodes.remove of an absent
                              node, cyberbattle_env.py:425 -> ValueError); the removal is a no-op here */

@@ -52,8 +52,12 @@ def test_cuda_replays_reference_trace(name, gemm, golden_dir):
     rec, consistent = replay(env, case["actions"], case["uniforms"], case["spec"].num_nodes, check_env=check_env,
                              follower=follower, policy_rows=case["policy_rows"], defender_draws=case["defender_draws"],
                              lockstep_batch=not subset)
+    edge = env.margin_edge_count()
     env.close()
     assert consistent, "envs fed identical inputs diverged"
+    # no decode came near the edge of the float32 re-score margin (k_decode.cu: the float64 winner's float32 score never sat in
+    # the outer half of the window), i.e. the scan's TF32 / half-precision error stayed below half the margin on this trace
+    assert edge == 0, f"{edge} decodes in the outer half of the re-score margin"
     report = tr.compare(rec, case["trace"], rtol=1e-5, atol=2e-5, label=f"{name}/gemm{gemm}")
     print(name, report, "near-tie flips:", follower.flips, "oracle-vs-record flips:", follower.oracle_flips, "max gap", follower.max_gap)
     # Every flip was individually verified as a near-tie of the oracle's own float64 distances (TieFollower asserts the gap per

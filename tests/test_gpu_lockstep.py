@@ -198,6 +198,8 @@ def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
         assert tables.vemb32.shape[0] > 256
     acc = env.stat_accum()
     assert acc["episodes"] == sum(episodes)
+    if cfg.distance_metric == "cosine":
+        assert env.margin_edge_count() == 0, "a decode came near the edge of the float32 re-score margin"
     if cfg.static_defender_agent == "reimage":
         assert acc["stat9"] > 0 and acc["lost"] > 0, "the defender never re-imaged a node / never evicted the attacker"
     if cfg.static_defender_agent == "events":

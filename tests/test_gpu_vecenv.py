@@ -187,3 +187,52 @@ def test_state_view_and_episode_stats_calls():
     assert env.lib.cbs_episode_stats(env._h, stats.ctypes.data_as(ct.c_void_p)) == 0
     assert np.array_equal(stats, env.last_stats()) and stats[:, 4].max() == 10
     env.close()
+
+
+def test_info_dicts_follow_on_device_scenario_switches():
+    """with switch_interval the device draws a new scenario at resets; the info dicts must name nodes / vulnerabilities
+    of the scenario in force during the step (carried in the info row), not of the env's initial assignment."""
+    import ccbs_b200 as cb
+    from ccbs_b200 import lib as L
+    from ccbs_b200.vec_env import CyberBattleVecEnv
+    specs = [cb.synthetic_spec(900 + k, 7 + 2 * k) for k in range(4)]
+    for k, sp in enumerate(specs):                       # node ids that tell the scenarios apart
+        for nd in sp.nodes:
+            nd.node_id = f"s{k}:{nd.node_id}"
+    B = 16
+    env = cb.BatchedCyberBattleEnv(specs, cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=B, seed=9, switch_interval=1,
+                                   scenario_of_env=np.zeros(B, np.int32))
+    venv = CyberBattleVecEnv(env, lazy_infos=False)
+    venv.reset()
+    rng = np.random.default_rng(1)
+    seen = set()
+    for t in range(150):
+        before = env.scalars()[L.S_SCENARIO].copy()      # the scenario every env is in while this step runs
+        _, _, dones, infos = venv.step(rng.uniform(-4, 4, size=(B, 905)).astype(np.float32))
+        for b in range(B):
+            assert infos[b]["source_node"].startswith(f"s{before[b]}:"), (t, b, infos[b]["source_node"], before[b])
+            assert infos[b]["target_node"].startswith(f"s{before[b]}:")
+            seen.add(int(before[b]))
+    assert len(seen) >= 3, "the device never switched scenarios: test too short"
+    venv.close()
+
+
+def test_raising_the_cutoffs_beyond_the_buffers_is_refused():
+    """cbs_set_cutoffs after load must not let episodes outgrow the snapshot / edge buffers silently."""
+    import ccbs_b200 as cb
+    from ccbs_b200.batched_env import CbsError
+    spec = cb.synthetic_spec(31, 20)
+    env = cb.BatchedCyberBattleEnv([spec], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=4, seed=4)
+    env.set_proportional_cutoff_coefficient(0.5)         # shorter episodes always fit
+    with pytest.raises(CbsError, match="max_slots"):
+        env.set_proportional_cutoff_coefficient(10)      # the reference's evaluation setting (utils/test_utils.py)
+    env.close()
+    big = cb.BatchedCyberBattleEnv([spec], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=4, seed=4, max_slots=39, max_edges=200)
+    big.set_proportional_cutoff_coefficient(10)          # sized for it at construction: accepted
+    big.reset()
+    rng = np.random.default_rng(0)
+    import torch
+    for _ in range(60):
+        big.step(torch.from_numpy(rng.uniform(-4, 4, size=(4, 905)).astype(np.float32)).to(big.device), None)
+    big.sync()                                           # no capacity flag
+    big.close()
