@@ -482,7 +482,12 @@ def main():
     sampler.armed = True
     # bring the episodes to their steady-state mix before anything is timed (a window that starts right after a cold reset
     # of all envs holds no episode end and no in-place reset), then the W warm-up steps of the contract
+    # (all envs start together and the proportional cut-off ends most episodes after the same ~32 steps: without the staggered
+    # resets below the batch stays in phase and a 20-step window either contains the whole burst of episode ends or none of it)
+    stagger = torch.arange(B, device=dev) % 32
     for i in range(args.presteps):
+        if i < 32:
+            env.reset((stagger == i).to(torch.uint8))
         env.step(ring[i % R], None, want_info=False)
     env.sync()
     env.reset_stat_accum()

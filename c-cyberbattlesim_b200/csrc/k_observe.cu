@@ -732,8 +732,12 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       if (flags & FL_REENCODE) {
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
-        if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true);
-        else build_table<false>(T, P, S, W, b, lane, false);
+        // (an env that finished in this step drops its action table at the reset that follows: only the sub-sampled table is
+        // still maintained, because every create_continuous_action_space advances the env's balance counter)
+        if (!(flags & FL_FINISHED_THIS_STEP) || P.subset_k) {
+          if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true);
+          else build_table<false>(T, P, S, W, b, lane, false);
+        }
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
         keep &= ~FL_DIRTY;
         if (is_node_goal(P)) keep |= FL_INTEREST_IN_GRAPH;
