@@ -211,7 +211,7 @@ class BatchedCyberBattleEnv:
         Philox) without a host round trip per step; every step's decoded action, outcome, reward, distance, state records and
         observation of the envs in ``log_envs`` (default: all) go to a device log, returned as a dict of numpy arrays
         [T, n_logged, ...] after ONE synchronisation.  Keys: sel, code, done, truncated, reason, step_count, episode, reward,
-        dist, masks (uint32 [T, n, N_MASKS, words]), disc_order, owned_order, counters, n_disc, n_owned, obs, reset_obs,
+        dist, masks (uint32 [T, n, N_MASKS, words]), disc_order, owned_order, counters, n_disc, n_owned, scenario, obs, reset_obs,
         reset_masks, stats.  ``forced`` = {step: (sel[4], distance)}: at those steps EVERY env takes that decoded action instead
         of its own (parity tests following a verified near-tie)."""
         T = int(actions.shape[0])
@@ -254,7 +254,7 @@ class BatchedCyberBattleEnv:
         unpack = lambda m: np.ascontiguousarray(m.view(np.uint32)[..., :C.N_MASKS * w].reshape(T, n, C.N_MASKS, w))   # noqa: E731
         out["masks"], out["reset_masks"] = unpack(out["masks"]), unpack(out["reset_masks"])
         out["code"], flags, out["step_count"], out["episode"] = meta[..., 0], meta[..., 1], meta[..., 2], meta[..., 3]
-        out["done"], out["truncated"], out["reason"] = flags & 1, (flags >> 1) & 1, (flags >> 2) & 3
+        out["done"], out["truncated"], out["reason"], out["scenario"] = flags & 1, (flags >> 1) & 1, (flags >> 2) & 3, flags >> 8
         out["n_disc"], out["n_owned"] = cnt[..., 7] & 0xFFFF, cnt[..., 7] >> 16
         out["counters"] = cnt[..., :7]
         return out

@@ -47,7 +47,7 @@ __global__ void replay_log_kernel(Params P, State S, cbs_replay_log L, int t, in
     const int flags = sc(S_FLAGS);
     if (lane < 4) {
       if (L.sel) L.sel[row * 4 + lane] = S.sel[(size_t)b * 4 + lane];
-      if (L.meta) L.meta[row * 4 + lane] = lane == 0 ? sc(S_OUTCOME) : (lane == 1 ? (flags & 15) : (lane == 2 ? sc(S_STEPCOUNT) : sc(S_EPISODES)));
+      if (L.meta) L.meta[row * 4 + lane] = lane == 0 ? sc(S_OUTCOME) : (lane == 1 ? ((flags & 15) | ((sc(S_SCST) >> 8) << 8)) : (lane == 2 ? sc(S_STEPCOUNT) : sc(S_EPISODES)));
     }
     if (lane == 0) {
       if (L.reward) L.reward[row] = S.reward64[b];

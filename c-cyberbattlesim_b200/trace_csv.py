@@ -2,7 +2,9 @@
 (_env/cyberbattle_env_switch.py:223-279: the variant without embeddings).
 
 The reference writes one row per step from Python object state; here the integer state of the traced envs is read back from
-the device before and after each step (a debugging aid: it synchronises, keep the traced subset small).  Node detail
+the device before and after each step (a debugging aid: it synchronises, keep the traced subset small).  :func:`write_replay_csv`
+writes the same rows for T steps from the device log of ``BatchedCyberBattleEnv.replay`` (``cbs_replay``): one synchronisation
+for the whole trace.  Node detail
 strings follow get_str_info (switch.py:307-334) character for character (tests/test_switch_rule.py compares them with the
 reference's own on a scripted-attacker trace); "Iteration" is the 0-based step of the episode (the reference writes the row before
 it increments steps_in_current_episode, switch.py:124-134).  Deliberate differences: the two outcome columns hold class names
@@ -98,3 +100,65 @@ class TraceCsvWriter:
 
     def close(self):
         self.file.close()
+
+
+def write_replay_csv(env, log: dict, path: str, env_ids: Sequence[int] = (0,), first_env: int = 0):
+    """The rows :class:`TraceCsvWriter` writes step by step, for all T steps of a ``BatchedCyberBattleEnv.replay`` log (the device
+    wrote every step's records into it; nothing is read back per step).  ``env_ids`` index the envs of the batch, ``first_env`` is
+    the first env the log covers.  The replay must have started right after a reset (episode starts are recovered from the
+    logged post-reset masks: a fresh episode's lists are [starter]).  Row for row identical to the step-by-step writer."""
+    t = env.tables
+    W = t.words
+    helper = TraceCsvWriter.__new__(TraceCsvWriter)
+    helper.env = env
+    T = log["sel"].shape[0]
+
+    def snap(masks_e, disc, owned, nd, no, sc, episode):      # the snapshot layout TraceCsvWriter's helpers read, one env at index 0
+        scal = np.zeros((L.NUM_SCALARS, 1), np.int64)
+        scal[L.S_SCENARIO, 0], scal[L.S_N_DISC, 0], scal[L.S_N_OWNED, 0], scal[L.S_EPISODES, 0] = sc, nd, no, episode
+        return dict(masks=np.ascontiguousarray(masks_e.reshape(C.N_MASKS, W, 1)), scal=scal, disc=disc[None, :], owned=owned[None, :])
+
+    def fresh(masks_e, sc, episode):                          # state right after a reset: the starter alone
+        own = masks_e[C.M_OWNED]
+        starter = next(32 * w + int(own[w]).bit_length() - 1 for w in range(W) if own[w])
+        lst = np.zeros(env.ncap, np.uint8)
+        lst[0] = starter
+        return snap(masks_e, lst, lst, 1, 1, sc, episode)
+
+    with open(path, "w", newline="") as f:
+        wr = csv.writer(f)
+        wr.writerow(HEADER)
+        for b in env_ids:
+            e = int(b) - first_env
+            edges = []
+            before = None
+            for k in range(T):
+                sc, ep = int(log["scenario"][k, e]), int(log["episode"][k, e])
+                if before is None:
+                    # first step of the log: the pre-step state is a fresh episode's (has_data / visible come from the scenario,
+                    # the starter is the head of the step's own owned list)
+                    m0 = np.zeros((C.N_MASKS, W), np.uint32)
+                    m0[C.M_HAS_DATA], m0[C.M_VISIBLE] = t.sc_init_has_data[sc], t.sc_init_visible[sc]
+                    starter = int(log["owned_order"][k, e, 0])
+                    bit = np.uint32(1 << (starter % 32))
+                    laa = int(t.nd_level_at_access[t.sc_node_off[sc] + starter])
+                    for plane in (C.M_OWNED, C.M_DISCOVERED) + ((C.M_PRIV_USER,) if laa >= 1 else ()) + ((C.M_PRIV_ROOT,) if laa == 3 else ()):
+                        m0[plane, starter // 32] |= bit
+                    before = fresh(m0, sc, ep)
+                s, tg, u, kind = (int(x) for x in log["sel"][k, e])
+                code, finished = int(log["code"][k, e]), bool(log["done"][k, e] or log["truncated"][k, e])
+                after = snap(log["masks"][k, e], log["disc_order"][k, e], log["owned_order"][k, e], int(log["n_disc"][k, e]),
+                             int(log["n_owned"][k, e]), sc, ep)
+                _, ids, disc, owned, alive = helper._lists(before, 0)
+                nxt = fresh(log["reset_masks"][k, e], int(log["scenario"][k + 1, e]) if k + 1 < T else sc, ep + 1) if finished else after
+                same = int(nxt["scal"][L.S_SCENARIO, 0]) == sc
+                reward = float(np.float32(log["reward"][k, e]))
+                if reward > 0 and not finished:
+                    edges.append(f"{ids[s]}:{ids[tg]}:{t.vuln_ids[sc][u]}")
+                wr.writerow([sc, ep, int(log["step_count"][k, e]) - 1, disc, owned, alive, ids[s], ids[tg], t.vuln_ids[sc][u],
+                             C.KIND_NAMES[kind], reward, C.KIND_NAMES[code] if code < 16 else C.OC_NAMES.get(code), finished,
+                             helper._node_str(nxt, 0, s) if same else "", helper._node_str(nxt, 0, tg) if same else "",
+                             helper._node_str(before, 0, s), helper._node_str(before, 0, tg), ",".join(edges)])
+                if finished:
+                    edges = []
+                before = nxt

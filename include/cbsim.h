@@ -263,7 +263,7 @@ int cbs_profile_step(cbs_handle* h, const float* actions_dev, const float* unifo
  * uniforms_dev [T][num_envs] float32 or NULL (Philox).  Starters come from cbs_set_starter_queue (or Philox).  The log covers envs
  * [first_env, first_env + num_logged); every pointer is device memory, [T][num_logged][...], and may be NULL to skip the field:
  *   after the transition, before the observe (i.e. before an in-place reset):
- *     sel int32[4] · meta int32[4] = { obtained outcome code, flags (bit0 done, bit1 truncated, bits2-3 end reason), step count,
+ *     sel int32[4] · meta int32[4] = { obtained outcome code, flags (bit0 done, bit1 truncated, bits2-3 end reason, bits 8.. scenario in force), step count,
  *     episodes finished before this step } · reward, dist float64 · masks uint32[mask_pitch] · disc_order uint8[max_nodes] ·
  *     owned_order uint8[owned_len] (owned_len = 2 * max_nodes under a static defender: env.owned_nodes itself, else max_nodes) ·
  *     counters int32[8] = { stepcount, num_iterations, discovered_amount, ownable, discoverable, disruptable, discoverable_amount,

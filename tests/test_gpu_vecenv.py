@@ -82,6 +82,24 @@ def test_csv_trace_writer(tmp_path):
     assert {r[11] for r in rows[1:]} & {"Reconnaissance", "RepeatedResult", "InvalidAction", "Discovery", "NoNeededAction"}
     assert "status : MachineStatus.Running" in rows[1][15]
     env.close()
+    # the same rows from cbs_replay's device log: one synchronisation for the whole trace instead of two state read-backs per step
+    from ccbs_b200.trace_csv import write_replay_csv
+    env = cb.BatchedCyberBattleEnv([cb.synthetic_spec(11, 9)], cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=6, seed=2)
+    env.reset()
+    g.manual_seed(0)
+    actions = torch.stack([torch.rand(6, 905, device="cuda", generator=g) * 8 - 4 for _ in range(25)]).contiguous()
+    log = env.replay(actions, None)
+    path2 = tmp_path / "logs_replay.csv"
+    write_replay_csv(env, log, str(path2), env_ids=(0, 4))
+    rows2 = list(csv.reader(open(path2)))
+    by_env = lambda rr: sorted(rr[1:], key=lambda r: 0)      # noqa: E731  (the step-by-step writer interleaves the envs, this one does not)
+    assert rows2[0] == HEADER and len(rows2) == len(rows)
+    step_rows = {0: rows[1::2], 4: rows[2::2]}
+    replay_rows = {0: rows2[1:26], 4: rows2[26:51]}
+    for b in (0, 4):
+        for k, (r1, r2) in enumerate(zip(step_rows[b], replay_rows[b])):
+            assert r1 == r2, (b, k, [(h, x, y) for h, x, y in zip(HEADER, r1, r2) if x != y])
+    env.close()
 
 
 def test_device_vec_normalize_runs():
