@@ -589,6 +589,22 @@ def main():
     torch.cuda.synchronize()
     h2d_ms = ev0.elapsed_time(ev1) / 20
     del d_probe
+    # the same probe with ALL ranks copying at once: what the host's memory system / PCIe root complexes deliver per GPU when
+    # every rank streams its action batch (the end-to-end leg's situation at N > 1)
+    h2d_all = [h2d_ms]
+    if world > 1:
+        d_probe = torch.empty(B, C.ACTION_DIM, dtype=torch.float32, device=dev)
+        barrier()
+        ev0.record()
+        for k in range(20):
+            d_probe.copy_(h_ring[k % 2], non_blocking=True)
+        ev1.record()
+        torch.cuda.synchronize()
+        mine = torch.tensor([ev0.elapsed_time(ev1) / 20], dtype=torch.float64, device=dev)
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        h2d_all = [float(x.item()) for x in gathered]
+        del d_probe
     e2e_single = time_host_steps(env.step_host)
     from ccbs_b200.host_pipeline import ShardedHostEnv
     e2e_api = f"ShardedHostEnv.step_host: {args.host_shards} handles x cbs_step_host_async, pinned host buffers"
@@ -665,7 +681,11 @@ def main():
                     "steps": e2e_steps, "api": e2e_api,
                     "gpu_launches_per_step": e2e_launches_per_step, "single_handle_value": e2e_single,
                     # the bare pinned copy of one rank's action batch, timed alone: what the link delivered on this box
-                    "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9},
+                    "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
+                    # per rank, all ranks copying concurrently: the ceiling of the end-to-end leg at N GPUs is
+                    # total_envs / max(copy time) — host memory / PCIe contention, not the kernels
+                    "h2d_gbs_per_rank_concurrent": [round(h2d / (m * 1e-3) / 1e9, 2) for m in h2d_all],
+                    "copy_bound_value": total_envs / (max(h2d_all) * 1e-3)},
             "roofline": roof, "cpu_baseline": cpu,
             "episodes": {k: acc[k] for k in ("episodes", "return_sum", "length_sum", "wins", "lost", "cutoff")},
             # decodes of the whole run whose float64 winner sat in the outer half of the float32 re-score margin (0 = the margin
