@@ -31,9 +31,6 @@ class BatchedCyberBattleEnv:
                  tables: Optional[ScenarioTables] = None, interest_nodes: Optional[Sequence[int]] = None,
                  gae_tables=None, **cfg_overrides):
         self.cfg = cfg or EnvConfig()
-        if getattr(self.cfg, "sample_subset_samples", 0) and self.cfg.distance_metric != "cosine":
-            raise NotImplementedError("sample_subset_samples together with the l1 / l2 / inf decode metrics is not implemented "
-                                      "(the sub-sampled table is scanned by the cosine decode only)")
         if getattr(self.cfg, "static_defender_agent", None) == "events":
             from .scenario import check_events_compatible
             for sp in (tables.specs if tables is not None else specs):

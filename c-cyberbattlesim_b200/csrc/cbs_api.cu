@@ -290,8 +290,6 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
         return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples: node %d has more than %d candidate rows", n, SUB_MAX_ROWS_PER_PAIR);
     for (int s = 0; s < t->num_scenarios; ++s)
       if (t->sc_num_uvuln[s] > 4096) return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples: scenario %d has more than 4096 vulnerabilities", s);
-    if (h->cfg.distance_metric != METRIC_COSINE)
-      return fail(h, CBS_ERR_INVALID_ARG, "sample_subset_samples is implemented for the cosine decode only");
   }
   CK(h, cudaSetDevice(h->cfg.device));
   Tables& T = h->T;

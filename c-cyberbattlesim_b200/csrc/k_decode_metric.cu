@@ -12,6 +12,7 @@
 // the summation order differs from numpy (<= 1e-15 relative); ties and NaN follow np.argmin (first NaN, else first minimum in
 // insertion order).  The non-default metrics run decode -> transition as two launches (no fused variant).
 #include "transition.cuh"
+#include "subset.cuh"
 
 namespace cbs {
 
@@ -97,6 +98,7 @@ struct MetWarp {
   int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
   uint32_t p_key[32];         // insertion epoch << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
   uint8_t oorder[MAX_NODES], dorder[MAX_NODES];
+  uint8_t opos[MAX_NODES], dpos[MAX_NODES];   // sample_subset_samples: node -> position in the two order lists (tie order)
 };
 
 // np.argmin over distances in insertion order: the first NaN wins if there is one, else the first minimum
@@ -147,7 +149,55 @@ __global__ void __launch_bounds__(MET_THREADS) metric_select_kernel(Tables T, Pa
     bool have = false;
     double best_d = 0.0;
     unsigned long long best_k = ~0ull;
-    const int combos = n_owned * n_disc;
+    int best_st = 0, best_r = 0;               // source | target << 8 and candidate row of the best distance so far
+    if (P.subset_k) {
+      // sample_subset_samples: the table is the env's explicit per-class row lists (subset.cuh); one row per lane, the node parts
+      // computed per row in float64 from the float32 snapshot embeddings
+      const int K = P.subset_k;
+      const uint32_t* lists = S.sub_rows + (size_t)b * SUB_CLASSES * K;
+      const int32_t* meta = S.sub_meta + (size_t)b * SUB_META;
+      int cls_end[SUB_CLASSES], total = 0;
+#pragma unroll
+      for (int c = 0; c < SUB_CLASSES; ++c) { total += meta[c]; cls_end[c] = total; }
+      const uint32_t rank_lo = (uint32_t)meta[11], rank_hi = (uint32_t)meta[12];
+      for (int i = lane; i < n_disc; i += 32) sh.dpos[sh.dorder[i]] = (uint8_t)i;
+      if (!P.defender) for (int i = lane; i < n_owned; i += 32) sh.opos[sh.oorder[i]] = (uint8_t)i;
+      __syncwarp();
+      for (int j = lane; j < total; j += 32) {
+        int c = 0, first = 0;
+#pragma unroll
+        for (int q = 0; q < SUB_CLASSES - 1; ++q) if (j >= cls_end[q]) { c = q + 1; first = cls_end[q]; }
+        const uint32_t e = lists[c * K + (j - first)];
+        const int s = e & 127, t = (e >> 7) & 127, rip = (e >> 14) & 255, epoch = (int)(e >> 22);
+        const int slot = S.pair_slot[pbase + s * P.ncap + t];
+        const int g = node_off + t;
+        const int r = T.nd_row_off[2 * g + (s == t ? 0 : 1)] + rip;
+        const uint32_t packed = T.row_packed[r];
+        const size_t zbase = ((size_t)b * P.slots + slot) * P.ncap;
+        const float4* zs = reinterpret_cast<const float4*>(S.z_hist + (zbase + s) * NODE_EMB);
+        const float4* zt = reinterpret_cast<const float4*>(S.z_hist + (zbase + t) * NODE_EMB);
+        double ms = 0.0, mt = 0.0;
+        for (int i = 0; i < NODE_EMB / 4; ++i) {
+          const float4 x = zs[i], y = zt[i];
+          macc<METRIC>(ms, (double)sh.a_st[4 * i + 0] - (double)x.x);
+          macc<METRIC>(ms, (double)sh.a_st[4 * i + 1] - (double)x.y);
+          macc<METRIC>(ms, (double)sh.a_st[4 * i + 2] - (double)x.z);
+          macc<METRIC>(ms, (double)sh.a_st[4 * i + 3] - (double)x.w);
+          macc<METRIC>(mt, (double)sh.a_st[NODE_EMB + 4 * i + 0] - (double)y.x);
+          macc<METRIC>(mt, (double)sh.a_st[NODE_EMB + 4 * i + 1] - (double)y.y);
+          macc<METRIC>(mt, (double)sh.a_st[NODE_EMB + 4 * i + 2] - (double)y.z);
+          macc<METRIC>(mt, (double)sh.a_st[NODE_EMB + 4 * i + 3] - (double)y.w);
+        }
+        const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
+        const double d = mfinish<METRIC>(mjoin<METRIC>(mjoin<METRIC>(mjoin<METRIC>(ms, mt), vt_row[u]), sh.d_o[oh]));
+        const uint32_t rank = ((c < 8 ? rank_lo : rank_hi) >> (4 * (c & 7))) & 15u;
+        const int opk = P.defender ? (int)S.pair_opos[pbase + s * P.ncap + t] : (int)sh.opos[s];
+        const unsigned long long k64 = ((unsigned long long)rank << 32) | ((unsigned long long)epoch << 24) | ((unsigned long long)opk << 16) |
+                                       ((unsigned long long)sh.dpos[t] << 8) | (unsigned long long)rip;
+        if (argmin_better(have, best_d, best_k, d, k64)) { have = true; best_d = d; best_k = k64; best_st = s | (t << 8); best_r = r; }
+      }
+    }
+    const int combos = P.subset_k ? 0 : n_owned * n_disc;
     for (int cbase = 0; cbase < combos; cbase += 32) {
       // ---- one (source, target) combination per lane: its two node parts ----
       const int c = cbase + lane;
@@ -218,7 +268,7 @@ __global__ void __launch_bounds__(MET_THREADS) metric_select_kernel(Tables T, Pa
         const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
         const double d = mfinish<METRIC>(mjoin<METRIC>(mjoin<METRIC>(sh.p_d[pi], vt_row[u]), sh.d_o[oh]));
         const unsigned long long k64 = ((unsigned long long)k << 32) | (unsigned long long)(unsigned)r;
-        if (argmin_better(have, best_d, best_k, d, k64)) { have = true; best_d = d; best_k = k64; }
+        if (argmin_better(have, best_d, best_k, d, k64)) { have = true; best_d = d; best_k = k64; best_st = s | (t << 8); best_r = r; }
       }
       __syncwarp();
     }
@@ -227,15 +277,15 @@ __global__ void __launch_bounds__(MET_THREADS) metric_select_kernel(Tables T, Pa
       const bool oh_ = __shfl_xor_sync(0xFFFFFFFFu, (int)have, o) != 0;
       const double od = __shfl_xor_sync(0xFFFFFFFFu, best_d, o);
       const unsigned long long ok = __shfl_xor_sync(0xFFFFFFFFu, best_k, o);
-      if (oh_ && argmin_better(have, best_d, best_k, od, ok)) { have = true; best_d = od; best_k = ok; }
+      const int ost = __shfl_xor_sync(0xFFFFFFFFu, best_st, o), orr = __shfl_xor_sync(0xFFFFFFFFu, best_r, o);
+      if (oh_ && argmin_better(have, best_d, best_k, od, ok)) { have = true; best_d = od; best_k = ok; best_st = ost; best_r = orr; }
     }
     if (lane == 0) {
       out = make_int4(starter, starter, 0, 0);
       dres = 1.0;
       if (have) {
-        const uint32_t k = (uint32_t)(best_k >> 32);
-        const int r = (int)(uint32_t)best_k;
-        out = make_int4(sh.oorder[k & 0xFF], sh.dorder[(k >> 8) & 0xFF], T.row_ulocal[r], (int)((T.row_packed[r] >> 20) & 15));
+        const int r = best_r;
+        out = make_int4(best_st & 0xFF, best_st >> 8, T.row_ulocal[r], (int)((T.row_packed[r] >> 20) & 15));
         dres = best_d;
       } else {
         atomicExch(S.errflag, 3);   // empty action table: outside the reference's domain

@@ -78,6 +78,7 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
     ("control", (8, 20), 100, 32, 70, dict(sample_subset_samples=6, proportional_cutoff_coefficient=3)),
     ("control", (6, 14), 100, 24, 80, dict(_DEFENDER, sample_subset_samples=10)),
     ("control", (8, 16), 100, 24, 70, dict(sample_subset_samples=8, precise_action_space_positions=True, proportional_cutoff_coefficient=3)),
+    ("control", (8, 16), 100, 24, 60, dict(sample_subset_samples=8, distance_metric="l2", proportional_cutoff_coefficient=3)),
     # ExternalRandomEvents defender on its Philox streams (16 + node): services stopped / started, firewall rules added / removed
     ("control", (6, 14), 100, 24, 90, dict(static_defender_agent="events", random_event_probability=0.05, proportional_cutoff_coefficient=4)),
     # BASELINE configs[3] (bench workload c4): mixed 10-100-node scenarios in one padded batch, pool of 600 vulnerabilities
@@ -85,7 +86,7 @@ _DEFENDER = dict(static_defender_agent="reimage", detect_probability=0.7, scan_c
 ], ids=["control-8-24", "discovery-8-14", "control-40-70", "disruption-odd-batch", "control-128-nodes", "single-env-tiny",
         "control-node", "discovery-node", "defender-philox", "precise-encoding", "precise-positions", "precise-both",
         "metric-l1", "metric-l2", "metric-inf", "metric-l2-defender", "subset-k100-32-nodes", "subset-k6", "subset-defender",
-        "subset-positions", "events-philox", "c4-mixed-10-100"])
+        "subset-positions", "subset-l2", "events-philox", "c4-mixed-10-100"])
 def test_lockstep_heterogeneous_batch(goal, sizes, pool_size, B, T, extra):
     import torch
     import ccbs_b200 as cb

@@ -36,9 +36,3 @@ def test_subset_keep_is_a_uniform_ordered_subset():
         assert keep in ([0, 1], [2, 3], [0, 2])
     with pytest.raises(ValueError):
         row_identity([128], [0], [0], [0])
-
-
-def test_cuda_env_refuses_oracle_only_options():
-    import ccbs_b200 as cb
-    with pytest.raises(NotImplementedError):
-        cb.BatchedCyberBattleEnv([cb.synthetic_spec(0, 8)], cb.GaeWeights.random(0), cb.EnvConfig(sample_subset_samples=100, distance_metric="l1"))
