@@ -264,7 +264,7 @@ def transition_roofline(specs, weights, device_index, n_envs, n_steps=8, seed=11
     try:
         kms = []
         same = None
-        for rep in range(3):
+        for rep in range(6):
             env.reset()
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -280,7 +280,7 @@ def transition_roofline(specs, weights, device_index, n_envs, n_steps=8, seed=11
                 for k in range(K):
                     same = same and bool(torch.equal(rk[k][running], rew_all[k][running]))
                     running &= dk[k] == 0
-        kms_mean = float(np.mean(kms))
+        kms_mean = float(np.median(kms))      # (the first launches after the resets of 1M envs still see allocator / page effects)
         # physical bytes the launch needs per env: records once (hot sector 32 in + 32 out, list lengths 16, masks 64 in + changed
         # words out) + per step sel 16 + dist 8 + uniform 4 + reward 4 + done 1
         phys = 150.0 + 33.0 * K
@@ -295,6 +295,43 @@ def transition_roofline(specs, weights, device_index, n_envs, n_steps=8, seed=11
         out["ksteps"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     env.close()
     del actions, sel_all, dist_all, uni_all, rew_all
+    torch.cuda.empty_cache()
+    return out
+
+
+def side_workload(key, device_index, steps=60, **cfg_kw):
+    """Device-resident env-steps/s of another workload (same measurement as the headline, plain launches, short): BASELINE
+    configs[1] / configs[3] next to the headline configs[2], and the headline workload with reference options switched on."""
+    import torch
+    import ccbs_b200 as cb
+    from ccbs_b200 import constants as C
+    wl = WORKLOADS[key]
+    specs = build_specs(wl)
+    B = wl["envs_per_gpu"]
+    dev = torch.device("cuda", device_index)
+    env = cb.BatchedCyberBattleEnv(specs, cb.GaeWeights.random(GAE_SEED), cb.EnvConfig(**cfg_kw), num_envs=B, device=device_index, seed=7)
+    R = max(2, int(np.ceil(160e6 / (B * C.ACTION_DIM * 4))))
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    ring = torch.rand(R, B, C.ACTION_DIM, device=dev, generator=gen) * 8.0 - 4.0
+    env.reset()
+    stagger = torch.arange(B, device=dev) % 32
+    for i in range(64):
+        if i < 32:
+            env.reset((stagger == i).to(torch.uint8))
+        env.step(ring[i % R], None, want_info=False)
+    env.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        env.step(ring[i % R], None, want_info=False)
+    e1.record()
+    env.sync()
+    ms = e0.elapsed_time(e1)
+    out = {"workload": wl["name"], "envs": B, "options": cfg_kw, "steps": steps, "ms_per_step": ms / steps,
+           "env_steps_per_s": B * steps / (ms * 1e-3), "state_gb": env.state_bytes / 1e9, "decode_margin_edge": env.margin_edge_count()}
+    env.close()
+    del ring
     torch.cuda.empty_cache()
     return out
 
@@ -698,6 +735,17 @@ def main():
                 out["configs4"] = configs4_leg(local_rank)
             except Exception as exc:  # noqa: BLE001
                 out["configs4"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            # the other BASELINE configs and the reference's training options, measured the same way (short side legs)
+            side = {}
+            for name, key, kw in (("configs1", "c1", {}), ("configs3_mixed_10_100", "c4", {}),
+                                  ("configs2_subset100", "c2", dict(sample_subset_samples=100)),
+                                  ("configs2_reimage_defender", "c2", dict(static_defender_agent="reimage")),
+                                  ("configs2_events_defender", "c2", dict(static_defender_agent="events"))):
+                try:
+                    side[name] = side_workload(key, local_rank, **kw)
+                except Exception as exc:  # noqa: BLE001
+                    side[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            out["other_workloads"] = side
         if world == 1 and args.transition_envs > 0:
             try:    # a side measurement must never cost the headline line (e.g. 60 GB of state not available on this box)
                 out["transition_roofline"] = transition_roofline(specs, weights, local_rank, args.transition_envs)

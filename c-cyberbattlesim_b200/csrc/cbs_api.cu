@@ -1,5 +1,6 @@
 // cbs_api.cu — C ABI (include/cbsim.h): handle lifetime, table upload, kernel launches.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>

@@ -14,6 +14,7 @@
 #include "cbs_device.cuh"
 #include "philox.cuh"
 #include "subset.cuh"
+#include <type_traits>
 
 namespace cbs {
 
@@ -166,11 +167,13 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   }
   __syncwarp();
 
-  // root term x_i W_root (+ conv bias folded into bn1 shift); four nodes per pass so that their table rows are in flight together
-  for (int i0 = 0; i0 < n; i0 += 4) {
-    float r0[4], r1[4];
+  // root term x_i W_root (+ conv bias folded into bn1 shift); ROOT_TILE nodes per pass so that their table rows are in flight
+  // together (a pass is one L2 round trip; four per pass made a 9-node graph wait three times)
+  constexpr int ROOT_TILE = 12;
+  for (int i0 = 0; i0 < n; i0 += ROOT_TILE) {
+    float r0[ROOT_TILE], r1[ROOT_TILE];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < ROOT_TILE; ++j) {
       const int i = i0 + j;
       r0[j] = r1[j] = 0.f;
       if (i < n) {
@@ -180,7 +183,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < ROOT_TILE; ++j) {
       const int i = i0 + j;
       if (i >= n) break;
       float vis, x[NUM_DYN];
@@ -206,11 +209,23 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   // NNConv messages: y[dst] += [relu(m_e + b1); 1] . T_src
   const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
   const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
+  // the next edge's end points and attribute are requested while the current edge is combined (one exposed round trip less per edge)
+  int js_n = 0, jd_n = 0;
+  float hm_n = 0.f;
+  if (E > 0) {
+    js_n = es[0]; jd_n = ed[0];
+    if (lane < NN_CH) hm_n = S.edge_m[((size_t)b * P.ecap) * NN_CH + lane];
+  }
   for (int e = 0; e < E; ++e) {
-    const int js = es[e], jd = ed[e];
+    const int js = js_n, jd = jd_n;
+    const float hm = hm_n;
+    if (e + 1 < E) {
+      js_n = es[e + 1]; jd_n = ed[e + 1];
+      if (lane < NN_CH) hm_n = S.edge_m[((size_t)b * P.ecap + e + 1) * NN_CH + lane];
+    }
     const int is = W.pos[js], id = W.pos[jd];
     float hl = 0.f;
-    if (lane < NN_CH) hl = fmaxf(S.edge_m[((size_t)b * P.ecap + e) * NN_CH + lane] + SW.nn0b[lane], 0.f);
+    if (lane < NN_CH) hl = fmaxf(hm + SW.nn0b[lane], 0.f);
     else if (lane == NN_CH) hl = 1.f;
     float vis, x[NUM_DYN];
     node_dyn(W.dynb[is], W.xst[is], vis, x);
@@ -246,24 +261,38 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     W.y[i * NODE_EMB + c1] = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn1s[c1], SW.bn1h[c1]), 0.f);
   }
   __syncwarp();
-  for (int i = 0; i < n; i += 2) {                // two nodes per pass: each weight pair feeds four FMAs
-    const int i2 = (i + 1 < n) ? i + 1 : i;
-    float g0 = 0.f, g1 = 0.f, h0 = 0.f, h1 = 0.f;
-#pragma unroll 8
+  // Several nodes per pass: each weight pair feeds two independent FMA chains per node, and a pass's broadcast reads of the
+  // nodes' activations are all in flight together (two nodes per pass left the loop a chain of dependent shared-memory reads).
+  // Passes of 8, then 4 / 2 / 1 for the remainder, so that no pass computes padding.  Every node's sum runs over k in the same
+  // order whatever the tile, so equal inputs still give bit-identical outputs.
+  auto gcn_pass = [&](auto tile_c, int i0) {
+    constexpr int TILE = decltype(tile_c)::value;
+    float acc0[TILE], acc1[TILE];
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+    const float* yrow = W.y + i0 * NODE_EMB;
+#pragma unroll 4
     for (int k = 0; k < NODE_EMB; ++k) {
       const float w0 = SW.gcn[k * NODE_EMB + c0], w1 = SW.gcn[k * NODE_EMB + c1];
-      const float a = W.y[i * NODE_EMB + k], bq = W.y[i2 * NODE_EMB + k];
-      g0 = fmaf(a, w0, g0);
-      g1 = fmaf(a, w1, g1);
-      h0 = fmaf(bq, w0, h0);
-      h1 = fmaf(bq, w1, h1);
+#pragma unroll
+      for (int j = 0; j < TILE; ++j) {
+        const float a = yrow[j * NODE_EMB + k];
+        acc0[j] = fmaf(a, w0, acc0[j]);
+        acc1[j] = fmaf(a, w1, acc1[j]);
+      }
     }
-    W.g[i * NODE_EMB + c0] = g0;
-    W.g[i * NODE_EMB + c1] = g1;
-    if (i2 != i) {
-      W.g[i2 * NODE_EMB + c0] = h0;
-      W.g[i2 * NODE_EMB + c1] = h1;
+#pragma unroll
+    for (int j = 0; j < TILE; ++j) {
+      W.g[(i0 + j) * NODE_EMB + c0] = acc0[j];
+      W.g[(i0 + j) * NODE_EMB + c1] = acc1[j];
     }
+  };
+  {
+    int i0 = 0;
+    for (; i0 + 8 <= n; i0 += 8) gcn_pass(std::integral_constant<int, 8>{}, i0);
+    if (i0 + 4 <= n) { gcn_pass(std::integral_constant<int, 4>{}, i0); i0 += 4; }
+    if (i0 + 2 <= n) { gcn_pass(std::integral_constant<int, 2>{}, i0); i0 += 2; }
+    if (i0 < n) gcn_pass(std::integral_constant<int, 1>{}, i0);
   }
   __syncwarp();
   // normalised aggregation, edges first and the self loop last (the order PyG's add_remaining_self_loops +
