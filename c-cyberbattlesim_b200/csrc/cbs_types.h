@@ -83,7 +83,9 @@ enum Scalar : int {
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,
               FL_NEEDS_RESET = 64, FL_FINISHED_THIS_STEP = 128,
               FL_DIRTY = 256,  // node features / edges / node sets changed since the last encode
-              FL_INTEREST_IN_GRAPH = 512;  // *_node goals: the interest node was added to the visible graph (compressed:254-256)
+              FL_INTEREST_IN_GRAPH = 512,  // *_node goals: the interest node was added to the visible graph (compressed:254-256)
+              FL_PENDING_SHIFT = 16;       // bits 16..31, sample_subset_samples: table builds skipped since the last one that ran (the
+                                           // encode of an unchanged graph is skipped, but the reference's balance step still draws)
 // vi_flags bits (scenario.py VI_*)
 constexpr uint32_t VI_LISTENING = 1u, VI_IN_ALLOWED = 2u;
 constexpr int VI_PRIVREQ_SHIFT = 2, VI_LEVEL_ANY_SHIFT = 4, VI_LEVEL_REMOTE_SHIFT = 6;

@@ -365,7 +365,8 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 // With sample_subset_samples the pairs this build touches are also listed in the warp's scratch and handed to subset_update
 // (subset.cuh), which keeps the explicit, sub-sampled table.
 template <bool PRECISE>
-__device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg) {
+__device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg,
+                            int skipped_builds = 0) {
   const bool refresh = PRECISE && refresh_arg;
   SubScratch sub;
   int n_newp = 0;
@@ -452,7 +453,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (!any_new) {
     // the reference still balances (and draws from its generator) at the end of this create_continuous_action_space
-    if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos);
+    if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos, skipped_builds);
     return;
   }
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
@@ -473,7 +474,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
   __syncwarp();
-  if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos);
+  if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos, skipped_builds);
 }
 
 // ---- get_statistics (cyberbattle_env.py:517-524) + episode accumulators ----
@@ -764,8 +765,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
         // (an env that finished in this step drops its action table at the reset that follows: only the sub-sampled table is
         // still maintained, because every create_continuous_action_space advances the env's balance counter)
         if (!(flags & FL_FINISHED_THIS_STEP) || P.subset_k) {
-          if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true);
-          else build_table<false>(T, P, S, W, b, lane, false);
+          const int skipped = (flags >> FL_PENDING_SHIFT) & 0xFFFF;
+          if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true, skipped);
+          else build_table<false>(T, P, S, W, b, lane, false, skipped);
+          keep &= 0xFFFF;
         }
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
         keep &= ~FL_DIRTY;
@@ -781,16 +784,29 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       __syncwarp();
     }
     if (do_reset) {
+      if (P.subset_k) {   // balance calls of skipped builds that no later build picked up
+        const int left = (mode == 1 ? flags : scalar(S, P, S_FLAGS, b)) >> FL_PENDING_SHIFT & 0xFFFF;
+        if (left && lane == 0) S.sub_meta[(size_t)b * SUB_META + 13] += left;
+        __syncwarp();
+      }
       const int2 ss = reset_env(T, P, S, b, lane);
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[3])); }
-      // (the sub-sampled table is rebuilt through the generic path: its balance step is per env, not per (scenario, starter))
-      if (P.subset_k || !reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
+      if (!reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
         if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
         else build_table<false>(T, P, S, W, b, lane, false);
-        if (!P.subset_k) reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
+        reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
+      } else if (P.subset_k) {
+        // the cached first observation is per (scenario, starter); the sub-sampled table is per env: its one pair (starter,
+        // starter) goes through the balance step like every build of the reference
+        SubScratch sub;
+        sub.carve(reinterpret_cast<unsigned char*>(W.ysm + SMEM_NODES * NODE_EMB), nullptr);
+        if (lane == 0) { sub.newp[0] = 0; W.pos[ss.y] = 0; }
+        __syncwarp();
+        subset_update(T, P, S, sub, b, lane, 0, 1, P.defender ? S.owned_raw + (size_t)b * P.ocap : S.owned_order + (size_t)b * P.ncap, 1,
+                      S.disc_order + (size_t)b * P.ncap, W.pos, 0);
       }
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[4])); }
       // *_node goals: that first encode put the interest node into the live graph, so the next re-encode differs even

@@ -49,6 +49,9 @@ struct SubScratch {
   uint32_t* first;              // [SUB_CLASSES] smallest insertion key among them
   uint32_t* ncand;              // [1]
   uint8_t* opos;                // [MAX_NODES] node -> position in owned_order
+  int* ch_r0;                   // [32] staged chunk of touched pairs: first candidate row of the pair
+  int* ch_pre;                  // [33] exclusive prefix of the chunk's row counts
+  uint32_t* ch_meta;            // [32] source | target << 7 | insertion position of the source << 14 | target position << 22 | refreshed << 30
   uint16_t* newp;               // pairs this build touches: target position | source position << 7 | refreshed-not-new << 15
   __device__ __forceinline__ void carve(unsigned char* base, uint16_t* newp_global) {
     hist = reinterpret_cast<uint32_t*>(base);
@@ -59,10 +62,13 @@ struct SubScratch {
     first = nnew + SUB_CLASSES;
     ncand = first + SUB_CLASSES;
     opos = base + 2304;
-    newp = newp_global ? newp_global : reinterpret_cast<uint16_t*>(base + 2432);
+    ch_r0 = reinterpret_cast<int*>(base + 2432);
+    ch_pre = ch_r0 + 32;
+    ch_meta = reinterpret_cast<uint32_t*>(ch_pre + 33);
+    newp = newp_global ? newp_global : reinterpret_cast<uint16_t*>(base + 2832);
   }
 };
-constexpr int SUB_NEWP_SMEM = (8192 - 2432) / 2;   // 2880 >= 32 x 32 pairs
+constexpr int SUB_NEWP_SMEM = (8192 - 2832) / 2;   // 2680 >= 32 x 32 pairs
 
 struct SubCtx {
   const Tables& T;
@@ -84,6 +90,54 @@ __device__ __forceinline__ bool sub_alive_bit(const SubCtx& C, int s, int t, int
   return (C.alive[((size_t)s * C.P.ncap + t) * (SUB_MAX_ROWS_PER_PAIR / 32) + (rip >> 5)] >> (rip & 31)) & 1u;
 }
 
+// g(kind, s, t, rip, r, opk, dp) for every row the pairs of this build add (all classes), the rows flattened over the lanes: the
+// touched pairs are staged 32 at a time (lane per pair: row range and identity), then lane j takes row j of the chunk, so that a
+// trip's 32 template loads are independent and in flight together (a lane walking the rows of "its" pair made every row a
+// dependent L2 round trip).  Rows that are filtered out of the table, or (refreshed pairs) still alive, are skipped.
+template <class G>
+__device__ __forceinline__ void sub_for_each_new(const SubCtx& C, G&& g) {
+  const int ncap = C.P.ncap;
+  for (int base = 0; base < C.n_newp; base += 32) {
+    const int pi = base + C.lane;
+    int cnt = 0;
+    __syncwarp();
+    if (pi < C.n_newp) {
+      const uint32_t pr = C.sc.newp[pi];
+      const int dp = pr & 127, op = (pr >> 7) & 255;
+      const int s = C.oorder[op], t = C.dorder[dp];
+      const int gn = C.node_off + t;
+      const int r0 = C.T.nd_row_off[2 * gn + (s == t ? 0 : 1)], r1 = C.T.nd_row_off[2 * gn + 2];
+      const int opk = C.popos ? (int)C.popos[s * ncap + t] : op;
+      C.sc.ch_r0[C.lane] = r0;
+      C.sc.ch_meta[C.lane] = (uint32_t)s | ((uint32_t)t << 7) | ((uint32_t)opk << 14) | ((uint32_t)dp << 22) | ((pr >> 15) << 30);
+      cnt = r1 - r0;
+    }
+    int run = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, run, o);
+      if (C.lane >= o) run += v;
+    }
+    C.sc.ch_pre[C.lane + 1] = run;
+    if (C.lane == 0) C.sc.ch_pre[0] = 0;
+    __syncwarp();
+    const int total = C.sc.ch_pre[32];
+    int q = 0;
+    for (int j = C.lane; j < total; j += 32) {
+      while (C.sc.ch_pre[q + 1] <= j) ++q;
+      const int rip = j - C.sc.ch_pre[q];
+      const int r = C.sc.ch_r0[q] + rip;
+      const uint32_t m = C.sc.ch_meta[q];
+      const int s = m & 127, t = (m >> 7) & 127, opk = (m >> 14) & 255, dp = (m >> 22) & 255;
+      const int kind = (C.T.row_packed[r] >> 20) & 15;
+      if (row_filtered(C.P, kind, s, t, C.starter, C.interest)) continue;
+      if ((m >> 30) && sub_alive_bit(C, s, t, rip)) continue;      // still in the table: overwritten in place, not re-added
+      g(kind, s, t, rip, r, opk, dp);
+    }
+  }
+  __syncwarp();
+}
+
 // f(composite key, entry) for every row of class c: the rows in its list, then the rows the pairs of this build add.
 // Lanes work independently (divergent): f may only use atomics on shared memory.
 template <class F>
@@ -99,30 +153,52 @@ __device__ __forceinline__ void sub_for_each(const SubCtx& C, int c, int n_old, 
     const uint32_t k32 = sub_key32(C.P, C.genv, C.call, s, t, c, C.T.row_ulocal[r]);
     f(((unsigned long long)k32 << 32) | ins, e);
   }
-  for (int pi = C.lane; pi < C.n_newp; pi += 32) {
-    const uint32_t pr = C.sc.newp[pi];
-    const int dp = pr & 127, op = (pr >> 7) & 255;
-    const bool refreshed = (pr >> 15) != 0;
-    const int s = C.oorder[op], t = C.dorder[dp];
-    const int g = C.node_off + t;
-    const int r0 = C.T.nd_row_off[2 * g + (s == t ? 0 : 1)], r1 = C.T.nd_row_off[2 * g + 2];
-    const int opk = C.popos ? (int)C.popos[s * ncap + t] : op;
-    for (int r = r0; r < r1; ++r) {
-      const uint32_t packed = C.T.row_packed[r];
-      const int kind = (packed >> 20) & 15;
-      if (kind != c || row_filtered(C.P, kind, s, t, C.starter, C.interest)) continue;
-      const int rip = r - r0;
-      if (refreshed && sub_alive_bit(C, s, t, rip)) continue;     // still in the table: overwritten in place, not re-added
-      const uint32_t ins = ((uint32_t)C.slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip;
-      const uint32_t k32 = sub_key32(C.P, C.genv, C.call, s, t, c, C.T.row_ulocal[r]);
-      f(((unsigned long long)k32 << 32) | ins, sub_entry(s, t, rip, C.slot));
-    }
-  }
+  sub_for_each_new(C, [&](int kind, int s, int t, int rip, int r, int opk, int dp) {
+    if (kind != c) return;
+    const uint32_t ins = ((uint32_t)C.slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip;
+    const uint32_t k32 = sub_key32(C.P, C.genv, C.call, s, t, c, C.T.row_ulocal[r]);
+    f(((unsigned long long)k32 << 32) | ins, sub_entry(s, t, rip, C.slot));
+  });
 }
 
 // the `need`-th smallest composite key among the rows of class c (radix select, 8 bits per level; a bucket of at most SUB_CAND
 // rows is ranked directly)
-static __device__ unsigned long long sub_select(const SubCtx& C, int c, int n_old, int need) {
+static __device__ unsigned long long sub_select(const SubCtx& C, int c, int n_old, int need, int n_total) {
+  // Fast path: the keys are uniform 32-bit draws, so the need-th smallest of n_total rows lies near need / n_total * 2^32.  One
+  // enumeration collects every row below 1.4x that estimate (+ slack) into the 256-entry buffer (histogram and candidate
+  // areas together); if at least `need` and at most 256 rows qualified, the need-th smallest of them is the answer.
+  if (need <= 160) {
+    unsigned long long* buf = reinterpret_cast<unsigned long long*>(C.sc.hist);      // hist (1 KB) + cand (1 KB) are contiguous
+    const double est = 1.4 * (double)need / (double)n_total + 24.0 / (double)n_total;
+    const unsigned long long cut = est >= 1.0 ? ~0ull : (unsigned long long)(est * 18446744073709551616.0);
+    if (C.lane == 0) *C.sc.ncand = 0u;
+    __syncwarp();
+    sub_for_each(C, c, n_old, [&](unsigned long long comp, uint32_t) {
+      if (comp <= cut) {
+        const uint32_t at = atomicAdd(C.sc.ncand, 1u);
+        if (at < 256u) buf[at] = comp;
+      }
+    });
+    __syncwarp();
+    const int m = (int)*C.sc.ncand;
+    if (m >= need && m <= 256) {
+      unsigned long long res = 0ull;
+      for (int i = C.lane; i < m; i += 32) {
+        const unsigned long long x = buf[i];
+        int rank = 0;
+        for (int j = 0; j < m; ++j) rank += buf[j] < x;
+        if (rank == need - 1) res = x;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long v = __shfl_xor_sync(0xFFFFFFFFu, res, o);
+        res = v > res ? v : res;
+      }
+      __syncwarp();
+      return res;
+    }
+    __syncwarp();
+  }
   unsigned long long prefix = 0ull;
   int nbits = 0, bucket = 0;
   for (;;) {
@@ -195,9 +271,14 @@ static __device__ unsigned long long sub_select(const SubCtx& C, int c, int n_ol
 // Adds the rows of the pairs in sc.newp[0, n_newp) to the lists and balances every class (one warp).  Called by every
 // create_continuous_action_space (reset included, and also when no pair is new: the balance counter still advances).
 // `oorder` / `dorder` / `dpos`: the source list of this build, the discovered order and its inverse.
+// `skipped`: table builds the env skipped since the last one that ran (FL_PENDING_SHIFT): each was a balance call of the reference.
 static __device__ void subset_update(const Tables& T, const Params& P, const State& S, SubScratch sc, int b, int lane, int slot, int n_newp,
-                              const uint8_t* oorder, int n_sources, const uint8_t* dorder, const uint8_t* dpos) {
+                              const uint8_t* oorder, int n_sources, const uint8_t* dorder, const uint8_t* dpos, int skipped) {
   int32_t* meta = S.sub_meta + (size_t)b * SUB_META;
+  if (skipped) {
+    if (lane == 0) meta[13] += skipped;
+    __syncwarp();
+  }
   const int sc_id = scalar(S, P, S_SCENARIO, b);
   SubCtx C{T, P, S, sc,
            S.sub_rows + (size_t)b * SUB_CLASSES * P.subset_k,
@@ -213,23 +294,10 @@ static __device__ void subset_update(const Tables& T, const Params& P, const Sta
     for (int i = lane; i < n_sources; i += 32) sc.opos[oorder[i]] = (uint8_t)i;
   __syncwarp();
   // ---- pass A: rows per class this build adds, and where each class first appears ----
-  for (int pi = lane; pi < n_newp; pi += 32) {
-    const uint32_t pr = sc.newp[pi];
-    const int dp = pr & 127, op = (pr >> 7) & 255;
-    const bool refreshed = (pr >> 15) != 0;
-    const int s = oorder[op], t = dorder[dp];
-    const int g = C.node_off + t;
-    const int r0 = T.nd_row_off[2 * g + (s == t ? 0 : 1)], r1 = T.nd_row_off[2 * g + 2];
-    const int opk = C.popos ? (int)C.popos[s * P.ncap + t] : op;
-    for (int r = r0; r < r1; ++r) {
-      const int kind = (T.row_packed[r] >> 20) & 15;
-      if (row_filtered(P, kind, s, t, C.starter, C.interest)) continue;
-      const int rip = r - r0;
-      if (refreshed && sub_alive_bit(C, s, t, rip)) continue;
-      atomicAdd(&sc.nnew[kind], 1u);
-      atomicMin(&sc.first[kind], ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip);
-    }
-  }
+  sub_for_each_new(C, [&](int kind, int, int, int rip, int, int opk, int dp) {
+    atomicAdd(&sc.nnew[kind], 1u);
+    atomicMin(&sc.first[kind], ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip);
+  });
   __syncwarp();
   // ---- classes that enter the table take the next ranks, in the order of their first rows ----
   if (lane == 0) {
@@ -254,7 +322,7 @@ static __device__ void subset_update(const Tables& T, const Params& P, const Sta
   for (int c = 0; c < SUB_CLASSES; ++c) {
     const int n_old = (int)sc.cnt[c], n_new = (int)sc.nnew[c];
     if (n_new == 0 || n_old + n_new <= K) continue;
-    const unsigned long long thr = sub_select(C, c, n_old, K);
+    const unsigned long long thr = sub_select(C, c, n_old, K, n_old + n_new);
     // compact the list in place
     int kept = 0;
     for (int base = 0; base < n_old; base += 32) {
@@ -283,34 +351,21 @@ static __device__ void subset_update(const Tables& T, const Params& P, const Sta
     __syncwarp();
   }
   // ---- pass B: the surviving new rows join their lists ----
-  for (int pi = lane; pi < n_newp; pi += 32) {
-    const uint32_t pr = sc.newp[pi];
-    const int dp = pr & 127, op = (pr >> 7) & 255;
-    const bool refreshed = (pr >> 15) != 0;
-    const int s = oorder[op], t = dorder[dp];
-    const int g = C.node_off + t;
-    const int r0 = T.nd_row_off[2 * g + (s == t ? 0 : 1)], r1 = T.nd_row_off[2 * g + 2];
-    const int opk = C.popos ? (int)C.popos[s * P.ncap + t] : op;
-    for (int r = r0; r < r1; ++r) {
-      const int kind = (T.row_packed[r] >> 20) & 15;
-      if (row_filtered(P, kind, s, t, C.starter, C.interest)) continue;
-      const int rip = r - r0;
-      if (refreshed && sub_alive_bit(C, s, t, rip)) continue;
-      const unsigned long long thr = sc.thr[kind];
-      if (thr != ~0ull) {
-        const uint32_t ins = ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip;
-        const uint32_t k32 = sub_key32(P, C.genv, C.call, s, t, kind, T.row_ulocal[r]);
-        if (((((unsigned long long)k32) << 32) | ins) > thr) continue;
-      }
-      const uint32_t at = atomicAdd(&sc.cnt[kind], 1u);
-      if (at < (uint32_t)K) {
-        C.lists[kind * K + at] = sub_entry(s, t, rip, slot);
-        if (C.alive) atomicOr(&C.alive[((size_t)s * P.ncap + t) * (SUB_MAX_ROWS_PER_PAIR / 32) + (rip >> 5)], 1u << (rip & 31));
-      } else {
-        atomicExch(S.errflag, 6);
-      }
+  sub_for_each_new(C, [&](int kind, int s, int t, int rip, int r, int opk, int dp) {
+    const unsigned long long thr = sc.thr[kind];
+    if (thr != ~0ull) {
+      const uint32_t ins = ((uint32_t)slot << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)rip;
+      const uint32_t k32 = sub_key32(P, C.genv, C.call, s, t, kind, T.row_ulocal[r]);
+      if (((((unsigned long long)k32) << 32) | ins) > thr) return;
     }
-  }
+    const uint32_t at = atomicAdd(&sc.cnt[kind], 1u);
+    if (at < (uint32_t)K) {
+      C.lists[kind * K + at] = sub_entry(s, t, rip, slot);
+      if (C.alive) atomicOr(&C.alive[((size_t)s * P.ncap + t) * (SUB_MAX_ROWS_PER_PAIR / 32) + (rip >> 5)], 1u << (rip & 31));
+    } else {
+      atomicExch(S.errflag, 6);
+    }
+  });
   __syncwarp();
   uint32_t total = lane < SUB_CLASSES ? (sc.cnt[lane] < (uint32_t)K ? sc.cnt[lane] : (uint32_t)K) : 0u;
   if (lane < SUB_CLASSES) meta[lane] = (int32_t)total;

@@ -618,10 +618,13 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   const int sticky = flags & FL_INTEREST_IN_GRAPH;          // survives until the episode's reset
   // (not with precise_action_space_positions: a re-encode of an unchanged graph still hands the current embeddings to
   // the pairs around THIS action's nodes, which an earlier refresh may have passed over)
-  // (nor with sample_subset_samples: every create_continuous_action_space advances the env's balance counter)
-  const bool encode_now = reencode && (dirty || P.precise_positions || P.subset_k);
+  // (with sample_subset_samples the skipped build still advances the env's balance counter: it is counted in the flags word and
+  // added by the next build that runs, or by the reset)
+  const bool encode_now = reencode && (dirty || P.precise_positions);
+  const int pending = ((h0.x >> FL_PENDING_SHIFT) & 0xFFFF) + ((P.subset_k && reencode && !encode_now) ? 1 : 0);
   flags = (done ? FL_DONE : 0) | (trunc ? FL_TRUNC : 0) | (reason << FL_REASON_SHIFT) | (add_edge ? FL_ADD_EDGE : 0) |
-          (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky;
+          (encode_now ? FL_REENCODE : 0) | ((done || trunc) ? FL_FINISHED_THIS_STEP : 0) | (dirty ? FL_DIRTY : 0) | sticky |
+          (pending << FL_PENDING_SHIFT);
   if (!PERSIST) M.close();
   if (!DEF && !PERSIST) {   // changed list lengths go back word by word (fire and forget)
     if (n_disc_w != in.c0.x) SC(S_N_DISC) = n_disc_w;
