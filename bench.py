@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--envs-per-gpu", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's local CPU cores")
     ap.add_argument("--ring", type=int, default=0, help="minimum number of action batches in the device-resident ring")
     ap.add_argument("--no-graph", action="store_true", help="time plain per-step launches instead of CUDA-graph replays")
     ap.add_argument("--presteps", type=int, default=64, help="untimed steps before the warm-up: episodes reach their steady-state mix")
@@ -477,6 +478,17 @@ def main():
     from ccbs_b200.batched_env import BatchedCyberBattleEnv
     from ccbs_b200.gae import GaeWeights
 
+    # host side of the end-to-end leg: run this rank on the cores next to its GPU, so that the pinned host buffers (first touch)
+    # and the launching thread sit on the GPU's own NUMA node and PCIe root complex
+    affinity = None
+    if not args.no_affinity:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(local_rank))
+            affinity = len(os.sched_getaffinity(0))
+        except Exception as exc:  # noqa: BLE001
+            affinity = f"unavailable ({type(exc).__name__})"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -718,7 +730,7 @@ def main():
                     "steps": e2e_steps, "api": e2e_api,
                     "gpu_launches_per_step": e2e_launches_per_step, "single_handle_value": e2e_single,
                     # the bare pinned copy of one rank's action batch, timed alone: what the link delivered on this box
-                    "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_copy_ms": h2d_ms, "h2d_gbs": h2d / (h2d_ms * 1e-3) / 1e9, "cpu_affinity_cores": affinity,
                     # per rank, all ranks copying concurrently: the ceiling of the end-to-end leg at N GPUs is
                     # total_envs / max(copy time) — host memory / PCIe contention, not the kernels
                     "h2d_gbs_per_rank_concurrent": [round(h2d / (m * 1e-3) / 1e9, 2) for m in h2d_all],
