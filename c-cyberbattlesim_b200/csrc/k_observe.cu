@@ -364,13 +364,15 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 //      place in the table's insertion order.
 // With sample_subset_samples the pairs this build touches are also listed in the warp's scratch and handed to subset_update
 // (subset.cuh), which keeps the explicit, sub-sampled table.
-template <bool PRECISE>
+// SUBSET: sample_subset_samples is configured (compile-time: the default instances carry none of its code — with the balance step
+// inlined behind a run-time test the default observe kernel ran 64 us instead of 43)
+template <bool PRECISE, bool SUBSET>
 __device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg,
                             int skipped_builds = 0) {
   const bool refresh = PRECISE && refresh_arg;
   SubScratch sub;
   int n_newp = 0;
-  if (P.subset_k) {
+  if constexpr (SUBSET) {
     const bool in_smem = W.g == W.ysm + SMEM_NODES * NODE_EMB;   // the projection buffer of a small graph; free once the encode is done
     sub.carve(reinterpret_cast<unsigned char*>(W.ysm + SMEM_NODES * NODE_EMB), in_smem ? nullptr : S.sub_newp + (size_t)b * P.ncap * P.ncap);
   }
@@ -445,7 +447,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
       }
       const unsigned fm = __ballot_sync(0xFFFFFFFFu, fresh);
       any_new |= fm != 0u;
-      if (P.subset_k && fm && slot < P.slots) {
+      if (SUBSET && fm && slot < P.slots) {
         if (fresh) sub.newp[n_newp + __popc(fm & ((1u << lane) - 1u))] = (uint16_t)(dp | (op << 7) | (fresh_refresh_only ? 0x8000 : 0));
         n_newp += __popc(fm);
       }
@@ -453,12 +455,12 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (!any_new) {
     // the reference still balances (and draws from its generator) at the end of this create_continuous_action_space
-    if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos, skipped_builds);
+    if constexpr (SUBSET) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos, skipped_builds);
     return;
   }
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
   new_rows = (int)warp_sum((float)new_rows);
-  if (lane == 0 && !P.subset_k) S.work_est[b] += new_rows;
+  if (lane == 0 && !SUBSET) S.work_est[b] += new_rows;
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
@@ -474,7 +476,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
   __syncwarp();
-  if (P.subset_k) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos, skipped_builds);
+  if constexpr (SUBSET) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos, skipped_builds);
 }
 
 // ---- get_statistics (cyberbattle_env.py:517-524) + episode accumulators ----
@@ -669,7 +671,7 @@ __device__ void reset_cache_publish(const Tables& T, const Params& P, const Stat
 }
 
 // BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
-template <bool BIG_GRAPHS>
+template <bool BIG_GRAPHS, bool SUBSET>
 __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(Tables T, Params P, State S,
                                                                 const uint8_t* __restrict__ reset_mask, int mode,
                                                                 long long* __restrict__ trace) {
@@ -764,10 +766,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
         // (an env that finished in this step drops its action table at the reset that follows: only the sub-sampled table is
         // still maintained, because every create_continuous_action_space advances the env's balance counter)
-        if (!(flags & FL_FINISHED_THIS_STEP) || P.subset_k) {
-          const int skipped = (flags >> FL_PENDING_SHIFT) & 0xFFFF;
-          if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, true, skipped);
-          else build_table<false>(T, P, S, W, b, lane, false, skipped);
+        if (!(flags & FL_FINISHED_THIS_STEP) || SUBSET) {
+          const int skipped = SUBSET ? (flags >> FL_PENDING_SHIFT) & 0xFFFF : 0;
+          if (P.precise_positions) build_table<true, SUBSET>(T, P, S, W, b, lane, true, skipped);
+          else build_table<false, SUBSET>(T, P, S, W, b, lane, false, skipped);
           keep &= 0xFFFF;
         }
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
@@ -784,7 +786,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       __syncwarp();
     }
     if (do_reset) {
-      if (P.subset_k) {   // balance calls of skipped builds that no later build picked up
+      if constexpr (SUBSET) {   // balance calls of skipped builds that no later build picked up
         const int left = (mode == 1 ? flags : scalar(S, P, S_FLAGS, b)) >> FL_PENDING_SHIFT & 0xFFFF;
         if (left && lane == 0) S.sub_meta[(size_t)b * SUB_META + 13] += left;
         __syncwarp();
@@ -795,10 +797,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
-        if (P.precise_positions) build_table<true>(T, P, S, W, b, lane, false);
-        else build_table<false>(T, P, S, W, b, lane, false);
+        if (P.precise_positions) build_table<true, SUBSET>(T, P, S, W, b, lane, false);
+        else build_table<false, SUBSET>(T, P, S, W, b, lane, false);
         reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
-      } else if (P.subset_k) {
+      } else if constexpr (SUBSET) {
         // the cached first observation is per (scenario, starter); the sub-sampled table is per env: its one pair (starter,
         // starter) goes through the balance step like every build of the reference
         SubScratch sub;
@@ -860,15 +862,16 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
   int grid = num_sms;
   const int need = (P.B + OBS_WARPS - 1) / OBS_WARPS;
   if (grid > need) grid = need;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[big]) {
-    cudaError_t e = big ? cudaFuncSetAttribute(observe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                        : cudaFuncSetAttribute(observe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  using KernelFn = void (*)(Tables, Params, State, const uint8_t*, int, long long*);
+  const KernelFn kernels[4] = {observe_kernel<false, false>, observe_kernel<true, false>, observe_kernel<false, true>, observe_kernel<true, true>};
+  const int which = (big ? 1 : 0) | (P.subset_k ? 2 : 0);
+  static bool attr_set[4] = {false, false, false, false};
+  if (!attr_set[which]) {
+    cudaError_t e = cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set[big] = true;
+    attr_set[which] = true;
   }
-  if (big) observe_kernel<true><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
-  else observe_kernel<false><<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
+  kernels[which]<<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
   return cudaGetLastError();
 }
 
