@@ -10,6 +10,7 @@ __device__ __forceinline__ uint32_t ld_mask(const State& S, const Params& P, int
 __device__ __forceinline__ bool bit_of(const State& S, const Params& P, int plane, int node, int b) {
   return (ld_mask(S, P, plane, node >> 5, b) >> (node & 31)) & 1u;
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // scalar `plane` of env b: sector-major arrays, State::scal[sector][B][8]
 __device__ __forceinline__ int32_t& scalar(const State& S, const Params& P, int plane, int b) {
   return S.scal[((size_t)(plane >> 3) * P.B + b) * 8 + (plane & 7)];

@@ -15,6 +15,8 @@
 #include "philox.cuh"
 #include "subset.cuh"
 #include <type_traits>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cbs {
 
@@ -24,17 +26,22 @@ namespace cbs {
 #ifndef CBS_OBS_MINB
 #define CBS_OBS_MINB 1
 #endif
+#ifndef CBS_OBS_BOUND
+#define CBS_OBS_BOUND (CBS_OBS_WARPS * 32)   // threads the register budget is sized for (experiments: > the CTA size caps the registers)
+#endif
 constexpr int OBS_WARPS = CBS_OBS_WARPS;          // warps per CTA (one CTA per SM)
 constexpr int SMEM_NODES = CBS_OBS_SMEM_NODES;    // graphs up to this many nodes keep their embeddings in shared memory
 
 struct SharedWeights {
   float gcn[NODE_EMB * NODE_EMB];               // [in][out]
-  float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]  (reading it through L1 instead of staging it was measured slower)
+  float dyn[NUM_DYN * PROJ_ROWS * NODE_EMB];    // [d][row][c]  (reading it through L1 instead of staging it, to fit 12 warps per SM, was measured slower: 57 us against 37)
   float bn1s[NODE_EMB], bn1h[NODE_EMB], bn2s[NODE_EMB], bn2h[NODE_EMB];
   float nn0b[NN_CH];
   double accum[N_ACCUM];   // this CTA's share of the episode sums (flushed to State::accum by its last warp)
   int warps_done;
 };
+
+constexpr size_t kSharedWeightsBytes = (sizeof(SharedWeights) + 15) & ~(size_t)15;   // the warps' buffers are read 128 bits at a time
 
 struct WarpScratch {
   float* y;           // [n][64]
@@ -139,16 +146,35 @@ __device__ void edge_update(const Tables& T, const Params& P, const State& S, in
 // ---- encode (compressed:249-306) : returns node embeddings z in W.y (position-major) and writes S.obs ----
 // EV: the ExternalRandomEvents defender is configured (compile-time: its feature corrections sit inside the unrolled hot loops,
 // and the default instance must not carry their code)
+#ifdef CBS_OBS_SUBTRACE
+#define SUBT(k) if (tsub) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tsub[k]))
+#else
+#define SUBT(k)
+#endif
 template <bool EV>
 __device__ void encode_env(const Tables& T, const Params& P, const State& S, const SharedWeights& SW, WarpScratch& W, int b,
-                           int lane) {
+                           int lane, long long* tsub = nullptr) {
+  // everything that depends on the env index alone is requested here, in one round trip: the scalars, the discovered order, the
+  // first 32 edges, and the two counters the observation's tail needs (loaded where they were used, each was an exposed trip)
   const int sc = scalar(S, P, S_SCENARIO, b);
-  const int node_off = T.sc_node_off[sc];
+  const int node_off = scalar(S, P, S_NODE_OFF, b);          // T.sc_node_off[sc], kept per env by the reset
   const int n_disc = scalar(S, P, S_N_DISC, b);
   const int E = scalar(S, P, S_N_EDGES, b);
+  const int n_owned_obs = scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);
+  const int n_encodes = scalar(S, P, S_N_ENCODES, b);
   const uint8_t* disc_order = S.disc_order + (size_t)b * P.ncap;
-  const int c0 = lane, c1 = lane + 32;
+  const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
+  const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
+  int my_es = 0, my_ed = 0;                                  // edge `lane` of the current block of 32 edges
+  if (lane < P.ecap) { my_es = es[lane]; my_ed = ed[lane]; }
+  float hm_n = 0.f;                                          // attribute of the next edge (requested one edge ahead)
+  if (lane < NN_CH) hm_n = S.edge_m[((size_t)b * P.ecap) * NN_CH + lane];
+  // lane l owns channels 2l and 2l+1 of every 64-wide row: one 64-bit access per row and lane
+  constexpr int C2 = NODE_EMB / 2;            // float2 per row
   constexpr int ROW = PROJ_ROWS * NODE_EMB;   // floats per (node, part)
+  float2* Y = reinterpret_cast<float2*>(W.y);
+  float2* G = reinterpret_cast<float2*>(W.g);
+  const float2* DYN = reinterpret_cast<const float2*>(SW.dyn);
   // *_node goals: once an encode has added the interest node to the live graph (compressed:254-256) it is part of
   // every later encode, discovered or not
   const int interest = is_node_goal(P) ? T.sc_interest[sc] : -1;
@@ -156,30 +182,65 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   const bool extra = interest >= 0 && !interest_known && (scalar(S, P, S_FLAGS, b) & FL_INTEREST_IN_GRAPH);
   const int n = n_disc + (extra ? 1 : 0);
   uint8_t* order = W.ord;
+#ifdef CBS_OBS_SUBTRACE
+  if (tsub && n + E + node_off >= 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tsub[0]));   // the scalars have arrived
+#endif
 
   for (int i = lane; i < n; i += 32) {
     const int node = i < n_disc ? disc_order[i] : interest;
     W.ord[i] = (uint8_t)node;
     W.pos[node] = (uint8_t)i;
     W.dinv[i] = 1.f;
-    W.dynb[i] = pack_dyn(S, P, b, node);
+    const uint8_t db = pack_dyn(S, P, b, node);
+    W.dynb[i] = db;
     W.xst[i] = pack_xstatus(S, P, b, node);
+    // the node's root row (256 bytes of the folded table) on its way into L1 before the tiles below ask for it
+    const float* rr = T.node_static + ((size_t)(node_off + node) * 2 + (db & 1)) * ROW + 17 * NODE_EMB;
+    prefetch_l1(rr);
+    prefetch_l1(rr + 32);
   }
   __syncwarp();
+  SUBT(1);
 
-  // root term x_i W_root (+ conv bias folded into bn1 shift); ROOT_TILE nodes per pass so that their table rows are in flight
-  // together (a pass is one L2 round trip; four per pass made a 9-node graph wait three times)
-  constexpr int ROOT_TILE = 12;
+  // per edge of the block: source / target positions and the source's table row (visible / not-visible variant), lane-local
+  int my_is = 0, my_id = 0, my_row = 0;
+  auto edge_block = [&](int base, bool reload) {
+    if (reload) {
+      my_es = my_ed = 0;
+      if (base + lane < E) { my_es = es[base + lane]; my_ed = ed[base + lane]; }
+    }
+    my_is = my_id = my_row = 0;
+    if (base + lane < E) {
+      my_is = W.pos[my_es]; my_id = W.pos[my_ed];
+      my_row = (node_off + my_es) * 2 + (W.dynb[my_is] & 1);
+    }
+  };
+  // the 18 rows (4.5 KB) a source contributes to an edge message, requested into L1 one edge ahead
+  auto prefetch_rows = [&](int row) {
+    const float* base = T.node_static + (size_t)row * ROW;
+    prefetch_l1(base + lane * 32);
+    if (lane < (ROW * 4 / 128) - 32) prefetch_l1(base + (32 + lane) * 32);
+  };
+  edge_block(0, false);
+  if (E > 0) prefetch_rows(__shfl_sync(0xFFFFFFFFu, my_row, 0));
+
+  // root term x_i W_root (+ conv bias folded into bn1 shift); ROOT_TILE nodes per pass, their rows requested together.  The six
+  // weight pairs of the root row stay in registers; a node is twelve straight FMAs.
+  float2 wr[NUM_DYN];
+#pragma unroll
+  for (int d = 0; d < NUM_DYN; ++d) wr[d] = DYN[(d * PROJ_ROWS + 17) * C2 + lane];
+  constexpr int ROOT_TILE = 4;      // (2 / 4 / 8 / 12 nodes per pass: 37.6 / 36.7 / 37.2 / 39.8 us for the kernel)
   for (int i0 = 0; i0 < n; i0 += ROOT_TILE) {
-    float r0[ROOT_TILE], r1[ROOT_TILE];
+    float2 r[ROOT_TILE];
+    uint32_t dx[ROOT_TILE];
 #pragma unroll
     for (int j = 0; j < ROOT_TILE; ++j) {
       const int i = i0 + j;
-      r0[j] = r1[j] = 0.f;
+      r[j] = make_float2(0.f, 0.f);
+      dx[j] = 0;
       if (i < n) {
-        const float* ns = T.node_static + ((size_t)(node_off + order[i]) * 2 + (W.dynb[i] & 1)) * ROW + 17 * NODE_EMB;
-        r0[j] = ns[c0];
-        r1[j] = ns[c1];
+        dx[j] = (uint32_t)W.dynb[i] | ((uint32_t)W.xst[i] << 8);
+        r[j] = reinterpret_cast<const float2*>(T.node_static + ((size_t)(node_off + order[i]) * 2 + (dx[j] & 1)) * ROW + 17 * NODE_EMB)[lane];
       }
     }
 #pragma unroll
@@ -187,104 +248,130 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
       const int i = i0 + j;
       if (i >= n) break;
       float vis, x[NUM_DYN];
-      node_dyn(W.dynb[i], W.xst[i], vis, x);
-      float a0 = r0[j], a1 = r1[j];
+      node_dyn((uint8_t)dx[j], (uint8_t)(dx[j] >> 8), vis, x);
+      float2 a = r[j];
 #pragma unroll
       for (int d = 0; d < NUM_DYN; ++d) {
-        a0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c0], a0);
-        a1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + 17) * NODE_EMB + c1], a1);
+        a.x = fmaf(x[d], wr[d].x, a.x);
+        a.y = fmaf(x[d], wr[d].y, a.y);
       }
       if (EV && vis != 0.f) {
         const uint16_t* evx = S.ev_x + ((size_t)b * P.ncap + order[i]) * 4;
         const uint16_t* ini = T.nd_ev_init + (size_t)(node_off + order[i]) * 4;
-        a0 += ev_delta(T.ev_proj, evx, ini, 17, c0);
-        a1 += ev_delta(T.ev_proj, evx, ini, 17, c1);
+        a.x += ev_delta(T.ev_proj, evx, ini, 17, 2 * lane);
+        a.y += ev_delta(T.ev_proj, evx, ini, 17, 2 * lane + 1);
       }
-      W.y[i * NODE_EMB + c0] = a0;
-      W.y[i * NODE_EMB + c1] = a1;
+      Y[i * C2 + lane] = a;
     }
   }
   __syncwarp();
+  SUBT(2);
 
   // NNConv messages: y[dst] += [relu(m_e + b1); 1] . T_src
-  const uint8_t* es = S.edge_src + (size_t)b * P.ecap;
-  const uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
-  // the next edge's end points and attribute are requested while the current edge is combined (one exposed round trip less per edge)
-  int js_n = 0, jd_n = 0;
-  float hm_n = 0.f;
-  if (E > 0) {
-    js_n = es[0]; jd_n = ed[0];
-    if (lane < NN_CH) hm_n = S.edge_m[((size_t)b * P.ecap) * NN_CH + lane];
-  }
   for (int e = 0; e < E; ++e) {
-    const int js = js_n, jd = jd_n;
+    if ((e & 31) == 0 && e) edge_block(e, true);
+    const int is = __shfl_sync(0xFFFFFFFFu, my_is, e & 31), id = __shfl_sync(0xFFFFFFFFu, my_id, e & 31);
+    const int row = __shfl_sync(0xFFFFFFFFu, my_row, e & 31);
     const float hm = hm_n;
     if (e + 1 < E) {
-      js_n = es[e + 1]; jd_n = ed[e + 1];
       if (lane < NN_CH) hm_n = S.edge_m[((size_t)b * P.ecap + e + 1) * NN_CH + lane];
+      if (((e + 1) & 31) != 0) prefetch_rows(__shfl_sync(0xFFFFFFFFu, my_row, (e + 1) & 31));
     }
-    const int is = W.pos[js], id = W.pos[jd];
     float hl = 0.f;
     if (lane < NN_CH) hl = fmaxf(hm + SW.nn0b[lane], 0.f);
     else if (lane == NN_CH) hl = 1.f;
     float vis, x[NUM_DYN];
     node_dyn(W.dynb[is], W.xst[is], vis, x);
-    const float* ns = T.node_static + ((size_t)(node_off + js) * 2 + (vis != 0.f ? 1 : 0)) * ROW;   // visible / not-visible variant
+    const float2* ns = reinterpret_cast<const float2*>(T.node_static + (size_t)row * ROW);
+    const int js = row / 2 - node_off;
     const bool evd = EV && vis != 0.f;
     const uint16_t* evx = evd ? S.ev_x + ((size_t)b * P.ncap + js) * 4 : nullptr;
     const uint16_t* ini = evd ? T.nd_ev_init + (size_t)(node_off + js) * 4 : nullptr;
     const bool ev_any = evd && (((evx[0] ^ ini[0]) | (evx[1] ^ ini[1]) | (evx[2] ^ ini[2])) & 0x3FF) != 0;
-    float m0 = 0.f, m1 = 0.f;
+    // t_k = static row k + sum over the NON-ZERO dynamic scalars (ascending d, so every t_k sums in the order it always did;
+    // fmaf(0, w, t) == t).  The 18 row loads stay unrolled — they must all be in flight together: with a rolled loop over k (three
+    // rows per pass) an edge took 2.9 us instead of 1.0 — but the pass per scalar is rolled: unrolled over the six scalars it was
+    // 5 KB of straight-line code that every warp streamed through the instruction cache once per edge (observe 39.8 -> 36.6 us).
+    float2 t[NN_CH + 1];
+#pragma unroll
+    for (int k = 0; k < NN_CH + 1; ++k) t[k] = ns[k * C2 + lane];
+    uint32_t nzl = 0;      // the non-zero scalars, ascending: 4 bits each
+    int nnz = 0;
+#pragma unroll
+    for (int d = 0; d < NUM_DYN; ++d) if (x[d] != 0.f) { nzl |= (uint32_t)d << (4 * nnz); ++nnz; }
+#pragma unroll 1
+    for (int q = 0; q < nnz; ++q) {
+      const int d = (nzl >> (4 * q)) & 15;
+      const float xd = d < 4 ? 1.f : (d == 4 ? x[4] : x[5]);
+      const float2* dw = DYN + (size_t)d * PROJ_ROWS * C2 + lane;
+#pragma unroll
+      for (int k = 0; k < NN_CH + 1; ++k) {
+        const float2 w = dw[k * C2];
+        t[k].x = fmaf(xd, w.x, t[k].x);
+        t[k].y = fmaf(xd, w.y, t[k].y);
+      }
+    }
+    float2 m = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < NN_CH + 1; ++k) {
       const float hk = __shfl_sync(0xFFFFFFFFu, hl, k);
-      float t0 = ns[k * NODE_EMB + c0];
-      float t1 = ns[k * NODE_EMB + c1];
-#pragma unroll
-      for (int d = 0; d < NUM_DYN; ++d) {
-        t0 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c0], t0);
-        t1 = fmaf(x[d], SW.dyn[(d * PROJ_ROWS + k) * NODE_EMB + c1], t1);
-      }
-      if (EV && ev_any) { t0 += ev_delta(T.ev_proj, evx, ini, k, c0); t1 += ev_delta(T.ev_proj, evx, ini, k, c1); }
-      m0 = fmaf(hk, t0, m0);
-      m1 = fmaf(hk, t1, m1);
+      if (EV && ev_any) { t[k].x += ev_delta(T.ev_proj, evx, ini, k, 2 * lane); t[k].y += ev_delta(T.ev_proj, evx, ini, k, 2 * lane + 1); }
+      m.x = fmaf(hk, t[k].x, m.x);
+      m.y = fmaf(hk, t[k].y, m.y);
     }
-    W.y[id * NODE_EMB + c0] += m0;
-    W.y[id * NODE_EMB + c1] += m1;
+    float2 yv = Y[id * C2 + lane];
+    yv.x += m.x; yv.y += m.y;
+    Y[id * C2 + lane] = yv;
     if (lane == 0 && is != id) W.dinv[id] += 1.f;           // GCN in-degree (self loops are replaced, not counted)
     __syncwarp();
   }
+  SUBT(3);
   for (int i = lane; i < n; i += 32) W.dinv[i] = rsqrtf(W.dinv[i]);
-  // BatchNorm(eval) + ReLU, then the GCN projection G = H1 Wg^T
-  for (int i = 0; i < n; ++i) {
-    W.y[i * NODE_EMB + c0] = fmaxf(fmaf(W.y[i * NODE_EMB + c0], SW.bn1s[c0], SW.bn1h[c0]), 0.f);
-    W.y[i * NODE_EMB + c1] = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn1s[c1], SW.bn1h[c1]), 0.f);
+  // BatchNorm(eval) + ReLU, then the GCN projection G = H1 Wg^T.  Node loops run four nodes per pass, loads before stores: one
+  // node per pass is a chain of dependent shared-memory round trips (the compiler must keep a load behind the previous store).
+  const float2 b1s = reinterpret_cast<const float2*>(SW.bn1s)[lane], b1h = reinterpret_cast<const float2*>(SW.bn1h)[lane];
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    float2 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (i0 + j < n) v[j] = Y[(i0 + j) * C2 + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + j < n) Y[(i0 + j) * C2 + lane] = make_float2(fmaxf(fmaf(v[j].x, b1s.x, b1h.x), 0.f), fmaxf(fmaf(v[j].y, b1s.y, b1h.y), 0.f));
   }
   __syncwarp();
+  SUBT(4);
   // Several nodes per pass: each weight pair feeds two independent FMA chains per node, and a pass's broadcast reads of the
-  // nodes' activations are all in flight together (two nodes per pass left the loop a chain of dependent shared-memory reads).
-  // Passes of 8, then 4 / 2 / 1 for the remainder, so that no pass computes padding.  Every node's sum runs over k in the same
-  // order whatever the tile, so equal inputs still give bit-identical outputs.
+  // nodes' activations (128 bits = four k at a time) are all in flight together.  Passes of 8, then 4 / 2 / 1 for the remainder,
+  // so that no pass computes padding.  Every node's sum runs over k in the same order whatever the tile, so equal inputs still
+  // give bit-identical outputs.  A pass ends by clearing its rows of Y for the aggregation that follows.
   auto gcn_pass = [&](auto tile_c, int i0) {
     constexpr int TILE = decltype(tile_c)::value;
-    float acc0[TILE], acc1[TILE];
+    float2 acc[TILE];
 #pragma unroll
-    for (int j = 0; j < TILE; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-    const float* yrow = W.y + i0 * NODE_EMB;
-#pragma unroll 4
-    for (int k = 0; k < NODE_EMB; ++k) {
-      const float w0 = SW.gcn[k * NODE_EMB + c0], w1 = SW.gcn[k * NODE_EMB + c1];
+    for (int j = 0; j < TILE; ++j) acc[j] = make_float2(0.f, 0.f);
+    const float4* yrow = reinterpret_cast<const float4*>(W.y + i0 * NODE_EMB);
+    const float2* gw = reinterpret_cast<const float2*>(SW.gcn);
+#pragma unroll 2
+    for (int k4 = 0; k4 < NODE_EMB / 4; ++k4) {
+      float2 w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = gw[(k4 * 4 + q) * C2 + lane];
+      float4 a[TILE];
+#pragma unroll
+      for (int j = 0; j < TILE; ++j) a[j] = yrow[j * (NODE_EMB / 4) + k4];
 #pragma unroll
       for (int j = 0; j < TILE; ++j) {
-        const float a = yrow[j * NODE_EMB + k];
-        acc0[j] = fmaf(a, w0, acc0[j]);
-        acc1[j] = fmaf(a, w1, acc1[j]);
+        acc[j].x = fmaf(a[j].x, w[0].x, acc[j].x); acc[j].y = fmaf(a[j].x, w[0].y, acc[j].y);
+        acc[j].x = fmaf(a[j].y, w[1].x, acc[j].x); acc[j].y = fmaf(a[j].y, w[1].y, acc[j].y);
+        acc[j].x = fmaf(a[j].z, w[2].x, acc[j].x); acc[j].y = fmaf(a[j].z, w[2].y, acc[j].y);
+        acc[j].x = fmaf(a[j].w, w[3].x, acc[j].x); acc[j].y = fmaf(a[j].w, w[3].y, acc[j].y);
       }
     }
+    __syncwarp();                       // every lane has read the whole rows before they are cleared
 #pragma unroll
     for (int j = 0; j < TILE; ++j) {
-      W.g[(i0 + j) * NODE_EMB + c0] = acc0[j];
-      W.g[(i0 + j) * NODE_EMB + c1] = acc1[j];
+      G[(i0 + j) * C2 + lane] = acc[j];
+      Y[(i0 + j) * C2 + lane] = make_float2(0.f, 0.f);
     }
   };
   {
@@ -295,45 +382,55 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
     if (i0 < n) gcn_pass(std::integral_constant<int, 1>{}, i0);
   }
   __syncwarp();
+  SUBT(5);
   // normalised aggregation, edges first and the self loop last (the order PyG's add_remaining_self_loops +
   // scatter-add gives).  Products and sums are rounded separately (no FMA contraction): a pair of nodes that
   // attack each other then gets bit-identical embeddings, exactly as in the reference, and the exact ties this
   // creates in the action table resolve by insertion order instead of by rounding noise.
-  for (int i = 0; i < n; ++i) {
-    W.y[i * NODE_EMB + c0] = 0.f;
-    W.y[i * NODE_EMB + c1] = 0.f;
-  }
-  __syncwarp();
+  if (E > 32) edge_block(0, true);
   for (int e = 0; e < E; ++e) {
-    const int is = W.pos[es[e]], id = W.pos[ed[e]];
+    if ((e & 31) == 0 && e) edge_block(e, true);
+    const int is = __shfl_sync(0xFFFFFFFFu, my_is, e & 31), id = __shfl_sync(0xFFFFFFFFu, my_id, e & 31);
     if (is == id) continue;
     const float w = __fmul_rn(W.dinv[is], W.dinv[id]);
-    W.y[id * NODE_EMB + c0] = __fadd_rn(W.y[id * NODE_EMB + c0], __fmul_rn(w, W.g[is * NODE_EMB + c0]));
-    W.y[id * NODE_EMB + c1] = __fadd_rn(W.y[id * NODE_EMB + c1], __fmul_rn(w, W.g[is * NODE_EMB + c1]));
+    const float2 g = G[is * C2 + lane];
+    float2 yv = Y[id * C2 + lane];
+    yv.x = __fadd_rn(yv.x, __fmul_rn(w, g.x));
+    yv.y = __fadd_rn(yv.y, __fmul_rn(w, g.y));
+    Y[id * C2 + lane] = yv;
     __syncwarp();
   }
-  for (int i = 0; i < n; ++i) {
-    const float d2 = __fmul_rn(W.dinv[i], W.dinv[i]);
-    W.y[i * NODE_EMB + c0] = __fadd_rn(W.y[i * NODE_EMB + c0], __fmul_rn(d2, W.g[i * NODE_EMB + c0]));
-    W.y[i * NODE_EMB + c1] = __fadd_rn(W.y[i * NODE_EMB + c1], __fmul_rn(d2, W.g[i * NODE_EMB + c1]));
-  }
-  __syncwarp();
-  // BatchNorm + ReLU -> z ; readout over Running nodes (mean | max | min), compressed:266-298
+  SUBT(6);
+  // self loop, BatchNorm + ReLU -> z ; readout over Running nodes (mean | max | min), compressed:266-298
+  const float2 b2s = reinterpret_cast<const float2*>(SW.bn2s)[lane], b2h = reinterpret_cast<const float2*>(SW.bn2h)[lane];
   float s0 = 0.f, s1 = 0.f, mx0 = -INFINITY, mx1 = -INFINITY, mn0 = INFINITY, mn1 = INFINITY;
   int running = 0;
-  for (int i = 0; i < n; ++i) {
-    const float z0 = fmaxf(fmaf(W.y[i * NODE_EMB + c0], SW.bn2s[c0], SW.bn2h[c0]), 0.f);
-    const float z1 = fmaxf(fmaf(W.y[i * NODE_EMB + c1], SW.bn2s[c1], SW.bn2h[c1]), 0.f);
-    W.y[i * NODE_EMB + c0] = z0;
-    W.y[i * NODE_EMB + c1] = z1;
-    if (W.dynb[i] & 0x80) {
-      ++running;
-      s0 += z0; s1 += z1;
-      mx0 = fmaxf(mx0, z0); mx1 = fmaxf(mx1, z1);
-      mn0 = fminf(mn0, z0); mn1 = fminf(mn1, z1);
+  for (int i0 = 0; i0 < n; i0 += 4) {
+    float2 yv[4], gv[4];
+    float dv[4];
+    uint8_t db[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) { yv[j] = Y[(i0 + j) * C2 + lane]; gv[j] = G[(i0 + j) * C2 + lane]; dv[j] = W.dinv[i0 + j]; db[j] = W.dynb[i0 + j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j >= n) break;
+      const float d2 = __fmul_rn(dv[j], dv[j]);
+      const float y0 = __fadd_rn(yv[j].x, __fmul_rn(d2, gv[j].x)), y1 = __fadd_rn(yv[j].y, __fmul_rn(d2, gv[j].y));
+      const float z0 = fmaxf(fmaf(y0, b2s.x, b2h.x), 0.f), z1 = fmaxf(fmaf(y1, b2s.y, b2h.y), 0.f);
+      Y[(i0 + j) * C2 + lane] = make_float2(z0, z1);
+      if (db[j] & 0x80) {
+        ++running;
+        s0 += z0; s1 += z1;
+        mx0 = fmaxf(mx0, z0); mx1 = fmaxf(mx1, z1);
+        mn0 = fminf(mn0, z0); mn1 = fminf(mn1, z1);
+      }
     }
   }
+  SUBT(7);
   float* obs = S.obs + (size_t)b * P.obs_dim;
+  const int c0 = 2 * lane, c1 = 2 * lane + 1;
   const bool none_running = running == 0;
   if (none_running) { s0 = s1 = mx0 = mx1 = mn0 = mn1 = 0.f; running = 1; }
   obs[c0] = s0 / (float)running;
@@ -345,13 +442,14 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
   if (interest >= 0) {   // compressed:299-303: the interest node's own embedding, zeros if it is not in the graph / not Running
     const int ip = interest_known ? (int)W.pos[interest] : (extra ? n_disc : -1);
     const bool have = ip >= 0 && !none_running && (W.dynb[ip] & 0x80);
+    __syncwarp();
     obs[OBS_GRAPH + c0] = have ? W.y[ip * NODE_EMB + c0] : 0.f;
     obs[OBS_GRAPH + c1] = have ? W.y[ip * NODE_EMB + c1] : 0.f;
   }
   if (lane == 0) {
     obs[P.obs_dim - 2] = (float)n_disc;                     // create_discrete_features, compressed:309-316
-    obs[P.obs_dim - 1] = (float)scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);   // len(owned_nodes)
-    scalar(S, P, S_N_ENCODES, b) += 1;
+    obs[P.obs_dim - 1] = (float)n_owned_obs;                // len(owned_nodes)
+    scalar(S, P, S_N_ENCODES, b) = n_encodes + 1;
   }
   __syncwarp();
 }
@@ -411,17 +509,34 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   auto in_reach = [&](int n) { return ((reach[n >> 5] >> (n & 31)) & 1u) != 0u; };
   // sources: env.owned_nodes.  Under a defender that is the exact list (removals, duplicates: the dict comprehension of
   // compressed:491-492 keeps the first occurrence); otherwise the append-only list.
+  // Everything that depends on the env index alone is requested first and together (the scalars, both node orders, the counter
+  // updated at the end, the pair plane on its way into L1): read where they were used, the loops below were a chain of dependent
+  // round trips, one per source and one per stored node.
   const int n_disc = scalar(S, P, S_N_DISC, b), n_owned = scalar(S, P, P.defender ? S_N_OWNED_RAW : S_N_OWNED, b);
   const uint8_t* dorder = S.disc_order + (size_t)b * P.ncap;
   const uint8_t* oorder = P.defender ? S.owned_raw + (size_t)b * P.ocap : S.owned_order + (size_t)b * P.ncap;
   uint8_t* ps = S.pair_slot + (size_t)b * P.ncap * P.ncap;
   uint8_t* po = S.pair_opos + (size_t)b * P.ncap * P.ncap;
   uint8_t* pe = S.pair_epoch + (size_t)b * P.ncap * P.ncap;
+  for (int l = lane; l * 128 < P.ncap * P.ncap; l += 32) prefetch_l1(ps + l * 128);
   const int slot = scalar(S, P, S_N_SLOTS, b);
+  int work_est0 = 0;
+  if (lane == 0 && !SUBSET) work_est0 = S.work_est[b];
+  int my_t = lane < P.ncap ? dorder[lane] : 0;                 // discovered position `lane` (first block of 32 targets)
+  int my_o = lane < (P.defender ? P.ocap : P.ncap) ? oorder[lane] : 0;   // owned position `lane` (first block of 32 sources)
+  // per target: candidate rows of a remote / a local pair (what a new pair adds to the env's decode work estimate)
+  int rows_remote0 = 0, rows_self0 = 0;
+  auto target_rows = [&](int t, int& rr, int& rs) {
+    const int g = node_off_bt + t;
+    const int o0 = T.nd_row_off[2 * g], o1 = T.nd_row_off[2 * g + 1], o2 = T.nd_row_off[2 * g + 2];
+    rr = o2 - o1; rs = o2 - o0;
+  };
+  if (lane < n_disc) target_rows(my_t, rows_remote0, rows_self0);
   bool any_new = false;
   uint32_t seen[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
   for (int op = 0; op < n_owned; ++op) {
-    const int s = oorder[op];
+    if ((op & 31) == 0 && op) my_o = op + lane < n_owned ? oorder[op + lane] : 0;
+    const int s = __shfl_sync(0xFFFFFFFFu, my_o, op & 31);
     if (P.defender) {
       if ((seen[s >> 5] >> (s & 31)) & 1u) continue;
       seen[s >> 5] |= 1u << (s & 31);
@@ -431,7 +546,8 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
       const int dp = base + lane;
       bool fresh = false, fresh_refresh_only = false;
       if (dp < n_disc) {
-        const int t = dorder[dp];
+        int t = my_t, rr = rows_remote0, rs = rows_self0;
+        if (base) { t = dorder[dp]; target_rows(t, rr, rs); }
         const bool is_new = ps[s * P.ncap + t] == 0xFF;
         fresh_refresh_only = !is_new;
         fresh = (W.dynb[dp] & 0x80) && (is_new || (PRECISE && refresh && (in_reach(s) || in_reach(t))));
@@ -440,8 +556,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
           if (is_new) {
             if (P.defender) po[s * P.ncap + t] = (uint8_t)op;   // insertion order inside the slot (exact-tie order of the decode)
             if (PRECISE) pe[s * P.ncap + t] = (uint8_t)slot;
-            const int g = node_off_bt + t;
-            new_rows += T.nd_row_off[2 * g + 2] - T.nd_row_off[2 * g + (s == t ? 0 : 1)];
+            new_rows += s == t ? rs : rr;
           }
         }
       }
@@ -460,12 +575,13 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   }
   if (slot >= P.slots) { if (lane == 0) atomicExch(S.errflag, 1); return; }
   new_rows = (int)warp_sum((float)new_rows);
-  if (lane == 0 && !SUBSET) S.work_est[b] += new_rows;
+  if (lane == 0 && !SUBSET) S.work_est[b] = work_est0 + new_rows;
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
+#pragma unroll 2
   for (int i = 0; i < n_disc; ++i) {
-    const int node = dorder[i];
+    const int node = i < 32 ? __shfl_sync(0xFFFFFFFFu, my_t, i) : (int)dorder[i];
     if (!(W.dynb[i] & 0x80)) continue;                   // only Running nodes have embeddings (compressed:266-280)
     const float2 z = reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane];   // channels 2*lane, 2*lane+1
     reinterpret_cast<float2*>(zh + node * NODE_EMB)[lane] = z;
@@ -671,8 +787,9 @@ __device__ void reset_cache_publish(const Tables& T, const Params& P, const Stat
 }
 
 // BIG_GRAPHS: scenarios with more than 32 nodes exist, so an env's graph may outgrow the shared-memory buffers
-template <bool BIG_GRAPHS, bool SUBSET>
-__global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(Tables T, Params P, State S,
+// PRECISE: precise_action_space_positions is configured (compile-time like SUBSET: one build_table instance per kernel)
+template <bool BIG_GRAPHS, bool SUBSET, bool PRECISE>
+__global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Tables T, Params P, State S,
                                                                 const uint8_t* __restrict__ reset_mask, int mode,
                                                                 long long* __restrict__ trace) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -709,7 +826,7 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
   const int gw = blockIdx.x * OBS_WARPS + warp, total_warps = gridDim.x * OBS_WARPS;
 
   // per-warp scratch
-  unsigned char* wbase = smem_raw + sizeof(SharedWeights);
+  unsigned char* wbase = smem_raw + kSharedWeightsBytes;
   constexpr size_t kWarpBytesSmem = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 4 * MAX_NODES;
   WarpScratch W;
   {
@@ -731,20 +848,31 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
   int count = 0;
 #pragma unroll
   for (int k = 0; k < OBS_CLASSES; ++k) { count += (mode == 1) ? (k == 0 ? P.B : 0) : S.work_ctr[4 + k]; cls_end[k] = count; }
-  int i = gw;                                   // mode 1: static stride.  mode 0: items are claimed one at a time
-  for (;;) {
-    if (mode == 0) {
-      if (lane == 0) i = atomicAdd(&S.work_ctr[2], 1);
-      i = __shfl_sync(0xFFFFFFFFu, i, 0);
-    }
-    if (i >= count) break;
-    int b = i;
-    if (mode == 0) {
-      int k = 0, first = 0;
+  // mode 1: static stride.  mode 0: items are claimed one at a time.  The claim for the NEXT item is issued when the current item
+  // is nearly done (after its encode; at once for the short edge-only items), so that the atomic's round trip is hidden but no
+  // warp sits on a claimed heavy item: claimed a whole item ahead, the kernel ran 51 us instead of 40 (the heaviest items are
+  // first in the queue, and a warp busy with one held the next one back).
+  int i = gw, pend = 0;
+  bool claimed = false;
+  auto claim_next = [&]() {
+    if (mode != 0 || claimed) return;
+    claimed = true;
+    if (lane == 0) pend = atomicAdd(&S.work_ctr[2], 1);
+  };
+  auto lookup = [&](int item) {
+    int k = 0, first = 0;
 #pragma unroll
-      for (int q = 0; q < OBS_CLASSES - 1; ++q) if (i >= cls_end[q]) { k = q + 1; first = cls_end[q]; }
-      b = S.worklist[(size_t)k * P.B + (i - first)];
-    }
+    for (int q = 0; q < OBS_CLASSES - 1; ++q) if (item >= cls_end[q]) { k = q + 1; first = cls_end[q]; }
+    return S.worklist[(size_t)k * P.B + (item - first)];
+  };
+  if (mode == 0) {
+    claim_next();
+    i = __shfl_sync(0xFFFFFFFFu, pend, 0);
+  }
+  for (;;) {
+    if (i >= count) break;
+    const int b = mode == 0 ? lookup(i) : i;
+    claimed = false;
     // node-embedding buffers: shared memory while the env's visible graph has <= 32 nodes (always, when the
     // scenarios have <= 32 nodes), its slab of the L2-resident scratch otherwise.  A reset shrinks the graph to 1 node.
     if (BIG_GRAPHS) {
@@ -753,23 +881,36 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
       W.g = small ? W.ysm + SMEM_NODES * NODE_EMB : W.y + (size_t)P.ncap * NODE_EMB;
     }
     const int flags = scalar(S, P, S_FLAGS, b);
-    long long t_item = 0, t_ph[5] = {0, 0, 0, 0, 0};
+#ifdef CBS_OBS_SUBTRACE
+    constexpr int TR_PH = 14;      // debug build: trace rows of 4 + 14 values, slots 5.. = the encode's sub-phases
+#else
+    constexpr int TR_PH = 5;
+#endif
+    long long t_item = 0, t_ph[TR_PH] = {};
     if (trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_item));
     bool do_reset = false;
     if (mode == 1) {
       do_reset = reset_mask ? (reset_mask[b] != 0) : true;
     } else if (!(flags & FL_NEEDS_RESET)) {
       int keep = flags & ~(FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP);
+      if (!(flags & (FL_REENCODE | FL_FINISHED_THIS_STEP))) claim_next();    // a short item
       if (flags & FL_ADD_EDGE) edge_update(T, P, S, b, lane);
+#ifdef CBS_OBS_SUBTRACE
+      if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[13])); }
+#endif
       if (flags & FL_REENCODE) {
+#ifdef CBS_OBS_SUBTRACE
+        if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane, trace ? t_ph + 5 : nullptr); else encode_env<false>(T, P, S, SW, W, b, lane, trace ? t_ph + 5 : nullptr);
+#else
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
+#endif
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
         // (an env that finished in this step drops its action table at the reset that follows: only the sub-sampled table is
         // still maintained, because every create_continuous_action_space advances the env's balance counter)
+        if (!(flags & FL_FINISHED_THIS_STEP)) claim_next();
         if (!(flags & FL_FINISHED_THIS_STEP) || SUBSET) {
           const int skipped = SUBSET ? (flags >> FL_PENDING_SHIFT) & 0xFFFF : 0;
-          if (P.precise_positions) build_table<true, SUBSET>(T, P, S, W, b, lane, true, skipped);
-          else build_table<false, SUBSET>(T, P, S, W, b, lane, false, skipped);
+          build_table<PRECISE, SUBSET>(T, P, S, W, b, lane, PRECISE, skipped);
           keep &= 0xFFFF;
         }
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }
@@ -792,13 +933,13 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
         __syncwarp();
       }
       const int2 ss = reset_env(T, P, S, b, lane);
+      claim_next();
       if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[3])); }
       if (!reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
-        if (P.precise_positions) build_table<true, SUBSET>(T, P, S, W, b, lane, false);
-        else build_table<false, SUBSET>(T, P, S, W, b, lane, false);
+        build_table<PRECISE, SUBSET>(T, P, S, W, b, lane, false);
         reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);
       } else if constexpr (SUBSET) {
         // the cached first observation is per (scenario, starter); the sub-sampled table is per env: its one pair (starter,
@@ -819,13 +960,14 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
     if (trace && lane == 0) {   // debug: per item {start ns, duration ns, flags at entry, nodes << 16 | edges}
       long long t_end;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
-      long long* tr = trace + (size_t)b * 9;
-      tr[0] = t_item; tr[1] = t_end - t_item; tr[2] = flags;
+      long long* tr = trace + (size_t)b * (4 + TR_PH);
+      tr[0] = t_item; tr[1] = t_end - t_item; tr[2] = (long long)(unsigned)flags | ((long long)(blockIdx.x * OBS_WARPS + warp) << 32);
       tr[3] = ((long long)scalar(S, P, S_N_DISC, b) << 16) | scalar(S, P, S_N_EDGES, b);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) tr[4 + k] = t_ph[k] ? t_ph[k] - t_item : 0;   // phase end times relative to the item start
+      for (int k = 0; k < TR_PH; ++k) tr[4 + k] = t_ph[k] ? t_ph[k] - t_item : 0;   // phase end times relative to the item start
     }
-    if (mode == 1) i += total_warps;
+    claim_next();
+    if (mode == 1) i += total_warps; else i = __shfl_sync(0xFFFFFFFFu, pend, 0);
   }
   // the CTA's last warp adds the CTA's episode sums to the global accumulators (one atomic per slot and CTA)
   __syncwarp();
@@ -836,9 +978,10 @@ __global__ void __launch_bounds__(OBS_WARPS * 32, CBS_OBS_MINB) observe_kernel(T
     const double v = SW.accum[lane];
     if (v != 0.0) atomicAdd(&S.accum[lane], v);
   }
-  if (mode == 0 && lane == 0) {   // the last warp to run dry clears the counters for the next transition
-    __threadfence();
-    if (atomicAdd(&S.work_ctr[1], 1) == total_warps - 1) {
+  // the last CTA to run dry clears the counters for the next transition.  No fence: a warp gets here after its last claim has
+  // RETURNED (the value ended its loop), so every claim precedes the count that detects the last CTA.
+  if (mode == 0 && last_in_cta && lane == 0) {
+    if (atomicAdd(&S.work_ctr[1], 1) == (int)gridDim.x - 1) {
       S.work_ctr[1] = 0; S.work_ctr[2] = 0;
 #pragma unroll
       for (int k = 0; k < OBS_CLASSES; ++k) S.work_ctr[4 + k] = 0;
@@ -851,7 +994,7 @@ long long* g_obs_trace = nullptr;   // debug: per-env {start ns, duration ns, fl
 
 size_t observe_smem_bytes() {
   const size_t per_warp = (size_t)2 * SMEM_NODES * NODE_EMB * 4 + MAX_NODES * 4 + 4 * MAX_NODES;
-  return sizeof(SharedWeights) + OBS_WARPS * per_warp;
+  return kSharedWeightsBytes + OBS_WARPS * per_warp;
 }
 
 cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, const uint8_t* reset_mask, int mode,
@@ -863,14 +1006,24 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
   const int need = (P.B + OBS_WARPS - 1) / OBS_WARPS;
   if (grid > need) grid = need;
   using KernelFn = void (*)(Tables, Params, State, const uint8_t*, int, long long*);
-  const KernelFn kernels[4] = {observe_kernel<false, false>, observe_kernel<true, false>, observe_kernel<false, true>, observe_kernel<true, true>};
-  const int which = (big ? 1 : 0) | (P.subset_k ? 2 : 0);
-  static bool attr_set[4] = {false, false, false, false};
+#ifdef CBS_OBS_ONLY_DEFAULT   // experiments: build the default instance alone (a full build of this file takes two minutes)
+  const KernelFn kernels[8] = {observe_kernel<false, false, false>, observe_kernel<false, false, false>, observe_kernel<false, false, false>,
+                               observe_kernel<false, false, false>, observe_kernel<false, false, false>, observe_kernel<false, false, false>,
+                               observe_kernel<false, false, false>, observe_kernel<false, false, false>};
+  if (big || P.subset_k || P.precise_positions) { fprintf(stderr, "CBS_OBS_ONLY_DEFAULT build\n"); abort(); }
+#else
+  const KernelFn kernels[8] = {observe_kernel<false, false, false>, observe_kernel<true, false, false>, observe_kernel<false, true, false>,
+                               observe_kernel<true, true, false>,   observe_kernel<false, false, true>, observe_kernel<true, false, true>,
+                               observe_kernel<false, true, true>,   observe_kernel<true, true, true>};
+#endif
+  const int which = (big ? 1 : 0) | (P.subset_k ? 2 : 0) | (P.precise_positions ? 4 : 0);
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
   if (!attr_set[which]) {
     cudaError_t e = cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     attr_set[which] = true;
   }
+  // (pinning the folded node table in L2 with an access-policy window on this launch changed nothing: 37.1 us either way)
   kernels[which]<<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
   return cudaGetLastError();
 }
