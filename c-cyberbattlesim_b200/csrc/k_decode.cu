@@ -198,16 +198,15 @@ __device__ __forceinline__ void flush_candidates(const Tables& T, const Params& 
   ncand = 0;
 }
 
-// every warp calls this exactly once when it is finished; the last one clears the cost bins for the next transition
+// Once per CTA, after the barrier that follows its schedule lookup: the last CTA to get there clears the cost bins for the next
+// transition.  Every CTA counts itself only after its own reads of the bins have returned (their values addressed the loads in
+// front of the barrier), so the clear needs no fence — the per-warp fence + atomic at the kernel's end was 4 % of its warp time.
 __device__ __forceinline__ void sched_done(const State& S, int buf) {
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
+  if (threadIdx.x == 0) {
     int32_t* cnt = S.bin_cnt + buf * (SCHED_BINS + 1);
-    __threadfence();
-    if (atomicAdd(&cnt[SCHED_BINS], 1) == (int)(gridDim.x * SEL_WARPS) - 1) {
+    if (atomicAdd(&cnt[SCHED_BINS], 1) == (int)gridDim.x - 1) {
 #pragma unroll
       for (int k = 0; k <= SCHED_BINS; ++k) cnt[k] = 0;
-      __threadfence();
     }
   }
 }
@@ -288,6 +287,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     na = sqrt(warp_sum(n0 + n1));
   }
   __syncthreads();
+  sched_done(S, sched_buf);
   // a finished env (the reference raises there, cyberbattle_env.py:300-302) decodes to zeros
   const bool active = in_range && !(flags & (FL_DONE | FL_TRUNC | FL_NEEDS_RESET));
   int4 out = make_int4(0, 0, 0, 0);      // lane 0 holds the env's result
@@ -565,7 +565,6 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
       tin.store_hot(S, bb);
     }
   }
-  sched_done(S, sched_buf);
 }
 
 long long* g_sel_trace = nullptr;   // debug: per-env {cycles, rows, live pairs, parked candidates, combos, start clock}
