@@ -25,8 +25,8 @@ constexpr int SCAL_PITCH = 32;  // int32 words per env in State::scal: four sect
 constexpr int RC_Z = 264;       // floats [0, obs_dim) observation, [RC_Z, RC_Z + 64) the starter's embedding, [RC_N2] its squared norm
 constexpr int RC_N2 = RC_Z + NODE_EMB;
 constexpr int RC_PITCH = 336;
-constexpr int OBS_CLASSES = 6;  // observe work classes, heaviest first (transition.cuh): the observe kernel's duration is set by its
-                                // longest items (an episode end behind a 30-node re-encode), so they must be claimed first
+constexpr int OBS_CLASSES = 16; // observe work classes, heaviest first (transition.cuh): cost buckets of 2.5 us.  The observe kernel's duration
+                                // is set by how well its ~2 heavy items per warp pack, so they are claimed longest first
 constexpr int SUB_CLASSES = 10;   // outcome kinds that can have action-table rows (K_DOS .. K_LATERAL; Execution never does)
 constexpr int SUB_META = 16;      // int32 per env in State::sub_meta: [0, 10) rows alive per class, [10] classes ranked so far, [11], [12] the
                                   // classes' first-appearance rank (4 bits per kind, 15 = not in the table yet), [13] lifetime count of balance calls
@@ -78,6 +78,7 @@ enum Scalar : int {
   S_SCENARIO = 16, S_STARTER, S_NODE_OFF, S_OWNABLE, S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES, S_DISCOVERABLE_AMOUNT,
   // sector 3
   S_EPISODES = 24,
+  S_UVULN_OFF,      // T.sc_uvuln_off[scenario], kept per env by the reset (one dependent table read less per edge update)
   N_SCALARS };
 // S_FLAGS bits
 constexpr int FL_DONE = 1, FL_TRUNC = 2, FL_REASON_SHIFT = 2 /*2 bits*/, FL_ADD_EDGE = 16, FL_REENCODE = 32,

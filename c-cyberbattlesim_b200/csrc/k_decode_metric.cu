@@ -301,12 +301,10 @@ __global__ void __launch_bounds__(MET_THREADS) metric_select_kernel(Tables T, Pa
   // every warp reports once; the last one clears this step's cost bins for the transition after next (as decode_select does)
   __syncwarp();
   if (lane == 0) {
-    int32_t* cnt = S.bin_cnt + sched_buf * (SCHED_BINS + 1);
-    __threadfence();
+    int32_t* cnt = S.bin_cnt + sched_buf * (SCHED_BINS + 1);     // (no fence: the warp's own reads of the bins returned long ago)
     if (atomicAdd(&cnt[SCHED_BINS], 1) == (int)(gridDim.x * MET_WARPS) - 1) {
 #pragma unroll
       for (int k = 0; k <= SCHED_BINS; ++k) cnt[k] = 0;
-      __threadfence();
     }
   }
 }

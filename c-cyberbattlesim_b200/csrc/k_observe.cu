@@ -101,25 +101,32 @@ __device__ __forceinline__ float ev_delta(const float* __restrict__ ev_proj, con
 }
 
 // ---- add_edge_evolving_visible_graph (compressed:214-246), mean aggregation, in the W1-projected space ----
+// Everything that depends on the env index alone is requested first (the selected action, the counters, the first 32 edges and
+// their counts): in program order — scenario -> vulnerability offset -> global vulnerability -> its hidden vector, then the edge
+// count -> the list -> the hit's accumulator — the function was six dependent round trips, 1.8 us per item and a tenth of the
+// kernel's warp time.
 __device__ void edge_update(const Tables& T, const Params& P, const State& S, int b, int lane) {
   const int4 sl = reinterpret_cast<const int4*>(S.sel)[b];
   const int s = sl.x, t = sl.y, u = sl.z;
-  const int sc = scalar(S, P, S_SCENARIO, b);
-  const int gv = T.uvuln_global[T.sc_uvuln_off[sc] + u];
-  const float p = lane < NN_CH ? T.vuln_h[(size_t)gv * NN_CH + lane] : 0.f;
-  int E = scalar(S, P, S_N_EDGES, b);
+  const int uvoff = scalar(S, P, S_UVULN_OFF, b);
+  const int E = scalar(S, P, S_N_EDGES, b);
   uint8_t* es = S.edge_src + (size_t)b * P.ecap;
   uint8_t* ed = S.edge_dst + (size_t)b * P.ecap;
   int32_t* ec = S.edge_cnt + (size_t)b * P.ecap;
-  int found = -1;
+  int my_s = -1, my_t = -1, my_c = 0;                 // edge `lane` of the first block of 32
+  if (lane < P.ecap) { my_s = es[lane]; my_t = ed[lane]; my_c = ec[lane]; }
+  const int gv = T.uvuln_global[uvoff + u];
+  const float p = lane < NN_CH ? T.vuln_h[(size_t)gv * NN_CH + lane] : 0.f;
+  int found = -1, cnt = 0;
   for (int base = 0; base < E; base += 32) {
     const int e = base + lane;
-    const bool hit = e < E && es[e] == s && ed[e] == t;
+    int cs = my_s, ct = my_t, cc = my_c;
+    if (base) { cs = ct = -1; if (e < E) { cs = es[e]; ct = ed[e]; cc = ec[e]; } }
+    const bool hit = e < E && cs == s && ct == t;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-    if (m) { found = base + __ffs(m) - 1; break; }
+    if (m) { found = base + __ffs(m) - 1; cnt = __shfl_sync(0xFFFFFFFFu, cc, __ffs(m) - 1); break; }
   }
   if (found >= 0) {
-    const int cnt = ec[found];
     float* sum = S.edge_sum + ((size_t)b * P.ecap + found) * NN_CH;
     if (lane < NN_CH) {
       const float v = (cnt == 0 ? 0.f : sum[lane]) + p;   // :226-228 (a wiped accumulator restarts)
@@ -132,7 +139,8 @@ __device__ void edge_update(const Tables& T, const Params& P, const State& S, in
     if (E >= P.ecap) { if (lane == 0) atomicExch(S.errflag, 2); return; }
     for (int base = 0; base < E; base += 32) {             // :237 wipes every accumulator of this source
       const int e = base + lane;
-      if (e < E && es[e] == s) ec[e] = 0;
+      const int cs = base ? (e < E ? (int)es[e] : -1) : my_s;
+      if (e < E && cs == s) ec[e] = 0;
     }
     if (lane < NN_CH) {
       S.edge_sum[((size_t)b * P.ecap + E) * NN_CH + lane] = p;
@@ -466,7 +474,7 @@ __device__ void encode_env(const Tables& T, const Params& P, const State& S, con
 // inlined behind a run-time test the default observe kernel ran 64 us instead of 43)
 template <bool PRECISE, bool SUBSET>
 __device__ void build_table(const Tables& T, const Params& P, const State& S, WarpScratch& W, int b, int lane, bool refresh_arg,
-                            int skipped_builds = 0) {
+                            int skipped_builds = 0, long long* tsub = nullptr) {
   const bool refresh = PRECISE && refresh_arg;
   SubScratch sub;
   int n_newp = 0;
@@ -534,6 +542,9 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   if (lane < n_disc) target_rows(my_t, rows_remote0, rows_self0);
   bool any_new = false;
   uint32_t seen[MAX_NODES / 32] = {0u, 0u, 0u, 0u};
+#ifdef CBS_OBS_SUBTRACE
+  if (tsub && n_disc + n_owned + slot + rows_self0 + my_o >= 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tsub[0]));
+#endif
   for (int op = 0; op < n_owned; ++op) {
     if ((op & 31) == 0 && op) my_o = op + lane < n_owned ? oorder[op + lane] : 0;
     const int s = __shfl_sync(0xFFFFFFFFu, my_o, op & 31);
@@ -568,6 +579,7 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
       }
     }
   }
+  SUBT(1);
   if (!any_new) {
     // the reference still balances (and draws from its generator) at the end of this create_continuous_action_space
     if constexpr (SUBSET) subset_update(T, P, S, sub, b, lane, slot, 0, oorder, n_owned, dorder, W.pos, skipped_builds);
@@ -579,17 +591,41 @@ __device__ void build_table(const Tables& T, const Params& P, const State& S, Wa
   float* zh = S.z_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB;
   float* zn = S.zn2_hist + ((size_t)b * P.slots + slot) * P.ncap;
   __half2* zh16 = reinterpret_cast<__half2*>(S.z16_hist + ((size_t)b * P.slots + slot) * P.ncap * NODE_EMB);
-#pragma unroll 2
-  for (int i = 0; i < n_disc; ++i) {
-    const int node = i < 32 ? __shfl_sync(0xFFFFFFFFu, my_t, i) : (int)dorder[i];
-    if (!(W.dynb[i] & 0x80)) continue;                   // only Running nodes have embeddings (compressed:266-280)
-    const float2 z = reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane];   // channels 2*lane, 2*lane+1
-    reinterpret_cast<float2*>(zh + node * NODE_EMB)[lane] = z;
-    zh16[node * (NODE_EMB / 2) + lane] = __floats2half2_rn(z.x, z.y);
-    if (fmaxf(fabsf(z.x), fabsf(z.y)) > 65504.f) atomicExch(S.errflag, 8);     // beyond half precision: the decode scan reads these copies
-    const float n2 = warp_sum(z.x * z.x + z.y * z.y);
-    if (lane == 0) zn[node] = n2;
+  // four nodes per pass: their squared norms go through the five butterfly levels together (one node per pass was a chain of five
+  // dependent shuffles per node, 0.23 us per node; every node's sum still runs in the same order)
+  for (int i0 = 0; i0 < n_disc; i0 += 4) {
+    float2 z[4];
+    float sq[4];
+    int node[4];
+    bool run[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + j;
+      run[j] = i < n_disc && (W.dynb[i < n_disc ? i : 0] & 0x80);       // only Running nodes have embeddings (compressed:266-280)
+      node[j] = i < 32 ? __shfl_sync(0xFFFFFFFFu, my_t, i & 31) : (i < n_disc ? (int)dorder[i] : 0);
+      z[j] = run[j] ? reinterpret_cast<const float2*>(W.y + i * NODE_EMB)[lane] : make_float2(0.f, 0.f);   // channels 2*lane, 2*lane+1
+      sq[j] = z[j].x * z[j].x + z[j].y * z[j].y;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (!run[j]) continue;
+      reinterpret_cast<float2*>(zh + node[j] * NODE_EMB)[lane] = z[j];
+      zh16[node[j] * (NODE_EMB / 2) + lane] = __floats2half2_rn(z[j].x, z[j].y);
+      if (fmaxf(fabsf(z[j].x), fabsf(z[j].y)) > 65504.f) atomicExch(S.errflag, 8);     // beyond half precision: the decode scan reads these copies
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sq[j] += __shfl_xor_sync(0xFFFFFFFFu, sq[j], o);
+    }
+    if (lane < 4) {
+      const int nd = lane == 0 ? node[0] : (lane == 1 ? node[1] : (lane == 2 ? node[2] : node[3]));
+      const float v = lane == 0 ? sq[0] : (lane == 1 ? sq[1] : (lane == 2 ? sq[2] : sq[3]));
+      const bool r = lane == 0 ? run[0] : (lane == 1 ? run[1] : (lane == 2 ? run[2] : run[3]));
+      if (r) zn[nd] = v;
+    }
   }
+  SUBT(2);
   if (lane == 0) scalar(S, P, S_N_SLOTS, b) = slot + 1;
   __syncwarp();
   if constexpr (SUBSET) subset_update(T, P, S, sub, b, lane, slot, n_newp, oorder, n_owned, dorder, W.pos, skipped_builds);
@@ -712,6 +748,7 @@ __device__ int2 reset_env(const Tables& T, const Params& P, const State& S, int 
   if (lane == 0) {
     scalar(S, P, S_SCENARIO, b) = sc;
     scalar(S, P, S_NODE_OFF, b) = T.sc_node_off[sc];
+    scalar(S, P, S_UVULN_OFF, b) = T.sc_uvuln_off[sc];
     scalar(S, P, S_STARTER, b) = starter;
     scalar(S, P, S_SCST, b) = (sc << 8) | starter;      // what the transition reads instead of the constant sector
     scalar(S, P, S_STEPCOUNT, b) = 0;
@@ -857,7 +894,7 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
   auto claim_next = [&]() {
     if (mode != 0 || claimed) return;
     claimed = true;
-    if (lane == 0) pend = atomicAdd(&S.work_ctr[2], 1);
+    if (lane == 0) pend = total_warps + atomicAdd(&S.work_ctr[2], 1);
   };
   auto lookup = [&](int item) {
     int k = 0, first = 0;
@@ -865,10 +902,8 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
     for (int q = 0; q < OBS_CLASSES - 1; ++q) if (item >= cls_end[q]) { k = q + 1; first = cls_end[q]; }
     return S.worklist[(size_t)k * P.B + (item - first)];
   };
-  if (mode == 0) {
-    claim_next();
-    i = __shfl_sync(0xFFFFFFFFu, pend, 0);
-  }
+  // (every warp's first item is its own index: 1184 simultaneous claims of one counter took the last of them microseconds; the
+  // counter then hands out the items behind the first round)
   for (;;) {
     if (i >= count) break;
     const int b = mode == 0 ? lookup(i) : i;
@@ -910,7 +945,11 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
         if (!(flags & FL_FINISHED_THIS_STEP)) claim_next();
         if (!(flags & FL_FINISHED_THIS_STEP) || SUBSET) {
           const int skipped = SUBSET ? (flags >> FL_PENDING_SHIFT) & 0xFFFF : 0;
+#ifdef CBS_OBS_SUBTRACE
+          build_table<PRECISE, SUBSET>(T, P, S, W, b, lane, PRECISE, skipped, trace ? t_ph + 2 : nullptr);
+#else
           build_table<PRECISE, SUBSET>(T, P, S, W, b, lane, PRECISE, skipped);
+#endif
           keep &= 0xFFFF;
         }
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[1])); }

@@ -639,11 +639,15 @@ static __device__ __forceinline__ int transition_env(const Tables& T, const Para
   }
   int cls = -1;
   if (!PERSIST && (flags & (FL_ADD_EDGE | FL_REENCODE | FL_FINISHED_THIS_STEP))) {   // the observe kernel only visits these envs
-    // OBS_CLASSES cost classes, claimed heaviest first.  An item costs about (re-encode ? 6 + 1.1 n : 0) + (episode end:
-    // statistics + reset + encode + table ? 18 : 0) + 2 us with n = discovered nodes; the kernel ends with its longest item.
+    // OBS_CLASSES cost classes of 2.5 us, claimed heaviest first (tools/observe_trace.py, n = discovered nodes): a re-encode with
+    // its table build costs about 9 + 0.85 n us, an episode end (statistics + reset + first observation) 13 us, an episode end
+    // behind a re-encode (no table build) 20 + 0.65 n us, an edge update alone 3 us.  With six coarse classes an episode end
+    // (13 us) was claimed before an 18-node re-encode (25 us), and the kernel ended a quarter later than its warps' mean load.
     const int n = DEF ? SC(S_N_DISC) : n_disc_w;
     const bool fin = flags & FL_FINISHED_THIS_STEP, enc = flags & FL_REENCODE;
-    cls = fin ? (enc ? 0 : 2) : (enc ? (n > 20 ? 1 : (n > 10 ? 3 : 4)) : 5);
+    const int cost10 = fin ? (enc ? 200 + (13 * n) / 2 : 130) : (enc ? 90 + (17 * n) / 2 : 30);     // tenths of a microsecond
+    const int bucket = cost10 / 25;
+    cls = OBS_CLASSES - 1 - (bucket < OBS_CLASSES - 1 ? bucket : OBS_CLASSES - 1);
     if (ENQ) {
       const int slot = atomicAdd(&S.work_ctr[4 + cls], 1);
       if (slot < P.B) S.worklist[(size_t)cls * P.B + slot] = b; else atomicExch(S.errflag, 4);

@@ -78,7 +78,7 @@ SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cb
 # cbs_field
 F_MASKS, F_DISC_ORDER, F_OWNED_ORDER, F_SCALARS, F_TERMINAL_OBS, F_OBS, F_LAST_STATS, F_STAT_ACCUM, F_PAIR_SLOT, \
     F_DIST, F_REWARD64, F_ERRFLAG, F_VT, F_OWNED_RAW, F_REIMAGE_LEFT, F_Z_HIST, F_SEL, F_DIVERGENCE, F_EV_CUR, F_EV_X, F_MARGIN_EDGE = range(21)
-NUM_SCALARS, NUM_ACCUM = 25, 20
+NUM_SCALARS, NUM_ACCUM = 26, 20
 # per-env scalar record (csrc/cbs_types.h enum Scalar): four 32-byte sectors — rewritten every step | list lengths and
 # counters | episode constants | misc
 (S_FLAGS, S_STEPCOUNT, S_NUM_ITER, S_TOTAL_STEPS, S_OUTCOME, S_SCST, S_EP_RETURN, S_EP_RETURN_HI) = range(8)
@@ -86,6 +86,7 @@ NUM_SCALARS, NUM_ACCUM = 25, 20
 (S_SCENARIO, S_STARTER, S_NODE_OFF, S_OWNABLE, S_DISCOVERABLE, S_DISRUPTABLE, S_PROP_NODES,
  S_DISCOVERABLE_AMOUNT) = range(16, 24)
 S_EPISODES = 24
+S_UVULN_OFF = 25
 ACCUM_NAMES = ["episodes", "return_sum", "length_sum", "wins", "lost", "cutoff"] + [f"stat{i}" for i in range(14)]
 
 

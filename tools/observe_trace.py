@@ -65,10 +65,10 @@ for lo, hi in ((1, 4), (5, 8), (9, 12), (13, 16), (17, 24), (25, 32)):
     if q.any(): print(f"re-encode nodes {lo}-{hi}: n {q.sum()} dur mean {dur[m][q].mean() / 1e3:.1f} max {dur[m][q].max() / 1e3:.1f} start mean {(start[m][q] - t0).mean() / 1e3:.1f}")
 
 if os.environ.get("CBS_OBS_SUBTRACE"):   # library built with -DCBS_OBS_SUBTRACE: 14 phase slots; 5.. = the encode's sub-phases, 13 = edge update done
-    m = (cls == 1) & (ph[:, 5] > 0)
+    m = (cls == 1) & (ph[:, 5] > 0) & (ph[:, 4] > 0)
     nn = ne[m] >> 16
-    names = ["edge_upd", "scalars", "pack", "root", "nnconv", "bn1", "proj", "agg", "final", "obs/enc", "table"]
-    cols = [13, 5, 6, 7, 8, 9, 10, 11, 12, 0, 1]
+    names = ["edge_upd", "scalars", "pack", "root", "nnconv", "bn1", "proj", "agg", "final", "obs/enc", "tbl loads", "tbl pairs", "tbl store", "table"]
+    cols = [13, 5, 6, 7, 8, 9, 10, 11, 12, 0, 2, 3, 4, 1]
     print("cumulative us at the end of each phase:", names)
     for lo, hi in ((1, 4), (5, 8), (9, 12), (13, 16), (17, 24), (25, 32)):
         q = (nn >= lo) & (nn <= hi)
