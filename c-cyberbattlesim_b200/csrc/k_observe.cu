@@ -38,6 +38,7 @@ struct SharedWeights {
   float bn1s[NODE_EMB], bn1h[NODE_EMB], bn2s[NODE_EMB], bn2h[NODE_EMB];
   float nn0b[NN_CH];
   double accum[N_ACCUM];   // this CTA's share of the episode sums (flushed to State::accum by its last warp)
+  unsigned long long wbar; // mbarrier: the staged weights have landed (one arrival per thread, when its cp.async copies complete)
   int warps_done;
 };
 
@@ -831,33 +832,47 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
                                                                 long long* __restrict__ trace) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SharedWeights& SW = *reinterpret_cast<SharedWeights*>(smem_raw);
-  {   // stage the weights with 128-bit loads, all requests in flight before the first store
+  // The weights (44 KB) are staged with asynchronous copies that nobody waits for here: a warp waits on the mbarrier right before its
+  // first encode, i.e. behind its first item's claim, flags and edge update — staged with plain loads behind a barrier, the copy
+  // was 2 us at the head of a 35 us kernel whose duration is its first (heaviest) items'.
+  const uint32_t wbar = (uint32_t)__cvta_generic_to_shared(&SW.wbar);
+  if (threadIdx.x < N_ACCUM) SW.accum[threadIdx.x] = 0.0;
+  if (threadIdx.x == 0) {
+    SW.warps_done = 0;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(wbar), "r"(OBS_WARPS * 32));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  {
     constexpr int NT = OBS_WARPS * 32;
     constexpr int G4 = NODE_EMB * NODE_EMB / 4, D4 = NUM_DYN * PROJ_ROWS * NODE_EMB / 4;   // 1024, 1728 float4
-    const float4* gsrc = reinterpret_cast<const float4*>(T.gcn_wt);
-    const float4* dsrc = reinterpret_cast<const float4*>(T.dyn_proj);
-    float4* gdst = reinterpret_cast<float4*>(SW.gcn);
-    float4* ddst = reinterpret_cast<float4*>(SW.dyn);
-    float4 tg[(G4 + NT - 1) / NT], td[(D4 + NT - 1) / NT];
-#pragma unroll
-    for (int i = 0; i < (G4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; tg[i] = j < G4 ? gsrc[j] : make_float4(0, 0, 0, 0); }
-#pragma unroll
-    for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; td[i] = j < D4 ? dsrc[j] : make_float4(0, 0, 0, 0); }
-#pragma unroll
-    for (int i = 0; i < (G4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; if (j < G4) gdst[j] = tg[i]; }
-#pragma unroll
-    for (int i = 0; i < (D4 + NT - 1) / NT; ++i) { const int j = threadIdx.x + i * NT; if (j < D4) ddst[j] = td[i]; }
+    auto cp16 = [](void* dst, const void* src) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    auto cp4 = [](void* dst, const void* src) {
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    for (int j = threadIdx.x; j < G4; j += NT) cp16(reinterpret_cast<float4*>(SW.gcn) + j, reinterpret_cast<const float4*>(T.gcn_wt) + j);
+    for (int j = threadIdx.x; j < D4; j += NT) cp16(reinterpret_cast<float4*>(SW.dyn) + j, reinterpret_cast<const float4*>(T.dyn_proj) + j);
+    if (threadIdx.x < NODE_EMB) {
+      cp4(&SW.bn1s[threadIdx.x], T.bn1_scale + threadIdx.x);
+      cp4(&SW.bn1h[threadIdx.x], T.bn1_shift + threadIdx.x);
+      cp4(&SW.bn2s[threadIdx.x], T.bn2_scale + threadIdx.x);
+      cp4(&SW.bn2h[threadIdx.x], T.bn2_shift + threadIdx.x);
+    }
+    if (threadIdx.x < NN_CH) cp4(&SW.nn0b[threadIdx.x], T.nn0_b + threadIdx.x);
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(wbar) : "memory");
   }
-  if (threadIdx.x < NODE_EMB) {
-    SW.bn1s[threadIdx.x] = T.bn1_scale[threadIdx.x];
-    SW.bn1h[threadIdx.x] = T.bn1_shift[threadIdx.x];
-    SW.bn2s[threadIdx.x] = T.bn2_scale[threadIdx.x];
-    SW.bn2h[threadIdx.x] = T.bn2_shift[threadIdx.x];
-  }
-  if (threadIdx.x < NN_CH) SW.nn0b[threadIdx.x] = T.nn0_b[threadIdx.x];
-  if (threadIdx.x < N_ACCUM) SW.accum[threadIdx.x] = 0.0;
-  if (threadIdx.x == 0) SW.warps_done = 0;
-  __syncthreads();
+  bool weights_ready = false;
+  auto wait_weights = [&]() {
+    if (weights_ready) return;
+    weights_ready = true;
+    uint32_t ok = 0;
+    do {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok) : "r"(wbar) : "memory");
+    } while (!ok);
+  };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * OBS_WARPS + warp, total_warps = gridDim.x * OBS_WARPS;
@@ -935,8 +950,10 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
 #endif
       if (flags & FL_REENCODE) {
 #ifdef CBS_OBS_SUBTRACE
+        wait_weights();
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane, trace ? t_ph + 5 : nullptr); else encode_env<false>(T, P, S, SW, W, b, lane, trace ? t_ph + 5 : nullptr);
 #else
+        wait_weights();
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
 #endif
         if (trace) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_ph[0])); }
@@ -977,6 +994,7 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
       if (!reset_from_cache(T, P, S, b, lane, ss.x, ss.y)) {
         W.y = W.ysm;                               // a fresh episode's graph is one node
         W.g = W.ysm + SMEM_NODES * NODE_EMB;
+        wait_weights();
         if (P.defender == 2) encode_env<true>(T, P, S, SW, W, b, lane); else encode_env<false>(T, P, S, SW, W, b, lane);
         build_table<PRECISE, SUBSET>(T, P, S, W, b, lane, false);
         reset_cache_publish(T, P, S, W, b, lane, ss.x, ss.y);

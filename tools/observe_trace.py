@@ -4,7 +4,7 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, ccbs_b200 as cb
 from ccbs_b200.batched_env import BatchedCyberBattleEnv
-B = 8192
+B = int(os.environ.get("CBS_TRACE_B", "8192"))
 env = BatchedCyberBattleEnv(bench.build_specs(bench.WORKLOADS["c2"]), cb.GaeWeights.random(0), cb.EnvConfig(), num_envs=B, seed=7)
 env.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(1)
