@@ -328,7 +328,7 @@ typedef enum {
                              node, cyberbattle_env.py:425 -> ValueError); the removal is a no-op here */
 } cbs_field;
 #define CBS_NUM_MASKS 15
-#define CBS_NUM_SCALARS 25
+#define CBS_NUM_SCALARS 26
 #define CBS_NUM_ACCUM 20
 /* synchronous device->host copy of one state field; bytes must equal the field size (query with dst NULL). */
 int64_t cbs_read_state(cbs_handle* h, int32_t field, void* dst_host, int64_t bytes);
