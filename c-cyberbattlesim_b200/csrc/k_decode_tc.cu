@@ -20,6 +20,7 @@
 #include "cbs_types.h"
 
 namespace cbs {
+extern long long* g_sel_trace;   // cbs_debug_select_trace's buffer (debug builds of this file append their own rows)
 
 namespace {
 
@@ -97,12 +98,22 @@ __global__ void __launch_bounds__(256) pack_actions_kernel(const float* __restri
 //            the A slab with 4-byte cp.async straight into the 128-byte-swizzled layout the UMMA descriptor expects
 //            (16-byte chunk c of row r lands at chunk c ^ (r & 7)) and arrive on the stage's full barrier when their
 //            copies land (cp.async.mbarrier.arrive.noinc); no repack pass over HBM.  256 threads.
+#ifdef CBS_GEMM_TRACE
+__device__ long long* g_sel_trace_dev = nullptr;
+#endif
 template <bool LDGSTS_A, int BM>
 __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                                  const float* __restrict__ actions, int act_stride,
                                                                                  float* __restrict__ vt, int B, int Upad, int nt_box,
                                                                                  int vt_stride, int32_t* errflag, int direct, int STAGES) {
+#ifdef CBS_GEMM_TRACE   // debug build (-DCBS_GEMM_TRACE): per-CTA, per-warp phase stamps, read by tools/gemm_trace.py
+  long long tt[6] = {0, 0, 0, 0, 0, 0};
+#define GT(k) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[k]))
+#else
+#define GT(k)
+#endif
+  GT(0);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB / 8 KB
@@ -130,6 +141,7 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
+  GT(1);
 
   if (warp == 0 && lane == 0) {
     // ---- TMA producer ----
@@ -189,7 +201,9 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
 
   // ---- epilogue: TMEM -> registers -> global.  Every warp owns TMEM lanes [32w, 32w+32): tile rows 32w + lane
   //      (M = 128) or rows 16w + lane on its lanes 0-15 (M = 64) ----
+  GT(2);
   const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
+  GT(3);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const bool lane_has_row = BM == 128 || lane < 16;
   const int row = lane_has_row ? m0 + warp * (BM / 4) + lane : B;
@@ -219,8 +233,16 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
       }
     }
   }
+  GT(4);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  GT(5);
+#ifdef CBS_GEMM_TRACE   // rows behind the select kernel's [B][6] trace block (the buffer is cbs_debug_select_trace's)
+  if (g_sel_trace_dev && (threadIdx.x & 31) == 0) {
+    long long* tr = g_sel_trace_dev + (size_t)B * 6 + ((size_t)blockIdx.x * 8 + warp) * 6;
+    for (int k = 0; k < 6; ++k) tr[k] = tt[k];
+  }
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
@@ -305,6 +327,9 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
     attr[which] = smem;
   }
   dim3 grid((B + bm - 1) / bm, ntiles_n);
+#ifdef CBS_GEMM_TRACE
+  cudaMemcpyToSymbolAsync(g_sel_trace_dev, &g_sel_trace, sizeof(g_sel_trace), 0, cudaMemcpyHostToDevice, stream);
+#endif
   kernels[which]<<<grid, ldgsts ? 256 : 128, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag,
                                                             direct ? 1 : 0, stages);
   return cudaGetLastError();

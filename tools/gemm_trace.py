@@ -1,4 +1,5 @@
-"""Per-CTA timeline of the decode contraction (debug aid; needs a library built with the trace stamps)."""
+"""Per-CTA timeline of the decode contraction (debug aid).  Needs k_decode_tc.cu compiled with -DCBS_GEMM_TRACE
+(nvcc ... -DCBS_GEMM_TRACE -c k_decode_tc.cu, relink libcbsim.so); the stock library leaves the rows zero."""
 import os, sys, ctypes as ct
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
