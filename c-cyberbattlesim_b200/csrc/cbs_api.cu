@@ -7,11 +7,16 @@
 #include <vector>
 
 #include "../../include/cbsim.h"
+#include <cuda_fp16.h>
+
 #include "cbs_types.h"
 
 namespace cbs {
 cudaError_t launch_decode_gemm_simt(const float*, int, const float*, float*, int, int, int, cudaStream_t);
 cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
+cudaError_t launch_decode_gemm_f16(const float*, int, const __half*, float*, int, int, int, int32_t*, cudaStream_t);
+cudaError_t convert_vemb_f16(const float*, __half*, size_t, cudaStream_t);
+bool decode_gemm_f16_applies(int, int);
 bool decode_gemm_tc_available();
 cudaError_t launch_decode_select(const Tables&, const Params&, const State&, const float*, int, int, int, const float*, float*, uint8_t*,
                                  int32_t*, double*, cudaStream_t);
@@ -117,6 +122,7 @@ struct cbs_handle {
   int sched_buf = 0;     // cost-bin buffer the next decode reads (the transitions of that step fill the other one)
   int num_sms = 148;
   float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
+  __half* vemb16 = nullptr;    // [Ug][768] the vulnerability embeddings in half precision (B operand of the FP16 contraction)
   double* vt64 = nullptr;      // [B][Ug] vulnerability part of the l1 / l2 / inf distances (distance_metric != cosine only)
   // host-step staging
   cudaStream_t hstream = nullptr;
@@ -432,6 +438,12 @@ int cbs_load_scenarios(cbs_handle* h, const cbs_scenario_tables* t, const cbs_ga
   if ((rc = dalloc(h, h->state_allocs, &h->d_sel, B * 4))) return rc;
   if ((rc = dalloc(h, h->state_allocs, &h->d_dist, B))) return rc;
   if (h->use_tc && (rc = dalloc(h, h->state_allocs, &h->a_packed, B * VULN_EMB))) return rc;
+  if (h->use_tc) {
+    const size_t n = (size_t)h->Ug * VULN_EMB;
+    if ((rc = dalloc(h, h->state_allocs, &h->vemb16, n, false))) return rc;
+    CK(h, convert_vemb_f16(h->T.vemb32, h->vemb16, n, 0));
+    CK(h, cudaDeviceSynchronize());
+  }
   if (P.metric != METRIC_COSINE && (rc = dalloc(h, h->state_allocs, &h->vt64, B * (size_t)h->Ug, false))) return rc;
   init_flags_kernel<<<(P.B + 255) / 256, 256>>>(S.scal, P.B);
   CK(h, cudaGetLastError());
@@ -568,7 +580,10 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
 
 static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st) {
   if (h->use_tc) {
-    CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+    if (h->vemb16 && decode_gemm_f16_applies(h->P.B, h->Ug))
+      CK(h, launch_decode_gemm_f16(actions_dev, h->P.act_stride, h->vemb16, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+    else
+      CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
     h->launches += 1;
   } else {
     CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));

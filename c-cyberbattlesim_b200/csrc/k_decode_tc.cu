@@ -14,8 +14,10 @@
 // [B,768] slab; with a 16-byte-multiple row pitch (cbs_set_action_stride) TMA reads in place.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "cbs_types.h"
 
@@ -249,6 +251,210 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
 }
 
 // ------------------------------------------------------------------------------------------------
+// Half-precision variant (default for half-height tiles).  What bounds the TF32 kernel above is, equally, the operands' way into
+// the SM and the rate of its K = 8 UMMAs (~220 cycles per tcgen05.mma whatever is knocked out around it).  FP16
+// operands halve both: a UMMA covers K = 16 and the B slab is half the bytes.  FP16 has TF32's 10-bit mantissa, so the operand
+// rounding the re-score margin of decode_select absorbs is the same; only the exponent range is narrower (the action space is
+// Box(-4, 4); values beyond +-65504 are clamped, embeddings below 6e-5 lose bits that cannot decide a 0.5-wide margin).
+//   * B: Vemb converted once to FP16 at table load; TMA boxes of 64 halfs (one 128-byte swizzle row) x N.
+//   * A: the dense float32 [B,905] rows (4-byte aligned only).  Eight producer warps read them as coalesced, ALIGNED 16-byte
+//     vectors (a half-warp per row and slab), each lane also its next vector, pick their floats at the row's shift, convert,
+//     and store into the 128-byte-swizzled FP16 tile of the MMA ring; A_AHEAD slabs are held in registers.
+//     Measured and replaced: (1) 4-byte cp.async into a float32 ring + a conversion pass through shared memory - 64
+//     load/store-unit instructions per thread and slab, copy and conversion serialise on that unit: 32.6 us (TF32 kernel: 22.8;
+//     A path knocked out: 17.6); (2) one (row, 16-float segment) per thread, five aligned vectors each - every warp request
+//     touches 32 different sectors in 16 lines: 44 us.
+//   * 12 ring stages of K = 64 instead of 24 of K = 32; 4 UMMAs (kind::f16, K = 16) per stage.
+constexpr int F16_BK = 64;        // halfs per K slab = 128 bytes = one SWIZZLE_128B row
+constexpr int F16_BM = 64;
+constexpr int A_AHEAD = 3;        // slabs of A a producer thread holds in registers ahead of the conversion (32 floats each)
+constexpr int F16_THREADS = 384;  // warp 0 TMA, warp 1 MMA, warps 0-3 epilogue, warps 4-11 A producers
+
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(256) convert_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(fminf(fmaxf(src[i], -65504.f), 65504.f));
+}
+
+__global__ void __launch_bounds__(F16_THREADS, 1) decode_gemm_f16_kernel(const __grid_constant__ CUtensorMap map_b,
+                                                                 const float* __restrict__ actions, int act_stride,
+                                                                 float* __restrict__ vt, int B, int Upad, int nt_box, int vt_stride,
+                                                                 int32_t* errflag, int STAGES, int knock) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int BM = F16_BM;
+  constexpr int A_STAGE_BYTES = BM * F16_BK * 2;      // 8 KB
+  const int stage_bytes = A_STAGE_BYTES + nt_box * F16_BK * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT_MAX;
+  const int nt = min(NT_MAX, Upad - n0);
+  constexpr int KB = VULN_EMB / F16_BK;               // 12 slabs
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + 8); mbar_init(empty0 + 8 * s, 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer (B) ----
+    const uint32_t bytes = (uint32_t)(stage_bytes - A_STAGE_BYTES);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (!mbar_wait(empty0 + 8 * s, ph ^ 1, errflag)) break;
+      if (knock & 8) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * s) : "memory"); continue; }
+      mbar_expect_tx(full0 + 8 * s, bytes);
+      tma_load_2d(smem_u32(smem + s * stage_bytes) + A_STAGE_BYTES, &map_b, full0 + 8 * s, kb * F16_BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer ----  D = F32 (bit 4), A = B = F16 (format 0), K-major both, N >> 3 at 17, M >> 4 at 24
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    bool ok = true;
+    for (int kb = 0; kb < KB && ok; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      ok = mbar_wait(full0 + 8 * s, ph, errflag);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem_u32(smem + s * stage_bytes);
+      const uint64_t ad = umma_desc(sa), bd = umma_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+      for (int k = 0; k < F16_BK / 16; ++k)   // K = 16 halfs = 32 bytes per instruction: +2 in the >>4 address field
+        if (!(knock & 2) || (kb | k) == 0) umma_f16(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+      umma_commit(empty0 + 8 * s);
+    }
+    umma_commit(tfull);
+  } else if (warp >= 4) {
+    // ---- A producers (8 warps; warp pw owns tile rows [8 pw, 8 pw + 8)) ----
+    // The rows are only 4-byte aligned.  Per slab a warp makes four passes over a PAIR of rows (r, r + 4: the same alignment
+    // class for any row pitch, so the shift below is warp-uniform): a half-warp reads one row's 256 bytes as 16 aligned 16-byte
+    // vectors - fully coalesced - plus each lane's NEXT vector (the same lines again, an L1 hit), picks its four floats at the
+    // row's shift (0-3 floats), converts and stores 8 bytes into the 128-byte-swizzled FP16 tile.  A_AHEAD slabs are held in
+    // registers ahead of the one being converted.
+    const int pw = warp - 4, v = lane & 15;
+    const float4* base[4];
+    int shift[4];
+    bool live[4];
+    uint32_t toff[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = 8 * pw + it + 4 * (lane >> 4), row = m0 + r;
+      const float* p0 = actions + (size_t)(row < B ? row : 0) * act_stride + 2 * NODE_EMB;
+      shift[it] = (int)((reinterpret_cast<uintptr_t>(p0) >> 2) & 3);
+      base[it] = reinterpret_cast<const float4*>(p0 - shift[it]) + v;        // 16-byte aligned
+      live[it] = row < B && !(knock & 1);
+      toff[it] = (uint32_t)r * 128 + ((((uint32_t)v >> 1) ^ ((uint32_t)r & 7u)) << 4) + ((uint32_t)v & 1u) * 8;
+    }
+    float4 q[A_AHEAD][4][2];
+    auto load = [&](float4 (&d)[4][2], int kk) {
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4* g = base[it] + kk * (F16_BK / 4);
+        d[it][0] = live[it] ? ld_nc_f4(g) : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[it][1] = (live[it] && shift[it]) ? ld_nc_f4(g + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+#pragma unroll
+    for (int d = 0; d < A_AHEAD; ++d) load(q[d], d);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      uint2 h[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float4 a = q[kb % A_AHEAD][it][0], c = q[kb % A_AHEAD][it][1];
+        float f0, f1, f2, f3;
+        switch (shift[it]) {
+          case 0: f0 = a.x; f1 = a.y; f2 = a.z; f3 = a.w; break;
+          case 1: f0 = a.y; f1 = a.z; f2 = a.w; f3 = c.x; break;
+          case 2: f0 = a.z; f1 = a.w; f2 = c.x; f3 = c.y; break;
+          default: f0 = a.w; f1 = c.x; f2 = c.y; f3 = c.z; break;
+        }
+        const __half2 lo = __floats2half2_rn(fminf(fmaxf(f0, -65504.f), 65504.f), fminf(fmaxf(f1, -65504.f), 65504.f));
+        const __half2 hi = __floats2half2_rn(fminf(fmaxf(f2, -65504.f), 65504.f), fminf(fmaxf(f3, -65504.f), 65504.f));
+        h[it] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+      }
+      if (kb + A_AHEAD < KB) load(q[kb % A_AHEAD], kb + A_AHEAD);
+      const int s = kb % STAGES;
+      const uint32_t ph = (kb / STAGES) & 1;
+      if (!mbar_wait(empty0 + 8 * s, ph ^ 1, errflag)) break;
+      unsigned char* tile = smem + s * stage_bytes;
+      if (!(knock & 4)) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) *reinterpret_cast<uint2*>(tile + toff[it]) = h[it];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy stores -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full0 + 8 * s) : "memory");
+    }
+  }
+  __syncwarp();
+
+  // ---- epilogue (M = 64: tile row 16 w + lane on lanes 0-15 of warp w's TMEM sub-partition) ----
+  const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = lane < 16 ? m0 + warp * (BM / 4) + lane : B;
+  if (ready) {
+    for (int c0 = 0; c0 < nt; c0 += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < B) {
+        float4* dst = reinterpret_cast<float4*>(vt + (size_t)row * vt_stride + n0 + c0);
+        const int ncols = min(32, vt_stride - n0 - c0);   // multiple of 4
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (4 * i < ncols)
+            dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                 __uint_as_float(r[4 * i + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 
 static bool load_encode() {
@@ -276,6 +482,60 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint32_
   return g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t convert_vemb_f16(const float* vemb32, __half* vemb16, size_t n, cudaStream_t stream) {
+  convert_f16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(vemb32, vemb16, n);
+  return cudaGetLastError();
+}
+
+// true when launch_decode_gemm_f16 is the kernel for this batch.  Opt-in (CBS_GEMM_F16=1): measured on B200 at 8192 envs it does
+// not beat the TF32 kernel yet (24.4 us against 22.8 us) - its MMA loop is half as long, but the A stream
+// (25 MB of fresh actions from DRAM per launch) then needs more bytes in flight than a register-staged conversion can hold.
+bool decode_gemm_f16_applies(int B, int Ug) {
+  static const bool opt_in = getenv("CBS_GEMM_F16") != nullptr;
+  if (!opt_in || getenv("CBS_GEMM_M128")) return false;
+  int dev = 0, num_sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  const int Upad = ((Ug + 15) / 16) * 16;
+  const int ntiles_n = (Upad + NT_MAX - 1) / NT_MAX;
+  return 2 * ((B + 127) / 128) * ntiles_n <= num_sms + num_sms / 4;
+}
+
+cudaError_t launch_decode_gemm_f16(const float* actions, int act_stride, const __half* vemb16, float* vt, int B, int Ug,
+                                   int vt_stride, int32_t* errflag, cudaStream_t stream) {
+  if (!load_encode()) return cudaErrorNotSupported;
+  const int Upad = ((Ug + 15) / 16) * 16;
+  const int nt_box = Upad < NT_MAX ? Upad : NT_MAX;
+  CUtensorMap map_b;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)VULN_EMB, (cuuint64_t)Ug};
+    const cuuint64_t strides[1] = {(cuuint64_t)VULN_EMB * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)F16_BK, (cuuint32_t)nt_box};
+    const cuuint32_t estr[2] = {1, 1};
+    if (g_encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(vemb16), dims, strides, box, estr,
+                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+  }
+  const int ntiles_n = (Upad + NT_MAX - 1) / NT_MAX;
+  const size_t stage_bytes = (size_t)F16_BM * F16_BK * 2 + (size_t)nt_box * F16_BK * 2;
+  const size_t fixed = 1024 + 256;
+  int stages = (int)((225 * 1024 - fixed) / stage_bytes);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages < 2) return cudaErrorInvalidValue;
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(decode_gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  dim3 grid((B + F16_BM - 1) / F16_BM, ntiles_n);
+  static const int knock = getenv("CBS_GEMM_KNOCK") ? atoi(getenv("CBS_GEMM_KNOCK")) : 0;   // debug: knock out A copies (1), MMAs (2), the conversion (4), B copies (8)
+  decode_gemm_f16_kernel<<<grid, F16_THREADS, smem, stream>>>(map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag, stages, knock);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const float* vemb, float* a_packed, float* vt, int B,

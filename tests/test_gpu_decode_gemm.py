@@ -5,9 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("gemm,tol", [(1, 1e-3), (0, 0.35)], ids=["simt", "tcgen05"])
-@pytest.mark.parametrize("num_envs,pool", [(300, 40), (1024, 200), (130, 330)])
-def test_decode_products(gemm, tol, num_envs, pool):
+def check_products(gemm, tol, num_envs, pool):
     import torch
     import ccbs_b200 as cb
     from ccbs_b200.batched_env import BatchedCyberBattleEnv
@@ -29,3 +27,20 @@ def test_decode_products(gemm, tol, num_envs, pool):
     print("Ug", Ug, "max abs err", err.max(), "rel fro", np.linalg.norm(got - want) / np.linalg.norm(want))
     assert err.max() < tol
     env.close()
+
+
+@pytest.mark.parametrize("gemm,tol", [(1, 1e-3), (0, 0.35)], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("num_envs,pool", [(300, 40), (1024, 200), (130, 330)])
+def test_decode_products(gemm, tol, num_envs, pool):
+    check_products(gemm, tol, num_envs, pool)
+
+
+def test_decode_products_f16_variant():
+    """The opt-in half-precision contraction (CBS_GEMM_F16=1, read once per process: run in a child)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); from tests.test_gpu_decode_gemm import check_products\n"
+            "for n, p in ((300, 40), (1024, 200), (130, 330)): check_products(0, 0.35, n, p)\nprint('f16 ok')" % root)
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, CBS_GEMM_F16="1"), capture_output=True, text=True, timeout=300)
+    print(r.stdout[-2000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "f16 ok" in r.stdout
