@@ -1,6 +1,7 @@
 // cbs_types.h — device-side layout shared by all kernels of libcbsim.
 // Numbers mirror c-cyberbattlesim_b200/constants.py (tests/test_constants.py keeps them in sync).
 #pragma once
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -208,5 +209,34 @@ struct State {  // mutable, device pointers
   uint16_t* sub_newp;    // [B][ncap*ncap]     scratch (graphs beyond the shared-memory buffers): the pairs one table build touches
 };
 
+
+// ---- programmatic dependent launch (the step's three kernels overlap their heads with the previous kernel's tail) ----
+// A kernel launched through launch_pdl may START before the previous kernel on the stream has finished (once every CTA of that
+// kernel has called pdl_trigger or exited); it must not read or write anything an earlier kernel touches before pdl_wait(),
+// which returns when the previous kernel has completed and its writes are visible.  Launched with a plain <<<>>> (or with
+// CBS_NO_PDL=1) both calls are no-ops and the stream order is the usual one.  Works under stream capture (programmatic edges).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = getenv("CBS_NO_PDL") == nullptr;
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool allow, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (allow && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
 
 }  // namespace cbs

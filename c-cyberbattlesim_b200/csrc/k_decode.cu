@@ -232,6 +232,12 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   float* vt_sh_all = vn2_sh + vt_cached;                                                      // [SEL_WARPS][vt_cached]
   const long long t_begin = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Programmatic dependent launch (cbs_types.h): this CTA may have been scheduled while the contraction that produces VT is still
+  // draining; nothing of the env state or VT is touched before pdl_wait().  The next kernel (observe) stages its constant
+  // weights while this grid's last wave runs.
+  pdl_trigger();
+  for (int i = threadIdx.x; i < vt_cached; i += SEL_THREADS) vn2_sh[i] = i < T.num_global_vulns ? (float)T.vnorm2[i] : 1.f;
+  pdl_wait();
   // Longest-first schedule: the transition kernel of the previous step binned every env by the size of its action
   // table; warp w takes the w-th env counting from the heaviest bin.  The kernel's duration is set by the largest
   // tables, so they must start first.  (No complete binning -> identity order.)
@@ -249,7 +255,6 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
       }
     }
   }
-  for (int i = threadIdx.x; i < vt_cached; i += SEL_THREADS) vn2_sh[i] = i < T.num_global_vulns ? (float)T.vnorm2[i] : 1.f;
   const bool in_range = b < P.B;
   SelWarp& sh = sh_all[warp];
   float* vt_sh = vt_sh_all + (size_t)warp * vt_cached;
@@ -591,8 +596,8 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
     attr[which] = smem;
   }
   const int grid = (P.B + SEL_WARPS - 1) / SEL_WARPS;
-  kern<<<grid, SEL_THREADS, smem, stream>>>(T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out, dist_out, g_sel_trace);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(SEL_THREADS), smem, stream, true, T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,
+                    dist_out, g_sel_trace);
 }
 
 }  // namespace cbs

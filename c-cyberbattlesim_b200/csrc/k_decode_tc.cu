@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT_MAX;
   const int nt = min(NT_MAX, Upad - n0);             // columns this CTA produces (multiple of 16)
+  pdl_trigger();   // the next kernel (decode_select) may be scheduled as SMs free up; it waits for this grid before reading VT
   constexpr int KB = VULN_EMB / BK;                  // 24 slabs
 
   if (threadIdx.x == 0) {
@@ -207,6 +208,9 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
   const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
   GT(3);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  // Everything above reads only the caller's actions and the constant embedding table; VT is still being read by the previous
+  // step's decode_select if that step's kernels have not drained (programmatic dependent launch, cbs_types.h).
+  pdl_wait();
   const bool lane_has_row = BM == 128 || lane < 16;
   const int row = lane_has_row ? m0 + warp * (BM / 4) + lane : B;
   if (ready) {
@@ -307,6 +311,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) decode_gemm_f16_kernel(const _
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * NT_MAX;
   const int nt = min(NT_MAX, Upad - n0);
   constexpr int KB = VULN_EMB / F16_BK;               // 12 slabs
+  pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + 8); mbar_init(empty0 + 8 * s, 1); }
@@ -420,6 +425,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) decode_gemm_f16_kernel(const _
   // ---- epilogue (M = 64: tile row 16 w + lane on lanes 0-15 of warp w's TMEM sub-partition) ----
   const bool ready = warp < 4 && mbar_wait(tfull, 0, errflag);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  pdl_wait();      // VT may still be read by the previous step's decode_select (see the TF32 kernel)
   const int row = lane < 16 ? m0 + warp * (BM / 4) + lane : B;
   if (ready) {
     for (int c0 = 0; c0 < nt; c0 += 32) {
@@ -534,8 +540,8 @@ cudaError_t launch_decode_gemm_f16(const float* actions, int act_stride, const _
   }
   dim3 grid((B + F16_BM - 1) / F16_BM, ntiles_n);
   static const int knock = getenv("CBS_GEMM_KNOCK") ? atoi(getenv("CBS_GEMM_KNOCK")) : 0;   // debug: knock out A copies (1), MMAs (2), the conversion (4), B copies (8)
-  decode_gemm_f16_kernel<<<grid, F16_THREADS, smem, stream>>>(map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag, stages, knock);
-  return cudaGetLastError();
+  return launch_pdl(decode_gemm_f16_kernel, grid, dim3(F16_THREADS), smem, stream, true, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride,
+                    errflag, stages, knock);
 }
 
 cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const float* vemb, float* a_packed, float* vt, int B,
@@ -590,9 +596,9 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
 #ifdef CBS_GEMM_TRACE
   cudaMemcpyToSymbolAsync(g_sel_trace_dev, &g_sel_trace, sizeof(g_sel_trace), 0, cudaMemcpyHostToDevice, stream);
 #endif
-  kernels[which]<<<grid, ldgsts ? 256 : 128, smem, stream>>>(map_a, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride, errflag,
-                                                            direct ? 1 : 0, stages);
-  return cudaGetLastError();
+  // (the repacked slab is written by pack_actions_kernel right before: that variant keeps the plain stream order)
+  return launch_pdl(kernels[which], grid, dim3(ldgsts ? 256 : 128), smem, stream, direct || ldgsts, map_a, map_b, actions, act_stride, vt, B,
+                    Upad, nt_box, vt_stride, errflag, direct ? 1 : 0, stages);
 }
 
 }  // namespace cbs

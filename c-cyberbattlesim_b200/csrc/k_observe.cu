@@ -863,6 +863,11 @@ __global__ void __launch_bounds__(CBS_OBS_BOUND, CBS_OBS_MINB) observe_kernel(Ta
     if (threadIdx.x < NN_CH) cp4(&SW.nn0b[threadIdx.x], T.nn0_b + threadIdx.x);
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(wbar) : "memory");
   }
+  // Programmatic dependent launch (cbs_types.h): up to here only constant tables were read, so this CTA may have started while the
+  // transition that feeds it was still running.  The trigger comes AFTER the wait: the next step's contraction may then start its
+  // operand pipeline as this kernel's SMs free up, and everything before this kernel is known to be complete by then.
+  pdl_wait();
+  pdl_trigger();
   bool weights_ready = false;
   auto wait_weights = [&]() {
     if (weights_ready) return;
@@ -1081,8 +1086,7 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
     attr_set[which] = true;
   }
   // (pinning the folded node table in L2 with an access-policy window on this launch changed nothing: 37.1 us either way)
-  kernels[which]<<<grid, OBS_WARPS * 32, smem, stream>>>(T, P, S, reset_mask, mode, g_obs_trace);
-  return cudaGetLastError();
+  return launch_pdl(kernels[which], dim3(grid), dim3(OBS_WARPS * 32), smem, stream, true, T, P, S, reset_mask, mode, g_obs_trace);
 }
 
 }  // namespace cbs
