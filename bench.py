@@ -431,6 +431,8 @@ def main():
                     help="side measurement: the same workload with the re-imaging static defender of train_config.yaml:39-44 "
                          "(not the headline configuration)")
     ap.add_argument("--host-shards", type=int, default=4, help="handles the batch is cut into for the pipelined end-to-end leg")
+    ap.add_argument("--host-shard-weights", type=str, default="", help="comma-separated relative slice sizes of the pipelined end-to-end leg "
+                    "(overrides --host-shards; a small last slice shortens the tail after the action copy)")
     ap.add_argument("--transition-envs", type=int, default=1 << 20,
                     help="envs of the large-batch transition-kernel roofline leg (rank 0, N=1 only; 0 = skip)")
     ap.add_argument("--action-pitch", type=int, default=905,
@@ -658,7 +660,10 @@ def main():
     from ccbs_b200.host_pipeline import ShardedHostEnv
     e2e_api = f"ShardedHostEnv.step_host: {args.host_shards} handles x cbs_step_host_async, pinned host buffers"
     try:
-        penv = ShardedHostEnv(specs, weights, cfg, num_envs=B, shards=args.host_shards, device=local_rank, seed=7,
+        sw = [float(x) for x in args.host_shard_weights.split(",")] if args.host_shard_weights else None
+        if sw:
+            e2e_api = f"ShardedHostEnv.step_host: {len(sw)} handles (slice weights {args.host_shard_weights}) x cbs_step_host_async, pinned host buffers"
+        penv = ShardedHostEnv(specs, weights, cfg, num_envs=B, shards=args.host_shards, shard_weights=sw, device=local_rank, seed=7,
                               global_env_offset=rank * B, auto_reset=True, decode_gemm=args.decode_gemm)
         penv.reset()
         for i in range(64):      # bring the episodes to their steady-state mix before timing
@@ -721,6 +726,7 @@ def main():
                        "action_pitch_floats": args.action_pitch,
                        "actions": f"ring of {R} x [{B},905] f32 batches = {R * B * 905 * 4 / 1e6:.0f} MB (> 126 MB L2), no L2 flush",
                        "launch": (f"CUDA graph of {G} steps replayed {args.steps // G}x" if graph is not None else "plain launches"),
+                       "programmatic_dependent_launch": os.environ.get("CBS_NO_PDL") is None,
                        "presteps": args.presteps, "stats_allreduce": "side stream, behind the window's last step",
                        "sample_subset_samples": args.subset,
                        "decode_gemm": "tcgen05-tf32" if env.tensor_core_decode else "simt-f32",

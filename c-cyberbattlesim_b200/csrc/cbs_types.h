@@ -2,6 +2,9 @@
 // Numbers mirror c-cyberbattlesim_b200/constants.py (tests/test_constants.py keeps them in sync).
 #pragma once
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdint>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -218,6 +221,20 @@ struct State {  // mutable, device pointers
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per DEVICE: remember what was granted per (device, kernel), not per process
+inline cudaError_t ensure_dyn_smem(const void* func, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = granted[std::make_pair(dev, func)];
+  if (smem <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) cur = smem;
+  return e;
+}
 
 inline bool pdl_enabled() {
   static const bool on = getenv("CBS_NO_PDL") == nullptr;

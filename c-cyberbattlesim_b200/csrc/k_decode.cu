@@ -580,7 +580,6 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
   const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
   const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
-  static size_t attr[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const int which = ((fuse_transition ? 1 : 0) | (P.defender ? 2 : (P.words == 1 ? 4 : 0))) + (P.subset_k ? 6 : 0);
   using KernelFn = void (*)(Tables, Params, State, const float*, int, int, int, FusedTransition, int32_t*, double*, long long*);
   const KernelFn kernels[12] = {decode_select_kernel<false, false, false, false>, decode_select_kernel<true, false, false, false>,
@@ -590,10 +589,9 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
                                 decode_select_kernel<false, true, false, true>,   decode_select_kernel<true, true, false, true>,
                                 decode_select_kernel<false, false, true, true>,   decode_select_kernel<true, false, true, true>};
   const KernelFn kern = kernels[which];
-  if (smem > 48 * 1024 && smem > attr[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024) {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kern), smem);
     if (e != cudaSuccess) return e;
-    attr[which] = smem;
   }
   const int grid = (P.B + SEL_WARPS - 1) / SEL_WARPS;
   return launch_pdl(kern, dim3(grid), dim3(SEL_THREADS), smem, stream, true, T, P, S, actions, vt_stride, vt_cached, sched_buf, ft, sel_out,

@@ -532,11 +532,9 @@ cudaError_t launch_decode_gemm_f16(const float* actions, int act_stride, const _
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return cudaErrorInvalidValue;
   const size_t smem = (size_t)stages * stage_bytes + fixed;
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(decode_gemm_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(decode_gemm_f16_kernel), smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
   dim3 grid((B + F16_BM - 1) / F16_BM, ntiles_n);
   static const int knock = getenv("CBS_GEMM_KNOCK") ? atoi(getenv("CBS_GEMM_KNOCK")) : 0;   // debug: knock out A copies (1), MMAs (2), the conversion (4), B copies (8)
@@ -586,11 +584,9 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
   const int which = (ldgsts ? 1 : 0) | (half ? 2 : 0);
   const KernelFn kernels[4] = {decode_gemm_tc_kernel<false, 128>, decode_gemm_tc_kernel<true, 128>,
                                decode_gemm_tc_kernel<false, 64>, decode_gemm_tc_kernel<true, 64>};
-  static size_t attr[4] = {0, 0, 0, 0};
-  if (smem > attr[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kernels[which]), smem);
     if (e != cudaSuccess) return e;
-    attr[which] = smem;
   }
   dim3 grid((B + bm - 1) / bm, ntiles_n);
 #ifdef CBS_GEMM_TRACE

@@ -1079,11 +1079,9 @@ cudaError_t launch_observe(const Tables& T, const Params& P, const State& S, con
                                observe_kernel<false, true, true>,   observe_kernel<true, true, true>};
 #endif
   const int which = (big ? 1 : 0) | (P.subset_k ? 2 : 0) | (P.precise_positions ? 4 : 0);
-  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
-  if (!attr_set[which]) {
-    cudaError_t e = cudaFuncSetAttribute(kernels[which], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(kernels[which]), smem);
     if (e != cudaSuccess) return e;
-    attr_set[which] = true;
   }
   // (pinning the folded node table in L2 with an access-policy window on this launch changed nothing: 37.1 us either way)
   return launch_pdl(kernels[which], dim3(grid), dim3(OBS_WARPS * 32), smem, stream, true, T, P, S, reset_mask, mode, g_obs_trace);

@@ -21,11 +21,35 @@ from .gae import GaeWeights, fold_gae
 from .scenario import ScenarioSpec, compile_scenarios
 
 
+def slice_bounds(num_envs: int, shards: int, weights: Optional[Sequence[float]] = None):
+    """Contiguous [start, stop) env ranges of the pipeline's slices: equal (`shard_range`) or proportional to `weights`
+    (every slice keeps at least one env)."""
+    if weights is None or len(weights) != shards:
+        return [shard_range(num_envs, k, shards) for k in range(shards)]
+    w = np.asarray(weights, dtype=np.float64)
+    if not np.all(w > 0):
+        raise ValueError("shard_weights must be positive")
+    cuts = np.round(np.cumsum(w) / w.sum() * num_envs).astype(np.int64)
+    cuts[-1] = num_envs
+    lo, out = 0, []
+    for k, hi in enumerate(cuts):
+        hi = int(min(max(hi, lo + 1), num_envs - (shards - 1 - k)))
+        out.append((lo, hi))
+        lo = hi
+    return out
+
+
 class ShardedHostEnv:
     def __init__(self, specs: Sequence[ScenarioSpec], gae_weights: GaeWeights, cfg: Optional[EnvConfig] = None,
                  num_envs: int = 1, shards: int = 4, device: int = 0, scenario_of_env: Optional[np.ndarray] = None,
-                 seed: int = 0, global_env_offset: int = 0, interest_nodes: Optional[Sequence[int]] = None, **kw):
+                 seed: int = 0, global_env_offset: int = 0, interest_nodes: Optional[Sequence[int]] = None,
+                 shard_weights: Optional[Sequence[float]] = None, **kw):
+        """`shard_weights`: relative slice sizes (default: equal).  What a host step costs beyond the action copy is the LAST
+        slice's kernels and copy-out, after the link has gone idle; the step-path kernels are latency bound, so a small last
+        slice shortens that tail (bench.py's end-to-end leg uses tapering slices)."""
         cfg = cfg or EnvConfig()
+        if shard_weights is not None:
+            shards = len(shard_weights)
         shards = max(1, min(int(shards), int(num_envs)))
         node_goal = cfg.goal.endswith("node")
         tables = compile_scenarios(specs, cfg.isolation_filter_threshold, interest_nodes=interest_nodes if node_goal else None,
@@ -34,7 +58,7 @@ class ShardedHostEnv:
         if scenario_of_env is None:
             scenario_of_env = np.arange(num_envs, dtype=np.int32) % tables.num_scenarios
         self.scenario_of_env = np.ascontiguousarray(scenario_of_env, dtype=np.int32)
-        self.bounds = [shard_range(num_envs, k, shards) for k in range(shards)]
+        self.bounds = slice_bounds(num_envs, shards, shard_weights)
         self.envs = [BatchedCyberBattleEnv(specs, gae_weights, cfg, num_envs=hi - lo, device=device,
                                            scenario_of_env=self.scenario_of_env[lo:hi], seed=seed,
                                            global_env_offset=global_env_offset + lo, tables=tables, gae_tables=gae_tables, **kw)
