@@ -106,7 +106,8 @@ constexpr int SEL_VT_SMEM_MAX = 2048;   // floats of VT row cached per warp (lar
 struct SelWarp {
   float a_st[2 * NODE_EMB];   // source | target parts of the action
   float a_o[16];
-  float p_st[32], p_n2[32];   // per staged pair: a_s.z_s + a_t.z_t (from the fp16 snapshots), |z_s|^2 + |z_t|^2 + 1
+  float2 p_sn[32];            // per staged pair: (a_s.z_s + a_t.z_t from the fp16 snapshots, |z_s|^2 + |z_t|^2 + 1)
+  uint32_t p_fm[32];          // per staged pair: bit k set = rows of outcome kind k never enter the table (row_filtered)
   int p_r0[32], p_pre[33];    // first candidate row, exclusive prefix of row counts
   uint32_t p_key[32];         // insertion epoch << 24 | source's insertion position << 16 | discovered position << 8 | index in owned_order
   int p_slot[32];             // snapshot slot the pair's rows carry (== the epoch unless precise_action_space_positions refreshed them)
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   extern __shared__ __align__(16) unsigned char sel_smem[];
   SelWarp* sh_all = reinterpret_cast<SelWarp*>(sel_smem);
   float* vn2_sh = reinterpret_cast<float*>(sel_smem + SEL_WARPS * sizeof(SelWarp));          // [vt_cached] shared by the CTA
-  float* vt_sh_all = vn2_sh + vt_cached;                                                      // [SEL_WARPS][vt_cached]
+  float2* vtn_all = reinterpret_cast<float2*>(vn2_sh + vt_cached);                            // [SEL_WARPS][vt_cached] (VT[u], |v_u|^2)
   const long long t_begin = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Programmatic dependent launch (cbs_types.h): this CTA may have been scheduled while the contraction that produces VT is still
@@ -238,6 +239,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   pdl_trigger();
   for (int i = threadIdx.x; i < vt_cached; i += SEL_THREADS) vn2_sh[i] = i < T.num_global_vulns ? (float)T.vnorm2[i] : 1.f;
   pdl_wait();
+  __syncthreads();     // vn2_sh is complete before the prologues below interleave it with the env's VT row
   // Longest-first schedule: the transition kernel of the previous step binned every env by the size of its action
   // table; warp w takes the w-th env counting from the heaviest bin.  The kernel's duration is set by the largest
   // tables, so they must start first.  (No complete binning -> identity order.)
@@ -257,7 +259,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
   }
   const bool in_range = b < P.B;
   SelWarp& sh = sh_all[warp];
-  float* vt_sh = vt_sh_all + (size_t)warp * vt_cached;
+  float2* vtn = vtn_all + (size_t)warp * vt_cached;
 
   // ---- prologue: one burst of independent loads ----
   int flags = FL_NEEDS_RESET, node_off = 0, starter = 0, n_disc = 0, n_owned = 0;
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
       reinterpret_cast<uint32_t*>(sh.oorder)[lane] = osrc[lane];
     }
     const float* vt_row = S.vt + (size_t)b * vt_stride;
-    for (int i = lane; i < vt_cached; i += 32) vt_sh[i] = vt_row[i];
+    for (int i = lane; i < vt_cached; i += 32) vtn[i] = make_float2(vt_row[i], vn2_sh[i]);
     float a[29];
 #pragma unroll
     for (int i = 0; i < 29; ++i) { const int e = lane + 32 * i; a[i] = e < ACTION_DIM ? act[e] : 0.f; }
@@ -319,9 +321,10 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
 #pragma unroll
     for (int c = 0; c < SUB_CLASSES; ++c) { total += meta[c]; cls_end[c] = total; }
     const uint32_t rank_lo = (uint32_t)meta[11], rank_hi = (uint32_t)meta[12];
-    // positions of the nodes in the two order lists (tie order); p_st / p_n2 double as byte arrays here
-    uint8_t* dpos = reinterpret_cast<uint8_t*>(sh.p_st);
-    uint8_t* opos = reinterpret_cast<uint8_t*>(sh.p_n2);
+    // positions of the nodes in the two order lists (tie order); p_sn (256 bytes) doubles as two byte arrays here
+    static_assert(sizeof(SelWarp::p_sn) >= 2 * MAX_NODES, "p_sn holds two MAX_NODES byte arrays in subset mode");
+    uint8_t* dpos = reinterpret_cast<uint8_t*>(sh.p_sn);
+    uint8_t* opos = dpos + MAX_NODES;
     for (int i = lane; i < n_disc; i += 32) dpos[sh.dorder[i]] = (uint8_t)i;
     if (!DEF) for (int i = lane; i < n_owned; i += 32) opos[sh.oorder[i]] = (uint8_t)i;
     __syncwarp();
@@ -358,9 +361,8 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
           st += dot8(ht[i], sh.a_st + NODE_EMB + 8 * i);
         }
         const int u = packed & 0xFFFFF, oh = (packed >> 24) & 15;
-        const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
-        const float vn2 = u < vt_cached ? vn2_sh[u] : (float)T.vnorm2[u];
-        score = (st + vtu + sh.a_o[oh]) * rsqrtf(n2 + vn2);
+        const float2 vv = u < vt_cached ? vtn[u] : make_float2(vt_g[u], (float)T.vnorm2[u]);
+        score = (st + vv.x + sh.a_o[oh]) * rsqrtf(n2 + vv.y);
         valid = true;
         // table order: the classes in first-appearance order, inside a class the insertion order
         const uint32_t rank = ((c < 8 ? rank_lo : rank_hi) >> (4 * (c & 7))) & 15u;
@@ -396,7 +398,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     bool live = false;
     float st = 0.f, n2 = 0.f;
     int r0 = 0, cnt = 0, slot_of_pair = 0;
-    uint32_t key = 0;
+    uint32_t key = 0, fm = 0;
     if (c < combos) {
       const int op = c / n_disc, dp = c - op * n_disc;
       const int s = sh.oorder[op], t = sh.dorder[dp];
@@ -425,6 +427,8 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
         key = ((uint32_t)epoch << 24) | ((uint32_t)opk << 16) | ((uint32_t)dp << 8) | (uint32_t)op;
         slot_of_pair = slot;
         live = cnt > 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) fm |= row_filtered(P, k, s, t, starter, interest) ? (1u << k) : 0u;   // folds to three tests
       }
     }
     const unsigned lmask = __ballot_sync(0xFFFFFFFFu, live);
@@ -432,7 +436,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     n_live += npairs;
     if (npairs == 0) continue;
     const int idx = __popc(lmask & ((1u << lane) - 1u));
-    if (live) { sh.p_st[idx] = st; sh.p_n2[idx] = n2; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_slot[idx] = slot_of_pair; sh.p_pre[idx + 1] = cnt; }
+    if (live) { sh.p_sn[idx] = make_float2(st, n2); sh.p_fm[idx] = fm; sh.p_r0[idx] = r0; sh.p_key[idx] = key; sh.p_slot[idx] = slot_of_pair; sh.p_pre[idx + 1] = cnt; }
     if (lane == 0) sh.p_pre[0] = 0;
     __syncwarp();
     int run = (lane < npairs) ? sh.p_pre[lane + 1] : 0;
@@ -487,13 +491,11 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
         score[q] = -INFINITY; valid[q] = false;
         if (j < total) {
           const int kind = (packed[q] >> 20) & 15;
-          const uint32_t k = sh.p_key[pp[q]];
-          const int s = sh.oorder[k & 0xFF], t = sh.dorder[(k >> 8) & 0xFF];
-          if (!row_filtered(P, kind, s, t, starter, interest)) {
+          if (!((sh.p_fm[pp[q]] >> kind) & 1u)) {
             const int u = packed[q] & 0xFFFFF, oh = (packed[q] >> 24) & 15;
-            const float vtu = u < vt_cached ? vt_sh[u] : vt_g[u];
-            const float vn2 = u < vt_cached ? vn2_sh[u] : (float)T.vnorm2[u];
-            score[q] = (sh.p_st[pp[q]] + vtu + sh.a_o[oh]) * rsqrtf(sh.p_n2[pp[q]] + vn2);
+            const float2 vv = u < vt_cached ? vtn[u] : make_float2(vt_g[u], (float)T.vnorm2[u]);
+            const float2 sn = sh.p_sn[pp[q]];
+            score[q] = (sn.x + vv.x + sh.a_o[oh]) * rsqrtf(sn.y + vv.y);
             valid[q] = true;
             cmax = fmaxf(cmax, score[q]);
           }
@@ -579,7 +581,7 @@ cudaError_t launch_decode_select(const Tables& T, const Params& P, const State& 
                                  int32_t* sel_out, double* dist_out, cudaStream_t stream) {
   const FusedTransition ft{fuse_transition, uniforms, reward, done};
   const int vt_cached = vt_stride <= SEL_VT_SMEM_MAX ? vt_stride : SEL_VT_SMEM_MAX;
-  const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(SEL_WARPS + 1) * vt_cached * sizeof(float);
+  const size_t smem = SEL_WARPS * sizeof(SelWarp) + (size_t)(2 * SEL_WARPS + 1) * vt_cached * sizeof(float);
   const int which = ((fuse_transition ? 1 : 0) | (P.defender ? 2 : (P.words == 1 ? 4 : 0))) + (P.subset_k ? 6 : 0);
   using KernelFn = void (*)(Tables, Params, State, const float*, int, int, int, FusedTransition, int32_t*, double*, long long*);
   const KernelFn kernels[12] = {decode_select_kernel<false, false, false, false>, decode_select_kernel<true, false, false, false>,
