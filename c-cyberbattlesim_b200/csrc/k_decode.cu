@@ -454,32 +454,30 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
     // ---- phase B: candidate rows of the staged pairs, flattened over the lanes, RPL rows per lane per trip; the
     //      row templates of the NEXT trip are requested before the current trip is scored ----
     int pi = 0;                                             // rows are visited in increasing order: the pair index only grows
-    int rr_n[RPL], pp_n[RPL];
+    int pp_n[RPL];                                          // (a row's table index is recomputed from its pair if it gets parked)
     uint32_t packed_n[RPL];
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
       const int j = q * 32 + lane;
-      rr_n[q] = 0; pp_n[q] = 0; packed_n[q] = 0;
+      pp_n[q] = 0; packed_n[q] = 0;
       if (j < total) {
         while (sh.p_pre[pi + 1] <= j) ++pi;
         pp_n[q] = pi;
-        rr_n[q] = sh.p_r0[pi] + (j - sh.p_pre[pi]);
-        packed_n[q] = T.row_packed[rr_n[q]];
+        packed_n[q] = T.row_packed[sh.p_r0[pi] + (j - sh.p_pre[pi])];
       }
     }
     for (int j0 = 0; j0 < total; j0 += RPL * 32) {
-      int rr[RPL], pp[RPL];
+      int pp[RPL];
       uint32_t packed[RPL];
 #pragma unroll
-      for (int q = 0; q < RPL; ++q) { rr[q] = rr_n[q]; pp[q] = pp_n[q]; packed[q] = packed_n[q]; }
+      for (int q = 0; q < RPL; ++q) { pp[q] = pp_n[q]; packed[q] = packed_n[q]; }
 #pragma unroll
       for (int q = 0; q < RPL; ++q) {                       // prefetch the next trip
         const int j = j0 + RPL * 32 + q * 32 + lane;
         if (j < total) {
           while (sh.p_pre[pi + 1] <= j) ++pi;
           pp_n[q] = pi;
-          rr_n[q] = sh.p_r0[pi] + (j - sh.p_pre[pi]);
-          packed_n[q] = T.row_packed[rr_n[q]];
+          packed_n[q] = T.row_packed[sh.p_r0[pi] + (j - sh.p_pre[pi])];
         }
       }
       float score[RPL];
@@ -501,8 +499,13 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
           }
         }
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xFFFFFFFFu, cmax, o));
+      {   // warp maximum in one REDUX on the order-preserving integer image of the float (cmax is never NaN: fmaxf dropped them)
+        int ci = __float_as_int(cmax);
+        ci ^= (ci >> 31) & 0x7FFFFFFF;
+        ci = __reduce_max_sync(0xFFFFFFFFu, ci);
+        ci ^= (ci >> 31) & 0x7FFFFFFF;
+        cmax = __int_as_float(ci);
+      }
       run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
 #pragma unroll
       for (int q = 0; q < RPL; ++q) {
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
           if (ncand == CAND_CAP) { n_exact += ncand; flush_candidates(T, P, S, act, sh, ncand, run_max - margin_s, b, na, lane, best); }
           const float cs = __shfl_sync(0xFFFFFFFFu, score[q], src);
           const int cpi = __shfl_sync(0xFFFFFFFFu, pp[q], src);
-          const int cr = __shfl_sync(0xFFFFFFFFu, rr[q], src);
+          const int cr = sh.p_r0[cpi] + (j0 + q * 32 + src - sh.p_pre[cpi]);
           const uint32_t cp = __shfl_sync(0xFFFFFFFFu, packed[q], src);
           if (lane == 0) {
             const uint32_t pk = sh.p_key[cpi];
