@@ -99,7 +99,7 @@ cudaError_t launch_decode_gemm_simt(const float* actions, int act_stride, const 
 #endif
 constexpr int SEL_WARPS = CBS_SEL_WARPS;
 constexpr int SEL_THREADS = SEL_WARPS * 32;
-constexpr int CAND_CAP = 4;
+constexpr int CAND_CAP = 16;
 constexpr int RPL = 4;          // rows per lane per trip
 constexpr int SEL_VT_SMEM_MAX = 2048;   // floats of VT row cached per warp (larger tables fall back to global gathers)
 
@@ -507,6 +507,10 @@ __global__ void __launch_bounds__(SEL_THREADS, CBS_SEL_MINB) decode_select_kerne
         cmax = __int_as_float(ci);
       }
       run_max = fmaxf(run_max, cmax);                       // fmaxf drops NaN; NaN rows are candidates below
+      bool any_c = false;
+#pragma unroll
+      for (int q = 0; q < RPL; ++q) any_c |= valid[q] && !(score[q] < run_max - margin_s);
+      if (!__any_sync(0xFFFFFFFFu, any_c)) continue;       // the common trip: nothing within the margin of the running maximum
 #pragma unroll
       for (int q = 0; q < RPL; ++q) {
         unsigned cand = __ballot_sync(0xFFFFFFFFu, valid[q] && !(score[q] < run_max - margin_s));
