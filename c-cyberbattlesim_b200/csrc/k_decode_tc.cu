@@ -575,7 +575,16 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
     if (!ldgsts) pack_actions_kernel<<<(B + 1) / 2, 256, 0, stream>>>(actions, a_packed, B, act_stride);
   }
   const size_t stage_bytes = (size_t)bm * BK * 4 + (size_t)nt_box * BK * 4;
-  int stages = (int)((225 * 1024 - 1024 - 256) / stage_bytes);
+  // Launched with a programmatic dependency (cbs_types.h), the kernel leaves kPdlReserve bytes of the SM's shared memory to the CTAs
+  // of the NEXT kernel (decode_select, ~17 KB each): they become resident beside this CTA, finish their constant-only head and
+  // start their table scans the moment this grid completes, instead of being launched then.  Measured (graph replay, 8192 envs):
+  // ring of 6 stages (209 KB, nothing fits beside it) 0.0970 ms per step, 5 or 4 stages 0.0932 ms, 3 stages 0.1042 ms; the kernel
+  // itself is no slower with 4-5 stages (beyond 4 stages the operand pipeline is not what bounds it).
+  constexpr size_t kPdlReserve = 48 * 1024;
+  const bool pdl = (direct || ldgsts) && pdl_enabled();
+  const int fit = (int)((225 * 1024 - 1024 - 256) / stage_bytes);
+  int stages = pdl ? (int)((225 * 1024 - 1024 - 256 - kPdlReserve) / stage_bytes) : fit;
+  if (stages < 4) stages = fit < 4 ? fit : 4;     // the reserve never costs the ring its fourth stage
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   static const char* stages_env = getenv("CBS_GEMM_STAGES");
   if (stages_env && atoi(stages_env) >= 2 && atoi(stages_env) < stages) stages = atoi(stages_env);
