@@ -423,6 +423,8 @@ def main():
     ap.add_argument("--no-affinity", action="store_true", help="do not bind the rank to its GPU's local CPU cores")
     ap.add_argument("--ring", type=int, default=0, help="minimum number of action batches in the device-resident ring")
     ap.add_argument("--no-graph", action="store_true", help="time plain per-step launches instead of CUDA-graph replays")
+    ap.add_argument("--no-prestaged", action="store_true", help="do not declare the action ring pre-staged (cbs_set_actions_prestaged): the "
+                    "contraction then waits for the previous step's observe kernel before reading its actions, as it must behind a policy")
     ap.add_argument("--presteps", type=int, default=64, help="untimed steps before the warm-up: episodes reach their steady-state mix")
     ap.add_argument("--subset", type=int, default=0, help="side measurement: sample_subset_samples=K (the reference's training default is 100)")
     ap.add_argument("--no-vecenv", action="store_true", help="skip the configs[4] leg (CyberBattleVecEnv.step and the PPO loop)")
@@ -450,6 +452,11 @@ def main():
         os.dup2(saved_stdout, 1)
         print(json.dumps(obj), flush=True)
 
+    # Every action batch this script steps with is generated before the timed window (a ring of device tensors, or pinned host
+    # buffers copied by the library itself): declare that to the library (include/cbsim.h: cbs_set_actions_prestaged), so that
+    # step t+1's contraction may read its actions while step t's observe kernel drains.  --no-prestaged measures without it.
+    if not args.no_prestaged:
+        os.environ.setdefault("CBS_ACTIONS_PRESTAGED", "1")
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -727,6 +734,7 @@ def main():
                        "actions": f"ring of {R} x [{B},905] f32 batches = {R * B * 905 * 4 / 1e6:.0f} MB (> 126 MB L2), no L2 flush",
                        "launch": (f"CUDA graph of {G} steps replayed {args.steps // G}x" if graph is not None else "plain launches"),
                        "programmatic_dependent_launch": os.environ.get("CBS_NO_PDL") is None,
+                       "actions_prestaged": os.environ.get("CBS_ACTIONS_PRESTAGED") is not None,
                        "presteps": args.presteps, "stats_allreduce": "side stream, behind the window's last step",
                        "sample_subset_samples": args.subset,
                        "decode_gemm": "tcgen05-tf32" if env.tensor_core_decode else "simt-f32",

@@ -140,6 +140,12 @@ class BatchedCyberBattleEnv:
         self._def_draws = (scan_nodes, detect_uniforms)          # keep them alive
         self._check(self.lib.cbs_set_defender_draws(self._h, self._p(scan_nodes), self._p(detect_uniforms)))
 
+    def set_actions_prestaged(self, on: bool = True):
+        """Declare that the action tensors passed to step() / decode() are complete long before the call (a pre-generated ring,
+        a recorded trace) - not produced by a kernel enqueued just before it.  Lets the contraction of the next step read them
+        while this step's observe kernel drains (include/cbsim.h: cbs_set_actions_prestaged).  Off by default."""
+        self._check(self.lib.cbs_set_actions_prestaged(self._h, 1 if on else 0))
+
     def set_cut_off(self, cut_off: int):
         """cyberbattle_env_switch.py:198-199"""
         self.cfg.episode_iterations = int(cut_off)

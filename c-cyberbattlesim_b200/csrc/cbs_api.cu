@@ -13,8 +13,8 @@
 
 namespace cbs {
 cudaError_t launch_decode_gemm_simt(const float*, int, const float*, float*, int, int, int, cudaStream_t);
-cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float*, int, int, int, int32_t*, cudaStream_t);
-cudaError_t launch_decode_gemm_f16(const float*, int, const __half*, float*, int, int, int, int32_t*, cudaStream_t);
+cudaError_t launch_decode_gemm_tc(const float*, int, const float*, float*, float*, int, int, int, int32_t*, int, cudaStream_t);
+cudaError_t launch_decode_gemm_f16(const float*, int, const __half*, float*, int, int, int, int32_t*, int, cudaStream_t);
 cudaError_t convert_vemb_f16(const float*, __half*, size_t, cudaStream_t);
 bool decode_gemm_f16_applies(int, int);
 bool decode_gemm_tc_available();
@@ -119,6 +119,7 @@ struct cbs_handle {
   int Ug = 0, vt_stride = 0;
   int64_t launches = 0;
   bool use_tc = false;
+  bool actions_prestaged = getenv("CBS_ACTIONS_PRESTAGED") != nullptr;   // cbs_set_actions_prestaged
   int sched_buf = 0;     // cost-bin buffer the next decode reads (the transitions of that step fill the other one)
   int num_sms = 148;
   float* a_packed = nullptr;   // [B][768] 16-byte aligned copy of the vulnerability part of the action (TMA source)
@@ -486,6 +487,12 @@ int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats) {
   return CBS_OK;
 }
 
+int cbs_set_actions_prestaged(cbs_handle* h, int32_t on) {
+  if (!h) return CBS_ERR_INVALID_ARG;
+  h->actions_prestaged = on != 0;
+  return CBS_OK;
+}
+
 int cbs_set_defender_draws(cbs_handle* h, const int32_t* scan_nodes_dev, const float* detect_uniforms_dev) {
   if (!h) return CBS_ERR_INVALID_ARG;
   if (!h->P.defender) return fail(h, CBS_ERR_INVALID_ARG, "no static defender configured");
@@ -510,7 +517,7 @@ int cbs_set_cutoffs(cbs_handle* h, int32_t episode_iterations, double prop) {
   return CBS_OK;
 }
 
-static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st);
+static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st, bool prestaged = false);
 
 static int check_ready(cbs_handle* h) {
   if (!h) return CBS_ERR_INVALID_ARG;
@@ -578,12 +585,14 @@ int cbs_observe(cbs_handle* h, float* obs_dev, uintptr_t stream) {
   return CBS_OK;
 }
 
-static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st) {
+// prestaged: this call's actions are known to be complete (cbs_replay's later steps); else the handle's declaration decides
+static int launch_gemm(cbs_handle* h, const float* actions_dev, cudaStream_t st, bool prestaged) {
+  const int wait_early = (prestaged || h->actions_prestaged) ? 0 : 1;
   if (h->use_tc) {
     if (h->vemb16 && decode_gemm_f16_applies(h->P.B, h->Ug))
-      CK(h, launch_decode_gemm_f16(actions_dev, h->P.act_stride, h->vemb16, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+      CK(h, launch_decode_gemm_f16(actions_dev, h->P.act_stride, h->vemb16, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, wait_early, st));
     else
-      CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, st));
+      CK(h, launch_decode_gemm_tc(actions_dev, h->P.act_stride, h->T.vemb32, h->a_packed, h->S.vt, h->P.B, h->Ug, h->vt_stride, h->S.errflag, wait_early, st));
     h->launches += 1;
   } else {
     CK(h, launch_decode_gemm_simt(actions_dev, h->P.act_stride, h->T.vemb32, h->S.vt, h->P.B, h->Ug, h->vt_stride, st));
@@ -644,7 +653,7 @@ int cbs_replay(cbs_handle* h, const float* actions_dev, const float* uniforms_de
         CK(h, launch_decode_metric(h->T, h->P, h->S, a, h->vt64, h->Ug, h->sched_buf, nullptr, nullptr, st));
         h->launches += 2;
       } else {
-        if ((rc = launch_gemm(h, a, st))) return rc;
+        if ((rc = launch_gemm(h, a, st, t > 0))) return rc;
         CK(h, launch_decode_select(h->T, h->P, h->S, a, h->vt_stride, h->sched_buf, 0, nullptr, nullptr, nullptr, nullptr, nullptr, st));
         h->launches += 1;
       }
@@ -655,7 +664,7 @@ int cbs_replay(cbs_handle* h, const float* actions_dev, const float* uniforms_de
       CK(h, launch_transition(h->T, h->P, h->S, h->S.sel, h->S.dist, u, h->sched_buf ^ 1, nullptr, nullptr, nullptr, nullptr, h->num_sms, st));
       h->launches += 1;
     } else {
-      if ((rc = launch_gemm(h, a, st))) return rc;
+      if ((rc = launch_gemm(h, a, st, t > 0))) return rc;   // (the whole [T, B, pitch] slab was staged before the call)
       CK(h, launch_decode_select(h->T, h->P, h->S, a, h->vt_stride, h->sched_buf, 1, u, nullptr, nullptr, nullptr, nullptr, st));
       h->launches += 1;
     }

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
                                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                                  const float* __restrict__ actions, int act_stride,
                                                                                  float* __restrict__ vt, int B, int Upad, int nt_box,
-                                                                                 int vt_stride, int32_t* errflag, int direct, int STAGES) {
+                                                                                 int vt_stride, int32_t* errflag, int direct, int STAGES, int wait_early) {
 #ifdef CBS_GEMM_TRACE   // debug build (-DCBS_GEMM_TRACE): per-CTA, per-warp phase stamps, read by tools/gemm_trace.py
   long long tt[6] = {0, 0, 0, 0, 0, 0};
 #define GT(k) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[k]))
@@ -145,6 +145,10 @@ __global__ void __launch_bounds__(LDGSTS_A ? 256 : 128, 1) decode_gemm_tc_kernel
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *tmem_slot;
   GT(1);
+  // wait_early (the default): nothing is READ before the previous kernel on the stream has completed - only the barrier / TMEM
+  // set-up above overlaps it.  With actions the caller declared pre-staged (cbs_set_actions_prestaged) the whole operand pipeline
+  // runs first and only the VT stores wait.
+  if (wait_early) pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ---- TMA producer ----
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(256) convert_f16_kernel(const float* __restric
 __global__ void __launch_bounds__(F16_THREADS, 1) decode_gemm_f16_kernel(const __grid_constant__ CUtensorMap map_b,
                                                                  const float* __restrict__ actions, int act_stride,
                                                                  float* __restrict__ vt, int B, int Upad, int nt_box, int vt_stride,
-                                                                 int32_t* errflag, int STAGES, int knock) {
+                                                                 int32_t* errflag, int STAGES, int knock, int wait_early) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int BM = F16_BM;
@@ -312,6 +316,7 @@ __global__ void __launch_bounds__(F16_THREADS, 1) decode_gemm_f16_kernel(const _
   const int nt = min(NT_MAX, Upad - n0);
   constexpr int KB = VULN_EMB / F16_BK;               // 12 slabs
   pdl_trigger();
+  if (wait_early) pdl_wait();      // (see the TF32 kernel)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full0 + 8 * s, 1 + 8); mbar_init(empty0 + 8 * s, 1); }
@@ -510,7 +515,7 @@ bool decode_gemm_f16_applies(int B, int Ug) {
 }
 
 cudaError_t launch_decode_gemm_f16(const float* actions, int act_stride, const __half* vemb16, float* vt, int B, int Ug,
-                                   int vt_stride, int32_t* errflag, cudaStream_t stream) {
+                                   int vt_stride, int32_t* errflag, int wait_early, cudaStream_t stream) {
   if (!load_encode()) return cudaErrorNotSupported;
   const int Upad = ((Ug + 15) / 16) * 16;
   const int nt_box = Upad < NT_MAX ? Upad : NT_MAX;
@@ -539,11 +544,11 @@ cudaError_t launch_decode_gemm_f16(const float* actions, int act_stride, const _
   dim3 grid((B + F16_BM - 1) / F16_BM, ntiles_n);
   static const int knock = getenv("CBS_GEMM_KNOCK") ? atoi(getenv("CBS_GEMM_KNOCK")) : 0;   // debug: knock out A copies (1), MMAs (2), the conversion (4), B copies (8)
   return launch_pdl(decode_gemm_f16_kernel, grid, dim3(F16_THREADS), smem, stream, true, map_b, actions, act_stride, vt, B, Upad, nt_box, vt_stride,
-                    errflag, stages, knock);
+                    errflag, stages, knock, wait_early);
 }
 
 cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const float* vemb, float* a_packed, float* vt, int B,
-                                  int Ug, int vt_stride, int32_t* errflag, cudaStream_t stream) {
+                                  int Ug, int vt_stride, int32_t* errflag, int wait_early, cudaStream_t stream) {
   if (!load_encode()) return cudaErrorNotSupported;
   const int Upad = ((Ug + 15) / 16) * 16;
   const int nt_box = Upad < NT_MAX ? Upad : NT_MAX;
@@ -589,7 +594,7 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
   static const char* stages_env = getenv("CBS_GEMM_STAGES");
   if (stages_env && atoi(stages_env) >= 2 && atoi(stages_env) < stages) stages = atoi(stages_env);
   const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const float*, int, float*, int, int, int, int, int32_t*, int, int);
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const float*, int, float*, int, int, int, int, int32_t*, int, int, int);
   const int which = (ldgsts ? 1 : 0) | (half ? 2 : 0);
   const KernelFn kernels[4] = {decode_gemm_tc_kernel<false, 128>, decode_gemm_tc_kernel<true, 128>,
                                decode_gemm_tc_kernel<false, 64>, decode_gemm_tc_kernel<true, 64>};
@@ -603,7 +608,7 @@ cudaError_t launch_decode_gemm_tc(const float* actions, int act_stride, const fl
 #endif
   // (the repacked slab is written by pack_actions_kernel right before: that variant keeps the plain stream order)
   return launch_pdl(kernels[which], grid, dim3(ldgsts ? 256 : 128), smem, stream, direct || ldgsts, map_a, map_b, actions, act_stride, vt, B,
-                    Upad, nt_box, vt_stride, errflag, direct ? 1 : 0, stages);
+                    Upad, nt_box, vt_stride, errflag, direct ? 1 : 0, stages, wait_early);
 }
 
 }  // namespace cbs

@@ -70,7 +70,7 @@ class CbsGaeTables(ct.Structure):
 
 # every symbol include/cbsim.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = ["cbs_abi_version", "cbs_create", "cbs_destroy", "cbs_last_error", "cbs_load_scenarios", "cbs_set_scenarios",
-           "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_defender_draws", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition",
+           "cbs_set_starter_queue", "cbs_set_action_stride", "cbs_set_actions_prestaged", "cbs_set_defender_draws", "cbs_set_cutoffs", "cbs_reset", "cbs_decode", "cbs_transition",
            "cbs_transition_ksteps", "cbs_observe",
            "cbs_step", "cbs_replay", "cbs_profile_step", "cbs_step_host", "cbs_step_host_async", "cbs_host_sync", "cbs_read_state", "cbs_state_ptr", "cbs_get_state", "cbs_episode_stats", "cbs_reset_stat_accum", "cbs_debug_select_trace", "cbs_debug_observe_trace", "cbs_launch_count",
            "cbs_sync", "cbs_struct_sizes", "cbs_state_bytes", "cbs_capacities"]
@@ -130,6 +130,7 @@ def load_library():
     lib.cbs_set_cutoffs.argtypes = [H, i32, f64]
     lib.cbs_set_defender_draws.argtypes = [H, P, P]
     lib.cbs_set_action_stride.argtypes = [H, i32]
+    lib.cbs_set_actions_prestaged.argtypes = [H, i32]
     lib.cbs_reset.argtypes = [H, P, P, P]
     lib.cbs_decode.argtypes = [H, P, P, P, P]
     lib.cbs_transition.argtypes = [H, P, P, P, P, P, P, P, P]

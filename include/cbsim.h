@@ -192,6 +192,15 @@ int cbs_set_starter_queue(cbs_handle* h, const int32_t* queue_host, int32_t qlen
  * that is a multiple of 4 floats the tensor-core contraction reads the tensor in place through TMA; a dense tensor
  * is repacked first (TMA cannot address 3620-byte rows). */
 int cbs_set_action_stride(cbs_handle* h, int32_t stride_floats);
+/* Declares that the action tensors handed to cbs_decode / cbs_step are COMPLETE well before the call is made - written by work
+ * that finished before the previous library call on the stream did (a pre-recorded trace, a ring of pre-generated batches; NOT
+ * the output of a policy kernel enqueued just before the call).  The step's kernels are launched with programmatic dependencies;
+ * with this declaration the tensor-core contraction of step t+1 reads its actions while step t's observation kernel is still
+ * draining (0.101 -> 0.093 ms per step at 8192 envs) instead of waiting for it first.  Off by default (always correct; costs
+ * nothing when a policy runs between the steps, since nothing could overlap then); the environment variable
+ * CBS_ACTIONS_PRESTAGED=1 turns it on for every handle of the process.  cbs_replay applies it to its steps 1..T-1 by itself
+ * (its whole action slab is staged before the call).  No reference counterpart (the reference steps one env on the host). */
+int cbs_set_actions_prestaged(cbs_handle* h, int32_t on);
 /* (events defender: detect_uniforms_dev is float32 [num_envs][max_nodes][4] = per node { function index 0 start service / 1 firewall
  * remove / 2 stop service / 3 firewall add, event uniform, pick uniform, side uniform } replacing random.choice /
  * numpy.random.random of _env/static_defender.py:80-161; scan_nodes_dev is ignored.) */

@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def check_products(gemm, tol, num_envs, pool):
+def check_products(gemm, tol, num_envs, pool, prestaged=False):
     import torch
     import ccbs_b200 as cb
     from ccbs_b200.batched_env import BatchedCyberBattleEnv
@@ -15,6 +15,8 @@ def check_products(gemm, tol, num_envs, pool):
     env = BatchedCyberBattleEnv(specs, GaeWeights.random(0), cb.EnvConfig(), num_envs=num_envs, decode_gemm=gemm)
     if gemm == 0:
         assert env.tensor_core_decode, "tcgen05 path not active on this device"
+    if prestaged:
+        env.set_actions_prestaged(True)
     env.reset()
     rng = np.random.default_rng(1)
     a = rng.uniform(-4, 4, size=(num_envs, 905)).astype(np.float32)
@@ -33,6 +35,11 @@ def check_products(gemm, tol, num_envs, pool):
 @pytest.mark.parametrize("num_envs,pool", [(300, 40), (1024, 200), (130, 330)])
 def test_decode_products(gemm, tol, num_envs, pool):
     check_products(gemm, tol, num_envs, pool)
+
+
+def test_decode_products_prestaged_actions():
+    """cbs_set_actions_prestaged: the contraction reads its actions before waiting for the previous kernel on the stream."""
+    check_products(0, 0.35, 1024, 200, prestaged=True)
 
 
 def test_decode_products_f16_variant():
