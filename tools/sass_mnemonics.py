@@ -6,13 +6,13 @@
 import collections, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "c-cyberbattlesim_b200", "libcbsim.so")
-KEYS = ["UTCHMMA", "UTCQMMA", "UTMALDG", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "LDGSTS", "REDUX", "ACQBULK", "PREEXIT", "LDG", "BAR.SYNC",
+KEYS = ["UTCHMMA", "UTCQMMA", "UTMALDG", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "LDGSTS", "CREDUX", "REDUX", "ACQBULK", "PREEXIT", "LDG", "BAR.SYNC",
         "SHFL", "STG", "MUFU.RSQ", "ATOMS", "ATOMG", "RED", "DFMA", "HFMA2", "F2FP"]
 sass = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(["c++filt"], input="\n".join(re.findall(r"Function : (\S+)", sass)), capture_output=True, text=True).stdout.split("\n")
 print("# cuobjdump -sass c-cyberbattlesim_b200/libcbsim.so (sm_100a), per kernel: total SASS instructions and the mnemonics that prove the")
 print("# hardware paths (UTCHMMA = tcgen05.mma, UTMALDG = TMA tensor load, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UBLKCP = cp.async.bulk,")
-print("# SYNCS = mbarrier, LDGSTS = cp.async, REDUX = warp reduction, ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents,")
+print("# SYNCS = mbarrier, LDGSTS = cp.async, CREDUX / REDUX = warp reduction (the row scan's maximum), ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents,")
 print("# DFMA = float64 re-score)")
 blocks = sass.split("Function : ")[1:]
 for blk, name in zip(blocks, names):
