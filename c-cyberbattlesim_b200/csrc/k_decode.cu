@@ -101,7 +101,9 @@ constexpr int SEL_WARPS = CBS_SEL_WARPS;
 constexpr int SEL_THREADS = SEL_WARPS * 32;
 constexpr int CAND_CAP = 16;
 constexpr int RPL = 4;          // rows per lane per trip
-constexpr int SEL_VT_SMEM_MAX = 2048;   // floats of VT row cached per warp (larger tables fall back to global gathers)
+constexpr int SEL_VT_SMEM_MAX = 2048;   // (VT[u], |v_u|^2) pairs cached per warp (larger pools fall back to global gathers for the rest).
+                                        // The CTA's share is (2 SEL_WARPS + 1) x 4 bytes per cached entry: five CTAs per SM fit up to
+                                        // ~1000 global vulnerabilities (the measured workloads: 200 and 600), four up to ~1300, two at 2048.
 
 struct SelWarp {
   float a_st[2 * NODE_EMB];   // source | target parts of the action
