@@ -40,3 +40,19 @@ def test_weights_must_be_positive_and_match_the_slice_count():
     with pytest.raises(ValueError):
         slice_bounds(100, 3, [1, 0, 1])
     assert slice_bounds(100, 4, [1, 2]) == [shard_range(100, r, 4) for r in range(4)]   # wrong length: ignored
+
+
+def test_order_preserving_integer_image_of_a_float():
+    """decode_select takes the warp maximum of float32 scores with one integer REDUX (k_decode.cu: ci ^= (ci >> 31) & 0x7FFFFFFF before
+    and after): the image must order like the floats (NaN never reaches it; -0.0 sorts below +0.0, which fmaxf may return either way)."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.standard_normal(4096).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 4096).astype(np.float32),
+                        np.array([0.0, -0.0, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38], dtype=np.float32)])
+    i = x.view(np.int32).copy()
+    img = i ^ ((i >> 31) & np.int32(0x7FFFFFFF))
+    order = np.argsort(img, kind="stable")
+    xs = x[order]
+    assert np.all(np.diff(xs.astype(np.float64)) >= 0)
+    back = img ^ ((img >> 31) & np.int32(0x7FFFFFFF))
+    assert np.array_equal(back, i)                                  # the map is its own inverse
+    assert x[np.argmax(img)] == x.max() and x[np.argmin(img)] == x.min()
